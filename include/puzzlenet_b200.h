@@ -1,0 +1,216 @@
+/*
+ * puzzlenet_b200.h -- C ABI of libpuzzlenet_sm100.so
+ *
+ * B200 (sm_100a) implementation of the PuzzleNet point-cloud encoder +
+ * pair-matching forward and the approximate-EMD loss.  The reference is pure
+ * Python/torch on this path; its "FFI" is the Python module boundary
+ * (pointnet_util.*, model5_b.TouchedRegraster.predict5) plus one pybind11
+ * module, emd_cuda (PyTorchEMD/cuda/emd.cpp:23-27).  Every entry point below
+ * names the reference interface it replaces (paths relative to the reference
+ * root).  INTEGRATION.md shows the ctypes binding the Python shims use.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name ends in _host;
+ *   - tensors are dense row-major fp32, indices are int64 at this boundary
+ *     (the reference returns torch.long);
+ *   - nothing is allocated inside: scratch comes from the caller through a
+ *     workspace pointer sized by the matching *_workspace_bytes() call;
+ *   - every call is asynchronous on `stream` (a cudaStream_t), re-entrant and
+ *     CUDA-graph capturable; no global state except the last-error string;
+ *   - return value: 0 = ok, <0 = argument error (PZ_ERR_*), >0 = cudaError_t.
+ *     pz_last_error() returns a thread-local description of the last failure.
+ */
+#ifndef PUZZLENET_B200_H_
+#define PUZZLENET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* pz_stream_t; /* cudaStream_t */
+
+#define PZ_OK 0
+#define PZ_ERR_ARG (-1)         /* null pointer / non-positive size / bad enum */
+#define PZ_ERR_UNSUPPORTED (-2) /* size outside the supported range (see each call) */
+#define PZ_ERR_WORKSPACE (-3)   /* workspace too small */
+
+#define PZ_PREC_FP32 0 /* fp32 CUDA-core math, matches the reference to ~1e-6 rel */
+#define PZ_PREC_BF16 1 /* bf16 operands, fp32 accumulate on tcgen05 tensor cores */
+
+#define PZ_ABI_VERSION 1
+
+int pz_abi_version(void);
+const char* pz_last_error(void);
+/* compute capability major*10+minor of the current device (100 on B200), <0 on error */
+int pz_device_arch(void);
+
+/* ---------------------------------------------------------------- geometry */
+
+/* farthest_point_sample(xyz, npoint) -- pointnet_util.py:53-73.
+ * xyz [B,N,3]; start [B] = the first centroid of each cloud (the reference draws it with
+ * torch.randint on the CPU generator, pointnet_util.py:65 -- the caller does that draw);
+ * out_idx [B,S].  Distances are ((dx*dx)+(dy*dy))+(dz*dz) in fp32 without FMA, argmax ties
+ * resolve to the lowest index: bit-exact with the reference's CPU result.
+ * new_xyz_or_null [B,S,3] receives xyz[out_idx] (index_points, pointnet_util.py:115).
+ * Supported: 1 <= N <= 16384, 1 <= S. */
+int pz_fps(const float* xyz, int B, int N, const int64_t* start, int S, int64_t* out_idx,
+           float* new_xyz_or_null, pz_stream_t stream);
+
+/* square_distance(src, dst) -- pointnet_util.py:22-36.  src [B,S,3], dst [B,N,3] -> out [B,S,N]. */
+int pz_sqdist(const float* src, const float* dst, int B, int S, int N, float* out,
+              pz_stream_t stream);
+
+/* kNN selection = square_distance(query, xyz).argsort()[:, :, :K] -- pointnet_util.py:118-119,
+ * without materialising [B,S,N].  query [B,S,3], xyz [B,N,3] -> out_idx [B,S,K] ascending by
+ * (distance, index) (the reference's order among equal distances is undefined);
+ * out_d2_or_null [B,S,K] the squared distances.  Supported: 1 <= K <= 32, N >= K. */
+int pz_knn(const float* query, const float* xyz, int B, int S, int N, int K, int64_t* out_idx,
+           float* out_d2_or_null, pz_stream_t stream);
+
+/* query_ball_point(radius, nsample, xyz, new_xyz) -- pointnet_util.py:76-96.
+ * First `nsample` indices (ascending) with d2 <= radius^2, padded with the first one; a query
+ * with no point in range yields N everywhere, as the reference does. */
+int pz_ball_query(const float* xyz, const float* new_xyz, int B, int N, int S, float radius,
+                  int nsample, int64_t* out_idx, pz_stream_t stream);
+
+/* index_points(points, idx) -- pointnet_util.py:39-50.  pts [B,N,C] of elem_bytes-sized
+ * elements, idx [B,M] -> out [B,M,C].  Indices must lie in [0,N). */
+int pz_gather(const void* pts, const int64_t* idx, int B, int N, int C, int M, int elem_bytes,
+              void* out, pz_stream_t stream);
+
+/* the grouping tail of sample_and_group -- pointnet_util.py:123-130.
+ * new_points[b,s,k,:] = cat(xyz[b,knn[b,s,k]] - new_xyz[b,s], feat[b,knn[b,s,k]]) ([B,S,K,3+D]);
+ * feat may be null (D = 0); grouped_xyz_or_null [B,S,K,3] = xyz[b,knn[b,s,k]] (returnfps=True). */
+int pz_group_concat(const float* xyz, const float* feat_or_null, const float* new_xyz,
+                    const int64_t* knn_idx, int B, int N, int D, int S, int K, float* new_points,
+                    float* grouped_xyz_or_null, pz_stream_t stream);
+
+/* ------------------------------------------------------------ fused blocks */
+
+/* sample_and_group's grouping + the shared MLP + neighbourhood max-pool in one pass, never
+ * materialising [B,S,K,3+D]: model5_b.py:449-454 / :456-461 with pointnet_util.py:123-130.
+ *   out[b,s,:] = max_k relu(W2 relu(W1 [xyz[j]-new_xyz[b,s] ; feat[j]] + b1) + b2),  j = knn[b,s,k]
+ * W1 [C1,3+D], W2 [C2,C1] row-major (nn.Linear layout), K must be 32.
+ * workspace: pz_group_mlp_workspace_bytes(B,N,D,S,K,C1,C2). */
+size_t pz_group_mlp_workspace_bytes(int B, int N, int D, int S, int K, int C1, int C2);
+int pz_group_mlp_maxpool(const float* xyz, const float* feat, const float* new_xyz,
+                         const int64_t* knn_idx, const float* W1, const float* b1,
+                         const float* W2, const float* b2, int B, int N, int D, int S, int K,
+                         int C1, int C2, int precision, float* out, void* workspace,
+                         size_t workspace_bytes, pz_stream_t stream);
+
+/* nn.Linear on this path (every mlpN, out and tfMLP layer of model5_b.py): y = act(x W^T + b) (+ residual).
+ * x [M,K] (row stride ldx), W [N,K], b [N] or null, residual_or_null [M,N] (row stride ldr) added
+ * AFTER the optional ReLU (model5_b.py:100), y [M,N] (row stride ldy). */
+int pz_linear(const float* x, int ldx, const float* W, const float* b, int M, int N, int K, int relu,
+              const float* residual_or_null, int ldr, float* y, int ldy, int precision,
+              pz_stream_t stream);
+
+/* layerAttention.forward -- model5_b.py:92-101.  x [B,L,C] -> out [B,L,C] = x + relu(Wo (x - A v) + bo),
+ * attention_or_null [B,L,L].  Wq,Wk [C/4,C]; Wv,Wo [C,C].  Supported: C == 256, L as pz_scaled_dot_attention.
+ * workspace: pz_offset_attention_workspace_bytes(B,L,C). */
+size_t pz_offset_attention_workspace_bytes(int B, int L, int C);
+int pz_offset_attention(const float* x, const float* Wq, const float* bq, const float* Wk,
+                        const float* bk, const float* Wv, const float* bv, const float* Wo,
+                        const float* bo, int B, int L, int C, int precision, float* out,
+                        float* attention_or_null, void* workspace, size_t workspace_bytes,
+                        pz_stream_t stream);
+
+/* scaled_dot_production(q,k,v) -- model5_b.py:67-75 (mask=None).
+ * q,k [B,L,Dk], v [B,L,Dv] -> values [B,L,Dv], attention_or_null [B,L,L].
+ * Supported: L % 64 == 0, L <= 256, Dk == 64, Dv % 128 == 0. */
+int pz_scaled_dot_attention(const float* q, const float* k, const float* v, int B, int L, int Dk,
+                            int Dv, float* values, float* attention_or_null, pz_stream_t stream);
+
+/* Parameters of one PCTransformer_nonsort (model5_b.py:417-441), nn.Linear layout
+ * (weight [out,in] row-major, bias [out]); BatchNorm1d(1024) tensors are [1024]. */
+typedef struct PzEncoderWeights {
+  const float *mlp1_w, *mlp1_b; /* [64,3]    */
+  const float *mlp2_w, *mlp2_b; /* [64,64]   */
+  const float *mlp3_w, *mlp3_b; /* [128,67]  */
+  const float *mlp4_w, *mlp4_b; /* [128,128] */
+  const float *mlp5_w, *mlp5_b; /* [256,131] */
+  const float *mlp6_w, *mlp6_b; /* [256,256] */
+  const float *bn1_w, *bn1_b, *bn1_mean, *bn1_var;
+  const float *bn2_w, *bn2_b, *bn2_mean, *bn2_var;
+  const float *q_w[4], *q_b[4]; /* atten{1..4}.mlpq [64,256]  */
+  const float *k_w[4], *k_b[4]; /* atten{1..4}.mlpk [64,256]  */
+  const float *v_w[4], *v_b[4]; /* atten{1..4}.mlpv [256,256] */
+  const float *o_w[4], *o_b[4]; /* atten{1..4}.out  [256,256] */
+  const float *out_w, *out_b;   /* [1024,1280] */
+} PzEncoderWeights;
+
+/* Outputs of PCTransformer_nonsort.forward (model5_b.py:478) for E*B clouds; any pointer may be
+ * null to skip that output (predict5 with need=False only consumes f_global and x_feature). */
+typedef struct PzEncoderOutputs {
+  float* f_global;  /* [E*B,1024]      */
+  float* x2;        /* [E*B,256,3]     */
+  float* attention; /* [E*B,256,256]   mean of the 4 maps (model5_b.py:468-469) */
+  float* out;       /* [E*B,256,1024]  */
+  float* x_feature; /* [E*B,1024,64]   */
+  /* extra intermediates for parity tests; null = skip */
+  int64_t* fps1;    /* [E*B,512]       */
+  int64_t* knn1;    /* [E*B,512,32]    */
+  float* f1f;       /* [E*B,512,128]   */
+  int64_t* fps2;    /* [E*B,256]       */
+  int64_t* knn2;    /* [E*B,256,32]    */
+  float* f2f;       /* [E*B,256,256]   */
+  float* att_cat;   /* [E*B,256,1280]  cat(att1..att4, f2f) (model5_b.py:467,472) */
+} PzEncoderOutputs;
+
+/* E encoders (different weight sets) over E*B clouds in one pass: cloud c uses weights[c / B].
+ * xyz [E*B,1024,3]; start1 [E*B], start2 [E*B] = FPS start indices of stage 1 (in [0,1024)) and
+ * stage 2 (in [0,512)).  Eval-mode BatchNorm (running statistics).  E in {1,2}. */
+size_t pz_encoder_workspace_bytes(int E, int B);
+int pz_encoder_forward(const PzEncoderWeights* weights_host, int E, int B, const float* xyz,
+                       const int64_t* start1, const int64_t* start2, int precision,
+                       const PzEncoderOutputs* outputs_host, void* workspace,
+                       size_t workspace_bytes, pz_stream_t stream);
+
+/* Parameters of the pair heads (model5_b.py:561-599). */
+typedef struct PzHeadWeights {
+  const float *tf_w[5], *tf_b[5];         /* tfMLP.{0,2,4,6,8}: 2048-1024-512-512-256-6 */
+  const float *pre_fpc_w[3], *pre_fpc_b[3]; /* MLPLocalPreFpc.{0,2,4} [64,64] */
+  const float *pre_rpc_w[3], *pre_rpc_b[3]; /* MLPLocalPreRpc.{0,2,4} [64,64] */
+  const float *seg_fpc_w[3], *seg_fpc_b[3]; /* MLPFpcb.{0,2,4}: 128-64-32-2 */
+  const float *seg_rpc_w[3], *seg_rpc_b[3]; /* MLPRpcb.{0,2,4}: 128-64-32-2 */
+} PzHeadWeights;
+
+/* TouchedRegraster.predict5(batch, _, need, training=False) -- model5_b.py:672-759.
+ * fpc, mrpc [B,1024,3]; starts [4,B] = FPS starts in the reference's draw order
+ * (Encoder stage 1, Encoder stage 2, Encoder2 stage 1, Encoder2 stage 2).
+ * out6 [B,6]; de_fpcb, de_mrpcb [B,2,1024].  need != 0 additionally fills x2_* [B,256,3] and
+ * attention_* [B,256,256] (may be null otherwise).  Reproduces the reference's use of the mrpc
+ * global feature for both boundary heads (model5_b.py:741-744). */
+size_t pz_predict5_workspace_bytes(int B);
+int pz_predict5(const PzEncoderWeights* enc_host /*[2]*/, const PzHeadWeights* heads_host,
+                const float* fpc, const float* mrpc, int B, const int64_t* starts, int precision,
+                int need, float* out6, float* de_fpcb, float* de_mrpcb, float* x2_fpc,
+                float* attention_fpc, float* x2_mrpc, float* attention_mrpc, void* workspace,
+                size_t workspace_bytes, pz_stream_t stream);
+
+/* se3.exp(x) -- se_math/se3.py:57-80.  twist [B,6] (omega, v) -> g [B,4,4]. */
+int pz_se3_exp(const float* twist, int B, float* g, pz_stream_t stream);
+
+/* --------------------------------------------------------------------- EMD */
+
+/* emd_cuda.approxmatch_forward(xyz1, xyz2) -- PyTorchEMD/cuda/emd_kernel.cu:171-193 (kernel :25-158).
+ * xyz1 [b,n,3], xyz2 [b,m,3] -> match [b,m,n].  workspace: pz_emd_workspace_bytes(b,n,m). */
+size_t pz_emd_workspace_bytes(int b, int n, int m);
+int pz_emd_approxmatch(const float* xyz1, const float* xyz2, int b, int n, int m, float* match,
+                       void* workspace, size_t workspace_bytes, pz_stream_t stream);
+/* emd_cuda.matchcost_forward -- emd_kernel.cu:257-279 (kernel :200-243) -> cost [b]. */
+int pz_emd_matchcost(const float* xyz1, const float* xyz2, const float* match, int b, int n, int m,
+                     float* cost, pz_stream_t stream);
+/* emd_cuda.matchcost_backward -- emd_kernel.cu:373-398 (kernels :286-355) -> grad1 [b,n,3], grad2 [b,m,3]. */
+int pz_emd_matchcost_grad(const float* grad_cost, const float* xyz1, const float* xyz2,
+                          const float* match, int b, int n, int m, float* grad1, float* grad2,
+                          pz_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PUZZLENET_B200_H_ */

@@ -1,0 +1,271 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU oracle for the PuzzleNet hot path.
+
+A plain torch-CPU (fp32, ATen) restatement of the reference algorithm for the
+encoder + pair-matching forward.  It is the checker the CUDA path is compared
+with; it is *never* on the product path.  Only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl
+reference`` legs may import it.
+
+Pinning: the reference has no golden vectors for this part of the path
+ -- it is pinned by executing the unmodified reference torch
+code in the build container (``oracle/make_golden.py`` -> ``tests/golden/``)
+and by ``tests/test_oracle_vs_reference.py`` which runs both side by side
+when ``/root/reference`` is present.
+
+Everything is functional: weights come in as a ``state_dict``-style mapping
+with the reference's key names, so the same dictionary
+drives the reference model, this oracle and the CUDA implementation.
+
+Each function cites the reference lines it restates (paths are relative to
+the reference root).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Mapping, Optional
+
+import torch
+
+Tensor = torch.Tensor
+
+# --------------------------------------------------------------------------
+# point-cloud operators (pointnet_util.py)
+# --------------------------------------------------------------------------
+
+
+def sq_norm3(diff: Tensor) -> Tensor:
+    """((dx*dx)+(dy*dy))+(dz*dz), every op rounded to fp32, no FMA.
+
+    This is the arithmetic contract for every distance on the path: ATen's CPU
+    ``sum(dim=-1)`` over 3 elements associates left to right,
+    which is what pointnet_util.py:36 and :70 evaluate.
+    """
+    sq = diff * diff
+    return (sq[..., 0] + sq[..., 1]) + sq[..., 2]
+
+
+def square_distance(src: Tensor, dst: Tensor) -> Tensor:
+    """pointnet_util.py:22-36 -- direct (src-dst)^2 form -> [B, S, N]."""
+    return sq_norm3(src.unsqueeze(2) - dst.unsqueeze(1))
+
+
+def index_points(points: Tensor, idx: Tensor) -> Tensor:
+    """pointnet_util.py:39-50 -- batched row gather; idx [B,S] or [B,S,K]."""
+    b = points.shape[0]
+    flat = idx.reshape(b, -1)
+    rows = torch.arange(b).unsqueeze(1)
+    return points[rows, flat].reshape(*idx.shape, points.shape[-1])
+
+
+def draw_fps_start(batch: int, n: int) -> Tensor:
+    """pointnet_util.py:65 -- ONE draw from the CPU default generator per call."""
+    return torch.randint(0, n, (batch,), dtype=torch.long)
+
+
+def farthest_point_sample(xyz: Tensor, npoint: int, start: Optional[Tensor] = None) -> Tensor:
+    """pointnet_util.py:53-73.
+
+    distance starts at 1e10; each step records the current farthest index,
+    lowers ``distance`` with the squared distance to it and picks the argmax
+    (first maximum wins, as ``torch.max`` does on CPU).
+    """
+    b, n, _ = xyz.shape
+    far = draw_fps_start(b, n) if start is None else start.clone().long()
+    picked = torch.empty(b, npoint, dtype=torch.long)
+    mind = torch.full((b, n), 1e10, dtype=xyz.dtype)
+    rows = torch.arange(b)
+    for s in range(npoint):
+        picked[:, s] = far
+        c = xyz[rows, far].unsqueeze(1)
+        mind = torch.minimum(mind, sq_norm3(xyz - c))
+        far = torch.max(mind, dim=-1).indices
+    return picked
+
+
+def knn_select(dists: Tensor, k: int):
+    """pointnet_util.py:119 -- ``argsort()[:, :, :k]``.
+
+    The reference's sort is unstable, so the order among equal distances is
+    undefined there; the oracle fixes it to (distance, index) ascending with a
+    stable sort.  Returns (idx [B,S,k], d2 [B,S,k]).
+    """
+    vals, idx = torch.sort(dists, dim=-1, stable=True)
+    return idx[..., :k], vals[..., :k]
+
+
+def query_ball_point(radius: float, nsample: int, xyz: Tensor, new_xyz: Tensor) -> Tensor:
+    """pointnet_util.py:76-96 -- first ``nsample`` in-radius indices, padded with the first."""
+    b, n, _ = xyz.shape
+    s = new_xyz.shape[1]
+    d2 = square_distance(new_xyz, xyz)
+    cand = torch.arange(n).view(1, 1, n).expand(b, s, n).clone()
+    cand[d2 > radius ** 2] = n
+    cand = torch.sort(cand, dim=-1).values[:, :, :nsample]
+    first = cand[:, :, :1].expand(-1, -1, nsample)
+    return torch.where(cand == n, first, cand)
+
+
+def sample_and_group(npoint: int, radius: float, nsample: int, xyz: Tensor, points: Optional[Tensor],
+                     returnfps: bool = False, knn: bool = False, start: Optional[Tensor] = None,
+                     return_idx: bool = False):
+    """pointnet_util.py:99-136 -- FPS, centre gather, kNN / ball query, group, centre, concat."""
+    b, n, c = xyz.shape
+    fps_idx = farthest_point_sample(xyz, npoint, start)
+    new_xyz = index_points(xyz, fps_idx)
+    if knn:
+        idx, _ = knn_select(square_distance(new_xyz, xyz), nsample)
+    else:
+        idx = query_ball_point(radius, nsample, xyz, new_xyz)
+    grouped_xyz = index_points(xyz, idx)
+    rel = grouped_xyz - new_xyz.view(b, npoint, 1, c)
+    new_points = rel if points is None else torch.cat([rel, index_points(points, idx)], dim=-1)
+    if return_idx:
+        return new_xyz, new_points, grouped_xyz, fps_idx, idx
+    if returnfps:
+        return new_xyz, new_points, grouped_xyz, fps_idx
+    return new_xyz, new_points
+
+
+# --------------------------------------------------------------------------
+# network blocks (model5_b.py)
+# --------------------------------------------------------------------------
+
+
+def _lin(sd: Mapping[str, Tensor], name: str, x: Tensor) -> Tensor:
+    return torch.nn.functional.linear(x, sd[name + ".weight"], sd[name + ".bias"])
+
+
+def _bn_point_index_eval(sd: Mapping[str, Tensor], name: str, x: Tensor, eps: float = 1e-5) -> Tensor:
+    """nn.BatchNorm1d(1024) on [B, 1024, 64]: dim 1 (the point index) is the channel
+    (model5_b.py:424-425, :447-448).  Eval mode -> running statistics."""
+    return torch.nn.functional.batch_norm(
+        x, sd[name + ".running_mean"], sd[name + ".running_var"],
+        sd[name + ".weight"], sd[name + ".bias"], training=False, momentum=0.1, eps=eps)
+
+
+def scaled_dot_production(q: Tensor, k: Tensor, v: Tensor):
+    """model5_b.py:67-75 (mask=None branch)."""
+    logits = torch.matmul(q, k.transpose(-2, -1)) / math.sqrt(q.shape[-1])
+    attn = torch.softmax(logits, dim=-1)
+    return torch.matmul(attn, v), attn
+
+
+def layer_attention(sd: Mapping[str, Tensor], prefix: str, x: Tensor):
+    """model5_b.py:92-101 -- offset attention: x + relu(W_o (x - A v))."""
+    vals, attn = scaled_dot_production(_lin(sd, prefix + ".mlpq", x), _lin(sd, prefix + ".mlpk", x),
+                                       _lin(sd, prefix + ".mlpv", x))
+    return x + torch.relu(_lin(sd, prefix + ".out", x - vals)), attn
+
+
+def encoder_forward(sd: Mapping[str, Tensor], prefix: str, xyz: Tensor,
+                    starts: Optional[tuple] = None) -> Dict[str, Tensor]:
+    """PCTransformer_nonsort.forward, model5_b.py:443-478, eval mode.
+
+    ``starts`` = (start1 [B], start2 [B]) FPS start indices; None -> drawn from the
+    CPU generator in the reference's order (stage 1 then stage 2).
+    Returns every intermediate of SURVEY.md Appendix A.
+    """
+    p = prefix
+    s1, s2 = (None, None) if starts is None else starts
+    x_feature = torch.relu(_bn_point_index_eval(sd, p + ".bn1", _lin(sd, p + ".mlp1", xyz)))
+    x_feature = torch.relu(_bn_point_index_eval(sd, p + ".bn2", _lin(sd, p + ".mlp2", x_feature)))
+    x1, f1, _, fps1, knn1 = sample_and_group(512, 0, 32, xyz, x_feature, knn=True, start=s1, return_idx=True)
+    f1f = torch.relu(_lin(sd, p + ".mlp4", torch.relu(_lin(sd, p + ".mlp3", f1)))).max(dim=-2).values
+    x2, f2, _, fps2, knn2 = sample_and_group(256, 0, 32, x1, f1f, knn=True, start=s2, return_idx=True)
+    f2f = torch.relu(_lin(sd, p + ".mlp6", torch.relu(_lin(sd, p + ".mlp5", f2)))).max(dim=-2).values
+    cur, atts, maps = f2f, [], []
+    for i in (1, 2, 3, 4):
+        cur, a = layer_attention(sd, f"{p}.atten{i}", cur)
+        atts.append(cur)
+        maps.append(a)
+    attention = (maps[0] + maps[1] + maps[2] + maps[3]) / 4
+    out = _lin(sd, p + ".out", torch.cat(atts + [f2f], dim=-1))
+    f_global = out.max(dim=1).values
+    return dict(f_global=f_global, x2=x2, attention=attention, out=out, x_feature=x_feature,
+                x1=x1, fps1=fps1, knn1=knn1, f1f=f1f, fps2=fps2, knn2=knn2, f2f=f2f,
+                att=atts, maps=maps)
+
+
+def _seq(sd: Mapping[str, Tensor], name: str, x: Tensor, layers) -> Tensor:
+    for j, li in enumerate(layers):
+        x = _lin(sd, f"{name}.{li}", x)
+        if j + 1 < len(layers):
+            x = torch.relu(x)
+    return x
+
+
+def predict5(sd: Mapping[str, Tensor], fpc: Tensor, mrpc: Tensor, need: bool = False,
+             starts: Optional[tuple] = None) -> Dict[str, Tensor]:
+    """TouchedRegraster.predict5, model5_b.py:672-759, eval mode.
+
+    ``starts`` = ((fpc stage1, fpc stage2), (mrpc stage1, mrpc stage2)); None draws the
+    four starts from the CPU generator in the reference's order.
+    Replicates D6: BOTH "global" vectors are max-pools of the *mrpc* local features
+    (model5_b.py:741-744).
+    """
+    if fpc.dim() == 2:
+        fpc, mrpc = fpc.unsqueeze(0), mrpc.unsqueeze(0)
+    st1, st2 = (None, None) if starts is None else starts
+    e1 = encoder_forward(sd, "Encoder", fpc, st1)
+    e2 = encoder_forward(sd, "Encoder2", mrpc, st2)
+    out6 = _seq(sd, "tfMLP", torch.cat([e1["f_global"], e2["f_global"]], dim=-1), (0, 2, 4, 6, 8))
+    loc_f = _seq(sd, "MLPLocalPreFpc", e1["x_feature"], (0, 2, 4))
+    loc_m = _seq(sd, "MLPLocalPreRpc", e2["x_feature"], (0, 2, 4))
+    g = loc_m.max(dim=1, keepdim=True).values.expand(-1, loc_m.shape[1], -1)      # D6
+    de_fpcb = _seq(sd, "MLPFpcb", torch.cat([g, loc_f], dim=-1), (0, 2, 4)).permute(0, 2, 1)
+    de_mrpcb = _seq(sd, "MLPRpcb", torch.cat([g, loc_m], dim=-1), (0, 2, 4)).permute(0, 2, 1)
+    return dict(out=out6, de_fpcb=de_fpcb, de_mrpcb=de_mrpcb, enc_fpc=e1, enc_mrpc=e2,
+                loc_fpc=loc_f, loc_mrpc=loc_m)
+
+
+# --------------------------------------------------------------------------
+# pose (se_math/se3.py, so3.py, sinc.py) and the pose-parity metrics (metrics.py)
+# --------------------------------------------------------------------------
+
+
+def _sinc123(t: Tensor):
+    """sinc.py:6-18, :96-108, :126-138 -- Taylor branch for |t| < 0.01."""
+    small = t.abs() < 0.01
+    t2 = t * t
+    ts = torch.where(small, torch.ones_like(t), t)          # keep the large branch finite
+    s1 = torch.where(small, 1 - t2 / 6 * (1 - t2 / 20 * (1 - t2 / 42)), torch.sin(ts) / ts)
+    s2 = torch.where(small, 1 / 2 * (1 - t2 / 12 * (1 - t2 / 30 * (1 - t2 / 56))), (1 - torch.cos(ts)) / (ts * ts))
+    s3 = torch.where(small, 1 / 6 * (1 - t2 / 20 * (1 - t2 / 42 * (1 - t2 / 72))), (ts - torch.sin(ts)) / ts ** 3)
+    return s1, s2, s3
+
+
+def se3_exp(x: Tensor) -> Tensor:
+    """se3.py:57-80 -- twist [.., 6] (omega first, v last) -> [.., 4, 4]."""
+    x_ = x.reshape(-1, 6)
+    w, v = x_[:, :3], x_[:, 3:]
+    t = w.norm(p=2, dim=1).view(-1, 1, 1)
+    zero = torch.zeros_like(w[:, 0])
+    W = torch.stack([torch.stack([zero, -w[:, 2], w[:, 1]], 1),
+                     torch.stack([w[:, 2], zero, -w[:, 0]], 1),
+                     torch.stack([-w[:, 1], w[:, 0], zero], 1)], 1)     # so3.py:16-26
+    S = W.bmm(W)
+    eye = torch.eye(3, dtype=x.dtype)
+    s1, s2, s3 = _sinc123(t)
+    R = eye + s1 * W + s2 * S
+    V = eye + s2 * W + s3 * S
+    p = V.bmm(v.reshape(-1, 3, 1))
+    g = torch.zeros(x_.shape[0], 4, 4, dtype=x.dtype)
+    g[:, :3, :3], g[:, :3, 3:], g[:, 3, 3] = R, p, 1
+    return g.view(*x.shape[:-1], 4, 4)
+
+
+def se3_transform(g: Tensor, a: Tensor) -> Tensor:
+    """se3.py:110-120 -- apply g [B,4,4] to a [B,3,N]."""
+    return g[..., :3, :3].matmul(a) + g[..., :3, 3].unsqueeze(-1)
+
+
+def rotation_error_deg(r1: Tensor, r2: Tensor) -> Tensor:
+    """metrics.py:54-70 isotropic_R_error."""
+    rr = r2.transpose(1, 2).matmul(r1)
+    tr = rr[:, 0, 0] + rr[:, 1, 1] + rr[:, 2, 2]
+    return torch.acos(torch.clamp((tr - 1) / 2, -1, 1)) / math.pi * 180
+
+
+def translation_error(t1: Tensor, t2: Tensor) -> Tensor:
+    """|t1 - t2| -- the quantity north_star bounds by 1e-4."""
+    return (t1 - t2).norm(dim=-1)

@@ -1,0 +1,842 @@
+// PuzzleNet encoder + pair heads on sm_100a (fp32-faithful path).
+// Reference: model5_b.py:443-478 (PCTransformer_nonsort.forward), :92-101 (layerAttention),
+// :67-75 (scaled_dot_production), :672-759 (TouchedRegraster.predict5); se_math/se3.py:57-80.
+//
+// Both encoders of predict5 run as ONE batch of 2B clouds (cloud c uses weight set c / B), so
+// every launch covers 128 clouds at B=64 instead of 64 -- FPS, the latency-bound stage, then
+// occupies 128 of the 148 SMs.
+#include "pz_common.cuh"
+
+namespace pz {
+
+constexpr int NPTS = 1024;  // BatchNorm1d(1024) over the point index pins N
+constexpr int S1 = 512, S2 = 256, KNN = 32;
+constexpr int D0 = 64, C1A = 128, C1B = 128, C2A = 256, C2B = 256, LATT = 256, CATT = 256;
+
+// ------------------------------------------------------------------ stem (model5_b.py:447-448)
+struct StemW {
+  const float *w1, *b1, *w2, *b2;
+  const float *g1, *be1, *m1, *v1, *g2, *be2, *m2, *v2;
+};
+
+__global__ void __launch_bounds__(128) stem_kernel(const float* __restrict__ xyz, StemW wa, StemW wb,
+                                                   int clouds_per_set, float* __restrict__ out) {
+  __shared__ __align__(16) float w2s[64 * 64];
+  __shared__ float w1s[64 * 3], b1s[64], b2s[64];
+  const size_t p = (size_t)blockIdx.x * 128 + threadIdx.x;  // global point id
+  const int cloud = (int)(p / NPTS);                        // uniform per block (128 | 1024)
+  const int n = (int)(p - (size_t)cloud * NPTS);
+  const StemW& w = (cloud / clouds_per_set) == 0 ? wa : wb;
+  for (int i = threadIdx.x; i < 64 * 64; i += 128) w2s[i] = w.w2[i];
+  for (int i = threadIdx.x; i < 64 * 3; i += 128) w1s[i] = w.w1[i];
+  if (threadIdx.x < 64) {
+    b1s[threadIdx.x] = w.b1[threadIdx.x];
+    b2s[threadIdx.x] = w.b2[threadIdx.x];
+  }
+  __syncthreads();
+  // eval-mode BatchNorm1d over the point index: y = x*alpha_n + beta_n
+  const float a1 = w.g1[n] * (1.0f / sqrtf(w.v1[n] + 1e-5f));
+  const float c1 = w.be1[n] - w.m1[n] * a1;
+  const float a2 = w.g2[n] * (1.0f / sqrtf(w.v2[n] + 1e-5f));
+  const float c2 = w.be2[n] - w.m2[n] * a2;
+  const float x = xyz[p * 3], y = xyz[p * 3 + 1], z = xyz[p * 3 + 2];
+  float h[64];
+#pragma unroll
+  for (int k = 0; k < 64; ++k) {
+    float v = b1s[k];
+    v = fmaf(w1s[k * 3 + 0], x, v);
+    v = fmaf(w1s[k * 3 + 1], y, v);
+    v = fmaf(w1s[k * 3 + 2], z, v);
+    h[k] = fmaxf(fmaf(v, a1, c1), 0.f);
+  }
+  float* o = out + p * 64;
+#pragma unroll 1
+  for (int k0 = 0; k0 < 64; k0 += 4) {
+    float r[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float4* wr = reinterpret_cast<const float4*>(&w2s[(k0 + u) * 64]);
+      float v = b2s[k0 + u];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float4 ww = wr[i];
+        v = fmaf(ww.x, h[i * 4 + 0], v);
+        v = fmaf(ww.y, h[i * 4 + 1], v);
+        v = fmaf(ww.z, h[i * 4 + 2], v);
+        v = fmaf(ww.w, h[i * 4 + 3], v);
+      }
+      r[u] = fmaxf(fmaf(v, a2, c2), 0.f);
+    }
+    *reinterpret_cast<float4*>(o + k0) = make_float4(r[0], r[1], r[2], r[3]);
+  }
+}
+
+// ------------------------------------------------- attention core (model5_b.py:67-75, :98-99)
+// One CTA per (cloud, 64 query rows): S = q k^T * scale in smem, row softmax, O = A v.
+// out = xres ? xres - O : O.   attn_mode: 0 none, 1 store A, 2 A += , 3 A = (A_old + A) * 0.25
+constexpr int AT_ROWS = 64;
+__global__ void __launch_bounds__(256) attention_kernel(const float* __restrict__ q, int ldq,
+                                                        const float* __restrict__ k, int ldk,
+                                                        const float* __restrict__ v, int ldv,
+                                                        int L, int Dv, float scale,
+                                                        const float* __restrict__ xres, int ldx,
+                                                        float* __restrict__ out, int ldo,
+                                                        float* __restrict__ attn, int attn_mode) {
+  extern __shared__ __align__(16) float at_smem[];
+  const int lds = L + 4;
+  float* Ss = at_smem;                 // [64][L+4]
+  float* T0 = Ss + AT_ROWS * lds;      // 64x64 q^T tile, later V chunk [32][128]
+  float* T1 = T0 + 64 * 64;            // 64x64 k^T tile
+  const int t = threadIdx.x;
+  const int cloud = blockIdx.y;
+  const int i0 = blockIdx.x * AT_ROWS;
+  const size_t row0 = (size_t)cloud * L;
+
+  {  // q^T tile: T0[d][i]
+    const int i = t & 63, dq = (t >> 6) * 16;
+    const float* src = q + (row0 + i0 + i) * ldq + dq;
+#pragma unroll
+    for (int u = 0; u < 16; u += 4) {
+      float4 x = *reinterpret_cast<const float4*>(src + u);
+      T0[(dq + u + 0) * 64 + i] = x.x; T0[(dq + u + 1) * 64 + i] = x.y;
+      T0[(dq + u + 2) * 64 + i] = x.z; T0[(dq + u + 3) * 64 + i] = x.w;
+    }
+  }
+  const int tx = t & 15, ty = t >> 4;
+  for (int jc = 0; jc < L; jc += 64) {
+    __syncthreads();
+    {
+      const int j = t & 63, dq = (t >> 6) * 16;
+      const float* src = k + (row0 + jc + j) * ldk + dq;
+#pragma unroll
+      for (int u = 0; u < 16; u += 4) {
+        float4 x = *reinterpret_cast<const float4*>(src + u);
+        T1[(dq + u + 0) * 64 + j] = x.x; T1[(dq + u + 1) * 64 + j] = x.y;
+        T1[(dq + u + 2) * 64 + j] = x.z; T1[(dq + u + 3) * 64 + j] = x.w;
+      }
+    }
+    __syncthreads();
+    float acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+#pragma unroll 16
+    for (int d = 0; d < 64; ++d) {
+      float4 a4 = *reinterpret_cast<const float4*>(&T0[d * 64 + ty * 4]);
+      float4 b4 = *reinterpret_cast<const float4*>(&T1[d * 64 + tx * 4]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) acc[x][y] = fmaf(a[x], b[y], acc[x][y]);
+    }
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+      *reinterpret_cast<float4*>(&Ss[(ty * 4 + x) * lds + jc + tx * 4]) =
+          make_float4(acc[x][0] * scale, acc[x][1] * scale, acc[x][2] * scale, acc[x][3] * scale);
+  }
+  __syncthreads();
+  {  // softmax over each of the 64 rows; warp w owns rows w*8 .. w*8+7
+    const int lane = t & 31, w = t >> 5;
+    for (int r = w * 8; r < w * 8 + 8; ++r) {
+      float* sr = Ss + r * lds;
+      float m = -INFINITY;
+      for (int c = lane; c < L; c += 32) m = fmaxf(m, sr[c]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      float sum = 0.f;
+      for (int c = lane; c < L; c += 32) {
+        float e = expf(sr[c] - m);
+        sr[c] = e;
+        sum += e;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      const float inv = 1.0f / sum;
+      float* ag = attn ? attn + (row0 + i0 + r) * L : nullptr;
+      for (int c = lane; c < L; c += 32) {
+        float a = sr[c] * inv;
+        sr[c] = a;
+        if (attn_mode == 1) ag[c] = a;
+        else if (attn_mode == 2) ag[c] += a;
+        else if (attn_mode == 3) ag[c] = (ag[c] + a) * 0.25f;
+      }
+    }
+  }
+  // O = A v: 128 output columns per pass, thread = 8 rows x 4 cols
+  const int px = t & 31, py = t >> 5;
+  float* Vs = T0;  // [32][128]
+  for (int cb = 0; cb < Dv; cb += 128) {
+    float acc[8][4];
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+    for (int j0 = 0; j0 < L; j0 += 32) {
+      __syncthreads();
+      for (int e = t; e < 32 * 32; e += 256) {  // 32 rows x 32 float4
+        const int jr = e >> 5, c4 = (e & 31) * 4;
+        *reinterpret_cast<float4*>(&Vs[jr * 128 + c4]) =
+            *reinterpret_cast<const float4*>(v + (row0 + j0 + jr) * ldv + cb + c4);
+      }
+      __syncthreads();
+#pragma unroll
+      for (int jj = 0; jj < 32; jj += 4) {
+        float4 a4[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) a4[r] = *reinterpret_cast<const float4*>(&Ss[(py * 8 + r) * lds + j0 + jj]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float4 b4 = *reinterpret_cast<const float4*>(&Vs[(jj + u) * 128 + px * 4]);
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            const float a = u == 0 ? a4[r].x : (u == 1 ? a4[r].y : (u == 2 ? a4[r].z : a4[r].w));
+            acc[r][0] = fmaf(a, b4.x, acc[r][0]);
+            acc[r][1] = fmaf(a, b4.y, acc[r][1]);
+            acc[r][2] = fmaf(a, b4.z, acc[r][2]);
+            acc[r][3] = fmaf(a, b4.w, acc[r][3]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const size_t row = row0 + i0 + py * 8 + r;
+      const int col = cb + px * 4;
+      float4 o4 = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+      if (xres) {
+        float4 x4 = *reinterpret_cast<const float4*>(xres + row * ldx + col);
+        o4 = make_float4(x4.x - o4.x, x4.y - o4.y, x4.z - o4.z, x4.w - o4.w);
+      }
+      *reinterpret_cast<float4*>(out + row * ldo + col) = o4;
+    }
+  }
+}
+
+static int launch_attention(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv,
+                            int clouds, int L, int Dk, int Dv, const float* xres, int ldx, float* out,
+                            int ldo, float* attn, int attn_mode, cudaStream_t st) {
+  PZ_REQUIRE(Dk == 64 && L % 64 == 0 && L >= 64 && L <= 256 && Dv % 128 == 0 && Dv >= 128, PZ_ERR_UNSUPPORTED,
+             "attention: need Dk == 64, L in {64,128,192,256}, Dv %% 128 == 0 (got L=%d Dk=%d Dv=%d)", L, Dk, Dv);
+  PZ_REQUIRE(clouds <= 65535, PZ_ERR_UNSUPPORTED, "attention: too many clouds");
+  PZ_REQUIRE(ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0 && ldo % 4 == 0 && (!xres || ldx % 4 == 0), PZ_ERR_ARG,
+             "attention: leading dimensions must be multiples of 4");
+  size_t smem = ((size_t)AT_ROWS * (L + 4) + 2 * 64 * 64) * sizeof(float);
+  PZ_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(L / AT_ROWS, clouds);
+  attention_kernel<<<grid, 256, smem, st>>>(q, ldq, k, ldk, v, ldv, L, Dv, 1.0f / sqrtf((float)Dk), xres, ldx,
+                                            out, ldo, attn, attn_mode);
+  PZ_LAUNCH_CHECK();
+  return 0;
+}
+
+// -------------------------------------------------------------------------- small kernels
+// out[(r % rmod) * ldo + (r / rmod) * coloff + c] = max over G consecutive rows of in[., c]
+__global__ void __launch_bounds__(256) rowblock_max_kernel(const float* __restrict__ in, int ldi, int G, int N,
+                                                           int R, int rmod, int coloff, float* __restrict__ out,
+                                                           int ldo) {
+  const int r = blockIdx.y;
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= N || r >= R) return;
+  const float* p = in + (size_t)r * G * ldi + c;
+  float m = -INFINITY;
+  for (int g = 0; g < G; ++g) m = fmaxf(m, p[(size_t)g * ldi]);
+  out[(size_t)(r % rmod) * ldo + (size_t)(r / rmod) * coloff + c] = m;
+}
+
+__global__ void __launch_bounds__(256) idx64_to_rows32_kernel(const int64_t* __restrict__ idx, size_t total,
+                                                              size_t per_cloud, int N, int* __restrict__ rows) {
+  for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (size_t)gridDim.x * 256)
+    rows[e] = (int)(e / per_cloud) * N + (int)idx[e];
+}
+
+// sum split-K partials, add bias, optional relu
+__global__ void __launch_bounds__(256) splitk_finish_kernel(const float* __restrict__ part, int splits, int M,
+                                                            int N, const float* __restrict__ bias, int relu,
+                                                            float* __restrict__ y, int ldy) {
+  const int e = blockIdx.x * 256 + threadIdx.x;
+  if (e >= M * N) return;
+  const int m = e / N, n = e - m * N;
+  float s = 0.f;
+  for (int z = 0; z < splits; ++z) s += part[(size_t)z * M * N + e];
+  if (bias) s += bias[n];
+  if (relu) s = fmaxf(s, 0.f);
+  y[(size_t)m * ldy + n] = s;
+}
+
+// Y = act(A W^T + b) for skinny M (the 5-layer pose MLP, model5_b.py:561-571): split K over CTAs
+static int skinny_linear(const float* A, int lda, const float* W, const float* bias, int M, int N, int K,
+                         int relu, float* Y, int ldy, float* partial, size_t partial_floats, cudaStream_t st) {
+  int splits = 1;
+  while (splits < 16 && K / (splits * 2) >= 64 && ((N + 127) / 128) * ((M + 127) / 128) * splits * 2 <= kNumSMs) splits *= 2;
+  if (splits == 1 || (size_t)splits * M * N > partial_floats) {
+    GemmF32 g;
+    g.A = A; g.lda = lda; g.W[0] = W; g.bias[0] = bias; g.ldw = K; g.Y = Y; g.ldy = ldy;
+    g.M = M; g.N = N; g.K = K; g.relu = relu;
+    return launch_gemm_f32(g, st);
+  }
+  GemmF32 g;  // grid.z = split index; raw partial sums, bias/relu applied by the finish kernel
+  g.A = A; g.lda = lda; g.W[0] = W; g.ldw = K; g.Y = partial; g.ldy = N; g.M = M; g.N = N; g.K = K;
+  g.ksplit = K / splits;  // K is a power-of-two multiple of 64 on this path
+  PZ_TRY(launch_gemm_f32(g, st));
+  splitk_finish_kernel<<<(M * N + 255) / 256, 256, 0, st>>>(partial, splits, M, N, bias, relu, Y, ldy);
+  PZ_LAUNCH_CHECK();
+  return 0;
+}
+
+// ----------------------------------------------------- boundary heads (model5_b.py:738-754)
+// MLPLocalPre{Fpc,Rpc}: 64-64-64-64 per point, one thread per point, weights broadcast from smem.
+struct Mlp3W {
+  const float *w0, *b0, *w1, *b1, *w2, *b2;
+};
+
+// out[k] = act(bias[k] + W[k,:] . in) for one point per thread; W rows broadcast from smem as
+// 128-bit loads, results parked in smem ([k][thread], conflict-free) so that the k loop need not be
+// unrolled (a register-array destination would force full unrolling of 64 x 64 FMAs per layer).
+template <int NOUT, bool RELU>
+__device__ __forceinline__ void dense64_rows(const float* __restrict__ ws, const float* __restrict__ bs,
+                                             const float (&in)[64], float* __restrict__ outs, int tid) {
+#pragma unroll 2
+  for (int k = 0; k < NOUT; ++k) {
+    const float4* wr = reinterpret_cast<const float4*>(ws + k * 64);
+    float v = bs[k];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      float4 ww = wr[i];
+      v = fmaf(ww.x, in[i * 4 + 0], v);
+      v = fmaf(ww.y, in[i * 4 + 1], v);
+      v = fmaf(ww.z, in[i * 4 + 2], v);
+      v = fmaf(ww.w, in[i * 4 + 3], v);
+    }
+    outs[k * 128 + tid] = RELU ? fmaxf(v, 0.f) : v;
+  }
+}
+
+__global__ void __launch_bounds__(128) head_local_kernel(const float* __restrict__ xfeat, Mlp3W wa, Mlp3W wb,
+                                                         int clouds_per_set, float* __restrict__ local) {
+  extern __shared__ __align__(16) float hl_smem[];  // 3 x (64*64 + 64) weights, then [64][128] staging
+  float* outs = hl_smem + 3 * 4160;
+  const int tid = threadIdx.x;
+  const size_t p = (size_t)blockIdx.x * 128 + tid;
+  const int cloud = (int)(p / NPTS);
+  const bool first = (cloud / clouds_per_set) == 0;
+  const float* ws[3] = {first ? wa.w0 : wb.w0, first ? wa.w1 : wb.w1, first ? wa.w2 : wb.w2};
+  const float* bs[3] = {first ? wa.b0 : wb.b0, first ? wa.b1 : wb.b1, first ? wa.b2 : wb.b2};
+  for (int l = 0; l < 3; ++l) {
+    for (int i = tid; i < 64 * 64; i += 128) hl_smem[l * 4160 + i] = ws[l][i];
+    if (tid < 64) hl_smem[l * 4160 + 4096 + tid] = bs[l][tid];
+  }
+  __syncthreads();
+  float a[64];
+  const float4* src = reinterpret_cast<const float4*>(xfeat + p * 64);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    float4 x = src[i];
+    a[i * 4] = x.x; a[i * 4 + 1] = x.y; a[i * 4 + 2] = x.z; a[i * 4 + 3] = x.w;
+  }
+  dense64_rows<64, true>(hl_smem, hl_smem + 4096, a, outs, tid);
+#pragma unroll
+  for (int i = 0; i < 64; ++i) a[i] = outs[i * 128 + tid];
+  dense64_rows<64, true>(hl_smem + 4160, hl_smem + 4160 + 4096, a, outs, tid);
+#pragma unroll
+  for (int i = 0; i < 64; ++i) a[i] = outs[i * 128 + tid];
+  dense64_rows<64, false>(hl_smem + 2 * 4160, hl_smem + 2 * 4160 + 4096, a, outs, tid);
+  float4* dst = reinterpret_cast<float4*>(local + p * 64);
+#pragma unroll
+  for (int i = 0; i < 16; ++i)
+    dst[i] = make_float4(outs[(i * 4) * 128 + tid], outs[(i * 4 + 1) * 128 + tid], outs[(i * 4 + 2) * 128 + tid],
+                         outs[(i * 4 + 3) * 128 + tid]);
+}
+
+// gbias[set][b][k] = W0_set[k, 0:64] . g[b] + b0_set[k]   (the "global" half of MLP{F,R}pcb.0)
+__global__ void __launch_bounds__(64) seg_bias_kernel(const float* __restrict__ g, const float* w0a,
+                                                      const float* b0a, const float* w0b, const float* b0b, int B,
+                                                      float* __restrict__ gbias) {
+  const int b = blockIdx.x, set = blockIdx.y, k = threadIdx.x;
+  const float* w0 = set == 0 ? w0a : w0b;
+  const float* b0 = set == 0 ? b0a : b0b;
+  float v = b0[k];
+  for (int i = 0; i < 64; ++i) v = fmaf(w0[k * 128 + i], g[b * 64 + i], v);
+  gbias[((size_t)set * B + b) * 64 + k] = v;
+}
+
+// MLP{F,R}pcb on cat([global, local]): 128-64-32-2, logits stored as [B,2,1024] (model5_b.py:751-754)
+__global__ void __launch_bounds__(128) head_seg_kernel(const float* __restrict__ local, Mlp3W wa, Mlp3W wb,
+                                                       const float* __restrict__ gbias, int B,
+                                                       float* __restrict__ de_a, float* __restrict__ de_b) {
+  extern __shared__ __align__(16) float hs_smem[];
+  float* w0s = hs_smem;            // [64][64] local half of layer 0
+  float* w1s = w0s + 64 * 64;      // [32][64]
+  float* gbs = w1s + 32 * 64;      // [64] per-cloud bias = global half + b0
+  float* b1s = gbs + 64;           // [32]
+  float* w2s = b1s + 32;           // [2][32]
+  float* b2s = w2s + 64;           // [2] (+2 pad)
+  float* outs = b2s + 4;           // [64][128]
+  const int tid = threadIdx.x;
+  const size_t p = (size_t)blockIdx.x * 128 + tid;
+  const int cloud = (int)(p / NPTS);
+  const int n = (int)(p - (size_t)cloud * NPTS);
+  const int set = cloud / B, b = cloud - set * B;
+  const Mlp3W& w = set == 0 ? wa : wb;
+  for (int i = tid; i < 64 * 64; i += 128) w0s[i] = w.w0[(i >> 6) * 128 + 64 + (i & 63)];
+  for (int i = tid; i < 32 * 64; i += 128) w1s[i] = w.w1[i];
+  if (tid < 64) {
+    w2s[tid] = w.w2[tid];
+    gbs[tid] = gbias[((size_t)set * B + b) * 64 + tid];
+  }
+  if (tid < 32) b1s[tid] = w.b1[tid];
+  if (tid < 2) b2s[tid] = w.b2[tid];
+  __syncthreads();
+  float a[64];
+  const float4* src = reinterpret_cast<const float4*>(local + p * 64);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    float4 x = src[i];
+    a[i * 4] = x.x; a[i * 4 + 1] = x.y; a[i * 4 + 2] = x.z; a[i * 4 + 3] = x.w;
+  }
+  dense64_rows<64, true>(w0s, gbs, a, outs, tid);
+#pragma unroll
+  for (int i = 0; i < 64; ++i) a[i] = outs[i * 128 + tid];
+  dense64_rows<32, true>(w1s, b1s, a, outs, tid);
+  float o0 = b2s[0], o1 = b2s[1];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    const float v = outs[k * 128 + tid];
+    o0 = fmaf(w2s[k], v, o0);
+    o1 = fmaf(w2s[32 + k], v, o1);
+  }
+  float* de = set == 0 ? de_a : de_b;
+  de[((size_t)b * 2 + 0) * NPTS + n] = o0;
+  de[((size_t)b * 2 + 1) * NPTS + n] = o1;
+}
+
+// ------------------------------------------------------------ se3.exp (se_math/se3.py:57-80)
+__global__ void se3_exp_kernel(const float* __restrict__ x, int B, float* __restrict__ g) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float w0 = x[b * 6], w1 = x[b * 6 + 1], w2 = x[b * 6 + 2];
+  const float v0 = x[b * 6 + 3], v1 = x[b * 6 + 4], v2 = x[b * 6 + 5];
+  const float t = sqrtf(w0 * w0 + w1 * w1 + w2 * w2);
+  const float t2 = t * t;
+  float s1, s2, s3;
+  if (fabsf(t) < 0.01f) {  // sinc.py:6-18, :96-108, :126-138 Taylor branches
+    s1 = 1.f - t2 / 6.f * (1.f - t2 / 20.f * (1.f - t2 / 42.f));
+    s2 = 0.5f * (1.f - t2 / 12.f * (1.f - t2 / 30.f * (1.f - t2 / 56.f)));
+    s3 = (1.f / 6.f) * (1.f - t2 / 20.f * (1.f - t2 / 42.f * (1.f - t2 / 72.f)));
+  } else {
+    const float sn = sinf(t), cs = cosf(t);
+    s1 = sn / t;
+    s2 = (1.f - cs) / t2;
+    s3 = (t - sn) / (t2 * t);
+  }
+  // W = hat(w), S = W*W
+  const float W[9] = {0.f, -w2, w1, w2, 0.f, -w0, -w1, w0, 0.f};
+  float S[9];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) S[i * 3 + j] = W[i * 3] * W[j] + W[i * 3 + 1] * W[3 + j] + W[i * 3 + 2] * W[6 + j];
+  const float v[3] = {v0, v1, v2};
+  float* o = g + (size_t)b * 16;
+  for (int i = 0; i < 3; ++i) {
+    float p = 0.f;
+    for (int j = 0; j < 3; ++j) {
+      const float id = i == j ? 1.f : 0.f;
+      o[i * 4 + j] = id + s1 * W[i * 3 + j] + s2 * S[i * 3 + j];
+      p += (id + s2 * W[i * 3 + j] + s3 * S[i * 3 + j]) * v[j];
+    }
+    o[i * 4 + 3] = p;
+  }
+  o[12] = 0.f; o[13] = 0.f; o[14] = 0.f; o[15] = 1.f;
+}
+
+// ======================================================================== orchestration
+static StemW stem_of(const PzEncoderWeights& w) {
+  return StemW{w.mlp1_w, w.mlp1_b, w.mlp2_w, w.mlp2_b, w.bn1_w, w.bn1_b, w.bn1_mean, w.bn1_var,
+               w.bn2_w, w.bn2_b, w.bn2_mean, w.bn2_var};
+}
+
+static bool encoder_weights_ok(const PzEncoderWeights& w) {
+  const void* const* p = reinterpret_cast<const void* const*>(&w);
+  for (size_t i = 0; i < sizeof(PzEncoderWeights) / sizeof(void*); ++i)
+    if (!p[i]) return false;
+  return true;
+}
+
+struct EncoderScratch {
+  float *xfeat, *F1, *nx1, *f1f, *F2, *nx2, *att_cat, *q, *k, *v, *r, *tailp, *fglob;
+  int *knn1r, *knn2r;
+};
+
+static size_t encoder_scratch_layout(int C, Arena& a, EncoderScratch& s) {
+  s.xfeat = a.take<float>((size_t)C * NPTS * D0);
+  s.F1 = a.take<float>((size_t)C * NPTS * C1A);
+  s.nx1 = a.take<float>((size_t)C * S1 * 3);
+  s.knn1r = a.take<int>((size_t)C * S1 * KNN);
+  s.f1f = a.take<float>((size_t)C * S1 * C1B);
+  s.F2 = a.take<float>((size_t)C * S1 * C2A);
+  s.nx2 = a.take<float>((size_t)C * S2 * 3);
+  s.knn2r = a.take<int>((size_t)C * S2 * KNN);
+  s.att_cat = a.take<float>((size_t)C * LATT * 1280);
+  s.q = a.take<float>((size_t)C * LATT * 64);
+  s.k = a.take<float>((size_t)C * LATT * 64);
+  s.v = a.take<float>((size_t)C * LATT * CATT);
+  s.r = a.take<float>((size_t)C * LATT * CATT);
+  s.tailp = a.take<float>((size_t)C * 2 * 1024);
+  s.fglob = a.take<float>((size_t)C * 1024);
+  return a.used;
+}
+
+// fglob_pair: optional [B, E*1024] destination laid out for the pose MLP's concat (model5_b.py:723)
+static int encoder_forward_impl(const PzEncoderWeights* w, int E, int B, const float* xyz, const int64_t* start1,
+                                const int64_t* start2, int precision, const PzEncoderOutputs& o, void* ws,
+                                size_t ws_bytes, float* fglob_pair, const float** xfeat_out, cudaStream_t st) {
+  PZ_REQUIRE(E == 1 || E == 2, PZ_ERR_ARG, "encoder: E must be 1 or 2 (got %d)", E);
+  PZ_REQUIRE(B >= 1, PZ_ERR_ARG, "encoder: B must be >= 1");
+  PZ_REQUIRE(precision == PZ_PREC_FP32, PZ_ERR_UNSUPPORTED,
+             "encoder: precision %d not available in this build (fp32 only)", precision);
+  for (int e = 0; e < E; ++e)
+    PZ_REQUIRE(encoder_weights_ok(w[e]), PZ_ERR_ARG, "encoder: weight set %d has a null pointer", e);
+  const int C = E * B;
+  Arena arena(ws, ws_bytes);
+  EncoderScratch s;
+  encoder_scratch_layout(C, arena, s);
+  PZ_REQUIRE(ws && arena.ok(), PZ_ERR_WORKSPACE, "encoder: workspace %zu B < required %zu B", ws_bytes, arena.used);
+  const PzEncoderWeights& wa = w[0];
+  const PzEncoderWeights& wb = w[E - 1];
+  float* xfeat = o.x_feature ? o.x_feature : s.xfeat;
+  float* f1f = o.f1f ? o.f1f : s.f1f;
+  float* att_cat = o.att_cat ? o.att_cat : s.att_cat;
+  float* nx2 = o.x2 ? o.x2 : s.nx2;
+  if (xfeat_out) *xfeat_out = xfeat;
+
+  // stem: Linear(3,64)+BN+ReLU, Linear(64,64)+BN+ReLU -> x_feature [C,1024,64]
+  stem_kernel<<<C * NPTS / 128, 128, 0, st>>>(xyz, stem_of(wa), stem_of(wb), B, xfeat);
+  PZ_LAUNCH_CHECK();
+
+  // ---- stage 1: FPS 1024->512, kNN 32, grouped MLP 67->128->128, max over K
+  PZ_TRY(launch_fps(xyz, C, NPTS, start1, S1, o.fps1, nullptr, s.nx1, st));
+  PZ_TRY(launch_knn(s.nx1, xyz, C, S1, NPTS, KNN, o.knn1, s.knn1r, nullptr, st));
+  {
+    GemmF32 g;  // F1 = x_feature * mlp3.weight[:, 3:]^T   (bias + xyz part are added per neighbour)
+    g.A = xfeat; g.lda = D0; g.W[0] = wa.mlp3_w + 3; g.W[1] = wb.mlp3_w + 3; g.ldw = 3 + D0;
+    g.rows_per_wset = B * NPTS; g.Y = s.F1; g.ldy = C1A; g.M = C * NPTS; g.N = C1A; g.K = D0;
+    PZ_TRY(launch_gemm_f32(g, st));
+  }
+  {
+    GemmF32 g;
+    g.A = s.F1; g.lda = C1A; g.rows = s.knn1r; g.xyz = xyz; g.centers = s.nx1;
+    g.W1[0] = wa.mlp3_w; g.W1[1] = wb.mlp3_w; g.b1[0] = wa.mlp3_b; g.b1[1] = wb.mlp3_b; g.ldw1 = 3 + D0;
+    g.W[0] = wa.mlp4_w; g.W[1] = wb.mlp4_w; g.bias[0] = wa.mlp4_b; g.bias[1] = wb.mlp4_b; g.ldw = C1A;
+    g.rows_per_wset = B * S1 * KNN; g.Y = f1f; g.ldy = C1B; g.M = C * S1 * KNN; g.N = C1B; g.K = C1A;
+    g.relu = 1; g.group = 32;
+    PZ_TRY(launch_gemm_f32(g, st));
+  }
+  // ---- stage 2: FPS 512->256 on the stage-1 centroids, kNN 32, grouped MLP 131->256->256
+  PZ_TRY(launch_fps(s.nx1, C, S1, start2, S2, o.fps2, nullptr, nx2, st));
+  PZ_TRY(launch_knn(nx2, s.nx1, C, S2, S1, KNN, o.knn2, s.knn2r, nullptr, st));
+  {
+    GemmF32 g;
+    g.A = f1f; g.lda = C1B; g.W[0] = wa.mlp5_w + 3; g.W[1] = wb.mlp5_w + 3; g.ldw = 3 + C1B;
+    g.rows_per_wset = B * S1; g.Y = s.F2; g.ldy = C2A; g.M = C * S1; g.N = C2A; g.K = C1B;
+    PZ_TRY(launch_gemm_f32(g, st));
+  }
+  float* f2f_slot = att_cat + 4 * CATT;  // cat([att1..att4, f2f]) (model5_b.py:467,472): f2f is columns 1024..1279
+  {
+    GemmF32 g;
+    g.A = s.F2; g.lda = C2A; g.rows = s.knn2r; g.xyz = s.nx1; g.centers = nx2;
+    g.W1[0] = wa.mlp5_w; g.W1[1] = wb.mlp5_w; g.b1[0] = wa.mlp5_b; g.b1[1] = wb.mlp5_b; g.ldw1 = 3 + C1B;
+    g.W[0] = wa.mlp6_w; g.W[1] = wb.mlp6_w; g.bias[0] = wa.mlp6_b; g.bias[1] = wb.mlp6_b; g.ldw = C2A;
+    g.rows_per_wset = B * S2 * KNN; g.Y = f2f_slot; g.ldy = 1280; g.M = C * S2 * KNN; g.N = C2B; g.K = C2A;
+    g.relu = 1; g.group = 32;
+    PZ_TRY(launch_gemm_f32(g, st));
+  }
+  if (o.f2f)
+    PZ_CUDA(cudaMemcpy2DAsync(o.f2f, CATT * sizeof(float), f2f_slot, 1280 * sizeof(float), CATT * sizeof(float),
+                              (size_t)C * LATT, cudaMemcpyDeviceToDevice, st));
+
+  // ---- 4 x offset attention (model5_b.py:92-101); layer i writes att_cat[:, i*256:(i+1)*256]
+  const int rows = C * LATT;
+  for (int l = 0; l < 4; ++l) {
+    const float* x = l == 0 ? f2f_slot : att_cat + (l - 1) * CATT;
+    auto proj = [&](const float* w0, const float* w1, const float* b0, const float* b1, int N, float* y) {
+      GemmF32 g;
+      g.A = x; g.lda = 1280; g.W[0] = w0; g.W[1] = w1; g.bias[0] = b0; g.bias[1] = b1; g.ldw = CATT;
+      g.rows_per_wset = B * LATT; g.Y = y; g.ldy = N; g.M = rows; g.N = N; g.K = CATT;
+      return launch_gemm_f32(g, st);
+    };
+    PZ_TRY(proj(wa.q_w[l], wb.q_w[l], wa.q_b[l], wb.q_b[l], 64, s.q));
+    PZ_TRY(proj(wa.k_w[l], wb.k_w[l], wa.k_b[l], wb.k_b[l], 64, s.k));
+    PZ_TRY(proj(wa.v_w[l], wb.v_w[l], wa.v_b[l], wb.v_b[l], CATT, s.v));
+    const int amode = o.attention ? (l == 0 ? 1 : (l == 3 ? 3 : 2)) : 0;
+    PZ_TRY(launch_attention(s.q, 64, s.k, 64, s.v, CATT, C, LATT, 64, CATT, x, 1280, s.r, CATT, o.attention, amode, st));
+    GemmF32 g;  // out = x + relu(W_o r + b_o)
+    g.A = s.r; g.lda = CATT; g.W[0] = wa.o_w[l]; g.W[1] = wb.o_w[l]; g.bias[0] = wa.o_b[l]; g.bias[1] = wb.o_b[l];
+    g.ldw = CATT; g.rows_per_wset = B * LATT; g.Y = att_cat + l * CATT; g.ldy = 1280; g.M = rows; g.N = CATT;
+    g.K = CATT; g.relu = 1; g.R = x; g.ldr = 1280;
+    PZ_TRY(launch_gemm_f32(g, st));
+  }
+
+  // ---- tail: Linear(1280,1024) then max over the 256 points (model5_b.py:472-475)
+  {
+    GemmF32 g;
+    g.A = att_cat; g.lda = 1280; g.W[0] = wa.out_w; g.W[1] = wb.out_w; g.bias[0] = wa.out_b; g.bias[1] = wb.out_b;
+    g.ldw = 1280; g.rows_per_wset = B * LATT; g.M = rows; g.N = 1024; g.K = 1280;
+    float* fg = o.f_global ? o.f_global : s.fglob;
+    if (o.out) {
+      g.Y = o.out; g.ldy = 1024;
+      PZ_TRY(launch_gemm_f32(g, st));
+      rowblock_max_kernel<<<dim3(4, C), 256, 0, st>>>(o.out, 1024, LATT, 1024, C, C, 0, fg, 1024);
+    } else {
+      g.Y = s.tailp; g.ldy = 1024; g.group = 128;
+      PZ_TRY(launch_gemm_f32(g, st));
+      rowblock_max_kernel<<<dim3(4, C), 256, 0, st>>>(s.tailp, 1024, LATT / 128, 1024, C, C, 0, fg, 1024);
+    }
+    PZ_LAUNCH_CHECK();
+    if (fglob_pair)  // [B, E*1024]: pair b = [f_global(cloud b), f_global(cloud B+b)]
+      PZ_CUDA(cudaMemcpy2DAsync(fglob_pair, (size_t)E * 1024 * sizeof(float), fg, 1024 * sizeof(float),
+                                1024 * sizeof(float), B, cudaMemcpyDeviceToDevice, st));
+    if (fglob_pair && E == 2)
+      PZ_CUDA(cudaMemcpy2DAsync(fglob_pair + 1024, (size_t)E * 1024 * sizeof(float), fg + (size_t)B * 1024,
+                                1024 * sizeof(float), 1024 * sizeof(float), B, cudaMemcpyDeviceToDevice, st));
+  }
+  return 0;
+}
+
+}  // namespace pz
+
+using namespace pz;
+
+// ------------------------------------------------------------------------------ C ABI
+extern "C" size_t pz_encoder_workspace_bytes(int E, int B) {
+  if (E < 1 || B < 1) return 0;
+  Arena a(nullptr, 0);
+  EncoderScratch s;
+  return align_up(encoder_scratch_layout(E * B, a, s), 256);
+}
+
+extern "C" int pz_encoder_forward(const PzEncoderWeights* weights_host, int E, int B, const float* xyz,
+                                  const int64_t* start1, const int64_t* start2, int precision,
+                                  const PzEncoderOutputs* outputs_host, void* workspace, size_t workspace_bytes,
+                                  pz_stream_t stream) {
+  PZ_REQUIRE(weights_host && xyz && start1 && start2 && outputs_host, PZ_ERR_ARG, "pz_encoder_forward: null pointer");
+  return encoder_forward_impl(weights_host, E, B, xyz, start1, start2, precision, *outputs_host, workspace,
+                              workspace_bytes, nullptr, nullptr, as_stream(stream));
+}
+
+namespace {
+struct PredictScratch {
+  float *xyz, *fpair, *h0, *h1, *partial, *local, *gmax, *gbias;
+  int64_t *st1, *st2;
+  void* enc;
+  size_t enc_bytes, partial_floats;
+};
+size_t predict_layout(int B, Arena& a, PredictScratch& s) {
+  s.xyz = a.take<float>((size_t)2 * B * NPTS * 3);
+  s.st1 = a.take<int64_t>((size_t)2 * B);
+  s.st2 = a.take<int64_t>((size_t)2 * B);
+  s.fpair = a.take<float>((size_t)B * 2048);
+  s.h0 = a.take<float>((size_t)B * 1024);
+  s.h1 = a.take<float>((size_t)B * 1024);
+  s.partial_floats = (size_t)16 * B * 1024;
+  s.partial = a.take<float>(s.partial_floats);
+  s.local = a.take<float>((size_t)2 * B * NPTS * 64);
+  s.gmax = a.take<float>((size_t)B * 64);
+  s.gbias = a.take<float>((size_t)2 * B * 64);
+  s.enc_bytes = pz_encoder_workspace_bytes(2, B);
+  s.enc = a.take<char>(s.enc_bytes);
+  return a.used;
+}
+}  // namespace
+
+extern "C" size_t pz_predict5_workspace_bytes(int B) {
+  if (B < 1) return 0;
+  Arena a(nullptr, 0);
+  PredictScratch s;
+  return align_up(predict_layout(B, a, s), 256);
+}
+
+extern "C" int pz_predict5(const PzEncoderWeights* enc_host, const PzHeadWeights* heads_host, const float* fpc,
+                           const float* mrpc, int B, const int64_t* starts, int precision, int need, float* out6,
+                           float* de_fpcb, float* de_mrpcb, float* x2_fpc, float* attention_fpc, float* x2_mrpc,
+                           float* attention_mrpc, void* workspace, size_t workspace_bytes, pz_stream_t stream) {
+  PZ_REQUIRE(enc_host && heads_host && fpc && mrpc && starts && out6 && de_fpcb && de_mrpcb, PZ_ERR_ARG,
+             "pz_predict5: null pointer");
+  PZ_REQUIRE(B >= 1, PZ_ERR_ARG, "pz_predict5: B must be >= 1");
+  if (need)
+    PZ_REQUIRE(x2_fpc && attention_fpc && x2_mrpc && attention_mrpc, PZ_ERR_ARG,
+               "pz_predict5: need=1 requires the x2/attention outputs");
+  {
+    const void* const* p = reinterpret_cast<const void* const*>(heads_host);
+    for (size_t i = 0; i < sizeof(PzHeadWeights) / sizeof(void*); ++i)
+      PZ_REQUIRE(p[i], PZ_ERR_ARG, "pz_predict5: head weight %zu is null", i);
+  }
+  cudaStream_t st = as_stream(stream);
+  Arena arena(workspace, workspace_bytes);
+  PredictScratch s;
+  predict_layout(B, arena, s);
+  PZ_REQUIRE(workspace && arena.ok(), PZ_ERR_WORKSPACE, "pz_predict5: workspace %zu B < required %zu B",
+             workspace_bytes, arena.used);
+  const size_t cloud_bytes = (size_t)B * NPTS * 3 * sizeof(float);
+  PZ_CUDA(cudaMemcpyAsync(s.xyz, fpc, cloud_bytes, cudaMemcpyDeviceToDevice, st));
+  PZ_CUDA(cudaMemcpyAsync(s.xyz + (size_t)B * NPTS * 3, mrpc, cloud_bytes, cudaMemcpyDeviceToDevice, st));
+  // starts [4,B]: (Encoder s1, Encoder s2, Encoder2 s1, Encoder2 s2) -> st1 = rows 0,2; st2 = rows 1,3
+  const size_t sb = (size_t)B * sizeof(int64_t);
+  PZ_CUDA(cudaMemcpyAsync(s.st1, starts, sb, cudaMemcpyDeviceToDevice, st));
+  PZ_CUDA(cudaMemcpyAsync(s.st2, starts + B, sb, cudaMemcpyDeviceToDevice, st));
+  PZ_CUDA(cudaMemcpyAsync(s.st1 + B, starts + 2 * (size_t)B, sb, cudaMemcpyDeviceToDevice, st));
+  PZ_CUDA(cudaMemcpyAsync(s.st2 + B, starts + 3 * (size_t)B, sb, cudaMemcpyDeviceToDevice, st));
+
+  PzEncoderOutputs eo = {};
+  float* x2_all = nullptr;
+  float* attn_all = nullptr;
+  // need=True: the encoder writes contiguous [2B,..] tensors but the caller's four outputs are
+  // separate, so attention [2B,256,256] and x2 [2B,256,3] go through scratch that is free until
+  // the heads run (`local`, `partial`) and are copied out per half.
+  if (need) {
+    attn_all = s.local;                                    // 2B*65536 floats == 2B*1024*64
+    x2_all = s.partial;                                    // 2B*768 floats  <= 16*B*1024
+    eo.attention = attn_all;
+    eo.x2 = x2_all;
+  }
+  const float* xfeat = nullptr;
+  PZ_TRY(encoder_forward_impl(enc_host, 2, B, s.xyz, s.st1, s.st2, precision, eo, s.enc, s.enc_bytes, s.fpair,
+                              &xfeat, st));
+  if (need) {
+    const size_t ab = (size_t)B * LATT * LATT * sizeof(float), xb = (size_t)B * S2 * 3 * sizeof(float);
+    PZ_CUDA(cudaMemcpyAsync(attention_fpc, attn_all, ab, cudaMemcpyDeviceToDevice, st));
+    PZ_CUDA(cudaMemcpyAsync(attention_mrpc, attn_all + (size_t)B * LATT * LATT, ab, cudaMemcpyDeviceToDevice, st));
+    PZ_CUDA(cudaMemcpyAsync(x2_fpc, x2_all, xb, cudaMemcpyDeviceToDevice, st));
+    PZ_CUDA(cudaMemcpyAsync(x2_mrpc, x2_all + (size_t)B * S2 * 3, xb, cudaMemcpyDeviceToDevice, st));
+  }
+  const PzHeadWeights& h = *heads_host;
+  // pose MLP on cat(ffpc, fmrpc): 2048-1024-512-512-256-6 (model5_b.py:723-725)
+  PZ_TRY(skinny_linear(s.fpair, 2048, h.tf_w[0], h.tf_b[0], B, 1024, 2048, 1, s.h0, 1024, s.partial, s.partial_floats, st));
+  PZ_TRY(skinny_linear(s.h0, 1024, h.tf_w[1], h.tf_b[1], B, 512, 1024, 1, s.h1, 512, s.partial, s.partial_floats, st));
+  PZ_TRY(skinny_linear(s.h1, 512, h.tf_w[2], h.tf_b[2], B, 512, 512, 1, s.h0, 512, s.partial, s.partial_floats, st));
+  PZ_TRY(skinny_linear(s.h0, 512, h.tf_w[3], h.tf_b[3], B, 256, 512, 1, s.h1, 256, s.partial, s.partial_floats, st));
+  PZ_TRY(skinny_linear(s.h1, 256, h.tf_w[4], h.tf_b[4], B, 6, 256, 0, out6, 6, s.partial, s.partial_floats, st));
+
+  // boundary heads (model5_b.py:738-754)
+  const size_t hl_smem = (3 * 4160 + 64 * 128) * sizeof(float);
+  const size_t hs_smem = (64 * 64 + 32 * 64 + 64 + 32 + 64 + 4 + 64 * 128) * sizeof(float);
+  PZ_CUDA(cudaFuncSetAttribute(head_seg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hs_smem));
+  PZ_CUDA(cudaFuncSetAttribute(head_local_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hl_smem));
+  Mlp3W pre_f = {h.pre_fpc_w[0], h.pre_fpc_b[0], h.pre_fpc_w[1], h.pre_fpc_b[1], h.pre_fpc_w[2], h.pre_fpc_b[2]};
+  Mlp3W pre_r = {h.pre_rpc_w[0], h.pre_rpc_b[0], h.pre_rpc_w[1], h.pre_rpc_b[1], h.pre_rpc_w[2], h.pre_rpc_b[2]};
+  head_local_kernel<<<2 * B * NPTS / 128, 128, hl_smem, st>>>(xfeat, pre_f, pre_r, B, s.local);
+  PZ_LAUNCH_CHECK();
+  // D6: BOTH heads use the max-pool of the *mrpc* local features (model5_b.py:741-744)
+  rowblock_max_kernel<<<dim3(1, B), 256, 0, st>>>(s.local + (size_t)B * NPTS * 64, 64, NPTS, 64, B, B, 0, s.gmax, 64);
+  PZ_LAUNCH_CHECK();
+  seg_bias_kernel<<<dim3(B, 2), 64, 0, st>>>(s.gmax, h.seg_fpc_w[0], h.seg_fpc_b[0], h.seg_rpc_w[0], h.seg_rpc_b[0], B, s.gbias);
+  PZ_LAUNCH_CHECK();
+  Mlp3W seg_f = {h.seg_fpc_w[0], h.seg_fpc_b[0], h.seg_fpc_w[1], h.seg_fpc_b[1], h.seg_fpc_w[2], h.seg_fpc_b[2]};
+  Mlp3W seg_r = {h.seg_rpc_w[0], h.seg_rpc_b[0], h.seg_rpc_w[1], h.seg_rpc_b[1], h.seg_rpc_w[2], h.seg_rpc_b[2]};
+  head_seg_kernel<<<2 * B * NPTS / 128, 128, hs_smem, st>>>(s.local, seg_f, seg_r, s.gbias, B, de_fpcb, de_mrpcb);
+  PZ_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int pz_se3_exp(const float* twist, int B, float* g, pz_stream_t stream) {
+  PZ_REQUIRE(twist && g, PZ_ERR_ARG, "pz_se3_exp: null pointer");
+  PZ_REQUIRE(B >= 0, PZ_ERR_ARG, "pz_se3_exp: B < 0");
+  if (B == 0) return 0;
+  se3_exp_kernel<<<(B + 127) / 128, 128, 0, as_stream(stream)>>>(twist, B, g);
+  PZ_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int pz_scaled_dot_attention(const float* q, const float* k, const float* v, int B, int L, int Dk, int Dv,
+                                       float* values, float* attention_or_null, pz_stream_t stream) {
+  PZ_REQUIRE(q && k && v && values, PZ_ERR_ARG, "pz_scaled_dot_attention: null pointer");
+  PZ_REQUIRE(B >= 0, PZ_ERR_ARG, "pz_scaled_dot_attention: B < 0");
+  if (B == 0) return 0;
+  return launch_attention(q, Dk, k, Dk, v, Dv, B, L, Dk, Dv, nullptr, 0, values, Dv, attention_or_null,
+                          attention_or_null ? 1 : 0, as_stream(stream));
+}
+
+extern "C" int pz_linear(const float* x, int ldx, const float* W, const float* b, int M, int N, int K, int relu,
+                         const float* residual_or_null, int ldr, float* y, int ldy, int precision,
+                         pz_stream_t stream) {
+  PZ_REQUIRE(x && W && y, PZ_ERR_ARG, "pz_linear: null pointer");
+  PZ_REQUIRE(M >= 0 && N >= 1 && K >= 1 && ldx >= K && ldy >= N, PZ_ERR_ARG, "pz_linear: bad sizes");
+  PZ_REQUIRE(precision == PZ_PREC_FP32, PZ_ERR_UNSUPPORTED, "pz_linear: precision %d not available", precision);
+  if (M == 0) return 0;
+  GemmF32 g;
+  g.A = x; g.lda = ldx; g.W[0] = W; g.bias[0] = b; g.ldw = K; g.Y = y; g.ldy = ldy; g.M = M; g.N = N; g.K = K;
+  g.relu = relu; g.R = residual_or_null; g.ldr = ldr;
+  return launch_gemm_f32(g, as_stream(stream));
+}
+
+extern "C" size_t pz_offset_attention_workspace_bytes(int B, int L, int C) {
+  if (B < 1 || L < 1 || C < 4) return 0;
+  const size_t rows = (size_t)B * L;
+  return align_up(rows * (C / 4) * sizeof(float), 256) * 2 + align_up(rows * C * sizeof(float), 256) * 2 + 256;
+}
+
+extern "C" int pz_offset_attention(const float* x, const float* Wq, const float* bq, const float* Wk, const float* bk,
+                                   const float* Wv, const float* bv, const float* Wo, const float* bo, int B, int L,
+                                   int C, int precision, float* out, float* attention_or_null, void* workspace,
+                                   size_t workspace_bytes, pz_stream_t stream) {
+  PZ_REQUIRE(x && Wq && bq && Wk && bk && Wv && bv && Wo && bo && out, PZ_ERR_ARG, "pz_offset_attention: null pointer");
+  PZ_REQUIRE(B >= 1 && C == 256, PZ_ERR_UNSUPPORTED, "pz_offset_attention: C must be 256 (got %d)", C);
+  PZ_REQUIRE(precision == PZ_PREC_FP32, PZ_ERR_UNSUPPORTED, "pz_offset_attention: precision %d not available", precision);
+  cudaStream_t st = as_stream(stream);
+  Arena a(workspace, workspace_bytes);
+  const size_t rows = (size_t)B * L;
+  float* q = a.take<float>(rows * (C / 4));
+  float* k = a.take<float>(rows * (C / 4));
+  float* v = a.take<float>(rows * C);
+  float* r = a.take<float>(rows * C);
+  PZ_REQUIRE(workspace && a.ok(), PZ_ERR_WORKSPACE, "pz_offset_attention: workspace %zu B < required %zu B",
+             workspace_bytes, a.used);
+  auto lin = [&](const float* in, const float* W, const float* b, int N, float* y, int relu, const float* R) {
+    GemmF32 g;
+    g.A = in; g.lda = C; g.W[0] = W; g.bias[0] = b; g.ldw = C; g.Y = y; g.ldy = N; g.M = (int)rows; g.N = N; g.K = C;
+    g.relu = relu; g.R = R; g.ldr = C;
+    return launch_gemm_f32(g, st);
+  };
+  PZ_TRY(lin(x, Wq, bq, C / 4, q, 0, nullptr));
+  PZ_TRY(lin(x, Wk, bk, C / 4, k, 0, nullptr));
+  PZ_TRY(lin(x, Wv, bv, C, v, 0, nullptr));
+  PZ_TRY(launch_attention(q, C / 4, k, C / 4, v, C, B, L, C / 4, C, x, C, r, C, attention_or_null,
+                          attention_or_null ? 1 : 0, st));
+  return lin(r, Wo, bo, C, out, 1, x);
+}
+
+extern "C" size_t pz_group_mlp_workspace_bytes(int B, int N, int D, int S, int K, int C1, int C2) {
+  (void)C2;
+  if (B < 1 || N < 1 || S < 1 || K < 1 || C1 < 1) return 0;
+  return align_up((size_t)B * N * C1 * sizeof(float), 256) + align_up((size_t)B * S * K * sizeof(int), 256) + 512;
+}
+
+extern "C" int pz_group_mlp_maxpool(const float* xyz, const float* feat, const float* new_xyz, const int64_t* knn_idx,
+                                    const float* W1, const float* b1, const float* W2, const float* b2, int B, int N,
+                                    int D, int S, int K, int C1, int C2, int precision, float* out, void* workspace,
+                                    size_t workspace_bytes, pz_stream_t stream) {
+  PZ_REQUIRE(xyz && feat && new_xyz && knn_idx && W1 && b1 && W2 && b2 && out, PZ_ERR_ARG,
+             "pz_group_mlp_maxpool: null pointer");
+  PZ_REQUIRE(B >= 1 && N >= 1 && D >= 1 && S >= 1 && C1 >= 1 && C2 >= 1, PZ_ERR_ARG, "pz_group_mlp_maxpool: bad sizes");
+  PZ_REQUIRE(K == 32, PZ_ERR_UNSUPPORTED, "pz_group_mlp_maxpool: K must be 32 (got %d)", K);
+  PZ_REQUIRE(C1 <= 256, PZ_ERR_UNSUPPORTED, "pz_group_mlp_maxpool: C1 must be <= 256 (got %d)", C1);
+  PZ_REQUIRE(((size_t)B * S * K) % 128 == 0, PZ_ERR_UNSUPPORTED, "pz_group_mlp_maxpool: B*S must be a multiple of 4");
+  PZ_REQUIRE(precision == PZ_PREC_FP32, PZ_ERR_UNSUPPORTED, "pz_group_mlp_maxpool: precision %d not available", precision);
+  cudaStream_t st = as_stream(stream);
+  Arena a(workspace, workspace_bytes);
+  float* F = a.take<float>((size_t)B * N * C1);
+  int* rows = a.take<int>((size_t)B * S * K);
+  PZ_REQUIRE(workspace && a.ok(), PZ_ERR_WORKSPACE, "pz_group_mlp_maxpool: workspace %zu B < required %zu B",
+             workspace_bytes, a.used);
+  const size_t total = (size_t)B * S * K;
+  idx64_to_rows32_kernel<<<(int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096), 256, 0, st>>>(
+      knn_idx, total, (size_t)S * K, N, rows);
+  PZ_LAUNCH_CHECK();
+  GemmF32 g1;
+  g1.A = feat; g1.lda = D; g1.W[0] = W1 + 3; g1.ldw = 3 + D; g1.Y = F; g1.ldy = C1; g1.M = B * N; g1.N = C1; g1.K = D;
+  PZ_TRY(launch_gemm_f32(g1, st));
+  GemmF32 g2;
+  g2.A = F; g2.lda = C1; g2.rows = rows; g2.xyz = xyz; g2.centers = new_xyz; g2.W1[0] = W1; g2.b1[0] = b1;
+  g2.ldw1 = 3 + D; g2.W[0] = W2; g2.bias[0] = b2; g2.ldw = C1; g2.Y = out; g2.ldy = C2; g2.M = (int)total;
+  g2.N = C2; g2.K = C1; g2.relu = 1; g2.group = 32;
+  return launch_gemm_f32(g2, st);
+}

@@ -1,0 +1,420 @@
+// Point-cloud geometry kernels for sm_100a: farthest-point sampling, kNN selection,
+// square_distance, ball query, row gather and the materialising grouping of
+// sample_and_group.  Reference semantics: pointnet_util.py:22-136.
+//
+// Arithmetic contract (bit-exact indices): every squared distance is
+//   ((dx*dx) + (dy*dy)) + (dz*dz)   in fp32, each op rounded, no FMA contraction
+// (the ATen CPU evaluation of pointnet_util.py:36 / :70), hence the explicit
+// __fmul_rn / __fadd_rn below.
+#include "pz_common.cuh"
+
+namespace pz {
+
+__device__ __forceinline__ float sqdist3(float ax, float ay, float az, float bx, float by, float bz) {
+  float dx = __fsub_rn(ax, bx), dy = __fsub_rn(ay, by), dz = __fsub_rn(az, bz);
+  return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+// ======================================================================================
+// Farthest point sampling: one CTA per cloud, cloud + running min-distance in registers
+// (PPT points per thread, strided so that a thread's points are in increasing index
+// order), coordinates mirrored in shared memory (SoA) for the centroid broadcast.
+// One __syncthreads per iteration: warp argmax with two redux.sync, per-warp winners in a
+// parity-double-buffered smem slot, every warp re-reduces the <=32 winners redundantly.
+// Key = (dist_bits << 32) | ~index: max key == largest distance, lowest index on ties
+// (torch.max on CPU returns the first maximum, pointnet_util.py:72).
+// ======================================================================================
+template <int PPT, int T>
+__global__ void __launch_bounds__(T) fps_kernel(const float* __restrict__ xyz, int N, int S,
+                                                const int64_t* __restrict__ start,
+                                                int64_t* __restrict__ out64,
+                                                int* __restrict__ out_rows32,
+                                                float* __restrict__ new_xyz) {
+  extern __shared__ float fps_smem[];
+  float* xs = fps_smem;
+  float* ys = xs + N;
+  float* zs = ys + N;
+  __shared__ unsigned int whi[2][32];
+  __shared__ unsigned int wlo[2][32];
+
+  const int c = blockIdx.x;
+  const int t = threadIdx.x;
+  const int lane = t & 31, warp = t >> 5;
+  constexpr int NW = T / 32;
+  const float* p = xyz + (size_t)c * N * 3;
+  for (int i = t; i < N * 3; i += T) {
+    float v = p[i];
+    int pt = i / 3, d = i - pt * 3;
+    fps_smem[d * N + pt] = v;
+  }
+  __syncthreads();
+
+  float px[PPT], py[PPT], pz_[PPT], md[PPT];
+#pragma unroll
+  for (int j = 0; j < PPT; ++j) {
+    int i = t + j * T;
+    bool ok = i < N;
+    px[j] = ok ? xs[i] : 0.f;
+    py[j] = ok ? ys[i] : 0.f;
+    pz_[j] = ok ? zs[i] : 0.f;
+    md[j] = ok ? 1e10f : 0.f;  // padding can never beat a real point (ties -> lowest index)
+  }
+
+  int far = (int)start[c];
+  far = min(max(far, 0), N - 1);
+  for (int s = 0; s < S; ++s) {
+    if (t == 0) {
+      if (out64) out64[(size_t)c * S + s] = far;
+      if (out_rows32) out_rows32[(size_t)c * S + s] = c * N + far;
+    }
+    const float cx = xs[far], cy = ys[far], cz = zs[far];
+    if (t < 3 && new_xyz) new_xyz[((size_t)c * S + s) * 3 + t] = (t == 0 ? cx : (t == 1 ? cy : cz));
+    if (s + 1 == S) break;
+
+    float best = -1.f;
+    int besti = 0;
+#pragma unroll
+    for (int j = 0; j < PPT; ++j) {
+      int i = t + j * T;
+      if (i < N) {
+        float d = sqdist3(px[j], py[j], pz_[j], cx, cy, cz);
+        md[j] = fminf(md[j], d);
+      }
+      if (md[j] > best) {  // strict: earlier (lower) index wins inside a thread
+        best = md[j];
+        besti = i;
+      }
+    }
+    unsigned int hi = __float_as_uint(best);  // distances are >= 0: bits are order preserving
+    unsigned int lo = ~(unsigned int)besti;
+    unsigned int mhi = __reduce_max_sync(0xffffffffu, hi);
+    unsigned int mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
+    const int par = s & 1;
+    if (lane == 0) {
+      whi[par][warp] = mhi;
+      wlo[par][warp] = mlo;
+    }
+    __syncthreads();
+    unsigned int h2 = lane < NW ? whi[par][lane] : 0u;
+    unsigned int l2 = lane < NW ? wlo[par][lane] : 0u;
+    unsigned int ghi = __reduce_max_sync(0xffffffffu, h2);
+    unsigned int glo = __reduce_max_sync(0xffffffffu, (h2 == ghi && lane < NW) ? l2 : 0u);
+    far = (int)(~glo);
+  }
+}
+
+template <int PPT, int T>
+static int fps_launch_t(const float* xyz, int B, int N, const int64_t* start, int S, int64_t* out64,
+                        int* out_rows32, float* new_xyz, cudaStream_t st) {
+  size_t smem = (size_t)N * 3 * sizeof(float);
+  if (smem > 48 * 1024)
+    PZ_CUDA(cudaFuncSetAttribute(fps_kernel<PPT, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  fps_kernel<PPT, T><<<B, T, smem, st>>>(xyz, N, S, start, out64, out_rows32, new_xyz);
+  PZ_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_fps(const float* xyz, int B, int N, const int64_t* start, int S, int64_t* out64,
+               int* out_rows32, float* new_xyz, cudaStream_t st) {
+  if (N <= 256) return fps_launch_t<2, 128>(xyz, B, N, start, S, out64, out_rows32, new_xyz, st);
+  if (N <= 512) return fps_launch_t<4, 128>(xyz, B, N, start, S, out64, out_rows32, new_xyz, st);
+  if (N <= 1024) return fps_launch_t<4, 256>(xyz, B, N, start, S, out64, out_rows32, new_xyz, st);
+  if (N <= 2048) return fps_launch_t<4, 512>(xyz, B, N, start, S, out64, out_rows32, new_xyz, st);
+  if (N <= 4096) return fps_launch_t<4, 1024>(xyz, B, N, start, S, out64, out_rows32, new_xyz, st);
+  if (N <= 8192) return fps_launch_t<8, 1024>(xyz, B, N, start, S, out64, out_rows32, new_xyz, st);
+  if (N <= 16384) return fps_launch_t<16, 1024>(xyz, B, N, start, S, out64, out_rows32, new_xyz, st);
+  return fail(PZ_ERR_UNSUPPORTED, "pz_fps: N=%d exceeds the supported maximum 16384", N);
+}
+
+// ======================================================================================
+// kNN: one warp per query.  Keys are (dist_bits << 32) | index, so one unsigned 64-bit
+// compare orders by (distance, index).  The warp keeps its current best 32 keys sorted
+// across lanes; candidates that beat the 32nd key are compacted (ballot + popc) into a
+// per-warp queue and folded in 32 at a time with a bitonic sort + bitonic merge
+// (WarpSelect-style), so the [B,S,N] distance matrix of pointnet_util.py:118 never exists.
+// ======================================================================================
+constexpr int KNN_WARPS = 8;      // queries per CTA
+constexpr int KNN_CHUNK = 2048;   // points staged in smem per pass
+typedef unsigned long long u64;
+
+__device__ __forceinline__ u64 bitonic_step(u64 v, int lane, int j, bool ascending_block) {
+  u64 o = __shfl_xor_sync(0xffffffffu, v, j);
+  bool lower = (lane & j) == 0;
+  bool keep_min = (lower == ascending_block);
+  u64 mn = v < o ? v : o, mx = v < o ? o : v;
+  return keep_min ? mn : mx;
+}
+
+// fold 32 candidate keys (one per lane, any order) into the sorted top-32 `top`
+__device__ __forceinline__ u64 knn_merge(u64 top, u64 cand, int lane) {
+#pragma unroll
+  for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) cand = bitonic_step(cand, lane, j, (lane & k) == 0 || k == 32);
+  }
+  u64 rev = __shfl_sync(0xffffffffu, cand, 31 - lane);
+  u64 m = top < rev ? top : rev;  // bitonic sequence holding the 32 smallest of the union
+#pragma unroll
+  for (int j = 16; j > 0; j >>= 1) m = bitonic_step(m, lane, j, true);
+  return m;
+}
+
+__global__ void __launch_bounds__(KNN_WARPS * 32) knn_kernel(const float* __restrict__ query,
+                                                             const float* __restrict__ xyz, int S,
+                                                             int N, int K,
+                                                             int64_t* __restrict__ out64,
+                                                             int* __restrict__ out_rows32,
+                                                             float* __restrict__ out_d2) {
+  __shared__ float xs[KNN_CHUNK], ys[KNN_CHUNK], zs[KNN_CHUNK];
+  __shared__ u64 queue[KNN_WARPS][64];
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int q = blockIdx.x * KNN_WARPS + warp;
+  const bool active = q < S;
+  float qx = 0.f, qy = 0.f, qz = 0.f;
+  if (active) {
+    const float* qp = query + ((size_t)b * S + q) * 3;
+    qx = qp[0]; qy = qp[1]; qz = qp[2];
+  }
+  const float* p = xyz + (size_t)b * N * 3;
+  u64 top = ~0ull;   // lane l holds the l-th smallest key so far
+  u64 tau = ~0ull;   // current 32nd smallest
+  int qn = 0;
+  u64* myq = queue[warp];
+  const unsigned lt_mask = (1u << lane) - 1u;
+
+  for (int base = 0; base < N; base += KNN_CHUNK) {
+    const int cnt = min(KNN_CHUNK, N - base);
+    __syncthreads();
+    for (int i = threadIdx.x; i < cnt * 3; i += KNN_WARPS * 32) {
+      float v = p[(size_t)base * 3 + i];
+      int pt = i / 3, d = i - pt * 3;
+      (d == 0 ? xs : (d == 1 ? ys : zs))[pt] = v;
+    }
+    __syncthreads();
+    if (!active) continue;
+    for (int i0 = 0; i0 < cnt; i0 += 32) {
+      const int i = i0 + lane;
+      bool pass = false;
+      u64 key = ~0ull;
+      if (i < cnt) {
+        float d = sqdist3(qx, qy, qz, xs[i], ys[i], zs[i]);
+        key = ((u64)__float_as_uint(d) << 32) | (unsigned)(base + i);
+        pass = key < tau;
+      }
+      unsigned m = __ballot_sync(0xffffffffu, pass);
+      if (m == 0u) continue;
+      if (pass) myq[qn + __popc(m & lt_mask)] = key;
+      qn += __popc(m);
+      __syncwarp();
+      if (qn >= 32) {
+        top = knn_merge(top, myq[lane], lane);
+        tau = __shfl_sync(0xffffffffu, top, 31);
+        const int rem = qn - 32;
+        u64 carry = lane < rem ? myq[32 + lane] : 0ull;
+        __syncwarp();
+        if (lane < rem) myq[lane] = carry;
+        __syncwarp();
+        qn = rem;
+      }
+    }
+  }
+  if (!active) return;
+  if (qn > 0) {
+    top = knn_merge(top, lane < qn ? myq[lane] : ~0ull, lane);
+  }
+  if (lane < K) {
+    const size_t o = ((size_t)b * S + q) * K + lane;
+    const unsigned idx = (unsigned)(top & 0xffffffffu);
+    if (out64) out64[o] = (int64_t)idx;
+    if (out_rows32) out_rows32[o] = b * N + (int)idx;
+    if (out_d2) out_d2[o] = __uint_as_float((unsigned)(top >> 32));
+  }
+}
+
+int launch_knn(const float* query, const float* xyz, int B, int S, int N, int K, int64_t* out64,
+               int* out_rows32, float* out_d2, cudaStream_t st) {
+  PZ_REQUIRE(K >= 1 && K <= 32, PZ_ERR_UNSUPPORTED, "pz_knn: K=%d not in [1,32]", K);
+  PZ_REQUIRE(N >= K, PZ_ERR_UNSUPPORTED, "pz_knn: N=%d < K=%d", N, K);
+  PZ_REQUIRE(B <= 65535, PZ_ERR_UNSUPPORTED, "pz_knn: B=%d > 65535", B);
+  dim3 grid((S + KNN_WARPS - 1) / KNN_WARPS, B);
+  knn_kernel<<<grid, KNN_WARPS * 32, 0, st>>>(query, xyz, S, N, K, out64, out_rows32, out_d2);
+  PZ_LAUNCH_CHECK();
+  return 0;
+}
+
+// ======================================================================================
+// square_distance (materialising API): HBM-write bound, 128-bit stores along N.
+// ======================================================================================
+__global__ void __launch_bounds__(256) sqdist_kernel(const float* __restrict__ src,
+                                                     const float* __restrict__ dst, int S, int N,
+                                                     float* __restrict__ out) {
+  const int b = blockIdx.z;
+  const int s = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (s >= S) return;
+  const float* sp = src + ((size_t)b * S + s) * 3;
+  const float sx = sp[0], sy = sp[1], sz = sp[2];
+  const float* dp = dst + (size_t)b * N * 3;
+  float* op = out + ((size_t)b * S + s) * N;
+  const int lane = threadIdx.x & 31;
+  for (int n = blockIdx.x * 32 * 4 + lane; n < N; n += gridDim.x * 32 * 4) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      int i = n + u * 32;
+      if (i < N) op[i] = sqdist3(sx, sy, sz, dp[i * 3 + 0], dp[i * 3 + 1], dp[i * 3 + 2]);
+    }
+  }
+}
+
+// ======================================================================================
+// ball query: one thread per query scans the cloud in index order (pointnet_util.py:76-96)
+// ======================================================================================
+__global__ void __launch_bounds__(128) ball_query_kernel(const float* __restrict__ xyz,
+                                                         const float* __restrict__ new_xyz, int N,
+                                                         int S, float r2, int nsample,
+                                                         int64_t* __restrict__ out) {
+  const int b = blockIdx.y;
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  const float* qp = new_xyz + ((size_t)b * S + s) * 3;
+  const float qx = qp[0], qy = qp[1], qz = qp[2];
+  const float* p = xyz + (size_t)b * N * 3;
+  int64_t* o = out + ((size_t)b * S + s) * nsample;
+  int cnt = 0;
+  int64_t first = N;
+  for (int i = 0; i < N && cnt < nsample; ++i) {
+    float d = sqdist3(qx, qy, qz, p[i * 3], p[i * 3 + 1], p[i * 3 + 2]);
+    if (!(d > r2)) {
+      if (cnt == 0) first = i;
+      o[cnt++] = i;
+    }
+  }
+  for (; cnt < nsample; ++cnt) o[cnt] = first;
+}
+
+// ======================================================================================
+// index_points: generic row gather in 4-byte or 1-byte units
+// ======================================================================================
+template <typename U>
+__global__ void __launch_bounds__(256) gather_rows_kernel(const U* __restrict__ pts,
+                                                          const int64_t* __restrict__ idx, int N,
+                                                          int row_units, int M, size_t total,
+                                                          U* __restrict__ out) {
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (size_t)gridDim.x * blockDim.x) {
+    size_t row = e / row_units;
+    int u = (int)(e - row * row_units);
+    size_t b = row / M;
+    int64_t j = idx[row];
+    out[e] = pts[(b * N + (size_t)j) * row_units + u];
+  }
+}
+
+// ======================================================================================
+// grouping tail of sample_and_group: new_points[b,s,k,:] = [xyz[j]-ctr, feat[j]]
+// ======================================================================================
+__global__ void __launch_bounds__(256) group_concat_kernel(const float* __restrict__ xyz,
+                                                           const float* __restrict__ feat,
+                                                           const float* __restrict__ new_xyz,
+                                                           const int64_t* __restrict__ knn, int N,
+                                                           int D, int S, int K, size_t rows,
+                                                           float* __restrict__ new_points,
+                                                           float* __restrict__ grouped_xyz) {
+  const int W = 3 + D;
+  const int lane = threadIdx.x & 31;
+  const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  for (size_t r = warp0; r < rows; r += nwarps) {  // r = (b*S + s)*K + k
+    const size_t bs = r / K;
+    const size_t b = bs / S;
+    const size_t j = b * N + (size_t)knn[r];
+    float* o = new_points + r * W;
+    if (lane < 3) {
+      float v = xyz[j * 3 + lane];
+      o[lane] = __fsub_rn(v, new_xyz[bs * 3 + lane]);
+      if (grouped_xyz) grouped_xyz[r * 3 + lane] = v;
+    }
+    for (int d = lane; d < D; d += 32) o[3 + d] = feat[j * D + d];
+  }
+}
+
+}  // namespace pz
+
+// ------------------------------------------------------------------------- C ABI
+using namespace pz;
+
+extern "C" int pz_fps(const float* xyz, int B, int N, const int64_t* start, int S, int64_t* out_idx,
+                      float* new_xyz_or_null, pz_stream_t stream) {
+  PZ_REQUIRE(xyz && start && out_idx, PZ_ERR_ARG, "pz_fps: null pointer");
+  PZ_REQUIRE(B >= 0 && N >= 1 && S >= 1, PZ_ERR_ARG, "pz_fps: bad sizes B=%d N=%d S=%d", B, N, S);
+  if (B == 0) return 0;
+  return launch_fps(xyz, B, N, start, S, out_idx, nullptr, new_xyz_or_null, as_stream(stream));
+}
+
+extern "C" int pz_knn(const float* query, const float* xyz, int B, int S, int N, int K,
+                      int64_t* out_idx, float* out_d2_or_null, pz_stream_t stream) {
+  PZ_REQUIRE(query && xyz && out_idx, PZ_ERR_ARG, "pz_knn: null pointer");
+  PZ_REQUIRE(B >= 0 && S >= 0 && N >= 1, PZ_ERR_ARG, "pz_knn: bad sizes B=%d S=%d N=%d", B, S, N);
+  if (B == 0 || S == 0) return 0;
+  return launch_knn(query, xyz, B, S, N, K, out_idx, nullptr, out_d2_or_null, as_stream(stream));
+}
+
+extern "C" int pz_sqdist(const float* src, const float* dst, int B, int S, int N, float* out,
+                         pz_stream_t stream) {
+  PZ_REQUIRE(src && dst && out, PZ_ERR_ARG, "pz_sqdist: null pointer");
+  PZ_REQUIRE(B >= 0 && S >= 0 && N >= 0, PZ_ERR_ARG, "pz_sqdist: bad sizes");
+  if (B == 0 || S == 0 || N == 0) return 0;
+  PZ_REQUIRE(B <= 65535 && (S + 7) / 8 <= 65535, PZ_ERR_UNSUPPORTED, "pz_sqdist: grid too large");
+  int gx = (N + 127) / 128;
+  if (gx > 64) gx = 64;
+  dim3 grid(gx, (S + 7) / 8, B);
+  sqdist_kernel<<<grid, 256, 0, as_stream(stream)>>>(src, dst, S, N, out);
+  PZ_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int pz_ball_query(const float* xyz, const float* new_xyz, int B, int N, int S,
+                             float radius, int nsample, int64_t* out_idx, pz_stream_t stream) {
+  PZ_REQUIRE(xyz && new_xyz && out_idx, PZ_ERR_ARG, "pz_ball_query: null pointer");
+  PZ_REQUIRE(B >= 0 && N >= 1 && S >= 0 && nsample >= 1, PZ_ERR_ARG, "pz_ball_query: bad sizes");
+  if (B == 0 || S == 0) return 0;
+  PZ_REQUIRE(B <= 65535, PZ_ERR_UNSUPPORTED, "pz_ball_query: B > 65535");
+  dim3 grid((S + 127) / 128, B);
+  ball_query_kernel<<<grid, 128, 0, as_stream(stream)>>>(xyz, new_xyz, N, S, radius * radius, nsample, out_idx);
+  PZ_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int pz_gather(const void* pts, const int64_t* idx, int B, int N, int C, int M,
+                         int elem_bytes, void* out, pz_stream_t stream) {
+  PZ_REQUIRE(pts && idx && out, PZ_ERR_ARG, "pz_gather: null pointer");
+  PZ_REQUIRE(B >= 0 && N >= 1 && C >= 1 && M >= 0 && elem_bytes >= 1, PZ_ERR_ARG, "pz_gather: bad sizes");
+  if (B == 0 || M == 0) return 0;
+  size_t row_bytes = (size_t)C * elem_bytes;
+  bool words = (row_bytes % 4 == 0) && ((uintptr_t)pts % 4 == 0) && ((uintptr_t)out % 4 == 0);
+  size_t unit = words ? 4 : 1;
+  int row_units = (int)(row_bytes / unit);
+  size_t total = (size_t)B * M * row_units;
+  int blocks = (int)((total + 255) / 256 < (size_t)kNumSMs * 16 ? (total + 255) / 256 : (size_t)kNumSMs * 16);
+  if (words)
+    gather_rows_kernel<uint32_t><<<blocks, 256, 0, as_stream(stream)>>>((const uint32_t*)pts, idx, N, row_units, M, total, (uint32_t*)out);
+  else
+    gather_rows_kernel<uint8_t><<<blocks, 256, 0, as_stream(stream)>>>((const uint8_t*)pts, idx, N, row_units, M, total, (uint8_t*)out);
+  PZ_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int pz_group_concat(const float* xyz, const float* feat_or_null, const float* new_xyz,
+                               const int64_t* knn_idx, int B, int N, int D, int S, int K,
+                               float* new_points, float* grouped_xyz_or_null, pz_stream_t stream) {
+  PZ_REQUIRE(xyz && new_xyz && knn_idx && new_points, PZ_ERR_ARG, "pz_group_concat: null pointer");
+  PZ_REQUIRE(feat_or_null || D == 0, PZ_ERR_ARG, "pz_group_concat: feat is null but D=%d", D);
+  PZ_REQUIRE(B >= 0 && N >= 1 && D >= 0 && S >= 0 && K >= 1, PZ_ERR_ARG, "pz_group_concat: bad sizes");
+  size_t rows = (size_t)B * S * K;
+  if (rows == 0) return 0;
+  size_t want = (rows + 7) / 8;
+  int blocks = (int)(want < (size_t)kNumSMs * 16 ? want : (size_t)kNumSMs * 16);
+  group_concat_kernel<<<blocks, 256, 0, as_stream(stream)>>>(xyz, feat_or_null, new_xyz, knn_idx, N, D, S, K, rows, new_points, grouped_xyz_or_null);
+  PZ_LAUNCH_CHECK();
+  return 0;
+}

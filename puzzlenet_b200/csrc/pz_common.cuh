@@ -1,0 +1,100 @@
+// Shared helpers for libpuzzlenet_sm100.so (internal; the public ABI is include/puzzlenet_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/puzzlenet_b200.h"
+
+namespace pz {
+
+// thread-local last-error text behind pz_last_error()
+char* error_buffer();
+int fail(int code, const char* fmt, ...);
+
+#define PZ_REQUIRE(cond, code, ...)                      \
+  do {                                                   \
+    if (!(cond)) return ::pz::fail((code), __VA_ARGS__); \
+  } while (0)
+
+#define PZ_CUDA(expr)                                                                   \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess)                                                              \
+      return ::pz::fail((int)_e, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                        __FILE__, __LINE__);                                            \
+  } while (0)
+
+#define PZ_LAUNCH_CHECK() PZ_CUDA(cudaGetLastError())
+
+// propagate a non-zero status from an internal call
+#define PZ_TRY(expr)         \
+  do {                       \
+    int _s = (expr);         \
+    if (_s != 0) return _s;  \
+  } while (0)
+
+static inline cudaStream_t as_stream(pz_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// bump allocator over the caller's workspace
+struct Arena {
+  char* base;
+  size_t size;
+  size_t used;
+  Arena(void* p, size_t n) : base(static_cast<char*>(p)), size(n), used(0) {}
+  template <typename T>
+  T* take(size_t count) {
+    size_t off = align_up(used, 256);
+    used = off + count * sizeof(T);
+    return reinterpret_cast<T*>(base + off);
+  }
+  bool ok() const { return used <= size; }
+};
+
+constexpr int kNumSMs = 148;  // B200
+
+// ---- internal launchers shared between translation units -------------------------------
+
+// fps.cu / knn.cu: int32 "global row" outputs feed the fused grouping kernels.
+int launch_fps(const float* xyz, int B, int N, const int64_t* start64, int S, int64_t* out64,
+               int* out_rows32, float* new_xyz, cudaStream_t st);
+int launch_knn(const float* query, const float* xyz, int B, int S, int N, int K, int64_t* out64,
+               int* out_rows32, float* out_d2, cudaStream_t st);
+
+// gemm_f32.cu
+struct GemmF32 {
+  // Y[M,N] = epilogue(A[M,K] * W[N,K]^T + bias[N]); all row-major, K contiguous.
+  const float* A = nullptr;
+  int lda = 0;
+  const float* W[2] = {nullptr, nullptr};  // weight set w = row / rows_per_wset
+  const float* bias[2] = {nullptr, nullptr};
+  int ldw = 0;
+  int rows_per_wset = 0;  // 0 -> single set
+  float* Y = nullptr;
+  int ldy = 0;
+  int M = 0, N = 0, K = 0;
+  int relu = 0;
+  float alpha = 1.f;  // applied to the accumulator before bias
+  int ksplit = 0;     // >0: split K over grid.z in chunks of ksplit, raw partials to Y + z*M*ldy
+  // EPI_RESIDUAL: Y = R + relu(acc + bias)
+  const float* R = nullptr;
+  int ldr = 0;
+  // EPI_ROWBIAS: extra per-row-block bias table rb[(row / rb_rows), N]
+  const float* rowbias = nullptr;
+  int rb_rows = 0;
+  // EPI_GROUPMAX: Y[M/G, N] = relu?(max over G consecutive rows + bias); G in {32, 128}
+  int group = 0;
+  // gathered A (grouped-MLP layer 2): A[r,k] = relu(F[rows[r],k] + b1[k] + W1x[k,:] . (xyz[rows[r]] - ctr[r/32]))
+  const int* rows = nullptr;      // [M] global row ids into F / xyz
+  const float* xyz = nullptr;     // [*,3]
+  const float* centers = nullptr; // [M/32,3]
+  const float* W1[2] = {nullptr, nullptr};  // [K, ldw1] first three columns used
+  const float* b1[2] = {nullptr, nullptr};  // [K]
+  int ldw1 = 0;
+};
+int launch_gemm_f32(const GemmF32& g, cudaStream_t st);
+
+}  // namespace pz

@@ -1,0 +1,167 @@
+"""Drop-in for the reference's ``pointnet_util`` on the PuzzleNet hot path.
+
+Same function names, argument order, defaults and return shapes as
+``pointnet_util.py`` of the reference (file:line cited per function); every
+function launches hand-written sm_100a kernels through the C ABI
+(``include/puzzlenet_b200.h``).  CUDA tensors only -- there is no CPU fallback.
+
+Index outputs are ``torch.int64`` like the reference.  FPS consumes exactly one
+``torch.randint(0, N, (B,))`` from the CPU default generator per call
+(pointnet_util.py:65), so seeding reproduces the reference's centroids.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+
+
+def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
+    _lib.require_cuda(t)
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32 (got {t.dtype})")
+    return t.contiguous()
+
+
+def _i64c(t: torch.Tensor, name: str) -> torch.Tensor:
+    _lib.require_cuda(t)
+    if t.dtype != torch.int64:
+        raise TypeError(f"{name} must be int64 (got {t.dtype})")
+    return t.contiguous()
+
+
+def square_distance(src, dst):
+    """pointnet_util.py:22-36 -- src [B,S,3], dst [B,N,3] -> [B,S,N] squared distances."""
+    src, dst = _f32c(src, "src"), _f32c(dst, "dst")
+    B, S, C = src.shape
+    if C != 3 or dst.shape[0] != B or dst.shape[2] != 3:
+        raise ValueError(f"square_distance expects [B,S,3] and [B,N,3] (got {tuple(src.shape)}, {tuple(dst.shape)})")
+    N = dst.shape[1]
+    out = torch.empty(B, S, N, device=src.device, dtype=torch.float32)
+    with torch.cuda.device(src.device):
+        _lib.call("pz_sqdist", src.data_ptr(), dst.data_ptr(), B, S, N, out.data_ptr(), _lib.stream_ptr())
+    return out
+
+
+def index_points(points, idx):
+    """pointnet_util.py:39-50 -- points [B,N,C], idx [B,S] or [B,S,K] -> [B,S,(K,)C]."""
+    _lib.require_cuda(points, idx)
+    points = points.contiguous()
+    idx = _i64c(idx, "idx")
+    B, N, Cc = points.shape
+    raw = idx.shape
+    M = idx.numel() // B if B else 0
+    out = torch.empty(B, M, Cc, device=points.device, dtype=points.dtype)
+    with torch.cuda.device(points.device):
+        _lib.call("pz_gather", points.data_ptr(), idx.data_ptr(), B, N, Cc, M, points.element_size(), out.data_ptr(),
+                  _lib.stream_ptr())
+    return out.reshape(*raw, Cc)
+
+
+def _draw_start(B: int, N: int, device) -> torch.Tensor:
+    # pointnet_util.py:65: drawn on the CPU generator, then moved to the device
+    return torch.randint(0, N, (B,), dtype=torch.long).to(device)
+
+
+def _fps(xyz: torch.Tensor, npoint: int, start: torch.Tensor, want_xyz: bool):
+    B, N, _ = xyz.shape
+    idx = torch.empty(B, npoint, device=xyz.device, dtype=torch.int64)
+    new_xyz = torch.empty(B, npoint, 3, device=xyz.device, dtype=torch.float32) if want_xyz else None
+    with torch.cuda.device(xyz.device):
+        _lib.call("pz_fps", xyz.data_ptr(), B, N, start.data_ptr(), npoint, idx.data_ptr(),
+                  new_xyz.data_ptr() if want_xyz else None, _lib.stream_ptr())
+    return idx, new_xyz
+
+
+def farthest_point_sample(xyz, npoint):
+    """pointnet_util.py:53-73 -- xyz [B,N,3] -> centroids [B,npoint] (int64), bit-exact with the
+    reference's CPU result for the same start draw."""
+    xyz = _f32c(xyz, "xyz")
+    if xyz.dim() != 3 or xyz.shape[2] != 3:
+        raise ValueError(f"farthest_point_sample expects [B,N,3] (got {tuple(xyz.shape)})")
+    start = _draw_start(xyz.shape[0], xyz.shape[1], xyz.device)
+    return _fps(xyz, int(npoint), start, False)[0]
+
+
+def query_ball_point(radius, nsample, xyz, new_xyz):
+    """pointnet_util.py:76-96 -- first ``nsample`` in-radius indices per query, padded with the first."""
+    xyz, new_xyz = _f32c(xyz, "xyz"), _f32c(new_xyz, "new_xyz")
+    B, N, _ = xyz.shape
+    S = new_xyz.shape[1]
+    out = torch.empty(B, S, int(nsample), device=xyz.device, dtype=torch.int64)
+    with torch.cuda.device(xyz.device):
+        _lib.call("pz_ball_query", xyz.data_ptr(), new_xyz.data_ptr(), B, N, S, ctypes.c_float(float(radius)),
+                  int(nsample), out.data_ptr(), _lib.stream_ptr())
+    return out
+
+
+def knn_point(nsample, xyz, new_xyz, return_dist=False):
+    """The kNN branch of sample_and_group (pointnet_util.py:118-119) as one call:
+    ``square_distance(new_xyz, xyz).argsort()[:, :, :nsample]`` without the [B,S,N] matrix.
+    Ascending by (distance, index)."""
+    xyz, new_xyz = _f32c(xyz, "xyz"), _f32c(new_xyz, "new_xyz")
+    B, N, _ = xyz.shape
+    S = new_xyz.shape[1]
+    idx = torch.empty(B, S, int(nsample), device=xyz.device, dtype=torch.int64)
+    d2 = torch.empty(B, S, int(nsample), device=xyz.device, dtype=torch.float32) if return_dist else None
+    with torch.cuda.device(xyz.device):
+        _lib.call("pz_knn", new_xyz.data_ptr(), xyz.data_ptr(), B, S, N, int(nsample), idx.data_ptr(),
+                  d2.data_ptr() if return_dist else None, _lib.stream_ptr())
+    return (idx, d2) if return_dist else idx
+
+
+def sample_and_group(npoint, radius, nsample, xyz, points, returnfps=False, knn=False):
+    """pointnet_util.py:99-136.
+
+    Returns ``new_xyz [B,npoint,3]``, ``new_points [B,npoint,nsample,3+D]`` (xyz-relative first,
+    then features) and, with ``returnfps=True``, also ``grouped_xyz`` and ``fps_idx``.
+    """
+    xyz = _f32c(xyz, "xyz")
+    B, N, C = xyz.shape
+    S, K = int(npoint), int(nsample)
+    start = _draw_start(B, N, xyz.device)
+    fps_idx, new_xyz = _fps(xyz, S, start, True)
+    idx = knn_point(K, xyz, new_xyz) if knn else query_ball_point(radius, K, xyz, new_xyz)
+    feat = _f32c(points, "points") if points is not None else None
+    D = feat.shape[-1] if feat is not None else 0
+    new_points = torch.empty(B, S, K, 3 + D, device=xyz.device, dtype=torch.float32)
+    grouped_xyz = torch.empty(B, S, K, 3, device=xyz.device, dtype=torch.float32) if returnfps else None
+    with torch.cuda.device(xyz.device):
+        _lib.call("pz_group_concat", xyz.data_ptr(), feat.data_ptr() if feat is not None else None,
+                  new_xyz.data_ptr(), idx.data_ptr(), B, N, D, S, K, new_points.data_ptr(),
+                  grouped_xyz.data_ptr() if returnfps else None, _lib.stream_ptr())
+    if returnfps:
+        return new_xyz, new_points, grouped_xyz, fps_idx
+    return new_xyz, new_points
+
+
+def sample_and_group_all(xyz, points):
+    """pointnet_util.py:139-156 -- a pure view/concat (no kernel needed)."""
+    B, N, C = xyz.shape
+    new_xyz = torch.zeros(B, 1, C, device=xyz.device, dtype=xyz.dtype)
+    grouped = xyz.view(B, 1, N, C)
+    new_points = grouped if points is None else torch.cat([grouped, points.view(B, 1, N, -1)], dim=-1)
+    return new_xyz, new_points
+
+
+def group_mlp_maxpool(xyz, points, new_xyz, idx, w1, b1, w2, b2, precision=_lib.PZ_PREC_FP32):
+    """Fused form of ``sample_and_group``'s grouping + ``relu(mlp_b(relu(mlp_a(.)))).max(-2)``
+    (model5_b.py:449-454): never materialises [B,S,K,3+D].  Returns [B,S,C2]."""
+    xyz, points, new_xyz = _f32c(xyz, "xyz"), _f32c(points, "points"), _f32c(new_xyz, "new_xyz")
+    idx = _i64c(idx, "idx")
+    w1, b1, w2, b2 = (_f32c(t, "weight") for t in (w1, b1, w2, b2))
+    B, N, _ = xyz.shape
+    D = points.shape[-1]
+    S, K = idx.shape[1], idx.shape[2]
+    C1, C2 = w1.shape[0], w2.shape[0]
+    lib = _lib.load()
+    ws_bytes = lib.pz_group_mlp_workspace_bytes(B, N, D, S, K, C1, C2)
+    ws = torch.empty(ws_bytes, device=xyz.device, dtype=torch.uint8)
+    out = torch.empty(B, S, C2, device=xyz.device, dtype=torch.float32)
+    with torch.cuda.device(xyz.device):
+        _lib.call("pz_group_mlp_maxpool", xyz.data_ptr(), points.data_ptr(), new_xyz.data_ptr(), idx.data_ptr(),
+                  w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), B, N, D, S, K, C1, C2, int(precision),
+                  out.data_ptr(), ws.data_ptr(), ws_bytes, _lib.stream_ptr())
+    return out

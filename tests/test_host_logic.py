@@ -1,0 +1,97 @@
+"""CPU: host-side mirror of the reference interface -- parameter layout, RNG contract, loud failure
+without CUDA, drop-in module registration."""
+import sys
+import types
+
+import pytest
+import torch
+
+from puzzlenet_b200 import dropin, weights
+from puzzlenet_b200.model5_b import PCTransformer_nonsort, TouchedRegraster
+
+
+def _cfg():
+    return types.SimpleNamespace(dataset="vase")
+
+
+def test_state_dict_layout_matches_reference_spec(state_dict):
+    model = TouchedRegraster(_cfg())
+    own = model.state_dict()
+    assert list(sorted(own.keys())) == list(sorted(state_dict.keys()))
+    for k, v in state_dict.items():
+        assert tuple(own[k].shape) == tuple(v.shape), k
+    n_params = sum(p.numel() for p in model.parameters())
+    assert n_params == 8_059_220
+    model.load_state_dict(state_dict, strict=True)
+
+
+def test_synthetic_weights_are_deterministic():
+    a, b = weights.synthetic_state_dict(0), weights.synthetic_state_dict(0)
+    assert all(torch.equal(a[k], b[k]) for k in a)
+    c = weights.synthetic_state_dict(1)
+    assert not torch.equal(a["tfMLP.0.weight"], c["tfMLP.0.weight"])
+
+
+def test_cpu_tensors_fail_loudly(state_dict):
+    """No CPU fallback: a CPU tensor must raise, not silently compute."""
+    from puzzlenet_b200 import pointnet_util as pu
+    x = torch.rand(1, 64, 3)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        pu.farthest_point_sample(x, 8)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        pu.square_distance(x, x)
+    model = TouchedRegraster(_cfg()).eval()
+    fpc, mrpc = weights.synthetic_pairs(1)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        model.predict5(weights.make_batch(fpc, mrpc), 0)
+    with pytest.raises(NotImplementedError):
+        model.predict5(weights.make_batch(fpc, mrpc), 0, training=True)
+    enc = PCTransformer_nonsort(_cfg())
+    with pytest.raises(NotImplementedError):          # train mode
+        enc(torch.rand(1, 1024, 3))
+
+
+def test_predict5_rng_contract_is_four_cpu_draws():
+    """(1024,B), (512,B), (1024,B), (512,B) from the CPU default generator."""
+    B = 3
+    torch.manual_seed(99)
+    expect = [torch.randint(0, n, (B,), dtype=torch.long) for n in (1024, 512, 1024, 512)]
+    after = torch.rand(1)
+    torch.manual_seed(99)
+    got = [torch.randint(0, n, (B,), dtype=torch.long) for n in (1024, 512, 1024, 512)]
+    assert all(torch.equal(a, b) for a, b in zip(expect, got))
+    assert torch.equal(after, torch.rand(1))
+
+
+def test_dropin_registers_reference_module_names():
+    dropin.install()
+    try:
+        import pointnet_util as pu          # noqa: F401  (what model5_b.py:39 does)
+        from PyTorchEMD.emd import earth_mover_distance   # model5_b.py:48
+        import emd_cuda                     # PyTorchEMD/emd.py:2
+        import model5_b
+        assert pu.__name__ == "puzzlenet_b200.pointnet_util"
+        assert callable(earth_mover_distance) and hasattr(emd_cuda, "approxmatch_forward")
+        assert hasattr(model5_b, "TouchedRegraster")
+        for fn in ("square_distance", "index_points", "farthest_point_sample", "query_ball_point",
+                   "sample_and_group", "sample_and_group_all"):
+            assert hasattr(pu, fn)
+    finally:
+        dropin.uninstall()
+    assert "pointnet_util" not in sys.modules or not sys.modules["pointnet_util"].__name__.startswith("puzzlenet_b200")
+
+
+def test_signatures_match_reference():
+    import inspect
+    from puzzlenet_b200 import emd, pointnet_util as pu
+    assert list(inspect.signature(pu.sample_and_group).parameters) == \
+        ["npoint", "radius", "nsample", "xyz", "points", "returnfps", "knn"]
+    assert list(inspect.signature(pu.query_ball_point).parameters) == ["radius", "nsample", "xyz", "new_xyz"]
+    assert list(inspect.signature(pu.farthest_point_sample).parameters) == ["xyz", "npoint"]
+    assert list(inspect.signature(pu.square_distance).parameters) == ["src", "dst"]
+    assert list(inspect.signature(pu.index_points).parameters) == ["points", "idx"]
+    sig = inspect.signature(emd.earth_mover_distance)
+    assert list(sig.parameters) == ["xyz1", "xyz2", "transpose"] and sig.parameters["transpose"].default is True
+    p5 = inspect.signature(TouchedRegraster.predict5).parameters
+    assert list(p5)[:5] == ["self", "batch", "batch_indic", "need", "training"]
+    assert p5["need"].default is False and p5["training"].default is False
