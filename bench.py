@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""bench.py -- pairs/sec of the PuzzleNet pair-matching forward (predict5) at B=64 pairs x 1024 points.
+
+One step = one pass of the hot path (`TouchedRegraster.predict5`, need=False, eval) over one batch of 64
+synthetic piece pairs per GPU (BASELINE.json configs[1]).  Prints ONE JSON line (rank 0).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--precision fp32|bf16]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+  python bench.py --impl reference ...     # the reference algorithm's CPU path (oracle port), same metric
+
+value : device-resident inputs, per-step CUDA events on the launching stream (L2 flushed between steps,
+        flush outside the events), max over ranks of the summed step time.
+e2e   : same metric through the public API from pinned HOST buffers: H2D of both clouds + FPS starts and
+        D2H of the twist + both boundary-logit tensors inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+B_PAIRS = 64          # pairs per GPU per step (train.py default batch, BASELINE configs[1])
+N_POINTS = 1024
+METRIC = "pairs/sec PuzzleNet fwd B=64 N=1024"
+UNIT = "pairs/s"
+
+# dense MACs of one pair forward as executed (SURVEY.md §8d counts 7.347 GFLOP/pair for the reference's
+# op sequence; layer 1 of each grouped MLP is applied per source point here, not per neighbour)
+FLOP_PER_PAIR_REFERENCE = 7.347e9
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        d = json.load(open(path))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        # "under load": the upper half of the samples (idle samples before/after the region drag the median)
+        sm.sort()
+        load = sm[len(sm) // 2:] if sm else []
+        return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU legs (oracle port): cpu_baseline and --impl reference
+# --------------------------------------------------------------------------------------------------
+def cpu_reference_pairs_per_s(pairs_per_step: int, steps: int, warmup: int):
+    """Times oracle.puzzle_oracle.predict5 (the reference's torch-CPU algorithm) with all host threads."""
+    import torch
+    from oracle import puzzle_oracle as po
+    from puzzlenet_b200.weights import synthetic_pairs, synthetic_state_dict
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = synthetic_state_dict(0)
+    fpc, mrpc = synthetic_pairs(pairs_per_step, seed=64)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            torch.manual_seed(1234 + i)
+            t0 = time.perf_counter()
+            po.predict5(sd, fpc, mrpc)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    total = sum(times)
+    return pairs_per_step * steps / total, total / steps, torch.get_num_threads()
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0                                    # the other ranks exit without work
+    pairs = 8                                       # bounded sample of the B=64 workload per step
+    value, sec_per_step, cores = cpu_reference_pairs_per_s(pairs, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec_per_step * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "predict5 fwd, B=64 pairs x 1024 pts (BASELINE configs[1])",
+                   "sample": f"{pairs} pairs per step on the host CPU"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} steps x {pairs} pairs, oracle.puzzle_oracle.predict5 (torch CPU fp32)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# --------------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------------
+def run_gpu_arm(args):
+    import types
+    import torch
+    import torch.distributed as dist
+    from puzzlenet_b200 import _lib
+    from puzzlenet_b200.model5_b import TouchedRegraster
+    from puzzlenet_b200.weights import make_batch, synthetic_pairs, synthetic_state_dict
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (puzzlenet_b200 has no CPU fallback; use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    model = TouchedRegraster(types.SimpleNamespace(dataset="vase"))
+    model.load_state_dict(synthetic_state_dict(0), strict=True)
+    model.to(dev).eval()
+    model.precision = args.precision
+    B = B_PAIRS
+    nsets = 4                                         # distinct synthetic batches, rotated
+    host = []
+    for i in range(nsets):
+        fpc, mrpc = synthetic_pairs(B, seed=64 + 1000 * rank + i)
+        g = torch.Generator().manual_seed(5 + i)
+        starts = torch.stack([torch.randint(0, n, (B,), generator=g) for n in (1024, 512, 1024, 512)])
+        host.append((fpc.pin_memory(), mrpc.pin_memory(), starts.pin_memory()))
+    resident = [(f.to(dev), m.to(dev), s.to(dev)) for f, m, s in host]
+    batches = [make_batch(f, m) for f, m, _ in resident]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident(i):
+        return model.predict5(batches[i % nsets], 0, starts=resident[i % nsets][2])
+
+    for i in range(args.warmup):
+        step_resident(i)
+    barrier()
+
+    # ---- value: device-resident inputs, per-step events, L2 flush between steps
+    sampler = ClockSampler(local) if rank == 0 else None
+    lib.pz_profile_enable(1)
+    launches0 = lib.pz_launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush.zero_()
+        ev[i][0].record()
+        step_resident(i)
+        ev[i][1].record()
+    barrier()
+    wall = time.perf_counter() - t_wall0
+    launches = lib.pz_launch_count() - launches0
+    calls, stages = _lib.profile_collect()
+    lib.pz_profile_enable(0)
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = sum(step_ms)
+
+    # ---- e2e: pinned host inputs -> H2D -> predict5 -> D2H of the results, every step
+    out_host = (torch.empty(B, 6).pin_memory(), torch.empty(B, 2, 1024).pin_memory(), torch.empty(B, 2, 1024).pin_memory())
+    h2d = sum(t.numel() * t.element_size() for t in host[0])
+    d2h = sum(t.numel() * t.element_size() for t in out_host)
+
+    def step_e2e(i):
+        f, m, s = host[i % nsets]
+        fd, md = f.to(dev, non_blocking=True), m.to(dev, non_blocking=True)
+        out, _, de_f, de_m = model.predict5(make_batch(fd, md), 0, starts=s)
+        out_host[0].copy_(out, non_blocking=True)
+        out_host[1].copy_(de_f, non_blocking=True)
+        out_host[2].copy_(de_m, non_blocking=True)
+
+    for i in range(max(3, args.warmup)):
+        step_e2e(i)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step_e2e(i)
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler else None
+
+    # ---- reduce over ranks: max time, total pairs
+    t = torch.tensor([total_ms, e2e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms = t.tolist()
+    pairs_total = B * args.steps * world
+    value = pairs_total / (total_ms / 1e3)
+    e2e_value = pairs_total / (e2e_ms / 1e3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant stage (live per-stage CUDA events from the timed steps)
+    peaks = _peaks()
+    agg = {}
+    for name, ms in stages:
+        agg[name] = agg.get(name, 0.0) + ms
+    per_step = {k: v / max(calls, 1) for k, v in agg.items()}
+    clouds = 2 * B
+    # algorithmic work of each stage per launch: flops or bytes
+    flop = {
+        "sg1_gather_layer2_maxpool": 2.0 * clouds * 512 * 32 * 128 * 128,
+        "sg2_gather_layer2_maxpool": 2.0 * clouds * 256 * 32 * 256 * 256,
+        "tail_linear_maxpool": 2.0 * clouds * 256 * 1280 * 1024,
+    }
+    top = max(per_step, key=per_step.get) if per_step else None
+    roofline = None
+    if top in flop:
+        launches_of_top = 1
+        achieved = flop[top] / (per_step[top] / 1e3) / 1e12
+        peak = peaks["tf_sust"]
+        roofline = {"bound": "tensor", "kernel": top, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                    "frac": achieved / peak, "traffic": None, "peak_source": f"{peaks['src']} bf16 sustained",
+                    "ms_per_launch": per_step[top] / launches_of_top,
+                    "note": "fp32 path runs this GEMM on CUDA cores (FFMA); shown against the tensor-pipe peak"
+                    if args.precision == "fp32" else "tcgen05 bf16 x bf16 -> fp32"}
+    elif top is not None:
+        # latency-bound geometry stages: report compulsory bytes against the HBM peak
+        byts = {"fps1": clouds * (12 * 1024 + 8 * 512), "fps2": clouds * (12 * 512 + 8 * 256),
+                "knn1": clouds * (12 * 1024 + 12 * 512 + 8 * 512 * 32), "knn2": clouds * (12 * 512 + 12 * 256 + 8 * 256 * 32)}
+        if top in byts:
+            achieved = byts[top] / (per_step[top] / 1e3) / 1e9
+            roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peaks["hbm"], "unit": "GB/s",
+                        "frac": achieved / peaks["hbm"], "traffic": None, "peak_source": f"{peaks['src']} copy"}
+
+    # ---- CPU baseline: oracle port on a bounded sample (rank 0, N=1 only)
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        v, sec, cores = cpu_reference_pairs_per_s(8, 3, 1)
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": "3 steps x 8 pairs of the same workload, oracle.puzzle_oracle.predict5 (torch CPU fp32), "
+                                  f"{sec:.2f} s/step"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
+        "config": {"workload": "predict5 fwd (need=False, eval), B=64 pairs x 1024 pts per GPU (BASELINE configs[1])",
+                   "pairs_per_gpu": B, "points": N_POINTS, "precision": args.precision, "parallelism": f"dp{world} (pairs sharded, no forward collective)",
+                   "l2": "256 MiB flush written between steps, outside the per-step CUDA events; 4 rotating batches",
+                   "weights": "synthetic_state_dict(0) (no checkpoint is shipped with the reference)"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+        "stages_ms_per_step": {k: round(v, 4) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])},
+        "gflop_per_pair_reference_count": FLOP_PER_PAIR_REFERENCE / 1e9,
+        "wall_s_timed_region": wall,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("PZ_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

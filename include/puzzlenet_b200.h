@@ -47,6 +47,16 @@ const char* pz_last_error(void);
 /* compute capability major*10+minor of the current device (100 on B200), <0 on error */
 int pz_device_arch(void);
 
+/* Instrumentation used by bench.py (the only process-global state besides the error string).
+ * pz_launch_count: kernels launched by this library in this process so far.
+ * pz_profile_enable(1): record CUDA events on the caller's stream between the stages of every following
+ * pz_predict5 / pz_encoder_forward call (at most 512 calls are kept); pz_profile_collect synchronises the
+ * device, sums the elapsed milliseconds per stage over those calls into ms[0..n), stores the stage names
+ * (static strings) and the number of profiled calls, resets the recorder and returns n. */
+long long pz_launch_count(void);
+int pz_profile_enable(int on);
+int pz_profile_collect(double* ms_host, const char** names_host, int* calls_host, int max_stages);
+
 /* ---------------------------------------------------------------- geometry */
 
 /* farthest_point_sample(xyz, npoint) -- pointnet_util.py:53-73.

@@ -44,6 +44,9 @@ SIGNATURES = {
     "pz_abi_version": (C.c_int, []),
     "pz_last_error": (C.c_char_p, []),
     "pz_device_arch": (C.c_int, []),
+    "pz_launch_count": (C.c_longlong, []),
+    "pz_profile_enable": (C.c_int, [C.c_int]),
+    "pz_profile_collect": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_char_p), C.POINTER(C.c_int), C.c_int]),
     "pz_fps": (C.c_int, [c_f32p, C.c_int, C.c_int, c_i64p, C.c_int, c_i64p, c_f32p, c_stream]),
     "pz_sqdist": (C.c_int, [c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, c_f32p, c_stream]),
     "pz_knn": (C.c_int, [c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_int, c_i64p, c_f32p, c_stream]),
@@ -129,3 +132,14 @@ def require_cuda(*tensors) -> None:
         if t is not None and not t.is_cuda:
             raise RuntimeError("puzzlenet_b200 only runs on CUDA tensors (no CPU fallback); got a "
                                f"{t.device} tensor")
+
+
+def profile_collect(max_stages: int = 48):
+    """-> (calls, [(stage name, summed ms)]) for the calls recorded since pz_profile_enable(1)."""
+    ms = (C.c_double * max_stages)()
+    names = (C.c_char_p * max_stages)()
+    calls = C.c_int(0)
+    n = load().pz_profile_collect(ms, names, C.byref(calls), max_stages)
+    if n < 0:
+        check(n, "pz_profile_collect")
+    return calls.value, [(names[i].decode(), ms[i]) for i in range(n)]

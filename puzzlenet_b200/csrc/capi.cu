@@ -1,4 +1,8 @@
 // Library-wide pieces of the C ABI (include/puzzlenet_b200.h): version, error text, device probe.
+#include <atomic>
+#include <mutex>
+#include <vector>
+
 #include "pz_common.cuh"
 
 namespace pz {
@@ -16,7 +20,81 @@ int fail(int code, const char* fmt, ...) {
   return code;
 }
 
+// ---- launch counter -------------------------------------------------------------------
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+// ---- stage profiler: event sets, one per profiled call ----------------------------------
+constexpr int PROF_MAX_SETS = 512, PROF_MAX_MARKS = 48;
+struct ProfSet {
+  cudaEvent_t ev[PROF_MAX_MARKS + 1];
+  const char* name[PROF_MAX_MARKS + 1];
+  int n = 0;
+  bool created = false;
+};
+static bool g_prof_on = false;
+static std::vector<ProfSet>* g_sets = nullptr;
+static int g_cur = -1;
+static std::mutex g_prof_mu;
+
+void prof_begin(cudaStream_t st) {
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (!g_sets) g_sets = new std::vector<ProfSet>(PROF_MAX_SETS);
+  if (g_cur + 1 >= PROF_MAX_SETS) { g_cur = PROF_MAX_SETS; return; }
+  ProfSet& s = (*g_sets)[++g_cur];
+  if (!s.created) {
+    for (auto& e : s.ev) cudaEventCreate(&e);
+    s.created = true;
+  }
+  s.n = 0;
+  s.name[0] = "begin";
+  cudaEventRecord(s.ev[0], st);
+}
+void prof_mark(const char* stage, cudaStream_t st) {
+  if (!g_prof_on || !g_sets || g_cur < 0 || g_cur >= PROF_MAX_SETS) return;
+  ProfSet& s = (*g_sets)[g_cur];
+  if (s.n >= PROF_MAX_MARKS) return;
+  ++s.n;
+  s.name[s.n] = stage;
+  cudaEventRecord(s.ev[s.n], st);
+}
+
 }  // namespace pz
+
+extern "C" long long pz_launch_count(void) { return pz::g_launches.load(); }
+
+extern "C" int pz_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(pz::g_prof_mu);
+  pz::g_prof_on = on != 0;
+  pz::g_cur = -1;
+  return 0;
+}
+
+// Sums, over every profiled call since pz_profile_enable(1), the elapsed ms of each stage (stages are
+// keyed by position; names[i] receives a static string).  Synchronises the device.  Returns the stage count.
+extern "C" int pz_profile_collect(double* ms, const char** names, int* calls, int max_stages) {
+  std::lock_guard<std::mutex> lk(pz::g_prof_mu);
+  if (calls) *calls = 0;
+  if (!pz::g_sets || pz::g_cur < 0) return 0;
+  if (cudaDeviceSynchronize() != cudaSuccess) return pz::fail(-1000, "pz_profile_collect: device sync failed");
+  const int nsets = pz::g_cur < pz::PROF_MAX_SETS ? pz::g_cur + 1 : pz::PROF_MAX_SETS;
+  int nstage = 0;
+  for (int i = 0; i < max_stages; ++i) ms[i] = 0.0;
+  for (int c = 0; c < nsets; ++c) {
+    pz::ProfSet& s = (*pz::g_sets)[c];
+    for (int i = 1; i <= s.n && i <= max_stages; ++i) {
+      float t = 0.f;
+      cudaEventElapsedTime(&t, s.ev[i - 1], s.ev[i]);
+      ms[i - 1] += t;
+      if (names) names[i - 1] = s.name[i];
+    }
+    if (s.n > nstage) nstage = s.n;
+  }
+  if (calls) *calls = nsets;
+  pz::g_cur = -1;
+  return nstage < max_stages ? nstage : max_stages;
+}
 
 extern "C" int pz_abi_version(void) { return PZ_ABI_VERSION; }
 

@@ -295,6 +295,7 @@ extern "C" int pz_emd_approxmatch(const float* xyz1, const float* xyz2, int b, i
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   PZ_CUDA(cudaLaunchKernelEx(&cfg, emd_approxmatch_kernel, n, m, xyz1, xyz2, match, static_cast<float*>(workspace), cl));
+  count_launch();
   return 0;
 }
 
@@ -316,6 +317,7 @@ extern "C" int pz_emd_matchcost_grad(const float* grad_cost, const float* xyz1, 
   if (b == 0) return 0;
   PZ_REQUIRE(b <= 65535, PZ_ERR_UNSUPPORTED, "pz_emd_matchcost_grad: b > 65535");
   emd_grad1_kernel<<<dim3((n + 127) / 128, b), 128, 0, as_stream(stream)>>>(n, m, grad_cost, xyz1, xyz2, match, grad1);
+  PZ_LAUNCH_CHECK();
   emd_grad2_kernel<<<dim3((m + 7) / 8, b), 256, 0, as_stream(stream)>>>(n, m, grad_cost, xyz1, xyz2, match, grad2);
   PZ_LAUNCH_CHECK();
   return 0;

@@ -512,15 +512,19 @@ static int encoder_forward_impl(const PzEncoderWeights* w, int E, int B, const f
   // stem: Linear(3,64)+BN+ReLU, Linear(64,64)+BN+ReLU -> x_feature [C,1024,64]
   stem_kernel<<<C * NPTS / 128, 128, 0, st>>>(xyz, stem_of(wa), stem_of(wb), B, xfeat);
   PZ_LAUNCH_CHECK();
+  prof_mark("stem", st);
 
   // ---- stage 1: FPS 1024->512, kNN 32, grouped MLP 67->128->128, max over K
   PZ_TRY(launch_fps(xyz, C, NPTS, start1, S1, o.fps1, nullptr, s.nx1, st));
+  prof_mark("fps1", st);
   PZ_TRY(launch_knn(s.nx1, xyz, C, S1, NPTS, KNN, o.knn1, s.knn1r, nullptr, st));
+  prof_mark("knn1", st);
   {
     GemmF32 g;  // F1 = x_feature * mlp3.weight[:, 3:]^T   (bias + xyz part are added per neighbour)
     g.A = xfeat; g.lda = D0; g.W[0] = wa.mlp3_w + 3; g.W[1] = wb.mlp3_w + 3; g.ldw = 3 + D0;
     g.rows_per_wset = B * NPTS; g.Y = s.F1; g.ldy = C1A; g.M = C * NPTS; g.N = C1A; g.K = D0;
     PZ_TRY(launch_gemm_f32(g, st));
+    prof_mark("sg1_layer1", st);
   }
   {
     GemmF32 g;
@@ -530,15 +534,19 @@ static int encoder_forward_impl(const PzEncoderWeights* w, int E, int B, const f
     g.rows_per_wset = B * S1 * KNN; g.Y = f1f; g.ldy = C1B; g.M = C * S1 * KNN; g.N = C1B; g.K = C1A;
     g.relu = 1; g.group = 32;
     PZ_TRY(launch_gemm_f32(g, st));
+    prof_mark("sg1_gather_layer2_maxpool", st);
   }
   // ---- stage 2: FPS 512->256 on the stage-1 centroids, kNN 32, grouped MLP 131->256->256
   PZ_TRY(launch_fps(s.nx1, C, S1, start2, S2, o.fps2, nullptr, nx2, st));
+  prof_mark("fps2", st);
   PZ_TRY(launch_knn(nx2, s.nx1, C, S2, S1, KNN, o.knn2, s.knn2r, nullptr, st));
+  prof_mark("knn2", st);
   {
     GemmF32 g;
     g.A = f1f; g.lda = C1B; g.W[0] = wa.mlp5_w + 3; g.W[1] = wb.mlp5_w + 3; g.ldw = 3 + C1B;
     g.rows_per_wset = B * S1; g.Y = s.F2; g.ldy = C2A; g.M = C * S1; g.N = C2A; g.K = C1B;
     PZ_TRY(launch_gemm_f32(g, st));
+    prof_mark("sg2_layer1", st);
   }
   float* f2f_slot = att_cat + 4 * CATT;  // cat([att1..att4, f2f]) (model5_b.py:467,472): f2f is columns 1024..1279
   {
@@ -549,6 +557,7 @@ static int encoder_forward_impl(const PzEncoderWeights* w, int E, int B, const f
     g.rows_per_wset = B * S2 * KNN; g.Y = f2f_slot; g.ldy = 1280; g.M = C * S2 * KNN; g.N = C2B; g.K = C2A;
     g.relu = 1; g.group = 32;
     PZ_TRY(launch_gemm_f32(g, st));
+    prof_mark("sg2_gather_layer2_maxpool", st);
   }
   if (o.f2f)
     PZ_CUDA(cudaMemcpy2DAsync(o.f2f, CATT * sizeof(float), f2f_slot, 1280 * sizeof(float), CATT * sizeof(float),
@@ -567,13 +576,16 @@ static int encoder_forward_impl(const PzEncoderWeights* w, int E, int B, const f
     PZ_TRY(proj(wa.q_w[l], wb.q_w[l], wa.q_b[l], wb.q_b[l], 64, s.q));
     PZ_TRY(proj(wa.k_w[l], wb.k_w[l], wa.k_b[l], wb.k_b[l], 64, s.k));
     PZ_TRY(proj(wa.v_w[l], wb.v_w[l], wa.v_b[l], wb.v_b[l], CATT, s.v));
+    prof_mark("attn_qkv_proj", st);
     const int amode = o.attention ? (l == 0 ? 1 : (l == 3 ? 3 : 2)) : 0;
     PZ_TRY(launch_attention(s.q, 64, s.k, 64, s.v, CATT, C, LATT, 64, CATT, x, 1280, s.r, CATT, o.attention, amode, st));
+    prof_mark("attn_softmax_av", st);
     GemmF32 g;  // out = x + relu(W_o r + b_o)
     g.A = s.r; g.lda = CATT; g.W[0] = wa.o_w[l]; g.W[1] = wb.o_w[l]; g.bias[0] = wa.o_b[l]; g.bias[1] = wb.o_b[l];
     g.ldw = CATT; g.rows_per_wset = B * LATT; g.Y = att_cat + l * CATT; g.ldy = 1280; g.M = rows; g.N = CATT;
     g.K = CATT; g.relu = 1; g.R = x; g.ldr = 1280;
     PZ_TRY(launch_gemm_f32(g, st));
+    prof_mark("attn_out_proj", st);
   }
 
   // ---- tail: Linear(1280,1024) then max over the 256 points (model5_b.py:472-475)
@@ -585,13 +597,16 @@ static int encoder_forward_impl(const PzEncoderWeights* w, int E, int B, const f
     if (o.out) {
       g.Y = o.out; g.ldy = 1024;
       PZ_TRY(launch_gemm_f32(g, st));
+      prof_mark("tail_linear", st);
       rowblock_max_kernel<<<dim3(4, C), 256, 0, st>>>(o.out, 1024, LATT, 1024, C, C, 0, fg, 1024);
     } else {
       g.Y = s.tailp; g.ldy = 1024; g.group = 128;
       PZ_TRY(launch_gemm_f32(g, st));
+      prof_mark("tail_linear_maxpool", st);
       rowblock_max_kernel<<<dim3(4, C), 256, 0, st>>>(s.tailp, 1024, LATT / 128, 1024, C, C, 0, fg, 1024);
     }
     PZ_LAUNCH_CHECK();
+    prof_mark("tail_point_max", st);
     if (fglob_pair)  // [B, E*1024]: pair b = [f_global(cloud b), f_global(cloud B+b)]
       PZ_CUDA(cudaMemcpy2DAsync(fglob_pair, (size_t)E * 1024 * sizeof(float), fg, 1024 * sizeof(float),
                                 1024 * sizeof(float), B, cudaMemcpyDeviceToDevice, st));
@@ -619,6 +634,7 @@ extern "C" int pz_encoder_forward(const PzEncoderWeights* weights_host, int E, i
                                   const PzEncoderOutputs* outputs_host, void* workspace, size_t workspace_bytes,
                                   pz_stream_t stream) {
   PZ_REQUIRE(weights_host && xyz && start1 && start2 && outputs_host, PZ_ERR_ARG, "pz_encoder_forward: null pointer");
+  prof_begin(as_stream(stream));
   return encoder_forward_impl(weights_host, E, B, xyz, start1, start2, precision, *outputs_host, workspace,
                               workspace_bytes, nullptr, nullptr, as_stream(stream));
 }
@@ -676,6 +692,7 @@ extern "C" int pz_predict5(const PzEncoderWeights* enc_host, const PzHeadWeights
   predict_layout(B, arena, s);
   PZ_REQUIRE(workspace && arena.ok(), PZ_ERR_WORKSPACE, "pz_predict5: workspace %zu B < required %zu B",
              workspace_bytes, arena.used);
+  prof_begin(st);
   const size_t cloud_bytes = (size_t)B * NPTS * 3 * sizeof(float);
   PZ_CUDA(cudaMemcpyAsync(s.xyz, fpc, cloud_bytes, cudaMemcpyDeviceToDevice, st));
   PZ_CUDA(cudaMemcpyAsync(s.xyz + (size_t)B * NPTS * 3, mrpc, cloud_bytes, cudaMemcpyDeviceToDevice, st));
@@ -686,6 +703,7 @@ extern "C" int pz_predict5(const PzEncoderWeights* enc_host, const PzHeadWeights
   PZ_CUDA(cudaMemcpyAsync(s.st1 + B, starts + 2 * (size_t)B, sb, cudaMemcpyDeviceToDevice, st));
   PZ_CUDA(cudaMemcpyAsync(s.st2 + B, starts + 3 * (size_t)B, sb, cudaMemcpyDeviceToDevice, st));
 
+  prof_mark("stage_inputs", st);
   PzEncoderOutputs eo = {};
   float* x2_all = nullptr;
   float* attn_all = nullptr;
@@ -715,6 +733,7 @@ extern "C" int pz_predict5(const PzEncoderWeights* enc_host, const PzHeadWeights
   PZ_TRY(skinny_linear(s.h1, 512, h.tf_w[2], h.tf_b[2], B, 512, 512, 1, s.h0, 512, s.partial, s.partial_floats, st));
   PZ_TRY(skinny_linear(s.h0, 512, h.tf_w[3], h.tf_b[3], B, 256, 512, 1, s.h1, 256, s.partial, s.partial_floats, st));
   PZ_TRY(skinny_linear(s.h1, 256, h.tf_w[4], h.tf_b[4], B, 6, 256, 0, out6, 6, s.partial, s.partial_floats, st));
+  prof_mark("pose_mlp", st);
 
   // boundary heads (model5_b.py:738-754)
   const size_t hl_smem = (3 * 4160 + 64 * 128) * sizeof(float);
@@ -734,6 +753,7 @@ extern "C" int pz_predict5(const PzEncoderWeights* enc_host, const PzHeadWeights
   Mlp3W seg_r = {h.seg_rpc_w[0], h.seg_rpc_b[0], h.seg_rpc_w[1], h.seg_rpc_b[1], h.seg_rpc_w[2], h.seg_rpc_b[2]};
   head_seg_kernel<<<2 * B * NPTS / 128, 128, hs_smem, st>>>(s.local, seg_f, seg_r, s.gbias, B, de_fpcb, de_mrpcb);
   PZ_LAUNCH_CHECK();
+  prof_mark("boundary_heads", st);
   return 0;
 }
 

@@ -26,7 +26,12 @@ int fail(int code, const char* fmt, ...);
                         __FILE__, __LINE__);                                            \
   } while (0)
 
-#define PZ_LAUNCH_CHECK() PZ_CUDA(cudaGetLastError())
+// every kernel launch site is followed by exactly one PZ_LAUNCH_CHECK(): it also feeds pz_launch_count()
+#define PZ_LAUNCH_CHECK()            \
+  do {                               \
+    ::pz::count_launch();            \
+    PZ_CUDA(cudaGetLastError());     \
+  } while (0)
 
 // propagate a non-zero status from an internal call
 #define PZ_TRY(expr)         \
@@ -34,6 +39,11 @@ int fail(int code, const char* fmt, ...);
     int _s = (expr);         \
     if (_s != 0) return _s;  \
   } while (0)
+
+void count_launch();
+// opt-in stage profiler (pz_profile_*): CUDA events between the stages of pz_predict5 / pz_encoder_forward
+void prof_begin(cudaStream_t st);
+void prof_mark(const char* stage, cudaStream_t st);
 
 static inline cudaStream_t as_stream(pz_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 

@@ -1,0 +1,150 @@
+"""GPU parity: encoder blocks and the pair-matching forward vs the CPU oracle / frozen reference outputs.
+Tolerances are the ones north_star states: indices bit-exact; features and boundary logits within 1e-4
+relative (fp32 path; relative to the tensor's max magnitude); rotation within 0.01 deg and translation
+within 1e-4 of the reference."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import puzzle_oracle as po
+from puzzlenet_b200.weights import make_batch, synthetic_pairs
+from tests.golden_inputs import FPS_SEED, golden_inputs
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+REL_FP32 = 1e-4
+
+
+def rel_err(got, ref):
+    ref = torch.as_tensor(ref)
+    got = torch.as_tensor(got).cpu().to(ref.dtype)
+    return ((got - ref).abs().max() / ref.abs().max().clamp_min(1e-30)).item()
+
+
+def test_se3_exp(goldens):
+    from puzzlenet_b200 import se3
+    _, _, _, twist = golden_inputs()
+    got = se3.exp(twist.to(DEV))
+    np.testing.assert_allclose(got.cpu().numpy(), goldens["se3_exp"], rtol=0, atol=2e-6)
+
+
+def test_linear_and_attention_blocks(state_dict):
+    from puzzlenet_b200.model5_b import layerAttention, scaled_dot_production
+    g = torch.Generator().manual_seed(1)
+    q, k, v = torch.randn(3, 256, 64, generator=g), torch.randn(3, 256, 64, generator=g), torch.randn(3, 256, 256, generator=g)
+    vals, attn = scaled_dot_production(q.to(DEV), k.to(DEV), v.to(DEV))
+    rv, ra = po.scaled_dot_production(q, k, v)
+    assert rel_err(vals, rv) < REL_FP32 and rel_err(attn, ra) < REL_FP32
+    np.testing.assert_allclose(attn.sum(-1).cpu().numpy(), 1.0, atol=1e-5)
+    layer = layerAttention(None, 256)
+    sd = {kk[len("Encoder.atten3."):]: vv for kk, vv in state_dict.items() if kk.startswith("Encoder.atten3.")}
+    layer.load_state_dict(sd)
+    x = torch.randn(2, 256, 256, generator=g) * 0.5
+    out, a = layer.to(DEV)(x.to(DEV))
+    ro, ra = po.layer_attention(state_dict, "Encoder.atten3", x)
+    assert rel_err(out, ro) < REL_FP32 and rel_err(a, ra) < REL_FP32
+
+
+def test_group_mlp_maxpool_matches_materialised_path(state_dict):
+    """Fused gather+MLP+max-pool == sample_and_group(...) -> mlp3 -> relu -> mlp4 -> relu -> max (oracle)."""
+    from puzzlenet_b200 import pointnet_util as pu
+    g = torch.Generator().manual_seed(2)
+    xyz = torch.rand(2, 1024, 3, generator=g) - 0.5
+    feat = torch.randn(2, 1024, 64, generator=g)
+    torch.manual_seed(8)
+    nx, npts, _, _, idx = po.sample_and_group(128, 0, 32, xyz, feat, knn=True, return_idx=True)
+    ref = torch.relu(po._lin(state_dict, "Encoder.mlp4", torch.relu(po._lin(state_dict, "Encoder.mlp3", npts)))).max(-2).values
+    got = pu.group_mlp_maxpool(xyz.to(DEV), feat.to(DEV), nx.to(DEV), idx.to(DEV),
+                               state_dict["Encoder.mlp3.weight"].to(DEV), state_dict["Encoder.mlp3.bias"].to(DEV),
+                               state_dict["Encoder.mlp4.weight"].to(DEV), state_dict["Encoder.mlp4.bias"].to(DEV))
+    assert got.shape == ref.shape
+    assert rel_err(got, ref) < REL_FP32
+
+
+def test_encoder_intermediates(cuda_model, state_dict, goldens):
+    fpc, _ = synthetic_pairs(2, seed=64)
+    torch.manual_seed(FPS_SEED)
+    got = cuda_model.Encoder(fpc.to(DEV), return_intermediates=True)
+    torch.manual_seed(FPS_SEED)
+    ref = po.encoder_forward(state_dict, "Encoder", fpc)
+    # indices: bit-exact, against the oracle AND the frozen reference
+    for name in ("fps1", "knn1", "fps2", "knn2"):
+        assert torch.equal(got[name].cpu(), ref[name]), name
+        assert np.array_equal(got[name].cpu().numpy(), goldens["enc_" + name]), name
+    assert torch.equal(got["x2"].cpu(), ref["x2"])
+    errs = {n: rel_err(got[n], ref[n]) for n in ("x_feature", "f1f", "f2f", "attention", "out", "f_global")}
+    errs["att_cat"] = rel_err(got["att_cat"], torch.cat(ref["att"] + [ref["f2f"]], -1))
+    print("encoder rel errors:", errs)
+    assert max(errs.values()) < REL_FP32, errs
+    assert rel_err(got["f_global"], goldens["enc_f_global"]) < REL_FP32
+    assert rel_err(got["out"][:, ::32], goldens["enc_out_rows"]) < REL_FP32
+
+
+def test_encoder_api_tuple(cuda_model):
+    fpc, _ = synthetic_pairs(1, seed=3)
+    out = cuda_model.Encoder2(fpc.to(DEV))
+    assert [tuple(t.shape) for t in out] == [(1, 1024), (1, 256, 3), (1, 256, 256), (1, 256, 1024), (1, 1024, 64)]
+    with pytest.raises(ValueError):
+        cuda_model.Encoder(torch.zeros(1, 512, 3, device=DEV))
+
+
+def test_predict5_goldens(cuda_model, goldens):
+    """B=2 against the frozen outputs of the unmodified reference (need=True tuple)."""
+    fpc, mrpc = synthetic_pairs(2, seed=64)
+    torch.manual_seed(FPS_SEED)
+    r = cuda_model.predict5(make_batch(fpc.to(DEV), mrpc.to(DEV)), 0, need=True)
+    assert len(r) == 8 and r[1] == [0]
+    assert np.array_equal(r[2].cpu().numpy(), goldens["p5_x2_fpc"])
+    assert np.array_equal(r[4].cpu().numpy(), goldens["p5_x2_mrpc"])
+    errs = dict(out=rel_err(r[0], goldens["p5_out"]), de_fpcb=rel_err(r[6], goldens["p5_de_fpcb"]),
+                de_mrpcb=rel_err(r[7], goldens["p5_de_mrpcb"]),
+                attn_f=rel_err(r[3][:, ::16], goldens["p5_attn_fpc_rows"]),
+                attn_m=rel_err(r[5][:, ::16], goldens["p5_attn_mrpc_rows"]))
+    print("predict5 rel errors vs reference goldens:", errs)
+    assert max(errs.values()) < REL_FP32, errs
+    # pose: rotation within 0.01 deg, translation within 1e-4 of the reference
+    from puzzlenet_b200 import se3
+    g = se3.exp(r[0]).cpu()
+    gref = torch.from_numpy(goldens["p5_mat"])
+    assert po.rotation_error_deg(g[:, :3, :3], gref[:, :3, :3]).max().item() < 0.01
+    assert po.translation_error(g[:, :3, 3], gref[:, :3, 3]).max().item() < 1e-4
+
+
+@pytest.mark.parametrize("B", [1, 5])
+def test_predict5_vs_oracle(cuda_model, state_dict, B):
+    fpc, mrpc = synthetic_pairs(B, seed=100 + B)
+    torch.manual_seed(B)
+    out, out_again, de_f, de_m = cuda_model.predict5(make_batch(fpc.to(DEV), mrpc.to(DEV)), 0)
+    assert out_again is out and de_f.shape == (B, 2, 1024)
+    torch.manual_seed(B)
+    ref = po.predict5(state_dict, fpc, mrpc)
+    errs = dict(out=rel_err(out, ref["out"]), de_f=rel_err(de_f, ref["de_fpcb"]), de_m=rel_err(de_m, ref["de_mrpcb"]))
+    print(f"B={B} rel errors:", errs)
+    assert max(errs.values()) < REL_FP32, errs
+
+
+def test_predict5_2d_input_and_forward_alias(cuda_model, state_dict):
+    fpc, mrpc = synthetic_pairs(1, seed=9)
+    batch = [fpc[0].to(DEV), mrpc[0].to(DEV)] + make_batch(fpc, mrpc)[2:]
+    torch.manual_seed(4)
+    out = cuda_model.forward(batch, 0)[0]                    # forward -> predict5; 2-D clouds get a batch dim
+    torch.manual_seed(4)
+    ref = po.predict5(state_dict, fpc[0], mrpc[0])
+    assert out.shape == (1, 6) and rel_err(out, ref["out"]) < REL_FP32
+
+
+def test_predict5_full_batch_properties(cuda_model):
+    """BASELINE config 2 size (B=64): permutation equivariance over pairs and determinism -- properties
+    that hold at any size, where the CPU oracle would take ~20 s."""
+    B = 64
+    fpc, mrpc = synthetic_pairs(B, seed=64)
+    starts = torch.stack([torch.randint(0, n, (B,), generator=torch.Generator().manual_seed(i))
+                          for i, n in enumerate((1024, 512, 1024, 512))])
+    fpc, mrpc = fpc.to(DEV), mrpc.to(DEV)
+    a = cuda_model.predict5(make_batch(fpc, mrpc), 0, starts=starts)
+    b = cuda_model.predict5(make_batch(fpc, mrpc), 0, starts=starts)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[2], b[2])                  # run-to-run deterministic
+    perm = torch.randperm(B, generator=torch.Generator().manual_seed(1))
+    c = cuda_model.predict5(make_batch(fpc[perm.to(DEV)], mrpc[perm.to(DEV)]), 0, starts=starts[:, perm])
+    assert torch.equal(c[0], a[0][perm.to(DEV)]) and torch.equal(c[3], a[3][perm.to(DEV)])
+    assert torch.isfinite(a[0]).all() and torch.isfinite(a[2]).all()
