@@ -345,25 +345,25 @@ using namespace pz;
 
 extern "C" int pz_fps(const float* xyz, int B, int N, const int64_t* start, int S, int64_t* out_idx,
                       float* new_xyz_or_null, pz_stream_t stream) {
-  PZ_REQUIRE(xyz && start && out_idx, PZ_ERR_ARG, "pz_fps: null pointer");
   PZ_REQUIRE(B >= 0 && N >= 1 && S >= 1, PZ_ERR_ARG, "pz_fps: bad sizes B=%d N=%d S=%d", B, N, S);
   if (B == 0) return 0;
+  PZ_REQUIRE(xyz && start && out_idx, PZ_ERR_ARG, "pz_fps: null pointer");
   return launch_fps(xyz, B, N, start, S, out_idx, nullptr, new_xyz_or_null, as_stream(stream));
 }
 
 extern "C" int pz_knn(const float* query, const float* xyz, int B, int S, int N, int K,
                       int64_t* out_idx, float* out_d2_or_null, pz_stream_t stream) {
-  PZ_REQUIRE(query && xyz && out_idx, PZ_ERR_ARG, "pz_knn: null pointer");
   PZ_REQUIRE(B >= 0 && S >= 0 && N >= 1, PZ_ERR_ARG, "pz_knn: bad sizes B=%d S=%d N=%d", B, S, N);
   if (B == 0 || S == 0) return 0;
+  PZ_REQUIRE(query && xyz && out_idx, PZ_ERR_ARG, "pz_knn: null pointer");
   return launch_knn(query, xyz, B, S, N, K, out_idx, nullptr, out_d2_or_null, as_stream(stream));
 }
 
 extern "C" int pz_sqdist(const float* src, const float* dst, int B, int S, int N, float* out,
                          pz_stream_t stream) {
-  PZ_REQUIRE(src && dst && out, PZ_ERR_ARG, "pz_sqdist: null pointer");
   PZ_REQUIRE(B >= 0 && S >= 0 && N >= 0, PZ_ERR_ARG, "pz_sqdist: bad sizes");
   if (B == 0 || S == 0 || N == 0) return 0;
+  PZ_REQUIRE(src && dst && out, PZ_ERR_ARG, "pz_sqdist: null pointer");
   PZ_REQUIRE(B <= 65535 && (S + 7) / 8 <= 65535, PZ_ERR_UNSUPPORTED, "pz_sqdist: grid too large");
   int gx = (N + 127) / 128;
   if (gx > 64) gx = 64;
@@ -375,9 +375,9 @@ extern "C" int pz_sqdist(const float* src, const float* dst, int B, int S, int N
 
 extern "C" int pz_ball_query(const float* xyz, const float* new_xyz, int B, int N, int S,
                              float radius, int nsample, int64_t* out_idx, pz_stream_t stream) {
-  PZ_REQUIRE(xyz && new_xyz && out_idx, PZ_ERR_ARG, "pz_ball_query: null pointer");
   PZ_REQUIRE(B >= 0 && N >= 1 && S >= 0 && nsample >= 1, PZ_ERR_ARG, "pz_ball_query: bad sizes");
   if (B == 0 || S == 0) return 0;
+  PZ_REQUIRE(xyz && new_xyz && out_idx, PZ_ERR_ARG, "pz_ball_query: null pointer");
   PZ_REQUIRE(B <= 65535, PZ_ERR_UNSUPPORTED, "pz_ball_query: B > 65535");
   dim3 grid((S + 127) / 128, B);
   ball_query_kernel<<<grid, 128, 0, as_stream(stream)>>>(xyz, new_xyz, N, S, radius * radius, nsample, out_idx);
@@ -387,9 +387,9 @@ extern "C" int pz_ball_query(const float* xyz, const float* new_xyz, int B, int 
 
 extern "C" int pz_gather(const void* pts, const int64_t* idx, int B, int N, int C, int M,
                          int elem_bytes, void* out, pz_stream_t stream) {
-  PZ_REQUIRE(pts && idx && out, PZ_ERR_ARG, "pz_gather: null pointer");
   PZ_REQUIRE(B >= 0 && N >= 1 && C >= 1 && M >= 0 && elem_bytes >= 1, PZ_ERR_ARG, "pz_gather: bad sizes");
   if (B == 0 || M == 0) return 0;
+  PZ_REQUIRE(pts && idx && out, PZ_ERR_ARG, "pz_gather: null pointer");
   size_t row_bytes = (size_t)C * elem_bytes;
   bool words = (row_bytes % 4 == 0) && ((uintptr_t)pts % 4 == 0) && ((uintptr_t)out % 4 == 0);
   size_t unit = words ? 4 : 1;
@@ -407,11 +407,11 @@ extern "C" int pz_gather(const void* pts, const int64_t* idx, int B, int N, int 
 extern "C" int pz_group_concat(const float* xyz, const float* feat_or_null, const float* new_xyz,
                                const int64_t* knn_idx, int B, int N, int D, int S, int K,
                                float* new_points, float* grouped_xyz_or_null, pz_stream_t stream) {
-  PZ_REQUIRE(xyz && new_xyz && knn_idx && new_points, PZ_ERR_ARG, "pz_group_concat: null pointer");
-  PZ_REQUIRE(feat_or_null || D == 0, PZ_ERR_ARG, "pz_group_concat: feat is null but D=%d", D);
   PZ_REQUIRE(B >= 0 && N >= 1 && D >= 0 && S >= 0 && K >= 1, PZ_ERR_ARG, "pz_group_concat: bad sizes");
   size_t rows = (size_t)B * S * K;
   if (rows == 0) return 0;
+  PZ_REQUIRE(xyz && new_xyz && knn_idx && new_points, PZ_ERR_ARG, "pz_group_concat: null pointer");
+  PZ_REQUIRE(feat_or_null || D == 0, PZ_ERR_ARG, "pz_group_concat: feat is null but D=%d", D);
   size_t want = (rows + 7) / 8;
   int blocks = (int)(want < (size_t)kNumSMs * 16 ? want : (size_t)kNumSMs * 16);
   group_concat_kernel<<<blocks, 256, 0, as_stream(stream)>>>(xyz, feat_or_null, new_xyz, knn_idx, N, D, S, K, rows, new_points, grouped_xyz_or_null);

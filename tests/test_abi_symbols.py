@@ -47,6 +47,7 @@ def test_argument_errors_without_gpu():
     assert lib.pz_fps(None, 1, 16, None, 4, None, None, None) == -1
     assert b"null" in lib.pz_last_error()
     assert lib.pz_knn(None, None, 1, 1, 1, 1, None, None, None) == -1
+    assert lib.pz_knn(None, None, 0, 0, 1, 1, None, None, None) == 0          # empty input is a no-op
     assert lib.pz_predict5_workspace_bytes(64) > 0
     assert lib.pz_encoder_workspace_bytes(2, 64) > lib.pz_encoder_workspace_bytes(1, 64)
     with pytest.raises((RuntimeError, ValueError)):
