@@ -119,6 +119,13 @@ int pz_linear(const float* x, int ldx, const float* W, const float* b, int M, in
               const float* residual_or_null, int ldr, float* y, int ldy, int precision,
               pz_stream_t stream);
 
+/* The same layer on the tcgen05 tensor cores with operands the caller already holds in bf16:
+ * x_bf16 [M,K] (row stride ldx, elements), w_bf16 [N,K]; fp32 accumulate, fp32 bias/residual/output.
+ * Supported: M % 256 == 0, N % 128 == 0, K % 64 == 0, 16-byte aligned rows. */
+int pz_linear_bf16(const void* x_bf16, int ldx, const void* w_bf16, const float* b, int M, int N, int K,
+                   int relu, const float* residual_or_null, int ldr, float* y, int ldy,
+                   pz_stream_t stream);
+
 /* layerAttention.forward -- model5_b.py:92-101.  x [B,L,C] -> out [B,L,C] = x + relu(Wo (x - A v) + bo),
  * attention_or_null [B,L,L].  Wq,Wk [C/4,C]; Wv,Wo [C,C].  Supported: C == 256, L as pz_scaled_dot_attention.
  * workspace: pz_offset_attention_workspace_bytes(B,L,C). */

@@ -59,6 +59,8 @@ SIGNATURES = {
                              + [C.c_int] * 8 + [c_f32p, C.c_void_p, C.c_size_t, c_stream]),
     "pz_linear": (C.c_int, [c_f32p, C.c_int, c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_int, c_f32p, C.c_int, c_f32p,
                             C.c_int, C.c_int, c_stream]),
+    "pz_linear_bf16": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_int, c_f32p,
+                                 C.c_int, c_f32p, C.c_int, c_stream]),
     "pz_offset_attention_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "pz_offset_attention": (C.c_int, [c_f32p] * 9 + [C.c_int] * 4 + [c_f32p, c_f32p, C.c_void_p, C.c_size_t, c_stream]),
     "pz_scaled_dot_attention": (C.c_int, [c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_int, c_f32p, c_f32p,

@@ -1,0 +1,435 @@
+// tcgen05 (5th-gen tensor core) GEMM family for the bf16 path (PZ_PREC_BF16), sm_100a only.
+//
+//   D^T[ch, row] = sum_k W[ch,k] * X[row,k]          (bf16 x bf16 -> fp32 in TMEM)
+//
+// The product is computed TRANSPOSED: output channels are the UMMA M dimension (TMEM lanes, one
+// per epilogue thread) and activation rows are the UMMA N dimension (TMEM columns).  Both operands
+// are K-major in shared memory, which is the natural layout of nn.Linear weights [out,in] and of
+// activations [rows,in].  With rows along TMEM columns, the max-pools of the model become purely
+// in-thread reductions over consecutive columns:
+//   * neighbourhood max-pool over the K=32 rows of a group (model5_b.py:454, :461)
+//   * point max-pool over the 256 rows of a cloud            (model5_b.py:475)
+// and a plain store writes 32 consecutive channels per warp instruction (coalesced).
+//
+// Warp roles (13 warps, 1 CTA/SM, persistent over tiles):
+//   warps 0-3  epilogue: tcgen05.ld accumulator -> bias/ReLU/residual/max -> global
+//   warp  4    TMEM allocation + the single MMA-issuing thread
+//   warps 5-12 producers: fill the K-major SWIZZLE_128B operand stages, either with cp.async copies
+//              (plain activations / streamed weights) or by *computing* the operand on the fly:
+//              grouped-MLP layer 2 gathers  relu(P[rows[r]] - Q[r/32])  (pointnet_util.py:123-130 +
+//              model5_b.py:452) so the [B,S,K,3+D] tensor and its layer-1 activations never exist.
+// Pipelines: smem stages (full/empty mbarriers, tcgen05.commit frees a stage) and a double-buffered
+// TMEM accumulator (accum_full/accum_empty) so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include <cuda_bf16.h>
+
+#include "pz_common.cuh"
+
+namespace pz {
+
+namespace tc {
+
+constexpr int EPI_WARPS = 4, PROD_WARPS = 8;
+constexpr int THREADS = (EPI_WARPS + 1 + PROD_WARPS) * 32;  // 416
+constexpr int PROD_THREADS = PROD_WARPS * 32;
+constexpr int KB = 64;                  // bf16 elements per k-block = one 128-byte swizzle row
+constexpr int TMEM_COLS = 512;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  for (uint32_t spin = 0; !ok; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!ok && spin > (1u << 24)) __trap();
+  }
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (sm_100 format): rows are 128 bytes, 8-row
+// atoms of 1024 bytes, stride-byte-offset = 1024, version 1, layout type 2.
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);       // start address, bits [0,14)
+  d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset, bits [32,46)
+  d |= (uint64_t)1 << 46;                            // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
+  return d;
+}
+// instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=n
+__host__ __device__ constexpr uint32_t make_idesc(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// byte offset of 16-byte chunk c (0..7) of row r inside a [rows x 128 B] SWIZZLE_128B tile
+__device__ __forceinline__ uint32_t sw128(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
+
+}  // namespace tc
+
+using namespace tc;
+
+// ROWS: activation rows per tile (UMMA N).  NCHB: 128-channel blocks per tile (accumulators).
+// RESIDENT: all of W for the tile's NCHB blocks stays in smem (K*NCHB*256 bytes).  GATHER: computed B.
+template <int ROWS, int NCHB, bool RESIDENT, bool GATHER, int NST>
+__global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcGemm g) {
+  extern __shared__ __align__(1024) uint8_t tc_smem_raw[];
+  // carve: [resident W][stages][barriers]
+  const uint32_t smem_base = (smem_u32(tc_smem_raw) + 1023u) & ~1023u;
+  const int kblocks = g.K / KB;
+  const uint32_t w_block_bytes = 128 * 128;                     // one [128 ch x 64 k] block
+  const uint32_t resident_bytes = RESIDENT ? (uint32_t)(NCHB * kblocks) * w_block_bytes : 0u;
+  constexpr uint32_t STAGE_W_BYTES = RESIDENT ? 0u : (uint32_t)NCHB * 128u * 128u;
+  constexpr uint32_t STAGE_X_BYTES = (uint32_t)ROWS * 128u;
+  constexpr uint32_t STAGE_BYTES = STAGE_W_BYTES + STAGE_X_BYTES;
+  const uint32_t stages_base = smem_base + resident_bytes;
+  const uint32_t bars_base = stages_base + NST * STAGE_BYTES;   // 8-byte aligned (multiple of 1024)
+  const uint32_t full_bar = bars_base, empty_bar = bars_base + 8 * NST;
+  const uint32_t accf_bar = bars_base + 16 * NST, acce_bar = accf_bar + 16;
+  const uint32_t tmem_slot = acce_bar + 16;
+  uint8_t* smem_gen = tc_smem_raw + (smem_base - smem_u32(tc_smem_raw));   // generic pointer to smem_base
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  // ---- tile partition: CTAs are split between the weight sets so a CTA never switches weights
+  const int nsets = (g.rows_per_wset > 0 && g.M > g.rows_per_wset) ? 2 : 1;
+  const int row_tiles = g.M / ROWS;
+  const int ch_tiles = g.Nout / (128 * NCHB);
+  const int tiles_per_set = (row_tiles / nsets) * ch_tiles;
+  const int ctas_per_set = gridDim.x / nsets;
+  const int wset = min((int)blockIdx.x / ctas_per_set, nsets - 1);
+  const int rank_in_set = blockIdx.x - wset * ctas_per_set;
+  const int step = (wset == nsets - 1) ? (int)gridDim.x - wset * ctas_per_set : ctas_per_set;
+  const int tile_begin = wset * tiles_per_set;
+  const __nv_bfloat16* __restrict__ W = g.W[wset];
+  const float* __restrict__ bias = g.bias[wset];
+
+  if (tid == 0) {
+    for (int s = 0; s < NST; ++s) {
+      mbar_init(full_bar + 8 * s, PROD_THREADS);
+      mbar_init(empty_bar + 8 * s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(accf_bar + 8 * b, 1);
+      mbar_init(acce_bar + 8 * b, EPI_WARPS * 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == EPI_WARPS) {  // TMEM allocation by one full warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (RESIDENT) {  // whole weight matrix of this set -> swizzled smem, once
+    const int chunks = NCHB * kblocks * 128 * 8;  // 16-byte chunks
+    for (int id = tid; id < chunks; id += THREADS) {
+      const int c = id & 7, r = (id >> 3) & 127, blk = id >> 10;  // blk = chb * kblocks + kb
+      const int chb = blk / kblocks, kb = blk - chb * kblocks;
+      const uint4 v = *reinterpret_cast<const uint4*>(W + (size_t)(chb * 128 + r) * g.ldw + kb * KB + c * 8);
+      *reinterpret_cast<uint4*>(smem_gen + (size_t)blk * w_block_bytes + sw128(r, c)) = v;
+    }
+    fence_proxy_async();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+
+  if (warp >= EPI_WARPS + 1) {
+    // =========================================================== producers
+    const int pt = tid - (EPI_WARPS + 1) * 32;
+    uint32_t issued = 0, arrived = 0;
+    for (int t = tile_begin + rank_in_set; t < tile_begin + tiles_per_set; t += step) {
+      const int cht = t % ch_tiles, rt = t / ch_tiles;
+      const int row0 = rt * ROWS;
+      for (int kb = 0; kb < kblocks; ++kb) {
+        const uint32_t s = issued % NST, ph = (issued / NST) & 1;
+        mbar_wait(empty_bar + 8 * s, ph ^ 1);
+        const uint32_t st_addr = stages_base + s * STAGE_BYTES;
+        uint8_t* st_gen = smem_gen + (st_addr - smem_base);
+        if (GATHER) {
+          // X[r, k] = relu(P[rows[r], k] - Q[(row0+r)/32, k])  -> bf16, swizzled
+          for (int id = pt; id < ROWS * 8; id += PROD_THREADS) {
+            const int c = id & 7, r = id >> 3;
+            const int src = g.rows[row0 + r];
+            const uint4 pv = *reinterpret_cast<const uint4*>(g.X + (size_t)src * g.ldx + kb * KB + c * 8);
+            const float4* qp = reinterpret_cast<const float4*>(g.Q + (size_t)((row0 + r) >> 5) * g.K + kb * KB + c * 8);
+            const float4 q0 = qp[0], q1 = qp[1];
+            const __nv_bfloat162* p2 = reinterpret_cast<const __nv_bfloat162*>(&pv);
+            const float2 a = __bfloat1622float2(p2[0]), b = __bfloat1622float2(p2[1]);
+            const float2 cc = __bfloat1622float2(p2[2]), d = __bfloat1622float2(p2[3]);
+            uint4 o;
+            __nv_bfloat162 t0 = __floats2bfloat162_rn(fmaxf(a.x - q0.x, 0.f), fmaxf(a.y - q0.y, 0.f));
+            __nv_bfloat162 t1 = __floats2bfloat162_rn(fmaxf(b.x - q0.z, 0.f), fmaxf(b.y - q0.w, 0.f));
+            __nv_bfloat162 t2 = __floats2bfloat162_rn(fmaxf(cc.x - q1.x, 0.f), fmaxf(cc.y - q1.y, 0.f));
+            __nv_bfloat162 t3 = __floats2bfloat162_rn(fmaxf(d.x - q1.z, 0.f), fmaxf(d.y - q1.w, 0.f));
+            o.x = *reinterpret_cast<uint32_t*>(&t0); o.y = *reinterpret_cast<uint32_t*>(&t1);
+            o.z = *reinterpret_cast<uint32_t*>(&t2); o.w = *reinterpret_cast<uint32_t*>(&t3);
+            *reinterpret_cast<uint4*>(st_gen + STAGE_W_BYTES + sw128(r, c)) = o;
+          }
+          fence_proxy_async();
+          mbar_arrive(full_bar + 8 * s);
+          ++issued;
+          ++arrived;
+        } else {
+          if (!RESIDENT) {
+            for (int id = pt; id < NCHB * 128 * 8; id += PROD_THREADS) {
+              const int c = id & 7, r = (id >> 3) & 127, chb = id >> 10;
+              cp_async16(st_addr + chb * w_block_bytes + sw128(r, c),
+                         W + (size_t)((cht * NCHB + chb) * 128 + r) * g.ldw + kb * KB + c * 8);
+            }
+          }
+          for (int id = pt; id < ROWS * 8; id += PROD_THREADS) {
+            const int c = id & 7, r = id >> 3;
+            cp_async16(st_addr + STAGE_W_BYTES + sw128(r, c), g.X + (size_t)(row0 + r) * g.ldx + kb * KB + c * 8);
+          }
+          cp_async_commit();
+          ++issued;
+          if (issued - arrived > 2) {  // keep two stages of loads in flight
+            cp_async_wait<2>();
+            fence_proxy_async();
+            mbar_arrive(full_bar + 8 * (arrived % NST));
+            ++arrived;
+          }
+        }
+      }
+    }
+    if (!GATHER) {
+      cp_async_wait<0>();
+      fence_proxy_async();
+      while (arrived < issued) {
+        mbar_arrive(full_bar + 8 * (arrived % NST));
+        ++arrived;
+      }
+    }
+  } else if (warp == EPI_WARPS) {
+    // =========================================================== MMA issuer (one thread)
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(ROWS);
+      uint32_t it = 0, tc_count = 0;
+      for (int t = tile_begin + rank_in_set; t < tile_begin + tiles_per_set; t += step, ++tc_count) {
+        const uint32_t buf = tc_count & 1, aph = (tc_count >> 1) & 1;
+        mbar_wait(acce_bar + 8 * buf, aph ^ 1);   // epilogue has drained this accumulator
+        tc_fence_after();
+        for (int kb = 0; kb < kblocks; ++kb, ++it) {
+          const uint32_t s = it % NST, ph = (it / NST) & 1;
+          mbar_wait(full_bar + 8 * s, ph);
+          tc_fence_after();
+          const uint32_t st_addr = stages_base + s * STAGE_BYTES;
+#pragma unroll
+          for (int chb = 0; chb < NCHB; ++chb) {
+            const uint32_t a_addr = RESIDENT ? smem_base + (uint32_t)(chb * kblocks + kb) * w_block_bytes
+                                             : st_addr + chb * w_block_bytes;
+            const uint64_t adesc = make_desc(a_addr), bdesc = make_desc(st_addr + STAGE_W_BYTES);
+            const uint32_t d_tmem = tmem_base + (buf * NCHB + chb) * ROWS;
+#pragma unroll
+            for (int k4 = 0; k4 < KB / 16; ++k4)   // +32 bytes per UMMA_K=16 step inside the swizzle row
+              umma_bf16(d_tmem, adesc + 2 * k4, bdesc + 2 * k4, idesc, (kb | k4) != 0);
+          }
+          umma_commit(empty_bar + 8 * s);          // stage reusable once these MMAs have read it
+        }
+        umma_commit(accf_bar + 8 * buf);           // accumulator complete
+      }
+    }
+  } else {
+    // =========================================================== epilogue (warps 0-3, TMEM lane = channel)
+    uint32_t tc_count = 0;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    for (int t = tile_begin + rank_in_set; t < tile_begin + tiles_per_set; t += step, ++tc_count) {
+      const int cht = t % ch_tiles, rt = t / ch_tiles;
+      const int row0 = rt * ROWS;
+      const uint32_t buf = tc_count & 1, aph = (tc_count >> 1) & 1;
+      mbar_wait(accf_bar + 8 * buf, aph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int chb = 0; chb < NCHB; ++chb) {
+        const int ch = (cht * NCHB + chb) * 128 + warp * 32 + lane;
+        const float bv = bias ? bias[ch] : 0.f;
+        float w1x = 0.f, w1y = 0.f, w1z = 0.f;
+        if (g.xyz) {
+          const float* wp = g.W1x[wset] + (size_t)ch * g.ldw1x;
+          w1x = wp[0]; w1y = wp[1]; w1z = wp[2];
+        }
+        const uint32_t t_addr = tmem_base + lane_base + (buf * NCHB + chb) * ROWS;
+        float cmax = -INFINITY;
+#pragma unroll 1
+        for (int c32 = 0; c32 < ROWS / 32; ++c32) {
+          float v[32];
+          tmem_ld32(t_addr + c32 * 32, v);
+          if (g.epi == 0) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const size_t row = (size_t)row0 + c32 * 32 + i;
+              float x = v[i] + bv;
+              if (g.xyz) {
+                const float* p = g.xyz + row * 3;
+                x = fmaf(w1x, p[0], fmaf(w1y, p[1], fmaf(w1z, p[2], x)));
+              }
+              if (g.relu) x = fmaxf(x, 0.f);
+              if (g.Rf) x += g.Rf[row * g.ldrf + ch];
+              if (g.Rb) x += __bfloat162float(g.Rb[row * g.ldrb + ch]);
+              if (g.Yf) g.Yf[row * g.ldyf + ch] = x;
+              if (g.Yb) g.Yb[row * g.ldyb + ch] = __float2bfloat16_rn(x);
+            }
+          } else {
+            float m = v[0];
+#pragma unroll
+            for (int i = 1; i < 32; ++i) m = fmaxf(m, v[i]);
+            if (g.epi == 1) {  // one output row per group of 32
+              float x = m + bv;
+              if (g.relu) x = fmaxf(x, 0.f);
+              const size_t grow = (size_t)(row0 >> 5) + c32;
+              if (g.Yf) g.Yf[grow * g.ldyf + ch] = x;
+              if (g.Yb) g.Yb[grow * g.ldyb + ch] = __float2bfloat16_rn(x);
+            } else {
+              cmax = fmaxf(cmax, m);
+            }
+          }
+        }
+        if (g.epi == 2) {  // max over all ROWS rows of the tile (one cloud)
+          float x = cmax + bv;
+          if (g.relu) x = fmaxf(x, 0.f);
+          if (g.Yf) g.Yf[(size_t)rt * g.ldyf + ch] = x;
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(acce_bar + 8 * buf);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == EPI_WARPS) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+template <int ROWS, int NCHB, bool RESIDENT, bool GATHER, int NST>
+static int tc_launch(const TcGemm& g, cudaStream_t st) {
+  const int kblocks = g.K / KB;
+  const size_t resident = RESIDENT ? (size_t)NCHB * kblocks * 128 * 128 : 0;
+  const size_t stage = (RESIDENT ? 0 : (size_t)NCHB * 128 * 128) + (size_t)ROWS * 128;
+  const size_t smem = 1024 + resident + NST * stage + 8 * (2 * NST + 4) + 16;
+  PZ_REQUIRE(smem <= 227 * 1024, PZ_ERR_UNSUPPORTED, "tc_gemm: needs %zu B of shared memory (K=%d too large for a resident weight)", smem, g.K);
+  auto kern = tc_gemm_kernel<ROWS, NCHB, RESIDENT, GATHER, NST>;
+  PZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int nsets = (g.rows_per_wset > 0 && g.M > g.rows_per_wset) ? 2 : 1;
+  const int tiles = (g.M / ROWS) * (g.Nout / (128 * NCHB));
+  int grid = tiles < kNumSMs ? tiles : kNumSMs;
+  if (nsets == 2 && (grid & 1)) --grid;   // equal CTA count per weight set
+  if (grid < nsets) grid = nsets;
+  kern<<<grid, THREADS, smem, st>>>(g);
+  PZ_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_tc_gemm(const TcGemm& g, cudaStream_t st) {
+  PZ_REQUIRE(g.W[0] && g.X && (g.Yf || g.Yb), PZ_ERR_ARG, "tc_gemm: null operand");
+  PZ_REQUIRE(g.M > 0 && g.Nout > 0 && g.K > 0, PZ_ERR_ARG, "tc_gemm: bad shape");
+  PZ_REQUIRE(g.K % 64 == 0 && g.Nout % 128 == 0 && g.ldx % 8 == 0 && g.ldw % 8 == 0, PZ_ERR_UNSUPPORTED,
+             "tc_gemm: needs K %% 64 == 0, Nout %% 128 == 0 and 16-byte aligned rows (K=%d Nout=%d)", g.K, g.Nout);
+  PZ_REQUIRE(((uintptr_t)g.X & 15) == 0 && ((uintptr_t)g.W[0] & 15) == 0 && (!g.W[1] || ((uintptr_t)g.W[1] & 15) == 0),
+             PZ_ERR_ARG, "tc_gemm: operands must be 16-byte aligned");
+  const int nsets = (g.rows_per_wset > 0 && g.M > g.rows_per_wset) ? 2 : 1;
+  if (nsets == 2) PZ_REQUIRE(g.W[1] && g.M == 2 * g.rows_per_wset, PZ_ERR_ARG, "tc_gemm: two weight sets need M == 2*rows_per_wset");
+  if (g.rows) {  // gathered B, resident weights
+    PZ_REQUIRE(g.Q && g.epi == 1, PZ_ERR_ARG, "tc_gemm: gathered operand needs Q and the group-max epilogue");
+    if (g.Nout == 128 && g.K <= 256) {
+      PZ_REQUIRE(g.M % (256 * nsets) == 0, PZ_ERR_UNSUPPORTED, "tc_gemm: M=%d must be a multiple of %d", g.M, 256 * nsets);
+      return tc_launch<256, 1, true, true, 4>(g, st);
+    }
+    if (g.Nout == 256 && g.K <= 256) {
+      PZ_REQUIRE(g.M % (128 * nsets) == 0, PZ_ERR_UNSUPPORTED, "tc_gemm: M=%d must be a multiple of %d", g.M, 128 * nsets);
+      return tc_launch<128, 2, true, true, 5>(g, st);
+    }
+    return fail(PZ_ERR_UNSUPPORTED, "tc_gemm: gathered GEMM supports (Nout,K) in {(128,<=256),(256,<=256)} (got %d,%d)", g.Nout, g.K);
+  }
+  PZ_REQUIRE(g.M % (256 * nsets) == 0, PZ_ERR_UNSUPPORTED, "tc_gemm: M=%d must be a multiple of %d", g.M, 256 * nsets);
+  return tc_launch<256, 1, false, false, 4>(g, st);
+}
+
+// fp32 -> bf16 with row strides (weights packs, activations entering the tensor-core path)
+__global__ void __launch_bounds__(256) cvt_bf16_kernel(const float* __restrict__ in, int ldi, int rows, int cols,
+                                                       __nv_bfloat16* __restrict__ out, int ldo) {
+  const size_t total = (size_t)rows * cols;
+  for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (size_t)gridDim.x * 256) {
+    const size_t r = e / cols;
+    const int c = (int)(e - r * cols);
+    out[r * ldo + c] = __float2bfloat16_rn(in[r * ldi + c]);
+  }
+}
+
+int launch_cvt_bf16(const float* in, int ldi, int rows, int cols, __nv_bfloat16* out, int ldo, cudaStream_t st) {
+  const size_t total = (size_t)rows * cols;
+  if (total == 0) return 0;
+  const int blocks = (int)((total + 255) / 256 < (size_t)kNumSMs * 8 ? (total + 255) / 256 : (size_t)kNumSMs * 8);
+  cvt_bf16_kernel<<<blocks, 256, 0, st>>>(in, ldi, rows, cols, out, ldo);
+  PZ_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace pz
+
+using namespace pz;
+
+extern "C" int pz_linear_bf16(const void* x_bf16, int ldx, const void* w_bf16, const float* bias, int M, int N, int K,
+                              int relu, const float* residual_or_null, int ldr, float* y, int ldy, pz_stream_t stream) {
+  PZ_REQUIRE(x_bf16 && w_bf16 && y, PZ_ERR_ARG, "pz_linear_bf16: null pointer");
+  PZ_REQUIRE(M >= 0 && N >= 1 && K >= 1 && ldx >= K && ldy >= N, PZ_ERR_ARG, "pz_linear_bf16: bad sizes");
+  if (M == 0) return 0;
+  TcGemm g;
+  g.X = static_cast<const __nv_bfloat16*>(x_bf16); g.ldx = ldx;
+  g.W[0] = static_cast<const __nv_bfloat16*>(w_bf16); g.ldw = K; g.bias[0] = bias;
+  g.M = M; g.Nout = N; g.K = K; g.relu = relu; g.Yf = y; g.ldyf = ldy; g.Rf = residual_or_null; g.ldrf = ldr;
+  return launch_tc_gemm(g, as_stream(stream));
+}

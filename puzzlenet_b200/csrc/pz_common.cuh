@@ -1,5 +1,6 @@
 // Shared helpers for libpuzzlenet_sm100.so (internal; the public ABI is include/puzzlenet_b200.h).
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -106,5 +107,33 @@ struct GemmF32 {
   int ldw1 = 0;
 };
 int launch_gemm_f32(const GemmF32& g, cudaStream_t st);
+
+// gemm_tc.cu -- tcgen05 bf16 GEMM: D^T[ch,row] = W[ch,:] . X[row,:]  (see the file header)
+struct TcGemm {
+  const __nv_bfloat16* W[2] = {nullptr, nullptr};  // [Nout, K] bf16 row-major, weight set = row / rows_per_wset
+  int ldw = 0;
+  const float* bias[2] = {nullptr, nullptr};       // [Nout] fp32
+  int rows_per_wset = 0;
+  const __nv_bfloat16* X = nullptr;                // plain: activations [M, K]; gathered: P [*, K]
+  int ldx = 0;
+  const int* rows = nullptr;                       // gathered: source row of P for each of the M rows
+  const float* Q = nullptr;                        // gathered: [M/32, K] fp32, X[r] = relu(P[rows[r]] - Q[r/32])
+  int M = 0, Nout = 0, K = 0;
+  int epi = 0;                                     // 0 store rows, 1 max over groups of 32 rows, 2 max over the tile's rows
+  int relu = 0;
+  float* Yf = nullptr;                             // fp32 output (optional)
+  int ldyf = 0;
+  __nv_bfloat16* Yb = nullptr;                     // bf16 output (optional)
+  int ldyb = 0;
+  const float* Rf = nullptr;                       // residual added after the ReLU (fp32 or bf16 source)
+  int ldrf = 0;
+  const __nv_bfloat16* Rb = nullptr;
+  int ldrb = 0;
+  const float* xyz = nullptr;                      // epi 0 only: y += W1x[ch,0:3] . xyz[row]  (layer 1 of a grouped MLP)
+  const float* W1x[2] = {nullptr, nullptr};
+  int ldw1x = 0;
+};
+int launch_tc_gemm(const TcGemm& g, cudaStream_t st);
+int launch_cvt_bf16(const float* in, int ldi, int rows, int cols, __nv_bfloat16* out, int ldo, cudaStream_t st);
 
 }  // namespace pz
