@@ -20,7 +20,8 @@ struct StemW {
 };
 
 __global__ void __launch_bounds__(128) stem_kernel(const float* __restrict__ xyz, StemW wa, StemW wb,
-                                                   int clouds_per_set, float* __restrict__ out) {
+                                                   int clouds_per_set, float* __restrict__ out,
+                                                   __nv_bfloat16* __restrict__ out_b) {
   __shared__ __align__(16) float w2s[64 * 64];
   __shared__ float w1s[64 * 3], b1s[64], b2s[64];
   const size_t p = (size_t)blockIdx.x * 128 + threadIdx.x;  // global point id
@@ -68,6 +69,11 @@ __global__ void __launch_bounds__(128) stem_kernel(const float* __restrict__ xyz
       r[u] = fmaxf(fmaf(v, a2, c2), 0.f);
     }
     *reinterpret_cast<float4*>(o + k0) = make_float4(r[0], r[1], r[2], r[3]);
+    if (out_b) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(r[0], r[1]), hi = __floats2bfloat162_rn(r[2], r[3]);
+      uint2 pk = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+      *reinterpret_cast<uint2*>(out_b + p * 64 + k0) = pk;
+    }
   }
 }
 
@@ -81,7 +87,9 @@ __global__ void __launch_bounds__(256) attention_kernel(const float* __restrict_
                                                         int L, int Dv, float scale,
                                                         const float* __restrict__ xres, int ldx,
                                                         float* __restrict__ out, int ldo,
-                                                        float* __restrict__ attn, int attn_mode) {
+                                                        float* __restrict__ attn, int attn_mode,
+                                                        const __nv_bfloat16* __restrict__ xres_b, int ldxb,
+                                                        __nv_bfloat16* __restrict__ out_b, int ldob) {
   extern __shared__ __align__(16) float at_smem[];
   const int lds = L + 4;
   float* Ss = at_smem;                 // [64][L+4]
@@ -209,14 +217,27 @@ __global__ void __launch_bounds__(256) attention_kernel(const float* __restrict_
         float4 x4 = *reinterpret_cast<const float4*>(xres + row * ldx + col);
         o4 = make_float4(x4.x - o4.x, x4.y - o4.y, x4.z - o4.z, x4.w - o4.w);
       }
-      *reinterpret_cast<float4*>(out + row * ldo + col) = o4;
+      if (xres_b) {
+        const uint2 xb = *reinterpret_cast<const uint2*>(xres_b + row * ldxb + col);
+        const float2 x01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xb.x));
+        const float2 x23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xb.y));
+        o4 = make_float4(x01.x - o4.x, x01.y - o4.y, x23.x - o4.z, x23.y - o4.w);
+      }
+      if (out) *reinterpret_cast<float4*>(out + row * ldo + col) = o4;
+      if (out_b) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(o4.x, o4.y), hi = __floats2bfloat162_rn(o4.z, o4.w);
+        *reinterpret_cast<uint2*>(out_b + row * ldob + col) =
+            make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+      }
     }
   }
 }
 
 static int launch_attention(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv,
                             int clouds, int L, int Dk, int Dv, const float* xres, int ldx, float* out,
-                            int ldo, float* attn, int attn_mode, cudaStream_t st) {
+                            int ldo, float* attn, int attn_mode, cudaStream_t st,
+                            const __nv_bfloat16* xres_b = nullptr, int ldxb = 0, __nv_bfloat16* out_b = nullptr,
+                            int ldob = 0) {
   PZ_REQUIRE(Dk == 64 && L % 64 == 0 && L >= 64 && L <= 256 && Dv % 128 == 0 && Dv >= 128, PZ_ERR_UNSUPPORTED,
              "attention: need Dk == 64, L in {64,128,192,256}, Dv %% 128 == 0 (got L=%d Dk=%d Dv=%d)", L, Dk, Dv);
   PZ_REQUIRE(clouds <= 65535, PZ_ERR_UNSUPPORTED, "attention: too many clouds");
@@ -226,7 +247,7 @@ static int launch_attention(const float* q, int ldq, const float* k, int ldk, co
   PZ_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(L / AT_ROWS, clouds);
   attention_kernel<<<grid, 256, smem, st>>>(q, ldq, k, ldk, v, ldv, L, Dv, 1.0f / sqrtf((float)Dk), xres, ldx,
-                                            out, ldo, attn, attn_mode);
+                                            out, ldo, attn, attn_mode, xres_b, ldxb, out_b, ldob);
   PZ_LAUNCH_CHECK();
   return 0;
 }
@@ -449,6 +470,43 @@ __global__ void se3_exp_kernel(const float* __restrict__ x, int B, float* __rest
   o[12] = 0.f; o[13] = 0.f; o[14] = 0.f; o[15] = 1.f;
 }
 
+// ------------------------------------------------ bf16 path helpers (PZ_PREC_BF16)
+// One launch converts / concatenates every weight the tensor-core path needs (fp32 reference layout ->
+// bf16 packs with 16-byte aligned rows).  Job y = blockIdx.y.
+struct PackJob {
+  const float* src;
+  void* dst;
+  int ldi, rows, cols, ldo, to_bf16;
+};
+constexpr int MAX_PACK_JOBS = 96;
+struct PackJobs {
+  PackJob j[MAX_PACK_JOBS];
+  int n;
+};
+__global__ void __launch_bounds__(256) pack_weights_kernel(const PackJobs jobs) {
+  const PackJob& jb = jobs.j[blockIdx.y];
+  const int total = jb.rows * jb.cols;
+  for (int e = blockIdx.x * 256 + threadIdx.x; e < total; e += gridDim.x * 256) {
+    const int r = e / jb.cols, c = e - r * jb.cols;
+    const float v = jb.src[(size_t)r * jb.ldi + c];
+    if (jb.to_bf16) static_cast<__nv_bfloat16*>(jb.dst)[(size_t)r * jb.ldo + c] = __float2bfloat16_rn(v);
+    else static_cast<float*>(jb.dst)[(size_t)r * jb.ldo + c] = v;
+  }
+}
+
+// Q[s, k] = W1[k, 0:3] . centre[s]  -- the centroid half of layer 1 of a grouped MLP (the per-neighbour
+// half, P, comes out of the layer-1 GEMM):  relu(W1 [xyz_j - c_s ; f_j] + b1) = relu(P_j - Q_s).
+__global__ void __launch_bounds__(256) centre_proj_kernel(const float* __restrict__ centres, const float* w1a,
+                                                          const float* w1b, int ldw1, int rows_per_set, int rows,
+                                                          int C1, float* __restrict__ Q) {
+  const size_t e = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (e >= (size_t)rows * C1) return;
+  const int s = (int)(e / C1), k = (int)(e - (size_t)s * C1);
+  const float* w = (s / rows_per_set == 0 ? w1a : w1b) + (size_t)k * ldw1;
+  const float* c = centres + (size_t)s * 3;
+  Q[e] = fmaf(w[0], c[0], fmaf(w[1], c[1], w[2] * c[2]));
+}
+
 // ======================================================================== orchestration
 static StemW stem_of(const PzEncoderWeights& w) {
   return StemW{w.mlp1_w, w.mlp1_b, w.mlp2_w, w.mlp2_b, w.bn1_w, w.bn1_b, w.bn1_mean, w.bn1_var,
@@ -465,7 +523,16 @@ static bool encoder_weights_ok(const PzEncoderWeights& w) {
 struct EncoderScratch {
   float *xfeat, *F1, *nx1, *f1f, *F2, *nx2, *att_cat, *q, *k, *v, *r, *tailp, *fglob;
   int *knn1r, *knn2r;
+  // bf16 path
+  __nv_bfloat16 *xfeat_b, *P1, *f1f_b, *P2, *att_cat_b, *r_b, *wpack;
+  float *Q1, *Q2, *qkv, *bqkv;
 };
+
+// bf16 weight pack of ONE encoder (elements): W3f[128,64] W4[128,128] W5f[256,128] W6[256,256]
+// 4 x (Wqkv[384,256] Wo[256,256]) Wout[1024,1280]
+constexpr size_t WP_W3F = 0, WP_W4 = WP_W3F + 128 * 64, WP_W5F = WP_W4 + 128 * 128, WP_W6 = WP_W5F + 256 * 128,
+                 WP_ATT = WP_W6 + 256 * 256, WP_ATT_STRIDE = 384 * 256 + 256 * 256, WP_WOUT = WP_ATT + 4 * WP_ATT_STRIDE,
+                 WP_TOTAL = WP_WOUT + 1024 * 1280;
 
 static size_t encoder_scratch_layout(int C, Arena& a, EncoderScratch& s) {
   s.xfeat = a.take<float>((size_t)C * NPTS * D0);
@@ -483,7 +550,188 @@ static size_t encoder_scratch_layout(int C, Arena& a, EncoderScratch& s) {
   s.r = a.take<float>((size_t)C * LATT * CATT);
   s.tailp = a.take<float>((size_t)C * 2 * 1024);
   s.fglob = a.take<float>((size_t)C * 1024);
+  s.xfeat_b = a.take<__nv_bfloat16>((size_t)C * NPTS * D0);
+  s.P1 = a.take<__nv_bfloat16>((size_t)C * NPTS * C1A);
+  s.Q1 = a.take<float>((size_t)C * S1 * C1A);
+  s.f1f_b = a.take<__nv_bfloat16>((size_t)C * S1 * C1B);
+  s.P2 = a.take<__nv_bfloat16>((size_t)C * S1 * C2A);
+  s.Q2 = a.take<float>((size_t)C * S2 * C2A);
+  s.att_cat_b = a.take<__nv_bfloat16>((size_t)C * LATT * 1280);
+  s.qkv = a.take<float>((size_t)C * LATT * 384);
+  s.r_b = a.take<__nv_bfloat16>((size_t)C * LATT * CATT);
+  s.wpack = a.take<__nv_bfloat16>(2 * WP_TOTAL);
+  s.bqkv = a.take<float>(2 * 4 * 384);
   return a.used;
+}
+
+// ---------------------------------------------------------------------------------------------
+// bf16 path: every dense layer on tcgen05 (gemm_tc.cu), geometry + softmax in fp32.
+// Layer 1 of each grouped MLP is split as  W1 [xyz_j - c_s ; f_j] + b1 = P_j - Q_s  with
+// P = f W1[:,3:]^T + b1 + W1[:,0:3] xyz_j (one GEMM over the SOURCE points, bf16 out) and
+// Q = W1[:,0:3] c_s (per centroid); the layer-2 GEMM gathers relu(P_j - Q_s) straight into its
+// shared-memory operand and max-pools over the 32 neighbours in its epilogue.
+// ---------------------------------------------------------------------------------------------
+static int encoder_forward_bf16(const PzEncoderWeights* w, int E, int B, const float* xyz, const int64_t* start1,
+                                const int64_t* start2, const PzEncoderOutputs& o, EncoderScratch& s, float* fglob_pair,
+                                const float** xfeat_out, cudaStream_t st) {
+  const int C = E * B;
+  const PzEncoderWeights& wa = w[0];
+  const PzEncoderWeights& wb = w[E - 1];
+  float* xfeat = o.x_feature ? o.x_feature : s.xfeat;
+  float* nx2 = o.x2 ? o.x2 : s.nx2;
+  if (xfeat_out) *xfeat_out = xfeat;
+
+  // ---- weights -> bf16 packs (one launch; ~8 MB read, cheap enough to redo every call, keeps the ABI stateless)
+  {
+    PackJobs jobs;
+    int n = 0;
+    auto add = [&](const float* src, int ldi, int rows, int cols, void* dst, int ldo, int bf) {
+      if (n < MAX_PACK_JOBS) jobs.j[n] = PackJob{src, dst, ldi, rows, cols, ldo, bf};
+      ++n;
+    };
+    for (int e = 0; e < E; ++e) {
+      const PzEncoderWeights& we = w[e];
+      __nv_bfloat16* wp = s.wpack + (size_t)e * WP_TOTAL;
+      add(we.mlp3_w + 3, 3 + D0, C1A, D0, wp + WP_W3F, D0, 1);
+      add(we.mlp4_w, C1A, C1B, C1A, wp + WP_W4, C1A, 1);
+      add(we.mlp5_w + 3, 3 + C1B, C2A, C1B, wp + WP_W5F, C1B, 1);
+      add(we.mlp6_w, C2A, C2B, C2A, wp + WP_W6, C2A, 1);
+      for (int l = 0; l < 4; ++l) {
+        __nv_bfloat16* wl = wp + WP_ATT + (size_t)l * WP_ATT_STRIDE;
+        add(we.q_w[l], CATT, 64, CATT, wl, CATT, 1);
+        add(we.k_w[l], CATT, 64, CATT, wl + 64 * CATT, CATT, 1);
+        add(we.v_w[l], CATT, CATT, CATT, wl + 128 * CATT, CATT, 1);
+        add(we.o_w[l], CATT, CATT, CATT, wl + 384 * CATT, CATT, 1);
+        float* bq = s.bqkv + ((size_t)e * 4 + l) * 384;
+        add(we.q_b[l], 64, 1, 64, bq, 64, 0);
+        add(we.k_b[l], 64, 1, 64, bq + 64, 64, 0);
+        add(we.v_b[l], CATT, 1, CATT, bq + 128, CATT, 0);
+      }
+      add(we.out_w, 1280, 1024, 1280, wp + WP_WOUT, 1280, 1);
+    }
+    PZ_REQUIRE(n <= MAX_PACK_JOBS, PZ_ERR_ARG, "encoder: %d weight pack jobs exceed the table", n);
+    jobs.n = n;
+    pack_weights_kernel<<<dim3(64, n), 256, 0, st>>>(jobs);
+    PZ_LAUNCH_CHECK();
+    prof_mark("pack_weights_bf16", st);
+  }
+  const __nv_bfloat16* wpa = s.wpack;
+  const __nv_bfloat16* wpb = s.wpack + (size_t)(E - 1) * WP_TOTAL;
+
+  stem_kernel<<<C * NPTS / 128, 128, 0, st>>>(xyz, stem_of(wa), stem_of(wb), B, xfeat, s.xfeat_b);
+  PZ_LAUNCH_CHECK();
+  prof_mark("stem", st);
+
+  // ---- stage 1
+  PZ_TRY(launch_fps(xyz, C, NPTS, start1, S1, o.fps1, nullptr, s.nx1, st));
+  prof_mark("fps1", st);
+  PZ_TRY(launch_knn(s.nx1, xyz, C, S1, NPTS, KNN, o.knn1, s.knn1r, nullptr, st));
+  prof_mark("knn1", st);
+  {
+    TcGemm g;  // P1 = x_feature W3[:,3:]^T + b3 + W3[:,0:3] xyz
+    g.X = s.xfeat_b; g.ldx = D0; g.W[0] = wpa + WP_W3F; g.W[1] = wpb + WP_W3F; g.ldw = D0;
+    g.bias[0] = wa.mlp3_b; g.bias[1] = wb.mlp3_b; g.rows_per_wset = B * NPTS; g.M = C * NPTS; g.Nout = C1A; g.K = D0;
+    g.Yb = s.P1; g.ldyb = C1A; g.xyz = xyz; g.W1x[0] = wa.mlp3_w; g.W1x[1] = wb.mlp3_w; g.ldw1x = 3 + D0;
+    PZ_TRY(launch_tc_gemm(g, st));
+    centre_proj_kernel<<<(int)(((size_t)C * S1 * C1A + 255) / 256), 256, 0, st>>>(s.nx1, wa.mlp3_w, wb.mlp3_w, 3 + D0,
+                                                                                   B * S1, C * S1, C1A, s.Q1);
+    PZ_LAUNCH_CHECK();
+    prof_mark("sg1_layer1", st);
+  }
+  {
+    TcGemm g;  // f1f = max_k relu(W4 relu(P1[j] - Q1[s]) + b4)
+    g.X = s.P1; g.ldx = C1A; g.rows = s.knn1r; g.Q = s.Q1; g.W[0] = wpa + WP_W4; g.W[1] = wpb + WP_W4; g.ldw = C1A;
+    g.bias[0] = wa.mlp4_b; g.bias[1] = wb.mlp4_b; g.rows_per_wset = B * S1 * KNN; g.M = C * S1 * KNN; g.Nout = C1B;
+    g.K = C1A; g.epi = 1; g.relu = 1; g.Yf = o.f1f; g.ldyf = C1B; g.Yb = s.f1f_b; g.ldyb = C1B;
+    PZ_TRY(launch_tc_gemm(g, st));
+    prof_mark("sg1_gather_layer2_maxpool", st);
+  }
+  // ---- stage 2
+  PZ_TRY(launch_fps(s.nx1, C, S1, start2, S2, o.fps2, nullptr, nx2, st));
+  prof_mark("fps2", st);
+  PZ_TRY(launch_knn(nx2, s.nx1, C, S2, S1, KNN, o.knn2, s.knn2r, nullptr, st));
+  prof_mark("knn2", st);
+  {
+    TcGemm g;
+    g.X = s.f1f_b; g.ldx = C1B; g.W[0] = wpa + WP_W5F; g.W[1] = wpb + WP_W5F; g.ldw = C1B;
+    g.bias[0] = wa.mlp5_b; g.bias[1] = wb.mlp5_b; g.rows_per_wset = B * S1; g.M = C * S1; g.Nout = C2A; g.K = C1B;
+    g.Yb = s.P2; g.ldyb = C2A; g.xyz = s.nx1; g.W1x[0] = wa.mlp5_w; g.W1x[1] = wb.mlp5_w; g.ldw1x = 3 + C1B;
+    PZ_TRY(launch_tc_gemm(g, st));
+    centre_proj_kernel<<<(int)(((size_t)C * S2 * C2A + 255) / 256), 256, 0, st>>>(nx2, wa.mlp5_w, wb.mlp5_w, 3 + C1B,
+                                                                                   B * S2, C * S2, C2A, s.Q2);
+    PZ_LAUNCH_CHECK();
+    prof_mark("sg2_layer1", st);
+  }
+  __nv_bfloat16* cat_b = s.att_cat_b;           // [C*256, 1280] bf16: cat(att1..att4, f2f)
+  float* cat_f = o.att_cat;                     // fp32 copy only when the caller asks for it
+  {
+    TcGemm g;
+    g.X = s.P2; g.ldx = C2A; g.rows = s.knn2r; g.Q = s.Q2; g.W[0] = wpa + WP_W6; g.W[1] = wpb + WP_W6; g.ldw = C2A;
+    g.bias[0] = wa.mlp6_b; g.bias[1] = wb.mlp6_b; g.rows_per_wset = B * S2 * KNN; g.M = C * S2 * KNN; g.Nout = C2B;
+    g.K = C2A; g.epi = 1; g.relu = 1; g.Yb = cat_b + 4 * CATT; g.ldyb = 1280;
+    if (cat_f) { g.Yf = cat_f + 4 * CATT; g.ldyf = 1280; }
+    else if (o.f2f) { g.Yf = o.f2f; g.ldyf = CATT; }
+    PZ_TRY(launch_tc_gemm(g, st));
+    prof_mark("sg2_gather_layer2_maxpool", st);
+  }
+  if (o.f2f && cat_f)
+    PZ_CUDA(cudaMemcpy2DAsync(o.f2f, CATT * sizeof(float), cat_f + 4 * CATT, 1280 * sizeof(float), CATT * sizeof(float),
+                              (size_t)C * LATT, cudaMemcpyDeviceToDevice, st));
+
+  // ---- 4 x offset attention
+  const int rows = C * LATT;
+  for (int l = 0; l < 4; ++l) {
+    const __nv_bfloat16* xb = l == 0 ? cat_b + 4 * CATT : cat_b + (l - 1) * CATT;
+    const __nv_bfloat16* wla = wpa + WP_ATT + (size_t)l * WP_ATT_STRIDE;
+    const __nv_bfloat16* wlb = wpb + WP_ATT + (size_t)l * WP_ATT_STRIDE;
+    {
+      TcGemm g;  // [q | k | v] = x Wqkv^T + b
+      g.X = xb; g.ldx = 1280; g.W[0] = wla; g.W[1] = wlb; g.ldw = CATT;
+      g.bias[0] = s.bqkv + (size_t)l * 384; g.bias[1] = s.bqkv + ((size_t)(E - 1) * 4 + l) * 384;
+      g.rows_per_wset = B * LATT; g.M = rows; g.Nout = 384; g.K = CATT; g.Yf = s.qkv; g.ldyf = 384;
+      PZ_TRY(launch_tc_gemm(g, st));
+      prof_mark("attn_qkv_proj", st);
+    }
+    const int amode = o.attention ? (l == 0 ? 1 : (l == 3 ? 3 : 2)) : 0;
+    PZ_TRY(launch_attention(s.qkv, 384, s.qkv + 64, 384, s.qkv + 128, 384, C, LATT, 64, CATT, nullptr, 0, nullptr, 0,
+                            o.attention, amode, st, xb, 1280, s.r_b, CATT));
+    prof_mark("attn_softmax_av", st);
+    {
+      TcGemm g;  // out = x + relu(Wo r + bo)
+      g.X = s.r_b; g.ldx = CATT; g.W[0] = wla + 384 * CATT; g.W[1] = wlb + 384 * CATT; g.ldw = CATT;
+      g.bias[0] = wa.o_b[l]; g.bias[1] = wb.o_b[l]; g.rows_per_wset = B * LATT; g.M = rows; g.Nout = CATT; g.K = CATT;
+      g.relu = 1; g.Rb = xb; g.ldrb = 1280; g.Yb = cat_b + l * CATT; g.ldyb = 1280;
+      if (cat_f) { g.Yf = cat_f + l * CATT; g.ldyf = 1280; }
+      PZ_TRY(launch_tc_gemm(g, st));
+      prof_mark("attn_out_proj", st);
+    }
+  }
+  // ---- tail
+  {
+    float* fg = o.f_global ? o.f_global : s.fglob;
+    TcGemm g;
+    g.X = cat_b; g.ldx = 1280; g.W[0] = wpa + WP_WOUT; g.W[1] = wpb + WP_WOUT; g.ldw = 1280;
+    g.bias[0] = wa.out_b; g.bias[1] = wb.out_b; g.rows_per_wset = B * LATT; g.M = rows; g.Nout = 1024; g.K = 1280;
+    if (o.out) {
+      g.Yf = o.out; g.ldyf = 1024;
+      PZ_TRY(launch_tc_gemm(g, st));
+      prof_mark("tail_linear", st);
+      rowblock_max_kernel<<<dim3(4, C), 256, 0, st>>>(o.out, 1024, LATT, 1024, C, C, 0, fg, 1024);
+      PZ_LAUNCH_CHECK();
+      prof_mark("tail_point_max", st);
+    } else {
+      g.epi = 2; g.Yf = fg; g.ldyf = 1024;      // one 256-row tile == one cloud: max over its rows in the epilogue
+      PZ_TRY(launch_tc_gemm(g, st));
+      prof_mark("tail_linear_maxpool", st);
+    }
+    if (fglob_pair)
+      PZ_CUDA(cudaMemcpy2DAsync(fglob_pair, (size_t)E * 1024 * sizeof(float), fg, 1024 * sizeof(float),
+                                1024 * sizeof(float), B, cudaMemcpyDeviceToDevice, st));
+    if (fglob_pair && E == 2)
+      PZ_CUDA(cudaMemcpy2DAsync(fglob_pair + 1024, (size_t)E * 1024 * sizeof(float), fg + (size_t)B * 1024,
+                                1024 * sizeof(float), 1024 * sizeof(float), B, cudaMemcpyDeviceToDevice, st));
+  }
+  return 0;
 }
 
 // fglob_pair: optional [B, E*1024] destination laid out for the pose MLP's concat (model5_b.py:723)
@@ -492,8 +740,7 @@ static int encoder_forward_impl(const PzEncoderWeights* w, int E, int B, const f
                                 size_t ws_bytes, float* fglob_pair, const float** xfeat_out, cudaStream_t st) {
   PZ_REQUIRE(E == 1 || E == 2, PZ_ERR_ARG, "encoder: E must be 1 or 2 (got %d)", E);
   PZ_REQUIRE(B >= 1, PZ_ERR_ARG, "encoder: B must be >= 1");
-  PZ_REQUIRE(precision == PZ_PREC_FP32, PZ_ERR_UNSUPPORTED,
-             "encoder: precision %d not available in this build (fp32 only)", precision);
+  PZ_REQUIRE(precision == PZ_PREC_FP32 || precision == PZ_PREC_BF16, PZ_ERR_ARG, "encoder: unknown precision %d", precision);
   for (int e = 0; e < E; ++e)
     PZ_REQUIRE(encoder_weights_ok(w[e]), PZ_ERR_ARG, "encoder: weight set %d has a null pointer", e);
   const int C = E * B;
@@ -501,6 +748,8 @@ static int encoder_forward_impl(const PzEncoderWeights* w, int E, int B, const f
   EncoderScratch s;
   encoder_scratch_layout(C, arena, s);
   PZ_REQUIRE(ws && arena.ok(), PZ_ERR_WORKSPACE, "encoder: workspace %zu B < required %zu B", ws_bytes, arena.used);
+  if (precision == PZ_PREC_BF16)
+    return encoder_forward_bf16(w, E, B, xyz, start1, start2, o, s, fglob_pair, xfeat_out, st);
   const PzEncoderWeights& wa = w[0];
   const PzEncoderWeights& wb = w[E - 1];
   float* xfeat = o.x_feature ? o.x_feature : s.xfeat;
@@ -510,7 +759,7 @@ static int encoder_forward_impl(const PzEncoderWeights* w, int E, int B, const f
   if (xfeat_out) *xfeat_out = xfeat;
 
   // stem: Linear(3,64)+BN+ReLU, Linear(64,64)+BN+ReLU -> x_feature [C,1024,64]
-  stem_kernel<<<C * NPTS / 128, 128, 0, st>>>(xyz, stem_of(wa), stem_of(wb), B, xfeat);
+  stem_kernel<<<C * NPTS / 128, 128, 0, st>>>(xyz, stem_of(wa), stem_of(wb), B, xfeat, nullptr);
   PZ_LAUNCH_CHECK();
   prof_mark("stem", st);
 

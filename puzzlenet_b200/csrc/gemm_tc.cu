@@ -137,6 +137,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcGemm g) {
   const uint32_t full_bar = bars_base, empty_bar = bars_base + 8 * NST;
   const uint32_t accf_bar = bars_base + 16 * NST, acce_bar = accf_bar + 16;
   const uint32_t tmem_slot = acce_bar + 16;
+  __shared__ float sxyz[ROWS * 3];
   uint8_t* smem_gen = tc_smem_raw + (smem_base - smem_u32(tc_smem_raw));   // generic pointer to smem_base
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -289,6 +290,11 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcGemm g) {
       const int cht = t % ch_tiles, rt = t / ch_tiles;
       const int row0 = rt * ROWS;
       const uint32_t buf = tc_count & 1, aph = (tc_count >> 1) & 1;
+      if (g.xyz) {   // coordinates of the tile's rows -> smem (coalesced), read back as broadcasts
+        asm volatile("bar.sync 1, 128;" ::: "memory");            // previous tile's readers are done
+        for (int i = tid; i < ROWS * 3; i += EPI_WARPS * 32) sxyz[i] = g.xyz[(size_t)row0 * 3 + i];
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
       mbar_wait(accf_bar + 8 * buf, aph);
       tc_fence_after();
 #pragma unroll 1
@@ -307,19 +313,35 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcGemm g) {
           float v[32];
           tmem_ld32(t_addr + c32 * 32, v);
           if (g.epi == 0) {
+            // all residual loads of the chunk are issued before the first dependent use / store, so
+            // their latency overlaps (one exposed L2 round trip per 32 rows instead of per row)
+            const size_t rbase = (size_t)row0 + c32 * 32;
+            float res[32];
+            if (g.Rf) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) res[i] = g.Rf[(rbase + i) * g.ldrf + ch];
+            } else if (g.Rb) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) res[i] = __bfloat162float(g.Rb[(rbase + i) * g.ldrb + ch]);
+            }
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-              const size_t row = (size_t)row0 + c32 * 32 + i;
               float x = v[i] + bv;
               if (g.xyz) {
-                const float* p = g.xyz + row * 3;
+                const float* p = sxyz + (c32 * 32 + i) * 3;     // tile's coordinates staged in smem
                 x = fmaf(w1x, p[0], fmaf(w1y, p[1], fmaf(w1z, p[2], x)));
               }
               if (g.relu) x = fmaxf(x, 0.f);
-              if (g.Rf) x += g.Rf[row * g.ldrf + ch];
-              if (g.Rb) x += __bfloat162float(g.Rb[row * g.ldrb + ch]);
-              if (g.Yf) g.Yf[row * g.ldyf + ch] = x;
-              if (g.Yb) g.Yb[row * g.ldyb + ch] = __float2bfloat16_rn(x);
+              if (g.Rf || g.Rb) x += res[i];
+              v[i] = x;
+            }
+            if (g.Yf) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) g.Yf[(rbase + i) * g.ldyf + ch] = v[i];
+            }
+            if (g.Yb) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) g.Yb[(rbase + i) * g.ldyb + ch] = __float2bfloat16_rn(v[i]);
             }
           } else {
             float m = v[0];
