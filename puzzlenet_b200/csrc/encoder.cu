@@ -524,8 +524,8 @@ struct EncoderScratch {
   float *xfeat, *F1, *nx1, *f1f, *F2, *nx2, *att_cat, *q, *k, *v, *r, *tailp, *fglob;
   int *knn1r, *knn2r;
   // bf16 path
-  __nv_bfloat16 *xfeat_b, *P1, *f1f_b, *P2, *att_cat_b, *r_b, *wpack;
-  float *Q1, *Q2, *qkv, *bqkv;
+  __nv_bfloat16 *xfeat_b, *P1, *f1f_b, *P2, *att_cat_b, *r_b, *wpack, *qk_b, *vT_b;
+  float *Q1, *Q2, *bqkv;
 };
 
 // bf16 weight pack of ONE encoder (elements): W3f[128,64] W4[128,128] W5f[256,128] W6[256,256]
@@ -557,7 +557,8 @@ static size_t encoder_scratch_layout(int C, Arena& a, EncoderScratch& s) {
   s.P2 = a.take<__nv_bfloat16>((size_t)C * S1 * C2A);
   s.Q2 = a.take<float>((size_t)C * S2 * C2A);
   s.att_cat_b = a.take<__nv_bfloat16>((size_t)C * LATT * 1280);
-  s.qkv = a.take<float>((size_t)C * LATT * 384);
+  s.qk_b = a.take<__nv_bfloat16>((size_t)C * LATT * 128);
+  s.vT_b = a.take<__nv_bfloat16>((size_t)C * LATT * CATT);
   s.r_b = a.take<__nv_bfloat16>((size_t)C * LATT * CATT);
   s.wpack = a.take<__nv_bfloat16>(2 * WP_TOTAL);
   s.bqkv = a.take<float>(2 * 4 * 384);
@@ -685,16 +686,16 @@ static int encoder_forward_bf16(const PzEncoderWeights* w, int E, int B, const f
     const __nv_bfloat16* wla = wpa + WP_ATT + (size_t)l * WP_ATT_STRIDE;
     const __nv_bfloat16* wlb = wpb + WP_ATT + (size_t)l * WP_ATT_STRIDE;
     {
-      TcGemm g;  // [q | k | v] = x Wqkv^T + b
+      TcGemm g;  // [q | k | v] = x Wqkv^T + b ; q|k stored row-major bf16, v stored TRANSPOSED per cloud (K-major for P v)
       g.X = xb; g.ldx = 1280; g.W[0] = wla; g.W[1] = wlb; g.ldw = CATT;
       g.bias[0] = s.bqkv + (size_t)l * 384; g.bias[1] = s.bqkv + ((size_t)(E - 1) * 4 + l) * 384;
-      g.rows_per_wset = B * LATT; g.M = rows; g.Nout = 384; g.K = CATT; g.Yf = s.qkv; g.ldyf = 384;
+      g.rows_per_wset = B * LATT; g.M = rows; g.Nout = 384; g.K = CATT; g.Yb = s.qk_b; g.ldyb = 128;
+      g.YT = s.vT_b; g.t_ch_begin = 128;
       PZ_TRY(launch_tc_gemm(g, st));
       prof_mark("attn_qkv_proj", st);
     }
     const int amode = o.attention ? (l == 0 ? 1 : (l == 3 ? 3 : 2)) : 0;
-    PZ_TRY(launch_attention(s.qkv, 384, s.qkv + 64, 384, s.qkv + 128, 384, C, LATT, 64, CATT, nullptr, 0, nullptr, 0,
-                            o.attention, amode, st, xb, 1280, s.r_b, CATT));
+    PZ_TRY(launch_attention_tc(s.qk_b, s.vT_b, xb, 1280, C, s.r_b, o.attention, amode, st));
     prof_mark("attn_softmax_av", st);
     {
       TcGemm g;  // out = x + relu(Wo r + bo)

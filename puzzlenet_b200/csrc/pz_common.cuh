@@ -129,11 +129,16 @@ struct TcGemm {
   int ldrf = 0;
   const __nv_bfloat16* Rb = nullptr;
   int ldrb = 0;
+  __nv_bfloat16* YT = nullptr;                     // epi 0: channels >= t_ch_begin are stored TRANSPOSED per row tile:
+  int t_ch_begin = 0;                              //   YT[(tile*(Nout-t_ch_begin) + ch-t_ch_begin)*ROWS + row_in_tile]
   const float* xyz = nullptr;                      // epi 0 only: y += W1x[ch,0:3] . xyz[row]  (layer 1 of a grouped MLP)
   const float* W1x[2] = {nullptr, nullptr};
   int ldw1x = 0;
 };
 int launch_tc_gemm(const TcGemm& g, cudaStream_t st);
+// attention_tc.cu: per cloud  r = x - softmax(q k^T / sqrt(64)) v   on tcgen05 (L == 256, d_k == 64, C == 256)
+int launch_attention_tc(const __nv_bfloat16* qk, const __nv_bfloat16* vT, const __nv_bfloat16* x, int ldx, int clouds,
+                        __nv_bfloat16* r, float* attn, int attn_mode, cudaStream_t st);
 int launch_cvt_bf16(const float* in, int ldi, int rows, int cols, __nv_bfloat16* out, int ldo, cudaStream_t st);
 
 }  // namespace pz
