@@ -29,6 +29,7 @@ constexpr int PROF_MAX_SETS = 512, PROF_MAX_MARKS = 48;
 struct ProfSet {
   cudaEvent_t ev[PROF_MAX_MARKS + 1];
   const char* name[PROF_MAX_MARKS + 1];
+  int lane[PROF_MAX_MARKS + 1];
   int n = 0;
   bool created = false;
 };
@@ -48,16 +49,36 @@ void prof_begin(cudaStream_t st) {
     s.created = true;
   }
   s.n = 0;
-  s.name[0] = "begin";
+  s.name[0] = "_begin";
+  s.lane[0] = 0;
   cudaEventRecord(s.ev[0], st);
 }
-void prof_mark(const char* stage, cudaStream_t st) {
+void prof_mark(const char* stage, cudaStream_t st, int lane) {
   if (!g_prof_on || !g_sets || g_cur < 0 || g_cur >= PROF_MAX_SETS) return;
   ProfSet& s = (*g_sets)[g_cur];
   if (s.n >= PROF_MAX_MARKS) return;
   ++s.n;
   s.name[s.n] = stage;
+  s.lane[s.n] = lane;
   cudaEventRecord(s.ev[s.n], st);
+}
+
+int side_stream(SideStream** out) {
+  static std::mutex mu;
+  static SideStream per_device[64];
+  int dev = 0;
+  PZ_CUDA(cudaGetDevice(&dev));
+  PZ_REQUIRE(dev >= 0 && dev < 64, PZ_ERR_UNSUPPORTED, "device ordinal %d out of range", dev);
+  std::lock_guard<std::mutex> lk(mu);
+  SideStream& s = per_device[dev];
+  if (!s.stream) {
+    PZ_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    PZ_CUDA(cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming));
+    PZ_CUDA(cudaEventCreateWithFlags(&s.join_a, cudaEventDisableTiming));
+    PZ_CUDA(cudaEventCreateWithFlags(&s.join_b, cudaEventDisableTiming));
+  }
+  *out = &s;
+  return 0;
 }
 
 }  // namespace pz
@@ -83,9 +104,12 @@ extern "C" int pz_profile_collect(double* ms, const char** names, int* calls, in
   for (int i = 0; i < max_stages; ++i) ms[i] = 0.0;
   for (int c = 0; c < nsets; ++c) {
     pz::ProfSet& s = (*pz::g_sets)[c];
+    int last[2] = {0, -1};
     for (int i = 1; i <= s.n && i <= max_stages; ++i) {
+      const int lane = s.lane[i] & 1;
       float t = 0.f;
-      cudaEventElapsedTime(&t, s.ev[i - 1], s.ev[i]);
+      if (last[lane] >= 0 && s.name[i][0] != '_') cudaEventElapsedTime(&t, s.ev[last[lane]], s.ev[i]);
+      last[lane] = i;
       ms[i - 1] += t;
       if (names) names[i - 1] = s.name[i];
     }

@@ -619,26 +619,44 @@ static int encoder_forward_bf16(const PzEncoderWeights* w, int E, int B, const f
   const __nv_bfloat16* wpa = s.wpack;
   const __nv_bfloat16* wpb = s.wpack + (size_t)(E - 1) * WP_TOTAL;
 
+  // ---- geometry (FPS -> kNN, both stages, plus the centroid halves Q of layer 1) depends on coordinates only:
+  // it runs on the side stream while the feature chain (stem, layer-1 GEMM) runs on the caller's stream.
+  SideStream* ss = nullptr;
+  PZ_TRY(side_stream(&ss));
+  cudaStream_t sg = ss->stream;
+  PZ_CUDA(cudaEventRecord(ss->fork, st));
+  PZ_CUDA(cudaStreamWaitEvent(sg, ss->fork, 0));
+  prof_mark("_side_begin", sg, 1);
+  PZ_TRY(launch_fps(xyz, C, NPTS, start1, S1, o.fps1, nullptr, s.nx1, sg));
+  prof_mark("fps1", sg, 1);
+  centre_proj_kernel<<<(int)(((size_t)C * S1 * C1A + 255) / 256), 256, 0, sg>>>(s.nx1, wa.mlp3_w, wb.mlp3_w, 3 + D0,
+                                                                                 B * S1, C * S1, C1A, s.Q1);
+  PZ_LAUNCH_CHECK();
+  PZ_TRY(launch_knn(s.nx1, xyz, C, S1, NPTS, KNN, o.knn1, s.knn1r, nullptr, sg));
+  prof_mark("knn1", sg, 1);
+  PZ_CUDA(cudaEventRecord(ss->join_a, sg));
+  PZ_TRY(launch_fps(s.nx1, C, S1, start2, S2, o.fps2, nullptr, nx2, sg));
+  prof_mark("fps2", sg, 1);
+  centre_proj_kernel<<<(int)(((size_t)C * S2 * C2A + 255) / 256), 256, 0, sg>>>(nx2, wa.mlp5_w, wb.mlp5_w, 3 + C1B,
+                                                                                 B * S2, C * S2, C2A, s.Q2);
+  PZ_LAUNCH_CHECK();
+  PZ_TRY(launch_knn(nx2, s.nx1, C, S2, S1, KNN, o.knn2, s.knn2r, nullptr, sg));
+  prof_mark("knn2", sg, 1);
+  PZ_CUDA(cudaEventRecord(ss->join_b, sg));
+
   stem_kernel<<<C * NPTS / 128, 128, 0, st>>>(xyz, stem_of(wa), stem_of(wb), B, xfeat, s.xfeat_b);
   PZ_LAUNCH_CHECK();
   prof_mark("stem", st);
-
-  // ---- stage 1
-  PZ_TRY(launch_fps(xyz, C, NPTS, start1, S1, o.fps1, nullptr, s.nx1, st));
-  prof_mark("fps1", st);
-  PZ_TRY(launch_knn(s.nx1, xyz, C, S1, NPTS, KNN, o.knn1, s.knn1r, nullptr, st));
-  prof_mark("knn1", st);
   {
     TcGemm g;  // P1 = x_feature W3[:,3:]^T + b3 + W3[:,0:3] xyz
     g.X = s.xfeat_b; g.ldx = D0; g.W[0] = wpa + WP_W3F; g.W[1] = wpb + WP_W3F; g.ldw = D0;
     g.bias[0] = wa.mlp3_b; g.bias[1] = wb.mlp3_b; g.rows_per_wset = B * NPTS; g.M = C * NPTS; g.Nout = C1A; g.K = D0;
     g.Yb = s.P1; g.ldyb = C1A; g.xyz = xyz; g.W1x[0] = wa.mlp3_w; g.W1x[1] = wb.mlp3_w; g.ldw1x = 3 + D0;
     PZ_TRY(launch_tc_gemm(g, st));
-    centre_proj_kernel<<<(int)(((size_t)C * S1 * C1A + 255) / 256), 256, 0, st>>>(s.nx1, wa.mlp3_w, wb.mlp3_w, 3 + D0,
-                                                                                   B * S1, C * S1, C1A, s.Q1);
-    PZ_LAUNCH_CHECK();
     prof_mark("sg1_layer1", st);
   }
+  PZ_CUDA(cudaStreamWaitEvent(st, ss->join_a, 0));   // kNN of stage 1 (and FPS 1, Q1) are done
+  prof_mark("_wait_geometry1", st);
   {
     TcGemm g;  // f1f = max_k relu(W4 relu(P1[j] - Q1[s]) + b4)
     g.X = s.P1; g.ldx = C1A; g.rows = s.knn1r; g.Q = s.Q1; g.W[0] = wpa + WP_W4; g.W[1] = wpb + WP_W4; g.ldw = C1A;
@@ -647,22 +665,16 @@ static int encoder_forward_bf16(const PzEncoderWeights* w, int E, int B, const f
     PZ_TRY(launch_tc_gemm(g, st));
     prof_mark("sg1_gather_layer2_maxpool", st);
   }
-  // ---- stage 2
-  PZ_TRY(launch_fps(s.nx1, C, S1, start2, S2, o.fps2, nullptr, nx2, st));
-  prof_mark("fps2", st);
-  PZ_TRY(launch_knn(nx2, s.nx1, C, S2, S1, KNN, o.knn2, s.knn2r, nullptr, st));
-  prof_mark("knn2", st);
   {
-    TcGemm g;
+    TcGemm g;  // P2 = f1f W5[:,3:]^T + b5 + W5[:,0:3] x1
     g.X = s.f1f_b; g.ldx = C1B; g.W[0] = wpa + WP_W5F; g.W[1] = wpb + WP_W5F; g.ldw = C1B;
     g.bias[0] = wa.mlp5_b; g.bias[1] = wb.mlp5_b; g.rows_per_wset = B * S1; g.M = C * S1; g.Nout = C2A; g.K = C1B;
     g.Yb = s.P2; g.ldyb = C2A; g.xyz = s.nx1; g.W1x[0] = wa.mlp5_w; g.W1x[1] = wb.mlp5_w; g.ldw1x = 3 + C1B;
     PZ_TRY(launch_tc_gemm(g, st));
-    centre_proj_kernel<<<(int)(((size_t)C * S2 * C2A + 255) / 256), 256, 0, st>>>(nx2, wa.mlp5_w, wb.mlp5_w, 3 + C1B,
-                                                                                   B * S2, C * S2, C2A, s.Q2);
-    PZ_LAUNCH_CHECK();
     prof_mark("sg2_layer1", st);
   }
+  PZ_CUDA(cudaStreamWaitEvent(st, ss->join_b, 0));   // stage-2 geometry is done (side stream joined)
+  prof_mark("_wait_geometry2", st);
   __nv_bfloat16* cat_b = s.att_cat_b;           // [C*256, 1280] bf16: cat(att1..att4, f2f)
   float* cat_f = o.att_cat;                     // fp32 copy only when the caller asks for it
   {

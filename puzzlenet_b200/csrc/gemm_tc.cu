@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcGemm g) {
 
   if (tid == 0) {
     for (int s = 0; s < NST; ++s) {
-      mbar_init(full_bar + 8 * s, PROD_THREADS);
+      mbar_init(full_bar + 8 * s, GATHER ? PROD_THREADS / 2 : PROD_THREADS);
       mbar_init(empty_bar + 8 * s, 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -109,30 +109,55 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcGemm g) {
     for (int t = tile_begin + rank_in_set; t < tile_begin + tiles_per_set; t += step) {
       const int cht = t % ch_tiles, rt = t / ch_tiles;
       const int row0 = rt * ROWS;
+      // GATHER: the 256 producer threads form two groups that fill alternate stages, so each group has two
+      // stage-times to hide the dependent index -> row -> operand latency chain; a thread keeps the source
+      // rows of its chunks for the whole tile and issues its operand loads in independent batches of 8.
+      constexpr int GCH = GATHER ? ROWS * 8 / (PROD_THREADS / 2) : 1;   // 16-byte chunks per thread per stage
+      const int grp = pt >> 7, gt = pt & 127, gc = gt & 7;
+      int src[GCH];
+      if (GATHER) {
+#pragma unroll
+        for (int i = 0; i < GCH; ++i) src[i] = g.rows[row0 + (gt >> 3) + i * 16];
+      }
       for (int kb = 0; kb < kblocks; ++kb) {
         const uint32_t s = issued % NST, ph = (issued / NST) & 1;
+        if (GATHER && (int)(issued & 1) != grp) {   // the other group's stage
+          ++issued;
+          ++arrived;
+          continue;
+        }
         mbar_wait(empty_bar + 8 * s, ph ^ 1);
         const uint32_t st_addr = stages_base + s * STAGE_BYTES;
         uint8_t* st_gen = smem_gen + (st_addr - smem_base);
         if (GATHER) {
           // X[r, k] = relu(P[rows[r], k] - Q[(row0+r)/32, k])  -> bf16, swizzled
-          for (int id = pt; id < ROWS * 8; id += PROD_THREADS) {
-            const int c = id & 7, r = id >> 3;
-            const int src = g.rows[row0 + r];
-            const uint4 pv = *reinterpret_cast<const uint4*>(g.X + (size_t)src * g.ldx + kb * KB + c * 8);
-            const float4* qp = reinterpret_cast<const float4*>(g.Q + (size_t)((row0 + r) >> 5) * g.K + kb * KB + c * 8);
-            const float4 q0 = qp[0], q1 = qp[1];
-            const __nv_bfloat162* p2 = reinterpret_cast<const __nv_bfloat162*>(&pv);
-            const float2 a = __bfloat1622float2(p2[0]), b = __bfloat1622float2(p2[1]);
-            const float2 cc = __bfloat1622float2(p2[2]), d = __bfloat1622float2(p2[3]);
-            uint4 o;
-            __nv_bfloat162 t0 = __floats2bfloat162_rn(fmaxf(a.x - q0.x, 0.f), fmaxf(a.y - q0.y, 0.f));
-            __nv_bfloat162 t1 = __floats2bfloat162_rn(fmaxf(b.x - q0.z, 0.f), fmaxf(b.y - q0.w, 0.f));
-            __nv_bfloat162 t2 = __floats2bfloat162_rn(fmaxf(cc.x - q1.x, 0.f), fmaxf(cc.y - q1.y, 0.f));
-            __nv_bfloat162 t3 = __floats2bfloat162_rn(fmaxf(d.x - q1.z, 0.f), fmaxf(d.y - q1.w, 0.f));
-            o.x = *reinterpret_cast<uint32_t*>(&t0); o.y = *reinterpret_cast<uint32_t*>(&t1);
-            o.z = *reinterpret_cast<uint32_t*>(&t2); o.w = *reinterpret_cast<uint32_t*>(&t3);
-            *reinterpret_cast<uint4*>(st_gen + STAGE_W_BYTES + sw128(r, c)) = o;
+#pragma unroll
+          for (int b0 = 0; b0 < GCH; b0 += 8) {
+            uint4 pv[8];
+            float4 q0[8], q1[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int r = (gt >> 3) + (b0 + i) * 16;
+              pv[i] = *reinterpret_cast<const uint4*>(g.X + (size_t)src[b0 + i] * g.ldx + kb * KB + gc * 8);
+              const float4* qp = reinterpret_cast<const float4*>(g.Q + (size_t)((row0 + r) >> 5) * g.K + kb * KB + gc * 8);
+              q0[i] = qp[0];
+              q1[i] = qp[1];
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int r = (gt >> 3) + (b0 + i) * 16;
+              const __nv_bfloat162* p2 = reinterpret_cast<const __nv_bfloat162*>(&pv[i]);
+              const float2 a = __bfloat1622float2(p2[0]), b = __bfloat1622float2(p2[1]);
+              const float2 cc = __bfloat1622float2(p2[2]), d = __bfloat1622float2(p2[3]);
+              uint4 o;
+              __nv_bfloat162 t0 = __floats2bfloat162_rn(fmaxf(a.x - q0[i].x, 0.f), fmaxf(a.y - q0[i].y, 0.f));
+              __nv_bfloat162 t1 = __floats2bfloat162_rn(fmaxf(b.x - q0[i].z, 0.f), fmaxf(b.y - q0[i].w, 0.f));
+              __nv_bfloat162 t2 = __floats2bfloat162_rn(fmaxf(cc.x - q1[i].x, 0.f), fmaxf(cc.y - q1[i].y, 0.f));
+              __nv_bfloat162 t3 = __floats2bfloat162_rn(fmaxf(d.x - q1[i].z, 0.f), fmaxf(d.y - q1[i].w, 0.f));
+              o.x = *reinterpret_cast<uint32_t*>(&t0); o.y = *reinterpret_cast<uint32_t*>(&t1);
+              o.z = *reinterpret_cast<uint32_t*>(&t2); o.w = *reinterpret_cast<uint32_t*>(&t3);
+              *reinterpret_cast<uint4*>(st_gen + STAGE_W_BYTES + sw128(r, gc)) = o;
+            }
           }
           fence_proxy_async();
           mbar_arrive(full_bar + 8 * s);

@@ -6,6 +6,8 @@
 //   ((dx*dx) + (dy*dy)) + (dz*dz)   in fp32, each op rounded, no FMA contraction
 // (the ATen CPU evaluation of pointnet_util.py:36 / :70), hence the explicit
 // __fmul_rn / __fadd_rn below.
+#include <stdlib.h>
+
 #include "pz_common.cuh"
 
 namespace pz {
@@ -34,21 +36,24 @@ __global__ void __launch_bounds__(T) fps_kernel(const float* __restrict__ xyz, i
   float* xs = fps_smem;
   float* ys = xs + N;
   float* zs = ys + N;
+  int* sel = reinterpret_cast<int*>(zs + N);   // [S] picked indices; written out coalesced after the loop
   __shared__ unsigned int whi[2][32];
   __shared__ unsigned int wlo[2][32];
 
   const int c = blockIdx.x;
   const int t = threadIdx.x;
   const int lane = t & 31, warp = t >> 5;
-  constexpr int NW = T / 32;
   const float* p = xyz + (size_t)c * N * 3;
   for (int i = t; i < N * 3; i += T) {
     float v = p[i];
     int pt = i / 3, d = i - pt * 3;
     fps_smem[d * N + pt] = v;
   }
+  if (t < 64) (&whi[0][0])[t] = 0u, (&wlo[0][0])[t] = 0u;   // slots of absent warps stay 0 = "no candidate"
   __syncthreads();
 
+  // Padding slots (index >= N) sit at the origin with min-distance 0: fminf(0, d) stays 0, so they need no
+  // bounds test in the loop and can never beat a real point (ties resolve to the lowest index).
   float px[PPT], py[PPT], pz_[PPT], md[PPT];
 #pragma unroll
   for (int j = 0; j < PPT; ++j) {
@@ -57,56 +62,59 @@ __global__ void __launch_bounds__(T) fps_kernel(const float* __restrict__ xyz, i
     px[j] = ok ? xs[i] : 0.f;
     py[j] = ok ? ys[i] : 0.f;
     pz_[j] = ok ? zs[i] : 0.f;
-    md[j] = ok ? 1e10f : 0.f;  // padding can never beat a real point (ties -> lowest index)
+    md[j] = ok ? 1e10f : 0.f;
   }
 
   int far = (int)start[c];
   far = min(max(far, 0), N - 1);
   for (int s = 0; s < S; ++s) {
-    if (t == 0) {
-      if (out64) out64[(size_t)c * S + s] = far;
-      if (out_rows32) out_rows32[(size_t)c * S + s] = c * N + far;
-    }
-    const float cx = xs[far], cy = ys[far], cz = zs[far];
-    if (t < 3 && new_xyz) new_xyz[((size_t)c * S + s) * 3 + t] = (t == 0 ? cx : (t == 1 ? cy : cz));
+    if (t == 0) sel[s] = far;
     if (s + 1 == S) break;
-
+    const float cx = xs[far], cy = ys[far], cz = zs[far];
     float best = -1.f;
-    int besti = 0;
+    int bestj = 0;
 #pragma unroll
     for (int j = 0; j < PPT; ++j) {
-      int i = t + j * T;
-      if (i < N) {
-        float d = sqdist3(px[j], py[j], pz_[j], cx, cy, cz);
-        md[j] = fminf(md[j], d);
-      }
-      if (md[j] > best) {  // strict: earlier (lower) index wins inside a thread
-        best = md[j];
-        besti = i;
-      }
+      md[j] = fminf(md[j], sqdist3(px[j], py[j], pz_[j], cx, cy, cz));
+      const bool gt = md[j] > best;   // strict: the earlier (lower) index wins inside a thread
+      best = gt ? md[j] : best;
+      bestj = gt ? j : bestj;
     }
-    unsigned int hi = __float_as_uint(best);  // distances are >= 0: bits are order preserving
-    unsigned int lo = ~(unsigned int)besti;
-    unsigned int mhi = __reduce_max_sync(0xffffffffu, hi);
-    unsigned int mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
+    const unsigned int hi = __float_as_uint(best);  // distances are >= 0: the bit pattern is order preserving
+    const unsigned int lo = ~(unsigned int)(t + bestj * T);
+    const unsigned int mhi = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned int mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
     const int par = s & 1;
     if (lane == 0) {
       whi[par][warp] = mhi;
       wlo[par][warp] = mlo;
     }
     __syncthreads();
-    unsigned int h2 = lane < NW ? whi[par][lane] : 0u;
-    unsigned int l2 = lane < NW ? wlo[par][lane] : 0u;
-    unsigned int ghi = __reduce_max_sync(0xffffffffu, h2);
-    unsigned int glo = __reduce_max_sync(0xffffffffu, (h2 == ghi && lane < NW) ? l2 : 0u);
+    const unsigned int h2 = whi[par][lane];
+    const unsigned int l2 = wlo[par][lane];
+    const unsigned int ghi = __reduce_max_sync(0xffffffffu, h2);
+    const unsigned int glo = __reduce_max_sync(0xffffffffu, h2 == ghi ? l2 : 0u);
     far = (int)(~glo);
+  }
+  __syncthreads();
+  for (int s = t; s < S; s += T) {
+    const int f = sel[s];
+    const size_t o = (size_t)c * S + s;
+    if (out64) out64[o] = f;
+    if (out_rows32) out_rows32[o] = c * N + f;
+    if (new_xyz) {
+      new_xyz[o * 3 + 0] = xs[f];
+      new_xyz[o * 3 + 1] = ys[f];
+      new_xyz[o * 3 + 2] = zs[f];
+    }
   }
 }
 
 template <int PPT, int T>
 static int fps_launch_t(const float* xyz, int B, int N, const int64_t* start, int S, int64_t* out64,
                         int* out_rows32, float* new_xyz, cudaStream_t st) {
-  size_t smem = (size_t)N * 3 * sizeof(float);
+  size_t smem = (size_t)N * 3 * sizeof(float) + (size_t)S * sizeof(int);
+  PZ_REQUIRE(smem <= 227 * 1024, PZ_ERR_UNSUPPORTED, "pz_fps: N=%d, S=%d need %zu B of shared memory", N, S, smem);
   if (smem > 48 * 1024)
     PZ_CUDA(cudaFuncSetAttribute(fps_kernel<PPT, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   fps_kernel<PPT, T><<<B, T, smem, st>>>(xyz, N, S, start, out64, out_rows32, new_xyz);
@@ -116,6 +124,15 @@ static int fps_launch_t(const float* xyz, int B, int N, const int64_t* start, in
 
 int launch_fps(const float* xyz, int B, int N, const int64_t* start, int S, int64_t* out64,
                int* out_rows32, float* new_xyz, cudaStream_t st) {
+  if (const char* e = getenv("PZ_FPS_T")) {   // tuning experiment hook: threads per cloud for N <= 1024
+    const int T = atoi(e);
+    if (N <= 1024) {
+      if (T == 64) return fps_launch_t<16, 64>(xyz, B, N, start, S, out64, out_rows32, new_xyz, st);
+      if (T == 128) return fps_launch_t<8, 128>(xyz, B, N, start, S, out64, out_rows32, new_xyz, st);
+      if (T == 512) return fps_launch_t<2, 512>(xyz, B, N, start, S, out64, out_rows32, new_xyz, st);
+      if (T == 1024) return fps_launch_t<1, 1024>(xyz, B, N, start, S, out64, out_rows32, new_xyz, st);
+    }
+  }
   if (N <= 256) return fps_launch_t<2, 128>(xyz, B, N, start, S, out64, out_rows32, new_xyz, st);
   if (N <= 512) return fps_launch_t<4, 128>(xyz, B, N, start, S, out64, out_rows32, new_xyz, st);
   if (N <= 1024) return fps_launch_t<4, 256>(xyz, B, N, start, S, out64, out_rows32, new_xyz, st);

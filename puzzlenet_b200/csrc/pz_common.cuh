@@ -44,7 +44,15 @@ int fail(int code, const char* fmt, ...);
 void count_launch();
 // opt-in stage profiler (pz_profile_*): CUDA events between the stages of pz_predict5 / pz_encoder_forward
 void prof_begin(cudaStream_t st);
-void prof_mark(const char* stage, cudaStream_t st);
+void prof_mark(const char* stage, cudaStream_t st, int lane = 0);   // lane 1 = the internal side stream
+
+// Internal fork/join helper: one non-blocking side stream + events per device, created on first use and
+// reused by every call (capturable: the side stream is always joined back into the caller's stream).
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join_a = nullptr, join_b = nullptr;
+};
+int side_stream(SideStream** out);
 
 static inline cudaStream_t as_stream(pz_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
