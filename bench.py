@@ -56,7 +56,7 @@ class ClockSampler:
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -206,6 +206,25 @@ def run_gpu_arm(args):
     step_ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = sum(step_ms)
 
+    # ---- the other precision of BASELINE configs[1] ("fp32 and bf16"), same protocol, fewer steps
+    other = None
+    other_prec = "fp32" if args.precision == "bf16" else "bf16"
+    if not args.single_precision:
+        model.precision = other_prec
+        k2 = min(args.steps, 20)
+        for i in range(3):
+            step_resident(i)
+        ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(k2)]
+        barrier()
+        for i in range(k2):
+            flush.zero_()
+            ev2[i][0].record()
+            step_resident(i)
+            ev2[i][1].record()
+        barrier()
+        other = [sum(a.elapsed_time(b) for a, b in ev2), k2]
+        model.precision = args.precision
+
     # ---- e2e: pinned host inputs -> H2D -> predict5 -> D2H of the results, every step
     out_host = (torch.empty(B, 6).pin_memory(), torch.empty(B, 2, 1024).pin_memory(), torch.empty(B, 2, 1024).pin_memory())
     h2d = sum(t.numel() * t.element_size() for t in host[0])
@@ -232,10 +251,10 @@ def run_gpu_arm(args):
     clocks = sampler.stop() if sampler else None
 
     # ---- reduce over ranks: max time, total pairs
-    t = torch.tensor([total_ms, e2e_ms], device=dev, dtype=torch.float64)
+    t = torch.tensor([total_ms, e2e_ms, other[0] if other else 0.0], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms = t.tolist()
+    total_ms, e2e_ms, other_ms = t.tolist()
     pairs_total = B * args.steps * world
     value = pairs_total / (total_ms / 1e3)
     e2e_value = pairs_total / (e2e_ms / 1e3)
@@ -252,31 +271,40 @@ def run_gpu_arm(args):
         agg[name] = agg.get(name, 0.0) + ms
     per_step = {k: v / max(calls, 1) for k, v in agg.items()}
     clouds = 2 * B
-    # algorithmic work of each stage per launch: flops or bytes
-    flop = {
-        "sg1_gather_layer2_maxpool": 2.0 * clouds * 512 * 32 * 128 * 128,
-        "sg2_gather_layer2_maxpool": 2.0 * clouds * 256 * 32 * 256 * 256,
-        "tail_linear_maxpool": 2.0 * clouds * 256 * 1280 * 1024,
+    # algorithmic work of each stage per step: FLOPs for the dense stages (tensor bound), compulsory
+    # bytes for the geometry stages (they are latency/issue bound, the HBM fraction is reported
+    # truthfully).  (work, bound, launches per step)
+    work = {
+        "sg1_gather_layer2_maxpool": (2.0 * clouds * 512 * 32 * 128 * 128, "tensor", 1),
+        "sg2_gather_layer2_maxpool": (2.0 * clouds * 256 * 32 * 256 * 256, "tensor", 1),
+        "tail_linear_maxpool": (2.0 * clouds * 256 * 1280 * 1024, "tensor", 1),
+        "attn_qkv_proj": (4 * 2.0 * clouds * 256 * 256 * 384, "tensor", 4 if args.precision == "bf16" else 12),
+        "attn_out_proj": (4 * 2.0 * clouds * 256 * 256 * 256, "tensor", 4),
+        "attn_softmax_av": (4 * 2.0 * clouds * 256 * 256 * (64 + 256), "tensor", 4),
+        "fps1": (clouds * (12 * 1024 + 8 * 512), "hbm", 1),
+        "fps2": (clouds * (12 * 512 + 8 * 256), "hbm", 1),
+        "knn1": (clouds * (12 * 1024 + 12 * 512 + 8 * 512 * 32), "hbm", 1),
+        "knn2": (clouds * (12 * 512 + 12 * 256 + 8 * 256 * 32), "hbm", 1),
     }
-    top = max(per_step, key=per_step.get) if per_step else None
-    roofline = None
-    if top in flop:
-        launches_of_top = 1
-        achieved = flop[top] / (per_step[top] / 1e3) / 1e12
-        peak = peaks["tf_sust"]
-        roofline = {"bound": "tensor", "kernel": top, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": f"{peaks['src']} bf16 sustained",
-                    "ms_per_launch": per_step[top] / launches_of_top,
-                    "note": "fp32 path runs this GEMM on CUDA cores (FFMA); shown against the tensor-pipe peak"
-                    if args.precision == "fp32" else "tcgen05 bf16 x bf16 -> fp32"}
-    elif top is not None:
-        # latency-bound geometry stages: report compulsory bytes against the HBM peak
-        byts = {"fps1": clouds * (12 * 1024 + 8 * 512), "fps2": clouds * (12 * 512 + 8 * 256),
-                "knn1": clouds * (12 * 1024 + 12 * 512 + 8 * 512 * 32), "knn2": clouds * (12 * 512 + 12 * 256 + 8 * 256 * 32)}
-        if top in byts:
-            achieved = byts[top] / (per_step[top] / 1e3) / 1e9
-            roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peaks["hbm"], "unit": "GB/s",
-                        "frac": achieved / peaks["hbm"], "traffic": None, "peak_source": f"{peaks['src']} copy"}
+    tensor_note = ("fp32 path: the GEMMs run on the FFMA pipe; shown against the tensor-pipe peak"
+                   if args.precision == "fp32" else "tcgen05 bf16 x bf16 -> fp32")
+
+    def roof(name):
+        w, bound, nl = work[name]
+        sec = per_step[name] / 1e3
+        if bound == "tensor":
+            ach, peak, unit, src = w / sec / 1e12, peaks["tf_sust"], "TFLOP/s", f"{peaks['src']} bf16 sustained"
+        else:
+            ach, peak, unit, src = w / sec / 1e9, peaks["hbm"], "GB/s", f"{peaks['src']} copy"
+        r = {"bound": bound, "kernel": name, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
+             "traffic": None, "peak_source": src, "ms_per_launch": per_step[name] / nl, "launches_per_step": nl}
+        if bound == "tensor":
+            r["note"] = tensor_note
+        return r
+
+    rooflines = {k: roof(k) for k in work if per_step.get(k, 0) > 0}
+    # dominant kernel = the stage with the largest live time among those with a defined roofline
+    roofline = rooflines[max(rooflines, key=lambda k: per_step[k])] if rooflines else None
 
     # ---- CPU baseline: oracle port on a bounded sample (rank 0, N=1 only)
     cpu_baseline = None
@@ -299,8 +327,12 @@ def run_gpu_arm(args):
                 "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": int(launches),
         "roofline": roofline,
+        "roofline_all": {k: {"bound": v["bound"], "achieved": round(v["achieved"], 3), "unit": v["unit"],
+                             "frac": round(v["frac"], 5)} for k, v in rooflines.items()},
         "cpu_baseline": cpu_baseline,
         "stages_ms_per_step": {k: round(v, 4) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])},
+        other_prec + "_path": ({"value": B * other[1] * world / (other_ms / 1e3), "unit": UNIT,
+                                "ms_per_step": other_ms / other[1], "steps": other[1]} if other else None),
         "gflop_per_pair_reference_count": FLOP_PER_PAIR_REFERENCE / 1e9,
         "wall_s_timed_region": wall,
     }
@@ -313,11 +345,12 @@ def run_gpu_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("PZ_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("PZ_PRECISION", "bf16"), choices=["fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--single-precision", action="store_true", help="skip the short run of the other precision")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

@@ -1,0 +1,60 @@
+"""CPU, world_size 2, gloo: the pair-sharding host logic (partition + the single all_gather of results)."""
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from puzzlenet_b200 import sharding
+
+
+def test_shard_bounds_cover_exactly_once():
+    for n in (0, 1, 7, 64, 496, 513):
+        for world in (1, 2, 3, 8):
+            spans = [sharding.shard_bounds(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        sharding.shard_bounds(4, 2, 2)
+
+
+def test_all_pairs_count():
+    p = sharding.all_pairs(32)
+    assert p.shape == (496, 2) and (p[:, 0] < p[:, 1]).all() and len({tuple(x) for x in p.tolist()}) == 496
+
+
+def _worker(rank, world, port, n_items, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        def score(lo, hi):                       # stand-in for predict5 on pairs [lo, hi): row = f(pair id)
+            ids = torch.arange(lo, hi, dtype=torch.float32)
+            return torch.stack([ids, ids * 2 + 1, torch.full_like(ids, float(rank))], dim=1)
+        out = sharding.run_sharded(n_items, score)
+        q.put((rank, out.tolist()))          # plain lists: tensors through a Queue need the sender alive
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_items", [496, 7, 1])
+def test_run_sharded_world2_gloo(n_items):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() + n_items) % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n_items, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = dict(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    ids = torch.arange(n_items, dtype=torch.float32)
+    for rank in (0, 1):
+        out = torch.tensor(results[rank], dtype=torch.float32).reshape(n_items, 3)
+        assert out.shape == (n_items, 3)
+        assert torch.equal(out[:, 0], ids) and torch.equal(out[:, 1], ids * 2 + 1)
+        lo, hi = sharding.shard_bounds(n_items, 0, 2)
+        assert (out[lo:hi, 2] == 0).all() and (out[hi:, 2] == 1).all()     # rows came from the right rank
