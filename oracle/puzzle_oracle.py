@@ -260,7 +260,10 @@ def se3_transform(g: Tensor, a: Tensor) -> Tensor:
 
 
 def rotation_error_deg(r1: Tensor, r2: Tensor) -> Tensor:
-    """metrics.py:54-70 isotropic_R_error."""
+    """metrics.py:54-70 isotropic_R_error, evaluated in float64: in fp32 the formula acos((tr-1)/2) cannot resolve
+    angles below ~0.03 deg (1 ulp of tr near 3 is 2.4e-7 -> acos(1 - 1.2e-7) = 0.028 deg), which is coarser than
+    the 0.01 deg bound this function is used to check."""
+    r1, r2 = r1.double(), r2.double()
     rr = r2.transpose(1, 2).matmul(r1)
     tr = rr[:, 0, 0] + rr[:, 1, 1] + rr[:, 2, 2]
     return torch.acos(torch.clamp((tr - 1) / 2, -1, 1)) / math.pi * 180

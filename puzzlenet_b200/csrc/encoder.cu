@@ -5,6 +5,8 @@
 // Both encoders of predict5 run as ONE batch of 2B clouds (cloud c uses weight set c / B), so
 // every launch covers 128 clouds at B=64 instead of 64 -- FPS, the latency-bound stage, then
 // occupies 128 of the 148 SMs.
+#include <functional>
+
 #include "pz_common.cuh"
 
 namespace pz {
@@ -286,9 +288,67 @@ __global__ void __launch_bounds__(256) splitk_finish_kernel(const float* __restr
   y[(size_t)m * ldy + n] = s;
 }
 
-// Y = act(A W^T + b) for skinny M (the 5-layer pose MLP, model5_b.py:561-571): split K over CTAs
+// Y[M,N] = act(X[M,K] W[N,K]^T + b) for skinny M (the pose MLP, model5_b.py:561-571: M = B <= 64 rows per block).
+// One CTA per 8 output columns and 64 rows: thread = (row, K-quarter); X and the 8 weight rows stream through
+// shared memory in 128-wide K chunks; the four K-quarters are summed in a fixed order (deterministic).
+constexpr int SK_COLS = 8, SK_ROWS = 64, SK_KC = 128;
+__global__ void __launch_bounds__(256) skinny_linear_kernel(const float* __restrict__ X, int ldx,
+                                                            const float* __restrict__ W, const float* __restrict__ bias,
+                                                            int M, int N, int K, int relu, float* __restrict__ Y, int ldy) {
+  __shared__ float xs[SK_ROWS][SK_KC + 1];
+  __shared__ __align__(16) float ws[SK_KC][SK_COLS];
+  __shared__ float red[4][SK_ROWS][SK_COLS];
+  const int tid = threadIdx.x, r = tid & 63, kq = tid >> 6;
+  const int n0 = blockIdx.x * SK_COLS, m0 = blockIdx.y * SK_ROWS;
+  float acc[SK_COLS];
+#pragma unroll
+  for (int n = 0; n < SK_COLS; ++n) acc[n] = 0.f;
+  for (int k0 = 0; k0 < K; k0 += SK_KC) {
+    __syncthreads();
+    for (int e = tid; e < SK_ROWS * SK_KC; e += 256) {
+      const int rr = e >> 7, kk = e & 127;
+      xs[rr][kk] = (m0 + rr < M && k0 + kk < K) ? X[(size_t)(m0 + rr) * ldx + k0 + kk] : 0.f;
+    }
+    for (int e = tid; e < SK_COLS * SK_KC; e += 256) {
+      const int nn = e >> 7, kk = e & 127;
+      ws[kk][nn] = (n0 + nn < N && k0 + kk < K) ? W[(size_t)(n0 + nn) * K + k0 + kk] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int kk = kq * 32; kk < kq * 32 + 32; ++kk) {
+      const float xv = xs[r][kk];
+      const float4 w0 = *reinterpret_cast<const float4*>(&ws[kk][0]);
+      const float4 w1 = *reinterpret_cast<const float4*>(&ws[kk][4]);
+      acc[0] = fmaf(xv, w0.x, acc[0]); acc[1] = fmaf(xv, w0.y, acc[1]);
+      acc[2] = fmaf(xv, w0.z, acc[2]); acc[3] = fmaf(xv, w0.w, acc[3]);
+      acc[4] = fmaf(xv, w1.x, acc[4]); acc[5] = fmaf(xv, w1.y, acc[5]);
+      acc[6] = fmaf(xv, w1.z, acc[6]); acc[7] = fmaf(xv, w1.w, acc[7]);
+    }
+  }
+#pragma unroll
+  for (int n = 0; n < SK_COLS; ++n) red[kq][r][n] = acc[n];
+  __syncthreads();
+  for (int e = tid; e < SK_ROWS * SK_COLS; e += 256) {
+    const int rr = e >> 3, nn = e & 7;
+    if (m0 + rr < M && n0 + nn < N) {
+      float v = ((red[0][rr][nn] + red[1][rr][nn]) + red[2][rr][nn]) + red[3][rr][nn];
+      if (bias) v += bias[n0 + nn];
+      if (relu) v = fmaxf(v, 0.f);
+      Y[(size_t)(m0 + rr) * ldy + n0 + nn] = v;
+    }
+  }
+}
+
+// Pose-MLP layer: wide layers go through the tiled GEMM with K split over grid.z (16 MB of L2 operand traffic for
+// layer 1 instead of every CTA re-reading all of X); narrow ones (N <= 64) through the one-launch skinny kernel.
 static int skinny_linear(const float* A, int lda, const float* W, const float* bias, int M, int N, int K,
                          int relu, float* Y, int ldy, float* partial, size_t partial_floats, cudaStream_t st) {
+  if (N <= 64) {
+    dim3 grid((N + SK_COLS - 1) / SK_COLS, (M + SK_ROWS - 1) / SK_ROWS);
+    skinny_linear_kernel<<<grid, 256, 0, st>>>(A, lda, W, bias, M, N, K, relu, Y, ldy);
+    PZ_LAUNCH_CHECK();
+    return 0;
+  }
   int splits = 1;
   while (splits < 16 && K / (splits * 2) >= 64 && ((N + 127) / 128) * ((M + 127) / 128) * splits * 2 <= kNumSMs) splits *= 2;
   if (splits == 1 || (size_t)splits * M * N > partial_floats) {
@@ -424,6 +484,70 @@ __global__ void __launch_bounds__(128) head_seg_kernel(const float* __restrict__
 #pragma unroll
   for (int k = 0; k < 32; ++k) {
     const float v = outs[k * 128 + tid];
+    o0 = fmaf(w2s[k], v, o0);
+    o1 = fmaf(w2s[32 + k], v, o1);
+  }
+  float* de = set == 0 ? de_a : de_b;
+  de[((size_t)b * 2 + 0) * NPTS + n] = o0;
+  de[((size_t)b * 2 + 1) * NPTS + n] = o1;
+}
+
+// bf16 path: gbias[set][b][k] = W0_set[k, 0:64] . max_tiles(tilemax[(B + b)*4 + t]) + b0_set[k]
+// (tilemax = per-256-row maxima of the mrpc local features written by the tensor-core epilogue)
+__global__ void __launch_bounds__(64) seg_bias_tiles_kernel(const float* __restrict__ tilemax, int ldmax,
+                                                            const float* w0a, const float* b0a, const float* w0b,
+                                                            const float* b0b, int B, float* __restrict__ gbias) {
+  __shared__ float g[64];
+  const int b = blockIdx.x, set = blockIdx.y, k = threadIdx.x;
+  const float* tm = tilemax + (size_t)(B + b) * 4 * ldmax;      // D6: the mrpc cloud's global feature for BOTH heads
+  g[k] = fmaxf(fmaxf(tm[k], tm[ldmax + k]), fmaxf(tm[2 * ldmax + k], tm[3 * ldmax + k]));
+  __syncthreads();
+  const float* w0 = set == 0 ? w0a : w0b;
+  float v = (set == 0 ? b0a : b0b)[k];
+  for (int i = 0; i < 64; ++i) v = fmaf(w0[k * 128 + i], g[i], v);
+  gbias[((size_t)set * B + b) * 64 + k] = v;
+}
+
+// bf16 path tail of MLP{F,R}pcb: h [P,64] bf16 -> relu(W1 h + b1) (32) -> W2 . + b2 (2), logits as [B,2,1024]
+__global__ void __launch_bounds__(128) head_seg_tail_kernel(const __nv_bfloat16* __restrict__ h, Mlp3W wa, Mlp3W wb, int B,
+                                                            float* __restrict__ de_a, float* __restrict__ de_b) {
+  __shared__ __align__(16) float w1s[32 * 64];
+  __shared__ float w2s[64], b1s[32], b2s[2];
+  const int tid = threadIdx.x;
+  const size_t p = (size_t)blockIdx.x * 128 + tid;
+  const int cloud = (int)(p / NPTS), n = (int)(p - (size_t)cloud * NPTS);
+  const int set = cloud / B, b = cloud - set * B;
+  const Mlp3W& w = set == 0 ? wa : wb;
+  for (int i = tid; i < 32 * 64; i += 128) w1s[i] = w.w1[i];
+  if (tid < 64) w2s[tid] = w.w2[tid];
+  if (tid < 32) b1s[tid] = w.b1[tid];
+  if (tid < 2) b2s[tid] = w.b2[tid];
+  __syncthreads();
+  float a[64];
+  const uint4* src = reinterpret_cast<const uint4*>(h + p * 64);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const uint4 u = src[i];
+    const __nv_bfloat162* p2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __bfloat1622float2(p2[j]);
+      a[i * 8 + 2 * j] = f.x;
+      a[i * 8 + 2 * j + 1] = f.y;
+    }
+  }
+  float o0 = b2s[0], o1 = b2s[1];
+#pragma unroll 4
+  for (int k = 0; k < 32; ++k) {
+    const float4* wr = reinterpret_cast<const float4*>(w1s + k * 64);
+    float v = b1s[k];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float4 ww = wr[i];
+      v = fmaf(ww.x, a[i * 4], v); v = fmaf(ww.y, a[i * 4 + 1], v);
+      v = fmaf(ww.z, a[i * 4 + 2], v); v = fmaf(ww.w, a[i * 4 + 3], v);
+    }
+    v = fmaxf(v, 0.f);
     o0 = fmaf(w2s[k], v, o0);
     o1 = fmaf(w2s[32 + k], v, o1);
   }
@@ -572,9 +696,13 @@ static size_t encoder_scratch_layout(int C, Arena& a, EncoderScratch& s) {
 // Q = W1[:,0:3] c_s (per centroid); the layer-2 GEMM gathers relu(P_j - Q_s) straight into its
 // shared-memory operand and max-pools over the 32 neighbours in its epilogue.
 // ---------------------------------------------------------------------------------------------
+// runs on the caller's stream right after the stem: work that only needs x_feature (the boundary heads of predict5)
+// fills the time the stream would otherwise spend waiting for the stage-1 geometry
+using AfterStem = std::function<int(const float* xfeat, const __nv_bfloat16* xfeat_b)>;
+
 static int encoder_forward_bf16(const PzEncoderWeights* w, int E, int B, const float* xyz, const int64_t* start1,
                                 const int64_t* start2, const PzEncoderOutputs& o, EncoderScratch& s, float* fglob_pair,
-                                const float** xfeat_out, cudaStream_t st) {
+                                const float** xfeat_out, const AfterStem* after_stem, cudaStream_t st) {
   const int C = E * B;
   const PzEncoderWeights& wa = w[0];
   const PzEncoderWeights& wb = w[E - 1];
@@ -655,6 +783,7 @@ static int encoder_forward_bf16(const PzEncoderWeights* w, int E, int B, const f
     PZ_TRY(launch_tc_gemm(g, st));
     prof_mark("sg1_layer1", st);
   }
+  if (after_stem) PZ_TRY((*after_stem)(xfeat, s.xfeat_b));
   PZ_CUDA(cudaStreamWaitEvent(st, ss->join_a, 0));   // kNN of stage 1 (and FPS 1, Q1) are done
   prof_mark("_wait_geometry1", st);
   {
@@ -750,7 +879,8 @@ static int encoder_forward_bf16(const PzEncoderWeights* w, int E, int B, const f
 // fglob_pair: optional [B, E*1024] destination laid out for the pose MLP's concat (model5_b.py:723)
 static int encoder_forward_impl(const PzEncoderWeights* w, int E, int B, const float* xyz, const int64_t* start1,
                                 const int64_t* start2, int precision, const PzEncoderOutputs& o, void* ws,
-                                size_t ws_bytes, float* fglob_pair, const float** xfeat_out, cudaStream_t st) {
+                                size_t ws_bytes, float* fglob_pair, const float** xfeat_out, const AfterStem* after_stem,
+                                cudaStream_t st) {
   PZ_REQUIRE(E == 1 || E == 2, PZ_ERR_ARG, "encoder: E must be 1 or 2 (got %d)", E);
   PZ_REQUIRE(B >= 1, PZ_ERR_ARG, "encoder: B must be >= 1");
   PZ_REQUIRE(precision == PZ_PREC_FP32 || precision == PZ_PREC_BF16, PZ_ERR_ARG, "encoder: unknown precision %d", precision);
@@ -762,7 +892,7 @@ static int encoder_forward_impl(const PzEncoderWeights* w, int E, int B, const f
   encoder_scratch_layout(C, arena, s);
   PZ_REQUIRE(ws && arena.ok(), PZ_ERR_WORKSPACE, "encoder: workspace %zu B < required %zu B", ws_bytes, arena.used);
   if (precision == PZ_PREC_BF16)
-    return encoder_forward_bf16(w, E, B, xyz, start1, start2, o, s, fglob_pair, xfeat_out, st);
+    return encoder_forward_bf16(w, E, B, xyz, start1, start2, o, s, fglob_pair, xfeat_out, after_stem, st);
   const PzEncoderWeights& wa = w[0];
   const PzEncoderWeights& wb = w[E - 1];
   float* xfeat = o.x_feature ? o.x_feature : s.xfeat;
@@ -775,6 +905,7 @@ static int encoder_forward_impl(const PzEncoderWeights* w, int E, int B, const f
   stem_kernel<<<C * NPTS / 128, 128, 0, st>>>(xyz, stem_of(wa), stem_of(wb), B, xfeat, nullptr);
   PZ_LAUNCH_CHECK();
   prof_mark("stem", st);
+  if (after_stem) PZ_TRY((*after_stem)(xfeat, nullptr));
 
   // ---- stage 1: FPS 1024->512, kNN 32, grouped MLP 67->128->128, max over K
   PZ_TRY(launch_fps(xyz, C, NPTS, start1, S1, o.fps1, nullptr, s.nx1, st));
@@ -898,12 +1029,13 @@ extern "C" int pz_encoder_forward(const PzEncoderWeights* weights_host, int E, i
   PZ_REQUIRE(weights_host && xyz && start1 && start2 && outputs_host, PZ_ERR_ARG, "pz_encoder_forward: null pointer");
   prof_begin(as_stream(stream));
   return encoder_forward_impl(weights_host, E, B, xyz, start1, start2, precision, *outputs_host, workspace,
-                              workspace_bytes, nullptr, nullptr, as_stream(stream));
+                              workspace_bytes, nullptr, nullptr, nullptr, as_stream(stream));
 }
 
 namespace {
 struct PredictScratch {
-  float *xyz, *fpair, *h0, *h1, *partial, *local, *gmax, *gbias;
+  float *xyz, *fpair, *h0, *h1, *partial, *local, *gmax, *gbias, *tilemax, *hbias;
+  __nv_bfloat16 *ha, *hb, *hpack;
   int64_t *st1, *st2;
   void* enc;
   size_t enc_bytes, partial_floats;
@@ -920,6 +1052,11 @@ size_t predict_layout(int B, Arena& a, PredictScratch& s) {
   s.local = a.take<float>((size_t)2 * B * NPTS * 64);
   s.gmax = a.take<float>((size_t)B * 64);
   s.gbias = a.take<float>((size_t)2 * B * 64);
+  s.tilemax = a.take<float>((size_t)2 * B * 4 * 128);
+  s.hbias = a.take<float>(2 * 3 * 128);
+  s.ha = a.take<__nv_bfloat16>((size_t)2 * B * NPTS * 64);
+  s.hb = a.take<__nv_bfloat16>((size_t)2 * B * NPTS * 64);
+  s.hpack = a.take<__nv_bfloat16>(2 * 4 * 128 * 64);
   s.enc_bytes = pz_encoder_workspace_bytes(2, B);
   s.enc = a.take<char>(s.enc_bytes);
   return a.used;
@@ -978,9 +1115,81 @@ extern "C" int pz_predict5(const PzEncoderWeights* enc_host, const PzHeadWeights
     eo.attention = attn_all;
     eo.x2 = x2_all;
   }
+  const PzHeadWeights& h = *heads_host;
+  const Mlp3W pre_f = {h.pre_fpc_w[0], h.pre_fpc_b[0], h.pre_fpc_w[1], h.pre_fpc_b[1], h.pre_fpc_w[2], h.pre_fpc_b[2]};
+  const Mlp3W pre_r = {h.pre_rpc_w[0], h.pre_rpc_b[0], h.pre_rpc_w[1], h.pre_rpc_b[1], h.pre_rpc_w[2], h.pre_rpc_b[2]};
+  const Mlp3W seg_f = {h.seg_fpc_w[0], h.seg_fpc_b[0], h.seg_fpc_w[1], h.seg_fpc_b[1], h.seg_fpc_w[2], h.seg_fpc_b[2]};
+  const Mlp3W seg_r = {h.seg_rpc_w[0], h.seg_rpc_b[0], h.seg_rpc_w[1], h.seg_rpc_b[1], h.seg_rpc_w[2], h.seg_rpc_b[2]};
+  const int P = 2 * B * NPTS;
+
+  // boundary heads (model5_b.py:738-754): they only need x_feature, so the encoder runs them right after its stem
+  AfterStem heads_fn = [&](const float* xfeat, const __nv_bfloat16* xfeat_b) -> int {
+    if (precision == PZ_PREC_BF16) {
+      // tensor-core version: 3 x (64->64) + the local half of MLP{F,R}pcb.0 as GEMMs with weights zero-padded to
+      // 128 output channels; the global max-pool over each cloud's 1024 points comes out of the third GEMM's
+      // epilogue as per-tile maxima; the global half of layer 0 is a per-cloud bias (rowbias).
+      PZ_CUDA(cudaMemsetAsync(s.hpack, 0, (size_t)2 * 4 * 128 * 64 * sizeof(__nv_bfloat16), st));
+      PZ_CUDA(cudaMemsetAsync(s.hbias, 0, (size_t)2 * 3 * 128 * sizeof(float), st));
+      PackJobs jobs;
+      int n = 0;
+      for (int e = 0; e < 2; ++e) {
+        const Mlp3W& pre = e == 0 ? pre_f : pre_r;
+        const Mlp3W& seg = e == 0 ? seg_f : seg_r;
+        __nv_bfloat16* wp = s.hpack + (size_t)e * 4 * 128 * 64;
+        float* bp = s.hbias + (size_t)e * 3 * 128;
+        jobs.j[n++] = PackJob{pre.w0, wp, 64, 64, 64, 64, 1};
+        jobs.j[n++] = PackJob{pre.w1, wp + 128 * 64, 64, 64, 64, 64, 1};
+        jobs.j[n++] = PackJob{pre.w2, wp + 2 * 128 * 64, 64, 64, 64, 64, 1};
+        jobs.j[n++] = PackJob{seg.w0 + 64, wp + 3 * 128 * 64, 128, 64, 64, 64, 1};   // local half: columns 64..127
+        jobs.j[n++] = PackJob{pre.b0, bp, 64, 1, 64, 64, 0};
+        jobs.j[n++] = PackJob{pre.b1, bp + 128, 64, 1, 64, 64, 0};
+        jobs.j[n++] = PackJob{pre.b2, bp + 256, 64, 1, 64, 64, 0};
+      }
+      jobs.n = n;
+      pack_weights_kernel<<<dim3(16, n), 256, 0, st>>>(jobs);
+      PZ_LAUNCH_CHECK();
+      auto layer = [&](const __nv_bfloat16* x, int li, int relu, __nv_bfloat16* y, bool with_max, bool seg0) {
+        TcGemm g;
+        g.X = x; g.ldx = 64; g.W[0] = s.hpack + (size_t)li * 128 * 64; g.W[1] = g.W[0] + 4 * 128 * 64; g.ldw = 64;
+        if (!seg0) { g.bias[0] = s.hbias + li * 128; g.bias[1] = s.hbias + 3 * 128 + li * 128; }
+        g.rows_per_wset = B * NPTS; g.M = P; g.Nout = 128; g.K = 64; g.relu = relu; g.n_valid = 64;
+        g.Yb = y; g.ldyb = 64;
+        if (with_max) { g.Ymax = s.tilemax; g.ldmax = 128; }
+        if (seg0) { g.rowbias = s.gbias; g.rb_rows = NPTS; g.rb_ld = 64; }
+        return launch_tc_gemm(g, st);
+      };
+      PZ_TRY(layer(xfeat_b, 0, 1, s.ha, false, false));
+      PZ_TRY(layer(s.ha, 1, 1, s.hb, false, false));
+      PZ_TRY(layer(s.hb, 2, 0, s.ha, true, false));                 // local features (no ReLU) + per-tile maxima
+      seg_bias_tiles_kernel<<<dim3(B, 2), 64, 0, st>>>(s.tilemax, 128, h.seg_fpc_w[0], h.seg_fpc_b[0], h.seg_rpc_w[0],
+                                                       h.seg_rpc_b[0], B, s.gbias);
+      PZ_LAUNCH_CHECK();
+      PZ_TRY(layer(s.ha, 3, 1, s.hb, false, true));                 // relu(W0[:,64:] local + W0[:,:64] g + b0)
+      head_seg_tail_kernel<<<P / 128, 128, 0, st>>>(s.hb, seg_f, seg_r, B, de_fpcb, de_mrpcb);
+      PZ_LAUNCH_CHECK();
+      prof_mark("boundary_heads", st);
+      return 0;
+    }
+    const size_t hl_smem = (3 * 4160 + 64 * 128) * sizeof(float);
+    const size_t hs_smem = (64 * 64 + 32 * 64 + 64 + 32 + 64 + 4 + 64 * 128) * sizeof(float);
+    PZ_CUDA(cudaFuncSetAttribute(head_seg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hs_smem));
+    PZ_CUDA(cudaFuncSetAttribute(head_local_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hl_smem));
+    head_local_kernel<<<P / 128, 128, hl_smem, st>>>(xfeat, pre_f, pre_r, B, s.local);
+    PZ_LAUNCH_CHECK();
+    // D6: BOTH heads use the max-pool of the *mrpc* local features (model5_b.py:741-744)
+    rowblock_max_kernel<<<dim3(1, B), 256, 0, st>>>(s.local + (size_t)B * NPTS * 64, 64, NPTS, 64, B, B, 0, s.gmax, 64);
+    PZ_LAUNCH_CHECK();
+    seg_bias_kernel<<<dim3(B, 2), 64, 0, st>>>(s.gmax, h.seg_fpc_w[0], h.seg_fpc_b[0], h.seg_rpc_w[0], h.seg_rpc_b[0], B, s.gbias);
+    PZ_LAUNCH_CHECK();
+    head_seg_kernel<<<P / 128, 128, hs_smem, st>>>(s.local, seg_f, seg_r, s.gbias, B, de_fpcb, de_mrpcb);
+    PZ_LAUNCH_CHECK();
+    prof_mark("boundary_heads", st);
+    return 0;
+  };
+
   const float* xfeat = nullptr;
   PZ_TRY(encoder_forward_impl(enc_host, 2, B, s.xyz, s.st1, s.st2, precision, eo, s.enc, s.enc_bytes, s.fpair,
-                              &xfeat, st));
+                              &xfeat, &heads_fn, st));
   if (need) {
     const size_t ab = (size_t)B * LATT * LATT * sizeof(float), xb = (size_t)B * S2 * 3 * sizeof(float);
     PZ_CUDA(cudaMemcpyAsync(attention_fpc, attn_all, ab, cudaMemcpyDeviceToDevice, st));
@@ -988,34 +1197,13 @@ extern "C" int pz_predict5(const PzEncoderWeights* enc_host, const PzHeadWeights
     PZ_CUDA(cudaMemcpyAsync(x2_fpc, x2_all, xb, cudaMemcpyDeviceToDevice, st));
     PZ_CUDA(cudaMemcpyAsync(x2_mrpc, x2_all + (size_t)B * S2 * 3, xb, cudaMemcpyDeviceToDevice, st));
   }
-  const PzHeadWeights& h = *heads_host;
-  // pose MLP on cat(ffpc, fmrpc): 2048-1024-512-512-256-6 (model5_b.py:723-725)
+  // pose MLP on cat(ffpc, fmrpc): 2048-1024-512-512-256-6 (model5_b.py:723-725), fp32 in both paths
   PZ_TRY(skinny_linear(s.fpair, 2048, h.tf_w[0], h.tf_b[0], B, 1024, 2048, 1, s.h0, 1024, s.partial, s.partial_floats, st));
   PZ_TRY(skinny_linear(s.h0, 1024, h.tf_w[1], h.tf_b[1], B, 512, 1024, 1, s.h1, 512, s.partial, s.partial_floats, st));
   PZ_TRY(skinny_linear(s.h1, 512, h.tf_w[2], h.tf_b[2], B, 512, 512, 1, s.h0, 512, s.partial, s.partial_floats, st));
   PZ_TRY(skinny_linear(s.h0, 512, h.tf_w[3], h.tf_b[3], B, 256, 512, 1, s.h1, 256, s.partial, s.partial_floats, st));
   PZ_TRY(skinny_linear(s.h1, 256, h.tf_w[4], h.tf_b[4], B, 6, 256, 0, out6, 6, s.partial, s.partial_floats, st));
   prof_mark("pose_mlp", st);
-
-  // boundary heads (model5_b.py:738-754)
-  const size_t hl_smem = (3 * 4160 + 64 * 128) * sizeof(float);
-  const size_t hs_smem = (64 * 64 + 32 * 64 + 64 + 32 + 64 + 4 + 64 * 128) * sizeof(float);
-  PZ_CUDA(cudaFuncSetAttribute(head_seg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hs_smem));
-  PZ_CUDA(cudaFuncSetAttribute(head_local_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hl_smem));
-  Mlp3W pre_f = {h.pre_fpc_w[0], h.pre_fpc_b[0], h.pre_fpc_w[1], h.pre_fpc_b[1], h.pre_fpc_w[2], h.pre_fpc_b[2]};
-  Mlp3W pre_r = {h.pre_rpc_w[0], h.pre_rpc_b[0], h.pre_rpc_w[1], h.pre_rpc_b[1], h.pre_rpc_w[2], h.pre_rpc_b[2]};
-  head_local_kernel<<<2 * B * NPTS / 128, 128, hl_smem, st>>>(xfeat, pre_f, pre_r, B, s.local);
-  PZ_LAUNCH_CHECK();
-  // D6: BOTH heads use the max-pool of the *mrpc* local features (model5_b.py:741-744)
-  rowblock_max_kernel<<<dim3(1, B), 256, 0, st>>>(s.local + (size_t)B * NPTS * 64, 64, NPTS, 64, B, B, 0, s.gmax, 64);
-  PZ_LAUNCH_CHECK();
-  seg_bias_kernel<<<dim3(B, 2), 64, 0, st>>>(s.gmax, h.seg_fpc_w[0], h.seg_fpc_b[0], h.seg_rpc_w[0], h.seg_rpc_b[0], B, s.gbias);
-  PZ_LAUNCH_CHECK();
-  Mlp3W seg_f = {h.seg_fpc_w[0], h.seg_fpc_b[0], h.seg_fpc_w[1], h.seg_fpc_b[1], h.seg_fpc_w[2], h.seg_fpc_b[2]};
-  Mlp3W seg_r = {h.seg_rpc_w[0], h.seg_rpc_b[0], h.seg_rpc_w[1], h.seg_rpc_b[1], h.seg_rpc_w[2], h.seg_rpc_b[2]};
-  head_seg_kernel<<<2 * B * NPTS / 128, 128, hs_smem, st>>>(s.local, seg_f, seg_r, s.gbias, B, de_fpcb, de_mrpcb);
-  PZ_LAUNCH_CHECK();
-  prof_mark("boundary_heads", st);
   return 0;
 }
 

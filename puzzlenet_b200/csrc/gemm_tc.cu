@@ -241,7 +241,9 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcGemm g) {
 #pragma unroll 1
       for (int chb = 0; chb < NCHB; ++chb) {
         const int ch = (cht * NCHB + chb) * 128 + warp * 32 + lane;
-        const float bv = bias ? bias[ch] : 0.f;
+        const bool ch_ok = g.n_valid <= 0 || ch < g.n_valid;
+        const float bv = (bias && ch_ok) ? bias[ch] : 0.f;
+        float tmax = -INFINITY;
         float w1x = 0.f, w1y = 0.f, w1z = 0.f;
         if (g.xyz) {
           const float* wp = g.W1x[wset] + (size_t)ch * g.ldw1x;
@@ -257,6 +259,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcGemm g) {
             // all residual loads of the chunk are issued before the first dependent use / store, so
             // their latency overlaps (one exposed L2 round trip per 32 rows instead of per row)
             const size_t rbase = (size_t)row0 + c32 * 32;
+            if (!ch_ok) continue;                  // padded channel: nothing to store
+            const float rbv = g.rowbias ? g.rowbias[(rbase / g.rb_rows) * g.rb_ld + ch] : 0.f;
             float res[32];
             if (g.Rf) {
 #pragma unroll
@@ -267,7 +271,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcGemm g) {
             }
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-              float x = v[i] + bv;
+              float x = v[i] + bv + rbv;
               if (g.xyz) {
                 const float* p = sxyz + (c32 * 32 + i) * 3;     // tile's coordinates staged in smem
                 x = fmaf(w1x, p[0], fmaf(w1y, p[1], fmaf(w1z, p[2], x)));
@@ -275,6 +279,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcGemm g) {
               if (g.relu) x = fmaxf(x, 0.f);
               if (g.Rf || g.Rb) x += res[i];
               v[i] = x;
+              tmax = fmaxf(tmax, x);
             }
             if (g.YT && (cht * NCHB + chb) * 128 >= g.t_ch_begin) {
               // transposed bf16 store: this thread's 32 consecutive rows are contiguous in YT
@@ -315,6 +320,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcGemm g) {
             }
           }
         }
+        if (g.epi == 0 && g.Ymax && ch_ok) g.Ymax[(size_t)rt * g.ldmax + ch] = tmax;
         if (g.epi == 2) {  // max over all ROWS rows of the tile (one cloud)
           float x = cmax + bv;
           if (g.relu) x = fmaxf(x, 0.f);

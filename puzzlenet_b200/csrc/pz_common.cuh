@@ -137,6 +137,11 @@ struct TcGemm {
   int ldrf = 0;
   const __nv_bfloat16* Rb = nullptr;
   int ldrb = 0;
+  int n_valid = 0;                                 // >0: only channels < n_valid exist (weights zero-padded to Nout)
+  const float* rowbias = nullptr;                  // epi 0: + rowbias[(row / rb_rows) * rb_ld + ch] before the ReLU
+  int rb_rows = 0, rb_ld = 0;
+  float* Ymax = nullptr;                           // epi 0: also Ymax[tile * ldmax + ch] = max over the tile's rows
+  int ldmax = 0;
   __nv_bfloat16* YT = nullptr;                     // epi 0: channels >= t_ch_begin are stored TRANSPOSED per row tile:
   int t_ch_begin = 0;                              //   YT[(tile*(Nout-t_ch_begin) + ch-t_ch_begin)*ROWS + row_in_tile]
   const float* xyz = nullptr;                      // epi 0 only: y += W1x[ch,0:3] . xyz[row]  (layer 1 of a grouped MLP)
