@@ -5,6 +5,8 @@
 // Both encoders of predict5 run as ONE batch of 2B clouds (cloud c uses weight set c / B), so
 // every launch covers 128 clouds at B=64 instead of 64 -- FPS, the latency-bound stage, then
 // occupies 128 of the 148 SMs.
+#include <stdlib.h>
+
 #include <functional>
 
 #include "pz_common.cuh"
@@ -499,8 +501,10 @@ __global__ void __launch_bounds__(64) seg_bias_tiles_kernel(const float* __restr
                                                             const float* b0b, int B, float* __restrict__ gbias) {
   __shared__ float g[64];
   const int b = blockIdx.x, set = blockIdx.y, k = threadIdx.x;
-  const float* tm = tilemax + (size_t)(B + b) * 4 * ldmax;      // D6: the mrpc cloud's global feature for BOTH heads
-  g[k] = fmaxf(fmaxf(tm[k], tm[ldmax + k]), fmaxf(tm[2 * ldmax + k], tm[3 * ldmax + k]));
+  const float* tm = tilemax + (size_t)(B + b) * 8 * ldmax;      // D6: the mrpc cloud's global feature for BOTH heads
+  float m = tm[k];                                               // 4 tiles x 2 epilogue halves per cloud
+  for (int t = 1; t < 8; ++t) m = fmaxf(m, tm[(size_t)t * ldmax + k]);
+  g[k] = m;
   __syncthreads();
   const float* w0 = set == 0 ? w0a : w0b;
   float v = (set == 0 ? b0a : b0b)[k];
@@ -751,7 +755,8 @@ static int encoder_forward_bf16(const PzEncoderWeights* w, int E, int B, const f
   // it runs on the side stream while the feature chain (stem, layer-1 GEMM) runs on the caller's stream.
   SideStream* ss = nullptr;
   PZ_TRY(side_stream(&ss));
-  cudaStream_t sg = ss->stream;
+  static const bool serial = getenv("PZ_NO_SIDE_STREAM") != nullptr;   // profiling aid: clean per-stage times
+  cudaStream_t sg = serial ? st : ss->stream;
   PZ_CUDA(cudaEventRecord(ss->fork, st));
   PZ_CUDA(cudaStreamWaitEvent(sg, ss->fork, 0));
   prof_mark("_side_begin", sg, 1);
@@ -1052,7 +1057,7 @@ size_t predict_layout(int B, Arena& a, PredictScratch& s) {
   s.local = a.take<float>((size_t)2 * B * NPTS * 64);
   s.gmax = a.take<float>((size_t)B * 64);
   s.gbias = a.take<float>((size_t)2 * B * 64);
-  s.tilemax = a.take<float>((size_t)2 * B * 4 * 128);
+  s.tilemax = a.take<float>((size_t)2 * B * 8 * 128);
   s.hbias = a.take<float>(2 * 3 * 128);
   s.ha = a.take<__nv_bfloat16>((size_t)2 * B * NPTS * 64);
   s.hb = a.take<__nv_bfloat16>((size_t)2 * B * NPTS * 64);

@@ -28,9 +28,7 @@
 namespace pz {
 
 namespace tc {
-constexpr int EPI_WARPS = 4, PROD_WARPS = 8;
-constexpr int THREADS = (EPI_WARPS + 1 + PROD_WARPS) * 32;  // 416
-constexpr int PROD_THREADS = PROD_WARPS * 32;
+constexpr int THREADS = 13 * 32;  // 416: epilogue + MMA + producer warps (split depends on the operand mode)
 }  // namespace tc
 
 using namespace tc;
@@ -53,10 +51,15 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcGemm g) {
   const uint32_t full_bar = bars_base, empty_bar = bars_base + 8 * NST;
   const uint32_t accf_bar = bars_base + 16 * NST, acce_bar = accf_bar + 16;
   const uint32_t tmem_slot = acce_bar + 16;
+  const uint32_t qstage_base = tmem_slot + 16;   // GATHER: NST x [ROWS/32 groups][64] fp32 Q tiles (16-byte aligned)
   __shared__ float sxyz[ROWS * 3];
   uint8_t* smem_gen = tc_smem_raw + (smem_base - smem_u32(tc_smem_raw));   // generic pointer to smem_base
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // Role split.  Plain operands (cp.async) need few producer threads but a heavy store epilogue, so two
+  // epilogue warps share each TMEM lane quarter (a warp may only touch lanes 32*(warp%4)..+31) and take
+  // alternate 32-column chunks; the gather mode computes its operand and keeps 8 producer warps.
+  constexpr int EPI_WARPS = GATHER ? 4 : 8, PROD_WARPS = 12 - EPI_WARPS, PROD_THREADS = PROD_WARPS * 32;
 
   // ---- tile partition: CTAs are split between the weight sets so a CTA never switches weights
   const int nsets = (g.rows_per_wset > 0 && g.M > g.rows_per_wset) ? 2 : 1;
@@ -73,7 +76,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcGemm g) {
 
   if (tid == 0) {
     for (int s = 0; s < NST; ++s) {
-      mbar_init(full_bar + 8 * s, GATHER ? PROD_THREADS / 2 : PROD_THREADS);
+      mbar_init(full_bar + 8 * s, 128);   // gather: one 128-thread producer group per stage; plain: 4 producer warps
       mbar_init(empty_bar + 8 * s, 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -105,65 +108,85 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcGemm g) {
   if (warp >= EPI_WARPS + 1) {
     // =========================================================== producers
     const int pt = tid - (EPI_WARPS + 1) * 32;
+    if (GATHER) {
+      // X[r, k] = relu(P[rows[r], k] - Q[(row0+r)/32, k]).  The 256 producer threads form two groups that own
+      // alternate stages.  A group gathers the raw bf16 rows of its NEXT stage with cp.async straight into the
+      // swizzled operand slot (plus the stage's Q tile), and only then transforms its CURRENT stage in place
+      // (each thread rewrites the 16-byte chunks it copied itself), so a whole stage of gathers per group is
+      // always in flight while the other one is being converted -- the L2 round trip is off the critical path.
+      constexpr int GCH = ROWS * 8 / 128;                  // 16-byte chunks per thread per stage
+      constexpr int QCH = (ROWS / 32) * 16;                // 16-byte chunks of the stage's Q tile ([groups][64] fp32)
+      const int grp = pt >> 7, gt = pt & 127, gc = gt & 7, r0 = gt >> 3;
+      int my_tiles = 0;
+      for (int t = tile_begin + rank_in_set; t < tile_begin + tiles_per_set; t += step) ++my_tiles;
+      const int jobs = my_tiles * kblocks;
+      auto issue = [&](int j) {
+        const int ti = j / kblocks, kb = j - ti * kblocks;
+        const int row0 = (tile_begin + rank_in_set + ti * step) * ROWS;      // ch_tiles == 1 in gather mode
+        const uint32_t s = (uint32_t)j % NST, ph = ((uint32_t)j / NST) & 1;
+        mbar_wait(empty_bar + 8 * s, ph ^ 1);
+        const uint32_t st_addr = stages_base + s * STAGE_BYTES;
+        int src[GCH];
+#pragma unroll
+        for (int i = 0; i < GCH; ++i) src[i] = g.rows[row0 + r0 + i * 16];
+#pragma unroll
+        for (int i = 0; i < GCH; ++i)
+          cp_async16(st_addr + sw128(r0 + i * 16, gc), g.X + (size_t)src[i] * g.ldx + kb * KB + gc * 8);
+        if (gt < QCH)
+          cp_async16(qstage_base + s * (QCH * 16) + gt * 16,
+                     g.Q + (size_t)((row0 >> 5) + (gt >> 4)) * g.K + kb * KB + (gt & 15) * 4);
+        cp_async_commit();
+      };
+      int j = grp;
+      if (j < jobs) issue(j);
+      for (; j < jobs; j += 2) {
+        if (j + 2 < jobs) {
+          issue(j + 2);
+          cp_async_wait<1>();
+        } else {
+          cp_async_wait<0>();
+        }
+        // the Q tile was copied by other threads of the group
+        asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory");
+        const uint32_t s = (uint32_t)j % NST;
+        uint8_t* st_gen = smem_gen + (stages_base + s * STAGE_BYTES - smem_base);
+        const float* qs = reinterpret_cast<const float*>(smem_gen + (qstage_base + s * (QCH * 16) - smem_base));
+#pragma unroll
+        for (int i = 0; i < GCH; ++i) {
+          const int r = r0 + i * 16;
+          uint4* slot = reinterpret_cast<uint4*>(st_gen + sw128(r, gc));
+          const uint4 pv = *slot;
+          const float4 q0 = *reinterpret_cast<const float4*>(qs + (r >> 5) * 64 + gc * 8);
+          const float4 q1 = *reinterpret_cast<const float4*>(qs + (r >> 5) * 64 + gc * 8 + 4);
+          const __nv_bfloat162* p2 = reinterpret_cast<const __nv_bfloat162*>(&pv);
+          const float2 a = __bfloat1622float2(p2[0]), b = __bfloat1622float2(p2[1]);
+          const float2 cc = __bfloat1622float2(p2[2]), d = __bfloat1622float2(p2[3]);
+          uint4 o;
+          __nv_bfloat162 t0 = __floats2bfloat162_rn(fmaxf(a.x - q0.x, 0.f), fmaxf(a.y - q0.y, 0.f));
+          __nv_bfloat162 t1 = __floats2bfloat162_rn(fmaxf(b.x - q0.z, 0.f), fmaxf(b.y - q0.w, 0.f));
+          __nv_bfloat162 t2 = __floats2bfloat162_rn(fmaxf(cc.x - q1.x, 0.f), fmaxf(cc.y - q1.y, 0.f));
+          __nv_bfloat162 t3 = __floats2bfloat162_rn(fmaxf(d.x - q1.z, 0.f), fmaxf(d.y - q1.w, 0.f));
+          o.x = *reinterpret_cast<uint32_t*>(&t0); o.y = *reinterpret_cast<uint32_t*>(&t1);
+          o.z = *reinterpret_cast<uint32_t*>(&t2); o.w = *reinterpret_cast<uint32_t*>(&t3);
+          *slot = o;
+        }
+        fence_proxy_async();
+        mbar_arrive(full_bar + 8 * s);
+        // a second group barrier keeps a fast thread from overwriting the Q tile of a slot that slower
+        // threads of the group are still reading (slot s is reused by this group's job j + 2*NST at the earliest,
+        // which is issued two iterations later -- so one barrier per iteration is enough)
+      }
+    } else {
     uint32_t issued = 0, arrived = 0;
     for (int t = tile_begin + rank_in_set; t < tile_begin + tiles_per_set; t += step) {
       const int cht = t % ch_tiles, rt = t / ch_tiles;
       const int row0 = rt * ROWS;
-      // GATHER: the 256 producer threads form two groups that fill alternate stages, so each group has two
-      // stage-times to hide the dependent index -> row -> operand latency chain; a thread keeps the source
-      // rows of its chunks for the whole tile and issues its operand loads in independent batches of 8.
-      constexpr int GCH = GATHER ? ROWS * 8 / (PROD_THREADS / 2) : 1;   // 16-byte chunks per thread per stage
-      const int grp = pt >> 7, gt = pt & 127, gc = gt & 7;
-      int src[GCH];
-      if (GATHER) {
-#pragma unroll
-        for (int i = 0; i < GCH; ++i) src[i] = g.rows[row0 + (gt >> 3) + i * 16];
-      }
       for (int kb = 0; kb < kblocks; ++kb) {
-        const uint32_t s = issued % NST, ph = (issued / NST) & 1;
-        if (GATHER && (int)(issued & 1) != grp) {   // the other group's stage
-          ++issued;
-          ++arrived;
-          continue;
-        }
-        mbar_wait(empty_bar + 8 * s, ph ^ 1);
-        const uint32_t st_addr = stages_base + s * STAGE_BYTES;
-        uint8_t* st_gen = smem_gen + (st_addr - smem_base);
-        if (GATHER) {
-          // X[r, k] = relu(P[rows[r], k] - Q[(row0+r)/32, k])  -> bf16, swizzled
-#pragma unroll
-          for (int b0 = 0; b0 < GCH; b0 += 8) {
-            uint4 pv[8];
-            float4 q0[8], q1[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int r = (gt >> 3) + (b0 + i) * 16;
-              pv[i] = *reinterpret_cast<const uint4*>(g.X + (size_t)src[b0 + i] * g.ldx + kb * KB + gc * 8);
-              const float4* qp = reinterpret_cast<const float4*>(g.Q + (size_t)((row0 + r) >> 5) * g.K + kb * KB + gc * 8);
-              q0[i] = qp[0];
-              q1[i] = qp[1];
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int r = (gt >> 3) + (b0 + i) * 16;
-              const __nv_bfloat162* p2 = reinterpret_cast<const __nv_bfloat162*>(&pv[i]);
-              const float2 a = __bfloat1622float2(p2[0]), b = __bfloat1622float2(p2[1]);
-              const float2 cc = __bfloat1622float2(p2[2]), d = __bfloat1622float2(p2[3]);
-              uint4 o;
-              __nv_bfloat162 t0 = __floats2bfloat162_rn(fmaxf(a.x - q0[i].x, 0.f), fmaxf(a.y - q0[i].y, 0.f));
-              __nv_bfloat162 t1 = __floats2bfloat162_rn(fmaxf(b.x - q0[i].z, 0.f), fmaxf(b.y - q0[i].w, 0.f));
-              __nv_bfloat162 t2 = __floats2bfloat162_rn(fmaxf(cc.x - q1[i].x, 0.f), fmaxf(cc.y - q1[i].y, 0.f));
-              __nv_bfloat162 t3 = __floats2bfloat162_rn(fmaxf(d.x - q1[i].z, 0.f), fmaxf(d.y - q1[i].w, 0.f));
-              o.x = *reinterpret_cast<uint32_t*>(&t0); o.y = *reinterpret_cast<uint32_t*>(&t1);
-              o.z = *reinterpret_cast<uint32_t*>(&t2); o.w = *reinterpret_cast<uint32_t*>(&t3);
-              *reinterpret_cast<uint4*>(st_gen + STAGE_W_BYTES + sw128(r, gc)) = o;
-            }
-          }
-          fence_proxy_async();
-          mbar_arrive(full_bar + 8 * s);
-          ++issued;
-          ++arrived;
-        } else {
+        const uint32_t s = issued % NST;
+        {
+          const uint32_t ph = (issued / NST) & 1;
+          mbar_wait(empty_bar + 8 * s, ph ^ 1);
+          const uint32_t st_addr = stages_base + s * STAGE_BYTES;
           if (!RESIDENT) {
             for (int id = pt; id < NCHB * 128 * 8; id += PROD_THREADS) {
               const int c = id & 7, r = (id >> 3) & 127, chb = id >> 10;
@@ -186,13 +209,12 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcGemm g) {
         }
       }
     }
-    if (!GATHER) {
-      cp_async_wait<0>();
-      fence_proxy_async();
-      while (arrived < issued) {
-        mbar_arrive(full_bar + 8 * (arrived % NST));
-        ++arrived;
-      }
+    cp_async_wait<0>();
+    fence_proxy_async();
+    while (arrived < issued) {
+      mbar_arrive(full_bar + 8 * (arrived % NST));
+      ++arrived;
+    }
     }
   } else if (warp == EPI_WARPS) {
     // =========================================================== MMA issuer (one thread)
@@ -226,21 +248,23 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcGemm g) {
   } else {
     // =========================================================== epilogue (warps 0-3, TMEM lane = channel)
     uint32_t tc_count = 0;
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    const int quarter = warp & 3, half = warp >> 2;            // half is 0 when there are only 4 epilogue warps
+    constexpr int HALVES = EPI_WARPS / 4;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     for (int t = tile_begin + rank_in_set; t < tile_begin + tiles_per_set; t += step, ++tc_count) {
       const int cht = t % ch_tiles, rt = t / ch_tiles;
       const int row0 = rt * ROWS;
       const uint32_t buf = tc_count & 1, aph = (tc_count >> 1) & 1;
       if (g.xyz) {   // coordinates of the tile's rows -> smem (coalesced), read back as broadcasts
-        asm volatile("bar.sync 1, 128;" ::: "memory");            // previous tile's readers are done
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");   // previous tile's readers are done
         for (int i = tid; i < ROWS * 3; i += EPI_WARPS * 32) sxyz[i] = g.xyz[(size_t)row0 * 3 + i];
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
       }
       mbar_wait(accf_bar + 8 * buf, aph);
       tc_fence_after();
 #pragma unroll 1
       for (int chb = 0; chb < NCHB; ++chb) {
-        const int ch = (cht * NCHB + chb) * 128 + warp * 32 + lane;
+        const int ch = (cht * NCHB + chb) * 128 + quarter * 32 + lane;
         const bool ch_ok = g.n_valid <= 0 || ch < g.n_valid;
         const float bv = (bias && ch_ok) ? bias[ch] : 0.f;
         float tmax = -INFINITY;
@@ -251,8 +275,11 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcGemm g) {
         }
         const uint32_t t_addr = tmem_base + lane_base + (buf * NCHB + chb) * ROWS;
         float cmax = -INFINITY;
+        // store epilogue: the two warps of a lane quarter take alternate chunks; max epilogues run on half 0 only
+        const int c_begin = g.epi == 0 ? half : (half == 0 ? 0 : ROWS / 32);
+        const int c_step = g.epi == 0 ? HALVES : 1;
 #pragma unroll 1
-        for (int c32 = 0; c32 < ROWS / 32; ++c32) {
+        for (int c32 = c_begin; c32 < ROWS / 32; c32 += c_step) {
           float v[32];
           tmem_ld32(t_addr + c32 * 32, v);
           if (g.epi == 0) {
@@ -263,11 +290,13 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcGemm g) {
             const float rbv = g.rowbias ? g.rowbias[(rbase / g.rb_rows) * g.rb_ld + ch] : 0.f;
             float res[32];
             if (g.Rf) {
+              const float* rp = g.Rf + rbase * g.ldrf + ch;
 #pragma unroll
-              for (int i = 0; i < 32; ++i) res[i] = g.Rf[(rbase + i) * g.ldrf + ch];
+              for (int i = 0; i < 32; ++i, rp += g.ldrf) res[i] = *rp;
             } else if (g.Rb) {
+              const __nv_bfloat16* rp = g.Rb + rbase * g.ldrb + ch;
 #pragma unroll
-              for (int i = 0; i < 32; ++i) res[i] = __bfloat162float(g.Rb[(rbase + i) * g.ldrb + ch]);
+              for (int i = 0; i < 32; ++i, rp += g.ldrb) res[i] = __bfloat162float(*rp);
             }
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
@@ -298,12 +327,14 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcGemm g) {
               continue;
             }
             if (g.Yf) {
+              float* yp = g.Yf + rbase * g.ldyf + ch;
 #pragma unroll
-              for (int i = 0; i < 32; ++i) g.Yf[(rbase + i) * g.ldyf + ch] = v[i];
+              for (int i = 0; i < 32; ++i, yp += g.ldyf) *yp = v[i];
             }
             if (g.Yb) {
+              __nv_bfloat16* yp = g.Yb + rbase * g.ldyb + ch;
 #pragma unroll
-              for (int i = 0; i < 32; ++i) g.Yb[(rbase + i) * g.ldyb + ch] = __float2bfloat16_rn(v[i]);
+              for (int i = 0; i < 32; ++i, yp += g.ldyb) *yp = __float2bfloat16_rn(v[i]);
             }
           } else {
             float m = v[0];
@@ -320,8 +351,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcGemm g) {
             }
           }
         }
-        if (g.epi == 0 && g.Ymax && ch_ok) g.Ymax[(size_t)rt * g.ldmax + ch] = tmax;
-        if (g.epi == 2) {  // max over all ROWS rows of the tile (one cloud)
+        if (g.epi == 0 && g.Ymax && ch_ok) g.Ymax[((size_t)rt * 2 + half) * g.ldmax + ch] = tmax;   // 2 partials per tile
+        if (g.epi == 2 && half == 0) {  // max over all ROWS rows of the tile (one cloud)
           float x = cmax + bv;
           if (g.relu) x = fmaxf(x, 0.f);
           if (g.Yf) g.Yf[(size_t)rt * g.ldyf + ch] = x;
@@ -344,7 +375,7 @@ static int tc_launch(const TcGemm& g, cudaStream_t st) {
   const int kblocks = g.K / KB;
   const size_t resident = RESIDENT ? (size_t)NCHB * kblocks * 128 * 128 : 0;
   const size_t stage = (RESIDENT ? 0 : (size_t)NCHB * 128 * 128) + (size_t)ROWS * 128;
-  const size_t smem = 1024 + resident + NST * stage + 8 * (2 * NST + 4) + 16;
+  const size_t smem = 1024 + resident + NST * stage + 8 * (2 * NST + 4) + 32 + (GATHER ? (size_t)NST * (ROWS / 32) * 256 : 0);
   PZ_REQUIRE(smem <= 227 * 1024, PZ_ERR_UNSUPPORTED, "tc_gemm: needs %zu B of shared memory (K=%d too large for a resident weight)", smem, g.K);
   auto kern = tc_gemm_kernel<ROWS, NCHB, RESIDENT, GATHER, NST>;
   PZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
