@@ -494,22 +494,29 @@ __global__ void __launch_bounds__(128) head_seg_kernel(const float* __restrict__
   de[((size_t)b * 2 + 1) * NPTS + n] = o1;
 }
 
-// bf16 path: gbias[set][b][k] = W0_set[k, 0:64] . max_tiles(tilemax[(B + b)*4 + t]) + b0_set[k]
-// (tilemax = per-256-row maxima of the mrpc local features written by the tensor-core epilogue)
-__global__ void __launch_bounds__(64) seg_bias_tiles_kernel(const float* __restrict__ tilemax, int ldmax,
-                                                            const float* w0a, const float* b0a, const float* w0b,
-                                                            const float* b0b, int B, float* __restrict__ gbias) {
+// bf16 path: g[b] = max over the 1024 points of mrpc cloud b of its local features (bf16 [*,64]), then
+// gbias[set][b][k] = W0_set[k, 0:64] . g[b] + b0_set[k] for both heads (D6: the mrpc global feature feeds BOTH).
+__global__ void __launch_bounds__(256) seg_bias_cloudmax_kernel(const __nv_bfloat16* __restrict__ local_mrpc,
+                                                                const float* w0a, const float* b0a, const float* w0b,
+                                                                const float* b0b, int B, float* __restrict__ gbias) {
+  __shared__ float part[4][64];
   __shared__ float g[64];
-  const int b = blockIdx.x, set = blockIdx.y, k = threadIdx.x;
-  const float* tm = tilemax + (size_t)(B + b) * 8 * ldmax;      // D6: the mrpc cloud's global feature for BOTH heads
-  float m = tm[k];                                               // 4 tiles x 2 epilogue halves per cloud
-  for (int t = 1; t < 8; ++t) m = fmaxf(m, tm[(size_t)t * ldmax + k]);
-  g[k] = m;
+  const int b = blockIdx.x, t = threadIdx.x, k = t & 63, q = t >> 6;
+  const __nv_bfloat16* p = local_mrpc + ((size_t)b * NPTS + q * 256) * 64 + k;
+  float m = -INFINITY;
+#pragma unroll 8
+  for (int r = 0; r < 256; ++r) m = fmaxf(m, __bfloat162float(p[(size_t)r * 64]));
+  part[q][k] = m;
   __syncthreads();
-  const float* w0 = set == 0 ? w0a : w0b;
-  float v = (set == 0 ? b0a : b0b)[k];
-  for (int i = 0; i < 64; ++i) v = fmaf(w0[k * 128 + i], g[i], v);
-  gbias[((size_t)set * B + b) * 64 + k] = v;
+  if (t < 64) g[t] = fmaxf(fmaxf(part[0][t], part[1][t]), fmaxf(part[2][t], part[3][t]));
+  __syncthreads();
+  if (t < 128) {
+    const int set = t >> 6;
+    const float* w0 = set == 0 ? w0a : w0b;
+    float v = (set == 0 ? b0a : b0b)[k];
+    for (int i = 0; i < 64; ++i) v = fmaf(w0[k * 128 + i], g[i], v);
+    gbias[((size_t)set * B + b) * 64 + k] = v;
+  }
 }
 
 // bf16 path tail of MLP{F,R}pcb: h [P,64] bf16 -> relu(W1 h + b1) (32) -> W2 . + b2 (2), logits as [B,2,1024]
@@ -785,7 +792,7 @@ static int encoder_forward_bf16(const PzEncoderWeights* w, int E, int B, const f
     g.X = s.xfeat_b; g.ldx = D0; g.W[0] = wpa + WP_W3F; g.W[1] = wpb + WP_W3F; g.ldw = D0;
     g.bias[0] = wa.mlp3_b; g.bias[1] = wb.mlp3_b; g.rows_per_wset = B * NPTS; g.M = C * NPTS; g.Nout = C1A; g.K = D0;
     g.Yb = s.P1; g.ldyb = C1A; g.xyz = xyz; g.W1x[0] = wa.mlp3_w; g.W1x[1] = wb.mlp3_w; g.ldw1x = 3 + D0;
-    PZ_TRY(launch_tc_gemm(g, st));
+    PZ_TRY(launch_tc_rowgemm(g, st));
     prof_mark("sg1_layer1", st);
   }
   if (after_stem) PZ_TRY((*after_stem)(xfeat, s.xfeat_b));
@@ -804,7 +811,7 @@ static int encoder_forward_bf16(const PzEncoderWeights* w, int E, int B, const f
     g.X = s.f1f_b; g.ldx = C1B; g.W[0] = wpa + WP_W5F; g.W[1] = wpb + WP_W5F; g.ldw = C1B;
     g.bias[0] = wa.mlp5_b; g.bias[1] = wb.mlp5_b; g.rows_per_wset = B * S1; g.M = C * S1; g.Nout = C2A; g.K = C1B;
     g.Yb = s.P2; g.ldyb = C2A; g.xyz = s.nx1; g.W1x[0] = wa.mlp5_w; g.W1x[1] = wb.mlp5_w; g.ldw1x = 3 + C1B;
-    PZ_TRY(launch_tc_gemm(g, st));
+    PZ_TRY(launch_tc_rowgemm(g, st));
     prof_mark("sg2_layer1", st);
   }
   PZ_CUDA(cudaStreamWaitEvent(st, ss->join_b, 0));   // stage-2 geometry is done (side stream joined)
@@ -832,12 +839,17 @@ static int encoder_forward_bf16(const PzEncoderWeights* w, int E, int B, const f
     const __nv_bfloat16* wla = wpa + WP_ATT + (size_t)l * WP_ATT_STRIDE;
     const __nv_bfloat16* wlb = wpb + WP_ATT + (size_t)l * WP_ATT_STRIDE;
     {
-      TcGemm g;  // [q | k | v] = x Wqkv^T + b ; q|k stored row-major bf16, v stored TRANSPOSED per cloud (K-major for P v)
-      g.X = xb; g.ldx = 1280; g.W[0] = wla; g.W[1] = wlb; g.ldw = CATT;
-      g.bias[0] = s.bqkv + (size_t)l * 384; g.bias[1] = s.bqkv + ((size_t)(E - 1) * 4 + l) * 384;
-      g.rows_per_wset = B * LATT; g.M = rows; g.Nout = 384; g.K = CATT; g.Yb = s.qk_b; g.ldyb = 128;
-      g.YT = s.vT_b; g.t_ch_begin = 128;
-      PZ_TRY(launch_tc_gemm(g, st));
+      // [q | k] = x Wqk^T + b  (row-major bf16, row-per-thread epilogue) and v^T = (x Wv^T + b)^T per cloud
+      // (channel-per-thread epilogue: the transposed store is contiguous there, and K-major for the P v MMA)
+      TcGemm gq;
+      gq.X = xb; gq.ldx = 1280; gq.W[0] = wla; gq.W[1] = wlb; gq.ldw = CATT;
+      gq.bias[0] = s.bqkv + (size_t)l * 384; gq.bias[1] = s.bqkv + ((size_t)(E - 1) * 4 + l) * 384;
+      gq.rows_per_wset = B * LATT; gq.M = rows; gq.Nout = 128; gq.K = CATT; gq.Yb = s.qk_b; gq.ldyb = 128;
+      PZ_TRY(launch_tc_rowgemm(gq, st));
+      TcGemm gv = gq;
+      gv.W[0] = wla + 128 * CATT; gv.W[1] = wlb + 128 * CATT; gv.bias[0] = gq.bias[0] + 128; gv.bias[1] = gq.bias[1] + 128;
+      gv.Nout = CATT; gv.Yb = nullptr; gv.YT = s.vT_b; gv.t_ch_begin = 0;
+      PZ_TRY(launch_tc_gemm(gv, st));
       prof_mark("attn_qkv_proj", st);
     }
     const int amode = o.attention ? (l == 0 ? 1 : (l == 3 ? 3 : 2)) : 0;
@@ -849,7 +861,7 @@ static int encoder_forward_bf16(const PzEncoderWeights* w, int E, int B, const f
       g.bias[0] = wa.o_b[l]; g.bias[1] = wb.o_b[l]; g.rows_per_wset = B * LATT; g.M = rows; g.Nout = CATT; g.K = CATT;
       g.relu = 1; g.Rb = xb; g.ldrb = 1280; g.Yb = cat_b + l * CATT; g.ldyb = 1280;
       if (cat_f) { g.Yf = cat_f + l * CATT; g.ldyf = 1280; }
-      PZ_TRY(launch_tc_gemm(g, st));
+      PZ_TRY(launch_tc_rowgemm(g, st));
       prof_mark("attn_out_proj", st);
     }
   }
@@ -1159,15 +1171,15 @@ extern "C" int pz_predict5(const PzEncoderWeights* enc_host, const PzHeadWeights
         if (!seg0) { g.bias[0] = s.hbias + li * 128; g.bias[1] = s.hbias + 3 * 128 + li * 128; }
         g.rows_per_wset = B * NPTS; g.M = P; g.Nout = 128; g.K = 64; g.relu = relu; g.n_valid = 64;
         g.Yb = y; g.ldyb = 64;
-        if (with_max) { g.Ymax = s.tilemax; g.ldmax = 128; }
+        (void)with_max;
         if (seg0) { g.rowbias = s.gbias; g.rb_rows = NPTS; g.rb_ld = 64; }
-        return launch_tc_gemm(g, st);
+        return launch_tc_rowgemm(g, st);
       };
       PZ_TRY(layer(xfeat_b, 0, 1, s.ha, false, false));
       PZ_TRY(layer(s.ha, 1, 1, s.hb, false, false));
       PZ_TRY(layer(s.hb, 2, 0, s.ha, true, false));                 // local features (no ReLU) + per-tile maxima
-      seg_bias_tiles_kernel<<<dim3(B, 2), 64, 0, st>>>(s.tilemax, 128, h.seg_fpc_w[0], h.seg_fpc_b[0], h.seg_rpc_w[0],
-                                                       h.seg_rpc_b[0], B, s.gbias);
+      seg_bias_cloudmax_kernel<<<B, 256, 0, st>>>(s.ha + (size_t)B * NPTS * 64, h.seg_fpc_w[0], h.seg_fpc_b[0],
+                                                  h.seg_rpc_w[0], h.seg_rpc_b[0], B, s.gbias);
       PZ_LAUNCH_CHECK();
       PZ_TRY(layer(s.ha, 3, 1, s.hb, false, true));                 // relu(W0[:,64:] local + W0[:,:64] g + b0)
       head_seg_tail_kernel<<<P / 128, 128, 0, st>>>(s.hb, seg_f, seg_r, B, de_fpcb, de_mrpcb);

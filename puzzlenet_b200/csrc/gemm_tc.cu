@@ -447,5 +447,5 @@ extern "C" int pz_linear_bf16(const void* x_bf16, int ldx, const void* w_bf16, c
   g.X = static_cast<const __nv_bfloat16*>(x_bf16); g.ldx = ldx;
   g.W[0] = static_cast<const __nv_bfloat16*>(w_bf16); g.ldw = K; g.bias[0] = bias;
   g.M = M; g.Nout = N; g.K = K; g.relu = relu; g.Yf = y; g.ldyf = ldy; g.Rf = residual_or_null; g.ldrf = ldr;
-  return launch_tc_gemm(g, as_stream(stream));
+  return launch_tc_rowgemm(g, as_stream(stream));
 }

@@ -149,6 +149,7 @@ struct TcGemm {
   int ldw1x = 0;
 };
 int launch_tc_gemm(const TcGemm& g, cudaStream_t st);
+int launch_tc_rowgemm(const TcGemm& g, cudaStream_t st);   // gemm_tc_rows.cu: same struct, row-major store epilogue
 // attention_tc.cu: per cloud  r = x - softmax(q k^T / sqrt(64)) v   on tcgen05 (L == 256, d_k == 64, C == 256)
 int launch_attention_tc(const __nv_bfloat16* qk, const __nv_bfloat16* vT, const __nv_bfloat16* x, int ldx, int clouds,
                         __nv_bfloat16* r, float* attn, int attn_mode, cudaStream_t st);
