@@ -150,30 +150,46 @@ int launch_fps(const float* xyz, int B, int N, const int64_t* start, int S, int6
 // per-warp queue and folded in 32 at a time with a bitonic sort + bitonic merge
 // (WarpSelect-style), so the [B,S,N] distance matrix of pointnet_util.py:118 never exists.
 // ======================================================================================
-constexpr int KNN_WARPS = 8;      // queries per CTA
+constexpr int KNN_WARPS = 8;      // warps per CTA
+constexpr int KNN_QPW = 4;        // queries per warp (amortises staging the cloud in shared memory)
 constexpr int KNN_CHUNK = 2048;   // points staged in smem per pass
-typedef unsigned long long u64;
 
-__device__ __forceinline__ u64 bitonic_step(u64 v, int lane, int j, bool ascending_block) {
-  u64 o = __shfl_xor_sync(0xffffffffu, v, j);
-  bool lower = (lane & j) == 0;
-  bool keep_min = (lower == ascending_block);
-  u64 mn = v < o ? v : o, mx = v < o ? o : v;
-  return keep_min ? mn : mx;
+// (distance bits, index) pairs kept in two 32-bit registers; order = distance, then index
+__device__ __forceinline__ bool key_less(unsigned ad, unsigned ai, unsigned bd, unsigned bi) {
+  return ad < bd || (ad == bd && ai < bi);
 }
-
-// fold 32 candidate keys (one per lane, any order) into the sorted top-32 `top`
-__device__ __forceinline__ u64 knn_merge(u64 top, u64 cand, int lane) {
+// one compare-exchange stage of a bitonic network across the warp; keep_min: this lane keeps the smaller key
+__device__ __forceinline__ void cx_stage(unsigned& d, unsigned& i, int j, bool keep_min) {
+  const unsigned od = __shfl_xor_sync(0xffffffffu, d, j), oi = __shfl_xor_sync(0xffffffffu, i, j);
+  const bool take = key_less(od, oi, d, i) == keep_min;
+  d = take ? od : d;
+  i = take ? oi : i;
+}
+// kmask bit s = keep_min of this lane in sort stage s (the 15 stages of a 32-wide bitonic sort, in order)
+__device__ __forceinline__ unsigned bitonic_keep_mask(int lane) {
+  unsigned m = 0;
+  int s = 0;
+  for (int k = 2; k <= 32; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1, ++s) {
+      const bool asc = (lane & k) == 0 || k == 32;
+      if (((lane & j) == 0) == asc) m |= 1u << s;
+    }
+  return m;
+}
+// fold 32 candidate keys (one per lane, any order) into the sorted top-32 (td, ti)
+__device__ __forceinline__ void knn_merge(unsigned& td, unsigned& ti, unsigned cd, unsigned ci, int lane, unsigned kmask) {
+  int s = 0;
 #pragma unroll
   for (int k = 2; k <= 32; k <<= 1) {
 #pragma unroll
-    for (int j = k >> 1; j > 0; j >>= 1) cand = bitonic_step(cand, lane, j, (lane & k) == 0 || k == 32);
+    for (int j = k >> 1; j > 0; j >>= 1, ++s) cx_stage(cd, ci, j, (kmask >> s) & 1u);
   }
-  u64 rev = __shfl_sync(0xffffffffu, cand, 31 - lane);
-  u64 m = top < rev ? top : rev;  // bitonic sequence holding the 32 smallest of the union
+  const unsigned rd = __shfl_sync(0xffffffffu, cd, 31 - lane), ri = __shfl_sync(0xffffffffu, ci, 31 - lane);
+  const bool lt = key_less(rd, ri, td, ti);   // elementwise min of ascending top and descending candidates:
+  td = lt ? rd : td;                          // a bitonic sequence holding the 32 smallest of the union
+  ti = lt ? ri : ti;
 #pragma unroll
-  for (int j = 16; j > 0; j >>= 1) m = bitonic_step(m, lane, j, true);
-  return m;
+  for (int j = 16, q = 10; j > 0; j >>= 1, ++q) cx_stage(td, ti, j, (kmask >> q) & 1u);   // = the k == 32 stages
 }
 
 __global__ void __launch_bounds__(KNN_WARPS * 32) knn_kernel(const float* __restrict__ query,
@@ -182,70 +198,92 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_kernel(const float* __rest
                                                              int64_t* __restrict__ out64,
                                                              int* __restrict__ out_rows32,
                                                              float* __restrict__ out_d2) {
-  __shared__ float xs[KNN_CHUNK], ys[KNN_CHUNK], zs[KNN_CHUNK];
-  __shared__ u64 queue[KNN_WARPS][64];
+  // the cloud is staged as raw xyz triples (coalesced copy, no index arithmetic); point i is read at words
+  // 3i..3i+2: stride 3 is coprime with the 32 banks, so the three scalar reads per lane are conflict-free
+  __shared__ float pts[KNN_CHUNK * 3];
+  __shared__ unsigned qd[KNN_WARPS][64], qi[KNN_WARPS][64];
   const int b = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int q = blockIdx.x * KNN_WARPS + warp;
-  const bool active = q < S;
-  float qx = 0.f, qy = 0.f, qz = 0.f;
-  if (active) {
-    const float* qp = query + ((size_t)b * S + q) * 3;
-    qx = qp[0]; qy = qp[1]; qz = qp[2];
-  }
+  const int q0 = (blockIdx.x * KNN_WARPS + warp) * KNN_QPW;
   const float* p = xyz + (size_t)b * N * 3;
-  u64 top = ~0ull;   // lane l holds the l-th smallest key so far
-  u64 tau = ~0ull;   // current 32nd smallest
-  int qn = 0;
-  u64* myq = queue[warp];
+  const unsigned kmask = bitonic_keep_mask(lane);
+  unsigned* myd = qd[warp];
+  unsigned* myi = qi[warp];
   const unsigned lt_mask = (1u << lane) - 1u;
+  // per-query selection state lives in registers while the query is being scanned and is parked in shared
+  // memory between chunks (only clouds larger than KNN_CHUNK points have more than one chunk); the query loop
+  // is deliberately not unrolled so that the two merge networks are emitted once (instruction-cache footprint)
+  __shared__ unsigned park_d[KNN_WARPS][KNN_QPW][32], park_i[KNN_WARPS][KNN_QPW][32];
 
   for (int base = 0; base < N; base += KNN_CHUNK) {
     const int cnt = min(KNN_CHUNK, N - base);
+    const bool first = base == 0, last = base + KNN_CHUNK >= N;
     __syncthreads();
-    for (int i = threadIdx.x; i < cnt * 3; i += KNN_WARPS * 32) {
-      float v = p[(size_t)base * 3 + i];
-      int pt = i / 3, d = i - pt * 3;
-      (d == 0 ? xs : (d == 1 ? ys : zs))[pt] = v;
-    }
+    for (int i = threadIdx.x; i < cnt * 3; i += KNN_WARPS * 32) pts[i] = p[(size_t)base * 3 + i];
     __syncthreads();
-    if (!active) continue;
-    for (int i0 = 0; i0 < cnt; i0 += 32) {
-      const int i = i0 + lane;
-      bool pass = false;
-      u64 key = ~0ull;
-      if (i < cnt) {
-        float d = sqdist3(qx, qy, qz, xs[i], ys[i], zs[i]);
-        key = ((u64)__float_as_uint(d) << 32) | (unsigned)(base + i);
-        pass = key < tau;
+#pragma unroll 1
+    for (int w = 0; w < KNN_QPW; ++w) {
+      const int q = q0 + w;
+      if (q >= S) break;                  // warp-uniform
+      const float* qp = query + ((size_t)b * S + q) * 3;
+      const float qx = qp[0], qy = qp[1], qz = qp[2];
+      unsigned td = first ? 0xffffffffu : park_d[warp][w][lane];   // lane l holds the l-th smallest key so far
+      unsigned ti = first ? 0xffffffffu : park_i[warp][w][lane];
+      unsigned tau = __shfl_sync(0xffffffffu, td, 31);              // distance bits of the current 32nd smallest
+      int qn = 0;
+      // four candidates per lane per iteration; a candidate is queued when its distance does not exceed the
+      // current 32nd distance (ties are over-included -- the merge orders them by index, so the result is exact)
+      for (int i0 = 0; i0 < cnt; i0 += 128) {
+        unsigned db[4];
+        bool any_pass = false;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * 32 + lane;
+          db[u] = 0xffffffffu;
+          if (i < cnt) db[u] = __float_as_uint(sqdist3(qx, qy, qz, pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]));
+          any_pass |= (i < cnt) && db[u] <= tau;
+        }
+        if (!__any_sync(0xffffffffu, any_pass)) continue;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * 32 + lane;
+          const bool pass = (i < cnt) && db[u] <= tau;
+          const unsigned m = __ballot_sync(0xffffffffu, pass);
+          if (m == 0u) continue;
+          if (pass) {
+            const int pos = qn + __popc(m & lt_mask);
+            myd[pos] = db[u];
+            myi[pos] = (unsigned)(base + i);
+          }
+          qn += __popc(m);
+          __syncwarp();
+          if (qn >= 32) {
+            knn_merge(td, ti, myd[lane], myi[lane], lane, kmask);
+            tau = __shfl_sync(0xffffffffu, td, 31);
+            const int rem = qn - 32;
+            const unsigned cd = lane < rem ? myd[32 + lane] : 0u, ci = lane < rem ? myi[32 + lane] : 0u;
+            __syncwarp();
+            if (lane < rem) {
+              myd[lane] = cd;
+              myi[lane] = ci;
+            }
+            __syncwarp();
+            qn = rem;
+          }
+        }
       }
-      unsigned m = __ballot_sync(0xffffffffu, pass);
-      if (m == 0u) continue;
-      if (pass) myq[qn + __popc(m & lt_mask)] = key;
-      qn += __popc(m);
+      if (qn > 0) knn_merge(td, ti, lane < qn ? myd[lane] : 0xffffffffu, lane < qn ? myi[lane] : 0xffffffffu, lane, kmask);
       __syncwarp();
-      if (qn >= 32) {
-        top = knn_merge(top, myq[lane], lane);
-        tau = __shfl_sync(0xffffffffu, top, 31);
-        const int rem = qn - 32;
-        u64 carry = lane < rem ? myq[32 + lane] : 0ull;
-        __syncwarp();
-        if (lane < rem) myq[lane] = carry;
-        __syncwarp();
-        qn = rem;
+      if (!last) {
+        park_d[warp][w][lane] = td;
+        park_i[warp][w][lane] = ti;
+      } else if (lane < K) {
+        const size_t o = ((size_t)b * S + q) * K + lane;
+        if (out64) out64[o] = (int64_t)ti;
+        if (out_rows32) out_rows32[o] = b * N + (int)ti;
+        if (out_d2) out_d2[o] = __uint_as_float(td);
       }
     }
-  }
-  if (!active) return;
-  if (qn > 0) {
-    top = knn_merge(top, lane < qn ? myq[lane] : ~0ull, lane);
-  }
-  if (lane < K) {
-    const size_t o = ((size_t)b * S + q) * K + lane;
-    const unsigned idx = (unsigned)(top & 0xffffffffu);
-    if (out64) out64[o] = (int64_t)idx;
-    if (out_rows32) out_rows32[o] = b * N + (int)idx;
-    if (out_d2) out_d2[o] = __uint_as_float((unsigned)(top >> 32));
   }
 }
 
@@ -254,7 +292,7 @@ int launch_knn(const float* query, const float* xyz, int B, int S, int N, int K,
   PZ_REQUIRE(K >= 1 && K <= 32, PZ_ERR_UNSUPPORTED, "pz_knn: K=%d not in [1,32]", K);
   PZ_REQUIRE(N >= K, PZ_ERR_UNSUPPORTED, "pz_knn: N=%d < K=%d", N, K);
   PZ_REQUIRE(B <= 65535, PZ_ERR_UNSUPPORTED, "pz_knn: B=%d > 65535", B);
-  dim3 grid((S + KNN_WARPS - 1) / KNN_WARPS, B);
+  dim3 grid((S + KNN_WARPS * KNN_QPW - 1) / (KNN_WARPS * KNN_QPW), B);
   knn_kernel<<<grid, KNN_WARPS * 32, 0, st>>>(query, xyz, S, N, K, out64, out_rows32, out_d2);
   PZ_LAUNCH_CHECK();
   return 0;
