@@ -40,7 +40,12 @@ typedef void* pz_stream_t; /* cudaStream_t */
 #define PZ_PREC_FP32 0 /* fp32 CUDA-core math, matches the reference to ~1e-6 rel */
 #define PZ_PREC_BF16 1 /* bf16 operands, fp32 accumulate on tcgen05 tensor cores */
 
-#define PZ_ABI_VERSION 1
+#define PZ_ABI_VERSION 2
+
+/* pz_predict5 flags */
+#define PZ_FLAG_NEED 1          /* also return x2 / attention of both clouds (predict5 need=True) */
+#define PZ_FLAG_REUSE_PACKS 2   /* the bf16 weight packs inside `workspace` are still valid: same workspace, same
+                                   precision and unchanged weights since the previous call (skips one repack launch) */
 
 int pz_abi_version(void);
 const char* pz_last_error(void);
@@ -199,13 +204,13 @@ typedef struct PzHeadWeights {
 /* TouchedRegraster.predict5(batch, _, need, training=False) -- model5_b.py:672-759.
  * fpc, mrpc [B,1024,3]; starts [4,B] = FPS starts in the reference's draw order
  * (Encoder stage 1, Encoder stage 2, Encoder2 stage 1, Encoder2 stage 2).
- * out6 [B,6]; de_fpcb, de_mrpcb [B,2,1024].  need != 0 additionally fills x2_* [B,256,3] and
+ * out6 [B,6]; de_fpcb, de_mrpcb [B,2,1024].  flags & PZ_FLAG_NEED additionally fills x2_* [B,256,3] and
  * attention_* [B,256,256] (may be null otherwise).  Reproduces the reference's use of the mrpc
  * global feature for both boundary heads (model5_b.py:741-744). */
 size_t pz_predict5_workspace_bytes(int B);
 int pz_predict5(const PzEncoderWeights* enc_host /*[2]*/, const PzHeadWeights* heads_host,
                 const float* fpc, const float* mrpc, int B, const int64_t* starts, int precision,
-                int need, float* out6, float* de_fpcb, float* de_mrpcb, float* x2_fpc,
+                int flags, float* out6, float* de_fpcb, float* de_mrpcb, float* x2_fpc,
                 float* attention_fpc, float* x2_mrpc, float* attention_mrpc, void* workspace,
                 size_t workspace_bytes, pz_stream_t stream);
 

@@ -15,7 +15,9 @@ LIB_PATH = os.path.join(_HERE, "lib", "libpuzzlenet_sm100.so")
 
 PZ_PREC_FP32 = 0
 PZ_PREC_BF16 = 1
-ABI_VERSION = 1
+ABI_VERSION = 2
+PZ_FLAG_NEED = 1
+PZ_FLAG_REUSE_PACKS = 2
 
 c_f32p = C.c_void_p   # device pointers travel as integers
 c_i64p = C.c_void_p

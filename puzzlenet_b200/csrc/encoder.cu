@@ -713,7 +713,7 @@ using AfterStem = std::function<int(const float* xfeat, const __nv_bfloat16* xfe
 
 static int encoder_forward_bf16(const PzEncoderWeights* w, int E, int B, const float* xyz, const int64_t* start1,
                                 const int64_t* start2, const PzEncoderOutputs& o, EncoderScratch& s, float* fglob_pair,
-                                const float** xfeat_out, const AfterStem* after_stem, cudaStream_t st) {
+                                const float** xfeat_out, const AfterStem* after_stem, bool reuse_pack, cudaStream_t st) {
   const int C = E * B;
   const PzEncoderWeights& wa = w[0];
   const PzEncoderWeights& wb = w[E - 1];
@@ -721,8 +721,9 @@ static int encoder_forward_bf16(const PzEncoderWeights* w, int E, int B, const f
   float* nx2 = o.x2 ? o.x2 : s.nx2;
   if (xfeat_out) *xfeat_out = xfeat;
 
-  // ---- weights -> bf16 packs (one launch; ~8 MB read, cheap enough to redo every call, keeps the ABI stateless)
-  {
+  // ---- weights -> bf16 packs (one launch, ~8 MB read).  The pack lives in the caller's workspace; a caller that
+  // knows the weights are unchanged since its previous call may say so (PZ_FLAG_REUSE_PACKS) and skip it.
+  if (!reuse_pack) {
     PackJobs jobs;
     int n = 0;
     auto add = [&](const float* src, int ldi, int rows, int cols, void* dst, int ldo, int bf) {
@@ -897,7 +898,7 @@ static int encoder_forward_bf16(const PzEncoderWeights* w, int E, int B, const f
 static int encoder_forward_impl(const PzEncoderWeights* w, int E, int B, const float* xyz, const int64_t* start1,
                                 const int64_t* start2, int precision, const PzEncoderOutputs& o, void* ws,
                                 size_t ws_bytes, float* fglob_pair, const float** xfeat_out, const AfterStem* after_stem,
-                                cudaStream_t st) {
+                                bool reuse_pack, cudaStream_t st) {
   PZ_REQUIRE(E == 1 || E == 2, PZ_ERR_ARG, "encoder: E must be 1 or 2 (got %d)", E);
   PZ_REQUIRE(B >= 1, PZ_ERR_ARG, "encoder: B must be >= 1");
   PZ_REQUIRE(precision == PZ_PREC_FP32 || precision == PZ_PREC_BF16, PZ_ERR_ARG, "encoder: unknown precision %d", precision);
@@ -909,7 +910,7 @@ static int encoder_forward_impl(const PzEncoderWeights* w, int E, int B, const f
   encoder_scratch_layout(C, arena, s);
   PZ_REQUIRE(ws && arena.ok(), PZ_ERR_WORKSPACE, "encoder: workspace %zu B < required %zu B", ws_bytes, arena.used);
   if (precision == PZ_PREC_BF16)
-    return encoder_forward_bf16(w, E, B, xyz, start1, start2, o, s, fglob_pair, xfeat_out, after_stem, st);
+    return encoder_forward_bf16(w, E, B, xyz, start1, start2, o, s, fglob_pair, xfeat_out, after_stem, reuse_pack, st);
   const PzEncoderWeights& wa = w[0];
   const PzEncoderWeights& wb = w[E - 1];
   float* xfeat = o.x_feature ? o.x_feature : s.xfeat;
@@ -1046,7 +1047,7 @@ extern "C" int pz_encoder_forward(const PzEncoderWeights* weights_host, int E, i
   PZ_REQUIRE(weights_host && xyz && start1 && start2 && outputs_host, PZ_ERR_ARG, "pz_encoder_forward: null pointer");
   prof_begin(as_stream(stream));
   return encoder_forward_impl(weights_host, E, B, xyz, start1, start2, precision, *outputs_host, workspace,
-                              workspace_bytes, nullptr, nullptr, nullptr, as_stream(stream));
+                              workspace_bytes, nullptr, nullptr, nullptr, false, as_stream(stream));
 }
 
 namespace {
@@ -1088,12 +1089,14 @@ extern "C" size_t pz_predict5_workspace_bytes(int B) {
 }
 
 extern "C" int pz_predict5(const PzEncoderWeights* enc_host, const PzHeadWeights* heads_host, const float* fpc,
-                           const float* mrpc, int B, const int64_t* starts, int precision, int need, float* out6,
+                           const float* mrpc, int B, const int64_t* starts, int precision, int flags, float* out6,
                            float* de_fpcb, float* de_mrpcb, float* x2_fpc, float* attention_fpc, float* x2_mrpc,
                            float* attention_mrpc, void* workspace, size_t workspace_bytes, pz_stream_t stream) {
   PZ_REQUIRE(enc_host && heads_host && fpc && mrpc && starts && out6 && de_fpcb && de_mrpcb, PZ_ERR_ARG,
              "pz_predict5: null pointer");
   PZ_REQUIRE(B >= 1, PZ_ERR_ARG, "pz_predict5: B must be >= 1");
+  const int need = flags & PZ_FLAG_NEED;
+  const bool reuse_pack = (flags & PZ_FLAG_REUSE_PACKS) != 0;
   if (need)
     PZ_REQUIRE(x2_fpc && attention_fpc && x2_mrpc && attention_mrpc, PZ_ERR_ARG,
                "pz_predict5: need=1 requires the x2/attention outputs");
@@ -1145,6 +1148,7 @@ extern "C" int pz_predict5(const PzEncoderWeights* enc_host, const PzHeadWeights
       // tensor-core version: 3 x (64->64) + the local half of MLP{F,R}pcb.0 as GEMMs with weights zero-padded to
       // 128 output channels; the global max-pool over each cloud's 1024 points comes out of the third GEMM's
       // epilogue as per-tile maxima; the global half of layer 0 is a per-cloud bias (rowbias).
+      if (!reuse_pack) {
       PZ_CUDA(cudaMemsetAsync(s.hpack, 0, (size_t)2 * 4 * 128 * 64 * sizeof(__nv_bfloat16), st));
       PZ_CUDA(cudaMemsetAsync(s.hbias, 0, (size_t)2 * 3 * 128 * sizeof(float), st));
       PackJobs jobs;
@@ -1165,6 +1169,7 @@ extern "C" int pz_predict5(const PzEncoderWeights* enc_host, const PzHeadWeights
       jobs.n = n;
       pack_weights_kernel<<<dim3(16, n), 256, 0, st>>>(jobs);
       PZ_LAUNCH_CHECK();
+      }
       auto layer = [&](const __nv_bfloat16* x, int li, int relu, __nv_bfloat16* y, bool with_max, bool seg0) {
         TcGemm g;
         g.X = x; g.ldx = 64; g.W[0] = s.hpack + (size_t)li * 128 * 64; g.W[1] = g.W[0] + 4 * 128 * 64; g.ldw = 64;
@@ -1206,7 +1211,7 @@ extern "C" int pz_predict5(const PzEncoderWeights* enc_host, const PzHeadWeights
 
   const float* xfeat = nullptr;
   PZ_TRY(encoder_forward_impl(enc_host, 2, B, s.xyz, s.st1, s.st2, precision, eo, s.enc, s.enc_bytes, s.fpair,
-                              &xfeat, &heads_fn, st));
+                              &xfeat, &heads_fn, reuse_pack, st));
   if (need) {
     const size_t ab = (size_t)B * LATT * LATT * sizeof(float), xb = (size_t)B * S2 * 3 * sizeof(float);
     PZ_CUDA(cudaMemcpyAsync(attention_fpc, attn_all, ab, cudaMemcpyDeviceToDevice, st));

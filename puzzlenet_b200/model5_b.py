@@ -236,6 +236,7 @@ class TouchedRegraster(_Base):
         self.MLPFpcb = _seq(128, 64, 32, 2)
         self.precision = "fp32"
         self._ws = {}
+        self._pack_keys = {}
 
     # ---- weights as C structs (rebuilt per call: ~100 data_ptr() reads, no device work)
     def _head_struct(self) -> _lib.PzHeadWeights:
@@ -251,12 +252,16 @@ class TouchedRegraster(_Base):
         return h
 
     def _workspace(self, B: int, device) -> torch.Tensor:
-        key = (B, str(device))
+        """One workspace per (batch size, device, CUDA stream): calls issued on different streams may overlap on
+        the GPU (a pipelined caller alternates streams), so they must not share scratch.  At most four are kept."""
+        key = (B, str(device), torch.cuda.current_stream(device).cuda_stream)
         ws = self._ws.get(key)
         if ws is None:
             nbytes = _lib.load().pz_predict5_workspace_bytes(B)
             ws = torch.empty(nbytes, device=device, dtype=torch.uint8)
-            self._ws = {key: ws}          # keep one workspace (the last batch size)
+            if len(self._ws) >= 4:
+                self._ws.pop(next(iter(self._ws)))
+            self._ws[key] = ws
         return ws
 
     def forward(self, batch, bat):
@@ -299,9 +304,21 @@ class TouchedRegraster(_Base):
         enc = (_lib.PzEncoderWeights * 2)(_encoder_struct(self.Encoder), _encoder_struct(self.Encoder2))
         heads = self._head_struct()
         ws = self._workspace(B, dev)
+        flags = _lib.PZ_FLAG_NEED if need else 0
+        if self.precision == "bf16":
+            # the bf16 weight packs live in the workspace: reusable while no parameter was touched (in-place writes
+            # bump _version, reallocation changes data_ptr) and the workspace / precision are the same
+            key = tuple((p.data_ptr(), p._version) for p in self.parameters())
+            if self._pack_keys.get(ws.data_ptr()) == key:
+                flags |= _lib.PZ_FLAG_REUSE_PACKS
+            if len(self._pack_keys) >= 8:
+                self._pack_keys.clear()
+            self._pack_keys[ws.data_ptr()] = key
+        else:
+            self._pack_keys.pop(ws.data_ptr(), None)
         with torch.cuda.device(dev):
             _lib.call("pz_predict5", enc, ctypes.byref(heads), fpc.data_ptr(), mrpc.data_ptr(), B, starts.data_ptr(),
-                      PRECISIONS[self.precision], 1 if need else 0, out6.data_ptr(), de_fpcb.data_ptr(),
+                      PRECISIONS[self.precision], flags, out6.data_ptr(), de_fpcb.data_ptr(),
                       de_mrpcb.data_ptr(), _ptr(x2f), _ptr(af), _ptr(x2m), _ptr(am), ws.data_ptr(), ws.numel(),
                       _lib.stream_ptr())
         if not need:
