@@ -633,13 +633,13 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const PackJobs jobs) 
 // half, P, comes out of the layer-1 GEMM):  relu(W1 [xyz_j - c_s ; f_j] + b1) = relu(P_j - Q_s).
 __global__ void __launch_bounds__(256) centre_proj_kernel(const float* __restrict__ centres, const float* w1a,
                                                           const float* w1b, int ldw1, int rows_per_set, int rows,
-                                                          int C1, float* __restrict__ Q) {
+                                                          int C1, __nv_bfloat16* __restrict__ Q) {
   const size_t e = (size_t)blockIdx.x * 256 + threadIdx.x;
   if (e >= (size_t)rows * C1) return;
   const int s = (int)(e / C1), k = (int)(e - (size_t)s * C1);
   const float* w = (s / rows_per_set == 0 ? w1a : w1b) + (size_t)k * ldw1;
   const float* c = centres + (size_t)s * 3;
-  Q[e] = fmaf(w[0], c[0], fmaf(w[1], c[1], w[2] * c[2]));
+  Q[e] = __float2bfloat16_rn(fmaf(w[0], c[0], fmaf(w[1], c[1], w[2] * c[2])));
 }
 
 // ======================================================================== orchestration
@@ -659,8 +659,8 @@ struct EncoderScratch {
   float *xfeat, *F1, *nx1, *f1f, *F2, *nx2, *att_cat, *q, *k, *v, *r, *tailp, *fglob;
   int *knn1r, *knn2r;
   // bf16 path
-  __nv_bfloat16 *xfeat_b, *P1, *f1f_b, *P2, *att_cat_b, *r_b, *wpack, *qk_b, *vT_b;
-  float *Q1, *Q2, *bqkv;
+  __nv_bfloat16 *xfeat_b, *P1, *f1f_b, *P2, *att_cat_b, *r_b, *wpack, *qk_b, *vT_b, *Q1, *Q2;
+  float *bqkv;
 };
 
 // bf16 weight pack of ONE encoder (elements): W3f[128,64] W4[128,128] W5f[256,128] W6[256,256]
@@ -687,10 +687,10 @@ static size_t encoder_scratch_layout(int C, Arena& a, EncoderScratch& s) {
   s.fglob = a.take<float>((size_t)C * 1024);
   s.xfeat_b = a.take<__nv_bfloat16>((size_t)C * NPTS * D0);
   s.P1 = a.take<__nv_bfloat16>((size_t)C * NPTS * C1A);
-  s.Q1 = a.take<float>((size_t)C * S1 * C1A);
+  s.Q1 = a.take<__nv_bfloat16>((size_t)C * S1 * C1A);
   s.f1f_b = a.take<__nv_bfloat16>((size_t)C * S1 * C1B);
   s.P2 = a.take<__nv_bfloat16>((size_t)C * S1 * C2A);
-  s.Q2 = a.take<float>((size_t)C * S2 * C2A);
+  s.Q2 = a.take<__nv_bfloat16>((size_t)C * S2 * C2A);
   s.att_cat_b = a.take<__nv_bfloat16>((size_t)C * LATT * 1280);
   s.qk_b = a.take<__nv_bfloat16>((size_t)C * LATT * 128);
   s.vT_b = a.take<__nv_bfloat16>((size_t)C * LATT * CATT);
@@ -801,7 +801,7 @@ static int encoder_forward_bf16(const PzEncoderWeights* w, int E, int B, const f
   prof_mark("_wait_geometry1", st);
   {
     TcGemm g;  // f1f = max_k relu(W4 relu(P1[j] - Q1[s]) + b4)
-    g.X = s.P1; g.ldx = C1A; g.rows = s.knn1r; g.Q = s.Q1; g.W[0] = wpa + WP_W4; g.W[1] = wpb + WP_W4; g.ldw = C1A;
+    g.X = s.P1; g.ldx = C1A; g.rows = s.knn1r; g.Qb = s.Q1; g.W[0] = wpa + WP_W4; g.W[1] = wpb + WP_W4; g.ldw = C1A;
     g.bias[0] = wa.mlp4_b; g.bias[1] = wb.mlp4_b; g.rows_per_wset = B * S1 * KNN; g.M = C * S1 * KNN; g.Nout = C1B;
     g.K = C1A; g.epi = 1; g.relu = 1; g.Yf = o.f1f; g.ldyf = C1B; g.Yb = s.f1f_b; g.ldyb = C1B;
     PZ_TRY(launch_tc_gemm(g, st));
@@ -821,7 +821,7 @@ static int encoder_forward_bf16(const PzEncoderWeights* w, int E, int B, const f
   float* cat_f = o.att_cat;                     // fp32 copy only when the caller asks for it
   {
     TcGemm g;
-    g.X = s.P2; g.ldx = C2A; g.rows = s.knn2r; g.Q = s.Q2; g.W[0] = wpa + WP_W6; g.W[1] = wpb + WP_W6; g.ldw = C2A;
+    g.X = s.P2; g.ldx = C2A; g.rows = s.knn2r; g.Qb = s.Q2; g.W[0] = wpa + WP_W6; g.W[1] = wpb + WP_W6; g.ldw = C2A;
     g.bias[0] = wa.mlp6_b; g.bias[1] = wb.mlp6_b; g.rows_per_wset = B * S2 * KNN; g.M = C * S2 * KNN; g.Nout = C2B;
     g.K = C2A; g.epi = 1; g.relu = 1; g.Yb = cat_b + 4 * CATT; g.ldyb = 1280;
     if (cat_f) { g.Yf = cat_f + 4 * CATT; g.ldyf = 1280; }

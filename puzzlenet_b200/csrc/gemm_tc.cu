@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcGemm g) {
       // (each thread rewrites the 16-byte chunks it copied itself), so a whole stage of gathers per group is
       // always in flight while the other one is being converted -- the L2 round trip is off the critical path.
       constexpr int GCH = ROWS * 8 / 128;                  // 16-byte chunks per thread per stage
-      constexpr int QCH = (ROWS / 32) * 16;                // 16-byte chunks of the stage's Q tile ([groups][64] fp32)
+      constexpr int QCH = (ROWS / 32) * 8;                 // 16-byte chunks of the stage's Q tile ([groups][64] bf16)
       const int grp = pt >> 7, gt = pt & 127, gc = gt & 7, r0 = gt >> 3;
       int my_tiles = 0;
       for (int t = tile_begin + rank_in_set; t < tile_begin + tiles_per_set; t += step) ++my_tiles;
@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcGemm g) {
           cp_async16(st_addr + sw128(r0 + i * 16, gc), g.X + (size_t)src[i] * g.ldx + kb * KB + gc * 8);
         if (gt < QCH)
           cp_async16(qstage_base + s * (QCH * 16) + gt * 16,
-                     g.Q + (size_t)((row0 >> 5) + (gt >> 4)) * g.K + kb * KB + (gt & 15) * 4);
+                     g.Qb + (size_t)((row0 >> 5) + (gt >> 3)) * g.K + kb * KB + (gt & 7) * 8);
         cp_async_commit();
       };
       int j = grp;
@@ -150,25 +150,23 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcGemm g) {
         asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory");
         const uint32_t s = (uint32_t)j % NST;
         uint8_t* st_gen = smem_gen + (stages_base + s * STAGE_BYTES - smem_base);
-        const float* qs = reinterpret_cast<const float*>(smem_gen + (qstage_base + s * (QCH * 16) - smem_base));
+        // packed bf16x2 arithmetic: relu(p - q) on two channels per instruction (HFMA2.BF16 rounds once)
+        const uint4* qs = reinterpret_cast<const uint4*>(smem_gen + (qstage_base + s * (QCH * 16) - smem_base));
+        const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
 #pragma unroll
-        for (int i = 0; i < GCH; ++i) {
+        for (int i = 0; i < GCH; i += 2) {   // chunks i and i+1 are rows r0+16i, r0+16(i+1): the same group of 32
           const int r = r0 + i * 16;
-          uint4* slot = reinterpret_cast<uint4*>(st_gen + sw128(r, gc));
-          const uint4 pv = *slot;
-          const float4 q0 = *reinterpret_cast<const float4*>(qs + (r >> 5) * 64 + gc * 8);
-          const float4 q1 = *reinterpret_cast<const float4*>(qs + (r >> 5) * 64 + gc * 8 + 4);
-          const __nv_bfloat162* p2 = reinterpret_cast<const __nv_bfloat162*>(&pv);
-          const float2 a = __bfloat1622float2(p2[0]), b = __bfloat1622float2(p2[1]);
-          const float2 cc = __bfloat1622float2(p2[2]), d = __bfloat1622float2(p2[3]);
-          uint4 o;
-          __nv_bfloat162 t0 = __floats2bfloat162_rn(fmaxf(a.x - q0.x, 0.f), fmaxf(a.y - q0.y, 0.f));
-          __nv_bfloat162 t1 = __floats2bfloat162_rn(fmaxf(b.x - q0.z, 0.f), fmaxf(b.y - q0.w, 0.f));
-          __nv_bfloat162 t2 = __floats2bfloat162_rn(fmaxf(cc.x - q1.x, 0.f), fmaxf(cc.y - q1.y, 0.f));
-          __nv_bfloat162 t3 = __floats2bfloat162_rn(fmaxf(d.x - q1.z, 0.f), fmaxf(d.y - q1.w, 0.f));
-          o.x = *reinterpret_cast<uint32_t*>(&t0); o.y = *reinterpret_cast<uint32_t*>(&t1);
-          o.z = *reinterpret_cast<uint32_t*>(&t2); o.w = *reinterpret_cast<uint32_t*>(&t3);
-          *slot = o;
+          const uint4 qv = qs[(r >> 5) * 8 + gc];
+          const __nv_bfloat162* q2 = reinterpret_cast<const __nv_bfloat162*>(&qv);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint4* slot = reinterpret_cast<uint4*>(st_gen + sw128(r + h * 16, gc));
+            uint4 pv = *slot;
+            __nv_bfloat162* p2 = reinterpret_cast<__nv_bfloat162*>(&pv);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) p2[e] = __hmax2(__hsub2(p2[e], q2[e]), zero2);
+            *slot = pv;
+          }
         }
         fence_proxy_async();
         mbar_arrive(full_bar + 8 * s);
@@ -375,7 +373,7 @@ static int tc_launch(const TcGemm& g, cudaStream_t st) {
   const int kblocks = g.K / KB;
   const size_t resident = RESIDENT ? (size_t)NCHB * kblocks * 128 * 128 : 0;
   const size_t stage = (RESIDENT ? 0 : (size_t)NCHB * 128 * 128) + (size_t)ROWS * 128;
-  const size_t smem = 1024 + resident + NST * stage + 8 * (2 * NST + 4) + 32 + (GATHER ? (size_t)NST * (ROWS / 32) * 256 : 0);
+  const size_t smem = 1024 + resident + NST * stage + 8 * (2 * NST + 4) + 32 + (GATHER ? (size_t)NST * (ROWS / 32) * 128 : 0);
   PZ_REQUIRE(smem <= 227 * 1024, PZ_ERR_UNSUPPORTED, "tc_gemm: needs %zu B of shared memory (K=%d too large for a resident weight)", smem, g.K);
   auto kern = tc_gemm_kernel<ROWS, NCHB, RESIDENT, GATHER, NST>;
   PZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -399,7 +397,7 @@ int launch_tc_gemm(const TcGemm& g, cudaStream_t st) {
   const int nsets = (g.rows_per_wset > 0 && g.M > g.rows_per_wset) ? 2 : 1;
   if (nsets == 2) PZ_REQUIRE(g.W[1] && g.M == 2 * g.rows_per_wset, PZ_ERR_ARG, "tc_gemm: two weight sets need M == 2*rows_per_wset");
   if (g.rows) {  // gathered B, resident weights
-    PZ_REQUIRE(g.Q && g.epi == 1, PZ_ERR_ARG, "tc_gemm: gathered operand needs Q and the group-max epilogue");
+    PZ_REQUIRE(g.Qb && g.epi == 1, PZ_ERR_ARG, "tc_gemm: gathered operand needs Qb and the group-max epilogue");
     if (g.Nout == 128 && g.K <= 256) {
       PZ_REQUIRE(g.M % (256 * nsets) == 0, PZ_ERR_UNSUPPORTED, "tc_gemm: M=%d must be a multiple of %d", g.M, 256 * nsets);
       return tc_launch<256, 1, true, true, 4>(g, st);

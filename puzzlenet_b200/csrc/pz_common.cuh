@@ -125,7 +125,7 @@ struct TcGemm {
   const __nv_bfloat16* X = nullptr;                // plain: activations [M, K]; gathered: P [*, K]
   int ldx = 0;
   const int* rows = nullptr;                       // gathered: source row of P for each of the M rows
-  const float* Q = nullptr;                        // gathered: [M/32, K] fp32, X[r] = relu(P[rows[r]] - Q[r/32])
+  const __nv_bfloat16* Qb = nullptr;               // gathered: [M/32, K] bf16, X[r] = relu(P[rows[r]] - Qb[r/32])
   int M = 0, Nout = 0, K = 0;
   int epi = 0;                                     // 0 store rows, 1 max over groups of 32 rows, 2 max over the tile's rows
   int relu = 0;
