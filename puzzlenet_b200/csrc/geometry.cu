@@ -154,6 +154,16 @@ constexpr int KNN_WARPS = 8;      // warps per CTA
 constexpr int KNN_QPW = 4;        // queries per warp (amortises staging the cloud in shared memory)
 constexpr int KNN_CHUNK = 2048;   // points staged in smem per pass
 
+__device__ __forceinline__ void knn_merge_inl(unsigned& td, unsigned& ti, unsigned cd, unsigned ci, int lane, unsigned kmask);
+// Out-of-line wrapper: the merge network is ~200 instructions and is reached from inside fully unrolled
+// candidate loops; one shared copy keeps the kernel inside the instruction cache.
+__device__ __noinline__ uint2 knn_merge_call(unsigned td, unsigned ti, unsigned cd, unsigned ci, int lane, unsigned kmask);
+__device__ __forceinline__ void knn_merge(unsigned& td, unsigned& ti, unsigned cd, unsigned ci, int lane, unsigned kmask) {
+  const uint2 r = knn_merge_call(td, ti, cd, ci, lane, kmask);
+  td = r.x;
+  ti = r.y;
+}
+
 // (distance bits, index) pairs kept in two 32-bit registers; order = distance, then index
 __device__ __forceinline__ bool key_less(unsigned ad, unsigned ai, unsigned bd, unsigned bi) {
   return ad < bd || (ad == bd && ai < bi);
@@ -177,7 +187,7 @@ __device__ __forceinline__ unsigned bitonic_keep_mask(int lane) {
   return m;
 }
 // fold 32 candidate keys (one per lane, any order) into the sorted top-32 (td, ti)
-__device__ __forceinline__ void knn_merge(unsigned& td, unsigned& ti, unsigned cd, unsigned ci, int lane, unsigned kmask) {
+__device__ __forceinline__ void knn_merge_inl(unsigned& td, unsigned& ti, unsigned cd, unsigned ci, int lane, unsigned kmask) {
   int s = 0;
 #pragma unroll
   for (int k = 2; k <= 32; k <<= 1) {
@@ -190,6 +200,11 @@ __device__ __forceinline__ void knn_merge(unsigned& td, unsigned& ti, unsigned c
   ti = lt ? ri : ti;
 #pragma unroll
   for (int j = 16, q = 10; j > 0; j >>= 1, ++q) cx_stage(td, ti, j, (kmask >> q) & 1u);   // = the k == 32 stages
+}
+
+__device__ __noinline__ uint2 knn_merge_call(unsigned td, unsigned ti, unsigned cd, unsigned ci, int lane, unsigned kmask) {
+  knn_merge_inl(td, ti, cd, ci, lane, kmask);
+  return make_uint2(td, ti);
 }
 
 __global__ void __launch_bounds__(KNN_WARPS * 32) knn_kernel(const float* __restrict__ query,
@@ -231,35 +246,55 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_kernel(const float* __rest
       unsigned ti = first ? 0xffffffffu : park_i[warp][w][lane];
       unsigned tau = __shfl_sync(0xffffffffu, td, 31);              // distance bits of the current 32nd smallest
       int qn = 0;
-      // four candidates per lane per iteration; a candidate is queued when its distance does not exceed the
-      // current 32nd distance (ties are over-included -- the merge orders them by index, so the result is exact)
-      for (int i0 = 0; i0 < cnt; i0 += 128) {
-        unsigned db[4];
-        bool any_pass = false;
+      // Two passes over sub-chunks of 1024 candidates (32 per lane, distances kept in registers):
+      //  pass 1  distances + each lane's two smallest (m0 <= m1);
+      //  bound   while no 32nd distance is known yet, bisect on the bit pattern for the smallest x (to 1/256 of
+      //          [min m1, max m0]) with at least 32 of the 64 lane minima <= x: an upper bound of the true 32nd
+      //          distance that typically admits only ~36 candidates;
+      //  pass 2  candidates <= bound are compacted into the warp queue and folded into the sorted top-32 by
+      //          bitonic sort + merge -- about two merges per query instead of one per ~30 admitted candidates.
+      for (int sub = 0; sub < cnt; sub += 1024) {
+        unsigned db[32];
+        unsigned m0 = 0xffffffffu, m1 = 0xffffffffu;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int i = i0 + u * 32 + lane;
-          db[u] = 0xffffffffu;
-          if (i < cnt) db[u] = __float_as_uint(sqdist3(qx, qy, qz, pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]));
-          any_pass |= (i < cnt) && db[u] <= tau;
+        for (int t = 0; t < 32; ++t) {
+          const int i = sub + t * 32 + lane;
+          unsigned x = 0xffffffffu;
+          if (i < cnt) x = __float_as_uint(sqdist3(qx, qy, qz, pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]));
+          db[t] = x;
+          m1 = min(m1, max(m0, x));
+          m0 = min(m0, x);
         }
-        if (!__any_sync(0xffffffffu, any_pass)) continue;
+        unsigned thr = tau;
+        if (thr == 0xffffffffu) {   // warp-uniform
+          unsigned hi = __reduce_max_sync(0xffffffffu, m0);   // >= 32 candidates are <= the largest lane minimum
+          unsigned lo = __reduce_min_sync(0xffffffffu, m1);
+          if (lo < hi) {
+#pragma unroll 1
+            for (int it = 0; it < 8 && lo < hi; ++it) {
+              const unsigned mid = lo + ((hi - lo) >> 1);
+              const int c = __popc(__ballot_sync(0xffffffffu, m0 <= mid)) + __popc(__ballot_sync(0xffffffffu, m1 <= mid));
+              if (c >= 32) hi = mid; else lo = mid + 1;
+            }
+          }
+          thr = hi;
+        }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int i = i0 + u * 32 + lane;
-          const bool pass = (i < cnt) && db[u] <= tau;
+        for (int t = 0; t < 32; ++t) {
+          const bool pass = db[t] <= thr && db[t] != 0xffffffffu;
           const unsigned m = __ballot_sync(0xffffffffu, pass);
           if (m == 0u) continue;
           if (pass) {
             const int pos = qn + __popc(m & lt_mask);
-            myd[pos] = db[u];
-            myi[pos] = (unsigned)(base + i);
+            myd[pos] = db[t];
+            myi[pos] = (unsigned)(base + sub + t * 32 + lane);
           }
           qn += __popc(m);
           __syncwarp();
           if (qn >= 32) {
             knn_merge(td, ti, myd[lane], myi[lane], lane, kmask);
             tau = __shfl_sync(0xffffffffu, td, 31);
+            thr = min(thr, tau);
             const int rem = qn - 32;
             const unsigned cd = lane < rem ? myd[32 + lane] : 0u, ci = lane < rem ? myi[32 + lane] : 0u;
             __syncwarp();
@@ -270,6 +305,12 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_kernel(const float* __rest
             __syncwarp();
             qn = rem;
           }
+        }
+        if (qn > 0) {   // flush so that the next sub-chunk starts from an exact 32nd distance
+          knn_merge(td, ti, lane < qn ? myd[lane] : 0xffffffffu, lane < qn ? myi[lane] : 0xffffffffu, lane, kmask);
+          tau = __shfl_sync(0xffffffffu, td, 31);
+          qn = 0;
+          __syncwarp();
         }
       }
       if (qn > 0) knn_merge(td, ti, lane < qn ? myd[lane] : 0xffffffffu, lane < qn ? myi[lane] : 0xffffffffu, lane, kmask);
