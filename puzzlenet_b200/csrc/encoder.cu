@@ -1297,9 +1297,13 @@ extern "C" int pz_offset_attention(const float* x, const float* Wq, const float*
 }
 
 extern "C" size_t pz_group_mlp_workspace_bytes(int B, int N, int D, int S, int K, int C1, int C2) {
-  (void)C2;
-  if (B < 1 || N < 1 || S < 1 || K < 1 || C1 < 1) return 0;
-  return align_up((size_t)B * N * C1 * sizeof(float), 256) + align_up((size_t)B * S * K * sizeof(int), 256) + 512;
+  if (B < 1 || N < 1 || S < 1 || K < 1 || C1 < 1 || C2 < 1 || D < 1) return 0;
+  const size_t fp32_path = align_up((size_t)B * N * C1 * sizeof(float), 256);
+  // bf16 path: feat_b [B*N, D], P [B*N, C1], Q [B*S, C1], W1f [C1, D], W2 [C2, C1] (all bf16)
+  const size_t bf16_path = align_up((size_t)B * N * D * 2, 256) + align_up((size_t)B * N * C1 * 2, 256) +
+                           align_up((size_t)B * S * C1 * 2, 256) + align_up((size_t)C1 * D * 2, 256) +
+                           align_up((size_t)C2 * C1 * 2, 256);
+  return (fp32_path > bf16_path ? fp32_path : bf16_path) + align_up((size_t)B * S * K * sizeof(int), 256) + 1024;
 }
 
 extern "C" int pz_group_mlp_maxpool(const float* xyz, const float* feat, const float* new_xyz, const int64_t* knn_idx,
@@ -1312,14 +1316,44 @@ extern "C" int pz_group_mlp_maxpool(const float* xyz, const float* feat, const f
   PZ_REQUIRE(K == 32, PZ_ERR_UNSUPPORTED, "pz_group_mlp_maxpool: K must be 32 (got %d)", K);
   PZ_REQUIRE(C1 <= 256, PZ_ERR_UNSUPPORTED, "pz_group_mlp_maxpool: C1 must be <= 256 (got %d)", C1);
   PZ_REQUIRE(((size_t)B * S * K) % 128 == 0, PZ_ERR_UNSUPPORTED, "pz_group_mlp_maxpool: B*S must be a multiple of 4");
-  PZ_REQUIRE(precision == PZ_PREC_FP32, PZ_ERR_UNSUPPORTED, "pz_group_mlp_maxpool: precision %d not available", precision);
+  PZ_REQUIRE(precision == PZ_PREC_FP32 || precision == PZ_PREC_BF16, PZ_ERR_ARG, "pz_group_mlp_maxpool: unknown precision %d", precision);
   cudaStream_t st = as_stream(stream);
   Arena a(workspace, workspace_bytes);
+  const size_t total = (size_t)B * S * K;
+  int* rows = a.take<int>(total);
+  if (precision == PZ_PREC_BF16) {
+    // tensor-core path: P = feat W1[:,3:]^T + b1 + W1[:,0:3] xyz (row GEMM), Q = W1[:,0:3] c, then the gathered GEMM
+    PZ_REQUIRE(D % 64 == 0 && (C1 == 128 || C1 == 256) && (C2 == 128 || C2 == 256) && ((size_t)B * N) % 128 == 0 &&
+                   total % 256 == 0,
+               PZ_ERR_UNSUPPORTED,
+               "pz_group_mlp_maxpool(bf16): needs D %% 64 == 0, C1,C2 in {128,256}, B*N %% 128 == 0, B*S %% 8 == 0");
+    __nv_bfloat16* feat_b = a.take<__nv_bfloat16>((size_t)B * N * D);
+    __nv_bfloat16* P = a.take<__nv_bfloat16>((size_t)B * N * C1);
+    __nv_bfloat16* Q = a.take<__nv_bfloat16>((size_t)B * S * C1);
+    __nv_bfloat16* w1f = a.take<__nv_bfloat16>((size_t)C1 * D);
+    __nv_bfloat16* w2b = a.take<__nv_bfloat16>((size_t)C2 * C1);
+    PZ_REQUIRE(workspace && a.ok(), PZ_ERR_WORKSPACE, "pz_group_mlp_maxpool: workspace %zu B < required %zu B",
+               workspace_bytes, a.used);
+    idx64_to_rows32_kernel<<<(int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096), 256, 0, st>>>(
+        knn_idx, total, (size_t)S * K, N, rows);
+    PZ_LAUNCH_CHECK();
+    PZ_TRY(launch_cvt_bf16(feat, D, B * N, D, feat_b, D, st));
+    PZ_TRY(launch_cvt_bf16(W1 + 3, 3 + D, C1, D, w1f, D, st));
+    PZ_TRY(launch_cvt_bf16(W2, C1, C2, C1, w2b, C1, st));
+    TcGemm g1;
+    g1.X = feat_b; g1.ldx = D; g1.W[0] = w1f; g1.ldw = D; g1.bias[0] = b1; g1.M = B * N; g1.Nout = C1; g1.K = D;
+    g1.Yb = P; g1.ldyb = C1; g1.xyz = xyz; g1.W1x[0] = W1; g1.ldw1x = 3 + D;
+    PZ_TRY(launch_tc_rowgemm(g1, st));
+    centre_proj_kernel<<<(int)(((size_t)B * S * C1 + 255) / 256), 256, 0, st>>>(new_xyz, W1, W1, 3 + D, B * S, B * S, C1, Q);
+    PZ_LAUNCH_CHECK();
+    TcGemm g2;
+    g2.X = P; g2.ldx = C1; g2.rows = rows; g2.Qb = Q; g2.W[0] = w2b; g2.ldw = C1; g2.bias[0] = b2; g2.M = (int)total;
+    g2.Nout = C2; g2.K = C1; g2.epi = 1; g2.relu = 1; g2.Yf = out; g2.ldyf = C2;
+    return launch_tc_gemm(g2, st);
+  }
   float* F = a.take<float>((size_t)B * N * C1);
-  int* rows = a.take<int>((size_t)B * S * K);
   PZ_REQUIRE(workspace && a.ok(), PZ_ERR_WORKSPACE, "pz_group_mlp_maxpool: workspace %zu B < required %zu B",
              workspace_bytes, a.used);
-  const size_t total = (size_t)B * S * K;
   idx64_to_rows32_kernel<<<(int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096), 256, 0, st>>>(
       knn_idx, total, (size_t)S * K, N, rows);
   PZ_LAUNCH_CHECK();

@@ -25,6 +25,20 @@ def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
     return t.contiguous()
 
 
+_WS_CACHE = {}
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    """Grow-only scratch per (device, stream): the fused ops need hundreds of MB at dataset shapes and a fresh
+    cudaMalloc per call would dominate their run time."""
+    key = (str(device), torch.cuda.current_stream(device).cuda_stream)
+    ws = _WS_CACHE.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1), device=device, dtype=torch.uint8)
+        _WS_CACHE[key] = ws
+    return ws
+
+
 def _i64c(t: torch.Tensor, name: str) -> torch.Tensor:
     _lib.require_cuda(t)
     if t.dtype != torch.int64:
@@ -158,7 +172,7 @@ def group_mlp_maxpool(xyz, points, new_xyz, idx, w1, b1, w2, b2, precision=_lib.
     C1, C2 = w1.shape[0], w2.shape[0]
     lib = _lib.load()
     ws_bytes = lib.pz_group_mlp_workspace_bytes(B, N, D, S, K, C1, C2)
-    ws = torch.empty(ws_bytes, device=xyz.device, dtype=torch.uint8)
+    ws = _workspace(ws_bytes, xyz.device)
     out = torch.empty(B, S, C2, device=xyz.device, dtype=torch.float32)
     with torch.cuda.device(xyz.device):
         _lib.call("pz_group_mlp_maxpool", xyz.data_ptr(), points.data_ptr(), new_xyz.data_ptr(), idx.data_ptr(),

@@ -61,6 +61,21 @@ def test_group_mlp_maxpool_matches_materialised_path(state_dict):
     assert rel_err(got, ref) < REL_FP32
 
 
+def test_group_mlp_maxpool_bf16(state_dict):
+    """Same fused op on the tcgen05 path (layer-1 split P - Q, gathered operand, max-pool epilogue): 2e-2."""
+    from puzzlenet_b200 import pointnet_util as pu
+    g = torch.Generator().manual_seed(2)
+    xyz = torch.rand(2, 1024, 3, generator=g) - 0.5
+    feat = torch.randn(2, 1024, 64, generator=g)
+    torch.manual_seed(8)
+    nx, npts, _, _, idx = po.sample_and_group(128, 0, 32, xyz, feat, knn=True, return_idx=True)
+    ref = torch.relu(po._lin(state_dict, "Encoder.mlp4", torch.relu(po._lin(state_dict, "Encoder.mlp3", npts)))).max(-2).values
+    got = pu.group_mlp_maxpool(xyz.to(DEV), feat.to(DEV), nx.to(DEV), idx.to(DEV),
+                               state_dict["Encoder.mlp3.weight"].to(DEV), state_dict["Encoder.mlp3.bias"].to(DEV),
+                               state_dict["Encoder.mlp4.weight"].to(DEV), state_dict["Encoder.mlp4.bias"].to(DEV), precision=1)
+    assert rel_err(got, ref) < 2e-2
+
+
 def test_encoder_intermediates(cuda_model, state_dict, goldens):
     fpc, _ = synthetic_pairs(2, seed=64)
     torch.manual_seed(FPS_SEED)
