@@ -227,7 +227,7 @@ def run_gpu_arm(args):
 
     # ---- e2e: pinned host inputs -> H2D -> predict5 -> D2H of the results, every step
     out_hosts = [(torch.empty(B, 6).pin_memory(), torch.empty(B, 2, 1024).pin_memory(), torch.empty(B, 2, 1024).pin_memory())
-                 for _ in range(2)]
+                 for _ in range(args.pipes)]
     h2d = sum(t.numel() * t.element_size() for t in host[0])
     d2h = sum(t.numel() * t.element_size() for t in out_hosts[0])
 
@@ -235,18 +235,19 @@ def run_gpu_arm(args):
         f, m, s = host[i % nsets]
         fd, md = f.to(dev, non_blocking=True), m.to(dev, non_blocking=True)
         out, _, de_f, de_m = model.predict5(make_batch(fd, md), 0, starts=s)
-        out_host = out_hosts[i % 2]
+        out_host = out_hosts[i % len(out_hosts)]
         out_host[0].copy_(out, non_blocking=True)
         out_host[1].copy_(de_f, non_blocking=True)
         out_host[2].copy_(de_m, non_blocking=True)
 
     # two CUDA streams alternate so that the copies and the latency-bound stages (FPS chain, pose MLP) of one
     # batch overlap the tensor-core stages of the other; every copy and kernel of all K steps is inside the region
-    pipes = [torch.cuda.Stream(device=dev) for _ in range(2)]
+    pipes = [torch.cuda.Stream(device=dev) for _ in range(args.pipes)]
+    model.cuda_graphs = not args.no_graphs          # one captured CUDA graph per stream replays the ~75 launches
 
     def run_e2e(n):
         for i in range(n):
-            with torch.cuda.stream(pipes[i % 2]):
+            with torch.cuda.stream(pipes[i % len(pipes)]):
                 step_e2e(i)
 
     run_e2e(max(4, args.warmup))
@@ -262,6 +263,7 @@ def run_gpu_arm(args):
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1)
+    model.cuda_graphs = False
     clocks = sampler.stop() if sampler else None
 
     # ---- reduce over ranks: max time, total pairs
@@ -339,7 +341,8 @@ def run_gpu_arm(args):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / args.steps,
-                "how": "public API predict5 from pinned host buffers, batches alternate over 2 CUDA streams"},
+                "how": f"public API predict5 from pinned host buffers; batches alternate over {args.pipes} CUDA streams"
+                       + ("" if args.no_graphs else ", each replaying one captured CUDA graph per forward")},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "roofline_all": {k: {"bound": v["bound"], "achieved": round(v["achieved"], 3), "unit": v["unit"],
@@ -366,6 +369,8 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("PZ_PRECISION", "bf16"), choices=["fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--single-precision", action="store_true", help="skip the short run of the other precision")
+    ap.add_argument("--pipes", type=int, default=3, help="CUDA streams the e2e leg alternates batches over")
+    ap.add_argument("--no-graphs", action="store_true", help="e2e leg: eager launches instead of CUDA-graph replay")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

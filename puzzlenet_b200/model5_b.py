@@ -237,6 +237,9 @@ class TouchedRegraster(_Base):
         self.precision = "fp32"
         self._ws = {}
         self._pack_keys = {}
+        self._graphs = {}
+        self._capture_stream = None
+        self.cuda_graphs = False      # opt-in: replay one captured CUDA graph per forward (see _graph_replay)
 
     # ---- weights as C structs (rebuilt per call: ~100 data_ptr() reads, no device work)
     def _head_struct(self) -> _lib.PzHeadWeights:
@@ -263,6 +266,83 @@ class TouchedRegraster(_Base):
                 self._ws.pop(next(iter(self._ws)))
             self._ws[key] = ws
         return ws
+
+    def _param_key(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def _launch(self, fpc, mrpc, starts, need, ws, outs, reuse_packs=None):
+        """Allocate (unless given) the outputs and the workspace and enqueue pz_predict5 on the current stream."""
+        B, dev = fpc.shape[0], fpc.device
+        f32 = dict(device=dev, dtype=torch.float32)
+        if outs is None:
+            out6, de_fpcb, de_mrpcb = torch.empty(B, 6, **f32), torch.empty(B, 2, 1024, **f32), torch.empty(B, 2, 1024, **f32)
+            x2f = x2m = af = am = None
+            if need:
+                x2f, x2m = torch.empty(B, 256, 3, **f32), torch.empty(B, 256, 3, **f32)
+                af, am = torch.empty(B, 256, 256, **f32), torch.empty(B, 256, 256, **f32)
+            outs = (out6, de_fpcb, de_mrpcb, x2f, af, x2m, am)
+        out6, de_fpcb, de_mrpcb, x2f, af, x2m, am = outs
+        enc = (_lib.PzEncoderWeights * 2)(_encoder_struct(self.Encoder), _encoder_struct(self.Encoder2))
+        heads = self._head_struct()
+        if ws is None:
+            ws = self._workspace(B, dev)
+        flags = _lib.PZ_FLAG_NEED if need else 0
+        if reuse_packs is None and self.precision == "bf16":
+            # the bf16 weight packs live in the workspace: reusable while no parameter was touched (in-place writes
+            # bump _version, reallocation changes data_ptr) and the workspace / precision are the same
+            key = self._param_key()
+            reuse_packs = self._pack_keys.get(ws.data_ptr()) == key
+            if len(self._pack_keys) >= 8:
+                self._pack_keys.clear()
+            self._pack_keys[ws.data_ptr()] = key
+        elif self.precision != "bf16":
+            self._pack_keys.pop(ws.data_ptr(), None)
+        if reuse_packs:
+            flags |= _lib.PZ_FLAG_REUSE_PACKS
+        with torch.cuda.device(dev):
+            _lib.call("pz_predict5", enc, ctypes.byref(heads), fpc.data_ptr(), mrpc.data_ptr(), B, starts.data_ptr(),
+                      PRECISIONS[self.precision], flags, out6.data_ptr(), de_fpcb.data_ptr(),
+                      de_mrpcb.data_ptr(), _ptr(x2f), _ptr(af), _ptr(x2m), _ptr(am), ws.data_ptr(), ws.numel(),
+                      _lib.stream_ptr())
+        return outs
+
+    def _graph_replay(self, fpc, mrpc, starts, need):
+        """CUDA-graph mode (``model.cuda_graphs = True``): the ~75 launches of one forward (both streams of the
+        internal fork/join included) are captured once per (batch size, need, precision, stream) and replayed.
+        Inputs are copied into static buffers; the returned tensors are static too -- they are overwritten by
+        the next call on the same stream.  A change of any parameter re-captures."""
+        B, dev = fpc.shape[0], fpc.device
+        stream = torch.cuda.current_stream(dev)
+        key = (B, bool(need), self.precision, str(dev), stream.cuda_stream)
+        g = self._graphs.get(key)
+        pkey = self._param_key()
+        if g is None or g["pkey"] != pkey:
+            f32 = dict(device=dev, dtype=torch.float32)
+            st = dict(fpc=torch.empty(B, 1024, 3, **f32), mrpc=torch.empty(B, 1024, 3, **f32),
+                      starts=torch.empty(4, B, device=dev, dtype=torch.int64),
+                      ws=torch.empty(_lib.load().pz_predict5_workspace_bytes(B), device=dev, dtype=torch.uint8))
+            st["fpc"].copy_(fpc); st["mrpc"].copy_(mrpc); st["starts"].copy_(starts)
+            outs = self._launch(st["fpc"], st["mrpc"], st["starts"], need, st["ws"], None, reuse_packs=False)  # builds the packs
+            stream.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            cap = stream
+            if stream.cuda_stream == 0:          # capture is not allowed on the legacy default stream
+                if self._capture_stream is None:
+                    self._capture_stream = torch.cuda.Stream(device=dev)
+                cap = self._capture_stream
+            with torch.cuda.graph(graph, stream=cap):
+                self._launch(st["fpc"], st["mrpc"], st["starts"], need, st["ws"], outs,
+                             reuse_packs=self.precision == "bf16")
+            g = dict(pkey=pkey, st=st, outs=outs, graph=graph)
+            if len(self._graphs) >= 8:
+                self._graphs.clear()
+            self._graphs[key] = g
+        st = g["st"]
+        st["fpc"].copy_(fpc, non_blocking=True)
+        st["mrpc"].copy_(mrpc, non_blocking=True)
+        st["starts"].copy_(starts, non_blocking=True)
+        g["graph"].replay()
+        return g["outs"]
 
     def forward(self, batch, bat):
         # The reference's forward() calls predict4, which needs modules that are commented out of
@@ -293,34 +373,10 @@ class TouchedRegraster(_Base):
                                   torch.randint(0, 1024, (B,), dtype=torch.long),
                                   torch.randint(0, 512, (B,), dtype=torch.long)])
         starts = starts.to(device=dev, dtype=torch.int64, non_blocking=True).contiguous()
-        f32 = dict(device=dev, dtype=torch.float32)
-        out6 = torch.empty(B, 6, **f32)
-        de_fpcb = torch.empty(B, 2, 1024, **f32)
-        de_mrpcb = torch.empty(B, 2, 1024, **f32)
-        x2f = x2m = af = am = None
-        if need:
-            x2f, x2m = torch.empty(B, 256, 3, **f32), torch.empty(B, 256, 3, **f32)
-            af, am = torch.empty(B, 256, 256, **f32), torch.empty(B, 256, 256, **f32)
-        enc = (_lib.PzEncoderWeights * 2)(_encoder_struct(self.Encoder), _encoder_struct(self.Encoder2))
-        heads = self._head_struct()
-        ws = self._workspace(B, dev)
-        flags = _lib.PZ_FLAG_NEED if need else 0
-        if self.precision == "bf16":
-            # the bf16 weight packs live in the workspace: reusable while no parameter was touched (in-place writes
-            # bump _version, reallocation changes data_ptr) and the workspace / precision are the same
-            key = tuple((p.data_ptr(), p._version) for p in self.parameters())
-            if self._pack_keys.get(ws.data_ptr()) == key:
-                flags |= _lib.PZ_FLAG_REUSE_PACKS
-            if len(self._pack_keys) >= 8:
-                self._pack_keys.clear()
-            self._pack_keys[ws.data_ptr()] = key
+        if self.cuda_graphs:
+            out6, de_fpcb, de_mrpcb, x2f, af, x2m, am = self._graph_replay(fpc, mrpc, starts, need)
         else:
-            self._pack_keys.pop(ws.data_ptr(), None)
-        with torch.cuda.device(dev):
-            _lib.call("pz_predict5", enc, ctypes.byref(heads), fpc.data_ptr(), mrpc.data_ptr(), B, starts.data_ptr(),
-                      PRECISIONS[self.precision], flags, out6.data_ptr(), de_fpcb.data_ptr(),
-                      de_mrpcb.data_ptr(), _ptr(x2f), _ptr(af), _ptr(x2m), _ptr(am), ws.data_ptr(), ws.numel(),
-                      _lib.stream_ptr())
+            out6, de_fpcb, de_mrpcb, x2f, af, x2m, am = self._launch(fpc, mrpc, starts, need, None, None)
         if not need:
             return out6, out6, de_fpcb, de_mrpcb
         return out6, [0], x2f, af, x2m, am, de_fpcb, de_mrpcb

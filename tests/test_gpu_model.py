@@ -219,3 +219,31 @@ def test_predict5_bf16_need_and_determinism(bf16_model):
     b = bf16_model.predict5(batch, 0, need=True, starts=starts)
     assert all(torch.equal(x, y) for x, y in zip(a[2:], b[2:])) and torch.equal(a[0], b[0])
     np.testing.assert_allclose(a[3].sum(-1).cpu().numpy(), 1.0, atol=1e-4)     # mean of 4 softmax maps
+
+
+def test_cuda_graph_mode_matches_eager(cuda_model):
+    """CUDA-graph replay (fork/join onto the internal side stream captured too) == eager, fp32 and bf16."""
+    fpc, mrpc = synthetic_pairs(4, seed=21)
+    starts = torch.stack([torch.randint(0, n, (4,), generator=torch.Generator().manual_seed(i))
+                          for i, n in enumerate((1024, 512, 1024, 512))])
+    batch = make_batch(fpc.to(DEV), mrpc.to(DEV))
+    try:
+        for prec in ("fp32", "bf16"):
+            cuda_model.precision = prec
+            cuda_model.cuda_graphs = False
+            eager = [t.clone() for t in cuda_model.predict5(batch, 0, starts=starts)[1:]]
+            cuda_model.cuda_graphs = True
+            for _ in range(3):                                   # capture, then two replays
+                graphed = cuda_model.predict5(batch, 0, starts=starts)[1:]
+            torch.cuda.synchronize()
+            assert all(torch.equal(a, b) for a, b in zip(eager, graphed)), prec
+            # different inputs through the same graph
+            fpc2, mrpc2 = synthetic_pairs(4, seed=22)
+            b2 = make_batch(fpc2.to(DEV), mrpc2.to(DEV))
+            g2 = [t.clone() for t in cuda_model.predict5(b2, 0, starts=starts)[1:]]
+            cuda_model.cuda_graphs = False
+            e2 = cuda_model.predict5(b2, 0, starts=starts)[1:]
+            assert all(torch.equal(a, b) for a, b in zip(e2, g2)), prec
+    finally:
+        cuda_model.cuda_graphs = False
+        cuda_model.precision = "fp32"
