@@ -770,17 +770,11 @@ static int encoder_forward_bf16(const PzEncoderWeights* w, int E, int B, const f
   prof_mark("_side_begin", sg, 1);
   PZ_TRY(launch_fps(xyz, C, NPTS, start1, S1, o.fps1, nullptr, s.nx1, sg));
   prof_mark("fps1", sg, 1);
-  centre_proj_kernel<<<(int)(((size_t)C * S1 * C1A + 255) / 256), 256, 0, sg>>>(s.nx1, wa.mlp3_w, wb.mlp3_w, 3 + D0,
-                                                                                 B * S1, C * S1, C1A, s.Q1);
-  PZ_LAUNCH_CHECK();
   PZ_TRY(launch_knn(s.nx1, xyz, C, S1, NPTS, KNN, o.knn1, s.knn1r, nullptr, sg));
   prof_mark("knn1", sg, 1);
   PZ_CUDA(cudaEventRecord(ss->join_a, sg));
   PZ_TRY(launch_fps(s.nx1, C, S1, start2, S2, o.fps2, nullptr, nx2, sg));
   prof_mark("fps2", sg, 1);
-  centre_proj_kernel<<<(int)(((size_t)C * S2 * C2A + 255) / 256), 256, 0, sg>>>(nx2, wa.mlp5_w, wb.mlp5_w, 3 + C1B,
-                                                                                 B * S2, C * S2, C2A, s.Q2);
-  PZ_LAUNCH_CHECK();
   PZ_TRY(launch_knn(nx2, s.nx1, C, S2, S1, KNN, o.knn2, s.knn2r, nullptr, sg));
   prof_mark("knn2", sg, 1);
   PZ_CUDA(cudaEventRecord(ss->join_b, sg));
@@ -801,7 +795,7 @@ static int encoder_forward_bf16(const PzEncoderWeights* w, int E, int B, const f
   prof_mark("_wait_geometry1", st);
   {
     TcGemm g;  // f1f = max_k relu(W4 relu(P1[j] - Q1[s]) + b4)
-    g.X = s.P1; g.ldx = C1A; g.rows = s.knn1r; g.Qb = s.Q1; g.W[0] = wpa + WP_W4; g.W[1] = wpb + WP_W4; g.ldw = C1A;
+    g.X = s.P1; g.ldx = C1A; g.rows = s.knn1r; g.centers = s.nx1; g.W1x[0] = wa.mlp3_w; g.W1x[1] = wb.mlp3_w; g.ldw1x = 3 + D0; g.W[0] = wpa + WP_W4; g.W[1] = wpb + WP_W4; g.ldw = C1A;
     g.bias[0] = wa.mlp4_b; g.bias[1] = wb.mlp4_b; g.rows_per_wset = B * S1 * KNN; g.M = C * S1 * KNN; g.Nout = C1B;
     g.K = C1A; g.epi = 1; g.relu = 1; g.Yf = o.f1f; g.ldyf = C1B; g.Yb = s.f1f_b; g.ldyb = C1B;
     PZ_TRY(launch_tc_gemm(g, st));
@@ -821,7 +815,7 @@ static int encoder_forward_bf16(const PzEncoderWeights* w, int E, int B, const f
   float* cat_f = o.att_cat;                     // fp32 copy only when the caller asks for it
   {
     TcGemm g;
-    g.X = s.P2; g.ldx = C2A; g.rows = s.knn2r; g.Qb = s.Q2; g.W[0] = wpa + WP_W6; g.W[1] = wpb + WP_W6; g.ldw = C2A;
+    g.X = s.P2; g.ldx = C2A; g.rows = s.knn2r; g.centers = nx2; g.W1x[0] = wa.mlp5_w; g.W1x[1] = wb.mlp5_w; g.ldw1x = 3 + C1B; g.W[0] = wpa + WP_W6; g.W[1] = wpb + WP_W6; g.ldw = C2A;
     g.bias[0] = wa.mlp6_b; g.bias[1] = wb.mlp6_b; g.rows_per_wset = B * S2 * KNN; g.M = C * S2 * KNN; g.Nout = C2B;
     g.K = C2A; g.epi = 1; g.relu = 1; g.Yb = cat_b + 4 * CATT; g.ldyb = 1280;
     if (cat_f) { g.Yf = cat_f + 4 * CATT; g.ldyf = 1280; }
@@ -1344,10 +1338,8 @@ extern "C" int pz_group_mlp_maxpool(const float* xyz, const float* feat, const f
     g1.X = feat_b; g1.ldx = D; g1.W[0] = w1f; g1.ldw = D; g1.bias[0] = b1; g1.M = B * N; g1.Nout = C1; g1.K = D;
     g1.Yb = P; g1.ldyb = C1; g1.xyz = xyz; g1.W1x[0] = W1; g1.ldw1x = 3 + D;
     PZ_TRY(launch_tc_rowgemm(g1, st));
-    centre_proj_kernel<<<(int)(((size_t)B * S * C1 + 255) / 256), 256, 0, st>>>(new_xyz, W1, W1, 3 + D, B * S, B * S, C1, Q);
-    PZ_LAUNCH_CHECK();
     TcGemm g2;
-    g2.X = P; g2.ldx = C1; g2.rows = rows; g2.Qb = Q; g2.W[0] = w2b; g2.ldw = C1; g2.bias[0] = b2; g2.M = (int)total;
+    g2.X = P; g2.ldx = C1; g2.rows = rows; g2.centers = new_xyz; g2.W1x[0] = W1; g2.ldw1x = 3 + D; (void)Q; g2.W[0] = w2b; g2.ldw = C1; g2.bias[0] = b2; g2.M = (int)total;
     g2.Nout = C2; g2.K = C1; g2.epi = 1; g2.relu = 1; g2.Yf = out; g2.ldyf = C2;
     return launch_tc_gemm(g2, st);
   }

@@ -51,7 +51,11 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcGemm g) {
   const uint32_t full_bar = bars_base, empty_bar = bars_base + 8 * NST;
   const uint32_t accf_bar = bars_base + 16 * NST, acce_bar = accf_bar + 16;
   const uint32_t tmem_slot = acce_bar + 16;
-  const uint32_t qstage_base = tmem_slot + 16;   // GATHER: NST x [ROWS/32 groups][64] fp32 Q tiles (16-byte aligned)
+  // GATHER extras (16-byte aligned): NST x [ROWS/32 groups][64] bf16 Q tiles, NST x [ROWS/32][4] fp32 group centres,
+  // and the layer-1 xyz weights W1[:,0:3] of all K channels as float4 (resident)
+  const uint32_t qstage_base = tmem_slot + 16;
+  const uint32_t cstage_base = qstage_base + NST * (ROWS / 32) * 128;
+  const uint32_t w1x_base = cstage_base + NST * (ROWS / 32) * 16;
   __shared__ float sxyz[ROWS * 3];
   uint8_t* smem_gen = tc_smem_raw + (smem_base - smem_u32(tc_smem_raw));   // generic pointer to smem_base
 
@@ -100,6 +104,12 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcGemm g) {
     }
     fence_proxy_async();
   }
+  if (GATHER) {
+    float4* w1x = reinterpret_cast<float4*>(smem_gen + (w1x_base - smem_base));
+    const float* src = g.W1x[wset];
+    for (int k = tid; k < g.K; k += THREADS)
+      w1x[k] = make_float4(src[(size_t)k * g.ldw1x], src[(size_t)k * g.ldw1x + 1], src[(size_t)k * g.ldw1x + 2], 0.f);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -132,9 +142,12 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcGemm g) {
 #pragma unroll
         for (int i = 0; i < GCH; ++i)
           cp_async16(st_addr + sw128(r0 + i * 16, gc), g.X + (size_t)src[i] * g.ldx + kb * KB + gc * 8);
-        if (gt < QCH)
-          cp_async16(qstage_base + s * (QCH * 16) + gt * 16,
-                     g.Qb + (size_t)((row0 >> 5) + (gt >> 3)) * g.K + kb * KB + (gt & 7) * 8);
+        if (gt < (ROWS / 32) * 3) {   // the stage's group centres (fp32 xyz), 4-byte copies into a padded [g][4] tile
+          const int gi = gt / 3, d = gt - gi * 3;
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(cstage_base + s * ((ROWS / 32) * 16) + gi * 16 + d * 4),
+                       "l"(g.centers + (size_t)((row0 >> 5) + gi) * 3 + d)
+                       : "memory");
+        }
         cp_async_commit();
       };
       int j = grp;
@@ -146,9 +159,23 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcGemm g) {
         } else {
           cp_async_wait<0>();
         }
-        // the Q tile was copied by other threads of the group
+        // the centres were copied by other threads of the group
         asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory");
         const uint32_t s = (uint32_t)j % NST;
+        {  // Q[g][k] = W1[k,0:3] . centre_g for the 64 channels of this k-block: (ROWS/32)*64 values, 128 threads
+          const int kb = j % kblocks;
+          const float4* w1x = reinterpret_cast<const float4*>(smem_gen + (w1x_base - smem_base)) + kb * KB;
+          const float4* cs = reinterpret_cast<const float4*>(smem_gen + (cstage_base + s * ((ROWS / 32) * 16) - smem_base));
+          __nv_bfloat162* qt = reinterpret_cast<__nv_bfloat162*>(smem_gen + (qstage_base + s * (QCH * 16) - smem_base));
+#pragma unroll
+          for (int e = gt; e < (ROWS / 32) * 32; e += 128) {   // one bf16 pair per iteration
+            const int gi = e >> 5, k2 = (e & 31) * 2;
+            const float4 c = cs[gi], wa = w1x[k2], wb = w1x[k2 + 1];
+            qt[e] = __floats2bfloat162_rn(fmaf(wa.x, c.x, fmaf(wa.y, c.y, wa.z * c.z)),
+                                          fmaf(wb.x, c.x, fmaf(wb.y, c.y, wb.z * c.z)));
+          }
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory");
         uint8_t* st_gen = smem_gen + (stages_base + s * STAGE_BYTES - smem_base);
         // packed bf16x2 arithmetic: relu(p - q) on two channels per instruction (HFMA2.BF16 rounds once)
         const uint4* qs = reinterpret_cast<const uint4*>(smem_gen + (qstage_base + s * (QCH * 16) - smem_base));
@@ -373,7 +400,8 @@ static int tc_launch(const TcGemm& g, cudaStream_t st) {
   const int kblocks = g.K / KB;
   const size_t resident = RESIDENT ? (size_t)NCHB * kblocks * 128 * 128 : 0;
   const size_t stage = (RESIDENT ? 0 : (size_t)NCHB * 128 * 128) + (size_t)ROWS * 128;
-  const size_t smem = 1024 + resident + NST * stage + 8 * (2 * NST + 4) + 32 + (GATHER ? (size_t)NST * (ROWS / 32) * 128 : 0);
+  const size_t smem = 1024 + resident + NST * stage + 8 * (2 * NST + 4) + 32 +
+                      (GATHER ? (size_t)NST * (ROWS / 32) * (128 + 16) + (size_t)g.K * 16 : 0);
   PZ_REQUIRE(smem <= 227 * 1024, PZ_ERR_UNSUPPORTED, "tc_gemm: needs %zu B of shared memory (K=%d too large for a resident weight)", smem, g.K);
   auto kern = tc_gemm_kernel<ROWS, NCHB, RESIDENT, GATHER, NST>;
   PZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -397,7 +425,7 @@ int launch_tc_gemm(const TcGemm& g, cudaStream_t st) {
   const int nsets = (g.rows_per_wset > 0 && g.M > g.rows_per_wset) ? 2 : 1;
   if (nsets == 2) PZ_REQUIRE(g.W[1] && g.M == 2 * g.rows_per_wset, PZ_ERR_ARG, "tc_gemm: two weight sets need M == 2*rows_per_wset");
   if (g.rows) {  // gathered B, resident weights
-    PZ_REQUIRE(g.Qb && g.epi == 1, PZ_ERR_ARG, "tc_gemm: gathered operand needs Qb and the group-max epilogue");
+    PZ_REQUIRE(g.centers && g.W1x[0] && g.epi == 1, PZ_ERR_ARG, "tc_gemm: gathered operand needs centres, W1x and the group-max epilogue");
     if (g.Nout == 128 && g.K <= 256) {
       PZ_REQUIRE(g.M % (256 * nsets) == 0, PZ_ERR_UNSUPPORTED, "tc_gemm: M=%d must be a multiple of %d", g.M, 256 * nsets);
       return tc_launch<256, 1, true, true, 4>(g, st);

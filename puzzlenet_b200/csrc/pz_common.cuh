@@ -125,7 +125,8 @@ struct TcGemm {
   const __nv_bfloat16* X = nullptr;                // plain: activations [M, K]; gathered: P [*, K]
   int ldx = 0;
   const int* rows = nullptr;                       // gathered: source row of P for each of the M rows
-  const __nv_bfloat16* Qb = nullptr;               // gathered: [M/32, K] bf16, X[r] = relu(P[rows[r]] - Qb[r/32])
+  const float* centers = nullptr;                  // gathered: [M/32, 3] fp32 group centres; X[r] = relu(P[rows[r]] - Q[r/32])
+                                                   //   with Q[g,k] = W1x[k,0:3] . centers[g] computed per stage in smem
   int M = 0, Nout = 0, K = 0;
   int epi = 0;                                     // 0 store rows, 1 max over groups of 32 rows, 2 max over the tile's rows
   int relu = 0;
