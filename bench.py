@@ -206,6 +206,17 @@ def run_gpu_arm(args):
     step_ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = sum(step_ms)
 
+    # ---- per-kernel durations for the rooflines: the same steps once more with the internal side stream switched
+    # off, so that every stage's CUDA-event time is its own (in the timed region above the geometry chain overlaps
+    # the feature chain and inflates both)
+    lib.pz_profile_enable(2)
+    for i in range(min(args.steps, 20)):
+        flush.zero_()
+        step_resident(i)
+    torch.cuda.synchronize()
+    calls_serial, stages_serial = _lib.profile_collect()
+    lib.pz_profile_enable(0)
+
     # ---- the other precision of BASELINE configs[1] ("fp32 and bf16"), same protocol, fewer steps
     other = None
     other_prec = "fp32" if args.precision == "bf16" else "bf16"
@@ -282,10 +293,15 @@ def run_gpu_arm(args):
 
     # ---- roofline of the dominant stage (live per-stage CUDA events from the timed steps)
     peaks = _peaks()
-    agg = {}
-    for name, ms in stages:
-        agg[name] = agg.get(name, 0.0) + ms
-    per_step = {k: v / max(calls, 1) for k, v in agg.items()}
+    def per_step_of(stage_list, ncalls):
+        agg = {}
+        for name, ms in stage_list:
+            if not name.startswith("_"):
+                agg[name] = agg.get(name, 0.0) + ms
+        return {k: v / max(ncalls, 1) for k, v in agg.items()}
+
+    per_step_overlapped = per_step_of(stages, calls)
+    per_step = per_step_of(stages_serial, calls_serial)
     clouds = 2 * B
     # algorithmic work of each stage per step: FLOPs for the dense stages (tensor bound), compulsory
     # bytes for the geometry stages (they are latency/issue bound, the HBM fraction is reported
@@ -318,7 +334,16 @@ def run_gpu_arm(args):
             r["note"] = tensor_note
         return r
 
+    # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed ncu --set full
+    # captures of this same command: profiles/r01_top_kernels_bf16.txt, profiles/r01_prof_knn.txt (bf16 path)
+    ncu_traffic = {"sg1_gather_layer2_maxpool": 58.84e6 + 3.92e6, "sg2_gather_layer2_maxpool": 54.84e6 + 3.96e6,
+                   "tail_linear_maxpool": 89.18e6 + 4.42e6, "fps1": 1.62e6, "knn1": 2.38e6,
+                   "attn_softmax_av": 41.97e6 + 0.08e6} if args.precision == "bf16" else {}
     rooflines = {k: roof(k) for k in work if per_step.get(k, 0) > 0}
+    for k, r in rooflines.items():
+        if k in ncu_traffic:
+            r["traffic"] = ncu_traffic[k]
+            r["traffic_source"] = "ncu --set full, profiles/r01_top_kernels_bf16.txt (per launch, bytes)"
     # dominant kernel = the stage with the largest live time among those with a defined roofline
     roofline = rooflines[max(rooflines, key=lambda k: per_step[k])] if rooflines else None
 
@@ -349,6 +374,10 @@ def run_gpu_arm(args):
                              "frac": round(v["frac"], 5)} for k, v in rooflines.items()},
         "cpu_baseline": cpu_baseline,
         "stages_ms_per_step": {k: round(v, 4) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])},
+        "stages_note": "stages_ms_per_step: CUDA events, stages back to back on one stream (used for the rooflines); "
+                       "stages_ms_per_step_timed_region: the same events inside the timed region, where the geometry chain "
+                       "runs on a second stream and overlaps the feature chain",
+        "stages_ms_per_step_timed_region": {k: round(v, 4) for k, v in sorted(per_step_overlapped.items(), key=lambda kv: -kv[1])},
         other_prec + "_path": ({"value": B * other[1] * world / (other_ms / 1e3), "unit": UNIT,
                                 "ms_per_step": other_ms / other[1], "steps": other[1]} if other else None),
         "gflop_per_pair_reference_count": FLOP_PER_PAIR_REFERENCE / 1e9,

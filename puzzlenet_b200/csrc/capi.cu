@@ -34,6 +34,7 @@ struct ProfSet {
   bool created = false;
 };
 static bool g_prof_on = false;
+static bool g_prof_serial = false;
 static std::vector<ProfSet>* g_sets = nullptr;
 static int g_cur = -1;
 static std::mutex g_prof_mu;
@@ -63,6 +64,8 @@ void prof_mark(const char* stage, cudaStream_t st, int lane) {
   cudaEventRecord(s.ev[s.n], st);
 }
 
+bool prof_serial() { return g_prof_serial; }
+
 int side_stream(SideStream** out) {
   static std::mutex mu;
   static SideStream per_device[64];
@@ -88,6 +91,7 @@ extern "C" long long pz_launch_count(void) { return pz::g_launches.load(); }
 extern "C" int pz_profile_enable(int on) {
   std::lock_guard<std::mutex> lk(pz::g_prof_mu);
   pz::g_prof_on = on != 0;
+  pz::g_prof_serial = on == 2;
   pz::g_cur = -1;
   return 0;
 }

@@ -763,20 +763,22 @@ static int encoder_forward_bf16(const PzEncoderWeights* w, int E, int B, const f
   // it runs on the side stream while the feature chain (stem, layer-1 GEMM) runs on the caller's stream.
   SideStream* ss = nullptr;
   PZ_TRY(side_stream(&ss));
-  static const bool serial = getenv("PZ_NO_SIDE_STREAM") != nullptr;   // profiling aid: clean per-stage times
+  static const bool env_serial = getenv("PZ_NO_SIDE_STREAM") != nullptr;   // profiling aid: clean per-stage times
+  const bool serial = env_serial || prof_serial();
   cudaStream_t sg = serial ? st : ss->stream;
+  const int gl = serial ? 0 : 1;   // profiler lane of the geometry marks
   PZ_CUDA(cudaEventRecord(ss->fork, st));
   PZ_CUDA(cudaStreamWaitEvent(sg, ss->fork, 0));
-  prof_mark("_side_begin", sg, 1);
+  prof_mark("_side_begin", sg, gl);
   PZ_TRY(launch_fps(xyz, C, NPTS, start1, S1, o.fps1, nullptr, s.nx1, sg));
-  prof_mark("fps1", sg, 1);
+  prof_mark("fps1", sg, gl);
   PZ_TRY(launch_knn(s.nx1, xyz, C, S1, NPTS, KNN, o.knn1, s.knn1r, nullptr, sg));
-  prof_mark("knn1", sg, 1);
+  prof_mark("knn1", sg, gl);
   PZ_CUDA(cudaEventRecord(ss->join_a, sg));
   PZ_TRY(launch_fps(s.nx1, C, S1, start2, S2, o.fps2, nullptr, nx2, sg));
-  prof_mark("fps2", sg, 1);
+  prof_mark("fps2", sg, gl);
   PZ_TRY(launch_knn(nx2, s.nx1, C, S2, S1, KNN, o.knn2, s.knn2r, nullptr, sg));
-  prof_mark("knn2", sg, 1);
+  prof_mark("knn2", sg, gl);
   PZ_CUDA(cudaEventRecord(ss->join_b, sg));
 
   stem_kernel<<<C * NPTS / 128, 128, 0, st>>>(xyz, stem_of(wa), stem_of(wb), B, xfeat, s.xfeat_b);

@@ -53,6 +53,7 @@ struct SideStream {
   cudaEvent_t fork = nullptr, join_a = nullptr, join_b = nullptr;
 };
 int side_stream(SideStream** out);
+bool prof_serial();   // pz_profile_enable(2): run the geometry chain on the caller's stream (clean per-stage times)
 
 static inline cudaStream_t as_stream(pz_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
