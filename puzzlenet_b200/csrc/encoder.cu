@@ -831,7 +831,21 @@ static int encoder_forward_bf16(const PzEncoderWeights* w, int E, int B, const f
 
   // ---- 4 x offset attention
   const int rows = C * LATT;
-  for (int l = 0; l < 4; ++l) {
+  static const bool fused_attn = !(getenv("PZ_FUSED_ATTN") && getenv("PZ_FUSED_ATTN")[0] == '0');
+  for (int l = 0; l < 4 && fused_attn; ++l) {   // one kernel per layer: nothing but x and out touches HBM
+    AttnLayerTc p;
+    p.x = l == 0 ? cat_b + 4 * CATT : cat_b + (l - 1) * CATT; p.ldx = 1280;
+    p.wqkv[0] = wpa + WP_ATT + (size_t)l * WP_ATT_STRIDE; p.wqkv[1] = wpb + WP_ATT + (size_t)l * WP_ATT_STRIDE;
+    p.wo[0] = p.wqkv[0] + 384 * CATT; p.wo[1] = p.wqkv[1] + 384 * CATT;
+    p.bqkv[0] = s.bqkv + (size_t)l * 384; p.bqkv[1] = s.bqkv + ((size_t)(E - 1) * 4 + l) * 384;
+    p.bo[0] = wa.o_b[l]; p.bo[1] = wb.o_b[l];
+    p.clouds_per_set = B; p.yb = cat_b + l * CATT; p.ldyb = 1280;
+    if (cat_f) { p.yf = cat_f + l * CATT; p.ldyf = 1280; }
+    p.attn = o.attention; p.attn_mode = o.attention ? (l == 0 ? 1 : (l == 3 ? 3 : 2)) : 0;
+    PZ_TRY(launch_attention_layer_tc(p, C, st));
+    prof_mark("attn_layer_fused", st);
+  }
+  for (int l = 0; l < 4 && !fused_attn; ++l) {
     const __nv_bfloat16* xb = l == 0 ? cat_b + 4 * CATT : cat_b + (l - 1) * CATT;
     const __nv_bfloat16* wla = wpa + WP_ATT + (size_t)l * WP_ATT_STRIDE;
     const __nv_bfloat16* wlb = wpb + WP_ATT + (size_t)l * WP_ATT_STRIDE;

@@ -155,6 +155,23 @@ int launch_tc_rowgemm(const TcGemm& g, cudaStream_t st);   // gemm_tc_rows.cu: s
 // attention_tc.cu: per cloud  r = x - softmax(q k^T / sqrt(64)) v   on tcgen05 (L == 256, d_k == 64, C == 256)
 int launch_attention_tc(const __nv_bfloat16* qk, const __nv_bfloat16* vT, const __nv_bfloat16* x, int ldx, int clouds,
                         __nv_bfloat16* r, float* attn, int attn_mode, cudaStream_t st);
+// attention_layer_tc.cu: one whole offset-attention layer per cloud (projections, softmax, P v, out-proj, residuals)
+struct AttnLayerTc {
+  const __nv_bfloat16* x = nullptr;       // [clouds*256, ldx] layer input
+  int ldx = 0;
+  const __nv_bfloat16* wqkv[2] = {nullptr, nullptr};   // [384, 256]: q rows 0-63, k 64-127, v 128-383
+  const __nv_bfloat16* wo[2] = {nullptr, nullptr};     // [256, 256]
+  const float* bqkv[2] = {nullptr, nullptr};           // [384]
+  const float* bo[2] = {nullptr, nullptr};             // [256]
+  int clouds_per_set = 0;
+  __nv_bfloat16* yb = nullptr;            // [clouds*256, ldyb] layer output (bf16)
+  int ldyb = 0;
+  float* yf = nullptr;                    // optional fp32 copy
+  int ldyf = 0;
+  float* attn = nullptr;                  // attention map accumulation (see attention_tc_kernel)
+  int attn_mode = 0;
+};
+int launch_attention_layer_tc(const AttnLayerTc& p, int clouds, cudaStream_t st);
 int launch_cvt_bf16(const float* in, int ldi, int rows, int cols, __nv_bfloat16* out, int ldo, cudaStream_t st);
 
 }  // namespace pz
