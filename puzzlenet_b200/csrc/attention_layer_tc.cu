@@ -194,54 +194,58 @@ __global__ void __launch_bounds__(FT, 1) attention_layer_tc_kernel(const AttnLay
     const uint32_t t_row = tmem + lane_base + qb * 256;
     const int lrow = quarter * 32 + lane;                   // row inside the query block
     const size_t grow = row0 + qb * 128 + lrow;
-    // ---- softmax rows (warps 0-3) -> un-normalised P (bf16, K-major) in R_B, 1/sum in smem
-    if (half == 0) {
-      float m = -INFINITY;
+    // ---- softmax rows -> un-normalised P (bf16, K-major) in R_B.  All 8 warps: the two warps of a lane quarter
+    // split the 256 key columns (4 chunks each) and exchange row max / row sum through the idle weight ring.
+    float* xch = reinterpret_cast<float*>(gen + (rw - base));   // [2 halves][128 rows] max, then [2][128] sums
+    float mloc = -INFINITY;
 #pragma unroll 1
-      for (int c32 = 0; c32 < 8; ++c32) {
+    for (int c32 = half * 4; c32 < half * 4 + 4; ++c32) {
+      float v[32];
+      tmem_ld32(t_row + c32 * 32, v);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) mloc = fmaxf(mloc, v[i]);
+    }
+    xch[half * 128 + lrow] = mloc;
+    __syncthreads();
+    const float mc = fmaxf(xch[lrow], xch[128 + lrow]) * cexp;
+    float sum = 0.f;
+#pragma unroll 1
+    for (int c32 = half * 4; c32 < half * 4 + 4; ++c32) {
+      float v[32];
+      tmem_ld32(t_row + c32 * 32, v);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        v[i] = exp2f(fmaf(v[i], cexp, -mc));
+        sum += v[i];
+      }
+      uint8_t* pk = gen + (rb - base) + (c32 >> 1) * (128 * 128);
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) *reinterpret_cast<uint4*>(pk + sw128(lrow, (c32 & 1) * 4 + q4)) = pack8(v + q4 * 8);
+    }
+    xch[256 + half * 128 + lrow] = sum;
+    __syncthreads();
+    const float inv_row = 1.0f / (xch[256 + lrow] + xch[384 + lrow]);
+    if (half == 0) invs[lrow] = inv_row;
+    if (p.attn_mode != 0) {  // attention map (need=True): mean of the four layers' maps, model5_b.py:468-469
+      float* ag = p.attn + grow * FL;
+#pragma unroll 1
+      for (int c32 = half * 4; c32 < half * 4 + 4; ++c32) {
         float v[32];
         tmem_ld32(t_row + c32 * 32, v);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) m = fmaxf(m, v[i]);
-      }
-      const float mc = m * cexp;
-      float sum = 0.f;
-#pragma unroll 1
-      for (int c32 = 0; c32 < 8; ++c32) {
-        float v[32];
-        tmem_ld32(t_row + c32 * 32, v);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          v[i] = exp2f(fmaf(v[i], cexp, -mc));
-          sum += v[i];
-        }
-        uint8_t* pk = gen + (rb - base) + (c32 >> 1) * (128 * 128);
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) *reinterpret_cast<uint4*>(pk + sw128(lrow, (c32 & 1) * 4 + q4)) = pack8(v + q4 * 8);
-      }
-      const float inv = 1.0f / sum;
-      invs[lrow] = inv;
-      if (p.attn_mode != 0) {  // attention map (need=True): mean of the four layers' maps, model5_b.py:468-469
-        float* ag = p.attn + grow * FL;
-#pragma unroll 1
-        for (int c32 = 0; c32 < 8; ++c32) {
-          float v[32];
-          tmem_ld32(t_row + c32 * 32, v);
-#pragma unroll
-          for (int q4 = 0; q4 < 8; ++q4) {
-            float4 a;
-            a.x = exp2f(fmaf(v[q4 * 4 + 0], cexp, -mc)) * inv;
-            a.y = exp2f(fmaf(v[q4 * 4 + 1], cexp, -mc)) * inv;
-            a.z = exp2f(fmaf(v[q4 * 4 + 2], cexp, -mc)) * inv;
-            a.w = exp2f(fmaf(v[q4 * 4 + 3], cexp, -mc)) * inv;
-            float4* dst = reinterpret_cast<float4*>(ag + c32 * 32 + q4 * 4);
-            if (p.attn_mode != 1) {
-              const float4 o = *dst;
-              a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w;
-              if (p.attn_mode == 3) { a.x *= 0.25f; a.y *= 0.25f; a.z *= 0.25f; a.w *= 0.25f; }
-            }
-            *dst = a;
+        for (int q4 = 0; q4 < 8; ++q4) {
+          float4 a;
+          a.x = exp2f(fmaf(v[q4 * 4 + 0], cexp, -mc)) * inv_row;
+          a.y = exp2f(fmaf(v[q4 * 4 + 1], cexp, -mc)) * inv_row;
+          a.z = exp2f(fmaf(v[q4 * 4 + 2], cexp, -mc)) * inv_row;
+          a.w = exp2f(fmaf(v[q4 * 4 + 3], cexp, -mc)) * inv_row;
+          float4* dst = reinterpret_cast<float4*>(ag + c32 * 32 + q4 * 4);
+          if (p.attn_mode != 1) {
+            const float4 o = *dst;
+            a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w;
+            if (p.attn_mode == 3) { a.x *= 0.25f; a.y *= 0.25f; a.z *= 0.25f; a.w *= 0.25f; }
           }
+          *dst = a;
         }
       }
     }
