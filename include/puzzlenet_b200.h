@@ -40,7 +40,7 @@ typedef void* pz_stream_t; /* cudaStream_t */
 #define PZ_PREC_FP32 0 /* fp32 CUDA-core math, matches the reference to ~1e-6 rel */
 #define PZ_PREC_BF16 1 /* bf16 operands, fp32 accumulate on tcgen05 tensor cores */
 
-#define PZ_ABI_VERSION 2
+#define PZ_ABI_VERSION 3
 
 /* pz_predict5 flags */
 #define PZ_FLAG_NEED 1          /* also return x2 / attention of both clouds (predict5 need=True) */
@@ -218,6 +218,55 @@ int pz_predict5(const PzEncoderWeights* enc_host /*[2]*/, const PzHeadWeights* h
 
 /* se3.exp(x) -- se_math/se3.py:57-80.  twist [B,6] (omega, v) -> g [B,4,4]. */
 int pz_se3_exp(const float* twist, int B, float* g, pz_stream_t stream);
+
+/* ------------------------------------------------- losses / post-forward epilogue */
+
+/* TouchedRegraster.chamfer_loss(a, b) -- model5_b.py:1495-1505 (dataset.py:1135-1145 is the same code):
+ * P[b,i,j] = (|x_i|^2 + |y_j|^2) - 2 x_i.y_j in fp32 (the expanded form the reference gets from three bmm's; it
+ * can go slightly negative).  x [B,n,3], y [B,m,3] -> min_over_x [B,m] = torch.min(P,1)[0],
+ * min_over_y [B,n] = torch.min(P,2)[0]; arg_* (int32, optional) are the minimising indices (first on ties). */
+int pz_chamfer(const float* x, const float* y, int B, int n, int m, float* min_over_x, float* min_over_y,
+               int32_t* arg_x_or_null, int32_t* arg_y_or_null, pz_stream_t stream);
+/* autograd of the above through the arg-mins: grad_x [B,n,3], grad_y [B,m,3] (overwritten). */
+int pz_chamfer_grad(const float* x, const float* y, int B, int n, int m, const int32_t* arg_x, const int32_t* arg_y,
+                    const float* grad_min_over_x, const float* grad_min_over_y, float* grad_x, float* grad_y,
+                    pz_stream_t stream);
+
+/* TouchedRegraster.comp(g, igt) -- model5_b.py:1512-1519: mse(g.igt, I)*16 -> loss [1]. */
+int pz_comp(const float* g, const float* igt, int B, float* loss, pz_stream_t stream);
+
+/* se3.transform(g, a) -- se_math/se3.py:110-120 for points stored [B,n,3]: out = R p + t. */
+int pz_se3_transform(const float* g, const float* pts, int B, int n, float* out, pz_stream_t stream);
+
+/* torch.topk(torch.softmax(logits, 1)[:, 1, :], K, 1)[1] -- model5_b.py:1323-1330 (test) / :1085-1092 (train).
+ * logits [B,2,N] -> idx [B,K] by descending class-1 probability (ties: lowest index first),
+ * prob_or_null [B,K].  Supported: N <= 1024. */
+int pz_boundary_topk(const float* logits, int B, int N, int K, int64_t* idx, float* prob_or_null,
+                     pz_stream_t stream);
+
+/* torch.topk(values, K, 1) (largest != 0) or torch.topk(-values, K, 1) (largest == 0) for rows of N <= 1024 floats:
+ * get_boundary, dataset.py:1359-1362, and the attention top-k of training_step, model5_b.py:939-942.
+ * idx [B,K] in selection order (ties: lowest index first), vals_or_null [B,K] the selected values. */
+int pz_topk(const float* values, int B, int N, int K, int largest, int64_t* idx, float* vals_or_null,
+            pz_stream_t stream);
+
+/* The whole post-forward part of test_step (model5_b.py:1314-1358 with metrics.py:7-10, :54-84) in one
+ * launch, one CTA per pair: se3.exp(out6), boundary top-128 of both clouds, gather, alignment of the second
+ * boundary by the predicted pose, the boundary chamfer distances, IoU counts and the isotropic pose errors.
+ * fpc, src [B,1024,3] (src = rpc in test_step; mrpc for assembly scoring), fpcb/rpcb [B,128,3],
+ * fpc_idx/rpc_idx [B,1024] (0/1 floats), igt [B,4,4]; any *_or_null input disables the columns that need it.
+ * scores [B,PZ_SCORE_COLS]:
+ *   0 isotropic rotation error (deg)   1 isotropic translation error   2 translation mse   3 translation mae
+ *   4 |pred & gt| fpc   5 |pred | gt| fpc   6 |pred & gt| mrpc   7 |pred | gt| mrpc   (IoU = sum(4)/sum(5) over the batch)
+ *   8 cd_fpc = mean+mean of chamfer_loss(fpcb, de_fpcb)    9 cd_rpc = chamfer_loss(rpcb, aligned de_rpcb)
+ *   10 chamfer_loss(de_fpcb, aligned de_mrpcb) -- the pair score used by the assembly driver   11 reserved (0)
+ * idx_f/idx_m [B,128] selected indices, bnd_f/bnd_m [B,128,3] the gathered (bnd_m: aligned) boundary points. */
+#define PZ_SCORE_COLS 12
+int pz_pair_score(const float* out6, const float* de_fpcb, const float* de_mrpcb, const float* fpc,
+                  const float* src, const float* fpcb_or_null, const float* rpcb_or_null,
+                  const float* fpc_idx_or_null, const float* rpc_idx_or_null, const float* igt_or_null, int B,
+                  float* scores, int64_t* idx_f_or_null, int64_t* idx_m_or_null, float* bnd_f_or_null,
+                  float* bnd_m_or_null, pz_stream_t stream);
 
 /* --------------------------------------------------------------------- EMD */
 

@@ -272,3 +272,145 @@ def rotation_error_deg(r1: Tensor, r2: Tensor) -> Tensor:
 def translation_error(t1: Tensor, t2: Tensor) -> Tensor:
     """|t1 - t2| -- the quantity north_star bounds by 1e-4."""
     return (t1 - t2).norm(dim=-1)
+
+
+# --------------------------------------------------------------------------
+# loss-side operators and the test_step epilogue (model5_b.py:1292-1358, :1495-1519)
+# --------------------------------------------------------------------------
+
+
+def chamfer_loss(a: Tensor, b: Tensor):
+    """model5_b.py:1495-1505 (dataset.py:1135-1145 is identical): the EXPANDED form through three bmm's,
+    P = rx^T + ry - 2 zz; returns (min over dim 1 [B,m], min over dim 2 [B,n]).  n must equal m (expand_as)."""
+    xx = torch.bmm(a, a.transpose(2, 1))
+    yy = torch.bmm(b, b.transpose(2, 1))
+    zz = torch.bmm(a, b.transpose(2, 1))
+    d = torch.arange(0, a.shape[1])
+    rx = xx[:, d, d].unsqueeze(1).expand_as(xx)
+    ry = yy[:, d, d].unsqueeze(1).expand_as(yy)
+    P = rx.transpose(2, 1) + ry - 2 * zz
+    return torch.min(P, 1)[0], torch.min(P, 2)[0]
+
+
+def comp(g: Tensor, igt: Tensor) -> Tensor:
+    """model5_b.py:1512-1519."""
+    A = g.matmul(igt)
+    eye = torch.eye(4).to(A).view(1, 4, 4).repeat(A.size(0), 1, 1)
+    return torch.nn.functional.mse_loss(A, eye, reduction="mean") * 16
+
+
+def boundary_prob(logits: Tensor) -> Tensor:
+    """model5_b.py:1323-1328: class-1 softmax probability, logits [B,2,N] -> [B,N]."""
+    return torch.softmax(logits, dim=1)[:, 1, :]
+
+
+def boundary_topk(logits: Tensor, k: int = 128) -> Tensor:
+    """model5_b.py:1327/:1329 -- torch.topk(prob, k, 1)[1]; ties are resolved to the LOWEST index here
+    (torch.topk leaves them unspecified), which is the order the CUDA kernel documents."""
+    p = boundary_prob(logits)
+    order = torch.sort(-p, dim=1, stable=True).indices
+    return order[:, :k]
+
+
+def inv_R_t(R: Tensor, t: Tensor):
+    """metrics.py:7-10."""
+    inv_R = R.permute(0, 2, 1).contiguous()
+    return inv_R, torch.squeeze(-inv_R @ t[..., None], -1)
+
+
+def test_step_scores(out6: Tensor, de_fpcb: Tensor, de_mrpcb: Tensor, fpc: Tensor, src: Tensor,
+                     fpcb: Tensor, rpcb: Tensor, fpc_idx: Tensor, rpc_idx: Tensor, igt: Tensor) -> Dict[str, Tensor]:
+    """Everything test_step does after predict5 (model5_b.py:1314-1358 with metrics.py:54-84), per pair.
+    ``src`` is the cloud the second boundary is gathered from (``rpc`` in test_step)."""
+    mat = se3_exp(out6)
+    R, t = mat[:, :3, :3], mat[:, :3, 3]
+    inv_R, inv_t = inv_R_t(igt[:, :3, :3], igt[:, :3, 3])
+    rr = torch.matmul(inv_R.permute(0, 2, 1).contiguous(), R)
+    tr = rr[:, 0, 0] + rr[:, 1, 1] + rr[:, 2, 2]
+    r_iso = torch.acos(torch.clamp((tr - 1) / 2, -1, 1)) / math.pi * 180
+    R2, t2 = inv_R_t(inv_R, inv_t)
+    t_iso = torch.norm(torch.squeeze(R2 @ t[..., None], -1) + t2, dim=-1)
+    t_mse = ((t - inv_t) ** 2).mean(1)
+    t_mae = (t - inv_t).abs().mean(1)
+    idx_f, idx_m = boundary_topk(de_fpcb), boundary_topk(de_mrpcb)
+    B = fpc.shape[0]
+    pred_f = torch.zeros(B, 1024).scatter(1, idx_f, 1)
+    pred_m = torch.zeros(B, 1024).scatter(1, idx_m, 1)
+    gf, gm = fpc_idx.reshape(B, 1024), rpc_idx.reshape(B, 1024)
+    inter_f = torch.logical_and(pred_f, gf).sum(1).float()
+    union_f = torch.logical_or(pred_f, gf).sum(1).float()
+    inter_m = torch.logical_and(pred_m, gm).sum(1).float()
+    union_m = torch.logical_or(pred_m, gm).sum(1).float()
+    bnd_f = torch.gather(fpc, 1, idx_f.unsqueeze(-1).repeat(1, 1, 3))
+    bnd_m = torch.gather(src, 1, idx_m.unsqueeze(-1).repeat(1, 1, 3))
+    bnd_m = se3_transform(mat, bnd_m.permute(0, 2, 1)).permute(0, 2, 1)
+    c1, c2 = chamfer_loss(fpcb, bnd_f)
+    cd_fpc = c1.mean(1) + c2.mean(1)
+    c1, c2 = chamfer_loss(rpcb, bnd_m)
+    cd_rpc = c1.mean(1) + c2.mean(1)
+    c1, c2 = chamfer_loss(bnd_f, bnd_m)
+    cd_pair = c1.mean(1) + c2.mean(1)
+    return dict(r_iso=r_iso, t_iso=t_iso, t_mse=t_mse, t_mae=t_mae, inter_f=inter_f, union_f=union_f,
+                inter_m=inter_m, union_m=union_m, cd_fpc=cd_fpc, cd_rpc=cd_rpc, cd_pair=cd_pair,
+                idx_f=idx_f, idx_m=idx_m, bnd_f=bnd_f, bnd_m=bnd_m, mat=mat)
+
+
+# --------------------------------------------------------------------------
+# dataset-side preprocessing (dataset.py) -- numpy, as in the reference
+# --------------------------------------------------------------------------
+
+
+def dataset_fps(points, npoints: int, start: Optional[int] = None):
+    """CADDataset.fps, dataset.py:1147-1163 (same code at :286, :437, :510, :582, :835, :1042): numpy FPS on ONE
+    cloud, float64 running distance, fp32 candidate distance, strict '<' update, first arg-max; returns the
+    selected POINTS (not indices).  ``start`` None draws np.random.randint(0, N) like the reference."""
+    import numpy as np
+    if points.shape[0] < npoints:
+        return None
+    N = points.shape[0]
+    xyz = points[:, :3]
+    centroids = np.zeros((npoints,))
+    distance = np.ones((N,)) * 1e10
+    farthest = np.random.randint(0, N) if start is None else int(start)
+    for i in range(npoints):
+        centroids[i] = farthest
+        centroid = xyz[farthest, :]
+        dist = np.sum((xyz - centroid) ** 2, -1)
+        mask = dist < distance
+        distance[mask] = dist[mask]
+        farthest = np.argmax(distance, -1)
+    return points[centroids.astype(np.int32)]
+
+
+def plane_split(points, z=None):
+    """dataset.py:761-775 -- random-plane cut (normal ~ U[0,1)^3, offset ~ U[0,1/3)) -> (up, down)."""
+    import numpy as np
+    normal = np.random.rand(3, 1)
+    if z is None:
+        z = np.random.rand(1) / 3
+    dis = np.dot(points, normal) + z
+    return points[(dis >= 0)[:, 0]], points[(dis < 0)[:, 0]]
+
+
+def get_boundary(fpc: Tensor, de_mrpc: Tensor):
+    """CADDataset.get_boundary, dataset.py:1357-1367: the 128 points of each half closest to the other half.
+    -> (fpc boundary [128,3], mrpc boundary [128,3], fpc_idx [1024] 0/1, rpc_idx [1024] 0/1)."""
+    cd1, cd2 = chamfer_loss(fpc.unsqueeze(0), de_mrpc.unsqueeze(0))
+    top1 = torch.topk(-cd1, 128)
+    cdxyz1 = de_mrpc[top1[1][0]]
+    top2 = torch.topk(-cd2, 128)
+    cdxyz2 = fpc[top2[1][0]]
+    fpc_idx = torch.zeros(1024)
+    fpc_idx[top2[1][0]] = 1
+    rpc_idx = torch.zeros(1024)
+    rpc_idx[top1[1][0]] = 1
+    return cdxyz2, cdxyz1, fpc_idx, rpc_idx
+
+
+def predict6(sd: Mapping[str, Tensor], fpc: Tensor, mrpc: Tensor, starts: Optional[tuple] = None) -> Dict[str, Tensor]:
+    """TouchedRegraster.predict6(pretrain=True), model5_b.py:612-658: both clouds through ``Encoder``, pose only."""
+    st1, st2 = (None, None) if starts is None else starts
+    e1 = encoder_forward(sd, "Encoder", fpc, st1)
+    e2 = encoder_forward(sd, "Encoder", mrpc, st2)
+    out6 = _seq(sd, "tfMLP", torch.cat([e1["f_global"], e2["f_global"]], dim=-1), (0, 2, 4, 6, 8))
+    return dict(out=out6, enc_fpc=e1, enc_mrpc=e2)

@@ -15,7 +15,8 @@ LIB_PATH = os.path.join(_HERE, "lib", "libpuzzlenet_sm100.so")
 
 PZ_PREC_FP32 = 0
 PZ_PREC_BF16 = 1
-ABI_VERSION = 2
+ABI_VERSION = 3
+PZ_SCORE_COLS = 12
 PZ_FLAG_NEED = 1
 PZ_FLAG_REUSE_PACKS = 2
 
@@ -75,6 +76,14 @@ SIGNATURES = {
                               C.c_int, C.c_int, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p,
                               C.c_size_t, c_stream]),
     "pz_se3_exp": (C.c_int, [c_f32p, C.c_int, c_f32p, c_stream]),
+    "pz_chamfer": (C.c_int, [c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, c_f32p, c_f32p, C.c_void_p, C.c_void_p, c_stream]),
+    "pz_chamfer_grad": (C.c_int, [c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, c_f32p, c_f32p,
+                                  c_f32p, c_f32p, c_stream]),
+    "pz_comp": (C.c_int, [c_f32p, c_f32p, C.c_int, c_f32p, c_stream]),
+    "pz_se3_transform": (C.c_int, [c_f32p, c_f32p, C.c_int, C.c_int, c_f32p, c_stream]),
+    "pz_boundary_topk": (C.c_int, [c_f32p, C.c_int, C.c_int, C.c_int, c_i64p, c_f32p, c_stream]),
+    "pz_topk": (C.c_int, [c_f32p, C.c_int, C.c_int, C.c_int, C.c_int, c_i64p, c_f32p, c_stream]),
+    "pz_pair_score": (C.c_int, [c_f32p] * 10 + [C.c_int, c_f32p, c_i64p, c_i64p, c_f32p, c_f32p, c_stream]),
     "pz_emd_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "pz_emd_approxmatch": (C.c_int, [c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, c_f32p, C.c_void_p, C.c_size_t,
                                      c_stream]),

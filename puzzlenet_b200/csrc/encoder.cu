@@ -10,6 +10,7 @@
 #include <functional>
 
 #include "pz_common.cuh"
+#include "se3_math.cuh"
 
 namespace pz {
 
@@ -571,38 +572,11 @@ __global__ void __launch_bounds__(128) head_seg_tail_kernel(const __nv_bfloat16*
 __global__ void se3_exp_kernel(const float* __restrict__ x, int B, float* __restrict__ g) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
-  const float w0 = x[b * 6], w1 = x[b * 6 + 1], w2 = x[b * 6 + 2];
-  const float v0 = x[b * 6 + 3], v1 = x[b * 6 + 4], v2 = x[b * 6 + 5];
-  const float t = sqrtf(w0 * w0 + w1 * w1 + w2 * w2);
-  const float t2 = t * t;
-  float s1, s2, s3;
-  if (fabsf(t) < 0.01f) {  // sinc.py:6-18, :96-108, :126-138 Taylor branches
-    s1 = 1.f - t2 / 6.f * (1.f - t2 / 20.f * (1.f - t2 / 42.f));
-    s2 = 0.5f * (1.f - t2 / 12.f * (1.f - t2 / 30.f * (1.f - t2 / 56.f)));
-    s3 = (1.f / 6.f) * (1.f - t2 / 20.f * (1.f - t2 / 42.f * (1.f - t2 / 72.f)));
-  } else {
-    const float sn = sinf(t), cs = cosf(t);
-    s1 = sn / t;
-    s2 = (1.f - cs) / t2;
-    s3 = (t - sn) / (t2 * t);
-  }
-  // W = hat(w), S = W*W
-  const float W[9] = {0.f, -w2, w1, w2, 0.f, -w0, -w1, w0, 0.f};
-  float S[9];
-  for (int i = 0; i < 3; ++i)
-    for (int j = 0; j < 3; ++j) S[i * 3 + j] = W[i * 3] * W[j] + W[i * 3 + 1] * W[3 + j] + W[i * 3 + 2] * W[6 + j];
-  const float v[3] = {v0, v1, v2};
+  float tw[6], m[16];
+  for (int i = 0; i < 6; ++i) tw[i] = x[b * 6 + i];
+  se3_exp_dev(tw, m);
   float* o = g + (size_t)b * 16;
-  for (int i = 0; i < 3; ++i) {
-    float p = 0.f;
-    for (int j = 0; j < 3; ++j) {
-      const float id = i == j ? 1.f : 0.f;
-      o[i * 4 + j] = id + s1 * W[i * 3 + j] + s2 * S[i * 3 + j];
-      p += (id + s2 * W[i * 3 + j] + s3 * S[i * 3 + j]) * v[j];
-    }
-    o[i * 4 + 3] = p;
-  }
-  o[12] = 0.f; o[13] = 0.f; o[14] = 0.f; o[15] = 1.f;
+  for (int i = 0; i < 16; ++i) o[i] = m[i];
 }
 
 // ------------------------------------------------ bf16 path helpers (PZ_PREC_BF16)

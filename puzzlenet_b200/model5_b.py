@@ -7,7 +7,8 @@ conventions:
 * ``layerAttention(config, embed_dim)``                    model5_b.py:83-101
 * ``PCTransformer_nonsort(config, num_points=1024)``       model5_b.py:411-478
 * ``BiDecoderNoneCross(config)`` (parameters only)         model5_b.py:325-352
-* ``TouchedRegraster(config)`` with ``predict5`` / ``forward``   model5_b.py:519-759
+* ``TouchedRegraster(config)`` with ``predict5`` / ``predict6`` / ``forward`` / ``test_step`` /
+  ``chamfer_loss`` / ``comp`` / ``compute_metrics``        model5_b.py:519-759, :612-668, :1292-1358, :1426-1519
 
 Parameters live in ordinary ``nn.Linear`` / ``nn.BatchNorm1d`` modules so that a reference
 checkpoint's ``state_dict`` loads unchanged, but ``forward`` never calls them: compute goes
@@ -30,6 +31,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
+from . import losses, metrics
 from . import se3 as se3  # noqa: F401  (model5_b.py:13 exposes se3 the same way)
 from . import pointnet_util as pu
 
@@ -270,8 +272,9 @@ class TouchedRegraster(_Base):
     def _param_key(self):
         return tuple((p.data_ptr(), p._version) for p in self.parameters())
 
-    def _launch(self, fpc, mrpc, starts, need, ws, outs, reuse_packs=None):
-        """Allocate (unless given) the outputs and the workspace and enqueue pz_predict5 on the current stream."""
+    def _launch(self, fpc, mrpc, starts, need, ws, outs, reuse_packs=None, shared=False):
+        """Allocate (unless given) the outputs and the workspace and enqueue pz_predict5 on the current stream.
+        ``shared``: both clouds go through ``self.Encoder`` (predict6, model5_b.py:647-653)."""
         B, dev = fpc.shape[0], fpc.device
         f32 = dict(device=dev, dtype=torch.float32)
         if outs is None:
@@ -282,7 +285,8 @@ class TouchedRegraster(_Base):
                 af, am = torch.empty(B, 256, 256, **f32), torch.empty(B, 256, 256, **f32)
             outs = (out6, de_fpcb, de_mrpcb, x2f, af, x2m, am)
         out6, de_fpcb, de_mrpcb, x2f, af, x2m, am = outs
-        enc = (_lib.PzEncoderWeights * 2)(_encoder_struct(self.Encoder), _encoder_struct(self.Encoder2))
+        enc = (_lib.PzEncoderWeights * 2)(_encoder_struct(self.Encoder),
+                                          _encoder_struct(self.Encoder if shared else self.Encoder2))
         heads = self._head_struct()
         if ws is None:
             ws = self._workspace(B, dev)
@@ -290,7 +294,7 @@ class TouchedRegraster(_Base):
         if reuse_packs is None and self.precision == "bf16":
             # the bf16 weight packs live in the workspace: reusable while no parameter was touched (in-place writes
             # bump _version, reallocation changes data_ptr) and the workspace / precision are the same
-            key = self._param_key()
+            key = (self._param_key(), shared)
             reuse_packs = self._pack_keys.get(ws.data_ptr()) == key
             if len(self._pack_keys) >= 8:
                 self._pack_keys.clear()
@@ -306,14 +310,14 @@ class TouchedRegraster(_Base):
                       _lib.stream_ptr())
         return outs
 
-    def _graph_replay(self, fpc, mrpc, starts, need):
+    def _graph_replay(self, fpc, mrpc, starts, need, shared=False):
         """CUDA-graph mode (``model.cuda_graphs = True``): the ~75 launches of one forward (both streams of the
         internal fork/join included) are captured once per (batch size, need, precision, stream) and replayed.
         Inputs are copied into static buffers; the returned tensors are static too -- they are overwritten by
         the next call on the same stream.  A change of any parameter re-captures."""
         B, dev = fpc.shape[0], fpc.device
         stream = torch.cuda.current_stream(dev)
-        key = (B, bool(need), self.precision, str(dev), stream.cuda_stream)
+        key = (B, bool(need), self.precision, str(dev), stream.cuda_stream, shared)
         g = self._graphs.get(key)
         pkey = self._param_key()
         if g is None or g["pkey"] != pkey:
@@ -322,7 +326,8 @@ class TouchedRegraster(_Base):
                       starts=torch.empty(4, B, device=dev, dtype=torch.int64),
                       ws=torch.empty(_lib.load().pz_predict5_workspace_bytes(B), device=dev, dtype=torch.uint8))
             st["fpc"].copy_(fpc); st["mrpc"].copy_(mrpc); st["starts"].copy_(starts)
-            outs = self._launch(st["fpc"], st["mrpc"], st["starts"], need, st["ws"], None, reuse_packs=False)  # builds the packs
+            outs = self._launch(st["fpc"], st["mrpc"], st["starts"], need, st["ws"], None, reuse_packs=False,
+                                shared=shared)                                           # builds the packs
             stream.synchronize()
             graph = torch.cuda.CUDAGraph()
             cap = stream
@@ -332,7 +337,7 @@ class TouchedRegraster(_Base):
                 cap = self._capture_stream
             with torch.cuda.graph(graph, stream=cap):
                 self._launch(st["fpc"], st["mrpc"], st["starts"], need, st["ws"], outs,
-                             reuse_packs=self.precision == "bf16")
+                             reuse_packs=self.precision == "bf16", shared=shared)
             g = dict(pkey=pkey, st=st, outs=outs, graph=graph)
             if len(self._graphs) >= 8:
                 self._graphs.clear()
@@ -356,6 +361,23 @@ class TouchedRegraster(_Base):
         if training:
             raise NotImplementedError("puzzlenet_b200.predict5 is inference-only (training=True needs batch-stat "
                                       "BatchNorm and backward kernels, which this build does not have)")
+        return self._predict(batch, need, starts, shared=False)
+
+    def predict6(self, batch, batch_indic, need=False, training=False, pretrain=False, starts=None):
+        """model5_b.py:612-668 -- the pretraining forward: BOTH clouds go through ``self.Encoder`` and only the pose
+        is predicted.  ``pretrain=False`` reaches ``self.Decoder`` / ``self.mrpcbDecoder`` in the reference, which
+        its constructor does not create (AttributeError there); it raises here as well."""
+        if training:
+            raise NotImplementedError("puzzlenet_b200.predict6 is inference-only, like predict5")
+        if not pretrain:
+            raise AttributeError("'TouchedRegraster' object has no attribute 'Decoder' (model5_b.py:661: predict6 "
+                                 "only works with pretrain=True)")
+        r = self._predict(batch, need, starts, shared=True)
+        if not need:
+            return r[0]
+        return r[0], [0], r[2], r[3], r[4], r[5]
+
+    def _predict(self, batch, need, starts, shared):
         for m in (self.Encoder, self.Encoder2, self.tfMLP, self.fpc_decoder, self.rpc_decoder):
             m.eval()                                              # model5_b.py:677-683
         fpc, mrpc = batch[0], batch[1]
@@ -374,9 +396,41 @@ class TouchedRegraster(_Base):
                                   torch.randint(0, 512, (B,), dtype=torch.long)])
         starts = starts.to(device=dev, dtype=torch.int64, non_blocking=True).contiguous()
         if self.cuda_graphs:
-            out6, de_fpcb, de_mrpcb, x2f, af, x2m, am = self._graph_replay(fpc, mrpc, starts, need)
+            out6, de_fpcb, de_mrpcb, x2f, af, x2m, am = self._graph_replay(fpc, mrpc, starts, need, shared)
         else:
-            out6, de_fpcb, de_mrpcb, x2f, af, x2m, am = self._launch(fpc, mrpc, starts, need, None, None)
+            out6, de_fpcb, de_mrpcb, x2f, af, x2m, am = self._launch(fpc, mrpc, starts, need, None, None,
+                                                                     shared=shared)
         if not need:
             return out6, out6, de_fpcb, de_mrpcb
         return out6, [0], x2f, af, x2m, am, de_fpcb, de_mrpcb
+
+    # ---- loss-side helpers and the evaluation step (same names as the reference methods)
+    def chamfer_loss(self, a, b):
+        """model5_b.py:1495-1505."""
+        return losses.chamfer_loss(a, b)
+
+    def comp(self, g, igt):
+        """model5_b.py:1512-1519."""
+        return losses.comp(g, igt)
+
+    def compute_metrics(self, R, t, igt):
+        """model5_b.py:1426-1440 (host-side numpy/scipy, as in the reference's metrics.py)."""
+        return metrics.compute_metrics(R, t, igt)
+
+    def test_step(self, batch, batch_idx):
+        """model5_b.py:1292-1358 -> ``[1,10]``: mean r_mse, r_mae, t_mse, t_mae, r_isotropic, t_isotropic, then the
+        batch IoU of both boundary predictions and the two boundary chamfer distances.  The forward is one
+        ``pz_predict5``; everything after it is ONE ``pz_pair_score`` launch plus the host-side Euler-angle
+        errors (scipy, exactly as the reference computes them)."""
+        batch = ([b.unsqueeze(0) if b.dim() == 2 else b for b in batch[:-2]]             # model5_b.py:1281-1292
+                 + [b.unsqueeze(0) if b.dim() == 1 else b for b in batch[-2:]])
+        fpc, mrpc, igt, rpc, fpcb, rpcb, fpc_idx, rpc_idx = batch[:8]
+        out, _, de_fpcb, de_mrpcb = self.predict5(batch, fpc.shape[0], training=False, need=False)
+        s = losses.pair_score(out, de_fpcb, de_mrpcb, fpc, rpc, fpcb, rpcb, fpc_idx, rpc_idx, igt).double()
+        mat = se3.exp(out)
+        r_mse, r_mae = metrics.anisotropic_R_error(mat[:, :3, :3], igt[:, :3, :3].permute(0, 2, 1))
+        m = s.mean(0)
+        tot = s.sum(0)
+        scores = [float(r_mse.mean()), float(r_mae.mean()), m[2], m[3], m[0], m[1], tot[4] / tot[5], tot[6] / tot[7],
+                  m[8], m[9]]
+        return torch.stack([torch.as_tensor(v, dtype=torch.float64, device=out.device) for v in scores]).unsqueeze(0)

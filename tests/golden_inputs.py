@@ -14,3 +14,24 @@ def golden_inputs():
     twist[0, :3] *= 1e-3
     twist[1, :3] = 0
     return xyz, feat, big, twist
+
+
+def epilogue_inputs(batch, se3_exp):
+    """Ground-truth side of a test batch (rpc, boundaries, boundary masks, igt) for the test_step goldens;
+    ``se3_exp`` is whichever exp map the caller pins (reference / oracle / CUDA -- igt is an input)."""
+    g = torch.Generator().manual_seed(5)
+    rpc = torch.rand(batch, 1024, 3, generator=g) - 0.5
+    fpcb = torch.rand(batch, 128, 3, generator=g) - 0.5
+    rpcb = torch.rand(batch, 128, 3, generator=g) - 0.5
+    fpc_idx = (torch.rand(batch, 1024, generator=g) < 0.125).float()
+    rpc_idx = (torch.rand(batch, 1024, generator=g) < 0.125).float()
+    twist = torch.randn(batch, 6, generator=g) * 0.3
+    twist2 = torch.randn(batch, 6, generator=g) * 0.3
+    return dict(rpc=rpc, fpcb=fpcb, rpcb=rpcb, fpc_idx=fpc_idx, rpc_idx=rpc_idx, twist=twist, twist2=twist2,
+                igt=se3_exp(twist))
+
+
+def dataset_inputs():
+    """One 'raw' piece for the dataset-side goldens: 6000 points of a unit-ish blob (numpy fp32)."""
+    g = torch.Generator().manual_seed(9)
+    return (torch.randn(6000, 3, generator=g) * 0.3).numpy()
