@@ -135,12 +135,22 @@ def _lin(sd: Mapping[str, Tensor], name: str, x: Tensor) -> Tensor:
     return torch.nn.functional.linear(x, sd[name + ".weight"], sd[name + ".bias"])
 
 
-def _bn_point_index_eval(sd: Mapping[str, Tensor], name: str, x: Tensor, eps: float = 1e-5) -> Tensor:
+def _bn_point_index_eval(sd: Mapping[str, Tensor], name: str, x: Tensor, eps: float = 1e-5,
+                         train: bool = False, bn_state: Optional[dict] = None) -> Tensor:
     """nn.BatchNorm1d(1024) on [B, 1024, 64]: dim 1 (the point index) is the channel
-    (model5_b.py:424-425, :447-448).  Eval mode -> running statistics."""
-    return torch.nn.functional.batch_norm(
-        x, sd[name + ".running_mean"], sd[name + ".running_var"],
-        sd[name + ".weight"], sd[name + ".bias"], training=False, momentum=0.1, eps=eps)
+    (model5_b.py:424-425, :447-448).  Eval mode -> running statistics; ``train`` -> batch statistics
+    over (B, 64) per point, with the momentum-0.1 running-stat update written into ``bn_state`` when given."""
+    if not train:
+        return torch.nn.functional.batch_norm(
+            x, sd[name + ".running_mean"], sd[name + ".running_var"],
+            sd[name + ".weight"], sd[name + ".bias"], training=False, momentum=0.1, eps=eps)
+    rm = sd[name + ".running_mean"].detach().clone()
+    rv = sd[name + ".running_var"].detach().clone()
+    y = torch.nn.functional.batch_norm(x, rm, rv, sd[name + ".weight"], sd[name + ".bias"], training=True,
+                                       momentum=0.1, eps=eps)
+    if bn_state is not None:
+        bn_state[name + ".running_mean"], bn_state[name + ".running_var"] = rm, rv
+    return y
 
 
 def scaled_dot_production(q: Tensor, k: Tensor, v: Tensor):
@@ -158,7 +168,8 @@ def layer_attention(sd: Mapping[str, Tensor], prefix: str, x: Tensor):
 
 
 def encoder_forward(sd: Mapping[str, Tensor], prefix: str, xyz: Tensor,
-                    starts: Optional[tuple] = None) -> Dict[str, Tensor]:
+                    starts: Optional[tuple] = None, train_bn: bool = False,
+                    bn_state: Optional[dict] = None) -> Dict[str, Tensor]:
     """PCTransformer_nonsort.forward, model5_b.py:443-478, eval mode.
 
     ``starts`` = (start1 [B], start2 [B]) FPS start indices; None -> drawn from the
@@ -167,8 +178,10 @@ def encoder_forward(sd: Mapping[str, Tensor], prefix: str, xyz: Tensor,
     """
     p = prefix
     s1, s2 = (None, None) if starts is None else starts
-    x_feature = torch.relu(_bn_point_index_eval(sd, p + ".bn1", _lin(sd, p + ".mlp1", xyz)))
-    x_feature = torch.relu(_bn_point_index_eval(sd, p + ".bn2", _lin(sd, p + ".mlp2", x_feature)))
+    x_feature = torch.relu(_bn_point_index_eval(sd, p + ".bn1", _lin(sd, p + ".mlp1", xyz), train=train_bn,
+                                                bn_state=bn_state))
+    x_feature = torch.relu(_bn_point_index_eval(sd, p + ".bn2", _lin(sd, p + ".mlp2", x_feature), train=train_bn,
+                                                bn_state=bn_state))
     x1, f1, _, fps1, knn1 = sample_and_group(512, 0, 32, xyz, x_feature, knn=True, start=s1, return_idx=True)
     f1f = torch.relu(_lin(sd, p + ".mlp4", torch.relu(_lin(sd, p + ".mlp3", f1)))).max(dim=-2).values
     x2, f2, _, fps2, knn2 = sample_and_group(256, 0, 32, x1, f1f, knn=True, start=s2, return_idx=True)
@@ -195,7 +208,8 @@ def _seq(sd: Mapping[str, Tensor], name: str, x: Tensor, layers) -> Tensor:
 
 
 def predict5(sd: Mapping[str, Tensor], fpc: Tensor, mrpc: Tensor, need: bool = False,
-             starts: Optional[tuple] = None) -> Dict[str, Tensor]:
+             starts: Optional[tuple] = None, train_bn: bool = False,
+             bn_state: Optional[dict] = None) -> Dict[str, Tensor]:
     """TouchedRegraster.predict5, model5_b.py:672-759, eval mode.
 
     ``starts`` = ((fpc stage1, fpc stage2), (mrpc stage1, mrpc stage2)); None draws the
@@ -206,8 +220,8 @@ def predict5(sd: Mapping[str, Tensor], fpc: Tensor, mrpc: Tensor, need: bool = F
     if fpc.dim() == 2:
         fpc, mrpc = fpc.unsqueeze(0), mrpc.unsqueeze(0)
     st1, st2 = (None, None) if starts is None else starts
-    e1 = encoder_forward(sd, "Encoder", fpc, st1)
-    e2 = encoder_forward(sd, "Encoder2", mrpc, st2)
+    e1 = encoder_forward(sd, "Encoder", fpc, st1, train_bn, bn_state)
+    e2 = encoder_forward(sd, "Encoder2", mrpc, st2, train_bn, bn_state)
     out6 = _seq(sd, "tfMLP", torch.cat([e1["f_global"], e2["f_global"]], dim=-1), (0, 2, 4, 6, 8))
     loc_f = _seq(sd, "MLPLocalPreFpc", e1["x_feature"], (0, 2, 4))
     loc_m = _seq(sd, "MLPLocalPreRpc", e2["x_feature"], (0, 2, 4))

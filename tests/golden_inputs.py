@@ -35,3 +35,19 @@ def dataset_inputs():
     """One 'raw' piece for the dataset-side goldens: 6000 points of a unit-ish blob (numpy fp32)."""
     g = torch.Generator().manual_seed(9)
     return (torch.randn(6000, 3, generator=g) * 0.3).numpy()
+
+
+def training_inputs(batch, se3_exp):
+    """A training batch with a consistent geometry: rpc is a cloud, mrpc = igt . rpc (so the pose losses have a
+    meaningful target), fpc an independent cloud, boundaries / masks random (they are inputs only)."""
+    g = torch.Generator().manual_seed(77)
+    fpc = torch.rand(batch, 1024, 3, generator=g) - 0.5
+    rpc = torch.rand(batch, 1024, 3, generator=g) - 0.5
+    twist = torch.randn(batch, 6, generator=g) * 0.3
+    igt = se3_exp(twist)
+    mrpc = (igt[:, :3, :3] @ rpc.permute(0, 2, 1) + igt[:, :3, 3:]).permute(0, 2, 1).contiguous()
+    fpcb = torch.rand(batch, 128, 3, generator=g) - 0.5
+    rpcb = torch.rand(batch, 128, 3, generator=g) - 0.5
+    fpc_idx = (torch.rand(batch, 1024, generator=g) < 0.125).float()
+    rpc_idx = (torch.rand(batch, 1024, generator=g) < 0.125).float()
+    return [fpc, mrpc, igt, rpc, fpcb, rpcb, fpc_idx, rpc_idx]
