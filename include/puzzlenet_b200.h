@@ -40,7 +40,7 @@ typedef void* pz_stream_t; /* cudaStream_t */
 #define PZ_PREC_FP32 0 /* fp32 CUDA-core math, matches the reference to ~1e-6 rel */
 #define PZ_PREC_BF16 1 /* bf16 operands, fp32 accumulate on tcgen05 tensor cores */
 
-#define PZ_ABI_VERSION 3
+#define PZ_ABI_VERSION 4
 
 /* pz_predict5 flags */
 #define PZ_FLAG_NEED 1          /* also return x2 / attention of both clouds (predict5 need=True) */
@@ -267,6 +267,70 @@ int pz_pair_score(const float* out6, const float* de_fpcb, const float* de_mrpcb
                   const float* fpc_idx_or_null, const float* rpc_idx_or_null, const float* igt_or_null, int B,
                   float* scores, int64_t* idx_f_or_null, int64_t* idx_m_or_null, float* bnd_f_or_null,
                   float* bnd_m_or_null, pz_stream_t stream);
+
+/* ---------------------------------------------------------------- training */
+/* Building blocks of the training step (TouchedRegraster.training_step, model5_b.py:912-1155, Adam per
+ * :1453-1457).  The reference gets its backward pass from torch autograd; here every op of the graph has an
+ * explicit kernel and puzzlenet_b200/training.py sequences them.  fp32 throughout, like the reference (no AMP). */
+
+/* C = epilogue(alpha * op(A) op(B) + beta * C), row-major.  op(A) is M x K: A[m*lda + k], or with transA the
+ * stored matrix is K x M: A[k*lda + m]; likewise op(B) is K x N.  batch > 1: independent problems at
+ * A + i*strideA, ... (mask and residual use strideC).  Epilogue order: + bias[n], + beta*C, ReLU (relu != 0),
+ * zero where mask[m*ldmask + n] <= 0 (the ReLU gate of a backward GEMM), + residual[m*ldres + n].
+ * splitk > 1 splits K over CTAs and atomically ADDS alpha*partial into C (pre-zero C; no batching / epilogue):
+ * used for weight gradients dW = dY^T X whose K is the row count (up to 2.1 M). */
+int pz_sgemm(int transA, int transB, int M, int N, int K, float alpha, const float* A, long long lda,
+             const float* B, long long ldb, float beta, float* C, long long ldc, int batch, long long strideA,
+             long long strideB, long long strideC, int splitk, const float* bias_or_null, int relu,
+             const float* mask_or_null, long long ldmask, const float* residual_or_null, long long ldres,
+             pz_stream_t stream);
+/* out[n] = beta*out[n] + sum_m x[m*ld + n]  (bias gradients). */
+int pz_colsum(const float* x, long long ld, long long M, int N, float beta, float* out, pz_stream_t stream);
+/* out[r,c] = a*x[r,c] + b*y[r,c] with row strides (y may be null). */
+int pz_axpby(long long rows, int cols, float a, const float* x, long long ldx, float b, const float* y_or_null,
+             long long ldy, float* out, long long ldo, pz_stream_t stream);
+/* out = mask > 0 ? dy : 0 (ReLU gate on an incoming gradient), strided 2-D. */
+int pz_relu_gate(long long rows, int cols, const float* dy, long long ldy, const float* mask, long long ldm,
+                 float* out, long long ldo, pz_stream_t stream);
+/* x.repeat(1, reps, 1) of per-cloud rows (model5_b.py:742, :744): dst[(g*reps + r)*ldd + c] = src[g*C + c]; and its
+ * backward y[g,c] = sum_k x[(g*K + k)*ld + c]. */
+int pz_broadcast_rows(const float* src, long long G, int reps, int C, float* dst, long long ldd, pz_stream_t stream);
+int pz_group_sum(const float* x, long long ld, long long G, int K, int C, float* y, pz_stream_t stream);
+/* nn.BatchNorm1d(P) applied to x [B,P,C] in TRAIN mode (model5_b.py:424-425, :447-448: the "channel" is the point
+ * index, statistics over the B*C values of a point; eps 1e-5, momentum 0.1, unbiased running variance), with the
+ * following ReLU fused when relu != 0.  save_mean/save_invstd [P] feed the backward. */
+int pz_bn_point_train_forward(const float* x, int B, int P, int C, const float* gamma, const float* beta,
+                              float* running_mean_or_null, float* running_var_or_null, float momentum, float eps,
+                              int relu, float* y, float* save_mean, float* save_invstd, pz_stream_t stream);
+int pz_bn_point_train_backward(const float* x, const float* y, const float* dy, int B, int P, int C,
+                               const float* gamma, const float* save_mean, const float* save_invstd, int relu,
+                               float* dx, float* dgamma, float* dbeta, pz_stream_t stream);
+/* torch.max(x, dim=-2) of x [G,K,C] with the arg-max (model5_b.py:454, :461, :474, :741) and its backward;
+ * relu_gate != 0 additionally applies the ReLU gate of the layer that produced x (dx is then the gradient of
+ * that layer's pre-activation). */
+int pz_maxpool_forward(const float* x, long long G, int K, int C, float* y, int32_t* arg, pz_stream_t stream);
+int pz_maxpool_backward(const float* dy, const float* y, const int32_t* arg, long long G, int K, int C,
+                        int relu_gate, float* dx, pz_stream_t stream);
+/* backward of index_points (pointnet_util.py:39-50): dst[(m / per_cloud)*N + idx[m], 0:C] += src[m, c0:c0+C]. */
+int pz_scatter_add_rows(const float* src, long long ld, int c0, int C, const int64_t* idx, long long M,
+                        long long per_cloud, int N, float* dst, long long ldd, pz_stream_t stream);
+/* backward of softmax(S * scale) w.r.t. S (model5_b.py:70-72): dS = scale * A * (dA - rowsum(dA*A)). */
+int pz_softmax_backward(const float* A, const float* dA, long long rows, int L, float scale, float* dS,
+                        pz_stream_t stream);
+/* F.cross_entropy(logits [B,2,N], target [B,N]) (model5_b.py:1063-1064): loss[0] += mean CE (zero it first);
+ * dlogits_or_null = grad_scale * d(mean CE)/dlogits.  point_major != 0: logits / dlogits are stored [B,N,2] (the
+ * layout the segmentation head produces before the reference's permute, model5_b.py:752). */
+int pz_cross_entropy(const float* logits, const float* target, int B, int N, int point_major, float grad_scale,
+                     float* loss, float* dlogits_or_null, pz_stream_t stream);
+/* d loss / d twist through mat = se3.exp(out6), q = R p + t (model5_b.py:947-949) and, when igt is given,
+ * comp_scale * comp(mat, igt) (model5_b.py:963-967):  dout6 = beta*dout6 + J^T(dR, dt), with
+ * dR = sum_n dpts_n p_n^T, dt = sum_n dpts_n.  pts/dpts [B,n,3] (both may be null: comp term only). */
+int pz_pose_grad(const float* out6, const float* pts_or_null, const float* dpts_or_null, int n,
+                 const float* igt_or_null, float comp_scale, int B, float beta, float* dout6, pz_stream_t stream);
+/* torch.optim.Adam (model5_b.py:1454; betas, eps as given) on flat buffers; grads are multiplied by grad_scale
+ * first (1/world_size after a sum all-reduce). */
+int pz_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr,
+                 float beta1, float beta2, float eps, int step, float grad_scale, pz_stream_t stream);
 
 /* --------------------------------------------------------------------- EMD */
 

@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libpuzzlenet_sm100.so")
 
 PZ_PREC_FP32 = 0
 PZ_PREC_BF16 = 1
-ABI_VERSION = 3
+ABI_VERSION = 4
 PZ_SCORE_COLS = 12
 PZ_FLAG_NEED = 1
 PZ_FLAG_REUSE_PACKS = 2
@@ -84,6 +84,31 @@ SIGNATURES = {
     "pz_boundary_topk": (C.c_int, [c_f32p, C.c_int, C.c_int, C.c_int, c_i64p, c_f32p, c_stream]),
     "pz_topk": (C.c_int, [c_f32p, C.c_int, C.c_int, C.c_int, C.c_int, c_i64p, c_f32p, c_stream]),
     "pz_pair_score": (C.c_int, [c_f32p] * 10 + [C.c_int, c_f32p, c_i64p, c_i64p, c_f32p, c_f32p, c_stream]),
+    "pz_sgemm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, c_f32p, C.c_longlong, c_f32p,
+                           C.c_longlong, C.c_float, c_f32p, C.c_longlong, C.c_int, C.c_longlong, C.c_longlong,
+                           C.c_longlong, C.c_int, c_f32p, C.c_int, c_f32p, C.c_longlong, c_f32p, C.c_longlong, c_stream]),
+    "pz_colsum": (C.c_int, [c_f32p, C.c_longlong, C.c_longlong, C.c_int, C.c_float, c_f32p, c_stream]),
+    "pz_axpby": (C.c_int, [C.c_longlong, C.c_int, C.c_float, c_f32p, C.c_longlong, C.c_float, c_f32p, C.c_longlong,
+                           c_f32p, C.c_longlong, c_stream]),
+    "pz_bn_point_train_forward": (C.c_int, [c_f32p, C.c_int, C.c_int, C.c_int, c_f32p, c_f32p, c_f32p, c_f32p,
+                                            C.c_float, C.c_float, C.c_int, c_f32p, c_f32p, c_f32p, c_stream]),
+    "pz_bn_point_train_backward": (C.c_int, [c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, c_f32p, c_f32p, c_f32p,
+                                             C.c_int, c_f32p, c_f32p, c_f32p, c_stream]),
+    "pz_maxpool_forward": (C.c_int, [c_f32p, C.c_longlong, C.c_int, C.c_int, c_f32p, C.c_void_p, c_stream]),
+    "pz_maxpool_backward": (C.c_int, [c_f32p, c_f32p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, c_f32p,
+                                      c_stream]),
+    "pz_scatter_add_rows": (C.c_int, [c_f32p, C.c_longlong, C.c_int, C.c_int, c_i64p, C.c_longlong, C.c_longlong,
+                                      C.c_int, c_f32p, C.c_longlong, c_stream]),
+    "pz_softmax_backward": (C.c_int, [c_f32p, c_f32p, C.c_longlong, C.c_int, C.c_float, c_f32p, c_stream]),
+    "pz_cross_entropy": (C.c_int, [c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_float, c_f32p, c_f32p, c_stream]),
+    "pz_relu_gate": (C.c_int, [C.c_longlong, C.c_int, c_f32p, C.c_longlong, c_f32p, C.c_longlong, c_f32p, C.c_longlong,
+                               c_stream]),
+    "pz_broadcast_rows": (C.c_int, [c_f32p, C.c_longlong, C.c_int, C.c_int, c_f32p, C.c_longlong, c_stream]),
+    "pz_group_sum": (C.c_int, [c_f32p, C.c_longlong, C.c_longlong, C.c_int, C.c_int, c_f32p, c_stream]),
+    "pz_pose_grad": (C.c_int, [c_f32p, c_f32p, c_f32p, C.c_int, c_f32p, C.c_float, C.c_int, C.c_float, c_f32p,
+                               c_stream]),
+    "pz_adam_step": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, C.c_longlong, C.c_float, C.c_float, C.c_float,
+                               C.c_float, C.c_int, C.c_float, c_stream]),
     "pz_emd_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "pz_emd_approxmatch": (C.c_int, [c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, c_f32p, C.c_void_p, C.c_size_t,
                                      c_stream]),

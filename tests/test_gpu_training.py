@@ -1,0 +1,169 @@
+"""GPU parity: the training step (train-mode forward, losses, backward, Adam) through the C ABI vs the CPU training
+oracle (oracle/train_oracle.py, itself pinned to the unmodified reference training_step) and the frozen reference
+gradient digests (tests/golden/reference_training.npz)."""
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import puzzle_oracle as po
+from oracle import train_oracle as to
+from puzzlenet_b200.weights import synthetic_state_dict
+from tests.golden_inputs import FPS_SEED, training_inputs
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "reference_training.npz")
+
+
+def _fresh_model():
+    from puzzlenet_b200.model5_b import TouchedRegraster
+    model = TouchedRegraster(types.SimpleNamespace(dataset="vase", loss_mode=1, loss_sum=False, lr=0.9e-3))
+    model.load_state_dict(synthetic_state_dict(0), strict=True)
+    return model.to(DEV)
+
+
+def _starts(B):
+    torch.manual_seed(FPS_SEED)
+    return torch.stack([torch.randint(0, 1024, (B,)), torch.randint(0, 512, (B,)),
+                        torch.randint(0, 1024, (B,)), torch.randint(0, 512, (B,))])
+
+
+@pytest.fixture(scope="module")
+def step_result():
+    """one forward_backward at B=2 on the GPU and the same step through the CPU oracle's autograd"""
+    from puzzlenet_b200.training import Trainer
+    model = _fresh_model()
+    tr = Trainer(model)
+    batch = training_inputs(2, po.se3_exp)
+    terms = tr.forward_backward([t.to(DEV) for t in batch], starts=_starts(2))
+    torch.cuda.synchronize()
+    sd = {k: (v.clone().requires_grad_() if v.is_floating_point() and "running" not in k else v.clone())
+          for k, v in synthetic_state_dict(0).items()}
+    bn_state = {}
+    torch.manual_seed(FPS_SEED)
+    ref = to.training_loss(sd, batch, bn_state=bn_state)
+    ref["loss"].backward()
+    return model, tr, terms, sd, ref, bn_state
+
+
+def test_loss_terms_match_oracle(step_result):
+    _, tr, terms, _, ref, _ = step_result
+    for k in ("loss_re", "loss_g", "loss_emd", "ce_f", "ce_m", "loss_fpcb", "loss_mrpcb", "emd_fpcb", "emd_mrpcb", "loss"):
+        np.testing.assert_allclose(terms[k], float(ref[k]), rtol=2e-4, err_msg=k)
+    np.testing.assert_allclose(tr.last["out"].cpu().numpy(), ref["out"].detach().numpy(), rtol=1e-4, atol=1e-5)
+
+
+def test_gradients_match_oracle_autograd(step_result):
+    """every live parameter: relative L2 error of the gradient tensor <= 1e-3 (fp32 accumulation-order noise of
+    ~1e-5 on the large tensors; the split-K atomics and the EMD's __expf vs expf are the slack)"""
+    model, tr, _, sd, _, _ = step_result
+    worst = {}
+    for name, p in model.named_parameters():
+        ref = sd[name].grad
+        if name.startswith(("fpc_decoder", "rpc_decoder")) or name == "dt":
+            assert ref is None
+            continue
+        got = tr.flat.g(p).cpu()
+        if name.endswith("mlpk.bias"):            # mathematically zero (constant per softmax row)
+            q = sd[name.replace("mlpk", "mlpq")].grad
+            assert got.norm() < 1e-3 * q.norm()
+            continue
+        err = (got - ref).norm() / ref.norm().clamp_min(1e-20)
+        worst[name] = err.item()
+    bad = {k: v for k, v in worst.items() if not v < 1e-3}
+    assert not bad, bad
+    assert len(worst) > 100
+
+
+def test_gradients_match_reference_goldens(step_result):
+    model, tr, terms, _, _, _ = step_result
+    gold = dict(np.load(GOLDEN))
+    np.testing.assert_allclose(terms["loss"], gold["loss"], rtol=2e-4)
+    for name, p in model.named_parameters():
+        key = "grad/" + name
+        if key not in gold or name.endswith("mlpk.bias"):
+            continue
+        d = to.grad_digest(tr.flat.g(p).cpu())
+        np.testing.assert_allclose(d[1], gold[key][1], rtol=5e-3, err_msg=name)
+        np.testing.assert_allclose(d[2:], gold[key][2:], rtol=0, atol=3e-3 * np.sqrt(gold[key][1]), err_msg=name)
+
+
+def test_bn_running_stats_updated(step_result):
+    model, _, _, _, _, bn_state = step_result
+    for name in ("Encoder.bn1", "Encoder.bn2", "Encoder2.bn1", "Encoder2.bn2"):
+        mod = model.get_submodule(name)
+        np.testing.assert_allclose(mod.running_mean.cpu().numpy(), bn_state[name + ".running_mean"].numpy(),
+                                   rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(mod.running_var.cpu().numpy(), bn_state[name + ".running_var"].numpy(),
+                                   rtol=1e-4, atol=1e-6)
+
+
+def test_adam_step_matches_torch_adam():
+    """three optimizer steps on the flat buffer vs torch.optim.Adam + StepLR on a CPU copy with the same grads"""
+    from puzzlenet_b200.training import Trainer
+    model = _fresh_model()
+    tr = Trainer(model, lr=1e-3)
+    ref_p = tr.flat.params.detach().cpu().clone().requires_grad_()
+    opt = torch.optim.Adam([ref_p], lr=1e-3)
+    sched = torch.optim.lr_scheduler.StepLR(opt, 50, 0.999)
+    g = torch.Generator().manual_seed(0)
+    for _ in range(3):
+        grad = torch.randn(tr.flat.n, generator=g) * 0.1
+        tr.flat.grads.copy_(grad)
+        tr.optimizer_step()
+        ref_p.grad = grad.clone()
+        opt.step()
+        sched.step()
+    np.testing.assert_allclose(tr.flat.params.cpu().numpy(), ref_p.detach().numpy(), rtol=1e-5, atol=1e-7)
+    # parameters are views of the flat buffer: the modules see the update
+    assert model.tfMLP[0].weight.data_ptr() >= tr.flat.params.data_ptr()
+
+
+def test_training_reduces_loss():
+    """a few full steps on one fixed batch with a small learning rate (the synthetic weights put the EMD term in the
+    thousands, where Adam's unit-size first steps at lr 1e-3 overshoot): the loss goes down step after step, and
+    eval-mode inference still runs afterwards"""
+    from puzzlenet_b200.training import Trainer
+    from puzzlenet_b200.weights import make_batch
+    model = _fresh_model()
+    tr = Trainer(model, lr=1e-5)
+    batch = [t.to(DEV) for t in training_inputs(4, po.se3_exp)]
+    st = _starts(4)
+    losses_seen = [tr.training_step(batch, starts=st)["loss"] for _ in range(6)]
+    assert all(np.isfinite(losses_seen)) and losses_seen[-1] < losses_seen[1] < losses_seen[0], losses_seen
+    model.eval()
+    out = model.predict5(make_batch(batch[0], batch[1]), 4)[0]
+    assert torch.isfinite(out).all()
+
+
+@pytest.mark.parametrize("ta,tb", [(False, False), (False, True), (True, False), (True, True)])
+def test_sgemm_variants(ta, tb):
+    from puzzlenet_b200 import training as T
+    g = torch.Generator().manual_seed(5)
+    M, N, K = 197, 131, 67
+    A = torch.randn((K, M) if ta else (M, K), generator=g)
+    B = torch.randn((N, K) if tb else (K, N), generator=g)
+    bias = torch.randn(N, generator=g)
+    ref = (A.T if ta else A) @ (B.T if tb else B)
+    Ad, Bd = A.to(DEV), B.to(DEV)
+    C = torch.empty(M, N, device=DEV)
+    T.gemm(Ad, Bd, C, M, N, K, ta=ta, tb=tb, lda=A.shape[1], ldb=B.shape[1], ldc=N, bias=bias.to(DEV), relu=True)
+    np.testing.assert_allclose(C.cpu().numpy(), torch.relu(ref + bias).numpy(), rtol=1e-4, atol=1e-4)
+    C.zero_()
+    T.gemm(Ad, Bd, C, M, N, K, ta=ta, tb=tb, lda=A.shape[1], ldb=B.shape[1], ldc=N, splitk=5, alpha=0.5)
+    np.testing.assert_allclose(C.cpu().numpy(), 0.5 * ref.numpy(), rtol=1e-4, atol=1e-4)
+    # batched, with beta / mask / residual
+    Ab = torch.randn(3, *A.shape, generator=g)
+    Bb = torch.randn(3, *B.shape, generator=g)
+    C0 = torch.randn(3, M, N, generator=g)
+    mask = torch.randn(3, M, N, generator=g)
+    res = torch.randn(3, M, N, generator=g)
+    refb = (Ab.transpose(1, 2) if ta else Ab) @ (Bb.transpose(1, 2) if tb else Bb) + 2.0 * C0
+    refb = torch.where(mask > 0, refb, torch.zeros(())) + res
+    Cd = C0.to(DEV)
+    T.gemm(Ab.to(DEV), Bb.to(DEV), Cd, M, N, K, ta=ta, tb=tb, lda=A.shape[1], ldb=B.shape[1], ldc=N, beta=2.0, batch=3,
+           sa=A.numel(), sb=B.numel(), sc=M * N, mask=mask.to(DEV), ldmask=N, residual=res.to(DEV), ldres=N)
+    np.testing.assert_allclose(Cd.cpu().numpy(), refb.numpy(), rtol=1e-4, atol=1e-4)
