@@ -18,8 +18,10 @@ through ``libpuzzlenet_sm100.so`` (hand-written sm_100a kernels, C ABI in
 Deviations from the reference, all documented in DESIGN.md:
 * ``TouchedRegraster.forward`` delegates to ``predict5`` (the reference's ``forward`` calls the
   broken ``predict4``).
-* ``predict5(training=True)`` raises ``NotImplementedError``: this build is inference-only
-  (batch-statistics BatchNorm and the backward pass are not implemented).
+* Training has no autograd graph: ``training_step`` runs forward, losses, the hand-written backward, the
+  gradient all-reduce and Adam itself (``puzzlenet_b200/training.py``; Lightning: manual optimization).
+  ``predict5(training=True)`` is the train-mode forward only; the ``predict6`` pretraining branch is
+  inference-only.
 * The class derives from ``nn.Module`` when ``pytorch_lightning`` is not installed.
 """
 from __future__ import annotations
@@ -153,8 +155,9 @@ class PCTransformer_nonsort(nn.Module):
 
     def forward(self, xyz, return_intermediates: bool = False):
         if self.training:
-            raise NotImplementedError("puzzlenet_b200 is inference-only: call .eval() (train-mode BatchNorm over "
-                                      "the point index and the backward pass are not implemented)")
+            raise NotImplementedError("a standalone PCTransformer_nonsort only runs in eval mode; the train-mode "
+                                      "forward/backward lives in TouchedRegraster.training_step "
+                                      "(puzzlenet_b200/training.py)")
         _lib.require_cuda(xyz)
         x = xyz.contiguous().float()
         if x.dim() != 3 or x.shape[1] != 1024 or x.shape[2] != 3:
@@ -241,6 +244,7 @@ class TouchedRegraster(_Base):
         self._pack_keys = {}
         self._graphs = {}
         self._capture_stream = None
+        self._trainer_state = None
         self.cuda_graphs = False      # opt-in: replay one captured CUDA graph per forward (see _graph_replay)
 
     # ---- weights as C structs (rebuilt per call: ~100 data_ptr() reads, no device work)
@@ -359,8 +363,12 @@ class TouchedRegraster(_Base):
         indices in the reference's draw order; when omitted the four ``torch.randint`` draws are taken
         from the CPU generator exactly as the reference does."""
         if training:
-            raise NotImplementedError("puzzlenet_b200.predict5 is inference-only (training=True needs batch-stat "
-                                      "BatchNorm and backward kernels, which this build does not have)")
+            # train-mode forward (model5_b.py:684-690: batch-statistics BatchNorm, running stats updated); fp32 only
+            _lib.require_cuda(batch[0], batch[1])
+            for mod in (self.Encoder, self.Encoder2, self.tfMLP, self.fpc_decoder, self.rpc_decoder):
+                mod.train()
+            r = self.trainer_state().predict5_train(batch[0], batch[1], starts)
+            return r if need else (r[0], r[0], r[6], r[7])
         return self._predict(batch, need, starts, shared=False)
 
     def predict6(self, batch, batch_indic, need=False, training=False, pretrain=False, starts=None):
@@ -403,6 +411,38 @@ class TouchedRegraster(_Base):
         if not need:
             return out6, out6, de_fpcb, de_mrpcb
         return out6, [0], x2f, af, x2m, am, de_fpcb, de_mrpcb
+
+    # ---- training (model5_b.py:912-1155, :1453-1457)
+    automatic_optimization = False     # Lightning: training_step below runs backward + optimizer itself
+
+    def trainer_state(self):
+        """The :class:`puzzlenet_b200.training.Trainer` bound to this model (created on first use: it re-homes the
+        live parameters into one flat buffer; options are read from ``self.C``)."""
+        if getattr(self, "_trainer_state", None) is None:
+            from .training import Trainer
+            self._trainer_state = Trainer(self, self.C)
+        return self._trainer_state
+
+    def training_step(self, batch, batch_indic, starts=None):
+        """model5_b.py:912-1155 (non-pretrain branch) + the optimizer step of :1453-1457.  The reference returns a
+        loss for autograd; there is no autograd graph here -- forward, losses, the hand-written backward, the
+        gradient all-reduce and Adam all happen inside this call (Lightning: manual optimization).  Returns
+        ``{'loss': 0-d tensor, 'terms': dict of the logged scalars}``."""
+        if getattr(self.C, "pretrain_epochs", 0) and getattr(self, "current_epoch", 1 << 30) < self.C.pretrain_epochs:
+            raise NotImplementedError("the predict6 pretraining branch (model5_b.py:928-931) has no backward here")
+        terms = self.trainer_state().training_step(batch, starts)
+        if hasattr(self, "log"):
+            try:
+                for k, v in terms.items():
+                    self.log("train/" + k, v)
+            except Exception:      # outside a Lightning loop self.log raises
+                pass
+        return {"loss": torch.tensor(terms["loss"]), "terms": terms}
+
+    def configure_optimizers(self):
+        """model5_b.py:1453-1457: Adam(lr) + StepLR(50, 0.999) are fused into ``pz_adam_step`` inside
+        :meth:`training_step`; nothing is handed to Lightning."""
+        return None
 
     # ---- loss-side helpers and the evaluation step (same names as the reference methods)
     def chamfer_loss(self, a, b):

@@ -292,12 +292,10 @@ class Trainer:
                 linear_bwd(dy, lin.weight.shape[0], xin, ldin, M, lin, G(lin.weight), G(lin.bias), dx, lddx)
 
     # -------------------------------------------------------------------------------------------- the step
-    def forward_backward(self, batch, starts=None) -> Dict[str, float]:
-        """Train-mode predict5 + losses + backward into ``self.flat.grads`` (zeroed first).  ``starts`` [4,B] as in
-        ``predict5``.  Returns the logged terms as python floats (one device->host copy)."""
+    def _forward(self, fpc, mrpc, starts):
+        """train-mode predict5 (model5_b.py:672-759 with training=True): both encoders, the pose head and the two
+        boundary heads; returns every buffer the backward pass reads.  Must run inside ``torch.cuda.device``."""
         m = self.model
-        fpc, mrpc, igt, rpc, fpcb, rpcb, fpc_idx, rpc_idx = [t.contiguous().float() for t in batch[:8]]
-        _lib.require_cuda(fpc, mrpc, igt, rpc, fpcb, rpcb, fpc_idx, rpc_idx)
         B = fpc.shape[0]
         if starts is None:
             starts = torch.stack([torch.randint(0, 1024, (B,), dtype=torch.long),
@@ -305,30 +303,65 @@ class Trainer:
                                   torch.randint(0, 1024, (B,), dtype=torch.long),
                                   torch.randint(0, 512, (B,), dtype=torch.long)])
         starts = starts.to(self.dev, torch.int64).contiguous()
+        ef = self._encoder_forward("E1", m.Encoder, fpc, starts[0], starts[1])
+        em = self._encoder_forward("E2", m.Encoder2, mrpc, starts[2], starts[3])
+        R0 = B * NPTS
+        # ---- pose head: tfMLP(cat(f_global_fpc, f_global_mrpc))  (model5_b.py:723-725)
+        f = self.buf("f", B, 2048)
+        axpby(B, 1024, 1.0, ef.fg, 1024, 0.0, None, 0, f, 2048)
+        axpby(B, 1024, 1.0, em.fg, 1024, 0.0, None, 0, f[:, 1024:], 2048)
+        tf_l, tf_a = self._mlp_forward("tf", m.tfMLP, f, 2048, B)
+        # ---- boundary heads (model5_b.py:729-754; both "global" vectors come from the mrpc branch, D6)
+        lf_l, lf_a = self._mlp_forward("lf", m.MLPLocalPreFpc, ef.xf, 64, R0)
+        lm_l, lm_a = self._mlp_forward("lm", m.MLPLocalPreRpc, em.xf, 64, R0)
+        gmax, garg = self.buf("gmax", B, 64), self.buf("garg", B, 64, dtype=torch.int32)
+        _lib.call("pz_maxpool_forward", _p(lm_a[-1]), B, NPTS, 64, _p(gmax), _p(garg), _st())
+        seg_f, seg_m = self.buf("seg_f", R0, 128), self.buf("seg_m", R0, 128)
+        for seg, loc in ((seg_f, lf_a[-1]), (seg_m, lm_a[-1])):
+            _lib.call("pz_broadcast_rows", _p(gmax), B, NPTS, 64, _p(seg), 128, _st())
+            axpby(R0, 64, 1.0, loc, 64, 0.0, None, 0, seg[:, 64:], 128)
+        sf_l, sf_a = self._mlp_forward("sf", m.MLPFpcb, seg_f, 128, R0)
+        sm_l, sm_a = self._mlp_forward("sm", m.MLPRpcb, seg_m, 128, R0)
+        return dict(ef=ef, em=em, f=f, tf_l=tf_l, tf_a=tf_a, out6=tf_a[-1], lf_l=lf_l, lf_a=lf_a, lm_l=lm_l, lm_a=lm_a,
+                    gmax=gmax, garg=garg, seg_f=seg_f, seg_m=seg_m, sf_l=sf_l, sf_a=sf_a, sm_l=sm_l, sm_a=sm_a,
+                    logit_f=sf_a[-1], logit_m=sm_a[-1])            # logits are [B*1024, 2] (point-major)
+
+    def predict5_train(self, fpc, mrpc, starts=None):
+        """``predict5(batch, _, need=True, training=True)`` (model5_b.py:672-759): the train-mode forward (batch
+        statistics in, and running statistics updated by, the four BatchNorm layers) without the backward pass ->
+        ``(out, [0], x2_fpc, attention_fpc, x2_mrpc, attention_mrpc, de_fpcb, de_mrpcb)``."""
+        fpc, mrpc = fpc.contiguous().float(), mrpc.contiguous().float()
+        _lib.require_cuda(fpc, mrpc)
+        B = fpc.shape[0]
+        with torch.cuda.device(self.dev):
+            fw = self._forward(fpc, mrpc, starts)
+            res = []
+            for e in (fw["ef"], fw["em"]):
+                att = torch.empty(B, S2, S2, device=self.dev)
+                n = B * S2
+                axpby(n, S2, 0.25, e.A[0], S2, 0.25, e.A[1], S2, att, S2)          # mean of the 4 maps (:468-469)
+                axpby(n, S2, 0.25, e.A[2], S2, 1.0, att, S2, att, S2)
+                axpby(n, S2, 0.25, e.A[3], S2, 1.0, att, S2, att, S2)
+                res += [e.x2.clone(), att]
+        de_f = fw["logit_f"].view(B, NPTS, 2).permute(0, 2, 1).contiguous()
+        de_m = fw["logit_m"].view(B, NPTS, 2).permute(0, 2, 1).contiguous()
+        return fw["out6"].clone(), [0], res[0], res[1], res[2], res[3], de_f, de_m
+
+    def forward_backward(self, batch, starts=None) -> Dict[str, float]:
+        """Train-mode predict5 + losses + backward into ``self.flat.grads`` (zeroed first).  ``starts`` [4,B] as in
+        ``predict5``.  Returns the logged terms as python floats (one device->host copy)."""
+        fpc, mrpc, igt, rpc, fpcb, rpcb, fpc_idx, rpc_idx = [t.contiguous().float() for t in batch[:8]]
+        _lib.require_cuda(fpc, mrpc, igt, rpc, fpcb, rpcb, fpc_idx, rpc_idx)
+        B = fpc.shape[0]
         G = self.flat.g
         self.flat.grads.zero_()
         with torch.cuda.device(self.dev):
-            ef = self._encoder_forward("E1", m.Encoder, fpc, starts[0], starts[1])
-            em = self._encoder_forward("E2", m.Encoder2, mrpc, starts[2], starts[3])
+            fw = self._forward(fpc, mrpc, starts)
+            ef, em, f, tf_l, tf_a, out6 = fw["ef"], fw["em"], fw["f"], fw["tf_l"], fw["tf_a"], fw["out6"]
+            lf_l, lf_a, lm_l, lm_a, gmax, garg = fw["lf_l"], fw["lf_a"], fw["lm_l"], fw["lm_a"], fw["gmax"], fw["garg"]
+            seg_f, seg_m, sf_l, sf_a, sm_l, sm_a = fw["seg_f"], fw["seg_m"], fw["sf_l"], fw["sf_a"], fw["sm_l"], fw["sm_a"]
+            logit_f, logit_m = fw["logit_f"], fw["logit_m"]
             R0 = B * NPTS
-            # ---- pose head: tfMLP(cat(f_global_fpc, f_global_mrpc))  (model5_b.py:723-725)
-            f = self.buf("f", B, 2048)
-            axpby(B, 1024, 1.0, ef.fg, 1024, 0.0, None, 0, f, 2048)
-            axpby(B, 1024, 1.0, em.fg, 1024, 0.0, None, 0, f[:, 1024:], 2048)
-            tf_l, tf_a = self._mlp_forward("tf", m.tfMLP, f, 2048, B)
-            out6 = tf_a[-1]
-            # ---- boundary heads (model5_b.py:729-754; both "global" vectors come from the mrpc branch, D6)
-            lf_l, lf_a = self._mlp_forward("lf", m.MLPLocalPreFpc, ef.xf, 64, R0)
-            lm_l, lm_a = self._mlp_forward("lm", m.MLPLocalPreRpc, em.xf, 64, R0)
-            gmax, garg = self.buf("gmax", B, 64), self.buf("garg", B, 64, dtype=torch.int32)
-            _lib.call("pz_maxpool_forward", _p(lm_a[-1]), B, NPTS, 64, _p(gmax), _p(garg), _st())
-            seg_f, seg_m = self.buf("seg_f", R0, 128), self.buf("seg_m", R0, 128)
-            for seg, loc in ((seg_f, lf_a[-1]), (seg_m, lm_a[-1])):
-                _lib.call("pz_broadcast_rows", _p(gmax), B, NPTS, 64, _p(seg), 128, _st())
-                axpby(R0, 64, 1.0, loc, 64, 0.0, None, 0, seg[:, 64:], 128)
-            sf_l, sf_a = self._mlp_forward("sf", m.MLPFpcb, seg_f, 128, R0)
-            sm_l, sm_a = self._mlp_forward("sm", m.MLPRpcb, seg_m, 128, R0)
-            logit_f, logit_m = sf_a[-1], sm_a[-1]                     # [B*1024, 2] (point-major)
             # ---- losses
             vals = self.buf("loss_terms", 16)
             vals.zero_()

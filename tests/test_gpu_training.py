@@ -167,3 +167,24 @@ def test_sgemm_variants(ta, tb):
     T.gemm(Ab.to(DEV), Bb.to(DEV), Cd, M, N, K, ta=ta, tb=tb, lda=A.shape[1], ldb=B.shape[1], ldc=N, beta=2.0, batch=3,
            sa=A.numel(), sb=B.numel(), sc=M * N, mask=mask.to(DEV), ldmask=N, residual=res.to(DEV), ldres=N)
     np.testing.assert_allclose(Cd.cpu().numpy(), refb.numpy(), rtol=1e-4, atol=1e-4)
+
+
+def test_predict5_training_mode_and_model_training_step():
+    """predict5(training=True, need=True) = the train-mode forward (batch-stat BN) vs the oracle; model.training_step
+    = Trainer.training_step behind the reference's method name."""
+    model = _fresh_model()
+    batch = training_inputs(2, po.se3_exp)
+    st = _starts(2)
+    r = model.predict5([t.to(DEV) for t in batch], 2, need=True, training=True, starts=st)
+    sd = synthetic_state_dict(0)
+    o = po.predict5(sd, batch[0], batch[1], need=True, starts=((st[0], st[1]), (st[2], st[3])), train_bn=True)
+    assert len(r) == 8 and r[1] == [0]
+    np.testing.assert_allclose(r[0].cpu().numpy(), o["out"].numpy(), rtol=1e-4, atol=1e-5)
+    np.testing.assert_array_equal(r[2].cpu().numpy(), o["enc_fpc"]["x2"].numpy())
+    for got, key in ((r[3], "enc_fpc"), (r[5], "enc_mrpc")):        # 1e-4 of the map's max magnitude, as for features
+        ref_a = o[key]["attention"].numpy()
+        assert np.abs(got.cpu().numpy() - ref_a).max() / np.abs(ref_a).max() < 1e-4
+    ref = o["de_fpcb"].numpy()
+    assert np.abs(r[6].cpu().numpy() - ref).max() / np.abs(ref).max() < 1e-4
+    out = model.training_step([t.to(DEV) for t in batch], 0, starts=st)
+    assert np.isfinite(float(out["loss"])) and "loss_emd" in out["terms"]

@@ -44,7 +44,7 @@ def test_cpu_tensors_fail_loudly(state_dict):
     fpc, mrpc = weights.synthetic_pairs(1)
     with pytest.raises(RuntimeError, match="CUDA"):
         model.predict5(weights.make_batch(fpc, mrpc), 0)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError, match="CUDA"):          # the train-mode forward is CUDA-only as well
         model.predict5(weights.make_batch(fpc, mrpc), 0, training=True)
     enc = PCTransformer_nonsort(_cfg())
     with pytest.raises(NotImplementedError):          # train mode
