@@ -105,6 +105,12 @@ int pz_group_concat(const float* xyz, const float* feat_or_null, const float* ne
                     const int64_t* knn_idx, int B, int N, int D, int S, int K, float* new_points,
                     float* grouped_xyz_or_null, pz_stream_t stream);
 
+/* the same with a caller-chosen row stride ld >= 3+D for new_points; columns [3+D, ld) are zero-filled (operand
+ * padding for the tensor-core training GEMMs, whose K must be a multiple of 32). */
+int pz_group_concat_padded(const float* xyz, const float* feat_or_null, const float* new_xyz,
+                           const int64_t* knn_idx, int B, int N, int D, int S, int K, int ld, float* new_points,
+                           float* grouped_xyz_or_null, pz_stream_t stream);
+
 /* ------------------------------------------------------------ fused blocks */
 
 /* sample_and_group's grouping + the shared MLP + neighbourhood max-pool in one pass, never
@@ -284,6 +290,15 @@ int pz_sgemm(int transA, int transB, int M, int N, int K, float alpha, const flo
              long long strideB, long long strideC, int splitk, const float* bias_or_null, int relu,
              const float* mask_or_null, long long ldmask, const float* residual_or_null, long long ldres,
              pz_stream_t stream);
+/* The same product on the tcgen05 tensor cores in TF32 (fp32 in memory, operands rounded to a 10-bit mantissa by
+ * the MMA, fp32 accumulate) -- what stock PyTorch 1.10, the version the reference pins, runs nn.Linear with on
+ * Ampere-or-newer GPUs.  C[m,n] = sum_k A(m,k) B(n,k); an operand is K-major (A[m*lda + k], B[n*ldb + k]) or, with
+ * *_mn_major != 0, MN-major (A[k*lda + m], B[k*ldb + n]).  Epilogue: + bias[n], + C (accumulate), ReLU, mask gate.
+ * splitk > 1: K is split over the persistent grid and partial tiles are atomically ADDED into C (pre-zero it).
+ * Supported: M % 128 == 0, N % 128 == 0, K % 32 == 0, 16-byte aligned rows. */
+int pz_gemm_tf32(int a_mn_major, int b_mn_major, int M, int N, int K, const float* A, long long lda, const float* B,
+                 long long ldb, float* C, long long ldc, int splitk, const float* bias_or_null, int relu,
+                 const float* mask_or_null, long long ldmask, int accumulate, pz_stream_t stream);
 /* out[n] = beta*out[n] + sum_m x[m*ld + n]  (bias gradients). */
 int pz_colsum(const float* x, long long ld, long long M, int N, float beta, float* out, pz_stream_t stream);
 /* out[r,c] = a*x[r,c] + b*y[r,c] with row strides (y may be null). */

@@ -57,6 +57,8 @@ SIGNATURES = {
     "pz_gather": (C.c_int, [C.c_void_p, c_i64p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, c_stream]),
     "pz_group_concat": (C.c_int, [c_f32p, c_f32p, c_f32p, c_i64p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                   c_f32p, c_f32p, c_stream]),
+    "pz_group_concat_padded": (C.c_int, [c_f32p, c_f32p, c_f32p, c_i64p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         C.c_int, c_f32p, c_f32p, c_stream]),
     "pz_group_mlp_workspace_bytes": (C.c_size_t, [C.c_int] * 7),
     "pz_group_mlp_maxpool": (C.c_int, [c_f32p, c_f32p, c_f32p, c_i64p, c_f32p, c_f32p, c_f32p, c_f32p]
                              + [C.c_int] * 8 + [c_f32p, C.c_void_p, C.c_size_t, c_stream]),
@@ -87,6 +89,8 @@ SIGNATURES = {
     "pz_sgemm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, c_f32p, C.c_longlong, c_f32p,
                            C.c_longlong, C.c_float, c_f32p, C.c_longlong, C.c_int, C.c_longlong, C.c_longlong,
                            C.c_longlong, C.c_int, c_f32p, C.c_int, c_f32p, C.c_longlong, c_f32p, C.c_longlong, c_stream]),
+    "pz_gemm_tf32": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_f32p, C.c_longlong, c_f32p, C.c_longlong,
+                               c_f32p, C.c_longlong, C.c_int, c_f32p, C.c_int, c_f32p, C.c_longlong, C.c_int, c_stream]),
     "pz_colsum": (C.c_int, [c_f32p, C.c_longlong, C.c_longlong, C.c_int, C.c_float, c_f32p, c_stream]),
     "pz_axpby": (C.c_int, [C.c_longlong, C.c_int, C.c_float, c_f32p, C.c_longlong, C.c_float, c_f32p, C.c_longlong,
                            c_f32p, C.c_longlong, c_stream]),

@@ -413,10 +413,10 @@ __global__ void __launch_bounds__(256) group_concat_kernel(const float* __restri
                                                            const float* __restrict__ feat,
                                                            const float* __restrict__ new_xyz,
                                                            const int64_t* __restrict__ knn, int N,
-                                                           int D, int S, int K, size_t rows,
+                                                           int D, int S, int K, size_t rows, int ld,
                                                            float* __restrict__ new_points,
                                                            float* __restrict__ grouped_xyz) {
-  const int W = 3 + D;
+  const int W = ld;                                // row stride >= 3 + D; the columns beyond 3 + D are zero-filled
   const int lane = threadIdx.x & 31;
   const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
@@ -431,6 +431,7 @@ __global__ void __launch_bounds__(256) group_concat_kernel(const float* __restri
       if (grouped_xyz) grouped_xyz[r * 3 + lane] = v;
     }
     for (int d = lane; d < D; d += 32) o[3 + d] = feat[j * D + d];
+    for (int d = 3 + D + lane; d < W; d += 32) o[d] = 0.f;
   }
 }
 
@@ -503,14 +504,22 @@ extern "C" int pz_gather(const void* pts, const int64_t* idx, int B, int N, int 
 extern "C" int pz_group_concat(const float* xyz, const float* feat_or_null, const float* new_xyz,
                                const int64_t* knn_idx, int B, int N, int D, int S, int K,
                                float* new_points, float* grouped_xyz_or_null, pz_stream_t stream) {
+  return pz_group_concat_padded(xyz, feat_or_null, new_xyz, knn_idx, B, N, D, S, K, 3 + D, new_points,
+                                grouped_xyz_or_null, stream);
+}
+
+extern "C" int pz_group_concat_padded(const float* xyz, const float* feat_or_null, const float* new_xyz,
+                                      const int64_t* knn_idx, int B, int N, int D, int S, int K, int ld,
+                                      float* new_points, float* grouped_xyz_or_null, pz_stream_t stream) {
   PZ_REQUIRE(B >= 0 && N >= 1 && D >= 0 && S >= 0 && K >= 1, PZ_ERR_ARG, "pz_group_concat: bad sizes");
+  PZ_REQUIRE(ld >= 3 + D, PZ_ERR_ARG, "pz_group_concat: row stride %d < 3 + D", ld);
   size_t rows = (size_t)B * S * K;
   if (rows == 0) return 0;
   PZ_REQUIRE(xyz && new_xyz && knn_idx && new_points, PZ_ERR_ARG, "pz_group_concat: null pointer");
   PZ_REQUIRE(feat_or_null || D == 0, PZ_ERR_ARG, "pz_group_concat: feat is null but D=%d", D);
   size_t want = (rows + 7) / 8;
   int blocks = (int)(want < (size_t)kNumSMs * 16 ? want : (size_t)kNumSMs * 16);
-  group_concat_kernel<<<blocks, 256, 0, as_stream(stream)>>>(xyz, feat_or_null, new_xyz, knn_idx, N, D, S, K, rows, new_points, grouped_xyz_or_null);
+  group_concat_kernel<<<blocks, 256, 0, as_stream(stream)>>>(xyz, feat_or_null, new_xyz, knn_idx, N, D, S, K, rows, ld, new_points, grouped_xyz_or_null);
   PZ_LAUNCH_CHECK();
   return 0;
 }

@@ -44,25 +44,57 @@ def _splitk(rows: int, out_tiles: int) -> int:
     return max(1, min(want, rows // 256 if rows >= 512 else 1))
 
 
-def linear_fwd(x, ldx, M, lin, out, ldo, relu=False, residual=None, ldres=0):
-    """out[M, N] = act(x[M, K] W^T + b) (+ residual)"""
-    N, K = lin.weight.shape
-    gemm(x, lin.weight, out, M, N, K, tb=True, lda=ldx, ldb=K, ldc=ldo, bias=lin.bias, relu=relu, residual=residual,
-         ldres=ldres)
+_TF32 = False     # set by Trainer around a step (module-level so the helpers below stay plain functions)
 
 
-def linear_bwd(dy, lddy, x, ldx, M, lin, gw, gb, dx=None, lddx=0, mask=None, ldmask=0, beta=0.0):
-    """dW += dy^T x, db += colsum(dy); dx = (beta*dx +) dy W, gated by (mask > 0) when given."""
-    N, K = lin.weight.shape
-    tiles = ((N + 127) // 128) * ((K + 127) // 128)
-    sk = _splitk(M, tiles)
-    if sk > 1:          # partial sums are atomically added into the (pre-zeroed) flat gradient buffer
-        gemm(dy, x, gw, N, K, M, ta=True, lda=lddy, ldb=ldx, ldc=K, splitk=sk)
+def _al16(*ts):
+    return all(t is None or t.data_ptr() % 16 == 0 for t in ts)
+
+
+def _gemm_tf32(a_mn, b_mn, M, N, K, A, lda, B, ldb, C, ldc, splitk=1, bias=None, relu=False, mask=None, ldmask=0,
+               accumulate=False):
+    _lib.call("pz_gemm_tf32", int(a_mn), int(b_mn), M, N, K, _p(A), lda, _p(B), ldb, _p(C), ldc, splitk, _p(bias),
+              int(relu), _p(mask), ldmask, int(accumulate), _st())
+
+
+def linear_fwd(x, ldx, M, lin, out, ldo, relu=False, W=None, K=None):
+    """out[M, N] = act(x[M, K] W^T + b).  ``W``/``K`` override the weight with a zero-padded copy (row stride K)."""
+    N, K0 = lin.weight.shape
+    W = lin.weight if W is None else W
+    K = K0 if K is None else K
+    if _TF32 and M % 128 == 0 and N % 128 == 0 and K % 32 == 0 and ldx % 4 == 0 and ldo % 4 == 0 \
+            and _al16(x, W, out, lin.bias):
+        _gemm_tf32(0, 0, M, N, K, x, ldx, W, K, out, ldo, bias=lin.bias, relu=relu)
     else:
-        gemm(dy, x, gw, N, K, M, ta=True, lda=lddy, ldb=ldx, ldc=K, beta=1.0)
+        gemm(x, W, out, M, N, K, tb=True, lda=ldx, ldb=K, ldc=ldo, bias=lin.bias, relu=relu)
+
+
+def linear_bwd(dy, lddy, x, ldx, M, lin, gw, gb, dx=None, lddx=0, mask=None, ldmask=0, beta=0.0, W=None, K=None):
+    """dW += dy^T x, db += colsum(dy); dx = (beta*dx +) dy W, gated by (mask > 0) when given.  ``W``/``K``: as in
+    linear_fwd (``gw`` then has row stride K as well)."""
+    N, K0 = lin.weight.shape
+    W = lin.weight if W is None else W
+    K = K0 if K is None else K
+    if _TF32 and N % 128 == 0 and K % 128 == 0 and M % 32 == 0 and M >= 4096 and lddy % 4 == 0 and ldx % 4 == 0 \
+            and _al16(dy, x, gw):
+        tiles = (N // 128) * (K // (256 if K % 256 == 0 else 128))
+        kblocks = M // 32
+        sk = max(2, min(max(kblocks // 8, 1), -(-2 * 148 // tiles)))
+        _gemm_tf32(1, 1, N, K, M, dy, lddy, x, ldx, gw, K, splitk=sk)
+    else:
+        tiles = ((N + 127) // 128) * ((K + 127) // 128)
+        sk = _splitk(M, tiles)
+        if sk > 1:          # partial sums are atomically added into the (pre-zeroed) flat gradient buffer
+            gemm(dy, x, gw, N, K, M, ta=True, lda=lddy, ldb=ldx, ldc=K, splitk=sk)
+        else:
+            gemm(dy, x, gw, N, K, M, ta=True, lda=lddy, ldb=ldx, ldc=K, beta=1.0)
     _lib.call("pz_colsum", _p(dy), lddy, M, N, 1.0, _p(gb), _st())
     if dx is not None:
-        gemm(dy, lin.weight, dx, M, K, N, lda=lddy, ldb=K, ldc=lddx, beta=beta, mask=mask, ldmask=ldmask)
+        if _TF32 and M % 128 == 0 and K % 128 == 0 and N % 32 == 0 and lddy % 4 == 0 and lddx % 4 == 0 \
+                and beta in (0.0, 1.0) and _al16(dy, W, dx, mask) and (mask is None or ldmask % 4 == 0):
+            _gemm_tf32(0, 1, M, K, N, dy, lddy, W, K, dx, lddx, mask=mask, ldmask=ldmask, accumulate=beta == 1.0)
+        else:
+            gemm(dy, W, dx, M, K, N, lda=lddy, ldb=K, ldc=lddx, beta=beta, mask=mask, ldmask=ldmask)
 
 
 def axpby(rows, cols, a, x, ldx, b, y, ldy, out, ldo):
@@ -76,16 +108,17 @@ def total(t: torch.Tensor, out: torch.Tensor, slot: int):
 
 class _Flat:
     """All live parameters as views of one flat fp32 buffer (+ a same-shaped gradient buffer): one all-reduce and
-    one Adam launch per step.  The parameters without gradient in the reference (the two unused decoders and ``dt``,
+    one Adam launch per step (views start on 256-byte boundaries; the padding stays zero).  The parameters without gradient in the reference (the two unused decoders and ``dt``,
     SURVEY.md Appendix C) stay outside."""
 
     def __init__(self, model):
         live = [(n, p) for n, p in model.named_parameters()
                 if not n.startswith(("fpc_decoder", "rpc_decoder")) and n != "dt"]
         self.names = [n for n, _ in live]
-        n_total = sum(p.numel() for _, p in live)
+        pad = lambda n: (n + 63) // 64 * 64          # 256-byte aligned views (the TF32 GEMMs need 16-byte rows)  # noqa: E731
+        n_total = sum(pad(p.numel()) for _, p in live)
         dev = live[0][1].device
-        self.params = torch.empty(n_total, device=dev, dtype=torch.float32)
+        self.params = torch.zeros(n_total, device=dev, dtype=torch.float32)
         self.grads = torch.zeros(n_total, device=dev, dtype=torch.float32)
         self.exp_avg = torch.zeros(n_total, device=dev, dtype=torch.float32)
         self.exp_avg_sq = torch.zeros(n_total, device=dev, dtype=torch.float32)
@@ -97,7 +130,7 @@ class _Flat:
                 self.params[off:off + n].copy_(p.reshape(-1))
                 p.data = self.params[off:off + n].view_as(p)
                 self.grad_of[id(p)] = self.grads[off:off + n].view_as(p)
-                off += n
+                off += pad(n)
         self.n = n_total
 
     def g(self, p):
@@ -113,7 +146,13 @@ class Trainer:
     ``loss_sum``, ``use_emd3``; ``use_emd2`` / ``use_cd2`` add terms that have no gradient w.r.t. the weights (they
     are functions of FPS-selected input points, model5_b.py:937-942) and are not evaluated here."""
 
-    def __init__(self, model, config=None, lr: Optional[float] = None):
+    def __init__(self, model, config=None, lr: Optional[float] = None, precision: str = "fp32"):
+        """``precision``: "fp32" (FFMA pipe, matches the reference's CPU arithmetic to ~1e-6) or "tf32" (every large
+        Linear of forward and backward on the tcgen05 tensor cores in TF32 -- the arithmetic stock PyTorch 1.10
+        uses for nn.Linear on Ampere-or-newer GPUs; gradients agree with fp32 to ~1e-2 relative)."""
+        if precision not in ("fp32", "tf32"):
+            raise ValueError("precision must be 'fp32' or 'tf32'")
+        self.precision = precision
         self.model = model
         c = config if config is not None else model.C
         self.loss_mode = int(getattr(c, "loss_mode", 0))
@@ -134,6 +173,31 @@ class Trainer:
             t = torch.empty(*shape, device=self.dev, dtype=dtype)
             self._buf[name] = t
         return t
+
+    def _padded_weight(self, name, lin, kpad):
+        """lin.weight [N, K] as a zero-padded [N, kpad] copy refreshed every step (the weight itself when kpad == K)"""
+        N, K = lin.weight.shape
+        if kpad == K:
+            return lin.weight
+        w = self._buf.get(name)
+        if w is None:
+            w = torch.zeros(N, kpad, device=self.dev, dtype=torch.float32)
+            self._buf[name] = w
+        axpby(N, K, 1.0, lin.weight, K, 0.0, None, 0, w, kpad)
+        return w
+
+    def _padded_grad(self, name, lin, kpad):
+        N, K = lin.weight.shape
+        if kpad == K:
+            return self.flat.g(lin.weight)
+        g = self.buf(name, N, kpad)
+        g.zero_()
+        return g
+
+    def _unpad_grad(self, g, lin, kpad):
+        N, K = lin.weight.shape
+        if kpad != K:
+            axpby(N, K, 1.0, g, kpad, 0.0, None, 0, self.flat.g(lin.weight), K)
 
     # -------------------------------------------------------------------------------------------- encoder
     def _encoder_forward(self, tag, enc, xyz, start1, start2):
@@ -158,9 +222,14 @@ class Trainer:
         _lib.call("pz_fps", _p(xyz), B, NPTS, _p(start1), S1, _p(c.fps1), _p(c.x1), _st())
         _lib.call("pz_knn", _p(c.x1), _p(xyz), B, S1, NPTS, KNN, _p(c.knn1), None, _st())
         R1 = B * S1 * KNN
-        c.g1, c.a1, c.a2 = b("g1", R1, 67), b("a1", R1, 128), b("a2", R1, 128)
-        _lib.call("pz_group_concat", _p(xyz), _p(c.xf), _p(c.x1), _p(c.knn1), B, NPTS, 64, S1, KNN, _p(c.g1), None, _st())
-        linear_fwd(c.g1, 67, R1, enc.mlp3, c.a1, 128, relu=True)
+        # tf32: the grouped rows (3+64 / 3+128 wide) are zero-padded to 128 / 256 columns so that layer 1 and its
+        # weight gradient can run on the tensor cores (K % 32 == 0, wgrad N % 128 == 0)
+        c.kp1, c.kp2 = (128, 256) if self.precision == "tf32" else (67, 131)
+        c.w3p, c.w5p = self._padded_weight(tag + ".w3p", enc.mlp3, c.kp1), self._padded_weight(tag + ".w5p", enc.mlp5, c.kp2)
+        c.g1, c.a1, c.a2 = b("g1", R1, c.kp1), b("a1", R1, 128), b("a2", R1, 128)
+        _lib.call("pz_group_concat_padded", _p(xyz), _p(c.xf), _p(c.x1), _p(c.knn1), B, NPTS, 64, S1, KNN, c.kp1,
+                  _p(c.g1), None, _st())
+        linear_fwd(c.g1, c.kp1, R1, enc.mlp3, c.a1, 128, relu=True, W=c.w3p, K=c.kp1)
         linear_fwd(c.a1, 128, R1, enc.mlp4, c.a2, 128, relu=True)
         c.f1f, c.arg1 = b("f1f", B * S1, 128), b("arg1", B * S1, 128, dtype=torch.int32)
         _lib.call("pz_maxpool_forward", _p(c.a2), B * S1, KNN, 128, _p(c.f1f), _p(c.arg1), _st())
@@ -170,9 +239,10 @@ class Trainer:
         _lib.call("pz_fps", _p(c.x1), B, S1, _p(start2), S2, _p(c.fps2), _p(c.x2), _st())
         _lib.call("pz_knn", _p(c.x2), _p(c.x1), B, S2, S1, KNN, _p(c.knn2), None, _st())
         R2 = B * S2 * KNN
-        c.g2, c.b1, c.b2 = b("g2", R2, 131), b("b1", R2, 256), b("b2", R2, 256)
-        _lib.call("pz_group_concat", _p(c.x1), _p(c.f1f), _p(c.x2), _p(c.knn2), B, S1, 128, S2, KNN, _p(c.g2), None, _st())
-        linear_fwd(c.g2, 131, R2, enc.mlp5, c.b1, 256, relu=True)
+        c.g2, c.b1, c.b2 = b("g2", R2, c.kp2), b("b1", R2, 256), b("b2", R2, 256)
+        _lib.call("pz_group_concat_padded", _p(c.x1), _p(c.f1f), _p(c.x2), _p(c.knn2), B, S1, 128, S2, KNN, c.kp2,
+                  _p(c.g2), None, _st())
+        linear_fwd(c.g2, c.kp2, R2, enc.mlp5, c.b1, 256, relu=True, W=c.w5p, K=c.kp2)
         linear_fwd(c.b1, 256, R2, enc.mlp6, c.b2, 256, relu=True)
         T = B * S2
         c.cat = b("cat", T, 1280)                   # [att1 | att2 | att3 | att4 | f2f]  (model5_b.py:467, :472)
@@ -242,19 +312,23 @@ class Trainer:
             src = dcat[:, 1024:] if l == 0 else dcat[:, (l - 1) * 256:]
             axpby(T, 256, 1.0, dcur, 256, 1.0, src, 1280, dcur, 256)
         # dcur = d loss / d f2f ;  sg2: max over neighbours <- relu(mlp6(relu(mlp5(g2))))
-        db2, db1, dg2 = b("db2", R2, 256), b("db1", R2, 256), b("dg2", R2, 131)
+        db2, db1, dg2 = b("db2", R2, 256), b("db1", R2, 256), b("dg2", R2, c.kp2)
         _lib.call("pz_maxpool_backward", _p(dcur), _p(c.f2f_c), _p(c.arg2), T, KNN, 256, 1, _p(db2), _st())
         linear_bwd(db2, 256, c.b1, 256, R2, enc.mlp6, G(enc.mlp6.weight), G(enc.mlp6.bias), db1, 256, mask=c.b1, ldmask=256)
-        linear_bwd(db1, 256, c.g2, 131, R2, enc.mlp5, G(enc.mlp5.weight), G(enc.mlp5.bias), dg2, 131)
+        gw5 = self._padded_grad(tag + ".gw5", enc.mlp5, c.kp2)
+        linear_bwd(db1, 256, c.g2, c.kp2, R2, enc.mlp5, gw5, G(enc.mlp5.bias), dg2, c.kp2, W=c.w5p, K=c.kp2)
+        self._unpad_grad(gw5, enc.mlp5, c.kp2)
         df1f = b("df1f", B * S1, 128)
         df1f.zero_()
-        _lib.call("pz_scatter_add_rows", _p(dg2), 131, 3, 128, _p(c.knn2), R2, S2 * KNN, S1, _p(df1f), 128, _st())
+        _lib.call("pz_scatter_add_rows", _p(dg2), c.kp2, 3, 128, _p(c.knn2), R2, S2 * KNN, S1, _p(df1f), 128, _st())
         # sg1
-        da2, da1, dg1 = b("da2", R1, 128), b("da1", R1, 128), b("dg1", R1, 67)
+        da2, da1, dg1 = b("da2", R1, 128), b("da1", R1, 128), b("dg1", R1, c.kp1)
         _lib.call("pz_maxpool_backward", _p(df1f), _p(c.f1f), _p(c.arg1), B * S1, KNN, 128, 1, _p(da2), _st())
         linear_bwd(da2, 128, c.a1, 128, R1, enc.mlp4, G(enc.mlp4.weight), G(enc.mlp4.bias), da1, 128, mask=c.a1, ldmask=128)
-        linear_bwd(da1, 128, c.g1, 67, R1, enc.mlp3, G(enc.mlp3.weight), G(enc.mlp3.bias), dg1, 67)
-        _lib.call("pz_scatter_add_rows", _p(dg1), 67, 3, 64, _p(c.knn1), R1, S1 * KNN, NPTS, _p(dxf), 64, _st())
+        gw3 = self._padded_grad(tag + ".gw3", enc.mlp3, c.kp1)
+        linear_bwd(da1, 128, c.g1, c.kp1, R1, enc.mlp3, gw3, G(enc.mlp3.bias), dg1, c.kp1, W=c.w3p, K=c.kp1)
+        self._unpad_grad(gw3, enc.mlp3, c.kp1)
+        _lib.call("pz_scatter_add_rows", _p(dg1), c.kp1, 3, 64, _p(c.knn1), R1, S1 * KNN, NPTS, _p(dxf), 64, _st())
         # stem
         dh2, dy1, dh1 = b("dh2", R0, 64), b("dy1", R0, 64), b("dh1", R0, 64)
         _lib.call("pz_bn_point_train_backward", _p(c.h2), _p(c.xf), _p(dxf), B, NPTS, 64, _p(enc.bn2.weight), _p(c.bn[2]),
@@ -333,6 +407,8 @@ class Trainer:
         fpc, mrpc = fpc.contiguous().float(), mrpc.contiguous().float()
         _lib.require_cuda(fpc, mrpc)
         B = fpc.shape[0]
+        global _TF32
+        _TF32 = self.precision == "tf32"
         with torch.cuda.device(self.dev):
             fw = self._forward(fpc, mrpc, starts)
             res = []
@@ -355,6 +431,8 @@ class Trainer:
         B = fpc.shape[0]
         G = self.flat.g
         self.flat.grads.zero_()
+        global _TF32
+        _TF32 = self.precision == "tf32"
         with torch.cuda.device(self.dev):
             fw = self._forward(fpc, mrpc, starts)
             ef, em, f, tf_l, tf_a, out6 = fw["ef"], fw["em"], fw["f"], fw["tf_l"], fw["tf_a"], fw["out6"]

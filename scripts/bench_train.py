@@ -42,6 +42,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--lr", type=float, default=1e-5)
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32"])
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -57,7 +58,7 @@ def main():
     model = TouchedRegraster(types.SimpleNamespace(dataset="vase", loss_mode=1, loss_sum=False, lr=a.lr))
     model.load_state_dict(synthetic_state_dict(0))
     model.to(dev)
-    tr = Trainer(model)
+    tr = Trainer(model, precision=a.precision)
     batch = make_training_batch(a.pairs, 64 + rank, dev)
     losses = []
     for _ in range(a.warmup):
@@ -95,7 +96,7 @@ def main():
         gflop = 3 * 7.347 * a.pairs
         print(json.dumps({"metric": "pairs/sec PuzzleNet training step (config 4)", "value": a.pairs * world / t * 1e3,
                           "unit": "pairs/s", "n_gpus": world, "pairs_per_gpu": a.pairs, "ms_per_step": t,
-                          "steps": a.steps, "warmup": a.warmup, "dtype": "f32", "scaling": "weak",
+                          "steps": a.steps, "warmup": a.warmup, "dtype": "f32" if a.precision == "fp32" else "tf32 tensor-core GEMMs, fp32 storage/accumulate", "scaling": "weak",
                           "achieved_tflops_per_gpu": gflop / t, "gpu_launches_per_step": launches / a.steps,
                           "grad_elems_allreduced": tr.flat.n, "phases": ph,
                           "loss_first_last": [losses[0], losses[-1]], "peak_mem_gb": torch.cuda.max_memory_allocated() / 2**30}))

@@ -188,3 +188,73 @@ def test_predict5_training_mode_and_model_training_step():
     assert np.abs(r[6].cpu().numpy() - ref).max() / np.abs(ref).max() < 1e-4
     out = model.training_step([t.to(DEV) for t in batch], 0, starts=st)
     assert np.isfinite(float(out["loss"])) and "loss_emd" in out["terms"]
+
+
+def _tf32_round(x):
+    """round-to-nearest-even to a 10-bit mantissa (what the MMA does to its operands, up to the rounding mode)"""
+    i = x.contiguous().view(torch.int32)
+    i = (i + 0x0FFF + ((i >> 13) & 1)) & ~0x1FFF
+    return i.view(torch.float32)
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 1), (1, 0)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (384, 256, 96), (256, 128, 4096)])
+def test_gemm_tf32_layouts(a_mn, b_mn, M, N, K):
+    """every operand-major combination of the tcgen05 TF32 GEMM vs a float64 product of the fp32 inputs: the error
+    must be explained by operand rounding to 10 mantissa bits (|err| <= 2^-10 * sum |a||b|), and far from the O(1)
+    error a wrong shared-memory layout / descriptor would give"""
+    from puzzlenet_b200 import _lib
+    g = torch.Generator().manual_seed(M + N + K + a_mn * 2 + b_mn)
+    A = torch.randn(M, K, generator=g)
+    B = torch.randn(N, K, generator=g)
+    ref = A.double() @ B.double().T
+    bound = (A.abs().double() @ B.abs().double().T) * 2.0 ** -10
+    Ad = (A.T.contiguous() if a_mn else A).to(DEV)
+    Bd = (B.T.contiguous() if b_mn else B).to(DEV)
+    C = torch.full((M, N), 7.0, device=DEV)
+    _lib.call("pz_gemm_tf32", a_mn, b_mn, M, N, K, Ad.data_ptr(), Ad.shape[1], Bd.data_ptr(), Bd.shape[1], C.data_ptr(), N,
+              1, None, 0, None, 0, 0, torch.cuda.current_stream().cuda_stream)
+    err = (C.cpu().double() - ref).abs()
+    assert (err <= bound + 1e-6).all(), (err.max().item(), bound.max().item())
+    # exact agreement with a product of pre-rounded operands, up to fp32 accumulation order
+    ref_t = _tf32_round(A).double() @ _tf32_round(B).double().T
+    assert (C.cpu().double() - ref_t).abs().max() <= 2e-3 * ref_t.abs().max()
+    # split-K (atomics into zeros) and the epilogue options
+    C2 = torch.zeros(M, N, device=DEV)
+    _lib.call("pz_gemm_tf32", a_mn, b_mn, M, N, K, Ad.data_ptr(), Ad.shape[1], Bd.data_ptr(), Bd.shape[1], C2.data_ptr(), N,
+              5, None, 0, None, 0, 0, torch.cuda.current_stream().cuda_stream)
+    assert (C2 - C).abs().max().item() <= 1e-3 * C.abs().max().item()
+    bias, mask = torch.randn(N, generator=g).to(DEV), torch.randn(M, N, generator=g).to(DEV)
+    C3 = torch.ones(M, N, device=DEV)
+    _lib.call("pz_gemm_tf32", a_mn, b_mn, M, N, K, Ad.data_ptr(), Ad.shape[1], Bd.data_ptr(), Bd.shape[1], C3.data_ptr(), N,
+              1, bias.data_ptr(), 1, mask.data_ptr(), N, 1, torch.cuda.current_stream().cuda_stream)
+    want = torch.where(mask > 0, torch.relu(C + bias + 1.0), torch.zeros((), device=DEV))
+    assert (C3 - want).abs().max().item() <= 1e-5 * want.abs().max().item() + 1e-5
+
+
+def test_tf32_training_step_close_to_fp32():
+    """precision='tf32' (tensor-core GEMMs for every large Linear, forward and backward; B=8 so that the row counts
+    reach the tensor-core path): loss terms within 3e-2 and every large gradient tensor within 3e-2 relative L2 of
+    the fp32 path on the same batch -- the operand rounding of TF32 (2^-11 relative) through ~20 layers."""
+    from puzzlenet_b200.training import Trainer
+    batch = [t.to(DEV) for t in training_inputs(8, po.se3_exp)]
+    st = _starts(8)
+    res = {}
+    for prec in ("fp32", "tf32"):
+        model = _fresh_model()
+        tr = Trainer(model, precision=prec)
+        n0 = __import__("puzzlenet_b200")._lib.load().pz_launch_count()
+        terms = tr.forward_backward(batch, starts=st)
+        torch.cuda.synchronize()
+        res[prec] = (terms, {n: tr.flat.g(p).clone() for n, p in model.named_parameters() if id(p) in tr.flat.grad_of})
+    t32, ttf = res["fp32"][0], res["tf32"][0]
+    for k in ("loss", "loss_re", "loss_emd", "ce_f", "ce_m"):
+        np.testing.assert_allclose(ttf[k], t32[k], rtol=3e-2, err_msg=k)
+    worst = {}
+    for n, g32 in res["fp32"][1].items():
+        if n.endswith("mlpk.bias") or g32.numel() < 4096:
+            continue
+        worst[n] = ((res["tf32"][1][n] - g32).norm() / g32.norm().clamp_min(1e-20)).item()
+    bad = {k: v for k, v in worst.items() if not v < 3e-2}
+    assert not bad, bad
+    assert max(worst.values()) > 1e-6          # the tensor-core path really ran (fp32 vs fp32 would be bit-equal)
