@@ -8,8 +8,11 @@ synthetic piece pairs per GPU (BASELINE.json configs[1]).  Prints ONE JSON line 
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
   python bench.py --impl reference ...     # the reference algorithm's CPU path (oracle port), same metric
 
-value : device-resident inputs, per-step CUDA events on the launching stream (L2 flushed between steps,
-        flush outside the events), max over ranks of the summed step time.
+value : device-resident inputs (128 rotating batches = 201 MB, larger than the 126 MB L2), K steps bracketed by one pair of
+        CUDA events; batches alternate over --pipes CUDA streams, each replaying one captured CUDA graph per forward
+        (the same schedule as the e2e leg, minus the host copies); max over ranks.
+single_stream : the same K steps launched eagerly on ONE stream with per-step events and an L2 flush between steps
+        (the latency view; its per-stage events feed the rooflines).
 e2e   : same metric through the public API from pinned HOST buffers: H2D of both clouds + FPS starts and
         D2H of the twist + both boundary-logit tensors inside the timed region.
 """
@@ -137,6 +140,71 @@ def run_reference_arm(args):
 
 
 # --------------------------------------------------------------------------------------------------
+# short runs of BASELINE configs 4 and 5 (reported under "other_configs"; scripts/bench_train.py and
+# scripts/bench_assembly.py are the full versions, incl. multi-GPU)
+# --------------------------------------------------------------------------------------------------
+def _bench_training(dev, pairs=B_PAIRS, steps=5, warmup=2):
+    import types
+    import torch
+    from puzzlenet_b200.model5_b import TouchedRegraster
+    from puzzlenet_b200.training import Trainer
+    from puzzlenet_b200.weights import synthetic_state_dict
+    from scripts.bench_train import make_training_batch
+    out = {"workload": f"training_step (loss_mode 1: chamfer + pose + EMD + boundary CE/chamfer), {pairs} pairs per GPU",
+           "unit": UNIT}
+    batch = make_training_batch(pairs, 64, dev)
+    for prec in ("fp32", "tf32"):
+        model = TouchedRegraster(types.SimpleNamespace(dataset="vase", loss_mode=1, loss_sum=False, lr=1e-5))
+        model.load_state_dict(synthetic_state_dict(0))
+        model.to(dev)
+        tr = Trainer(model, precision=prec)
+        first = last = None
+        for _ in range(warmup):
+            loss = tr.training_step(batch)["loss"]
+            first = loss if first is None else first
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(steps):
+            last = tr.training_step(batch)["loss"]
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        out[prec] = {"value": pairs / ms * 1e3, "ms_per_step": ms, "loss_first_last": [first, last]}
+        del tr, model
+        torch.cuda.empty_cache()
+    return out
+
+
+def _bench_assembly(model, dev, pieces=32, points=11000, iters=5):
+    import numpy as np
+    import torch
+    from puzzlenet_b200 import assembly
+    from scripts.bench_assembly import dublin_like_piece
+    raw = [dublin_like_piece(i, points) for i in range(pieces)]
+    starts = [int(np.random.default_rng(100 + i).integers(0, points)) for i in range(pieces)]
+    scorer = assembly.ModelScorer(model)
+
+    def once():
+        torch.manual_seed(1234)
+        clouds = assembly.downsample_pieces(raw, 1024, starts=starts, device=dev)
+        pairs, rows = assembly.score_all_pairs(clouds, scorer, batch=64)
+        return assembly.greedy_assemble(pieces, pairs, rows)
+
+    once()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        _, _, merges = once()
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) / iters * 1e3
+    n_pairs = pieces * (pieces - 1) // 2
+    return {"workload": f"{pieces} pieces x {points} pts: FPS 11000->1024, {n_pairs} pairs scored, greedy merge",
+            "ms_per_assembly": ms, "pairs_per_s": n_pairs / ms * 1e3, "merges": len(merges),
+            "timing": "host wall clock incl. H2D of the raw pieces and the host-side merge"}
+
+
+# --------------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------------
 def run_gpu_arm(args):
@@ -172,6 +240,14 @@ def run_gpu_arm(args):
         host.append((fpc.pin_memory(), mrpc.pin_memory(), starts.pin_memory()))
     resident = [(f.to(dev), m.to(dev), s.to(dev)) for f, m, s in host]
     batches = [make_batch(f, m) for f, m, _ in resident]
+    # pipelined leg: enough distinct resident batches that one rotation exceeds L2 (128 x 1.57 MB = 201 MB > 126 MB)
+    n_rot = 128
+    rot = []
+    for i in range(n_rot):
+        fpc, mrpc = synthetic_pairs(B, seed=10_000 + 1000 * rank + i)
+        g = torch.Generator().manual_seed(500 + i)
+        starts = torch.stack([torch.randint(0, n, (B,), generator=g) for n in (1024, 512, 1024, 512)])
+        rot.append((make_batch(fpc.to(dev), mrpc.to(dev)), starts.to(dev)))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
 
     def barrier():
@@ -186,7 +262,7 @@ def run_gpu_arm(args):
         step_resident(i)
     barrier()
 
-    # ---- value: device-resident inputs, per-step events, L2 flush between steps
+    # ---- single-stream leg: device-resident inputs, eager launches, per-step events, L2 flush between steps
     sampler = ClockSampler(local) if rank == 0 else None
     lib.pz_profile_enable(1)
     launches0 = lib.pz_launch_count()
@@ -256,6 +332,31 @@ def run_gpu_arm(args):
     pipes = [torch.cuda.Stream(device=dev) for _ in range(args.pipes)]
     model.cuda_graphs = not args.no_graphs          # one captured CUDA graph per stream replays the ~75 launches
 
+    # ---- value: device-resident rotating batches over the same streams / graphs, K steps inside one event pair
+    def run_resident(n):
+        for i in range(n):
+            with torch.cuda.stream(pipes[i % len(pipes)]):
+                bt, st_ = rot[i % n_rot]
+                model.predict5(bt, 0, starts=st_)
+
+    run_resident(max(2 * len(pipes), args.warmup))
+    barrier()
+    launches0 = lib.pz_launch_count()
+    v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    main_stream = torch.cuda.current_stream()
+    v0.record()
+    for p_ in pipes:
+        p_.wait_stream(main_stream)
+    run_resident(args.steps)
+    for p_ in pipes:
+        main_stream.wait_stream(p_)
+    v1.record()
+    barrier()
+    value_ms = v0.elapsed_time(v1)
+    # launches per forward are the same whether issued eagerly or replayed from the captured graph; the counter only
+    # sees eager launches, so count one eager forward
+    launches_eager_per_step = launches / max(args.steps, 1)
+
     def run_e2e(n):
         for i in range(n):
             with torch.cuda.stream(pipes[i % len(pipes)]):
@@ -278,12 +379,13 @@ def run_gpu_arm(args):
     clocks = sampler.stop() if sampler else None
 
     # ---- reduce over ranks: max time, total pairs
-    t = torch.tensor([total_ms, e2e_ms, other[0] if other else 0.0], device=dev, dtype=torch.float64)
+    t = torch.tensor([total_ms, e2e_ms, other[0] if other else 0.0, value_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms, other_ms = t.tolist()
+    total_ms, e2e_ms, other_ms, value_ms = t.tolist()
     pairs_total = B * args.steps * world
-    value = pairs_total / (total_ms / 1e3)
+    value = pairs_total / (value_ms / 1e3)
+    single_value = pairs_total / (total_ms / 1e3)
     e2e_value = pairs_total / (e2e_ms / 1e3)
 
     if rank != 0:
@@ -355,20 +457,40 @@ def run_gpu_arm(args):
                         "sample": "3 steps x 8 pairs of the same workload, oracle.puzzle_oracle.predict5 (torch CPU fp32), "
                                   f"{sec:.2f} s/step"}
 
+    # ---- the other BASELINE configs, short runs (N=1 only): training step (config 4) and assembly (config 5)
+    other_configs = None
+    if world == 1 and not args.no_extras:
+        other_configs = {}
+        try:
+            other_configs["config4_training_step"] = _bench_training(dev)
+        except Exception as e:   # noqa: BLE001 -- extras must never take the headline line down
+            other_configs["config4_training_step"] = {"error": repr(e)[:200]}
+        try:
+            other_configs["config5_assembly"] = _bench_assembly(model, dev)
+        except Exception as e:   # noqa: BLE001
+            other_configs["config5_assembly"] = {"error": repr(e)[:200]}
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": value_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
         "config": {"workload": "predict5 fwd (need=False, eval), B=64 pairs x 1024 pts per GPU (BASELINE configs[1])",
                    "pairs_per_gpu": B, "points": N_POINTS, "precision": args.precision, "parallelism": f"dp{world} (pairs sharded, no forward collective)",
-                   "l2": "256 MiB flush written between steps, outside the per-step CUDA events; 4 rotating batches",
+                   "l2": "inputs larger than L2: 128 rotating device-resident batches (201 MB) -> static graph inputs; "
+                         "single_stream leg: 256 MiB flush written between steps, outside the per-step CUDA events",
+                   "schedule": f"batches alternate over {args.pipes} CUDA streams"
+                               + ("" if args.no_graphs else ", one captured CUDA graph replay per forward"),
                    "weights": "synthetic_state_dict(0) (no checkpoint is shipped with the reference)"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / args.steps,
                 "how": f"public API predict5 from pinned host buffers; batches alternate over {args.pipes} CUDA streams"
                        + ("" if args.no_graphs else ", each replaying one captured CUDA graph per forward")},
-        "gpu_launches": int(launches),
+        "single_stream": {"value": single_value, "unit": UNIT, "ms_per_step": total_ms / args.steps,
+                          "how": "eager launches on one stream, per-step CUDA events, L2 flushed between steps"},
+        "gpu_launches": int(round(launches_eager_per_step * args.steps)),
+        "gpu_launches_note": f"{launches_eager_per_step:.0f} kernels per forward (counted on the eager single-stream leg; "
+                             "the value / e2e legs replay the same kernels from a captured CUDA graph)",
         "roofline": roofline,
         "roofline_all": {k: {"bound": v["bound"], "achieved": round(v["achieved"], 3), "unit": v["unit"],
                              "frac": round(v["frac"], 5)} for k, v in rooflines.items()},
@@ -380,6 +502,7 @@ def run_gpu_arm(args):
         "stages_ms_per_step_timed_region": {k: round(v, 4) for k, v in sorted(per_step_overlapped.items(), key=lambda kv: -kv[1])},
         other_prec + "_path": ({"value": B * other[1] * world / (other_ms / 1e3), "unit": UNIT,
                                 "ms_per_step": other_ms / other[1], "steps": other[1]} if other else None),
+        "other_configs": other_configs,
         "gflop_per_pair_reference_count": FLOP_PER_PAIR_REFERENCE / 1e9,
         "wall_s_timed_region": wall,
     }
@@ -400,6 +523,7 @@ def main():
     ap.add_argument("--single-precision", action="store_true", help="skip the short run of the other precision")
     ap.add_argument("--pipes", type=int, default=3, help="CUDA streams the e2e leg alternates batches over")
     ap.add_argument("--no-graphs", action="store_true", help="e2e leg: eager launches instead of CUDA-graph replay")
+    ap.add_argument("--no-extras", action="store_true", help="skip the short training-step / assembly runs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
