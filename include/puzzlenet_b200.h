@@ -40,7 +40,7 @@ typedef void* pz_stream_t; /* cudaStream_t */
 #define PZ_PREC_FP32 0 /* fp32 CUDA-core math, matches the reference to ~1e-6 rel */
 #define PZ_PREC_BF16 1 /* bf16 operands, fp32 accumulate on tcgen05 tensor cores */
 
-#define PZ_ABI_VERSION 4
+#define PZ_ABI_VERSION 5
 
 /* pz_predict5 flags */
 #define PZ_FLAG_NEED 1          /* also return x2 / attention of both clouds (predict5 need=True) */
@@ -317,9 +317,10 @@ int pz_group_sum(const float* x, long long ld, long long G, int K, int C, float*
 int pz_bn_point_train_forward(const float* x, int B, int P, int C, const float* gamma, const float* beta,
                               float* running_mean_or_null, float* running_var_or_null, float momentum, float eps,
                               int relu, float* y, float* save_mean, float* save_invstd, pz_stream_t stream);
+/* accumulate != 0: dgamma / dbeta are added to (a module applied twice per step, predict6). */
 int pz_bn_point_train_backward(const float* x, const float* y, const float* dy, int B, int P, int C,
                                const float* gamma, const float* save_mean, const float* save_invstd, int relu,
-                               float* dx, float* dgamma, float* dbeta, pz_stream_t stream);
+                               int accumulate, float* dx, float* dgamma, float* dbeta, pz_stream_t stream);
 /* torch.max(x, dim=-2) of x [G,K,C] with the arg-max (model5_b.py:454, :461, :474, :741) and its backward;
  * relu_gate != 0 additionally applies the ReLU gate of the layer that produced x (dx is then the gradient of
  * that layer's pre-activation). */

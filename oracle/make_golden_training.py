@@ -51,6 +51,27 @@ def main():
     for name, b in model.named_buffers():
         if "running" in name:
             out["buf/" + name] = b.detach().numpy()[:16].copy()
+    # ---- the pretraining branch (current_epoch < pretrain_epochs -> predict6, pose losses only)
+    model2 = m5.TouchedRegraster(ref_shim.reference_config())
+    model2.load_state_dict(synthetic_state_dict(0), strict=True)
+    model2.device = torch.device("cpu")
+    model2.C.pretrain_epochs = 700
+    model2.current_epoch = 0
+    model2.vis = lambda *a, **k: None
+    model2.vis_attention = lambda *a, **k: None
+    model2.logger = ref_shim._Anything()
+    model2.scheduler = _Sched()
+    model2.train()
+    torch.manual_seed(FPS_SEED)
+    loss2 = model2.training_step(batch, 0)["loss"]
+    loss2.backward()
+    out["pre/loss"] = loss2.detach().numpy()
+    for name, p in model2.named_parameters():
+        if p.grad is not None:
+            out["pre/grad/" + name] = train_oracle.grad_digest(p.grad)
+    for name, b in model2.named_buffers():
+        if "running" in name:
+            out["pre/buf/" + name] = b.detach().numpy()[:16].copy()
     np.savez_compressed(GOLDEN, **out)
     print("wrote", GOLDEN, f"{os.path.getsize(GOLDEN) / 1024:.0f} KiB;", len(out), "arrays; loss", float(loss))
 

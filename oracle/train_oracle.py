@@ -55,12 +55,16 @@ def earth_mover_distance(xyz1, xyz2, transpose=True):
 
 def training_loss(sd: Mapping[str, Tensor], batch, starts=None, loss_mode: int = 1, loss_sum: bool = False,
                   use_emd2: bool = False, use_cd2: bool = False, use_emd3: bool = False,
-                  bn_state: Dict[str, Tensor] = None) -> Dict[str, Tensor]:
-    """model5_b.py:912-1155 with ``pretrain=False``: returns every logged term and the total ``loss``.
+                  bn_state: Dict[str, Tensor] = None, pretrain: bool = False) -> Dict[str, Tensor]:
+    """model5_b.py:912-1155: returns every logged term and the total ``loss``.  ``pretrain`` selects the predict6
+    branch (:928-931: both clouds through ``Encoder``, the step returns after the pose losses, :1048-1050).
     ``sd`` tensors may require grad; ``bn_state`` (optional dict) receives the updated running statistics."""
     fpc, mrpc, igt, rpc, fpcb, rpcb, fpc_idx, rpc_idx = batch[:8]
-    o = po.predict5(sd, fpc, mrpc, need=True, starts=starts, train_bn=True, bn_state=bn_state)
-    out, de_fpcb, de_mrpcb = o["out"], o["de_fpcb"], o["de_mrpcb"]
+    if pretrain:
+        o = predict6_train(sd, fpc, mrpc, starts, bn_state)
+    else:
+        o = po.predict5(sd, fpc, mrpc, need=True, starts=starts, train_bn=True, bn_state=bn_state)
+    out, de_fpcb, de_mrpcb = o["out"], o.get("de_fpcb"), o.get("de_mrpcb")
     x2, attention = o["enc_fpc"]["x2"], o["enc_fpc"]["attention"]
     mrpc_x2, mrpc_attention = o["enc_mrpc"]["x2"], o["enc_mrpc"]["attention"]
     att1, att2 = attention.mean(dim=1), mrpc_attention.mean(dim=1)
@@ -83,6 +87,9 @@ def training_loss(sd: Mapping[str, Tensor], batch, starts=None, loss_mode: int =
         loss = loss + emd2
     if use_cd2:
         loss = loss + loss_cd2
+    if pretrain:
+        return dict(loss=loss, loss_re=loss_re, loss_g=loss_g, loss_emd=loss_emd, loss_cd2=loss_cd2, emd2=emd2,
+                    out=out, de_mrpc=de_mrpc, mat=mat, fwd=o)
     ce_f = F.cross_entropy(de_fpcb, fpc_idx.squeeze().long().reshape(de_fpcb.shape[0], -1))
     ce_m = F.cross_entropy(de_mrpcb, rpc_idx.squeeze().long().reshape(de_mrpcb.shape[0], -1))
     loss = loss + ce_f + ce_m
@@ -104,6 +111,19 @@ def training_loss(sd: Mapping[str, Tensor], batch, starts=None, loss_mode: int =
                 ce_f=ce_f, ce_m=ce_m, loss_fpcb=loss_fpcb, loss_mrpcb=loss_mrpcb, emd_fpcb=emd_fpcb,
                 emd_mrpcb=emd_mrpcb, out=out, de_fpcb=de_fpcb, de_mrpcb=de_mrpcb, de_mrpc=de_mrpc, mat=mat,
                 idx_f=idx_f, idx_m=idx_m, fwd=o)
+
+
+def predict6_train(sd, fpc, mrpc, starts=None, bn_state=None):
+    """predict6(training=True, need=True, pretrain=True), model5_b.py:612-658: ``Encoder`` on both clouds (two
+    train-mode passes: its BatchNorm running statistics are updated twice), pose head only."""
+    st1, st2 = (None, None) if starts is None else starts
+    e1 = po.encoder_forward(sd, "Encoder", fpc, st1, True, bn_state)
+    sd2 = dict(sd)
+    if bn_state:       # the second pass starts from the running statistics the first one left behind
+        sd2.update({k: v for k, v in bn_state.items() if k.startswith("Encoder.")})
+    e2 = po.encoder_forward(sd2, "Encoder", mrpc, st2, True, bn_state)
+    out6 = po._seq(sd, "tfMLP", torch.cat([e1["f_global"], e2["f_global"]], dim=-1), (0, 2, 4, 6, 8))
+    return dict(out=out6, enc_fpc=e1, enc_mrpc=e2)
 
 
 def grad_digest(g: Tensor) -> np.ndarray:

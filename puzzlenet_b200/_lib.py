@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libpuzzlenet_sm100.so")
 
 PZ_PREC_FP32 = 0
 PZ_PREC_BF16 = 1
-ABI_VERSION = 4
+ABI_VERSION = 5
 PZ_SCORE_COLS = 12
 PZ_FLAG_NEED = 1
 PZ_FLAG_REUSE_PACKS = 2
@@ -97,7 +97,7 @@ SIGNATURES = {
     "pz_bn_point_train_forward": (C.c_int, [c_f32p, C.c_int, C.c_int, C.c_int, c_f32p, c_f32p, c_f32p, c_f32p,
                                             C.c_float, C.c_float, C.c_int, c_f32p, c_f32p, c_f32p, c_stream]),
     "pz_bn_point_train_backward": (C.c_int, [c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, c_f32p, c_f32p, c_f32p,
-                                             C.c_int, c_f32p, c_f32p, c_f32p, c_stream]),
+                                             C.c_int, C.c_int, c_f32p, c_f32p, c_f32p, c_stream]),
     "pz_maxpool_forward": (C.c_int, [c_f32p, C.c_longlong, C.c_int, C.c_int, c_f32p, C.c_void_p, c_stream]),
     "pz_maxpool_backward": (C.c_int, [c_f32p, c_f32p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, c_f32p,
                                       c_stream]),

@@ -279,8 +279,8 @@ __global__ void __launch_bounds__(256) bn_point_bwd_kernel(const float* __restri
                                                            const float* __restrict__ gamma,
                                                            const float* __restrict__ save_mean,
                                                            const float* __restrict__ save_invstd, int relu,
-                                                           float* __restrict__ dx, float* __restrict__ dgamma,
-                                                           float* __restrict__ dbeta) {
+                                                           int accumulate, float* __restrict__ dx,
+                                                           float* __restrict__ dgamma, float* __restrict__ dbeta) {
   __shared__ float red[9];
   const int p = blockIdx.x;
   const int cnt = B * C;
@@ -304,8 +304,8 @@ __global__ void __launch_bounds__(256) bn_point_bwd_kernel(const float* __restri
     dx[off] = g * invstd * (d - db * inv_cnt - xh * dg * inv_cnt);
   }
   if (threadIdx.x == 0) {
-    dgamma[p] = dg;
-    dbeta[p] = db;
+    dgamma[p] = accumulate ? dgamma[p] + dg : dg;
+    dbeta[p] = accumulate ? dbeta[p] + db : db;
   }
 }
 
@@ -649,12 +649,13 @@ extern "C" int pz_bn_point_train_forward(const float* x, int B, int P, int C, co
 
 extern "C" int pz_bn_point_train_backward(const float* x, const float* y, const float* dy, int B, int P, int C,
                                           const float* gamma, const float* save_mean, const float* save_invstd,
-                                          int relu, float* dx, float* dgamma, float* dbeta, pz_stream_t stream) {
+                                          int relu, int accumulate, float* dx, float* dgamma, float* dbeta,
+                                          pz_stream_t stream) {
   PZ_REQUIRE(x && y && dy && gamma && save_mean && save_invstd && dx && dgamma && dbeta, PZ_ERR_ARG,
              "pz_bn_point_train_backward: null pointer");
   PZ_REQUIRE(B >= 1 && P >= 1 && C >= 1, PZ_ERR_ARG, "pz_bn_point_train_backward: bad size");
-  bn_point_bwd_kernel<<<P, 256, 0, as_stream(stream)>>>(x, y, dy, B, P, C, gamma, save_mean, save_invstd, relu, dx,
-                                                        dgamma, dbeta);
+  bn_point_bwd_kernel<<<P, 256, 0, as_stream(stream)>>>(x, y, dy, B, P, C, gamma, save_mean, save_invstd, relu,
+                                                        accumulate, dx, dgamma, dbeta);
   PZ_LAUNCH_CHECK();
   return PZ_OK;
 }

@@ -20,8 +20,8 @@ Deviations from the reference, all documented in DESIGN.md:
   broken ``predict4``).
 * Training has no autograd graph: ``training_step`` runs forward, losses, the hand-written backward, the
   gradient all-reduce and Adam itself (``puzzlenet_b200/training.py``; Lightning: manual optimization).
-  ``predict5(training=True)`` is the train-mode forward only; the ``predict6`` pretraining branch is
-  inference-only.
+  ``predict5(training=True)`` is the train-mode forward only; the ``predict6`` pretraining branch trains through
+  ``training_step(pretrain=True)`` (or ``current_epoch < C.pretrain_epochs`` under Lightning).
 * The class derives from ``nn.Module`` when ``pytorch_lightning`` is not installed.
 """
 from __future__ import annotations
@@ -423,14 +423,15 @@ class TouchedRegraster(_Base):
             self._trainer_state = Trainer(self, self.C)
         return self._trainer_state
 
-    def training_step(self, batch, batch_indic, starts=None):
+    def training_step(self, batch, batch_indic, starts=None, pretrain=None):
         """model5_b.py:912-1155 (non-pretrain branch) + the optimizer step of :1453-1457.  The reference returns a
         loss for autograd; there is no autograd graph here -- forward, losses, the hand-written backward, the
         gradient all-reduce and Adam all happen inside this call (Lightning: manual optimization).  Returns
         ``{'loss': 0-d tensor, 'terms': dict of the logged scalars}``."""
-        if getattr(self.C, "pretrain_epochs", 0) and getattr(self, "current_epoch", 1 << 30) < self.C.pretrain_epochs:
-            raise NotImplementedError("the predict6 pretraining branch (model5_b.py:928-931) has no backward here")
-        terms = self.trainer_state().training_step(batch, starts)
+        if pretrain is None:      # model5_b.py:928: pretrain = self.current_epoch < self.C.pretrain_epochs
+            epoch = getattr(self, "current_epoch", None)
+            pretrain = epoch is not None and epoch < getattr(self.C, "pretrain_epochs", 0)
+        terms = self.trainer_state().training_step(batch, starts, pretrain=bool(pretrain))
         if hasattr(self, "log"):
             try:
                 for k, v in terms.items():

@@ -196,8 +196,9 @@ class Trainer:
 
     def _unpad_grad(self, g, lin, kpad):
         N, K = lin.weight.shape
-        if kpad != K:
-            axpby(N, K, 1.0, g, kpad, 0.0, None, 0, self.flat.g(lin.weight), K)
+        if kpad != K:       # added (not copied): a shared encoder back-propagates twice per step
+            gw = self.flat.g(lin.weight)
+            axpby(N, K, 1.0, g, kpad, 1.0, gw, K, gw, K)
 
     # -------------------------------------------------------------------------------------------- encoder
     def _encoder_forward(self, tag, enc, xyz, start1, start2):
@@ -272,7 +273,7 @@ class Trainer:
         _lib.call("pz_maxpool_forward", _p(c.out), B, S2, 1024, _p(c.fg), _p(c.argo), _st())
         return c
 
-    def _encoder_backward(self, c, dfg, dxf):
+    def _encoder_backward(self, c, dfg, dxf, accumulate=False):
         """dfg [B,1024] = d loss / d f_global; dxf [B*1024,64] = d loss / d x_feature from the boundary heads
         (accumulated into, then consumed).  Writes every parameter gradient of the encoder."""
         enc, B, tag, G = c.enc, c.B, c.tag, self.flat.g
@@ -332,10 +333,10 @@ class Trainer:
         # stem
         dh2, dy1, dh1 = b("dh2", R0, 64), b("dy1", R0, 64), b("dh1", R0, 64)
         _lib.call("pz_bn_point_train_backward", _p(c.h2), _p(c.xf), _p(dxf), B, NPTS, 64, _p(enc.bn2.weight), _p(c.bn[2]),
-                  _p(c.bn[3]), 1, _p(dh2), _p(G(enc.bn2.weight)), _p(G(enc.bn2.bias)), _st())
+                  _p(c.bn[3]), 1, int(accumulate), _p(dh2), _p(G(enc.bn2.weight)), _p(G(enc.bn2.bias)), _st())
         linear_bwd(dh2, 64, c.y1, 64, R0, enc.mlp2, G(enc.mlp2.weight), G(enc.mlp2.bias), dy1, 64)
         _lib.call("pz_bn_point_train_backward", _p(c.h1), _p(c.y1), _p(dy1), B, NPTS, 64, _p(enc.bn1.weight), _p(c.bn[0]),
-                  _p(c.bn[1]), 1, _p(dh1), _p(G(enc.bn1.weight)), _p(G(enc.bn1.bias)), _st())
+                  _p(c.bn[1]), 1, int(accumulate), _p(dh1), _p(G(enc.bn1.weight)), _p(G(enc.bn1.bias)), _st())
         linear_bwd(dh1, 64, c.xyz, 3, R0, enc.mlp1, G(enc.mlp1.weight), G(enc.mlp1.bias))
 
     # -------------------------------------------------------------------------------------------- MLP stacks
@@ -366,7 +367,7 @@ class Trainer:
                 linear_bwd(dy, lin.weight.shape[0], xin, ldin, M, lin, G(lin.weight), G(lin.bias), dx, lddx)
 
     # -------------------------------------------------------------------------------------------- the step
-    def _forward(self, fpc, mrpc, starts):
+    def _forward(self, fpc, mrpc, starts, pretrain=False):
         """train-mode predict5 (model5_b.py:672-759 with training=True): both encoders, the pose head and the two
         boundary heads; returns every buffer the backward pass reads.  Must run inside ``torch.cuda.device``."""
         m = self.model
@@ -378,13 +379,15 @@ class Trainer:
                                   torch.randint(0, 512, (B,), dtype=torch.long)])
         starts = starts.to(self.dev, torch.int64).contiguous()
         ef = self._encoder_forward("E1", m.Encoder, fpc, starts[0], starts[1])
-        em = self._encoder_forward("E2", m.Encoder2, mrpc, starts[2], starts[3])
+        em = self._encoder_forward("E2", m.Encoder if pretrain else m.Encoder2, mrpc, starts[2], starts[3])
         R0 = B * NPTS
         # ---- pose head: tfMLP(cat(f_global_fpc, f_global_mrpc))  (model5_b.py:723-725)
         f = self.buf("f", B, 2048)
         axpby(B, 1024, 1.0, ef.fg, 1024, 0.0, None, 0, f, 2048)
         axpby(B, 1024, 1.0, em.fg, 1024, 0.0, None, 0, f[:, 1024:], 2048)
         tf_l, tf_a = self._mlp_forward("tf", m.tfMLP, f, 2048, B)
+        if pretrain:           # predict6 (model5_b.py:647-658): shared encoder, pose head only
+            return dict(ef=ef, em=em, f=f, tf_l=tf_l, tf_a=tf_a, out6=tf_a[-1])
         # ---- boundary heads (model5_b.py:729-754; both "global" vectors come from the mrpc branch, D6)
         lf_l, lf_a = self._mlp_forward("lf", m.MLPLocalPreFpc, ef.xf, 64, R0)
         lm_l, lm_a = self._mlp_forward("lm", m.MLPLocalPreRpc, em.xf, 64, R0)
@@ -423,6 +426,71 @@ class Trainer:
         de_m = fw["logit_m"].view(B, NPTS, 2).permute(0, 2, 1).contiguous()
         return fw["out6"].clone(), [0], res[0], res[1], res[2], res[3], de_f, de_m
 
+    def _pose_losses(self, out6, mrpc, rpc, igt, B):
+        """The pose part of training_step (model5_b.py:947-1029): mat = se3.exp(out), de_mrpc = mat . mrpc,
+        chamfer(rpc, de_mrpc), comp(mat, igt), EMD(de_mrpc, rpc) -> loss sums in ``vals[0..3]`` and d loss / d out6
+        for the configured ``loss_mode``."""
+        vals = self.buf("loss_terms", 16)
+        vals.zero_()
+        mat = self.buf("mat", B, 4, 4)
+        _lib.call("pz_se3_exp", _p(out6), B, _p(mat), _st())
+        de_mrpc = losses.transform_points(mat, mrpc)
+        red = 1.0 if self.loss_sum else 1.0 / (B * NPTS)
+        d1, d2, a1, a2 = losses._chamfer_raw(rpc, de_mrpc, True)           # d1 per de_mrpc point, d2 per rpc point
+        total(d1, vals, 0)
+        total(d2, vals, 1)
+        _lib.call("pz_comp", _p(mat), _p(igt), B, vals.data_ptr() + 4 * 2, _st())
+        from . import emd_cuda
+        match = emd_cuda.approxmatch_forward(de_mrpc, rpc)
+        cost = emd_cuda.matchcost_forward(de_mrpc, rpc, match)
+        total(cost, vals, 3)
+        w_re = {0: 1, 1: 1, 2: 0, 3: 0, 4: 1, 5: 0, 6: 1}[self.loss_mode]
+        w_g = {0: 1, 1: 1, 2: 0, 3: 1, 4: 0, 5: 1, 6: 0}[self.loss_mode]
+        w_emd = {0: 0, 1: 1, 2: 1, 3: 1, 4: 1, 5: 0, 6: 0}[self.loss_mode]
+        emd_red = 1.0 if self.loss_sum else 1.0 / B
+        dde = self.buf("dde", B, NPTS, 3)
+        gw1 = torch.full((B, NPTS), red * w_re, device=self.dev)
+        gx, gy = self.buf("ch_gx", B, NPTS, 3), self.buf("ch_gy", B, NPTS, 3)
+        _lib.call("pz_chamfer_grad", _p(rpc), _p(de_mrpc), B, NPTS, NPTS, _p(a1), _p(a2), _p(gw1), _p(gw1), _p(gx),
+                  _p(gy), _st())
+        gc = torch.full((B,), emd_red * w_emd, device=self.dev)
+        g1, _ = emd_cuda.matchcost_backward(gc, de_mrpc, rpc, match)
+        axpby(B * NPTS, 3, 1.0, gy, 3, 1.0, g1, 3, dde, 3)
+        dout6 = self.buf("dout6", B, 6)
+        _lib.call("pz_pose_grad", _p(out6), _p(mrpc), _p(dde), NPTS, _p(igt), float(w_g), B, 0.0, _p(dout6), _st())
+        return vals, mat, de_mrpc, dout6, (w_re, w_g, w_emd)
+
+    def forward_backward_pretrain(self, batch, starts=None) -> Dict[str, float]:
+        """The pretraining branch of training_step (model5_b.py:928-931, :1048-1050: ``current_epoch <
+        pretrain_epochs``): predict6 -- BOTH clouds through ``Encoder`` -- and the pose losses only.  ``Encoder``
+        back-propagates twice, its gradients add; ``Encoder2`` and the boundary heads get none."""
+        fpc, mrpc, igt, rpc = [t.contiguous().float() for t in batch[:4]]
+        _lib.require_cuda(fpc, mrpc, igt, rpc)
+        B = fpc.shape[0]
+        self.flat.grads.zero_()
+        global _TF32
+        _TF32 = self.precision == "tf32"
+        with torch.cuda.device(self.dev):
+            fw = self._forward(fpc, mrpc, starts, pretrain=True)
+            out6 = fw["out6"]
+            vals, mat, de_mrpc, dout6, (w_re, w_g, w_emd) = self._pose_losses(out6, mrpc, rpc, igt, B)
+            df = self.buf("df", B, 2048)
+            self._mlp_backward("tf", fw["tf_l"], fw["tf_a"], fw["f"], 2048, B, dout6, df, 2048)
+            dfg_f, dfg_m = self.buf("dfg_f", B, 1024), self.buf("dfg_m", B, 1024)
+            axpby(B, 1024, 1.0, df, 2048, 0.0, None, 0, dfg_f, 1024)
+            axpby(B, 1024, 1.0, df[:, 1024:], 2048, 0.0, None, 0, dfg_m, 1024)
+            dxf = self.buf("dxf_f", B * NPTS, 64)
+            dxf.zero_()
+            self._encoder_backward(fw["ef"], dfg_f, dxf, accumulate=False)
+            dxf.zero_()
+            self._encoder_backward(fw["em"], dfg_m, dxf, accumulate=True)
+            v = vals.cpu().tolist()
+        self.last = dict(out=out6, de_mrpc=de_mrpc, mat=mat)
+        n_re = 1.0 if self.loss_sum else B * NPTS
+        terms = dict(loss_re=(v[0] + v[1]) / n_re, loss_g=v[2], loss_emd=v[3] * (1.0 if self.loss_sum else 1.0 / B))
+        terms["loss"] = w_re * terms["loss_re"] + w_g * terms["loss_g"] + w_emd * terms["loss_emd"]
+        return terms
+
     def forward_backward(self, batch, starts=None) -> Dict[str, float]:
         """Train-mode predict5 + losses + backward into ``self.flat.grads`` (zeroed first).  ``starts`` [4,B] as in
         ``predict5``.  Returns the logged terms as python floats (one device->host copy)."""
@@ -441,34 +509,8 @@ class Trainer:
             logit_f, logit_m = fw["logit_f"], fw["logit_m"]
             R0 = B * NPTS
             # ---- losses
-            vals = self.buf("loss_terms", 16)
-            vals.zero_()
-            mat = self.buf("mat", B, 4, 4)
-            _lib.call("pz_se3_exp", _p(out6), B, _p(mat), _st())
-            de_mrpc = losses.transform_points(mat, mrpc)
-            red = 1.0 if self.loss_sum else 1.0 / (B * NPTS)
-            d1, d2, a1, a2 = losses._chamfer_raw(rpc, de_mrpc, True)           # d1 per de_mrpc point, d2 per rpc point
-            total(d1, vals, 0)
-            total(d2, vals, 1)
-            _lib.call("pz_comp", _p(mat), _p(igt), B, vals.data_ptr() + 4 * 2, _st())
+            vals, mat, de_mrpc, dout6, (w_re, w_g, w_emd) = self._pose_losses(out6, mrpc, rpc, igt, B)
             from . import emd_cuda
-            match = emd_cuda.approxmatch_forward(de_mrpc, rpc)
-            cost = emd_cuda.matchcost_forward(de_mrpc, rpc, match)
-            total(cost, vals, 3)
-            w_re = {0: 1, 1: 1, 2: 0, 3: 0, 4: 1, 5: 0, 6: 1}[self.loss_mode]
-            w_g = {0: 1, 1: 1, 2: 0, 3: 1, 4: 0, 5: 1, 6: 0}[self.loss_mode]
-            w_emd = {0: 0, 1: 1, 2: 1, 3: 1, 4: 1, 5: 0, 6: 0}[self.loss_mode]
-            emd_red = 1.0 if self.loss_sum else 1.0 / B
-            dde = self.buf("dde", B, NPTS, 3)
-            gw1 = torch.full((B, NPTS), red * w_re, device=self.dev)
-            gx, gy = self.buf("ch_gx", B, NPTS, 3), self.buf("ch_gy", B, NPTS, 3)
-            _lib.call("pz_chamfer_grad", _p(rpc), _p(de_mrpc), B, NPTS, NPTS, _p(a1), _p(a2), _p(gw1), _p(gw1), _p(gx),
-                      _p(gy), _st())
-            gc = torch.full((B,), emd_red * w_emd, device=self.dev)
-            g1, _ = emd_cuda.matchcost_backward(gc, de_mrpc, rpc, match)
-            axpby(B * NPTS, 3, 1.0, gy, 3, 1.0, g1, 3, dde, 3)
-            dout6 = self.buf("dout6", B, 6)
-            _lib.call("pz_pose_grad", _p(out6), _p(mrpc), _p(dde), NPTS, _p(igt), float(w_g), B, 0.0, _p(dout6), _st())
             # cross entropy of both boundary heads
             dlf, dlm = self.buf("dlf", R0, 2), self.buf("dlm", R0, 2)
             _lib.call("pz_cross_entropy", _p(logit_f), _p(fpc_idx), B, NPTS, 1, 1.0, vals.data_ptr() + 4 * 4, _p(dlf), _st())
@@ -559,8 +601,8 @@ class Trainer:
             getattr(self.model, attr, {}).clear()
         return lr
 
-    def training_step(self, batch, starts=None) -> Dict[str, float]:
-        terms = self.forward_backward(batch, starts)
+    def training_step(self, batch, starts=None, pretrain: bool = False) -> Dict[str, float]:
+        terms = self.forward_backward_pretrain(batch, starts) if pretrain else self.forward_backward(batch, starts)
         world = self.all_reduce_grads()
         terms["lr"] = self.optimizer_step(world)
         return terms
