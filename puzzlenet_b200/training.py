@@ -123,10 +123,15 @@ class _Flat:
         self.exp_avg = torch.zeros(n_total, device=dev, dtype=torch.float32)
         self.exp_avg_sq = torch.zeros(n_total, device=dev, dtype=torch.float32)
         self.grad_of: Dict[int, torch.Tensor] = {}
+        self.segments: Dict[str, list] = {}          # gradient buckets: "Encoder", "Encoder2", "heads" -> [lo, hi)
         off = 0
         with torch.no_grad():
-            for _, p in live:
+            for name, p in live:
                 n = p.numel()
+                seg = name.split(".")[0] if name.startswith(("Encoder.", "Encoder2.")) else "heads"
+                lo_hi = self.segments.setdefault(seg, [off, off])
+                assert lo_hi[1] == off, "parameters of one bucket must be contiguous in named_parameters() order"
+                lo_hi[1] = off + pad(n)
                 self.params[off:off + n].copy_(p.reshape(-1))
                 p.data = self.params[off:off + n].view_as(p)
                 self.grad_of[id(p)] = self.grads[off:off + n].view_as(p)
@@ -139,6 +144,14 @@ class _Flat:
 
 class _EncoderCtx:
     pass
+
+
+def all_reduce_bucket(flat: torch.Tensor, lo: int, hi: int, async_op: bool = True):
+    """Sum ``flat[lo:hi]`` over the ranks of the default process group (NCCL on GPUs, gloo in the CPU tests).
+    Returns the work handle (``None`` outside a process group)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1 or hi <= lo:
+        return None
+    return dist.all_reduce(flat[lo:hi], op=dist.ReduceOp.SUM, async_op=async_op)
 
 
 class Trainer:
@@ -163,6 +176,8 @@ class Trainer:
         self.lr0 = float(lr if lr is not None else getattr(c, "lr", 0.9e-3))
         self.flat = _Flat(model)
         self.step_count = 0
+        self.overlap_allreduce = True        # bucketed all-reduce started from inside backward (no-op for world size 1)
+        self._pending, self._reduced = [], set()
         self.dev = self.flat.params.device
         self._buf: Dict[str, torch.Tensor] = {}
 
@@ -564,9 +579,12 @@ class Trainer:
             dxf_f, dxf_m = self.buf("dxf_f", R0, 64), self.buf("dxf_m", R0, 64)
             self._mlp_backward("lf", lf_l, lf_a, ef.xf, 64, R0, dloc_f, dxf_f, 64)
             self._mlp_backward("lm", lm_l, lm_a, em.xf, 64, R0, dloc_m, dxf_m, 64)
+            self._bucket_ready("heads")
             # ---- backward: encoders
             self._encoder_backward(ef, dfg_f, dxf_f)
+            self._bucket_ready("Encoder")
             self._encoder_backward(em, dfg_m, dxf_m)
+            self._bucket_ready("Encoder2")
             v = vals.cpu().tolist()
         self.last = dict(out=out6, de_fpcb=de_f, de_mrpcb=de_m, de_mrpc=de_mrpc, mat=mat, idx_f=idx_f, idx_m=idx_m)
         n_re = 1.0 if self.loss_sum else B * NPTS
@@ -580,12 +598,33 @@ class Trainer:
         terms["loss"] = loss
         return terms
 
+    def _bucket_ready(self, name):
+        """Called by the backward pass as soon as a gradient bucket is final: start its all-reduce so that it
+        overlaps the rest of backward (heads -> Encoder -> Encoder2)."""
+        if self.overlap_allreduce:
+            lo, hi = self.flat.segments[name]
+            w = all_reduce_bucket(self.flat.grads, lo, hi)
+            if w is not None:
+                self._pending.append(w)
+                self._reduced.add(name)
+
     def all_reduce_grads(self):
-        """The one collective of the training step: sum the flat gradient buffer over ranks (NCCL on GPUs)."""
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(self.flat.grads, op=dist.ReduceOp.SUM)
-            return dist.get_world_size()
-        return 1
+        """Finish the gradient all-reduce: wait for the buckets started during backward and reduce the ones that
+        were not (all of them when ``overlap_allreduce`` is off).  Returns the world size."""
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return 1
+        rest = [n for n in self.flat.segments if n not in self._reduced]
+        if len(rest) == len(self.flat.segments):
+            dist.all_reduce(self.flat.grads, op=dist.ReduceOp.SUM)          # one collective for the whole buffer
+        else:
+            for n in rest:
+                lo, hi = self.flat.segments[n]
+                self._pending.append(all_reduce_bucket(self.flat.grads, lo, hi))
+        for w in self._pending:
+            if w is not None:
+                w.wait()
+        self._pending, self._reduced = [], set()
+        return dist.get_world_size()
 
     def optimizer_step(self, world: int = 1):
         """Adam(lr) with StepLR(step_size=50, gamma=0.999) stepped per iteration (model5_b.py:1453-1457)."""

@@ -58,3 +58,35 @@ def test_run_sharded_world2_gloo(n_items):
         assert torch.equal(out[:, 0], ids) and torch.equal(out[:, 1], ids * 2 + 1)
         lo, hi = sharding.shard_bounds(n_items, 0, 2)
         assert (out[lo:hi, 2] == 0).all() and (out[hi:, 2] == 1).all()     # rows came from the right rank
+
+
+def _bucket_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from puzzlenet_b200.training import all_reduce_bucket
+        flat = torch.arange(1000, dtype=torch.float32) * (rank + 1)
+        works = [all_reduce_bucket(flat, lo, hi) for lo, hi in ((0, 320), (320, 704), (704, 1000), (10, 10))]
+        assert works[-1] is None                                   # empty bucket: nothing to do
+        for w in works:
+            if w is not None:
+                w.wait()
+        q.put((rank, flat.tolist()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gradient_buckets_all_reduce_world2_gloo():
+    """the training step's bucketed gradient all-reduce (heads / Encoder / Encoder2 segments of the flat buffer)"""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 27500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_bucket_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = (torch.arange(1000, dtype=torch.float32) * 3).tolist()
+    assert res[0] == want and res[1] == want

@@ -95,3 +95,28 @@ def test_signatures_match_reference():
     p5 = inspect.signature(TouchedRegraster.predict5).parameters
     assert list(p5)[:5] == ["self", "batch", "batch_indic", "need", "training"]
     assert p5["need"].default is False and p5["training"].default is False
+
+
+def test_flat_parameter_buffer_and_gradient_buckets():
+    """training._Flat: live parameters become 256-byte aligned views of one buffer; the three all-reduce buckets
+    (Encoder, Encoder2, heads) tile it exactly; the unused decoders and dt stay outside."""
+    from puzzlenet_b200.training import _Flat
+    model = TouchedRegraster(_cfg())
+    before = {n: p.detach().clone() for n, p in model.named_parameters()}
+    flat = _Flat(model)
+    assert set(flat.segments) == {"Encoder", "Encoder2", "heads"}
+    spans = sorted(flat.segments.values())
+    assert spans[0][0] == 0 and spans[-1][1] == flat.n and all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+    live = 0
+    for n, p in model.named_parameters():
+        assert torch.equal(p.detach(), before[n])                       # values survive the re-homing
+        if n.startswith(("fpc_decoder", "rpc_decoder")) or n == "dt":
+            assert id(p) not in flat.grad_of
+            continue
+        live += p.numel()
+        assert flat.g(p).shape == p.shape
+        assert (p.data_ptr() - flat.params.data_ptr()) % 256 == 0        # cudaMalloc bases are 256-byte aligned
+        assert (flat.g(p).data_ptr() - flat.grads.data_ptr()) == (p.data_ptr() - flat.params.data_ptr())
+        lo = (p.data_ptr() - flat.params.data_ptr()) // 4
+        assert 0 <= lo and lo + p.numel() <= flat.n
+    assert live == 7_270_218
