@@ -412,6 +412,8 @@ def run_gpu_arm(args):
         "sg1_gather_layer2_maxpool": (2.0 * clouds * 512 * 32 * 128 * 128, "tensor", 1),
         "sg2_gather_layer2_maxpool": (2.0 * clouds * 256 * 32 * 256 * 256, "tensor", 1),
         "tail_linear_maxpool": (2.0 * clouds * 256 * 1280 * 1024, "tensor", 1),
+        # bf16 path: one fused kernel per layer = q|k|v projections + Q K^T + P V + out-projection (125.8 MFLOP per cloud)
+        "attn_layer_fused": (4 * 2.0 * clouds * 256 * 256 * (384 + 64 + 256 + 256), "tensor", 4),
         "attn_qkv_proj": (4 * 2.0 * clouds * 256 * 256 * 384, "tensor", 4 if args.precision == "bf16" else 12),
         "attn_out_proj": (4 * 2.0 * clouds * 256 * 256 * 256, "tensor", 4),
         "attn_softmax_av": (4 * 2.0 * clouds * 256 * 256 * (64 + 256), "tensor", 4),
@@ -437,15 +439,18 @@ def run_gpu_arm(args):
         return r
 
     # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed ncu --set full
-    # captures of this same command: profiles/r01_top_kernels_bf16.txt, profiles/r01_prof_knn.txt (bf16 path)
+    # captures of this same command: profiles/r01_top_kernels_bf16.txt, profiles/r01_top_kernels_fwd_full.txt,
+    # profiles/r01_prof_knn.txt (bf16 path)
     ncu_traffic = {"sg1_gather_layer2_maxpool": 58.84e6 + 3.92e6, "sg2_gather_layer2_maxpool": 54.84e6 + 3.96e6,
-                   "tail_linear_maxpool": 89.18e6 + 4.42e6, "fps1": 1.62e6, "knn1": 2.38e6,
+                   "tail_linear_maxpool": 89.18e6 + 4.42e6, "fps1": 1.62e6, "knn1": 2.43e6,
+                   "attn_layer_fused": 17.55e6 + 0.07e6,
                    "attn_softmax_av": 41.97e6 + 0.08e6} if args.precision == "bf16" else {}
     rooflines = {k: roof(k) for k in work if per_step.get(k, 0) > 0}
     for k, r in rooflines.items():
         if k in ncu_traffic:
             r["traffic"] = ncu_traffic[k]
-            r["traffic_source"] = "ncu --set full, profiles/r01_top_kernels_bf16.txt (per launch, bytes)"
+            r["traffic_source"] = ("ncu --set full, profiles/r01_top_kernels_fwd_full.txt / r01_top_kernels_bf16.txt "
+                                   "(per launch, bytes)")
     # dominant kernel = the stage with the largest live time among those with a defined roofline
     roofline = rooflines[max(rooflines, key=lambda k: per_step[k])] if rooflines else None
 
