@@ -156,8 +156,8 @@ def all_reduce_bucket(flat: torch.Tensor, lo: int, hi: int, async_op: bool = Tru
 
 class Trainer:
     """``Trainer(model, config)``: ``config`` carries the reference's options (train.py:40-55): ``lr``, ``loss_mode``,
-    ``loss_sum``, ``use_emd3``; ``use_emd2`` / ``use_cd2`` add terms that have no gradient w.r.t. the weights (they
-    are functions of FPS-selected input points, model5_b.py:937-942) and are not evaluated here."""
+    ``loss_sum``, ``use_emd3``, ``use_emd2``, ``use_cd2`` (the last two add terms that are functions of FPS-selected
+    input points only, model5_b.py:937-942: they shift the loss value but carry no weight gradient)."""
 
     def __init__(self, model, config=None, lr: Optional[float] = None, precision: str = "fp32"):
         """``precision``: "fp32" (FFMA pipe, matches the reference's CPU arithmetic to ~1e-6) or "tf32" (every large
@@ -171,8 +171,8 @@ class Trainer:
         self.loss_mode = int(getattr(c, "loss_mode", 0))
         self.loss_sum = bool(getattr(c, "loss_sum", False))
         self.use_emd3 = bool(getattr(c, "use_emd3", False))
-        if getattr(c, "use_emd2", False) or getattr(c, "use_cd2", False):
-            raise NotImplementedError("use_emd2 / use_cd2 only shift the loss value (no weight gradient); not built")
+        self.use_emd2 = bool(getattr(c, "use_emd2", False))
+        self.use_cd2 = bool(getattr(c, "use_cd2", False))
         self.lr0 = float(lr if lr is not None else getattr(c, "lr", 0.9e-3))
         self.flat = _Flat(model)
         self.step_count = 0
@@ -475,6 +475,34 @@ class Trainer:
         _lib.call("pz_pose_grad", _p(out6), _p(mrpc), _p(dde), NPTS, _p(igt), float(w_g), B, 0.0, _p(dout6), _st())
         return vals, mat, de_mrpc, dout6, (w_re, w_g, w_emd)
 
+    def _attention_peak_terms(self, ef, em, B, vals):
+        """model5_b.py:937-942, :1001-1012: ``x2att = x2[:, topk(attention.mean(1), 32)[1][:, 0]]`` -- for every
+        cloud the FPS point that receives the most attention, gathered for ALL batch items (the reference's indexing
+        yields [B,B,3]) -- then chamfer (``loss_cd2``) and EMD (``emd2``) between the two [B,B,3] sets -> vals[12..14].
+        Values only: nothing here depends on the weights differentiably."""
+        from . import emd_cuda, pointnet_util as pu
+        peaks = []
+        for e in (ef, em):
+            att = self.buf(e.tag + ".attmean", B, S2, S2)
+            n = B * S2
+            axpby(n, S2, 0.25, e.A[0], S2, 0.25, e.A[1], S2, att, S2)            # mean of the 4 maps (:468-469)
+            axpby(n, S2, 0.25, e.A[2], S2, 1.0, att, S2, att, S2)
+            axpby(n, S2, 0.25, e.A[3], S2, 1.0, att, S2, att, S2)
+            colmean = self.buf(e.tag + ".attcol", B, S2)
+            _lib.call("pz_group_sum", _p(att), S2, B, S2, S2, _p(colmean), _st())   # sum over the query index (dim 1)
+            _, top = losses.topk(colmean, 32, largest=True)
+            idx = top[:, 0].contiguous().view(1, B).expand(B, B).contiguous()       # the same B indices for every cloud
+            peaks.append(pu.index_points(e.x2, idx))                                # [B, B, 3]
+        c1, c2, _, _ = losses._chamfer_raw(peaks[0], peaks[1], False)
+        total(c1, vals, 12)
+        total(c2, vals, 13)
+        match = emd_cuda.approxmatch_forward(peaks[0], peaks[1])
+        total(emd_cuda.matchcost_forward(peaks[0], peaks[1], match), vals, 14)
+
+    def _peak_term_values(self, v, B):
+        red = 1.0 if self.loss_sum else 1.0 / (B * B)
+        return dict(loss_cd2=(v[12] + v[13]) * red, emd2=v[14])               # emd2 is summed in both modes (:1033-1036)
+
     def forward_backward_pretrain(self, batch, starts=None) -> Dict[str, float]:
         """The pretraining branch of training_step (model5_b.py:928-931, :1048-1050: ``current_epoch <
         pretrain_epochs``): predict6 -- BOTH clouds through ``Encoder`` -- and the pose losses only.  ``Encoder``
@@ -499,11 +527,16 @@ class Trainer:
             self._encoder_backward(fw["ef"], dfg_f, dxf, accumulate=False)
             dxf.zero_()
             self._encoder_backward(fw["em"], dfg_m, dxf, accumulate=True)
+            if self.use_emd2 or self.use_cd2:
+                self._attention_peak_terms(fw["ef"], fw["em"], B, vals)
             v = vals.cpu().tolist()
         self.last = dict(out=out6, de_mrpc=de_mrpc, mat=mat)
         n_re = 1.0 if self.loss_sum else B * NPTS
         terms = dict(loss_re=(v[0] + v[1]) / n_re, loss_g=v[2], loss_emd=v[3] * (1.0 if self.loss_sum else 1.0 / B))
         terms["loss"] = w_re * terms["loss_re"] + w_g * terms["loss_g"] + w_emd * terms["loss_emd"]
+        if self.use_emd2 or self.use_cd2:
+            terms.update(self._peak_term_values(v, B))
+            terms["loss"] += (terms["emd2"] if self.use_emd2 else 0.0) + (terms["loss_cd2"] if self.use_cd2 else 0.0)
         return terms
 
     def forward_backward(self, batch, starts=None) -> Dict[str, float]:
@@ -585,6 +618,8 @@ class Trainer:
             self._bucket_ready("Encoder")
             self._encoder_backward(em, dfg_m, dxf_m)
             self._bucket_ready("Encoder2")
+            if self.use_emd2 or self.use_cd2:
+                self._attention_peak_terms(ef, em, B, vals)
             v = vals.cpu().tolist()
         self.last = dict(out=out6, de_fpcb=de_f, de_mrpcb=de_m, de_mrpc=de_mrpc, mat=mat, idx_f=idx_f, idx_m=idx_m)
         n_re = 1.0 if self.loss_sum else B * NPTS
@@ -595,6 +630,9 @@ class Trainer:
         loss += terms["ce_f"] + terms["ce_m"] + terms["loss_mrpcb"] + terms["loss_fpcb"]
         if self.use_emd3:
             loss += terms["emd_fpcb"] + terms["emd_mrpcb"]
+        if self.use_emd2 or self.use_cd2:
+            terms.update(self._peak_term_values(v, B))
+            loss += (terms["emd2"] if self.use_emd2 else 0.0) + (terms["loss_cd2"] if self.use_cd2 else 0.0)
         terms["loss"] = loss
         return terms
 

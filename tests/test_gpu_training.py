@@ -311,3 +311,25 @@ def test_pretraining_branch_matches_oracle_and_reference():
         np.testing.assert_allclose(mod.running_var.cpu().numpy(), bn_state[name + ".running_var"].numpy(), rtol=1e-4, atol=1e-6)
     out = model.training_step([t.to(DEV) for t in batch], 0, starts=_starts(2), pretrain=True)
     assert np.isfinite(float(out["loss"]))
+
+
+def test_attention_peak_loss_terms_and_loss_modes():
+    """use_emd2 / use_cd2 (model5_b.py:937-942, :1001-1043: value-only terms on the [B,B,3] attention-peak points),
+    use_emd3 and another loss_mode / loss_sum combination vs the oracle."""
+    from puzzlenet_b200.training import Trainer
+    batch = training_inputs(3, po.se3_exp)
+    st = _starts(3)
+    for cfg in (dict(loss_mode=1, loss_sum=False, use_emd2=True, use_cd2=True, use_emd3=True),
+                dict(loss_mode=4, loss_sum=True, use_emd2=False, use_cd2=True, use_emd3=False)):
+        model = _fresh_model()
+        tr = Trainer(model, types.SimpleNamespace(lr=1e-3, **cfg))
+        terms = tr.forward_backward([t.to(DEV) for t in batch], starts=st)
+        sd = {k: (v.clone().requires_grad_() if v.is_floating_point() and "running" not in k else v.clone())
+              for k, v in synthetic_state_dict(0).items()}
+        ref = to.training_loss(sd, batch, starts=((st[0], st[1]), (st[2], st[3])), **cfg)
+        for k in ("loss", "loss_cd2", "emd2", "loss_re", "loss_emd"):
+            np.testing.assert_allclose(terms[k], float(ref[k]), rtol=3e-4, err_msg=f"{k} {cfg}")
+        ref["loss"].backward()
+        for name in ("tfMLP.8.weight", "Encoder2.out.weight", "MLPFpcb.4.weight"):
+            got, want = tr.flat.g(model.get_parameter(name)).cpu(), sd[name].grad
+            assert ((got - want).norm() / want.norm()).item() < 1e-3, (name, cfg)
