@@ -52,3 +52,41 @@ def test_argument_errors_without_gpu():
     assert lib.pz_encoder_workspace_bytes(2, 64) > lib.pz_encoder_workspace_bytes(1, 64)
     with pytest.raises((RuntimeError, ValueError)):
         _lib.call("pz_sqdist", None, None, 1, 1, 1, None, None)
+
+
+def test_argument_errors_of_loss_and_training_entry_points():
+    """error convention of the entry points added for the loss / epilogue / training rows: 0 for empty inputs,
+    PZ_ERR_ARG (-1) for null pointers and bad sizes, PZ_ERR_UNSUPPORTED (-2) for shapes outside the supported range;
+    all decided before the first CUDA call (safe without a GPU)."""
+    lib = _lib.load()
+    one = ctypes.c_void_p(16)            # a non-null, 16-byte aligned dummy: only reached by checks that pass first
+    assert lib.pz_chamfer(None, None, 0, 8, 8, None, None, None, None, None) == 0
+    assert lib.pz_chamfer(None, None, 2, 8, 8, None, None, None, None, None) == -1
+    assert lib.pz_chamfer(one, one, 2, 0, 8, one, one, None, None, None) == -1       # min over an empty set
+    assert b"empty" in lib.pz_last_error()
+    assert lib.pz_comp(one, one, 0, one, None) == -1
+    assert lib.pz_boundary_topk(one, 1, 2048, 128, one, None, None) == -2
+    assert lib.pz_boundary_topk(one, 1, 1024, 2000, one, None, None) == -1
+    assert lib.pz_topk(one, 1, 0, 1, 1, one, None, None) == -2
+    assert lib.pz_topk(None, 0, 10, 1, 1, None, None, None) == 0
+    assert lib.pz_pair_score(None, None, None, None, None, None, None, None, None, None, 0, None, None, None, None,
+                             None, None) == 0
+    assert lib.pz_pair_score(None, None, None, None, None, None, None, None, None, None, 3, None, None, None, None,
+                             None, None) == -1
+    assert lib.pz_se3_transform(None, None, 2, 0, None, None) == 0
+    # pz_sgemm: split-K excludes epilogues and batching
+    assert lib.pz_sgemm(0, 0, 8, 8, 8, 1.0, one, 8, one, 8, 0.0, one, 8, 1, 0, 0, 0, 4, one, 0, None, 0, None, 0, None) == -2
+    assert lib.pz_sgemm(0, 0, 8, 8, 0, 1.0, one, 8, one, 8, 0.0, one, 8, 1, 0, 0, 0, 1, None, 0, None, 0, None, 0, None) == -1
+    assert lib.pz_sgemm(0, 0, 0, 8, 8, 1.0, None, 8, None, 8, 0.0, None, 8, 1, 0, 0, 0, 1, None, 0, None, 0, None, 0, None) == 0
+    # pz_gemm_tf32: shape and alignment contract
+    assert lib.pz_gemm_tf32(0, 0, 100, 128, 32, one, 32, one, 32, one, 128, 1, None, 0, None, 0, 0, None) == -2
+    assert b"M % 128" in lib.pz_last_error()
+    assert lib.pz_gemm_tf32(0, 0, 128, 128, 32, one, 30, one, 32, one, 128, 1, None, 0, None, 0, 0, None) == -1
+    assert lib.pz_gemm_tf32(0, 0, 128, 128, 32, one, 32, one, 32, one, 128, 4, one, 0, None, 0, 0, None) == -2
+    assert lib.pz_bn_point_train_forward(one, 2, 4, 4, one, one, one, None, 0.1, 1e-5, 1, one, one, one, None) == -1
+    assert lib.pz_maxpool_forward(None, 0, 4, 4, None, None, None) == 0
+    assert lib.pz_maxpool_forward(one, 2, 0, 4, one, one, None) == -1
+    assert lib.pz_cross_entropy(one, one, 0, 8, 0, 1.0, one, None, None) == -1
+    assert lib.pz_adam_step(one, one, one, one, 8, 1e-3, 0.9, 0.999, 1e-8, 0, 1.0, None) == -1      # step >= 1
+    assert lib.pz_group_concat_padded(one, one, one, one, 1, 8, 4, 2, 2, 5, one, None, None) == -1  # ld < 3 + D
+    assert lib.pz_pose_grad(one, one, None, 8, None, 0.0, 2, 0.0, one, None) == -1                  # pts without dpts
