@@ -44,9 +44,6 @@ def _splitk(rows: int, out_tiles: int) -> int:
     return max(1, min(want, rows // 256 if rows >= 512 else 1))
 
 
-_TF32 = False     # set by Trainer around a step (module-level so the helpers below stay plain functions)
-
-
 def _al16(*ts):
     return all(t is None or t.data_ptr() % 16 == 0 for t in ts)
 
@@ -57,25 +54,27 @@ def _gemm_tf32(a_mn, b_mn, M, N, K, A, lda, B, ldb, C, ldc, splitk=1, bias=None,
               int(relu), _p(mask), ldmask, int(accumulate), _st())
 
 
-def linear_fwd(x, ldx, M, lin, out, ldo, relu=False, W=None, K=None):
-    """out[M, N] = act(x[M, K] W^T + b).  ``W``/``K`` override the weight with a zero-padded copy (row stride K)."""
+def linear_fwd(x, ldx, M, lin, out, ldo, relu=False, W=None, K=None, tf32=False):
+    """out[M, N] = act(x[M, K] W^T + b).  ``W``/``K`` override the weight with a zero-padded copy (row stride K);
+    ``tf32`` routes shapes the tensor-core kernel supports to ``pz_gemm_tf32``."""
     N, K0 = lin.weight.shape
     W = lin.weight if W is None else W
     K = K0 if K is None else K
-    if _TF32 and M % 128 == 0 and N % 128 == 0 and K % 32 == 0 and ldx % 4 == 0 and ldo % 4 == 0 \
+    if tf32 and M % 128 == 0 and N % 128 == 0 and K % 32 == 0 and ldx % 4 == 0 and ldo % 4 == 0 \
             and _al16(x, W, out, lin.bias):
         _gemm_tf32(0, 0, M, N, K, x, ldx, W, K, out, ldo, bias=lin.bias, relu=relu)
     else:
         gemm(x, W, out, M, N, K, tb=True, lda=ldx, ldb=K, ldc=ldo, bias=lin.bias, relu=relu)
 
 
-def linear_bwd(dy, lddy, x, ldx, M, lin, gw, gb, dx=None, lddx=0, mask=None, ldmask=0, beta=0.0, W=None, K=None):
+def linear_bwd(dy, lddy, x, ldx, M, lin, gw, gb, dx=None, lddx=0, mask=None, ldmask=0, beta=0.0, W=None, K=None,
+               tf32=False):
     """dW += dy^T x, db += colsum(dy); dx = (beta*dx +) dy W, gated by (mask > 0) when given.  ``W``/``K``: as in
     linear_fwd (``gw`` then has row stride K as well)."""
     N, K0 = lin.weight.shape
     W = lin.weight if W is None else W
     K = K0 if K is None else K
-    if _TF32 and N % 128 == 0 and K % 128 == 0 and M % 32 == 0 and M >= 4096 and lddy % 4 == 0 and ldx % 4 == 0 \
+    if tf32 and N % 128 == 0 and K % 128 == 0 and M % 32 == 0 and M >= 4096 and lddy % 4 == 0 and ldx % 4 == 0 \
             and _al16(dy, x, gw):
         tiles = (N // 128) * (K // (256 if K % 256 == 0 else 128))
         kblocks = M // 32
@@ -90,7 +89,7 @@ def linear_bwd(dy, lddy, x, ldx, M, lin, gw, gb, dx=None, lddx=0, mask=None, ldm
             gemm(dy, x, gw, N, K, M, ta=True, lda=lddy, ldb=ldx, ldc=K, beta=1.0)
     _lib.call("pz_colsum", _p(dy), lddy, M, N, 1.0, _p(gb), _st())
     if dx is not None:
-        if _TF32 and M % 128 == 0 and K % 128 == 0 and N % 32 == 0 and lddy % 4 == 0 and lddx % 4 == 0 \
+        if tf32 and M % 128 == 0 and K % 128 == 0 and N % 32 == 0 and lddy % 4 == 0 and lddx % 4 == 0 \
                 and beta in (0.0, 1.0) and _al16(dy, W, dx, mask) and (mask is None or ldmask % 4 == 0):
             _gemm_tf32(0, 1, M, K, N, dy, lddy, W, K, dx, lddx, mask=mask, ldmask=ldmask, accumulate=beta == 1.0)
         else:
@@ -166,6 +165,7 @@ class Trainer:
         if precision not in ("fp32", "tf32"):
             raise ValueError("precision must be 'fp32' or 'tf32'")
         self.precision = precision
+        self.tf32 = precision == "tf32"
         self.model = model
         c = config if config is not None else model.C
         self.loss_mode = int(getattr(c, "loss_mode", 0))
@@ -226,10 +226,10 @@ class Trainer:
         # stem: relu(bn(linear)) x2, BatchNorm1d(1024) over the point index with batch statistics
         c.h1, c.y1, c.h2, c.xf = b("h1", R0, 64), b("y1", R0, 64), b("h2", R0, 64), b("xf", R0, 64)
         c.bn = [b("bn1m", NPTS), b("bn1s", NPTS), b("bn2m", NPTS), b("bn2s", NPTS)]
-        linear_fwd(xyz, 3, R0, enc.mlp1, c.h1, 64)
+        linear_fwd(xyz, 3, R0, enc.mlp1, c.h1, 64, tf32=self.tf32)
         _lib.call("pz_bn_point_train_forward", _p(c.h1), B, NPTS, 64, _p(enc.bn1.weight), _p(enc.bn1.bias),
                   _p(enc.bn1.running_mean), _p(enc.bn1.running_var), 0.1, 1e-5, 1, _p(c.y1), _p(c.bn[0]), _p(c.bn[1]), _st())
-        linear_fwd(c.y1, 64, R0, enc.mlp2, c.h2, 64)
+        linear_fwd(c.y1, 64, R0, enc.mlp2, c.h2, 64, tf32=self.tf32)
         _lib.call("pz_bn_point_train_forward", _p(c.h2), B, NPTS, 64, _p(enc.bn2.weight), _p(enc.bn2.bias),
                   _p(enc.bn2.running_mean), _p(enc.bn2.running_var), 0.1, 1e-5, 1, _p(c.xf), _p(c.bn[2]), _p(c.bn[3]), _st())
         # sample_and_group(512, 0, 32, xyz, x_feature, knn) + mlp3/mlp4 + max over the 32 neighbours
@@ -245,8 +245,8 @@ class Trainer:
         c.g1, c.a1, c.a2 = b("g1", R1, c.kp1), b("a1", R1, 128), b("a2", R1, 128)
         _lib.call("pz_group_concat_padded", _p(xyz), _p(c.xf), _p(c.x1), _p(c.knn1), B, NPTS, 64, S1, KNN, c.kp1,
                   _p(c.g1), None, _st())
-        linear_fwd(c.g1, c.kp1, R1, enc.mlp3, c.a1, 128, relu=True, W=c.w3p, K=c.kp1)
-        linear_fwd(c.a1, 128, R1, enc.mlp4, c.a2, 128, relu=True)
+        linear_fwd(c.g1, c.kp1, R1, enc.mlp3, c.a1, 128, relu=True, W=c.w3p, K=c.kp1, tf32=self.tf32)
+        linear_fwd(c.a1, 128, R1, enc.mlp4, c.a2, 128, relu=True, tf32=self.tf32)
         c.f1f, c.arg1 = b("f1f", B * S1, 128), b("arg1", B * S1, 128, dtype=torch.int32)
         _lib.call("pz_maxpool_forward", _p(c.a2), B * S1, KNN, 128, _p(c.f1f), _p(c.arg1), _st())
         # stage 2 on the 512 centroids
@@ -258,8 +258,8 @@ class Trainer:
         c.g2, c.b1, c.b2 = b("g2", R2, c.kp2), b("b1", R2, 256), b("b2", R2, 256)
         _lib.call("pz_group_concat_padded", _p(c.x1), _p(c.f1f), _p(c.x2), _p(c.knn2), B, S1, 128, S2, KNN, c.kp2,
                   _p(c.g2), None, _st())
-        linear_fwd(c.g2, c.kp2, R2, enc.mlp5, c.b1, 256, relu=True, W=c.w5p, K=c.kp2)
-        linear_fwd(c.b1, 256, R2, enc.mlp6, c.b2, 256, relu=True)
+        linear_fwd(c.g2, c.kp2, R2, enc.mlp5, c.b1, 256, relu=True, W=c.w5p, K=c.kp2, tf32=self.tf32)
+        linear_fwd(c.b1, 256, R2, enc.mlp6, c.b2, 256, relu=True, tf32=self.tf32)
         T = B * S2
         c.cat = b("cat", T, 1280)                   # [att1 | att2 | att3 | att4 | f2f]  (model5_b.py:467, :472)
         c.f2f, c.arg2 = c.cat[:, 1024:], b("arg2", T, 256, dtype=torch.int32)
@@ -273,17 +273,17 @@ class Trainer:
             x = c.cat[:, 1024:] if l == 0 else c.cat[:, (l - 1) * 256:]
             q, k, v = b(f"q{l}", T, 64), b(f"k{l}", T, 64), b(f"v{l}", T, 256)
             A, r, ro, vals = b(f"A{l}", B, S2, S2), b(f"r{l}", T, 256), b(f"ro{l}", T, 256), b("vals", T, 256)
-            linear_fwd(x, 1280, T, att.mlpq, q, 64)
-            linear_fwd(x, 1280, T, att.mlpk, k, 64)
-            linear_fwd(x, 1280, T, att.mlpv, v, 256)
+            linear_fwd(x, 1280, T, att.mlpq, q, 64, tf32=self.tf32)
+            linear_fwd(x, 1280, T, att.mlpk, k, 64, tf32=self.tf32)
+            linear_fwd(x, 1280, T, att.mlpv, v, 256, tf32=self.tf32)
             _lib.call("pz_scaled_dot_attention", _p(q), _p(k), _p(v), B, S2, 64, 256, _p(vals), _p(A), _st())
             axpby(T, 256, 1.0, x, 1280, -1.0, vals, 256, r, 256)                              # r = x - A v
-            linear_fwd(r, 256, T, att.out, ro, 256, relu=True)                                # relu(W_o r + b_o)
+            linear_fwd(r, 256, T, att.out, ro, 256, relu=True, tf32=self.tf32)                                # relu(W_o r + b_o)
             axpby(T, 256, 1.0, x, 1280, 1.0, ro, 256, c.cat[:, l * 256:], 1280)               # x + relu(...)
             for lst, t in zip((c.q, c.k, c.v, c.A, c.r, c.ro), (q, k, v, A, r, ro)):
                 lst.append(t)
         c.out = b("out", T, 1024)
-        linear_fwd(c.cat, 1280, T, enc.out, c.out, 1024)
+        linear_fwd(c.cat, 1280, T, enc.out, c.out, 1024, tf32=self.tf32)
         c.fg, c.argo = b("fg", B, 1024), b("argo", B, 1024, dtype=torch.int32)
         _lib.call("pz_maxpool_forward", _p(c.out), B, S2, 1024, _p(c.fg), _p(c.argo), _st())
         return c
@@ -297,7 +297,7 @@ class Trainer:
         dout = b("dout", T, 1024)
         _lib.call("pz_maxpool_backward", _p(dfg), _p(c.fg), _p(c.argo), B, S2, 1024, 0, _p(dout), _st())
         dcat = b("dcat", T, 1280)
-        linear_bwd(dout, 1024, c.cat, 1280, T, enc.out, G(enc.out.weight), G(enc.out.bias), dcat, 1280)
+        linear_bwd(dout, 1024, c.cat, 1280, T, enc.out, G(enc.out.weight), G(enc.out.bias), dcat, 1280, tf32=self.tf32)
         dcur, dz, dr = b("dcur", T, 256), b("dz", T, 256), b("dr", T, 256)
         dq, dk, dv = b("dq", T, 64), b("dk", T, 64), b("dv", T, 256)
         dA, dS = b("dA", B, S2, S2), b("dS", B, S2, S2)
@@ -309,7 +309,7 @@ class Trainer:
             q, k, v, A, r, ro = c.q[l], c.k[l], c.v[l], c.A[l], c.r[l], c.ro[l]
             # out_l = x + relu(W_o r + b_o)
             _lib.call("pz_relu_gate", T, 256, _p(dcur), 256, _p(ro), 256, _p(dz), 256, _st())
-            linear_bwd(dz, 256, r, 256, T, att.out, G(att.out.weight), G(att.out.bias), dr, 256)
+            linear_bwd(dz, 256, r, 256, T, att.out, G(att.out.weight), G(att.out.bias), dr, 256, tf32=self.tf32)
             # r = x - A v :  dx = dcur + dr ; dvals = -dr
             axpby(T, 256, 1.0, dcur, 256, 1.0, dr, 256, dcur, 256)
             # vals = A v (per cloud):  dv = A^T dvals ; dA = dvals v^T
@@ -321,18 +321,18 @@ class Trainer:
             # S = q k^T :  dq = dS k ; dk = dS^T q
             gemm(dS, k, dq, S2, 64, S2, lda=S2, ldb=64, ldc=64, batch=B, sa=LL, sb=S2 * 64, sc=S2 * 64)
             gemm(dS, q, dk, S2, 64, S2, ta=True, lda=S2, ldb=64, ldc=64, batch=B, sa=LL, sb=S2 * 64, sc=S2 * 64)
-            linear_bwd(dq, 64, x, 1280, T, att.mlpq, G(att.mlpq.weight), G(att.mlpq.bias), dcur, 256, beta=1.0)
-            linear_bwd(dk, 64, x, 1280, T, att.mlpk, G(att.mlpk.weight), G(att.mlpk.bias), dcur, 256, beta=1.0)
-            linear_bwd(dv, 256, x, 1280, T, att.mlpv, G(att.mlpv.weight), G(att.mlpv.bias), dcur, 256, beta=1.0)
+            linear_bwd(dq, 64, x, 1280, T, att.mlpq, G(att.mlpq.weight), G(att.mlpq.bias), dcur, 256, beta=1.0, tf32=self.tf32)
+            linear_bwd(dk, 64, x, 1280, T, att.mlpk, G(att.mlpk.weight), G(att.mlpk.bias), dcur, 256, beta=1.0, tf32=self.tf32)
+            linear_bwd(dv, 256, x, 1280, T, att.mlpv, G(att.mlpv.weight), G(att.mlpv.bias), dcur, 256, beta=1.0, tf32=self.tf32)
             # dcur is now d loss / d x of this layer; x is also a column slice of cat
             src = dcat[:, 1024:] if l == 0 else dcat[:, (l - 1) * 256:]
             axpby(T, 256, 1.0, dcur, 256, 1.0, src, 1280, dcur, 256)
         # dcur = d loss / d f2f ;  sg2: max over neighbours <- relu(mlp6(relu(mlp5(g2))))
         db2, db1, dg2 = b("db2", R2, 256), b("db1", R2, 256), b("dg2", R2, c.kp2)
         _lib.call("pz_maxpool_backward", _p(dcur), _p(c.f2f_c), _p(c.arg2), T, KNN, 256, 1, _p(db2), _st())
-        linear_bwd(db2, 256, c.b1, 256, R2, enc.mlp6, G(enc.mlp6.weight), G(enc.mlp6.bias), db1, 256, mask=c.b1, ldmask=256)
+        linear_bwd(db2, 256, c.b1, 256, R2, enc.mlp6, G(enc.mlp6.weight), G(enc.mlp6.bias), db1, 256, mask=c.b1, ldmask=256, tf32=self.tf32)
         gw5 = self._padded_grad(tag + ".gw5", enc.mlp5, c.kp2)
-        linear_bwd(db1, 256, c.g2, c.kp2, R2, enc.mlp5, gw5, G(enc.mlp5.bias), dg2, c.kp2, W=c.w5p, K=c.kp2)
+        linear_bwd(db1, 256, c.g2, c.kp2, R2, enc.mlp5, gw5, G(enc.mlp5.bias), dg2, c.kp2, W=c.w5p, K=c.kp2, tf32=self.tf32)
         self._unpad_grad(gw5, enc.mlp5, c.kp2)
         df1f = b("df1f", B * S1, 128)
         df1f.zero_()
@@ -340,19 +340,19 @@ class Trainer:
         # sg1
         da2, da1, dg1 = b("da2", R1, 128), b("da1", R1, 128), b("dg1", R1, c.kp1)
         _lib.call("pz_maxpool_backward", _p(df1f), _p(c.f1f), _p(c.arg1), B * S1, KNN, 128, 1, _p(da2), _st())
-        linear_bwd(da2, 128, c.a1, 128, R1, enc.mlp4, G(enc.mlp4.weight), G(enc.mlp4.bias), da1, 128, mask=c.a1, ldmask=128)
+        linear_bwd(da2, 128, c.a1, 128, R1, enc.mlp4, G(enc.mlp4.weight), G(enc.mlp4.bias), da1, 128, mask=c.a1, ldmask=128, tf32=self.tf32)
         gw3 = self._padded_grad(tag + ".gw3", enc.mlp3, c.kp1)
-        linear_bwd(da1, 128, c.g1, c.kp1, R1, enc.mlp3, gw3, G(enc.mlp3.bias), dg1, c.kp1, W=c.w3p, K=c.kp1)
+        linear_bwd(da1, 128, c.g1, c.kp1, R1, enc.mlp3, gw3, G(enc.mlp3.bias), dg1, c.kp1, W=c.w3p, K=c.kp1, tf32=self.tf32)
         self._unpad_grad(gw3, enc.mlp3, c.kp1)
         _lib.call("pz_scatter_add_rows", _p(dg1), c.kp1, 3, 64, _p(c.knn1), R1, S1 * KNN, NPTS, _p(dxf), 64, _st())
         # stem
         dh2, dy1, dh1 = b("dh2", R0, 64), b("dy1", R0, 64), b("dh1", R0, 64)
         _lib.call("pz_bn_point_train_backward", _p(c.h2), _p(c.xf), _p(dxf), B, NPTS, 64, _p(enc.bn2.weight), _p(c.bn[2]),
                   _p(c.bn[3]), 1, int(accumulate), _p(dh2), _p(G(enc.bn2.weight)), _p(G(enc.bn2.bias)), _st())
-        linear_bwd(dh2, 64, c.y1, 64, R0, enc.mlp2, G(enc.mlp2.weight), G(enc.mlp2.bias), dy1, 64)
+        linear_bwd(dh2, 64, c.y1, 64, R0, enc.mlp2, G(enc.mlp2.weight), G(enc.mlp2.bias), dy1, 64, tf32=self.tf32)
         _lib.call("pz_bn_point_train_backward", _p(c.h1), _p(c.y1), _p(dy1), B, NPTS, 64, _p(enc.bn1.weight), _p(c.bn[0]),
                   _p(c.bn[1]), 1, int(accumulate), _p(dh1), _p(G(enc.bn1.weight)), _p(G(enc.bn1.bias)), _st())
-        linear_bwd(dh1, 64, c.xyz, 3, R0, enc.mlp1, G(enc.mlp1.weight), G(enc.mlp1.bias))
+        linear_bwd(dh1, 64, c.xyz, 3, R0, enc.mlp1, G(enc.mlp1.weight), G(enc.mlp1.bias), tf32=self.tf32)
 
     # -------------------------------------------------------------------------------------------- MLP stacks
     def _mlp_forward(self, tag, seq, x, ldx, M):
@@ -362,7 +362,7 @@ class Trainer:
         cur, ld = x, ldx
         for i, lin in enumerate(lins):
             y = self.buf(f"{tag}.y{i}", M, lin.weight.shape[0])
-            linear_fwd(cur, ld, M, lin, y, lin.weight.shape[0], relu=i + 1 < len(lins))
+            linear_fwd(cur, ld, M, lin, y, lin.weight.shape[0], relu=i + 1 < len(lins), tf32=self.tf32)
             acts.append(y)
             cur, ld = y, lin.weight.shape[0]
         return lins, acts
@@ -376,10 +376,10 @@ class Trainer:
             if i > 0:
                 dprev = self.buf(f"{tag}.d{i - 1}", M, ldin)
                 linear_bwd(dy, lin.weight.shape[0], xin, ldin, M, lin, G(lin.weight), G(lin.bias), dprev, ldin,
-                           mask=acts[i - 1], ldmask=ldin)
+                           mask=acts[i - 1], ldmask=ldin, tf32=self.tf32)
                 dy = dprev
             else:
-                linear_bwd(dy, lin.weight.shape[0], xin, ldin, M, lin, G(lin.weight), G(lin.bias), dx, lddx)
+                linear_bwd(dy, lin.weight.shape[0], xin, ldin, M, lin, G(lin.weight), G(lin.bias), dx, lddx, tf32=self.tf32)
 
     # -------------------------------------------------------------------------------------------- the step
     def _forward(self, fpc, mrpc, starts, pretrain=False):
@@ -425,8 +425,6 @@ class Trainer:
         fpc, mrpc = fpc.contiguous().float(), mrpc.contiguous().float()
         _lib.require_cuda(fpc, mrpc)
         B = fpc.shape[0]
-        global _TF32
-        _TF32 = self.precision == "tf32"
         with torch.cuda.device(self.dev):
             fw = self._forward(fpc, mrpc, starts)
             res = []
@@ -511,8 +509,6 @@ class Trainer:
         _lib.require_cuda(fpc, mrpc, igt, rpc)
         B = fpc.shape[0]
         self.flat.grads.zero_()
-        global _TF32
-        _TF32 = self.precision == "tf32"
         with torch.cuda.device(self.dev):
             fw = self._forward(fpc, mrpc, starts, pretrain=True)
             out6 = fw["out6"]
@@ -547,8 +543,6 @@ class Trainer:
         B = fpc.shape[0]
         G = self.flat.g
         self.flat.grads.zero_()
-        global _TF32
-        _TF32 = self.precision == "tf32"
         with torch.cuda.device(self.dev):
             fw = self._forward(fpc, mrpc, starts)
             ef, em, f, tf_l, tf_a, out6 = fw["ef"], fw["em"], fw["f"], fw["tf_l"], fw["tf_a"], fw["out6"]

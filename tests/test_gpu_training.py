@@ -333,3 +333,30 @@ def test_attention_peak_loss_terms_and_loss_modes():
         for name in ("tfMLP.8.weight", "Encoder2.out.weight", "MLPFpcb.4.weight"):
             got, want = tr.flat.g(model.get_parameter(name)).cpu(), sd[name].grad
             assert ((got - want).norm() / want.norm()).item() < 1e-3, (name, cfg)
+
+
+@pytest.mark.parametrize("a_mn,b_mn,N,K", [(0, 0, 128, 128), (0, 1, 256, 256), (1, 0, 128, 64), (0, 1, 128, 256)])
+def test_gemm_tf32_weights_resident_mode(a_mn, b_mn, N, K):
+    """large-M forward / data-gradient shapes take the weights-resident path of pz_gemm_tf32 (B loaded once per CTA);
+    result vs a float64 product within operand-rounding error, and identical to the streaming path (forced by a
+    split-K of 1 on a zeroed output... i.e. by splitk=2 which disables residency) up to accumulation order."""
+    from puzzlenet_b200 import _lib
+    g = torch.Generator().manual_seed(N + K + a_mn + 2 * b_mn)
+    M = 128 * 640
+    A = torch.randn(M, K, generator=g)
+    B = torch.randn(N, K, generator=g)
+    bias = torch.randn(N, generator=g)
+    Ad = (A.T.contiguous() if a_mn else A).to(DEV)
+    Bd = (B.T.contiguous() if b_mn else B).to(DEV)
+    st = torch.cuda.current_stream().cuda_stream
+    C = torch.empty(M, N, device=DEV)
+    _lib.call("pz_gemm_tf32", a_mn, b_mn, M, N, K, Ad.data_ptr(), Ad.shape[1], Bd.data_ptr(), Bd.shape[1], C.data_ptr(), N,
+              1, bias.to(DEV).data_ptr(), 1, None, 0, 0, st)
+    ref = torch.relu(A.double() @ B.double().T + bias.double())
+    bound = (A.abs().double() @ B.abs().double().T) * 2.0 ** -10 + 1e-6
+    assert ((C.cpu().double() - ref).abs() <= bound).all()
+    C2 = torch.zeros(M, N, device=DEV)
+    _lib.call("pz_gemm_tf32", a_mn, b_mn, M, N, K, Ad.data_ptr(), Ad.shape[1], Bd.data_ptr(), Bd.shape[1], C2.data_ptr(), N,
+              2, None, 0, None, 0, 0, st)
+    want = torch.relu(C2 + bias.to(DEV))
+    assert (C - want).abs().max().item() <= 2e-3 * want.abs().max().item()
