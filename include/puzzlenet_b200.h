@@ -304,6 +304,9 @@ int pz_colsum(const float* x, long long ld, long long M, int N, float beta, floa
 /* out[r,c] = a*x[r,c] + b*y[r,c] with row strides (y may be null). */
 int pz_axpby(long long rows, int cols, float a, const float* x, long long ldx, float b, const float* y_or_null,
              long long ldy, float* out, long long ldo, pz_stream_t stream);
+/* x = act(x + bias[c]) in place, strided 2-D: finishes a split-K forward GEMM (the skinny pose-MLP layers, M = 64). */
+int pz_bias_act(long long rows, int cols, float* x, long long ld, const float* bias_or_null, int relu,
+                pz_stream_t stream);
 /* out = mask > 0 ? dy : 0 (ReLU gate on an incoming gradient), strided 2-D. */
 int pz_relu_gate(long long rows, int cols, const float* dy, long long ldy, const float* mask, long long ldm,
                  float* out, long long ldo, pz_stream_t stream);

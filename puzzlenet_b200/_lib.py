@@ -105,6 +105,7 @@ SIGNATURES = {
                                       C.c_int, c_f32p, C.c_longlong, c_stream]),
     "pz_softmax_backward": (C.c_int, [c_f32p, c_f32p, C.c_longlong, C.c_int, C.c_float, c_f32p, c_stream]),
     "pz_cross_entropy": (C.c_int, [c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_float, c_f32p, c_f32p, c_stream]),
+    "pz_bias_act": (C.c_int, [C.c_longlong, C.c_int, c_f32p, C.c_longlong, c_f32p, C.c_int, c_stream]),
     "pz_relu_gate": (C.c_int, [C.c_longlong, C.c_int, c_f32p, C.c_longlong, c_f32p, C.c_longlong, c_f32p, C.c_longlong,
                                c_stream]),
     "pz_broadcast_rows": (C.c_int, [c_f32p, C.c_longlong, C.c_int, C.c_int, c_f32p, C.c_longlong, c_stream]),

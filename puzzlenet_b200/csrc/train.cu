@@ -171,6 +171,17 @@ __global__ void __launch_bounds__(256) axpby_kernel(long long n, float a, const 
   if (i < n) out[i] = a * x[i] + (y ? b * y[i] : 0.f);
 }
 
+// x[r*ld + c] = act(x[r*ld + c] + bias[c])  (finishes a split-K forward GEMM)
+__global__ void __launch_bounds__(256) bias_act_kernel(long long rows, int cols, float* __restrict__ x, long long ld,
+                                                       const float* __restrict__ bias, int relu) {
+  const long long e = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (e >= rows * cols) return;
+  const long long r = e / cols;
+  const int c = (int)(e - r * cols);
+  float v = x[r * ld + c] + (bias ? bias[c] : 0.f);
+  x[r * ld + c] = relu ? fmaxf(v, 0.f) : v;
+}
+
 // strided 2-D variant: out[r*ldo + c] = a*x[r*ldx + c] + b*y[r*ldy + c]
 __global__ void __launch_bounds__(256) axpby2d_kernel(long long rows, int cols, float a, const float* __restrict__ x,
                                                       long long ldx, float b, const float* __restrict__ y, long long ldy,
@@ -597,6 +608,16 @@ extern "C" int pz_axpby(long long rows, int cols, float a, const float* x, long 
   else
     axpby2d_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(rows, cols, a, x, ldx, b, y_or_null, ldy,
                                                                                out, ldo);
+  PZ_LAUNCH_CHECK();
+  return PZ_OK;
+}
+
+extern "C" int pz_bias_act(long long rows, int cols, float* x, long long ld, const float* bias_or_null, int relu,
+                           pz_stream_t stream) {
+  PZ_REQUIRE(rows >= 0 && cols >= 0, PZ_ERR_ARG, "pz_bias_act: negative size");
+  if (rows == 0 || cols == 0) return PZ_OK;
+  PZ_REQUIRE(x, PZ_ERR_ARG, "pz_bias_act: null pointer");
+  bias_act_kernel<<<(unsigned)((rows * cols + 255) / 256), 256, 0, as_stream(stream)>>>(rows, cols, x, ld, bias_or_null, relu);
   PZ_LAUNCH_CHECK();
   return PZ_OK;
 }

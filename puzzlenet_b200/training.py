@@ -63,6 +63,12 @@ def linear_fwd(x, ldx, M, lin, out, ldo, relu=False, W=None, K=None, tf32=False)
     if tf32 and M % 128 == 0 and N % 128 == 0 and K % 32 == 0 and ldx % 4 == 0 and ldo % 4 == 0 \
             and _al16(x, W, out, lin.bias):
         _gemm_tf32(0, 0, M, N, K, x, ldx, W, K, out, ldo, bias=lin.bias, relu=relu)
+    elif M <= 128 and K >= 512 and ldo == N:
+        # skinny layer (the pose MLP: M = batch size): one 128-row tile per 128 columns would leave the GPU idle for a
+        # 2048-deep reduction -> split K over the grid into a zeroed output, then bias + ReLU in place
+        out.zero_()
+        gemm(x, W, out, M, N, K, tb=True, lda=ldx, ldb=K, ldc=ldo, splitk=max(2, min(K // 64, 296 // max(1, (N + 127) // 128))))
+        _lib.call("pz_bias_act", M, N, _p(out), ldo, _p(lin.bias), int(relu), _st())
     else:
         gemm(x, W, out, M, N, K, tb=True, lda=ldx, ldb=K, ldc=ldo, bias=lin.bias, relu=relu)
 
@@ -92,6 +98,11 @@ def linear_bwd(dy, lddy, x, ldx, M, lin, gw, gb, dx=None, lddx=0, mask=None, ldm
         if tf32 and M % 128 == 0 and K % 128 == 0 and N % 32 == 0 and lddy % 4 == 0 and lddx % 4 == 0 \
                 and beta in (0.0, 1.0) and _al16(dy, W, dx, mask) and (mask is None or ldmask % 4 == 0):
             _gemm_tf32(0, 1, M, K, N, dy, lddy, W, K, dx, lddx, mask=mask, ldmask=ldmask, accumulate=beta == 1.0)
+        elif M <= 128 and N >= 256 and beta == 0.0 and lddx == K:
+            dx.zero_()                       # skinny data gradient: split the reduction over the output channels
+            gemm(dy, W, dx, M, K, N, lda=lddy, ldb=K, ldc=lddx, splitk=max(2, min(N // 64, 296 // max(1, (K + 127) // 128))))
+            if mask is not None:
+                _lib.call("pz_relu_gate", M, K, _p(dx), lddx, _p(mask), ldmask, _p(dx), lddx, _st())
         else:
             gemm(dy, W, dx, M, K, N, lda=lddy, ldb=K, ldc=lddx, beta=beta, mask=mask, ldmask=ldmask)
 
