@@ -295,7 +295,7 @@ int pz_sgemm(int transA, int transB, int M, int N, int K, float alpha, const flo
  * Ampere-or-newer GPUs.  C[m,n] = sum_k A(m,k) B(n,k); an operand is K-major (A[m*lda + k], B[n*ldb + k]) or, with
  * *_mn_major != 0, MN-major (A[k*lda + m], B[k*ldb + n]).  Epilogue: + bias[n], + C (accumulate), ReLU, mask gate.
  * splitk > 1: K is split over the persistent grid and partial tiles are atomically ADDED into C (pre-zero it).
- * Supported: M % 128 == 0, N % 128 == 0, K % 32 == 0, 16-byte aligned rows. */
+ * Supported: M % 128 == 0, N % 64 == 0, K % 32 == 0, 16-byte aligned rows. */
 int pz_gemm_tf32(int a_mn_major, int b_mn_major, int M, int N, int K, const float* A, long long lda, const float* B,
                  long long ldb, float* C, long long ldc, int splitk, const float* bias_or_null, int relu,
                  const float* mask_or_null, long long ldmask, int accumulate, pz_stream_t stream);

@@ -334,8 +334,8 @@ extern "C" int pz_gemm_tf32(int a_mn_major, int b_mn_major, int M, int N, int K,
   PZ_REQUIRE(M >= 0 && N >= 0 && K >= 0, PZ_ERR_ARG, "pz_gemm_tf32: negative size");
   if (M == 0 || N == 0) return PZ_OK;
   PZ_REQUIRE(A && B && C, PZ_ERR_ARG, "pz_gemm_tf32: null pointer");
-  PZ_REQUIRE(M % 128 == 0 && N % 128 == 0 && K % 32 == 0 && K >= 32, PZ_ERR_UNSUPPORTED,
-             "pz_gemm_tf32: needs M %% 128 == 0, N %% 128 == 0, K %% 32 == 0 (M=%d N=%d K=%d)", M, N, K);
+  PZ_REQUIRE(M % 128 == 0 && N % 64 == 0 && K % 32 == 0 && K >= 32, PZ_ERR_UNSUPPORTED,
+             "pz_gemm_tf32: needs M %% 128 == 0, N %% 64 == 0, K %% 32 == 0 (M=%d N=%d K=%d)", M, N, K);
   PZ_REQUIRE(lda % 4 == 0 && ldb % 4 == 0 && ldc % 4 == 0 && ((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0 &&
                  ((uintptr_t)C & 15) == 0,
              PZ_ERR_ARG, "pz_gemm_tf32: operands and output need 16-byte aligned rows");
@@ -357,5 +357,6 @@ extern "C" int pz_gemm_tf32(int a_mn_major, int b_mn_major, int M, int N, int K,
     if (K <= 256) return tf32_launch<128, 4, true>(g, as_stream(stream));     // 128 KB + 4 x 16 KB
   }
   if (N % 256 == 0) return tf32_launch<256, 4, false>(g, as_stream(stream));
-  return tf32_launch<128, 4, false>(g, as_stream(stream));
+  if (N % 128 == 0) return tf32_launch<128, 4, false>(g, as_stream(stream));
+  return tf32_launch<64, 6, false>(g, as_stream(stream));                     // the 64-wide layers (q, k, stem, heads)
 }

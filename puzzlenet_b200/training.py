@@ -60,7 +60,7 @@ def linear_fwd(x, ldx, M, lin, out, ldo, relu=False, W=None, K=None, tf32=False)
     N, K0 = lin.weight.shape
     W = lin.weight if W is None else W
     K = K0 if K is None else K
-    if tf32 and M % 128 == 0 and N % 128 == 0 and K % 32 == 0 and ldx % 4 == 0 and ldo % 4 == 0 \
+    if tf32 and M % 128 == 0 and N % 64 == 0 and K % 32 == 0 and ldx % 4 == 0 and ldo % 4 == 0 \
             and _al16(x, W, out, lin.bias):
         _gemm_tf32(0, 0, M, N, K, x, ldx, W, K, out, ldo, bias=lin.bias, relu=relu)
     elif M <= 128 and K >= 512 and ldo == N:
@@ -80,7 +80,7 @@ def linear_bwd(dy, lddy, x, ldx, M, lin, gw, gb, dx=None, lddx=0, mask=None, ldm
     N, K0 = lin.weight.shape
     W = lin.weight if W is None else W
     K = K0 if K is None else K
-    if tf32 and N % 128 == 0 and K % 128 == 0 and M % 32 == 0 and M >= 4096 and lddy % 4 == 0 and ldx % 4 == 0 \
+    if tf32 and N % 128 == 0 and K % 64 == 0 and M % 32 == 0 and M >= 4096 and lddy % 4 == 0 and ldx % 4 == 0 \
             and _al16(dy, x, gw):
         tiles = (N // 128) * (K // (256 if K % 256 == 0 else 128))
         kblocks = M // 32
@@ -95,7 +95,7 @@ def linear_bwd(dy, lddy, x, ldx, M, lin, gw, gb, dx=None, lddx=0, mask=None, ldm
             gemm(dy, x, gw, N, K, M, ta=True, lda=lddy, ldb=ldx, ldc=K, beta=1.0)
     _lib.call("pz_colsum", _p(dy), lddy, M, N, 1.0, _p(gb), _st())
     if dx is not None:
-        if tf32 and M % 128 == 0 and K % 128 == 0 and N % 32 == 0 and lddy % 4 == 0 and lddx % 4 == 0 \
+        if tf32 and M % 128 == 0 and K % 64 == 0 and N % 32 == 0 and lddy % 4 == 0 and lddx % 4 == 0 \
                 and beta in (0.0, 1.0) and _al16(dy, W, dx, mask) and (mask is None or ldmask % 4 == 0):
             _gemm_tf32(0, 1, M, K, N, dy, lddy, W, K, dx, lddx, mask=mask, ldmask=ldmask, accumulate=beta == 1.0)
         elif M <= 128 and N >= 256 and beta == 0.0 and lddx == K:

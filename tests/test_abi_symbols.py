@@ -80,6 +80,7 @@ def test_argument_errors_of_loss_and_training_entry_points():
     assert lib.pz_sgemm(0, 0, 0, 8, 8, 1.0, None, 8, None, 8, 0.0, None, 8, 1, 0, 0, 0, 1, None, 0, None, 0, None, 0, None) == 0
     # pz_gemm_tf32: shape and alignment contract
     assert lib.pz_gemm_tf32(0, 0, 100, 128, 32, one, 32, one, 32, one, 128, 1, None, 0, None, 0, 0, None) == -2
+    assert lib.pz_gemm_tf32(0, 0, 128, 96, 32, one, 32, one, 32, one, 96, 1, None, 0, None, 0, 0, None) == -2
     assert b"M % 128" in lib.pz_last_error()
     assert lib.pz_gemm_tf32(0, 0, 128, 128, 32, one, 30, one, 32, one, 128, 1, None, 0, None, 0, 0, None) == -1
     assert lib.pz_gemm_tf32(0, 0, 128, 128, 32, one, 32, one, 32, one, 128, 4, one, 0, None, 0, 0, None) == -2

@@ -198,7 +198,7 @@ def _tf32_round(x):
 
 
 @pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 1), (1, 0)])
-@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (384, 256, 96), (256, 128, 4096)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (384, 256, 96), (256, 128, 4096), (256, 64, 64), (128, 192, 32)])
 def test_gemm_tf32_layouts(a_mn, b_mn, M, N, K):
     """every operand-major combination of the tcgen05 TF32 GEMM vs a float64 product of the fp32 inputs: the error
     must be explained by operand rounding to 10 mantissa bits (|err| <= 2^-10 * sum |a||b|), and far from the O(1)
