@@ -37,10 +37,14 @@ struct SgemmArgs {
   long long ldres, bsres;
 };
 
-constexpr int GT = 128, GK = 8;
+constexpr int GK = 8;
 
-template <bool A_KCONTIG, bool B_NCONTIG>
+// GT x GT output tile (128: 8x8 micro-tiles; 64: 4x4, for outputs no wider than 64 -- the weight gradients of the
+// 64-channel layers, where a 128-wide tile would be 3/4 empty), GK-deep k-steps, 256 threads.
+template <bool A_KCONTIG, bool B_NCONTIG, int GT>
 __global__ void __launch_bounds__(256) sgemm_kernel(const SgemmArgs p) {
+  constexpr int MT = GT / 16;            // micro-tile edge per thread
+  constexpr int EPT = GT * GK / 256;     // operand elements each thread loads per k-step (4 or 2)
   __shared__ __align__(16) float As[2][GK][GT + 4];
   __shared__ __align__(16) float Bs[2][GK][GT + 4];
   const int t = threadIdx.x;
@@ -62,14 +66,16 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const SgemmArgs p) {
     if (mask) mask += (long long)blockIdx.z * p.bsmask;
     if (residual) residual += (long long)blockIdx.z * p.bsres;
   }
-  // loader coordinates: 4 elements per thread per operand
+  // loader coordinates: EPT consecutive elements (along the contiguous dimension) per thread per operand
+  constexpr int KT = GK / EPT;           // threads along k when k is contiguous
+  constexpr int MTH = GT / EPT;          // threads along m / n when that dimension is contiguous
   int a_m, a_k, b_k, b_n;
-  if (A_KCONTIG) { a_m = t >> 1; a_k = (t & 1) * 4; } else { a_k = t >> 5; a_m = (t & 31) * 4; }
-  if (B_NCONTIG) { b_k = t >> 5; b_n = (t & 31) * 4; } else { b_n = t >> 1; b_k = (t & 1) * 4; }
-  float ra[4], rb[4];
+  if (A_KCONTIG) { a_m = t / KT; a_k = (t % KT) * EPT; } else { a_k = t / MTH; a_m = (t % MTH) * EPT; }
+  if (B_NCONTIG) { b_k = t / MTH; b_n = (t % MTH) * EPT; } else { b_n = t / KT; b_k = (t % KT) * EPT; }
+  float ra[EPT], rb[EPT];
   auto fetch = [&](int k0) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < EPT; ++i) {
       const int m = m0 + a_m + (A_KCONTIG ? 0 : i), k = k0 + a_k + (A_KCONTIG ? i : 0);
       ra[i] = (m < p.M && k < kend) ? A[(long long)m * p.sam + (long long)k * p.sak] : 0.f;
       const int kk = k0 + b_k + (B_NCONTIG ? 0 : i), n = n0 + b_n + (B_NCONTIG ? i : 0);
@@ -78,16 +84,16 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const SgemmArgs p) {
   };
   auto stash = [&](int buf) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < EPT; ++i) {
       if (A_KCONTIG) As[buf][a_k + i][a_m] = ra[i]; else As[buf][a_k][a_m + i] = ra[i];
       if (B_NCONTIG) Bs[buf][b_k][b_n + i] = rb[i]; else Bs[buf][b_k + i][b_n] = rb[i];
     }
   };
-  float acc[8][8];
+  float acc[MT][MT];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < MT; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < MT; ++j) acc[i][j] = 0.f;
   const int ty = t >> 4, tx = t & 15;
   fetch(kbeg);
   stash(0);
@@ -98,17 +104,19 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const SgemmArgs p) {
     if (more) fetch(k0 + GK);
 #pragma unroll
     for (int kk = 0; kk < GK; ++kk) {
-      float a[8], b[8];
-      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
-      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][64 + ty * 4]);
-      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
-      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][64 + tx * 4]);
-      a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
-      b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+      float a[MT], b[MT];
+      // rows ty*4+{0..3} (and GT/2 + the same for the 8x8 micro-tile); likewise columns from tx
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int h = 0; h < MT / 4; ++h) {
+        const float4 a4 = *reinterpret_cast<const float4*>(&As[buf][kk][h * (GT / 2) + ty * 4]);
+        const float4 b4 = *reinterpret_cast<const float4*>(&Bs[buf][kk][h * (GT / 2) + tx * 4]);
+        a[h * 4] = a4.x; a[h * 4 + 1] = a4.y; a[h * 4 + 2] = a4.z; a[h * 4 + 3] = a4.w;
+        b[h * 4] = b4.x; b[h * 4 + 1] = b4.y; b[h * 4 + 2] = b4.z; b[h * 4 + 3] = b4.w;
+      }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < MT; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
     }
     if (more) {
       stash(buf ^ 1);
@@ -116,14 +124,13 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const SgemmArgs p) {
       buf ^= 1;
     }
   }
-  // epilogue: rows ty*4+{0..3} and 64+ty*4+{0..3}; columns tx*4+{0..3} and 64+tx*4+{0..3}
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + i - 4);
+  for (int i = 0; i < MT; ++i) {
+    const int m = m0 + (i >> 2) * (GT / 2) + ty * 4 + (i & 3);
     if (m >= p.M) continue;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int n = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + j - 4);
+    for (int j = 0; j < MT; ++j) {
+      const int n = n0 + (j >> 2) * (GT / 2) + tx * 4 + (j & 3);
       if (n >= p.N) continue;
       float v = p.alpha * acc[i][j];
       float* c = C + (long long)m * p.ldc + n;
@@ -139,6 +146,15 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const SgemmArgs p) {
       *c = v;
     }
   }
+}
+
+template <int GT>
+static void sgemm_dispatch(const SgemmArgs& p, int transA, int transB, int batch_or_splits, cudaStream_t st) {
+  dim3 grid((p.N + GT - 1) / GT, (p.M + GT - 1) / GT, batch_or_splits);
+  if (!transA && !transB) sgemm_kernel<true, true, GT><<<grid, 256, 0, st>>>(p);
+  else if (!transA && transB) sgemm_kernel<true, false, GT><<<grid, 256, 0, st>>>(p);
+  else if (transA && !transB) sgemm_kernel<false, true, GT><<<grid, 256, 0, st>>>(p);
+  else sgemm_kernel<false, false, GT><<<grid, 256, 0, st>>>(p);
 }
 
 // =============================================================================== small helpers
@@ -568,13 +584,11 @@ extern "C" int pz_sgemm(int transA, int transB, int M, int N, int K, float alpha
   p.M = M; p.N = N; p.K = K; p.splitk = splitk; p.alpha = alpha; p.beta = beta;
   p.bias = bias_or_null; p.relu = relu; p.mask = mask_or_null; p.ldmask = ldmask; p.bsmask = strideC;
   p.residual = residual_or_null; p.ldres = ldres; p.bsres = strideC;
-  dim3 grid((N + GT - 1) / GT, (M + GT - 1) / GT, splitk > 1 ? splitk : batch);
-  PZ_REQUIRE(grid.y <= 65535 && grid.z <= 65535, PZ_ERR_UNSUPPORTED, "pz_sgemm: grid too large (M=%d batch=%d)", M, batch);
-  cudaStream_t st = as_stream(stream);
-  if (!transA && !transB) sgemm_kernel<true, true><<<grid, 256, 0, st>>>(p);
-  else if (!transA && transB) sgemm_kernel<true, false><<<grid, 256, 0, st>>>(p);
-  else if (transA && !transB) sgemm_kernel<false, true><<<grid, 256, 0, st>>>(p);
-  else sgemm_kernel<false, false><<<grid, 256, 0, st>>>(p);
+  const int gt = (M <= 64 || N <= 64) ? 64 : 128;          // narrow outputs: 64 x 64 tiles
+  const int nz = splitk > 1 ? splitk : batch;
+  PZ_REQUIRE((M + gt - 1) / gt <= 65535 && nz <= 65535, PZ_ERR_UNSUPPORTED, "pz_sgemm: grid too large (M=%d batch=%d)", M, batch);
+  if (gt == 64) sgemm_dispatch<64>(p, transA, transB, nz, as_stream(stream));
+  else sgemm_dispatch<128>(p, transA, transB, nz, as_stream(stream));
   PZ_LAUNCH_CHECK();
   return PZ_OK;
 }
