@@ -299,6 +299,14 @@ int pz_sgemm(int transA, int transB, int M, int N, int K, float alpha, const flo
 int pz_gemm_tf32(int a_mn_major, int b_mn_major, int M, int N, int K, const float* A, long long lda, const float* B,
                  long long ldb, float* C, long long ldc, int splitk, const float* bias_or_null, int relu,
                  const float* mask_or_null, long long ldmask, int accumulate, pz_stream_t stream);
+/* batch independent problems (the per-cloud attention products): operand i at A + i*strideA, B + i*strideB, output and
+ * mask at + i*strideC; splitk must be 1. */
+int pz_gemm_tf32_batched(int a_mn_major, int b_mn_major, int M, int N, int K, const float* A, long long lda,
+                         const float* B, long long ldb, float* C, long long ldc, int batch, long long strideA,
+                         long long strideB, long long strideC, int splitk, const float* bias_or_null, int relu,
+                         const float* mask_or_null, long long ldmask, int accumulate, pz_stream_t stream);
+/* softmax(scale * S) over the last dimension of S [rows, L] (model5_b.py:70-72 forward). */
+int pz_softmax_forward(const float* S, long long rows, int L, float scale, float* A, pz_stream_t stream);
 /* out[n] = beta*out[n] + sum_m x[m*ld + n]  (bias gradients). */
 int pz_colsum(const float* x, long long ld, long long M, int N, float beta, float* out, pz_stream_t stream);
 /* out[r,c] = a*x[r,c] + b*y[r,c] with row strides (y may be null). */

@@ -72,6 +72,8 @@ struct Tf32Gemm {
   const float* mask;          // zero where mask[m*ldmask + n] <= 0
   long long ldmask;
   int accumulate;             // C += result (splitk == 1)
+  int batch;                  // independent problems at A + i*sA, B + i*sB, C / mask + i*sC (streaming mode only)
+  long long sA, sB, sC;
 };
 // BRES (B resident): when all k-blocks of one B column tile fit in shared memory (a weight matrix: NCOLS * K * 4 bytes
 // <= 128 KB) every CTA loads them ONCE, keeps one column tile for its whole life and streams only A -- the streaming
@@ -94,7 +96,8 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tf32_gemm_kernel(const Tf32Gemm
   const int nsplit = (kblocks + kb_per_split - 1) / kb_per_split;       // every split is non-empty
   const int row_tiles = g.M / TG_ROWS, col_tiles = g.N / NCOLS;
   // BRES: CTA b owns column tile b % col_tiles (the grid is a multiple of col_tiles) and row tiles b / col_tiles + i * stride
-  const int work = BRES ? row_tiles : row_tiles * col_tiles * nsplit;
+  const int per_batch = row_tiles * col_tiles * nsplit;
+  const int work = BRES ? row_tiles : per_batch * g.batch;
   const int w_begin = BRES ? (int)blockIdx.x / col_tiles : (int)blockIdx.x;
   const int w_step = BRES ? (int)gridDim.x / col_tiles : (int)gridDim.x;
   const int my_ct = BRES ? (int)blockIdx.x % col_tiles : 0;
@@ -122,11 +125,14 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tf32_gemm_kernel(const Tf32Gemm
 
   // work item -> (row tile, column tile, k range); the split index varies fastest so that the CTAs working on one
   // output tile run at the same time (their atomics meet in L2)
-  auto decode = [&](int w, int& rt, int& ct, int& kb0, int& kb1) {
+  auto decode = [&](int w, int& rt, int& ct, int& kb0, int& kb1, int& bi) {
+    bi = 0;
     if (BRES) {
       rt = w; ct = my_ct; kb0 = 0; kb1 = kblocks;
       return;
     }
+    bi = w / per_batch;
+    w -= bi * per_batch;
     const int sp = w % nsplit, t = w / nsplit;
     ct = t % col_tiles;
     rt = t / col_tiles;
@@ -138,31 +144,33 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tf32_gemm_kernel(const Tf32Gemm
     // ================================================= producers
     const int pt = tid - (TG_EPI + 1) * 32;
     uint32_t issued = 0, arrived = 0;
-    auto load_b = [&](uint32_t dst, int col0, long long k0) {
+    auto load_b = [&](uint32_t dst, const float* Bp, int col0, long long k0) {
       if (!g.b_mn) {
         for (int id = pt; id < NCOLS * 8; id += TG_PROD_THREADS) {
           const int c = id & 7, r = id >> 3;
-          cp_async16(dst + sw128(r, c), g.B + (long long)(col0 + r) * g.ldb + k0 + c * 4);
+          cp_async16(dst + sw128(r, c), Bp + (long long)(col0 + r) * g.ldb + k0 + c * 4);
         }
       } else {
         constexpr int NB = NCOLS / 32;
         for (int id = pt; id < NCOLS * 8; id += TG_PROD_THREADS) {
           const int c = id & 7, j = (id >> 3) % NB, kk = (id >> 3) / NB;
-          cp_async16(dst + j * (TG_KB * 128) + sw128_32(kk, c), g.B + (k0 + kk) * g.ldb + col0 + j * 32 + c * 4);
+          cp_async16(dst + j * (TG_KB * 128) + sw128_32(kk, c), Bp + (k0 + kk) * g.ldb + col0 + j * 32 + c * 4);
         }
       }
     };
     if (BRES) {
-      for (int kb = 0; kb < kblocks; ++kb) load_b(bres_base + kb * STAGE_B, my_ct * NCOLS, (long long)kb * TG_KB);
+      for (int kb = 0; kb < kblocks; ++kb) load_b(bres_base + kb * STAGE_B, g.B, my_ct * NCOLS, (long long)kb * TG_KB);
       cp_async_commit();
       cp_async_wait<0>();
       fence_proxy_async();
       mbar_arrive(bres_bar);
     }
     for (int w = w_begin; w < work; w += w_step) {
-      int rt, ct, kb0, kb1;
-      decode(w, rt, ct, kb0, kb1);
+      int rt, ct, kb0, kb1, bi;
+      decode(w, rt, ct, kb0, kb1, bi);
       const int row0 = rt * TG_ROWS, col0 = ct * NCOLS;
+      const float* Ab = g.A + (long long)bi * g.sA;
+      const float* Bb = g.B + (long long)bi * g.sB;
       for (int kb = kb0; kb < kb1; ++kb) {
         const uint32_t s = issued % NST, ph = (issued / NST) & 1;
         mbar_wait(empty_bar + 8 * s, ph ^ 1);
@@ -171,15 +179,15 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tf32_gemm_kernel(const Tf32Gemm
         if (!g.a_mn) {
           for (int id = pt; id < TG_ROWS * 8; id += TG_PROD_THREADS) {
             const int c = id & 7, r = id >> 3;
-            cp_async16(st_addr + sw128(r, c), g.A + (long long)(row0 + r) * g.lda + k0 + c * 4);
+            cp_async16(st_addr + sw128(r, c), Ab + (long long)(row0 + r) * g.lda + k0 + c * 4);
           }
         } else {
           for (int id = pt; id < TG_ROWS * 8; id += TG_PROD_THREADS) {
             const int c = id & 7, j = (id >> 3) & 3, kk = id >> 5;      // 8 chunks x 4 MN blocks x 32 k
-            cp_async16(st_addr + j * (TG_KB * 128) + sw128_32(kk, c), g.A + (k0 + kk) * g.lda + row0 + j * 32 + c * 4);
+            cp_async16(st_addr + j * (TG_KB * 128) + sw128_32(kk, c), Ab + (k0 + kk) * g.lda + row0 + j * 32 + c * 4);
           }
         }
-        if (!BRES) load_b(st_addr + STAGE_A, col0, k0);
+        if (!BRES) load_b(st_addr + STAGE_A, Bb, col0, k0);
         cp_async_commit();
         ++issued;
         // stages whose loads may be outstanding before the oldest is waited for and published; must stay below NST - 1,
@@ -209,8 +217,8 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tf32_gemm_kernel(const Tf32Gemm
         tc_fence_after();
       }
       for (int w = w_begin; w < work; w += w_step, ++tcn) {
-        int rt, ct, kb0, kb1;
-        decode(w, rt, ct, kb0, kb1);
+        int rt, ct, kb0, kb1, bi;
+        decode(w, rt, ct, kb0, kb1, bi);
         const uint32_t buf = tcn & 1, aph = (tcn >> 1) & 1;
         mbar_wait(acce_bar + 8 * buf, aph ^ 1);
         tc_fence_after();
@@ -237,10 +245,12 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tf32_gemm_kernel(const Tf32Gemm
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     uint32_t tcn = 0;
     for (int w = w_begin; w < work; w += w_step, ++tcn) {
-      int rt, ct, kb0, kb1;
-      decode(w, rt, ct, kb0, kb1);
+      int rt, ct, kb0, kb1, bi;
+      decode(w, rt, ct, kb0, kb1, bi);
       const int col0 = ct * NCOLS;
       const long long row = (long long)rt * TG_ROWS + quarter * 32 + lane;
+      float* Cb = g.C + (long long)bi * g.sC;
+      const float* maskb = g.mask ? g.mask + (long long)bi * g.sC : nullptr;
       const uint32_t buf = tcn & 1, aph = (tcn >> 1) & 1;
       mbar_wait(accf_bar + 8 * buf, aph);
       tc_fence_after();
@@ -249,7 +259,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tf32_gemm_kernel(const Tf32Gemm
         const int cb = col0 + c32 * 32;
         float v[32];
         tmem_ld32(tmem_base + lane_base + buf * NCOLS + c32 * 32, v);
-        float* cp = g.C + row * g.ldc + cb;
+        float* cp = Cb + row * g.ldc + cb;
         if (g.atomic) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) atomicAdd(cp + i, v[i]);
@@ -274,7 +284,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tf32_gemm_kernel(const Tf32Gemm
           for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
         }
         if (g.mask) {
-          const float* mp = g.mask + row * g.ldmask + cb;
+          const float* mp = maskb + row * g.ldmask + cb;
 #pragma unroll
           for (int q4 = 0; q4 < 8; ++q4) {
             const float4 m4 = *reinterpret_cast<const float4*>(mp + q4 * 4);
@@ -315,7 +325,7 @@ static int tf32_launch(const Tf32Gemm& g, cudaStream_t st) {
   } else {
     const int kbps = (kblocks + g.splitk - 1) / g.splitk;
     const int nsplit = (kblocks + kbps - 1) / kbps;
-    const long long work = (long long)(g.M / TG_ROWS) * (g.N / NCOLS) * nsplit;
+    const long long work = (long long)(g.M / TG_ROWS) * (g.N / NCOLS) * nsplit * g.batch;
     grid = (int)(work < kNumSMs ? work : kNumSMs);
   }
   kern<<<grid, TG_THREADS, smem, st>>>(g);
@@ -331,6 +341,19 @@ extern "C" int pz_gemm_tf32(int a_mn_major, int b_mn_major, int M, int N, int K,
                             const float* B, long long ldb, float* C, long long ldc, int splitk,
                             const float* bias_or_null, int relu, const float* mask_or_null, long long ldmask,
                             int accumulate, pz_stream_t stream) {
+  return pz_gemm_tf32_batched(a_mn_major, b_mn_major, M, N, K, A, lda, B, ldb, C, ldc, 1, 0, 0, 0, splitk, bias_or_null,
+                              relu, mask_or_null, ldmask, accumulate, stream);
+}
+
+extern "C" int pz_gemm_tf32_batched(int a_mn_major, int b_mn_major, int M, int N, int K, const float* A, long long lda,
+                                    const float* B, long long ldb, float* C, long long ldc, int batch, long long strideA,
+                                    long long strideB, long long strideC, int splitk, const float* bias_or_null,
+                                    int relu, const float* mask_or_null, long long ldmask, int accumulate,
+                                    pz_stream_t stream) {
+  PZ_REQUIRE(batch >= 0, PZ_ERR_ARG, "pz_gemm_tf32: batch < 0");
+  if (batch == 0) return PZ_OK;
+  PZ_REQUIRE(batch == 1 || (splitk == 1 && strideA % 4 == 0 && strideB % 4 == 0 && strideC % 4 == 0), PZ_ERR_ARG,
+             "pz_gemm_tf32: batched problems need 16-byte aligned strides and splitk == 1");
   PZ_REQUIRE(M >= 0 && N >= 0 && K >= 0, PZ_ERR_ARG, "pz_gemm_tf32: negative size");
   if (M == 0 || N == 0) return PZ_OK;
   PZ_REQUIRE(A && B && C, PZ_ERR_ARG, "pz_gemm_tf32: null pointer");
@@ -346,13 +369,13 @@ extern "C" int pz_gemm_tf32(int a_mn_major, int b_mn_major, int M, int N, int K,
   PZ_REQUIRE(!(splitk > 1 && (bias_or_null || relu || mask_or_null || accumulate)), PZ_ERR_UNSUPPORTED,
              "pz_gemm_tf32: split-K adds raw partial sums into a pre-zeroed C (no epilogue)");
   Tf32Gemm g{A, lda, a_mn_major ? 1 : 0, B, ldb, b_mn_major ? 1 : 0, C, ldc, M, N, K, splitk, splitk > 1 ? 1 : 0,
-             bias_or_null, relu, mask_or_null, ldmask, accumulate};
+             bias_or_null, relu, mask_or_null, ldmask, accumulate, batch, strideA, strideB, strideC};
   // weights-resident mode: forward / data-gradient GEMMs whose B operand (one 128-column tile, all of K) fits in 128 KB
   // and that have enough row tiles to amortise loading it once per CTA
   static const bool no_bres = getenv("PZ_TF32_NO_BRES") != nullptr;      // tuning hook: force the streaming kernel
   // (measured: 17 % faster than streaming for the 128-wide layers, 4.7 TB/s on compulsory bytes; for N = 256 the A
   // operand would be read once per column tile, which costs more than the weights it saves)
-  if (!no_bres && splitk == 1 && N == 128 && M / 128 >= 4 * kNumSMs) {
+  if (!no_bres && batch == 1 && splitk == 1 && N == 128 && M / 128 >= 4 * kNumSMs) {
     if (K <= 128) return tf32_launch<128, 8, true>(g, as_stream(stream));     // 64 KB of weights + 8 x 16 KB of A in flight
     if (K <= 256) return tf32_launch<128, 4, true>(g, as_stream(stream));     // 128 KB + 4 x 16 KB
   }

@@ -384,6 +384,24 @@ __global__ void __launch_bounds__(256) scatter_add_rows_kernel(const float* __re
   if (v != 0.f) atomicAdd(dst + ((m / per_cloud) * N + idx[m]) * ldd + c, v);
 }
 
+// =============================================================================== softmax forward
+// A[r,:] = softmax(scale * S[r,:]);  one warp per row (exp of the shifted logits, as torch.softmax evaluates it)
+__global__ void __launch_bounds__(256) softmax_fwd_kernel(const float* __restrict__ S, long long rows, int L, float scale,
+                                                          float* __restrict__ A) {
+  const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float* s = S + r * L;
+  float mx = -INFINITY;
+  for (int j = lane; j < L; j += 32) mx = fmaxf(mx, s[j] * scale);
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float sum = 0.f;
+  for (int j = lane; j < L; j += 32) sum += expf(s[j] * scale - mx);
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float inv = 1.f / sum;
+  for (int j = lane; j < L; j += 32) A[r * L + j] = expf(s[j] * scale - mx) * inv;
+}
+
 // =============================================================================== softmax backward
 // dS[r,:] = scale * A[r,:] * (dA[r,:] - sum_j dA[r,j] A[r,j]);  one warp per row
 __global__ void __launch_bounds__(256) softmax_bwd_kernel(const float* __restrict__ A, const float* __restrict__ dA,
@@ -726,6 +744,15 @@ extern "C" int pz_scatter_add_rows(const float* src, long long ld, int c0, int C
   PZ_REQUIRE((n + 255) / 256 <= 2147483647LL, PZ_ERR_UNSUPPORTED, "pz_scatter_add_rows: too many elements");
   scatter_add_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(src, ld, c0, C, idx, M, per_cloud,
                                                                                       N, dst, ldd);
+  PZ_LAUNCH_CHECK();
+  return PZ_OK;
+}
+
+extern "C" int pz_softmax_forward(const float* S, long long rows, int L, float scale, float* A, pz_stream_t stream) {
+  PZ_REQUIRE(rows >= 0 && L >= 1, PZ_ERR_ARG, "pz_softmax_forward: bad size");
+  if (rows == 0) return PZ_OK;
+  PZ_REQUIRE(S && A, PZ_ERR_ARG, "pz_softmax_forward: null pointer");
+  softmax_fwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, as_stream(stream)>>>(S, rows, L, scale, A);
   PZ_LAUNCH_CHECK();
   return PZ_OK;
 }

@@ -54,6 +54,12 @@ def _gemm_tf32(a_mn, b_mn, M, N, K, A, lda, B, ldb, C, ldc, splitk=1, bias=None,
               int(relu), _p(mask), ldmask, int(accumulate), _st())
 
 
+def bgemm_tf32(a_mn, b_mn, M, N, K, A, lda, B, ldb, C, ldc, batch, sa, sb, sc):
+    """per-cloud products of the attention layers on the tensor cores (TF32)"""
+    _lib.call("pz_gemm_tf32_batched", int(a_mn), int(b_mn), M, N, K, _p(A), lda, _p(B), ldb, _p(C), ldc, batch, sa, sb, sc,
+              1, None, 0, None, 0, 0, _st())
+
+
 def linear_fwd(x, ldx, M, lin, out, ldo, relu=False, W=None, K=None, tf32=False):
     """out[M, N] = act(x[M, K] W^T + b).  ``W``/``K`` override the weight with a zero-padded copy (row stride K);
     ``tf32`` routes shapes the tensor-core kernel supports to ``pz_gemm_tf32``."""
@@ -287,7 +293,12 @@ class Trainer:
             linear_fwd(x, 1280, T, att.mlpq, q, 64, tf32=self.tf32)
             linear_fwd(x, 1280, T, att.mlpk, k, 64, tf32=self.tf32)
             linear_fwd(x, 1280, T, att.mlpv, v, 256, tf32=self.tf32)
-            _lib.call("pz_scaled_dot_attention", _p(q), _p(k), _p(v), B, S2, 64, 256, _p(vals), _p(A), _st())
+            if self.tf32:       # S = q k^T, softmax, vals = A v: two batched TF32 GEMMs around one softmax kernel
+                bgemm_tf32(0, 0, S2, S2, 64, q, 64, k, 64, A, S2, B, S2 * 64, S2 * 64, S2 * S2)
+                _lib.call("pz_softmax_forward", _p(A), B * S2, S2, 1.0 / math.sqrt(64.0), _p(A), _st())
+                bgemm_tf32(0, 1, S2, 256, S2, A, S2, v, 256, vals, 256, B, S2 * S2, S2 * 256, S2 * 256)
+            else:
+                _lib.call("pz_scaled_dot_attention", _p(q), _p(k), _p(v), B, S2, 64, 256, _p(vals), _p(A), _st())
             axpby(T, 256, 1.0, x, 1280, -1.0, vals, 256, r, 256)                              # r = x - A v
             linear_fwd(r, 256, T, att.out, ro, 256, relu=True, tf32=self.tf32)                                # relu(W_o r + b_o)
             axpby(T, 256, 1.0, x, 1280, 1.0, ro, 256, c.cat[:, l * 256:], 1280)               # x + relu(...)
@@ -324,14 +335,24 @@ class Trainer:
             # r = x - A v :  dx = dcur + dr ; dvals = -dr
             axpby(T, 256, 1.0, dcur, 256, 1.0, dr, 256, dcur, 256)
             # vals = A v (per cloud):  dv = A^T dvals ; dA = dvals v^T
-            gemm(A, dr, dv, S2, 256, S2, ta=True, lda=S2, ldb=256, ldc=256, alpha=-1.0, batch=B, sa=LL, sb=S2 * 256,
-                 sc=S2 * 256)
-            gemm(dr, v, dA, S2, S2, 256, tb=True, lda=256, ldb=256, ldc=S2, alpha=-1.0, batch=B, sa=S2 * 256,
-                 sb=S2 * 256, sc=LL)
+            if self.tf32:
+                dvals = b("dvals", T, 256)
+                axpby(T, 256, -1.0, dr, 256, 0.0, None, 0, dvals, 256)
+                bgemm_tf32(1, 1, S2, 256, S2, A, S2, dvals, 256, dv, 256, B, LL, S2 * 256, S2 * 256)
+                bgemm_tf32(0, 0, S2, S2, 256, dvals, 256, v, 256, dA, S2, B, S2 * 256, S2 * 256, LL)
+            else:
+                gemm(A, dr, dv, S2, 256, S2, ta=True, lda=S2, ldb=256, ldc=256, alpha=-1.0, batch=B, sa=LL, sb=S2 * 256,
+                     sc=S2 * 256)
+                gemm(dr, v, dA, S2, S2, 256, tb=True, lda=256, ldb=256, ldc=S2, alpha=-1.0, batch=B, sa=S2 * 256,
+                     sb=S2 * 256, sc=LL)
             _lib.call("pz_softmax_backward", _p(A), _p(dA), B * S2, S2, 1.0 / math.sqrt(64.0), _p(dS), _st())
             # S = q k^T :  dq = dS k ; dk = dS^T q
-            gemm(dS, k, dq, S2, 64, S2, lda=S2, ldb=64, ldc=64, batch=B, sa=LL, sb=S2 * 64, sc=S2 * 64)
-            gemm(dS, q, dk, S2, 64, S2, ta=True, lda=S2, ldb=64, ldc=64, batch=B, sa=LL, sb=S2 * 64, sc=S2 * 64)
+            if self.tf32:
+                bgemm_tf32(0, 1, S2, 64, S2, dS, S2, k, 64, dq, 64, B, LL, S2 * 64, S2 * 64)
+                bgemm_tf32(1, 1, S2, 64, S2, dS, S2, q, 64, dk, 64, B, LL, S2 * 64, S2 * 64)
+            else:
+                gemm(dS, k, dq, S2, 64, S2, lda=S2, ldb=64, ldc=64, batch=B, sa=LL, sb=S2 * 64, sc=S2 * 64)
+                gemm(dS, q, dk, S2, 64, S2, ta=True, lda=S2, ldb=64, ldc=64, batch=B, sa=LL, sb=S2 * 64, sc=S2 * 64)
             linear_bwd(dq, 64, x, 1280, T, att.mlpq, G(att.mlpq.weight), G(att.mlpq.bias), dcur, 256, beta=1.0, tf32=self.tf32)
             linear_bwd(dk, 64, x, 1280, T, att.mlpk, G(att.mlpk.weight), G(att.mlpk.bias), dcur, 256, beta=1.0, tf32=self.tf32)
             linear_bwd(dv, 256, x, 1280, T, att.mlpv, G(att.mlpv.weight), G(att.mlpv.bias), dcur, 256, beta=1.0, tf32=self.tf32)

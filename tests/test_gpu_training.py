@@ -360,3 +360,27 @@ def test_gemm_tf32_weights_resident_mode(a_mn, b_mn, N, K):
               2, None, 0, None, 0, 0, st)
     want = torch.relu(C2 + bias.to(DEV))
     assert (C - want).abs().max().item() <= 2e-3 * want.abs().max().item()
+
+
+def test_gemm_tf32_batched_and_softmax_forward():
+    """the per-cloud attention products: batched TF32 GEMM in the four operand layouts used by the attention
+    backward, and the softmax forward kernel vs torch"""
+    from puzzlenet_b200 import training as T
+    g = torch.Generator().manual_seed(9)
+    Bt, L = 5, 256
+    for a_mn, b_mn, N, K in ((0, 0, 256, 64), (0, 1, 256, 256), (1, 1, 64, 256), (0, 1, 64, 256), (1, 1, 256, 256)):
+        A = torch.randn(Bt, L, K, generator=g)
+        Bm = torch.randn(Bt, N, K, generator=g)
+        ref = A.double() @ Bm.double().transpose(1, 2)
+        Ad = (A.transpose(1, 2).contiguous() if a_mn else A).to(DEV)
+        Bd = (Bm.transpose(1, 2).contiguous() if b_mn else Bm).to(DEV)
+        C = torch.empty(Bt, L, N, device=DEV)
+        T.bgemm_tf32(a_mn, b_mn, L, N, K, Ad, Ad.shape[2], Bd, Bd.shape[2], C, N, Bt, Ad[0].numel(), Bd[0].numel(), L * N)
+        bound = (A.abs().double() @ Bm.abs().double().transpose(1, 2)) * 2.0 ** -10 + 1e-6
+        assert ((C.cpu().double() - ref).abs() <= bound).all(), (a_mn, b_mn, N, K)
+    S = torch.randn(Bt * L, L, generator=g) * 5
+    out = torch.empty(Bt * L, L, device=DEV)
+    Sd = S.to(DEV)
+    from puzzlenet_b200 import _lib
+    _lib.call("pz_softmax_forward", Sd.data_ptr(), Bt * L, L, 0.125, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    np.testing.assert_allclose(out.cpu().numpy(), torch.softmax(S * 0.125, -1).numpy(), rtol=1e-5, atol=1e-7)
