@@ -111,6 +111,12 @@ int pz_group_concat_padded(const float* xyz, const float* feat_or_null, const fl
                            const int64_t* knn_idx, int B, int N, int D, int S, int K, int ld, float* new_points,
                            float* grouped_xyz_or_null, pz_stream_t stream);
 
+/* plane_split(points, z) -- dataset.py:761-775: order-preserving partition of one cloud pts [n,C] (xyz first) by the
+ * sign of p . normal + z, evaluated in float64 like numpy; up (dis >= 0) and down (dis < 0) have room for n rows,
+ * counts [2] (device) receives the two sizes.  The caller draws normal and z (np.random in the reference). */
+int pz_plane_split(const float* pts, int n, int C, double nx, double ny, double nz, double z, float* up, float* down,
+                   int32_t* counts, pz_stream_t stream);
+
 /* ------------------------------------------------------------ fused blocks */
 
 /* sample_and_group's grouping + the shared MLP + neighbourhood max-pool in one pass, never

@@ -435,10 +435,62 @@ __global__ void __launch_bounds__(256) group_concat_kernel(const float* __restri
   }
 }
 
+// ------------------------------------------------------------------ plane_split (dataset.py:761-775)
+// Order-preserving two-way partition of one cloud by the sign of  p . normal + z  (evaluated in float64, as numpy does
+// for a float32 cloud and a float64 normal).  One CTA walks the cloud in chunks of 1024 points: ballot + warp counts +
+// a scan over the 32 warps give every point its slot in `up` (dis >= 0) or `down` (dis < 0).
+__global__ void __launch_bounds__(1024) plane_split_kernel(const float* __restrict__ pts, int n, int C, double nx,
+                                                           double ny, double nz, double z, float* __restrict__ up,
+                                                           float* __restrict__ down, int* __restrict__ counts) {
+  __shared__ int warp_up[32], warp_dn[32];
+  __shared__ int base_up, base_dn;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  if (t == 0) { base_up = 0; base_dn = 0; }
+  __syncthreads();
+  for (int c0 = 0; c0 < n; c0 += 1024) {
+    const int i = c0 + t;
+    bool valid = i < n, is_up = false;
+    if (valid) {
+      const float* p = pts + (size_t)i * C;
+      const double dis = ((double)p[0] * nx + (double)p[1] * ny) + (double)p[2] * nz + z;
+      is_up = dis >= 0.0;
+    }
+    const unsigned mu = __ballot_sync(0xffffffffu, valid && is_up), md = __ballot_sync(0xffffffffu, valid && !is_up);
+    if (lane == 0) { warp_up[warp] = __popc(mu); warp_dn[warp] = __popc(md); }
+    __syncthreads();
+    int off_u = base_up, off_d = base_dn;
+    for (int w = 0; w < warp; ++w) { off_u += warp_up[w]; off_d += warp_dn[w]; }
+    if (valid) {
+      const unsigned lt = (1u << lane) - 1u;
+      float* dst = is_up ? up + (size_t)(off_u + __popc(mu & lt)) * C : down + (size_t)(off_d + __popc(md & lt)) * C;
+      const float* p = pts + (size_t)i * C;
+      for (int c = 0; c < C; ++c) dst[c] = p[c];
+    }
+    __syncthreads();
+    if (t == 0) {
+      int su = 0, sd = 0;
+      for (int w = 0; w < 32; ++w) { su += warp_up[w]; sd += warp_dn[w]; }
+      base_up += su;
+      base_dn += sd;
+    }
+    __syncthreads();
+  }
+  if (t == 0) { counts[0] = base_up; counts[1] = base_dn; }
+}
+
 }  // namespace pz
 
 // ------------------------------------------------------------------------- C ABI
 using namespace pz;
+
+extern "C" int pz_plane_split(const float* pts, int n, int C, double nx, double ny, double nz, double z, float* up,
+                              float* down, int32_t* counts, pz_stream_t stream) {
+  PZ_REQUIRE(n >= 0 && C >= 3, PZ_ERR_ARG, "pz_plane_split: need n >= 0 and at least 3 columns (got n=%d C=%d)", n, C);
+  PZ_REQUIRE(counts && (n == 0 || (pts && up && down)), PZ_ERR_ARG, "pz_plane_split: null pointer");
+  plane_split_kernel<<<1, 1024, 0, as_stream(stream)>>>(pts, n, C, nx, ny, nz, z, up, down, counts);
+  PZ_LAUNCH_CHECK();
+  return 0;
+}
 
 extern "C" int pz_fps(const float* xyz, int B, int N, const int64_t* start, int S, int64_t* out_idx,
                       float* new_xyz_or_null, pz_stream_t stream) {

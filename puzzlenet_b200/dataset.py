@@ -7,7 +7,7 @@ motion (``se_math/transforms.py:151-196``).  Here the same steps run on the GPU 
 
 * :func:`fps`              -- ``CADDataset.fps(points, npoints)``; returns the selected POINTS like the reference
 * :func:`fps_batch`        -- the same for a ragged list of pieces in one launch (what assembly config 5 needs)
-* :func:`plane_split`      -- ``plane_split(points, z=None)`` (host RNG as in the reference, side test on the GPU)
+* :func:`plane_split`      -- ``plane_split(points, z=None)`` (host RNG as in the reference, partition by ``pz_plane_split``)
 * :func:`get_boundary`     -- ``CADDataset.get_boundary(fpc, de_mrpc)``
 * :class:`RandomTransformSE3` -- ``transforms.RandomTransformSE3``
 * :func:`make_pair`        -- ``CADDataset.getitem_non_random`` + ``MovedCADDataset2.__getitem__`` for one piece
@@ -97,9 +97,16 @@ def plane_split(points, z=None, device=None):
     if z is None:
         z = np.random.rand(1) / 3
     pts, was_numpy = _to_cuda(points, device)
-    nrm = torch.from_numpy(normal[:, 0]).to(pts.device)
-    dis = (pts[:, :3].double() * nrm).sum(1) + float(np.asarray(z).reshape(-1)[0])
-    up, down = pts[dis >= 0], pts[dis < 0]
+    pts = pts.contiguous().float()
+    n, C = pts.shape
+    up_buf, down_buf = torch.empty_like(pts), torch.empty_like(pts)
+    counts = torch.empty(2, device=pts.device, dtype=torch.int32)
+    with torch.cuda.device(pts.device):
+        _lib.call("pz_plane_split", pts.data_ptr(), n, C, float(normal[0, 0]), float(normal[1, 0]), float(normal[2, 0]),
+                  float(np.asarray(z).reshape(-1)[0]), up_buf.data_ptr(), down_buf.data_ptr(), counts.data_ptr(),
+                  _lib.stream_ptr())
+    n_up, n_down = counts.tolist()
+    up, down = up_buf[:n_up], down_buf[:n_down]
     if was_numpy:
         return up.cpu().numpy(), down.cpu().numpy()
     return up, down
