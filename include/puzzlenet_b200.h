@@ -111,11 +111,13 @@ int pz_group_concat_padded(const float* xyz, const float* feat_or_null, const fl
                            const int64_t* knn_idx, int B, int N, int D, int S, int K, int ld, float* new_points,
                            float* grouped_xyz_or_null, pz_stream_t stream);
 
-/* plane_split(points, z) -- dataset.py:761-775: order-preserving partition of one cloud pts [n,C] (xyz first) by the
- * sign of p . normal + z, evaluated in float64 like numpy; up (dis >= 0) and down (dis < 0) have room for n rows,
- * counts [2] (device) receives the two sizes.  The caller draws normal and z (np.random in the reference). */
-int pz_plane_split(const float* pts, int n, int C, double nx, double ny, double nz, double z, float* up, float* down,
-                   int32_t* counts, pz_stream_t stream);
+/* plane_split(points, z) -- dataset.py:761-775, batched: P clouds stored [P, n_stride, C] (xyz first; cloud i has
+ * sizes[i] valid rows, all n_stride when sizes is null) are each partitioned, order preserved, by the sign of
+ * p . normal_i + z_i evaluated in float64 like numpy; planes [P,4] = (normal, z) as doubles ON THE DEVICE (the caller
+ * draws them: np.random in the reference).  up (dis >= 0) / down (dis < 0) are [P, n_stride, C], counts [P,2].
+ * pad_tail != 0 fills the unused rows with copies of the half's first row (safe padding for pz_fps). */
+int pz_plane_split(const float* pts, const int32_t* sizes_or_null, int P, int n_stride, int C, const double* planes,
+                   float* up, float* down, int32_t* counts, int pad_tail, pz_stream_t stream);
 
 /* ------------------------------------------------------------ fused blocks */
 

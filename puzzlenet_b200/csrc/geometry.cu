@@ -436,14 +436,22 @@ __global__ void __launch_bounds__(256) group_concat_kernel(const float* __restri
 }
 
 // ------------------------------------------------------------------ plane_split (dataset.py:761-775)
-// Order-preserving two-way partition of one cloud by the sign of  p . normal + z  (evaluated in float64, as numpy does
-// for a float32 cloud and a float64 normal).  One CTA walks the cloud in chunks of 1024 points: ballot + warp counts +
-// a scan over the 32 warps give every point its slot in `up` (dis >= 0) or `down` (dis < 0).
-__global__ void __launch_bounds__(1024) plane_split_kernel(const float* __restrict__ pts, int n, int C, double nx,
-                                                           double ny, double nz, double z, float* __restrict__ up,
-                                                           float* __restrict__ down, int* __restrict__ counts) {
+// Order-preserving two-way partition of clouds by the sign of  p . normal + z  (evaluated in float64, as numpy does
+// for a float32 cloud and a float64 normal).  One CTA per cloud walks it in chunks of 1024 points: ballot + warp
+// counts + a scan over the 32 warps give every point its slot in `up` (dis >= 0) or `down` (dis < 0).  With
+// pad != 0 the unused tail rows of both outputs are filled with copies of their first row (FPS-safe padding).
+__global__ void __launch_bounds__(1024) plane_split_kernel(const float* __restrict__ pts_all, const int* __restrict__ sizes,
+                                                           int n_stride, int C, const double* __restrict__ planes,
+                                                           float* __restrict__ up_all, float* __restrict__ down_all,
+                                                           int* __restrict__ counts, int pad) {
   __shared__ int warp_up[32], warp_dn[32];
   __shared__ int base_up, base_dn;
+  const int piece = blockIdx.x;
+  const int n = sizes ? sizes[piece] : n_stride;
+  const float* pts = pts_all + (size_t)piece * n_stride * C;
+  float* up = up_all + (size_t)piece * n_stride * C;
+  float* down = down_all + (size_t)piece * n_stride * C;
+  const double nx = planes[piece * 4], ny = planes[piece * 4 + 1], nz = planes[piece * 4 + 2], z = planes[piece * 4 + 3];
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   if (t == 0) { base_up = 0; base_dn = 0; }
   __syncthreads();
@@ -475,7 +483,12 @@ __global__ void __launch_bounds__(1024) plane_split_kernel(const float* __restri
     }
     __syncthreads();
   }
-  if (t == 0) { counts[0] = base_up; counts[1] = base_dn; }
+  if (t == 0) { counts[piece * 2] = base_up; counts[piece * 2 + 1] = base_dn; }
+  if (pad) {
+    const int nu = base_up, nd = base_dn;
+    for (int e = nu * C + t; e < n_stride * C; e += 1024) up[e] = nu > 0 ? up[e % C] : 0.f;
+    for (int e = nd * C + t; e < n_stride * C; e += 1024) down[e] = nd > 0 ? down[e % C] : 0.f;
+  }
 }
 
 }  // namespace pz
@@ -483,11 +496,13 @@ __global__ void __launch_bounds__(1024) plane_split_kernel(const float* __restri
 // ------------------------------------------------------------------------- C ABI
 using namespace pz;
 
-extern "C" int pz_plane_split(const float* pts, int n, int C, double nx, double ny, double nz, double z, float* up,
-                              float* down, int32_t* counts, pz_stream_t stream) {
-  PZ_REQUIRE(n >= 0 && C >= 3, PZ_ERR_ARG, "pz_plane_split: need n >= 0 and at least 3 columns (got n=%d C=%d)", n, C);
-  PZ_REQUIRE(counts && (n == 0 || (pts && up && down)), PZ_ERR_ARG, "pz_plane_split: null pointer");
-  plane_split_kernel<<<1, 1024, 0, as_stream(stream)>>>(pts, n, C, nx, ny, nz, z, up, down, counts);
+extern "C" int pz_plane_split(const float* pts, const int32_t* sizes_or_null, int P, int n_stride, int C,
+                              const double* planes, float* up, float* down, int32_t* counts, int pad_tail,
+                              pz_stream_t stream) {
+  PZ_REQUIRE(P >= 0 && n_stride >= 0 && C >= 3, PZ_ERR_ARG, "pz_plane_split: need P, n >= 0 and at least 3 columns (C=%d)", C);
+  if (P == 0) return 0;
+  PZ_REQUIRE(planes && counts && (n_stride == 0 || (pts && up && down)), PZ_ERR_ARG, "pz_plane_split: null pointer");
+  plane_split_kernel<<<P, 1024, 0, as_stream(stream)>>>(pts, sizes_or_null, n_stride, C, planes, up, down, counts, pad_tail);
   PZ_LAUNCH_CHECK();
   return 0;
 }

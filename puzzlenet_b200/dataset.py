@@ -89,6 +89,17 @@ def fps_batch(pieces, npoints: int, starts=None, device=None) -> torch.Tensor:
     return torch.gather(xyz, 1, idx.unsqueeze(-1).expand(-1, -1, 3))
 
 
+def _split_device(pts, sizes, planes, pad):
+    """pz_plane_split on [P, nmax, C] clouds -> (up [P,nmax,C], down [P,nmax,C], counts [P,2] int32), all on the GPU"""
+    P, nmax, C = pts.shape
+    up, down = torch.empty_like(pts), torch.empty_like(pts)
+    counts = torch.empty(P, 2, device=pts.device, dtype=torch.int32)
+    with torch.cuda.device(pts.device):
+        _lib.call("pz_plane_split", pts.data_ptr(), None if sizes is None else sizes.data_ptr(), P, nmax, C,
+                  planes.data_ptr(), up.data_ptr(), down.data_ptr(), counts.data_ptr(), int(pad), _lib.stream_ptr())
+    return up, down, counts
+
+
 def plane_split(points, z=None, device=None):
     """dataset.py:761-775: cut with the plane ``points . normal + z = 0``, ``normal ~ U[0,1)^3`` and (unless given)
     ``z ~ U[0,1)/3`` from ``np.random`` in the reference's order -> (up, down), order preserved.  The signed
@@ -99,14 +110,11 @@ def plane_split(points, z=None, device=None):
     pts, was_numpy = _to_cuda(points, device)
     pts = pts.contiguous().float()
     n, C = pts.shape
-    up_buf, down_buf = torch.empty_like(pts), torch.empty_like(pts)
-    counts = torch.empty(2, device=pts.device, dtype=torch.int32)
-    with torch.cuda.device(pts.device):
-        _lib.call("pz_plane_split", pts.data_ptr(), n, C, float(normal[0, 0]), float(normal[1, 0]), float(normal[2, 0]),
-                  float(np.asarray(z).reshape(-1)[0]), up_buf.data_ptr(), down_buf.data_ptr(), counts.data_ptr(),
-                  _lib.stream_ptr())
-    n_up, n_down = counts.tolist()
-    up, down = up_buf[:n_up], down_buf[:n_down]
+    plane = torch.tensor([[normal[0, 0], normal[1, 0], normal[2, 0], float(np.asarray(z).reshape(-1)[0])]],
+                         dtype=torch.float64).to(pts.device)
+    up_buf, down_buf, counts = _split_device(pts.unsqueeze(0), None, plane, pad=False)
+    n_up, n_down = counts[0].tolist()
+    up, down = up_buf[0, :n_up], down_buf[0, :n_down]
     if was_numpy:
         return up.cpu().numpy(), down.cpu().numpy()
     return up, down
@@ -188,3 +196,79 @@ def make_pair(piece, rigid_transform: RandomTransformSE3, device=None, max_tries
     igt = rigid_transform.igt
     rigid_transform(rpcb)            # the reference also moves the boundary (and discards it), consuming one twist draw
     return down, mup, igt, up, fpcb, rpcb, fpc_idx, rpc_idx
+
+
+def make_pair_batch(pieces, mag: float = 0.8, device=None, max_tries: int = 100):
+    """``make_pair`` for a whole batch of raw pieces with a handful of launches instead of ~25 per sample:
+    one batched plane cut (re-drawn only for the pieces whose cut leaves fewer than 1024 points on a side), ONE FPS
+    launch for all 2P halves, one chamfer + two top-k launches for the boundaries, one ``se3.exp`` + one transform.
+    Returns the batched 8-tuple ``(down, mup, igt, up, downb, upb, fpc_idx, rpc_idx)`` = ``[P,1024,3]``,
+    ``[P,1024,3]``, ``[P,4,4]``, ``[P,1024,3]``, ``[P,128,3]``, ``[P,128,3]``, ``[P,1024]``, ``[P,1024]`` that
+    ``predict5`` / ``test_step`` / ``training_step`` take.
+
+    Random numbers come from the reference's generators but are drawn per STAGE, not per sample: first the cut of every
+    piece in order (``np.random.rand(3,1)``, ``np.random.rand(1)/3``; failed cuts are re-drawn afterwards, in piece
+    order, until they succeed), then the two FPS starts of every piece (``np.random.randint(0, n_up)``,
+    ``randint(0, n_down)``), then per piece the twist of ``mup`` and the discarded one of ``mupb`` (``torch.randn(1,6)``
+    twice).  Sample by sample the arithmetic is that of :func:`make_pair`."""
+    P = len(pieces)
+    if P == 0:
+        raise ValueError("make_pair_batch: empty list")
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    sizes_h = [int(p.shape[0]) for p in pieces]
+    nmax = max(sizes_h)
+    if nmax > MAX_FPS_POINTS:
+        raise ValueError(f"make_pair_batch: at most {MAX_FPS_POINTS} points per piece (got {nmax})")
+    host = torch.zeros(P, nmax, 3, dtype=torch.float32)
+    for i, p in enumerate(pieces):
+        host[i, :sizes_h[i]] = (p if isinstance(p, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(p)))[:, :3].float().cpu()
+    pts = host.to(device)
+    sizes = torch.tensor(sizes_h, dtype=torch.int32, device=device)
+
+    def draw_planes(k):
+        out = np.empty((k, 4))
+        for i in range(k):
+            out[i, :3] = np.random.rand(3, 1)[:, 0]
+            out[i, 3] = np.random.rand(1)[0] / 3
+        return out
+
+    planes_h = draw_planes(P)
+    up, down, counts = _split_device(pts, sizes, torch.from_numpy(planes_h).to(device), pad=True)
+    cnt = counts.cpu().numpy()
+    tries = 0
+    bad = np.nonzero((cnt < 1024).any(axis=1))[0]
+    while len(bad):
+        tries += 1
+        if tries > max_tries:
+            raise RuntimeError("make_pair_batch: no cut leaves 1024 points on both sides of a piece")
+        idx = torch.from_numpy(bad).to(device)
+        u2, d2, c2 = _split_device(pts[idx].contiguous(), sizes[idx].contiguous(),
+                                   torch.from_numpy(draw_planes(len(bad))).to(device), pad=True)
+        up[idx], down[idx] = u2, d2
+        cnt[bad] = c2.cpu().numpy()
+        bad = bad[(cnt[bad] < 1024).any(axis=1)]
+    starts = torch.tensor([[np.random.randint(0, int(cnt[i, 0])), np.random.randint(0, int(cnt[i, 1]))] for i in range(P)],
+                          dtype=torch.int64)
+    # one FPS launch over the 2P padded halves ([up_0, down_0, up_1, ...]); padding rows duplicate row 0 of the half
+    halves = torch.stack([up, down], dim=1).reshape(2 * P, nmax, 3)
+    idx = _fps_indices(halves, starts.reshape(-1).to(device), 1024)
+    sel = torch.gather(halves, 1, idx.unsqueeze(-1).expand(-1, -1, 3)).reshape(P, 2, 1024, 3)
+    up_s, down_s = sel[:, 0].contiguous(), sel[:, 1].contiguous()
+    # boundaries: get_boundary(fpc=down, de_mrpc=up) for every piece
+    cd1, cd2 = losses.chamfer_loss(down_s, up_s)              # cd1 per up point, cd2 per down point
+    _, top1 = losses.topk(cd1, 128, largest=False)
+    _, top2 = losses.topk(cd2, 128, largest=False)
+    upb = torch.gather(up_s, 1, top1.unsqueeze(-1).expand(-1, -1, 3))
+    downb = torch.gather(down_s, 1, top2.unsqueeze(-1).expand(-1, -1, 3))
+    fpc_idx = torch.zeros(P, 1024, device=device).scatter_(1, top2, 1.0)
+    rpc_idx = torch.zeros(P, 1024, device=device).scatter_(1, top1, 1.0)
+    # rigid motion of the `up` half: per piece one twist for mup and one (discarded) for the boundary
+    tw = torch.empty(P, 6)
+    for i in range(P):
+        x = torch.randn(1, 6)
+        tw[i] = (x / x.norm(p=2, dim=1, keepdim=True) * mag)[0]
+        torch.randn(1, 6)
+    igt = se3.exp(tw.to(device))
+    mup = losses.transform_points(igt, up_s)
+    return down_s, mup, igt, up_s, downb, upb, fpc_idx, rpc_idx

@@ -311,3 +311,54 @@ def test_make_pair_matches_oracle_pipeline():
     # the boundary points are rows of the sampled halves
     assert set(map(tuple, fpcb.cpu().numpy().tolist())) == set(map(tuple, down[fpc_idx.bool()].cpu().numpy().tolist()))
     assert set(map(tuple, rpcb.cpu().numpy().tolist())) == set(map(tuple, up[rpc_idx.bool()].cpu().numpy().tolist()))
+
+
+def test_make_pair_batch_matches_per_sample_pipeline():
+    """the batched dataset pipeline (one cut / FPS / chamfer / top-k / transform launch for P pieces) against the
+    oracle's per-sample pipeline fed with the same random draws in the documented stage order"""
+    from puzzlenet_b200 import dataset as D
+    g = torch.Generator().manual_seed(50)
+    pieces = [(torch.randn(n, 3, generator=g) * 0.3).numpy() for n in (6000, 4500, 7001)]
+    np.random.seed(60)
+    torch.manual_seed(61)
+    down, mup, igt, up, downb, upb, fpc_idx, rpc_idx = D.make_pair_batch(pieces, 0.8)
+    assert down.shape == (3, 1024, 3) and igt.shape == (3, 4, 4) and downb.shape == (3, 128, 3)
+    np.random.seed(60)
+    torch.manual_seed(61)
+    def cut(p):
+        nrm = np.random.rand(3, 1)
+        z = np.random.rand(1) / 3
+        dis = np.dot(p, nrm) + z
+        return p[(dis >= 0)[:, 0]], p[(dis < 0)[:, 0]]
+
+    halves = [cut(p) for p in pieces]                     # stage 1: every piece once, in order ...
+    bad = [i for i, (u, d) in enumerate(halves) if u.shape[0] < 1024 or d.shape[0] < 1024]
+    rounds = 0
+    while bad:                                            # ... then re-draws for the failed ones, in piece order
+        rounds += 1
+        for i in bad:
+            halves[i] = cut(pieces[i])
+        bad = [i for i in bad if halves[i][0].shape[0] < 1024 or halves[i][1].shape[0] < 1024]
+    assert rounds >= 1                                    # this seed exercises the re-draw path
+    starts = [(np.random.randint(0, u.shape[0]), np.random.randint(0, d.shape[0])) for u, d in halves]
+    for i, ((u, d), (su, sd)) in enumerate(zip(halves, starts)):
+        us, ds = po.dataset_fps(u, 1024, start=su), po.dataset_fps(d, 1024, start=sd)
+        np.testing.assert_array_equal(up[i].cpu().numpy(), us)
+        np.testing.assert_array_equal(down[i].cpu().numpy(), ds)
+        x = torch.randn(1, 6)
+        x = x / x.norm(p=2, dim=1, keepdim=True) * 0.8
+        torch.randn(1, 6)
+        gi = po.se3_exp(x)
+        np.testing.assert_allclose(igt[i].cpu().numpy(), gi[0].numpy(), atol=1e-6)
+        ref_mup = po.se3_transform(gi, torch.from_numpy(us).T[None])[0].T
+        np.testing.assert_allclose(mup[i].cpu().numpy(), ref_mup.numpy(), atol=1e-6)
+        fb, rb, fi, ri = po.get_boundary(torch.from_numpy(ds), torch.from_numpy(us))
+        cd1, cd2 = po.chamfer_loss(torch.from_numpy(ds)[None], torch.from_numpy(us)[None])
+        for got, ref, cd in ((fpc_idx[i], fi, cd2[0]), (rpc_idx[i], ri, cd1[0])):
+            gm, rm = got.cpu().numpy() > 0, ref.numpy() > 0
+            assert gm.sum() == 128
+            thr = np.sort(cd.numpy())[127]
+            for j in np.nonzero(gm ^ rm)[0]:
+                assert abs(cd[j].item() - thr) < 5e-7
+    # the tuple feeds the model directly
+    assert fpc_idx.sum().item() == 3 * 128 and torch.isfinite(mup).all()
