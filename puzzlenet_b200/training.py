@@ -80,7 +80,7 @@ def linear_fwd(x, ldx, M, lin, out, ldo, relu=False, W=None, K=None, tf32=False)
 
 
 def linear_bwd(dy, lddy, x, ldx, M, lin, gw, gb, dx=None, lddx=0, mask=None, ldmask=0, beta=0.0, W=None, K=None,
-               tf32=False):
+               tf32=False, bias_grad=True):
     """dW += dy^T x, db += colsum(dy); dx = (beta*dx +) dy W, gated by (mask > 0) when given.  ``W``/``K``: as in
     linear_fwd (``gw`` then has row stride K as well)."""
     N, K0 = lin.weight.shape
@@ -99,7 +99,8 @@ def linear_bwd(dy, lddy, x, ldx, M, lin, gw, gb, dx=None, lddx=0, mask=None, ldm
             gemm(dy, x, gw, N, K, M, ta=True, lda=lddy, ldb=ldx, ldc=K, splitk=sk)
         else:
             gemm(dy, x, gw, N, K, M, ta=True, lda=lddy, ldb=ldx, ldc=K, beta=1.0)
-    _lib.call("pz_colsum", _p(dy), lddy, M, N, 1.0, _p(gb), _st())
+    if bias_grad:
+        _lib.call("pz_colsum", _p(dy), lddy, M, N, 1.0, _p(gb), _st())
     if dx is not None:
         if tf32 and M % 128 == 0 and K % 64 == 0 and N % 32 == 0 and lddy % 4 == 0 and lddx % 4 == 0 \
                 and beta in (0.0, 1.0) and _al16(dy, W, dx, mask) and (mask is None or ldmask % 4 == 0):
@@ -362,7 +363,13 @@ class Trainer:
         # dcur = d loss / d f2f ;  sg2: max over neighbours <- relu(mlp6(relu(mlp5(g2))))
         db2, db1, dg2 = b("db2", R2, 256), b("db1", R2, 256), b("dg2", R2, c.kp2)
         _lib.call("pz_maxpool_backward", _p(dcur), _p(c.f2f_c), _p(c.arg2), T, KNN, 256, 1, _p(db2), _st())
-        linear_bwd(db2, 256, c.b1, 256, R2, enc.mlp6, G(enc.mlp6.weight), G(enc.mlp6.bias), db1, 256, mask=c.b1, ldmask=256, tf32=self.tf32)
+        # bias gradient of the pooled layer from the [groups, C] gradient (32x fewer rows than the scattered db2):
+        # sum_rows db2 = sum_groups (f2f > 0 ? dcur : 0)
+        gated = b("gated2", T, 256)
+        _lib.call("pz_relu_gate", T, 256, _p(dcur), 256, _p(c.f2f_c), 256, _p(gated), 256, _st())
+        _lib.call("pz_colsum", _p(gated), 256, T, 256, 1.0, _p(G(enc.mlp6.bias)), _st())
+        linear_bwd(db2, 256, c.b1, 256, R2, enc.mlp6, G(enc.mlp6.weight), G(enc.mlp6.bias), db1, 256, mask=c.b1, ldmask=256,
+                   tf32=self.tf32, bias_grad=False)
         gw5 = self._padded_grad(tag + ".gw5", enc.mlp5, c.kp2)
         linear_bwd(db1, 256, c.g2, c.kp2, R2, enc.mlp5, gw5, G(enc.mlp5.bias), dg2, c.kp2, W=c.w5p, K=c.kp2, tf32=self.tf32)
         self._unpad_grad(gw5, enc.mlp5, c.kp2)
@@ -372,7 +379,11 @@ class Trainer:
         # sg1
         da2, da1, dg1 = b("da2", R1, 128), b("da1", R1, 128), b("dg1", R1, c.kp1)
         _lib.call("pz_maxpool_backward", _p(df1f), _p(c.f1f), _p(c.arg1), B * S1, KNN, 128, 1, _p(da2), _st())
-        linear_bwd(da2, 128, c.a1, 128, R1, enc.mlp4, G(enc.mlp4.weight), G(enc.mlp4.bias), da1, 128, mask=c.a1, ldmask=128, tf32=self.tf32)
+        gated1 = b("gated1", B * S1, 128)
+        _lib.call("pz_relu_gate", B * S1, 128, _p(df1f), 128, _p(c.f1f), 128, _p(gated1), 128, _st())
+        _lib.call("pz_colsum", _p(gated1), 128, B * S1, 128, 1.0, _p(G(enc.mlp4.bias)), _st())
+        linear_bwd(da2, 128, c.a1, 128, R1, enc.mlp4, G(enc.mlp4.weight), G(enc.mlp4.bias), da1, 128, mask=c.a1, ldmask=128,
+                   tf32=self.tf32, bias_grad=False)
         gw3 = self._padded_grad(tag + ".gw3", enc.mlp3, c.kp1)
         linear_bwd(da1, 128, c.g1, c.kp1, R1, enc.mlp3, gw3, G(enc.mlp3.bias), dg1, c.kp1, W=c.w3p, K=c.kp1, tf32=self.tf32)
         self._unpad_grad(gw3, enc.mlp3, c.kp1)
