@@ -179,3 +179,131 @@ def group_mlp_maxpool(xyz, points, new_xyz, idx, w1, b1, w2, b2, precision=_lib.
                   w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), B, N, D, S, K, C1, C2, int(precision),
                   out.data_ptr(), ws.data_ptr(), ws_bytes, _lib.stream_ptr())
     return out
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# PointNet++ blocks of the reference (pointnet_util.py:159-315).  model5_b never instantiates them (SURVEY.md §2:
+# dead code on the live path); they are mirrored for API completeness (row F4) on the same kernels: FPS / kNN /
+# ball query / gathers for the geometry, pz_linear for every 1x1 convolution with its eval-mode BatchNorm folded in,
+# pz_maxpool_forward for the neighbourhood max.  Inference only: train-mode BatchNorm2d raises.
+# ----------------------------------------------------------------------------------------------------------------
+import torch.nn as nn  # noqa: E402
+
+
+def _folded_linear(conv, bn):
+    """1x1 conv (weight [O,I,1(,1)]) followed by eval-mode BatchNorm -> (W [O,I], b [O]) of the equivalent Linear."""
+    if bn.training:
+        raise NotImplementedError("puzzlenet_b200 PointNet++ blocks run in eval mode only (call .eval())")
+    w = conv.weight.detach().reshape(conv.weight.shape[0], -1).float()
+    b = conv.bias.detach().float() if conv.bias is not None else torch.zeros(w.shape[0], device=w.device)
+    scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+    return (w * scale[:, None]).contiguous(), ((b - bn.running_mean.detach().float()) * scale + bn.bias.detach().float()).contiguous()
+
+
+def _mlp_rows(x, convs, bns):
+    """relu(bn(conv(.))) for every layer on rows x [M, C] (the reference applies them as 1x1 convolutions)."""
+    M = x.shape[0]
+    for conv, bn in zip(convs, bns):
+        w, b = _folded_linear(conv, bn)
+        y = torch.empty(M, w.shape[0], device=x.device, dtype=torch.float32)
+        with torch.cuda.device(x.device):
+            _lib.call("pz_linear", x.data_ptr(), x.shape[1], w.data_ptr(), b.data_ptr(), M, w.shape[0], w.shape[1], 1,
+                      None, 0, y.data_ptr(), w.shape[0], _lib.PZ_PREC_FP32, _lib.stream_ptr())
+        x = y
+    return x
+
+
+def _max_over_neighbours(x, G, K):
+    """x [G*K, C] -> [G, C] = max over the K consecutive rows of a group"""
+    C = x.shape[1]
+    y = torch.empty(G, C, device=x.device, dtype=torch.float32)
+    arg = torch.empty(G, C, device=x.device, dtype=torch.int32)
+    with torch.cuda.device(x.device):
+        _lib.call("pz_maxpool_forward", x.data_ptr(), G, K, C, y.data_ptr(), arg.data_ptr(), _lib.stream_ptr())
+    return y
+
+
+class PointNetSetAbstraction(nn.Module):
+    """pointnet_util.py:159-197."""
+
+    def __init__(self, npoint, radius, nsample, in_channel, mlp, group_all, knn=False):
+        super().__init__()
+        self.npoint, self.radius, self.nsample, self.knn, self.group_all = npoint, radius, nsample, knn, group_all
+        self.mlp_convs, self.mlp_bns = nn.ModuleList(), nn.ModuleList()
+        last = in_channel
+        for out_channel in mlp:
+            self.mlp_convs.append(nn.Conv2d(last, out_channel, 1))
+            self.mlp_bns.append(nn.BatchNorm2d(out_channel))
+            last = out_channel
+
+    def forward(self, xyz, points):
+        if self.group_all:
+            new_xyz, new_points = sample_and_group_all(xyz, points)
+        else:
+            new_xyz, new_points = sample_and_group(self.npoint, self.radius, self.nsample, xyz, points, knn=self.knn)
+        B, S, K, C = new_points.shape
+        rows = _mlp_rows(_f32c(new_points, "new_points").reshape(B * S * K, C), self.mlp_convs, self.mlp_bns)
+        return new_xyz, _max_over_neighbours(rows, B * S, K).view(B, S, -1)
+
+
+class PointNetSetAbstractionMsg(nn.Module):
+    """pointnet_util.py:200-264 (multi-scale grouping; features first, then relative xyz)."""
+
+    def __init__(self, npoint, radius_list, nsample_list, in_channel, mlp_list, knn=False):
+        super().__init__()
+        self.npoint, self.radius_list, self.nsample_list, self.knn = npoint, radius_list, nsample_list, knn
+        self.conv_blocks, self.bn_blocks = nn.ModuleList(), nn.ModuleList()
+        for mlp in mlp_list:
+            convs, bns = nn.ModuleList(), nn.ModuleList()
+            last = in_channel + 3
+            for out_channel in mlp:
+                convs.append(nn.Conv2d(last, out_channel, 1))
+                bns.append(nn.BatchNorm2d(out_channel))
+                last = out_channel
+            self.conv_blocks.append(convs)
+            self.bn_blocks.append(bns)
+
+    def forward(self, xyz, points, seed_idx=None):
+        xyz = _f32c(xyz, "xyz")
+        B, N, C = xyz.shape
+        S = self.npoint
+        new_xyz = index_points(xyz, farthest_point_sample(xyz, S) if seed_idx is None else seed_idx)
+        outs = []
+        for i, radius in enumerate(self.radius_list):
+            K = self.nsample_list[i]
+            idx = knn_point(K, xyz, new_xyz) if self.knn else query_ball_point(radius, K, xyz, new_xyz)
+            grouped_xyz = index_points(xyz, idx) - new_xyz.view(B, S, 1, C)
+            grouped = grouped_xyz if points is None else torch.cat([index_points(_f32c(points, "points"), idx), grouped_xyz], dim=-1)
+            rows = _mlp_rows(grouped.reshape(B * S * K, -1).contiguous(), self.conv_blocks[i], self.bn_blocks[i])
+            outs.append(_max_over_neighbours(rows, B * S, K).view(B, S, -1))
+        return new_xyz, torch.cat(outs, dim=-1)
+
+
+class PointNetFeaturePropagation(nn.Module):
+    """pointnet_util.py:268-315 -- inverse-distance interpolation from the 3 nearest sampled points + an MLP.
+    Channel-first tensors ([B,C,N]) in and out, like the reference."""
+
+    def __init__(self, in_channel, mlp):
+        super().__init__()
+        self.mlp_convs, self.mlp_bns = nn.ModuleList(), nn.ModuleList()
+        last = in_channel
+        for out_channel in mlp:
+            self.mlp_convs.append(nn.Conv1d(last, out_channel, 1))
+            self.mlp_bns.append(nn.BatchNorm1d(out_channel))
+            last = out_channel
+
+    def forward(self, xyz1, xyz2, points1, points2):
+        xyz1, xyz2 = _f32c(xyz1.permute(0, 2, 1), "xyz1"), _f32c(xyz2.permute(0, 2, 1), "xyz2")
+        points2 = _f32c(points2.permute(0, 2, 1), "points2")
+        B, N, _ = xyz1.shape
+        S = xyz2.shape[1]
+        if S == 1:
+            interpolated = points2.repeat(1, N, 1)
+        else:
+            idx, d2 = knn_point(3, xyz2, xyz1, return_dist=True)            # the 3 nearest of xyz2 for every xyz1 point
+            recip = 1.0 / (d2 + 1e-8)
+            weight = recip / recip.sum(dim=2, keepdim=True)
+            interpolated = (index_points(points2, idx) * weight.view(B, N, 3, 1)).sum(dim=2)
+        new_points = interpolated if points1 is None else torch.cat([_f32c(points1.permute(0, 2, 1), "points1"), interpolated], dim=-1)
+        rows = _mlp_rows(new_points.reshape(B * N, -1).contiguous(), self.mlp_convs, self.mlp_bns)
+        return rows.view(B, N, -1).permute(0, 2, 1)

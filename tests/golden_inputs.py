@@ -51,3 +51,27 @@ def training_inputs(batch, se3_exp):
     fpc_idx = (torch.rand(batch, 1024, generator=g) < 0.125).float()
     rpc_idx = (torch.rand(batch, 1024, generator=g) < 0.125).float()
     return [fpc, mrpc, igt, rpc, fpcb, rpcb, fpc_idx, rpc_idx]
+
+
+def pointnet_block_inputs():
+    g = torch.Generator().manual_seed(17)
+    return torch.rand(2, 200, 3, generator=g) - 0.5, torch.randn(2, 200, 8, generator=g)
+
+
+def seed_block(module, seed):
+    """deterministic parameters + non-trivial BatchNorm running statistics for a PointNet++ block (either the
+    reference's class or the mirror: the state_dict keys are the same)"""
+    g = torch.Generator().manual_seed(1000 + seed)
+    with torch.no_grad():
+        for name, p in sorted(module.state_dict().items()):
+            if "num_batches_tracked" in name:
+                continue
+            if name.endswith("running_var"):
+                p.copy_(torch.rand(p.shape, generator=g) + 0.5)
+            elif name.endswith("running_mean") or name.endswith("bias"):
+                p.copy_(torch.randn(p.shape, generator=g) * 0.1)
+            elif name.endswith("weight") and p.dim() == 1:
+                p.copy_(torch.rand(p.shape, generator=g) + 0.5)
+            else:
+                p.copy_(torch.randn(p.shape, generator=g) * 0.3)
+    return module
