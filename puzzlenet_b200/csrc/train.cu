@@ -337,51 +337,87 @@ __global__ void __launch_bounds__(256) bn_point_bwd_kernel(const float* __restri
 }
 
 // =============================================================================== max-pool with arg-max
-// x [G, K, C] -> y [G, C] = max_k, arg [G, C] = first maximising k
-__global__ void __launch_bounds__(256) maxpool_fwd_kernel(const float* __restrict__ x, long long G, int K, int C,
+// x [G, K, C] -> y [G, C] = max_k, arg [G, C] = first maximising k.  Both directions are pure streaming (the
+// backward writes 537 MB per set-abstraction layer at 64 pairs): one CTA per group, every thread owns 4 consecutive
+// channels (128-bit accesses) and a subset of the K rows; no per-element index division.
+template <int VEC>
+__global__ void __launch_bounds__(256) maxpool_fwd_kernel(const float* __restrict__ x, int K, int C,
                                                           float* __restrict__ y, int* __restrict__ arg) {
-  const long long e = (long long)blockIdx.x * 256 + threadIdx.x;
-  if (e >= G * C) return;
-  const long long g = e / C;
-  const int c = (int)(e - g * C);
-  const float* px = x + g * K * C + c;
-  float best = px[0];
-  int bi = 0;
-  for (int k = 1; k < K; ++k) {
-    const float v = px[(long long)k * C];
-    if (v > best) { best = v; bi = k; }
+  const long long g = blockIdx.x;
+  const float* px = x + g * (long long)K * C;
+  for (int c = threadIdx.x * VEC; c < C; c += blockDim.x * VEC) {      // blockDim = min(256, C / VEC) rounded to a warp
+    float best[VEC];
+    int bi[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) { best[v] = -INFINITY; bi[v] = 0; }
+    for (int k = 0; k < K; ++k) {
+      float val[VEC];
+      if (VEC == 4) {
+        const float4 t = *reinterpret_cast<const float4*>(px + (long long)k * C + c);
+        val[0] = t.x; val[1] = t.y; val[2] = t.z; val[3] = t.w;
+      } else {
+        val[0] = px[(long long)k * C + c];
+      }
+#pragma unroll
+      for (int v = 0; v < VEC; ++v)
+        if (val[v] > best[v] || k == 0) { best[v] = val[v]; bi[v] = k; }
+    }
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      y[g * C + c + v] = best[v];
+      arg[g * C + c + v] = bi[v];
+    }
   }
-  y[e] = best;
-  arg[e] = bi;
 }
 // dx [G, K, C] = (k == arg && (!relu_gate || y > 0)) ? dy : 0   (relu_gate: x was a ReLU output, dx is w.r.t. its input)
+template <int VEC>
 __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y,
-                                                          const int* __restrict__ arg, long long G, int K, int C,
-                                                          int relu_gate, float* __restrict__ dx) {
-  const long long e = (long long)blockIdx.x * 256 + threadIdx.x;
-  if (e >= G * K * C) return;
-  const int c = (int)(e % C);
-  const long long gk = e / C;
-  const int k = (int)(gk % K);
-  const long long g = gk / K;
-  const long long o = g * C + c;
-  float v = 0.f;
-  if (arg[o] == k && (!relu_gate || y[o] > 0.f)) v = dy[o];
-  dx[e] = v;
+                                                          const int* __restrict__ arg, int K, int C, int relu_gate,
+                                                          float* __restrict__ dx) {
+  const long long g = blockIdx.x;
+  const int cols = C / VEC;                       // column groups per row
+  const int c = (threadIdx.x % cols) * VEC;       // this thread's channels (cols <= 256 is checked by the launcher
+  const int k0 = threadIdx.x / cols;              //  for VEC == 4; the scalar variant loops over column groups)
+  const int kstep = 256 / cols;
+  if (VEC == 4) {
+    if (threadIdx.x >= cols * kstep) return;
+    const float4 d4 = *reinterpret_cast<const float4*>(dy + g * C + c);
+    const float4 y4 = *reinterpret_cast<const float4*>(y + g * C + c);
+    const int4 a4 = *reinterpret_cast<const int4*>(arg + g * C + c);
+    const float d[4] = {(!relu_gate || y4.x > 0.f) ? d4.x : 0.f, (!relu_gate || y4.y > 0.f) ? d4.y : 0.f,
+                        (!relu_gate || y4.z > 0.f) ? d4.z : 0.f, (!relu_gate || y4.w > 0.f) ? d4.w : 0.f};
+    float* px = dx + g * (long long)K * C + c;
+    for (int k = k0; k < K; k += kstep)
+      *reinterpret_cast<float4*>(px + (long long)k * C) =
+          make_float4(a4.x == k ? d[0] : 0.f, a4.y == k ? d[1] : 0.f, a4.z == k ? d[2] : 0.f, a4.w == k ? d[3] : 0.f);
+  } else {
+    for (int cc = threadIdx.x; cc < C; cc += 256) {
+      const long long o = g * C + cc;
+      const float d = (!relu_gate || y[o] > 0.f) ? dy[o] : 0.f;
+      const int a = arg[o];
+      float* px = dx + g * (long long)K * C + cc;
+      for (int k = 0; k < K; ++k) px[(long long)k * C] = a == k ? d : 0.f;
+    }
+  }
 }
 
 // =============================================================================== index_points backward
-// dst[(m / per_cloud) * N + idx[m], 0:C] += src[m*ld + c0 : c0+C]
+// dst[(m / per_cloud) * N + idx[m], 0:C] += src[m*ld + c0 : c0+C];  one warp per source row (coalesced reads, atomics to
+// consecutive addresses), zero entries skipped (the gradient of a max-pooled layer is mostly zeros)
 __global__ void __launch_bounds__(256) scatter_add_rows_kernel(const float* __restrict__ src, long long ld, int c0, int C,
                                                                const int64_t* __restrict__ idx, long long M,
                                                                long long per_cloud, int N, float* __restrict__ dst,
                                                                long long ldd) {
-  const long long e = (long long)blockIdx.x * 256 + threadIdx.x;
-  if (e >= M * C) return;
-  const long long m = e / C;
-  const int c = (int)(e - m * C);
-  const float v = src[m * ld + c0 + c];
-  if (v != 0.f) atomicAdd(dst + ((m / per_cloud) * N + idx[m]) * ldd + c, v);
+  const int lane = threadIdx.x & 31;
+  const long long warps = (long long)gridDim.x * 8;
+  for (long long m = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); m < M; m += warps) {
+    const float* ps = src + m * ld + c0;
+    float* pd = dst + ((m / per_cloud) * N + idx[m]) * ldd;
+    for (int c = lane; c < C; c += 32) {
+      const float v = ps[c];
+      if (v != 0.f) atomicAdd(pd + c, v);
+    }
+  }
 }
 
 // =============================================================================== softmax forward
@@ -718,7 +754,12 @@ extern "C" int pz_maxpool_forward(const float* x, long long G, int K, int C, flo
   PZ_REQUIRE(G >= 0 && K >= 1 && C >= 1, PZ_ERR_ARG, "pz_maxpool_forward: bad size");
   if (G == 0) return PZ_OK;
   PZ_REQUIRE(x && y && arg, PZ_ERR_ARG, "pz_maxpool_forward: null pointer");
-  maxpool_fwd_kernel<<<(unsigned)((G * C + 255) / 256), 256, 0, as_stream(stream)>>>(x, G, K, C, y, arg);
+  PZ_REQUIRE(G <= 2147483647LL, PZ_ERR_UNSUPPORTED, "pz_maxpool_forward: too many groups");
+  const bool vec = C % 4 == 0 && ((uintptr_t)x & 15) == 0;
+  int threads = ((vec ? C / 4 : C) + 31) / 32 * 32;
+  if (threads > 256) threads = 256;
+  if (vec) maxpool_fwd_kernel<4><<<(unsigned)G, threads, 0, as_stream(stream)>>>(x, K, C, y, arg);
+  else maxpool_fwd_kernel<1><<<(unsigned)G, threads, 0, as_stream(stream)>>>(x, K, C, y, arg);
   PZ_LAUNCH_CHECK();
   return PZ_OK;
 }
@@ -728,9 +769,11 @@ extern "C" int pz_maxpool_backward(const float* dy, const float* y, const int32_
   PZ_REQUIRE(G >= 0 && K >= 1 && C >= 1, PZ_ERR_ARG, "pz_maxpool_backward: bad size");
   if (G == 0) return PZ_OK;
   PZ_REQUIRE(dy && y && arg && dx, PZ_ERR_ARG, "pz_maxpool_backward: null pointer");
-  const long long n = G * K * C;
-  PZ_REQUIRE((n + 255) / 256 <= 2147483647LL, PZ_ERR_UNSUPPORTED, "pz_maxpool_backward: too many elements");
-  maxpool_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(dy, y, arg, G, K, C, relu_gate, dx);
+  PZ_REQUIRE(G <= 2147483647LL, PZ_ERR_UNSUPPORTED, "pz_maxpool_backward: too many groups");
+  const bool vec = C % 4 == 0 && C / 4 <= 256 && 256 % (C / 4) == 0 && ((uintptr_t)dy & 15) == 0 && ((uintptr_t)y & 15) == 0 &&
+                   ((uintptr_t)arg & 15) == 0 && ((uintptr_t)dx & 15) == 0;
+  if (vec) maxpool_bwd_kernel<4><<<(unsigned)G, 256, 0, as_stream(stream)>>>(dy, y, arg, K, C, relu_gate, dx);
+  else maxpool_bwd_kernel<1><<<(unsigned)G, 256, 0, as_stream(stream)>>>(dy, y, arg, K, C, relu_gate, dx);
   PZ_LAUNCH_CHECK();
   return PZ_OK;
 }
@@ -740,10 +783,9 @@ extern "C" int pz_scatter_add_rows(const float* src, long long ld, int c0, int C
   PZ_REQUIRE(M >= 0 && C >= 0, PZ_ERR_ARG, "pz_scatter_add_rows: negative size");
   if (M == 0 || C == 0) return PZ_OK;
   PZ_REQUIRE(src && idx && dst && per_cloud >= 1 && N >= 1, PZ_ERR_ARG, "pz_scatter_add_rows: bad argument");
-  const long long n = M * C;
-  PZ_REQUIRE((n + 255) / 256 <= 2147483647LL, PZ_ERR_UNSUPPORTED, "pz_scatter_add_rows: too many elements");
-  scatter_add_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(src, ld, c0, C, idx, M, per_cloud,
-                                                                                      N, dst, ldd);
+  const long long want = (M + 7) / 8;
+  const unsigned blocks = (unsigned)(want < 32LL * kNumSMs ? want : 32LL * kNumSMs);
+  scatter_add_rows_kernel<<<blocks, 256, 0, as_stream(stream)>>>(src, ld, c0, C, idx, M, per_cloud, N, dst, ldd);
   PZ_LAUNCH_CHECK();
   return PZ_OK;
 }
