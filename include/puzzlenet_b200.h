@@ -313,6 +313,15 @@ int pz_gemm_tf32_batched(int a_mn_major, int b_mn_major, int M, int N, int K, co
                          const float* B, long long ldb, float* C, long long ldc, int batch, long long strideA,
                          long long strideB, long long strideC, int splitk, const float* bias_or_null, int relu,
                          const float* mask_or_null, long long ldmask, int accumulate, pz_stream_t stream);
+/* Layer 1 of a grouped MLP without the [B,S,K,3+D] tensor (model5_b.py:449-452 with pointnet_util.py:123-130):
+ * W1 [xyz_j - c_s ; f_j] + b1 = P_j - Q_s with P [clouds*N, C] per source point and Q [groups, C] per centroid, so
+ *   out[r,:] = relu(P[cloud*N + idx[r], :] - Q[r / K, :]),  r = (cloud*S + s)*K + k,  groups = clouds*S,
+ * and its backward for a gradient d [groups*K, C] w.r.t. the pre-activation (already ReLU-gated):
+ *   dP[cloud*N + idx[r], :] += d[r,:]  (dP is accumulated into),  dQ[g,:] = -sum_k d[g*K + k, :]  (overwritten). */
+int pz_gather_sub_relu(const float* P, const float* Q, const int64_t* idx, long long groups, int K, int S, int N, int C,
+                       float* out, pz_stream_t stream);
+int pz_group_scatter_grad(const float* d, const int64_t* idx, long long groups, int K, int S, int N, int C, float* dP,
+                          float* dQ, pz_stream_t stream);
 /* softmax(scale * S) over the last dimension of S [rows, L] (model5_b.py:70-72 forward). */
 int pz_softmax_forward(const float* S, long long rows, int L, float scale, float* A, pz_stream_t stream);
 /* out[n] = beta*out[n] + sum_m x[m*ld + n]  (bias gradients). */

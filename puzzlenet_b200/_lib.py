@@ -96,6 +96,10 @@ SIGNATURES = {
     "pz_gemm_tf32_batched": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_f32p, C.c_longlong, c_f32p,
                                        C.c_longlong, c_f32p, C.c_longlong, C.c_int, C.c_longlong, C.c_longlong,
                                        C.c_longlong, C.c_int, c_f32p, C.c_int, c_f32p, C.c_longlong, C.c_int, c_stream]),
+    "pz_gather_sub_relu": (C.c_int, [c_f32p, c_f32p, c_i64p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, c_f32p,
+                                     c_stream]),
+    "pz_group_scatter_grad": (C.c_int, [c_f32p, c_i64p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, c_f32p, c_f32p,
+                                        c_stream]),
     "pz_softmax_forward": (C.c_int, [c_f32p, C.c_longlong, C.c_int, C.c_float, c_f32p, c_stream]),
     "pz_colsum": (C.c_int, [c_f32p, C.c_longlong, C.c_longlong, C.c_int, C.c_float, c_f32p, c_stream]),
     "pz_axpby": (C.c_int, [C.c_longlong, C.c_int, C.c_float, c_f32p, C.c_longlong, C.c_float, c_f32p, C.c_longlong,

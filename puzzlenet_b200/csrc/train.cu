@@ -420,6 +420,55 @@ __global__ void __launch_bounds__(256) scatter_add_rows_kernel(const float* __re
   }
 }
 
+// =============================================================================== grouped layer 1 without [G*K, 3+D]
+// Layer 1 of a grouped MLP splits as  W1 [xyz_j - c_s ; f_j] + b1 = P_j - Q_s  with P (per SOURCE point) and Q (per
+// centroid) computed by small GEMMs; the grouped activation is then a gather:
+//   out[r, :] = relu(P[cloud*N + idx[r], :] - Q[r / K, :]),   r = (cloud*S + s)*K + k.   One warp per row.
+__global__ void __launch_bounds__(256) gather_sub_relu_kernel(const float* __restrict__ P, const float* __restrict__ Q,
+                                                              const int64_t* __restrict__ idx, long long rows, int K,
+                                                              int S, int N, int C, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long warps = (long long)gridDim.x * 8;
+  for (long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); r < rows; r += warps) {
+    const long long g = r / K;
+    const float* p = P + ((g / S) * N + idx[r]) * C;
+    const float* q = Q + g * C;
+    float* o = out + r * C;
+    for (int c = lane * 4; c < C; c += 128) {
+      const float4 a = *reinterpret_cast<const float4*>(p + c), b = *reinterpret_cast<const float4*>(q + c);
+      *reinterpret_cast<float4*>(o + c) =
+          make_float4(fmaxf(a.x - b.x, 0.f), fmaxf(a.y - b.y, 0.f), fmaxf(a.z - b.z, 0.f), fmaxf(a.w - b.w, 0.f));
+    }
+  }
+}
+// backward of the gather above for d = gradient w.r.t. the PRE-activation (already ReLU-gated):
+//   dP[cloud*N + idx[r], :] += d[r, :] (atomics, zeros skipped),   dQ[g, :] = -sum_k d[g*K + k, :].  One warp per group.
+__global__ void __launch_bounds__(256) group_scatter_grad_kernel(const float* __restrict__ d, const int64_t* __restrict__ idx,
+                                                                 long long groups, int K, int S, int N, int C,
+                                                                 float* __restrict__ dP, float* __restrict__ dQ) {
+  const int lane = threadIdx.x & 31;
+  const long long warps = (long long)gridDim.x * 8;
+  for (long long g = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); g < groups; g += warps) {
+    const long long base = (g / S) * N;
+    for (int c = lane * 4; c < C; c += 128) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int k = 0; k < K; ++k) {
+        const long long r = g * K + k;
+        const float4 v = *reinterpret_cast<const float4*>(d + r * C + c);
+        if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) {
+          float* t = dP + (base + idx[r]) * C + c;
+          if (v.x != 0.f) atomicAdd(t, v.x);
+          if (v.y != 0.f) atomicAdd(t + 1, v.y);
+          if (v.z != 0.f) atomicAdd(t + 2, v.z);
+          if (v.w != 0.f) atomicAdd(t + 3, v.w);
+          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+      }
+      *reinterpret_cast<float4*>(dQ + g * C + c) = make_float4(-acc.x, -acc.y, -acc.z, -acc.w);
+    }
+  }
+}
+
 // =============================================================================== softmax forward
 // A[r,:] = softmax(scale * S[r,:]);  one warp per row (exp of the shifted logits, as torch.softmax evaluates it)
 __global__ void __launch_bounds__(256) softmax_fwd_kernel(const float* __restrict__ S, long long rows, int L, float scale,
@@ -786,6 +835,34 @@ extern "C" int pz_scatter_add_rows(const float* src, long long ld, int c0, int C
   const long long want = (M + 7) / 8;
   const unsigned blocks = (unsigned)(want < 32LL * kNumSMs ? want : 32LL * kNumSMs);
   scatter_add_rows_kernel<<<blocks, 256, 0, as_stream(stream)>>>(src, ld, c0, C, idx, M, per_cloud, N, dst, ldd);
+  PZ_LAUNCH_CHECK();
+  return PZ_OK;
+}
+
+extern "C" int pz_gather_sub_relu(const float* P, const float* Q, const int64_t* idx, long long groups, int K, int S, int N,
+                                  int C, float* out, pz_stream_t stream) {
+  PZ_REQUIRE(groups >= 0 && K >= 1 && S >= 1 && N >= 1, PZ_ERR_ARG, "pz_gather_sub_relu: bad size");
+  if (groups == 0) return PZ_OK;
+  PZ_REQUIRE(P && Q && idx && out, PZ_ERR_ARG, "pz_gather_sub_relu: null pointer");
+  PZ_REQUIRE(C >= 4 && C % 4 == 0 && ((uintptr_t)P & 15) == 0 && ((uintptr_t)Q & 15) == 0 && ((uintptr_t)out & 15) == 0,
+             PZ_ERR_UNSUPPORTED, "pz_gather_sub_relu: C must be a multiple of 4 and the tensors 16-byte aligned");
+  const long long rows = groups * K, want = (rows + 7) / 8;
+  const unsigned blocks = (unsigned)(want < 64LL * kNumSMs ? want : 64LL * kNumSMs);
+  gather_sub_relu_kernel<<<blocks, 256, 0, as_stream(stream)>>>(P, Q, idx, rows, K, S, N, C, out);
+  PZ_LAUNCH_CHECK();
+  return PZ_OK;
+}
+
+extern "C" int pz_group_scatter_grad(const float* d, const int64_t* idx, long long groups, int K, int S, int N, int C,
+                                     float* dP, float* dQ, pz_stream_t stream) {
+  PZ_REQUIRE(groups >= 0 && K >= 1 && S >= 1 && N >= 1, PZ_ERR_ARG, "pz_group_scatter_grad: bad size");
+  if (groups == 0) return PZ_OK;
+  PZ_REQUIRE(d && idx && dP && dQ, PZ_ERR_ARG, "pz_group_scatter_grad: null pointer");
+  PZ_REQUIRE(C >= 4 && C % 4 == 0 && ((uintptr_t)d & 15) == 0 && ((uintptr_t)dQ & 15) == 0, PZ_ERR_UNSUPPORTED,
+             "pz_group_scatter_grad: C must be a multiple of 4 and the tensors 16-byte aligned");
+  const long long want = (groups + 7) / 8;
+  const unsigned blocks = (unsigned)(want < 64LL * kNumSMs ? want : 64LL * kNumSMs);
+  group_scatter_grad_kernel<<<blocks, 256, 0, as_stream(stream)>>>(d, idx, groups, K, S, N, C, dP, dQ);
   PZ_LAUNCH_CHECK();
   return PZ_OK;
 }

@@ -88,7 +88,7 @@ def linear_bwd(dy, lddy, x, ldx, M, lin, gw, gb, dx=None, lddx=0, mask=None, ldm
     K = K0 if K is None else K
     if tf32 and N % 128 == 0 and K % 64 == 0 and M % 32 == 0 and M >= 4096 and lddy % 4 == 0 and ldx % 4 == 0 \
             and _al16(dy, x, gw):
-        tiles = (N // 128) * (K // (256 if K % 256 == 0 else 128))
+        tiles = (N // 128) * (K // (256 if K % 256 == 0 else 128 if K % 128 == 0 else 64))
         kblocks = M // 32
         sk = max(2, min(max(kblocks // 8, 1), -(-2 * 148 // tiles)))
         _gemm_tf32(1, 1, N, K, M, dy, lddy, x, ldx, gw, K, splitk=sk)
@@ -163,6 +163,13 @@ class _EncoderCtx:
     pass
 
 
+class _LinView:
+    """the (weight, bias) pair linear_fwd / linear_bwd read, for a weight that is a copy of a column block"""
+
+    def __init__(self, weight, bias):
+        self.weight, self.bias = weight, bias
+
+
 def all_reduce_bucket(flat: torch.Tensor, lo: int, hi: int, async_op: bool = True):
     """Sum ``flat[lo:hi]`` over the ranks of the default process group (NCCL on GPUs, gloo in the CPU tests).
     Returns the work handle (``None`` outside a process group)."""
@@ -207,31 +214,41 @@ class Trainer:
             self._buf[name] = t
         return t
 
-    def _padded_weight(self, name, lin, kpad):
-        """lin.weight [N, K] as a zero-padded [N, kpad] copy refreshed every step (the weight itself when kpad == K)"""
-        N, K = lin.weight.shape
-        if kpad == K:
-            return lin.weight
-        w = self._buf.get(name)
-        if w is None:
-            w = torch.zeros(N, kpad, device=self.dev, dtype=torch.float32)
-            self._buf[name] = w
-        axpby(N, K, 1.0, lin.weight, K, 0.0, None, 0, w, kpad)
-        return w
+    # -------------------------------------------------------------------------------------------- grouped layer 1
+    def _group_layer1_forward(self, tag, lin, xyz, feat, D, centres, idx, B, N, S, out):
+        """relu(lin([xyz_j - c_s ; feat_j])) for every (group, neighbour) WITHOUT the [B,S,K,3+D] tensor:
+        W [xyz_j - c_s ; f_j] + b = P_j - Q_s  with  P = feat W_f^T + xyz W_x^T + b  per source point and
+        Q = centres W_x^T per group (two small GEMMs), then one gather kernel writes relu(P_j - Q_s).
+        Returns what the backward needs."""
+        C1 = lin.weight.shape[0]
+        wx, wf = self.buf(tag + ".wx", C1, 3), self.buf(tag + ".wf", C1, D)
+        axpby(C1, 3, 1.0, lin.weight, 3 + D, 0.0, None, 0, wx, 3)                     # W[:, 0:3]
+        axpby(C1, D, 1.0, lin.weight[:, 3:], 3 + D, 0.0, None, 0, wf, D)              # W[:, 3:]
+        lin_f = _LinView(wf, lin.bias)
+        P, Q = self.buf(tag + ".P", B * N, C1), self.buf(tag + ".Q", B * S, C1)
+        linear_fwd(feat, D, B * N, lin_f, P, C1, tf32=self.tf32)
+        gemm(xyz, wx, P, B * N, C1, 3, tb=True, lda=3, ldb=3, ldc=C1, beta=1.0)
+        gemm(centres, wx, Q, B * S, C1, 3, tb=True, lda=3, ldb=3, ldc=C1)
+        _lib.call("pz_gather_sub_relu", _p(P), _p(Q), _p(idx), B * S, KNN, S, N, C1, _p(out), _st())
+        return dict(lin=lin, lin_f=lin_f, wx=wx, xyz=xyz, feat=feat, D=D, centres=centres, idx=idx, N=N, S=S, C1=C1)
 
-    def _padded_grad(self, name, lin, kpad):
-        N, K = lin.weight.shape
-        if kpad == K:
-            return self.flat.g(lin.weight)
-        g = self.buf(name, N, kpad)
-        g.zero_()
-        return g
-
-    def _unpad_grad(self, g, lin, kpad):
-        N, K = lin.weight.shape
-        if kpad != K:       # added (not copied): a shared encoder back-propagates twice per step
-            gw = self.flat.g(lin.weight)
-            axpby(N, K, 1.0, g, kpad, 1.0, gw, K, gw, K)
+    def _group_layer1_backward(self, tag, st, B, d_pre, dfeat):
+        """d_pre [B*S*K, C1] = gradient w.r.t. the layer's pre-activation (ReLU-gated).  Adds the weight / bias
+        gradients of ``lin`` and accumulates d loss / d feat into ``dfeat`` [B*N, D]."""
+        G, lin, C1, D, N, S = self.flat.g, st["lin"], st["C1"], st["D"], st["N"], st["S"]
+        dP, dQ = self.buf(tag + ".dP", B * N, C1), self.buf(tag + ".dQ", B * S, C1)
+        dP.zero_()
+        _lib.call("pz_group_scatter_grad", _p(d_pre), _p(st["idx"]), B * S, KNN, S, N, C1, _p(dP), _p(dQ), _st())
+        gwf, gwx = self.buf(tag + ".gwf", C1, D), self.buf(tag + ".gwx", C1, 3)
+        gwf.zero_()
+        gwx.zero_()
+        # P = feat W_f^T + b + xyz W_x^T :  dW_f, db, dfeat from dP;  dW_x = dP^T xyz + dQ^T centres
+        linear_bwd(dP, C1, st["feat"], D, B * N, st["lin_f"], gwf, G(lin.bias), dfeat, D, beta=1.0, tf32=self.tf32)
+        gemm(dP, st["xyz"], gwx, C1, 3, B * N, ta=True, lda=C1, ldb=3, ldc=3, splitk=_splitk(B * N, 1))
+        gemm(dQ, st["centres"], gwx, C1, 3, B * S, ta=True, lda=C1, ldb=3, ldc=3, splitk=max(2, _splitk(B * S, 1)))
+        gw = G(lin.weight)                                                            # [C1, 3 + D]: add both column blocks
+        axpby(C1, 3, 1.0, gwx, 3, 1.0, gw, 3 + D, gw, 3 + D)
+        axpby(C1, D, 1.0, gwf, D, 1.0, gw[:, 3:], 3 + D, gw[:, 3:], 3 + D)
 
     # -------------------------------------------------------------------------------------------- encoder
     def _encoder_forward(self, tag, enc, xyz, start1, start2):
@@ -256,14 +273,8 @@ class Trainer:
         _lib.call("pz_fps", _p(xyz), B, NPTS, _p(start1), S1, _p(c.fps1), _p(c.x1), _st())
         _lib.call("pz_knn", _p(c.x1), _p(xyz), B, S1, NPTS, KNN, _p(c.knn1), None, _st())
         R1 = B * S1 * KNN
-        # tf32: the grouped rows (3+64 / 3+128 wide) are zero-padded to 128 / 256 columns so that layer 1 and its
-        # weight gradient can run on the tensor cores (K % 32 == 0, wgrad N % 128 == 0)
-        c.kp1, c.kp2 = (128, 256) if self.precision == "tf32" else (67, 131)
-        c.w3p, c.w5p = self._padded_weight(tag + ".w3p", enc.mlp3, c.kp1), self._padded_weight(tag + ".w5p", enc.mlp5, c.kp2)
-        c.g1, c.a1, c.a2 = b("g1", R1, c.kp1), b("a1", R1, 128), b("a2", R1, 128)
-        _lib.call("pz_group_concat_padded", _p(xyz), _p(c.xf), _p(c.x1), _p(c.knn1), B, NPTS, 64, S1, KNN, c.kp1,
-                  _p(c.g1), None, _st())
-        linear_fwd(c.g1, c.kp1, R1, enc.mlp3, c.a1, 128, relu=True, W=c.w3p, K=c.kp1, tf32=self.tf32)
+        c.a1, c.a2 = b("a1", R1, 128), b("a2", R1, 128)
+        c.sg1 = self._group_layer1_forward(tag + ".sg1", enc.mlp3, xyz, c.xf, 64, c.x1, c.knn1, B, NPTS, S1, c.a1)
         linear_fwd(c.a1, 128, R1, enc.mlp4, c.a2, 128, relu=True, tf32=self.tf32)
         c.f1f, c.arg1 = b("f1f", B * S1, 128), b("arg1", B * S1, 128, dtype=torch.int32)
         _lib.call("pz_maxpool_forward", _p(c.a2), B * S1, KNN, 128, _p(c.f1f), _p(c.arg1), _st())
@@ -273,10 +284,8 @@ class Trainer:
         _lib.call("pz_fps", _p(c.x1), B, S1, _p(start2), S2, _p(c.fps2), _p(c.x2), _st())
         _lib.call("pz_knn", _p(c.x2), _p(c.x1), B, S2, S1, KNN, _p(c.knn2), None, _st())
         R2 = B * S2 * KNN
-        c.g2, c.b1, c.b2 = b("g2", R2, c.kp2), b("b1", R2, 256), b("b2", R2, 256)
-        _lib.call("pz_group_concat_padded", _p(c.x1), _p(c.f1f), _p(c.x2), _p(c.knn2), B, S1, 128, S2, KNN, c.kp2,
-                  _p(c.g2), None, _st())
-        linear_fwd(c.g2, c.kp2, R2, enc.mlp5, c.b1, 256, relu=True, W=c.w5p, K=c.kp2, tf32=self.tf32)
+        c.b1, c.b2 = b("b1", R2, 256), b("b2", R2, 256)
+        c.sg2 = self._group_layer1_forward(tag + ".sg2", enc.mlp5, c.x1, c.f1f, 128, c.x2, c.knn2, B, S1, S2, c.b1)
         linear_fwd(c.b1, 256, R2, enc.mlp6, c.b2, 256, relu=True, tf32=self.tf32)
         T = B * S2
         c.cat = b("cat", T, 1280)                   # [att1 | att2 | att3 | att4 | f2f]  (model5_b.py:467, :472)
@@ -361,7 +370,7 @@ class Trainer:
             src = dcat[:, 1024:] if l == 0 else dcat[:, (l - 1) * 256:]
             axpby(T, 256, 1.0, dcur, 256, 1.0, src, 1280, dcur, 256)
         # dcur = d loss / d f2f ;  sg2: max over neighbours <- relu(mlp6(relu(mlp5(g2))))
-        db2, db1, dg2 = b("db2", R2, 256), b("db1", R2, 256), b("dg2", R2, c.kp2)
+        db2, db1 = b("db2", R2, 256), b("db1", R2, 256)
         _lib.call("pz_maxpool_backward", _p(dcur), _p(c.f2f_c), _p(c.arg2), T, KNN, 256, 1, _p(db2), _st())
         # bias gradient of the pooled layer from the [groups, C] gradient (32x fewer rows than the scattered db2):
         # sum_rows db2 = sum_groups (f2f > 0 ? dcur : 0)
@@ -370,24 +379,18 @@ class Trainer:
         _lib.call("pz_colsum", _p(gated), 256, T, 256, 1.0, _p(G(enc.mlp6.bias)), _st())
         linear_bwd(db2, 256, c.b1, 256, R2, enc.mlp6, G(enc.mlp6.weight), G(enc.mlp6.bias), db1, 256, mask=c.b1, ldmask=256,
                    tf32=self.tf32, bias_grad=False)
-        gw5 = self._padded_grad(tag + ".gw5", enc.mlp5, c.kp2)
-        linear_bwd(db1, 256, c.g2, c.kp2, R2, enc.mlp5, gw5, G(enc.mlp5.bias), dg2, c.kp2, W=c.w5p, K=c.kp2, tf32=self.tf32)
-        self._unpad_grad(gw5, enc.mlp5, c.kp2)
         df1f = b("df1f", B * S1, 128)
         df1f.zero_()
-        _lib.call("pz_scatter_add_rows", _p(dg2), c.kp2, 3, 128, _p(c.knn2), R2, S2 * KNN, S1, _p(df1f), 128, _st())
+        self._group_layer1_backward(tag + ".sg2", c.sg2, B, db1, df1f)
         # sg1
-        da2, da1, dg1 = b("da2", R1, 128), b("da1", R1, 128), b("dg1", R1, c.kp1)
+        da2, da1 = b("da2", R1, 128), b("da1", R1, 128)
         _lib.call("pz_maxpool_backward", _p(df1f), _p(c.f1f), _p(c.arg1), B * S1, KNN, 128, 1, _p(da2), _st())
         gated1 = b("gated1", B * S1, 128)
         _lib.call("pz_relu_gate", B * S1, 128, _p(df1f), 128, _p(c.f1f), 128, _p(gated1), 128, _st())
         _lib.call("pz_colsum", _p(gated1), 128, B * S1, 128, 1.0, _p(G(enc.mlp4.bias)), _st())
         linear_bwd(da2, 128, c.a1, 128, R1, enc.mlp4, G(enc.mlp4.weight), G(enc.mlp4.bias), da1, 128, mask=c.a1, ldmask=128,
                    tf32=self.tf32, bias_grad=False)
-        gw3 = self._padded_grad(tag + ".gw3", enc.mlp3, c.kp1)
-        linear_bwd(da1, 128, c.g1, c.kp1, R1, enc.mlp3, gw3, G(enc.mlp3.bias), dg1, c.kp1, W=c.w3p, K=c.kp1, tf32=self.tf32)
-        self._unpad_grad(gw3, enc.mlp3, c.kp1)
-        _lib.call("pz_scatter_add_rows", _p(dg1), c.kp1, 3, 64, _p(c.knn1), R1, S1 * KNN, NPTS, _p(dxf), 64, _st())
+        self._group_layer1_backward(tag + ".sg1", c.sg1, B, da1, dxf)
         # stem
         dh2, dy1, dh1 = b("dh2", R0, 64), b("dy1", R0, 64), b("dh1", R0, 64)
         _lib.call("pz_bn_point_train_backward", _p(c.h2), _p(c.xf), _p(dxf), B, NPTS, 64, _p(enc.bn2.weight), _p(c.bn[2]),
