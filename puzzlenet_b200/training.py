@@ -718,6 +718,21 @@ class Trainer:
             getattr(self.model, attr, {}).clear()
         return lr
 
+    # -------------------------------------------------------------------------------------------- checkpoint / resume
+    def state_dict(self):
+        """Optimizer state for checkpoint / resume (the model's own ``state_dict()`` holds the parameters -- they are
+        views of the flat buffer, so nothing else is needed): Adam moments, step count, base learning rate."""
+        return {"step": self.step_count, "lr0": self.lr0, "precision": self.precision, "n": self.flat.n,
+                "exp_avg": self.flat.exp_avg.detach().clone(), "exp_avg_sq": self.flat.exp_avg_sq.detach().clone()}
+
+    def load_state_dict(self, sd):
+        if int(sd["n"]) != self.flat.n:
+            raise ValueError(f"optimizer state holds {sd['n']} elements, this model's flat buffer {self.flat.n}")
+        self.step_count = int(sd["step"])
+        self.lr0 = float(sd["lr0"])
+        self.flat.exp_avg.copy_(sd["exp_avg"])
+        self.flat.exp_avg_sq.copy_(sd["exp_avg_sq"])
+
     def training_step(self, batch, starts=None, pretrain: bool = False) -> Dict[str, float]:
         terms = self.forward_backward_pretrain(batch, starts) if pretrain else self.forward_backward(batch, starts)
         world = self.all_reduce_grads()

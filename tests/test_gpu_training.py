@@ -384,3 +384,30 @@ def test_gemm_tf32_batched_and_softmax_forward():
     from puzzlenet_b200 import _lib
     _lib.call("pz_softmax_forward", Sd.data_ptr(), Bt * L, L, 0.125, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
     np.testing.assert_allclose(out.cpu().numpy(), torch.softmax(S * 0.125, -1).numpy(), rtol=1e-5, atol=1e-7)
+
+
+def test_checkpoint_resume_continues_the_run():
+    """model.state_dict() + Trainer.state_dict() after 2 steps, loaded into a fresh model / trainer, continue with
+    the same third step as the uninterrupted run (same learning rate and step count, loss to 2e-5)."""
+    from puzzlenet_b200.training import Trainer
+    batch = [t.to(DEV) for t in training_inputs(2, po.se3_exp)]
+    st = _starts(2)
+    a = _fresh_model()
+    ta = Trainer(a, lr=1e-5)
+    for _ in range(2):
+        ta.training_step(batch, starts=st)
+    ck_model = {k: v.detach().clone() for k, v in a.state_dict().items()}
+    ck_opt = ta.state_dict()
+    ref = ta.training_step(batch, starts=st)
+    b = _fresh_model()
+    b.load_state_dict(ck_model)
+    tb = Trainer(b, lr=123.0)                  # wrong lr on purpose: the checkpoint restores it
+    tb.load_state_dict(ck_opt)
+    got = tb.training_step(batch, starts=st)
+    assert got["lr"] == ref["lr"] and tb.step_count == 3
+    np.testing.assert_allclose(got["loss"], ref["loss"], rtol=2e-5)      # split-K atomics in the pose-MLP forward
+    # Adam normalises every gradient entry by its own magnitude: entries whose gradient is pure fp32-atomics noise
+    # (|g| ~ 1e-12) still move by up to +-lr, in a direction the summation order decides -> atol = 2 lr
+    np.testing.assert_allclose(tb.flat.params.cpu().numpy(), ta.flat.params.cpu().numpy(), rtol=1e-5, atol=2e-5)
+    for name in ("Encoder.bn1.running_mean", "Encoder2.bn2.running_var"):
+        np.testing.assert_allclose(b.state_dict()[name].cpu().numpy(), a.state_dict()[name].cpu().numpy(), rtol=1e-6)
