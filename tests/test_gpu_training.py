@@ -350,15 +350,16 @@ def test_gemm_tf32_weights_resident_mode(a_mn, b_mn, N, K):
     Bd = (B.T.contiguous() if b_mn else B).to(DEV)
     st = torch.cuda.current_stream().cuda_stream
     C = torch.empty(M, N, device=DEV)
+    bias_d = bias.to(DEV)
     _lib.call("pz_gemm_tf32", a_mn, b_mn, M, N, K, Ad.data_ptr(), Ad.shape[1], Bd.data_ptr(), Bd.shape[1], C.data_ptr(), N,
-              1, bias.to(DEV).data_ptr(), 1, None, 0, 0, st)
+              1, bias_d.data_ptr(), 1, None, 0, 0, st)
     ref = torch.relu(A.double() @ B.double().T + bias.double())
     bound = (A.abs().double() @ B.abs().double().T) * 2.0 ** -10 + 1e-6
     assert ((C.cpu().double() - ref).abs() <= bound).all()
     C2 = torch.zeros(M, N, device=DEV)
     _lib.call("pz_gemm_tf32", a_mn, b_mn, M, N, K, Ad.data_ptr(), Ad.shape[1], Bd.data_ptr(), Bd.shape[1], C2.data_ptr(), N,
               2, None, 0, None, 0, 0, st)
-    want = torch.relu(C2 + bias.to(DEV))
+    want = torch.relu(C2 + bias_d)
     assert (C - want).abs().max().item() <= 2e-3 * want.abs().max().item()
 
 
