@@ -105,12 +105,6 @@ int pz_group_concat(const float* xyz, const float* feat_or_null, const float* ne
                     const int64_t* knn_idx, int B, int N, int D, int S, int K, float* new_points,
                     float* grouped_xyz_or_null, pz_stream_t stream);
 
-/* the same with a caller-chosen row stride ld >= 3+D for new_points; columns [3+D, ld) are zero-filled (operand
- * padding for the tensor-core training GEMMs, whose K must be a multiple of 32). */
-int pz_group_concat_padded(const float* xyz, const float* feat_or_null, const float* new_xyz,
-                           const int64_t* knn_idx, int B, int N, int D, int S, int K, int ld, float* new_points,
-                           float* grouped_xyz_or_null, pz_stream_t stream);
-
 /* plane_split(points, z) -- dataset.py:761-775, batched: P clouds stored [P, n_stride, C] (xyz first; cloud i has
  * sizes[i] valid rows, all n_stride when sizes is null) are each partitioned, order preserved, by the sign of
  * p . normal_i + z_i evaluated in float64 like numpy; planes [P,4] = (normal, z) as doubles ON THE DEVICE (the caller

@@ -57,8 +57,6 @@ SIGNATURES = {
     "pz_gather": (C.c_int, [C.c_void_p, c_i64p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, c_stream]),
     "pz_group_concat": (C.c_int, [c_f32p, c_f32p, c_f32p, c_i64p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                   c_f32p, c_f32p, c_stream]),
-    "pz_group_concat_padded": (C.c_int, [c_f32p, c_f32p, c_f32p, c_i64p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
-                                         C.c_int, c_f32p, c_f32p, c_stream]),
     "pz_plane_split": (C.c_int, [c_f32p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, c_f32p, c_f32p, C.c_void_p,
                                  C.c_int, c_stream]),
     "pz_group_mlp_workspace_bytes": (C.c_size_t, [C.c_int] * 7),

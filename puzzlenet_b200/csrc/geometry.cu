@@ -571,15 +571,8 @@ extern "C" int pz_gather(const void* pts, const int64_t* idx, int B, int N, int 
 extern "C" int pz_group_concat(const float* xyz, const float* feat_or_null, const float* new_xyz,
                                const int64_t* knn_idx, int B, int N, int D, int S, int K,
                                float* new_points, float* grouped_xyz_or_null, pz_stream_t stream) {
-  return pz_group_concat_padded(xyz, feat_or_null, new_xyz, knn_idx, B, N, D, S, K, 3 + D, new_points,
-                                grouped_xyz_or_null, stream);
-}
-
-extern "C" int pz_group_concat_padded(const float* xyz, const float* feat_or_null, const float* new_xyz,
-                                      const int64_t* knn_idx, int B, int N, int D, int S, int K, int ld,
-                                      float* new_points, float* grouped_xyz_or_null, pz_stream_t stream) {
   PZ_REQUIRE(B >= 0 && N >= 1 && D >= 0 && S >= 0 && K >= 1, PZ_ERR_ARG, "pz_group_concat: bad sizes");
-  PZ_REQUIRE(ld >= 3 + D, PZ_ERR_ARG, "pz_group_concat: row stride %d < 3 + D", ld);
+  const int ld = 3 + D;
   size_t rows = (size_t)B * S * K;
   if (rows == 0) return 0;
   PZ_REQUIRE(xyz && new_xyz && knn_idx && new_points, PZ_ERR_ARG, "pz_group_concat: null pointer");

@@ -89,5 +89,4 @@ def test_argument_errors_of_loss_and_training_entry_points():
     assert lib.pz_maxpool_forward(one, 2, 0, 4, one, one, None) == -1
     assert lib.pz_cross_entropy(one, one, 0, 8, 0, 1.0, one, None, None) == -1
     assert lib.pz_adam_step(one, one, one, one, 8, 1e-3, 0.9, 0.999, 1e-8, 0, 1.0, None) == -1      # step >= 1
-    assert lib.pz_group_concat_padded(one, one, one, one, 1, 8, 4, 2, 2, 5, one, None, None) == -1  # ld < 3 + D
     assert lib.pz_pose_grad(one, one, None, 8, None, 0.0, 2, 0.0, one, None) == -1                  # pts without dpts
