@@ -2,14 +2,33 @@
 //   q|k = x Wqk^T + b,  v = x Wv^T + b,  A = softmax(q k^T / sqrt(64)),  r = x - A v,  out = x + relu(r Wo^T + bo)
 // for L = 256 tokens, C = 256 channels, d_k = 64 (bf16 operands, fp32 accumulation in TMEM).
 // Nothing but x (in) and out (written into its 256-column slice of att_cat) touches HBM: q, k, v^T, P and r live
-// in shared memory as K-major SWIZZLE_128B MMA operands; the weights stream through a 2-stage ring of
-// [128 x 64] tiles.  Replaces 4 launches per layer (q|k GEMM, v^T GEMM, attention core, out-proj GEMM).
+// in shared memory as K-major SWIZZLE_128B MMA operands.  x enters through TMA tensor loads ([128 tok x 64 ch] boxes,
+// SWIZZLE_128B) three times -- as the projections' operand, then again straight into the slots where r and the output
+// tile are formed in place (the residuals) -- and the output leaves through TMA tensor stores: a thread owns a token
+// row (its TMEM lane), so direct global accesses would touch 32 cache lines per warp instruction.
 //
-// Shared memory (224 KB of operands):  R_A 128 KB: x [256 tok x 256 ch] as 4 k-blocks, later v^T [256 ch x 256 tok];
-//                                      R_B  64 KB: q,k tiles -> P (per query block) -> r (per query block);
-//                                      R_W  32 KB: weight-tile ring.
-// TMEM (512 columns): q|k accumulators (2 x 128) -> v^T (2 x 256) -> S (2 x 256) -> O (in place) -> out (in place).
-// Epilogue mappings follow the operand they produce: thread = token row for q|k, S, O, out; thread = channel for v^T.
+// Warp-specialised: warps 0-7 are the epilogue group (TMEM -> registers -> shared-memory operands / global output),
+// warp 8 lane 0 is the weight producer, warp 9 lane 0 issues every MMA.  The three roles only meet through
+// single-use mbarriers (one cloud per CTA, so every barrier completes exactly once: parity 0 everywhere):
+//   full[t]  weight tile t has landed (bulk-copy complete_tx)     cons[t]  the MMAs reading tile t have completed
+//   c_*      tcgen05.commit of an MMA phase (accumulator ready, operands dead)
+//   g_*      256 epilogue arrivals: operand written to shared memory and the accumulator columns drained
+// so the q|k epilogue runs under the v^T MMAs, weight tiles stream under epilogues, and no phase starts with a cold
+// weight ring.
+//
+// Weights arrive as pre-swizzled 16 KB tile images ([128 rows x 64 k] bf16, SWIZZLE_128B byte order, written once by
+// the weight pack): one cp.async.bulk per tile, 20 tiles per layer:
+//   t 0-3   Wqk  k-block t          (B operand of phase 1)      -> slots B0-B3 (R_B is idle until q|k are written)
+//   t 4-11  Wv   (ch block, k-block) (A operand of phase 2)      -> ring W0/W1
+//   t 12-19 Wo   (ch half, k-block)  (B operand of the out-projection, streamed ONCE for both query blocks)
+//                                                                -> W0/W1, and A4-A7 once v^T is dead
+// Shared memory, 14 slots of 16 KB:  R_A = A0-A7: x [256 tok x 256 ch] as 4 k-blocks -> v^T [256 ch x 256 tok]
+//                                          -> r of query block 1 (A0-A3) + Wo tiles (A4-A7);
+//                                    R_B = B0-B3: Wqk tiles -> q,k -> P0 -> P1 -> r of query block 0;   R_W = W0,W1.
+// TMEM (512 columns): q|k [0,256) | v^T ch 0-127 [256,512) -> v^T ch 128-255 [0,256) -> S0 [0,256) S1 [256,512)
+//                     -> O in place -> out in place.
+#include <cuda.h>   // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint)
+
 #include "pz_common.cuh"
 #include "tc_common.cuh"
 
@@ -19,39 +38,19 @@ using namespace tc;
 
 namespace {
 constexpr int FL = 256, FC = 256, FDK = 64;
-constexpr uint32_t RA_BYTES = 4 * 256 * 128, RB_BYTES = 64 * 1024, WTILE = 128 * 128, RW_BYTES = 2 * WTILE;
-constexpr int FT = 256;  // threads
+constexpr uint32_t SLOT = 128 * 128;                       // one [128 x 64] bf16 tile
+constexpr uint32_t RA_BYTES = 8 * SLOT, RB_BYTES = 4 * SLOT, RW_BYTES = 2 * SLOT;
+constexpr int NEPI = 256, FT = 320;                        // epilogue threads, all threads
+constexpr int NTILES = 20;
 
-// stream T weight tiles ([128 rows x 64 k], row stride ld elements) through the 2-stage ring; tile t's MMAs are
-// issued by thread 0 once the tile has landed, and free the stage through wbar when they complete
-template <class SrcFn, class MmaFn>
-__device__ __forceinline__ void stream_phase(int T, int ld, SrcFn src, MmaFn mma, uint32_t rw, uint32_t wbar,
-                                             uint32_t (&wuse)[2], int tid) {
-  for (int t = 0; t <= T; ++t) {
-    if (t < T) {
-      const int st = t & 1;
-      if (wuse[st] > 0) mbar_wait(wbar + 8 * st, (wuse[st] - 1) & 1);   // the stage's previous tile has been consumed
-      const __nv_bfloat16* wp = src(t);
-      for (int id = tid; id < 128 * 8; id += FT) {
-        const int r = id >> 3, c = id & 7;
-        cp_async16(rw + st * WTILE + sw128(r, c), wp + (size_t)r * ld + c * 8);
-      }
-      cp_async_commit();
-    }
-    if (t >= 1) {
-      if (t < T) cp_async_wait<1>(); else cp_async_wait<0>();
-      fence_proxy_async();
-      __syncthreads();
-      const int st = (t - 1) & 1;
-      if (tid == 0) {
-        tc_fence_after();
-        mma(t - 1, rw + st * WTILE);
-        umma_commit(wbar + 8 * st);
-      }
-      ++wuse[st];
-    }
-  }
-}
+// barrier indices (8 bytes each)
+constexpr int B_FULL = 0, B_CONS = NTILES, B_C = 2 * NTILES;            // c_qk c_v c_s c_pv0 c_pv1 c_out
+constexpr int C_QK = B_C, C_V = B_C + 1, C_S = B_C + 2, C_PV0 = B_C + 3, C_PV1 = B_C + 4, C_OUT = B_C + 5;
+constexpr int F_X = B_C + 6;                                            // 4: x k-block landed (TMA), + x for r, x for out
+constexpr int F_XR = F_X + 4, F_XO = F_X + 5;
+constexpr int G_QK = F_X + 6, G_V = G_QK + 1, G_P0 = G_QK + 2, G_R = G_QK + 4;   // G_P1 = G_P0 + 1
+constexpr int NBARS = G_R + 1;
+constexpr uint32_t MISC_BYTES = 1024 /*xch*/ + 512 /*q|k bias*/ + NBARS * 8 + 16;
 
 __device__ __forceinline__ uint4 pack8(const float* v) {
   uint4 o;
@@ -61,224 +60,345 @@ __device__ __forceinline__ uint4 pack8(const float* v) {
   o.z = *reinterpret_cast<uint32_t*>(&h2); o.w = *reinterpret_cast<uint32_t*>(&h3);
   return o;
 }
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// pz_profile_attention_timeline: CTA 0 stamps %globaltimer-free SM clocks at its phase boundaries
+__device__ __forceinline__ void stamp(long long* prof, int slot) {
+  if (prof != nullptr && blockIdx.x == 0) prof[slot] = clock64();
+}
+__device__ __forceinline__ void expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// one [128 rows x 64 ch] bf16 box at (column c0, row c1) <-> a 16 KB SWIZZLE_128B slot
+__device__ __forceinline__ void tma_load(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store(const CUtensorMap* tm, int c0, int c1, uint32_t src) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(NEPI) : "memory"); }
 }  // namespace
 
-__global__ void __launch_bounds__(FT, 1) attention_layer_tc_kernel(const AttnLayerTc p) {
+__global__ void __launch_bounds__(FT, 1) attention_layer_tc_kernel(const AttnLayerTc p,
+                                                                   const __grid_constant__ CUtensorMap tmx,
+                                                                   const __grid_constant__ CUtensorMap tmy) {
   extern __shared__ __align__(1024) uint8_t fl_smem_raw[];
   const uint32_t base = (smem_u32(fl_smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = fl_smem_raw + (base - smem_u32(fl_smem_raw));
   const uint32_t ra = base, rb = ra + RA_BYTES, rw = rb + RB_BYTES;
-  const uint32_t tab_s = rw + RW_BYTES, inv_s = tab_s + 1024, wbar = inv_s + 512, dbar = wbar + 16, tmem_slot = dbar + 8;
-  float* tab = reinterpret_cast<float*>(gen + (tab_s - base));
-  float* invs = reinterpret_cast<float*>(gen + (inv_s - base));
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, quarter = warp & 3, half = warp >> 2;
+  const uint32_t xch_s = rw + RW_BYTES, tab_s = xch_s + 1024, bars = tab_s + 512, tmem_slot = bars + NBARS * 8;
+  float* xch = reinterpret_cast<float*>(gen + (xch_s - base));   // [2 halves][128 rows]
+  float* tab = reinterpret_cast<float*>(gen + (tab_s - base));   // q|k bias
+  auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cloud = blockIdx.x, set = cloud / p.clouds_per_set;
   const size_t row0 = (size_t)cloud * FL;
-  const __nv_bfloat16* __restrict__ wqkv = p.wqkv[set];
-  const __nv_bfloat16* __restrict__ wo = p.wo[set];
-  const float* __restrict__ bqkv = p.bqkv[set];
-  const float* __restrict__ bo = p.bo[set];
+  stamp(tid == 0 ? p.prof : nullptr, 15);
 
-  // ---- x -> R_A (4 k-blocks of [256 tokens x 64 ch])
-  for (int id = tid; id < 256 * 32; id += FT) {
-    const int row = id >> 5, c32 = id & 31, kb = c32 >> 3, c = c32 & 7;
-    cp_async16(ra + kb * (256 * 128) + sw128(row, c), p.x + (row0 + row) * p.ldx + kb * 64 + c * 8);
-  }
-  cp_async_commit();
-  if (tid < 128) tab[tid] = bqkv[tid];
-  if (tid == 0) {
-    mbar_init(wbar, 1);
-    mbar_init(wbar + 8, 1);
-    mbar_init(dbar, 1);
+  auto slot_of = [&](int t) -> uint32_t {
+    if (t < 4) return rb + t * SLOT;
+    if (t >= 14 && t < 18) return ra + (4 + t - 14) * SLOT;
+    return rw + (t & 1) * SLOT;
+  };
+  const uint8_t* wimg = reinterpret_cast<const uint8_t*>(p.wimg[set]);
+  auto load_w = [&](int t) { bulk_load(slot_of(t), wimg + (size_t)t * SLOT, SLOT, bar(B_FULL + t)); };
+
+  if (tid < 128) tab[tid] = p.bqkv[set][tid];
+  if (tid == NEPI) {
+    // the producer thread initialises the barriers and starts the first loads before anyone else needs them:
+    // x -> R_A (4 k-blocks of [256 tokens x 64 ch] = 2 boxes each), Wqk -> B0-B3, the first two Wv tiles -> W0/W1
+    for (int i = 0; i < NBARS; ++i) mbar_init(bar(i), i >= G_QK ? NEPI : 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_proxy_async();
+    for (int kb = 0; kb < 4; ++kb) {
+      expect_tx(bar(F_X + kb), 2 * SLOT);
+      tma_load(ra + kb * (2 * SLOT), &tmx, kb * 64, (int)row0, bar(F_X + kb));
+      tma_load(ra + kb * (2 * SLOT) + SLOT, &tmx, kb * 64, (int)row0 + 128, bar(F_X + kb));
+      load_w(kb);
+    }
+    load_w(4);
+    load_w(5);
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  cp_async_wait<0>();
-  fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
-  const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
-  uint32_t wuse[2] = {0u, 0u};
-  uint32_t dphase = 0;
-  auto all_mma_done = [&]() {   // thread 0 has issued every MMA of the phase: wait for their completion
-    if (tid == 0) umma_commit(dbar);
-    mbar_wait(dbar, dphase);
-    dphase ^= 1;
-    tc_fence_after();
-  };
 
-  // ================= phase 1: q|k[tok, 0:128] = x Wqk^T   (rows on lanes; two 128-token blocks; N = 128)
-  {
-    const uint32_t idesc = make_idesc(128);
-    stream_phase(4, FC, [&](int t) { return wqkv + t * 64; },
-                 [&](int t, uint32_t wt) {
-                   const uint64_t bd = make_desc(wt);
-#pragma unroll
-                   for (int blk = 0; blk < 2; ++blk) {
-                     const uint64_t ad = make_desc(ra + t * (256 * 128) + blk * (128 * 128));
-#pragma unroll
-                     for (int k4 = 0; k4 < 4; ++k4) umma_bf16(tmem + blk * 128, ad + 2 * k4, bd + 2 * k4, idesc, (t | k4) != 0);
-                   }
-                 },
-                 rw, wbar, wuse, tid);
-    all_mma_done();
-    // epilogue: warp half h owns token block h; q -> R_B[0:32K) as [256 x 64], k -> R_B[32K:64K)
-    const int row = half * 128 + quarter * 32 + lane;
-#pragma unroll 1
-    for (int c32 = 0; c32 < 4; ++c32) {
-      float v[32];
-      tmem_ld32(tmem + lane_base + half * 128 + c32 * 32, v);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] += tab[c32 * 32 + i];
-      uint8_t* dst = gen + (rb - base) + (c32 >> 1) * (256 * 128);
-#pragma unroll
-      for (int q4 = 0; q4 < 4; ++q4) *reinterpret_cast<uint4*>(dst + sw128(row, (c32 & 1) * 4 + q4)) = pack8(v + q4 * 8);
+  if (warp == 8) {
+    // ================= weight producer
+    if (lane == 0) {
+      for (int t = 6; t < 14; ++t) {
+        mbar_wait(bar(B_CONS + t - 2), 0);
+        load_w(t);
+      }
+      // P and v^T are dead: x comes back into the slots where r is formed in place (block 0 in R_B, block 1 in
+      // A0-A3), and the upper half of R_A takes four Wo tiles
+      auto load_x_blocks = [&](int b) {
+        expect_tx(bar(b), 8 * SLOT);
+        for (int kb = 0; kb < 4; ++kb) {
+          tma_load(rb + kb * SLOT, &tmx, kb * 64, (int)row0, bar(b));
+          tma_load(ra + kb * SLOT, &tmx, kb * 64, (int)row0 + 128, bar(b));
+        }
+      };
+      mbar_wait(bar(C_PV1), 0);
+      load_x_blocks(F_XR);
+      for (int t = 14; t < 18; ++t) load_w(t);
+      for (int t = 18; t < 20; ++t) {
+        mbar_wait(bar(B_CONS + t - 6), 0);
+        load_w(t);
+      }
+      mbar_wait(bar(C_OUT), 0);   // r is dead: x once more, for the output residual
+      load_x_blocks(F_XO);
     }
-    tc_fence_before();
-    __syncthreads();   // q|k accumulators drained
-    tc_fence_after();
-  }
-
-  // ================= phase 2: v^T[ch, tok] = Wv x^T   (channels on lanes; two 128-channel blocks; N = 256 tokens)
-  {
-    const uint32_t idesc = make_idesc(256);
-    stream_phase(8, FC, [&](int t) { return wqkv + (size_t)(128 + (t >> 2) * 128) * FC + (t & 3) * 64; },
-                 [&](int t, uint32_t wt) {
-                   const int chb = t >> 2, kb = t & 3;
-                   const uint64_t ad = make_desc(wt), bd = make_desc(ra + kb * (256 * 128));
+    __syncwarp();
+  } else if (warp == 9) {
+    // ================= MMA issuer
+    if (lane == 0) {
+      const uint32_t id128 = make_idesc(128), id256 = make_idesc(256);
+      stamp(p.prof, 32);
+      // phase 1: q|k[tok, 0:128] = x Wqk^T   (rows on lanes; two 128-token blocks; N = 128) -> cols [0,256)
+      for (int t = 0; t < 4; ++t) {
+        mbar_wait(bar(F_X + t), 0);
+        mbar_wait(bar(B_FULL + t), 0);
+        tc_fence_after();
+        const uint64_t bd = make_desc(slot_of(t));
 #pragma unroll
-                   for (int k4 = 0; k4 < 4; ++k4) umma_bf16(tmem + chb * 256, ad + 2 * k4, bd + 2 * k4, idesc, (kb | k4) != 0);
-                 },
-                 rw, wbar, wuse, tid);
-    all_mma_done();   // x in R_A is dead from here on: v^T takes its place
-    const int ch = half * 128 + quarter * 32 + lane;
-    const float bv = bqkv[128 + ch];
-#pragma unroll 1
-    for (int c32 = 0; c32 < 8; ++c32) {
-      float v[32];
-      tmem_ld32(tmem + lane_base + half * 256 + c32 * 32, v);
+        for (int blk = 0; blk < 2; ++blk) {
+          const uint64_t ad = make_desc(ra + t * (2 * SLOT) + blk * SLOT);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] += bv;
-      uint8_t* dst = gen + (ra - base) + (c32 >> 1) * (256 * 128);
+          for (int k4 = 0; k4 < 4; ++k4) umma_bf16(tmem + blk * 128, ad + 2 * k4, bd + 2 * k4, id128, (t | k4) != 0);
+        }
+      }
+      umma_commit(bar(C_QK));
+      stamp(p.prof, 33);
+      // phase 2: v^T[ch, tok] = Wv x^T  (channels on lanes; N = 256 tokens): ch block 0 -> cols [256,512),
+      // ch block 1 -> cols [0,256) once the q|k accumulators are drained
+      for (int j = 0; j < 8; ++j) {
+        const int t = 4 + j, chb = j >> 2, kb = j & 3;
+        if (j == 4) {
+          stamp(p.prof, 34);
+          mbar_wait(bar(G_QK), 0);
+          tc_fence_after();
+          stamp(p.prof, 35);
+        }
+        mbar_wait(bar(B_FULL + t), 0);
+        tc_fence_after();
+        const uint64_t ad = make_desc(slot_of(t)), bd = make_desc(ra + kb * (2 * SLOT));
 #pragma unroll
-      for (int q4 = 0; q4 < 4; ++q4) *reinterpret_cast<uint4*>(dst + sw128(ch, (c32 & 1) * 4 + q4)) = pack8(v + q4 * 8);
-    }
-    if (tid < 256) tab[tid] = bo[tid];   // the q|k bias table is dead; out-proj bias takes its place
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-  }
-
-  // ================= phase 3: S_qb = q_qb k^T for both query blocks (N = 256 keys, K = 64)
-  {
-    const uint32_t idesc = make_idesc(256);
-    if (tid == 0) {
+        for (int k4 = 0; k4 < 4; ++k4) umma_bf16(tmem + (1 - chb) * 256, ad + 2 * k4, bd + 2 * k4, id256, (kb | k4) != 0);
+        umma_commit(bar(B_CONS + t));
+      }
+      umma_commit(bar(C_V));
+      stamp(p.prof, 36);
+      // phase 3: S_qb = q_qb k^T for both query blocks (N = 256 keys, K = 64)
+      mbar_wait(bar(G_V), 0);
+      tc_fence_after();
+      stamp(p.prof, 37);
 #pragma unroll
       for (int qb = 0; qb < 2; ++qb) {
-        const uint64_t ad = make_desc(rb + qb * (128 * 128)), bd = make_desc(rb + 256 * 128);
+        const uint64_t ad = make_desc(rb + qb * SLOT), bd = make_desc(rb + 2 * SLOT);
 #pragma unroll
-        for (int k4 = 0; k4 < FDK / 16; ++k4) umma_bf16(tmem + qb * 256, ad + 2 * k4, bd + 2 * k4, idesc, k4 != 0);
+        for (int k4 = 0; k4 < FDK / 16; ++k4) umma_bf16(tmem + qb * 256, ad + 2 * k4, bd + 2 * k4, id256, k4 != 0);
       }
+      umma_commit(bar(C_S));
+      // O_qb = P_qb v  (A = P [128 x 256 keys], B = v^T [256 ch x 256 keys]); overwrites S_qb
+      for (int qb = 0; qb < 2; ++qb) {
+        mbar_wait(bar(G_P0 + qb), 0);
+        tc_fence_after();
+        stamp(p.prof, 38 + qb);
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) {
+          const uint64_t ad = make_desc(rb + kb * SLOT), bd = make_desc(ra + kb * (2 * SLOT));
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) umma_bf16(tmem + qb * 256, ad + 2 * k4, bd + 2 * k4, id256, (kb | k4) != 0);
+        }
+        umma_commit(bar(C_PV0 + qb));
+      }
+      // out[tok, ch] = r Wo^T for both query blocks per weight tile, into the columns O occupied
+      mbar_wait(bar(G_R), 0);
+      tc_fence_after();
+      stamp(p.prof, 40);
+      for (int j = 0; j < 8; ++j) {
+        const int t = 12 + j, chh = j >> 2, kb = j & 3;
+        mbar_wait(bar(B_FULL + t), 0);
+        tc_fence_after();
+        const uint64_t bd = make_desc(slot_of(t));
+#pragma unroll
+        for (int blk = 0; blk < 2; ++blk) {
+          const uint64_t ad = make_desc((blk == 0 ? rb : ra) + kb * SLOT);
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4)
+            umma_bf16(tmem + blk * 256 + chh * 128, ad + 2 * k4, bd + 2 * k4, id128, (kb | k4) != 0);
+        }
+        umma_commit(bar(B_CONS + t));
+      }
+      umma_commit(bar(C_OUT));
+      stamp(p.prof, 41);
     }
-    all_mma_done();   // q,k tiles in R_B are dead: P / r reuse the region
-  }
+    __syncwarp();
+  } else {
+    // ================= epilogue group (256 threads): thread = TMEM lane quarter*32 + lane, two warps per quarter
+    const int quarter = warp & 3, half = warp >> 2;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    const int lrow = quarter * 32 + lane;
+    const float* __restrict__ bqkv = p.bqkv[set];
+    const float* __restrict__ bo = p.bo[set];
+    auto publish = [&](int b) {   // operand written / accumulator drained -> MMA issuer
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(bar(b));
+    };
+    auto acquire = [&](int b) {   // an MMA phase has completed
+      mbar_wait(bar(b), 0);
+      tc_fence_after();
+    };
+    long long* eprof = tid == 0 ? p.prof : nullptr;
+    stamp(eprof, 0);
+    // x has landed, k-block by k-block
 
-  const float cexp = 1.4426950408889634f / 8.0f;  // log2(e) / sqrt(d_k)
-  for (int qb = 0; qb < 2; ++qb) {
-    const uint32_t t_row = tmem + lane_base + qb * 256;
-    const int lrow = quarter * 32 + lane;                   // row inside the query block
-    const size_t grow = row0 + qb * 128 + lrow;
-    // ---- softmax rows -> un-normalised P (bf16, K-major) in R_B.  All 8 warps: the two warps of a lane quarter
-    // split the 256 key columns (4 chunks each) and exchange row max / row sum through the idle weight ring.
-    float* xch = reinterpret_cast<float*>(gen + (rw - base));   // [2 halves][128 rows] max, then [2][128] sums
-    float mloc = -INFINITY;
+    // ---- q|k epilogue (under the v^T MMAs of channel block 0): warp half h owns token block h;
+    // q -> R_B[0:32K) as [256 x 64], k -> R_B[32K:64K)
+    acquire(C_QK);
+    stamp(eprof, 2);
+    {
+      const int row = half * 128 + lrow;
 #pragma unroll 1
-    for (int c32 = half * 4; c32 < half * 4 + 4; ++c32) {
-      float v[32];
-      tmem_ld32(t_row + c32 * 32, v);
+      for (int c32 = 0; c32 < 4; ++c32) {
+        float v[32];
+        tmem_ld32(tmem + lane_base + half * 128 + c32 * 32, v);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) mloc = fmaxf(mloc, v[i]);
-    }
-    xch[half * 128 + lrow] = mloc;
-    __syncthreads();
-    const float mc = fmaxf(xch[lrow], xch[128 + lrow]) * cexp;
-    float sum = 0.f;
-#pragma unroll 1
-    for (int c32 = half * 4; c32 < half * 4 + 4; ++c32) {
-      float v[32];
-      tmem_ld32(t_row + c32 * 32, v);
+        for (int i = 0; i < 32; ++i) v[i] += tab[c32 * 32 + i];
+        uint8_t* dst = gen + (rb - base) + (c32 >> 1) * (2 * SLOT);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        v[i] = exp2f(fmaf(v[i], cexp, -mc));
-        sum += v[i];
+        for (int q4 = 0; q4 < 4; ++q4) *reinterpret_cast<uint4*>(dst + sw128(row, (c32 & 1) * 4 + q4)) = pack8(v + q4 * 8);
       }
-      uint8_t* pk = gen + (rb - base) + (c32 >> 1) * (128 * 128);
-#pragma unroll
-      for (int q4 = 0; q4 < 4; ++q4) *reinterpret_cast<uint4*>(pk + sw128(lrow, (c32 & 1) * 4 + q4)) = pack8(v + q4 * 8);
     }
-    xch[256 + half * 128 + lrow] = sum;
-    __syncthreads();
-    const float inv_row = 1.0f / (xch[256 + lrow] + xch[384 + lrow]);
-    if (half == 0) invs[lrow] = inv_row;
-    if (p.attn_mode != 0) {  // attention map (need=True): mean of the four layers' maps, model5_b.py:468-469
-      float* ag = p.attn + grow * FL;
+    publish(G_QK);
+    stamp(eprof, 3);
+
+    // ---- v^T epilogue: thread = channel; x in R_A is dead, v^T takes its place
+    acquire(C_V);
+    stamp(eprof, 4);
+    {
+      const int ch = half * 128 + lrow;
+      const float bv = bqkv[128 + ch];
+      const uint32_t t_v = tmem + lane_base + (1 - half) * 256;
+#pragma unroll 1
+      for (int c32 = 0; c32 < 8; ++c32) {
+        float v[32];
+        tmem_ld32(t_v + c32 * 32, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] += bv;
+        uint8_t* dst = gen + (ra - base) + (c32 >> 1) * (2 * SLOT);
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) *reinterpret_cast<uint4*>(dst + sw128(ch, (c32 & 1) * 4 + q4)) = pack8(v + q4 * 8);
+      }
+    }
+    publish(G_V);
+    stamp(eprof, 5);
+
+    // ---- softmax rows -> un-normalised P (bf16, K-major) in R_B.  The two warps of a lane quarter split the 256
+    // key columns (4 chunks each) and exchange row max / row sum through xch: a thread publishes in its own slot
+    // first (max), then in its partner's slot (sum), so the 1 KB is reused without a further barrier.
+    const float cexp = 1.4426950408889634f / 8.0f;  // log2(e) / sqrt(d_k)
+    float inv0 = 0.f, inv1 = 0.f;
+    acquire(C_S);   // q,k tiles in R_B are dead
+    stamp(eprof, 6);
+#pragma unroll 1
+    for (int qb = 0; qb < 2; ++qb) {
+      const uint32_t t_row = tmem + lane_base + qb * 256;
+      const size_t grow = row0 + qb * 128 + lrow;
+      float mloc = -INFINITY;
 #pragma unroll 1
       for (int c32 = half * 4; c32 < half * 4 + 4; ++c32) {
         float v[32];
         tmem_ld32(t_row + c32 * 32, v);
 #pragma unroll
-        for (int q4 = 0; q4 < 8; ++q4) {
-          float4 a;
-          a.x = exp2f(fmaf(v[q4 * 4 + 0], cexp, -mc)) * inv_row;
-          a.y = exp2f(fmaf(v[q4 * 4 + 1], cexp, -mc)) * inv_row;
-          a.z = exp2f(fmaf(v[q4 * 4 + 2], cexp, -mc)) * inv_row;
-          a.w = exp2f(fmaf(v[q4 * 4 + 3], cexp, -mc)) * inv_row;
-          float4* dst = reinterpret_cast<float4*>(ag + c32 * 32 + q4 * 4);
-          if (p.attn_mode != 1) {
-            const float4 o = *dst;
-            a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w;
-            if (p.attn_mode == 3) { a.x *= 0.25f; a.y *= 0.25f; a.z *= 0.25f; a.w *= 0.25f; }
-          }
-          *dst = a;
-        }
+        for (int i = 0; i < 32; ++i) mloc = fmaxf(mloc, v[i]);
       }
-    }
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    // ---- O = P v  (A = P [128 x 256 keys], B = v^T [256 ch x 256 keys]); overwrites S_qb
-    if (tid == 0) {
-      const uint32_t idesc = make_idesc(256);
-#pragma unroll
-      for (int kb = 0; kb < 4; ++kb) {
-        const uint64_t ad = make_desc(rb + kb * (128 * 128)), bd = make_desc(ra + kb * (256 * 128));
-#pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4) umma_bf16(tmem + qb * 256, ad + 2 * k4, bd + 2 * k4, idesc, (kb | k4) != 0);
+      xch[half * 128 + lrow] = mloc;
+      epi_bar();
+      const float mc = fmaxf(mloc, xch[(1 - half) * 128 + lrow]) * cexp;
+      if (qb == 1) {
+        stamp(eprof, 8);
+        acquire(C_PV0);   // P0 has been consumed: R_B takes P1
+        stamp(eprof, 9);
       }
-    }
-    all_mma_done();   // P is dead: r takes its place
-    // ---- r = x - O / sum  -> R_B as the A operand of the out-projection; the two warp halves take alternate chunks
-    {
-      const float inv = invs[lrow];
-      const __nv_bfloat16* xr = p.x + grow * p.ldx;
+      float sum = 0.f;
 #pragma unroll 1
-      for (int c32 = half; c32 < 8; c32 += 2) {
-        uint4 xv[4];
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) xv[q4] = *reinterpret_cast<const uint4*>(xr + c32 * 32 + q4 * 8);
+      for (int c32 = half * 4; c32 < half * 4 + 4; ++c32) {
         float v[32];
         tmem_ld32(t_row + c32 * 32, v);
-        uint8_t* dst = gen + (rb - base) + (c32 >> 1) * (128 * 128);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          v[i] = exp2f(fmaf(v[i], cexp, -mc));
+          sum += v[i];
+        }
+        uint8_t* pk = gen + (rb - base) + (c32 >> 1) * SLOT;
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) *reinterpret_cast<uint4*>(pk + sw128(lrow, (c32 & 1) * 4 + q4)) = pack8(v + q4 * 8);
+      }
+      xch[(1 - half) * 128 + lrow] = sum;
+      epi_bar();
+      const float inv_row = 1.0f / (sum + xch[half * 128 + lrow]);
+      if (qb == 0) inv0 = inv_row; else inv1 = inv_row;
+      if (p.attn_mode != 0) {  // attention map (need=True): mean of the four layers' maps, model5_b.py:468-469
+        float* ag = p.attn + grow * FL;
+#pragma unroll 1
+        for (int c32 = half * 4; c32 < half * 4 + 4; ++c32) {
+          float v[32];
+          tmem_ld32(t_row + c32 * 32, v);
+#pragma unroll
+          for (int q4 = 0; q4 < 8; ++q4) {
+            float4 a;
+            a.x = exp2f(fmaf(v[q4 * 4 + 0], cexp, -mc)) * inv_row;
+            a.y = exp2f(fmaf(v[q4 * 4 + 1], cexp, -mc)) * inv_row;
+            a.z = exp2f(fmaf(v[q4 * 4 + 2], cexp, -mc)) * inv_row;
+            a.w = exp2f(fmaf(v[q4 * 4 + 3], cexp, -mc)) * inv_row;
+            float4* dst = reinterpret_cast<float4*>(ag + c32 * 32 + q4 * 4);
+            if (p.attn_mode != 1) {
+              const float4 o = *dst;
+              a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w;
+              if (p.attn_mode == 3) { a.x *= 0.25f; a.y *= 0.25f; a.z *= 0.25f; a.w *= 0.25f; }
+            }
+            *dst = a;
+          }
+        }
+      }
+      publish(G_P0 + qb);
+      stamp(eprof, qb == 0 ? 7 : 10);
+    }
+
+    // ---- from here on warp half h owns query block h
+    const int qb = half;
+    const size_t grow = row0 + qb * 128 + lrow;
+    const uint32_t t_row = tmem + lane_base + qb * 256;
+    uint8_t* rdst = gen + ((qb == 0 ? rb : ra) - base);   // the block's 4 slots: x -> r in place, x -> out in place
+    // r = x - O / sum  -> the A operand of the out-projection, formed over the x tiles the producer brought back
+    acquire(C_PV1);
+    stamp(eprof, 11);   // both P v products are complete (commits complete in order): P and v^T are dead
+    mbar_wait(bar(F_XR), 0);
+    stamp(eprof, 1);
+    {
+      const float inv = qb == 0 ? inv0 : inv1;
+#pragma unroll 1
+      for (int c32 = 0; c32 < 8; ++c32) {
+        float v[32];
+        tmem_ld32(t_row + c32 * 32, v);
+        uint8_t* dst = rdst + (c32 >> 1) * SLOT;
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) {
-          const __nv_bfloat162* xp = reinterpret_cast<const __nv_bfloat162*>(&xv[q4]);
+          const uint4 xv = *reinterpret_cast<const uint4*>(dst + sw128(lrow, (c32 & 1) * 4 + q4));
+          const __nv_bfloat162* xp = reinterpret_cast<const __nv_bfloat162*>(&xv);
           float rr[8];
 #pragma unroll
           for (int h = 0; h < 4; ++h) {
@@ -290,48 +410,38 @@ __global__ void __launch_bounds__(FT, 1) attention_layer_tc_kernel(const AttnLay
         }
       }
     }
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();   // r complete, O_qb drained
-    tc_fence_after();
-    // ---- out[tok, ch] = r Wo^T : two 128-channel halves into the columns O_qb occupied
-    {
-      const uint32_t idesc = make_idesc(128);
-      stream_phase(8, FC, [&](int t) { return wo + (size_t)((t >> 2) * 128) * FC + (t & 3) * 64; },
-                   [&](int t, uint32_t wt) {
-                     const int chh = t >> 2, kb = t & 3;
-                     const uint64_t ad = make_desc(rb + kb * (128 * 128)), bd = make_desc(wt);
-#pragma unroll
-                     for (int k4 = 0; k4 < 4; ++k4)
-                       umma_bf16(tmem + qb * 256 + chh * 128, ad + 2 * k4, bd + 2 * k4, idesc, (kb | k4) != 0);
-                   },
-                   rw, wbar, wuse, tid);
-      all_mma_done();
-    }
+    publish(G_R);
+    stamp(eprof, 12);
+    epi_bar();            // every thread is past the softmax exchange: xch takes the out-projection bias
+    xch[tid] = bo[tid];
+    epi_bar();
+
     // ---- out = x + relu(acc + bo): thread = token row, 128-bit stores into the layer's slice of att_cat
+    acquire(C_OUT);
+    stamp(eprof, 13);
+    mbar_wait(bar(F_XO), 0);
+    stamp(eprof, 16);
     {
-      const __nv_bfloat16* xr = p.x + grow * p.ldx;
-      __nv_bfloat16* yb = p.yb + grow * p.ldyb;
       float* yf = p.yf ? p.yf + grow * p.ldyf : nullptr;
 #pragma unroll 1
-      for (int c32 = half; c32 < 8; c32 += 2) {
-        uint4 xv[4];
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) xv[q4] = *reinterpret_cast<const uint4*>(xr + c32 * 32 + q4 * 8);
+      for (int c32 = 0; c32 < 8; ++c32) {
         float v[32];
         tmem_ld32(t_row + c32 * 32, v);
+        uint8_t* dst = rdst + (c32 >> 1) * SLOT;
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) {
-          const __nv_bfloat162* xp = reinterpret_cast<const __nv_bfloat162*>(&xv[q4]);
+          uint4* slot16 = reinterpret_cast<uint4*>(dst + sw128(lrow, (c32 & 1) * 4 + q4));
+          const uint4 xv = *slot16;
+          const __nv_bfloat162* xp = reinterpret_cast<const __nv_bfloat162*>(&xv);
+          const float* bb = xch + c32 * 32 + q4 * 8;
           float o8[8];
 #pragma unroll
           for (int h = 0; h < 4; ++h) {
             const float2 xf = __bfloat1622float2(xp[h]);
-            const int c = c32 * 32 + q4 * 8 + 2 * h;
-            o8[2 * h] = xf.x + fmaxf(v[q4 * 8 + 2 * h] + tab[c], 0.f);
-            o8[2 * h + 1] = xf.y + fmaxf(v[q4 * 8 + 2 * h + 1] + tab[c + 1], 0.f);
+            o8[2 * h] = xf.x + fmaxf(v[q4 * 8 + 2 * h] + bb[2 * h], 0.f);
+            o8[2 * h + 1] = xf.y + fmaxf(v[q4 * 8 + 2 * h + 1] + bb[2 * h + 1], 0.f);
           }
-          *reinterpret_cast<uint4*>(yb + c32 * 32 + q4 * 8) = pack8(o8);
+          *slot16 = pack8(o8);
           if (yf) {
             *reinterpret_cast<float4*>(yf + c32 * 32 + q4 * 8) = make_float4(o8[0], o8[1], o8[2], o8[3]);
             *reinterpret_cast<float4*>(yf + c32 * 32 + q4 * 8 + 4) = make_float4(o8[4], o8[5], o8[6], o8[7]);
@@ -340,24 +450,91 @@ __global__ void __launch_bounds__(FT, 1) attention_layer_tc_kernel(const AttnLay
       }
     }
     tc_fence_before();
-    __syncthreads();   // R_B (r) and the out columns are free for the next query block
-    tc_fence_after();
+    // the block's output tile is complete in its 4 slots: one thread hands it to TMA
+    fence_proxy_async();
+    asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory");
+    if (lrow == 0) {
+      const uint32_t src = qb == 0 ? rb : ra;
+#pragma unroll
+      for (int kb = 0; kb < 4; ++kb) tma_store(&tmy, kb * 64, (int)row0 + qb * 128, src + kb * SLOT);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+    stamp(eprof, 14);
   }
+  __syncthreads();   // every TMEM read has retired, the TMA stores have read their tiles
   if (warp == 0) {
+    tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
   }
 }
 
-int launch_attention_layer_tc(const AttnLayerTc& p, int clouds, cudaStream_t st) {
-  PZ_REQUIRE(p.x && p.wqkv[0] && p.wo[0] && p.bqkv[0] && p.bo[0] && p.yb, PZ_ERR_ARG, "attention_layer_tc: null pointer");
+// fp32 [rows, 256] weight block -> pre-swizzled [128 x 64] bf16 tile images; image tile = (row / 128) * 4 + col / 64
+__global__ void __launch_bounds__(256) attn_weight_image_kernel(const float* __restrict__ src, int rows, int row_off,
+                                                                __nv_bfloat16* __restrict__ img) {
+  const int e = blockIdx.x * 256 + threadIdx.x;
+  if (e >= rows * FC) return;
+  const int r = e / FC + row_off, c = e % FC;
+  const int tile = (r >> 7) * 4 + (c >> 6), rr = r & 127, cc = c & 63;
+  const uint32_t off = sw128(rr, cc >> 3) + (cc & 7) * 2;
+  img[(size_t)tile * (SLOT / 2) + off / 2] = __float2bfloat16_rn(src[(size_t)(e / FC) * FC + c]);
+}
+
+int launch_attn_weight_image(const float* src, int rows, int row_off, __nv_bfloat16* img, cudaStream_t st) {
+  attn_weight_image_kernel<<<(rows * FC + 255) / 256, 256, 0, st>>>(src, rows, row_off, img);
+  PZ_LAUNCH_CHECK();
+  return 0;
+}
+
+static long long* g_attn_timeline = nullptr;
+
+// [rows, 256] bf16 view with a row stride of ld elements, traversed in [128 rows x 64 ch] SWIZZLE_128B boxes
+static int make_tile_map(const __nv_bfloat16* ptr, int ld, size_t rows, CUtensorMap* out) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      fn = nullptr;
+    return reinterpret_cast<EncodeFn>(fn);
+  }();
+  PZ_REQUIRE(encode != nullptr, PZ_ERR_UNSUPPORTED, "attention_layer_tc: the driver does not export cuTensorMapEncodeTiled");
+  const cuuint64_t dims[2] = {(cuuint64_t)FC, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(__nv_bfloat16)};
+  const cuuint32_t box[2] = {64, 128}, estr[2] = {1, 1};
+  const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(ptr), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PZ_REQUIRE(r == CUDA_SUCCESS, PZ_ERR_ARG, "attention_layer_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return 0;
+}
+
+int launch_attention_layer_tc(const AttnLayerTc& p_in, int clouds, cudaStream_t st) {
+  AttnLayerTc p = p_in;
+  p.prof = g_attn_timeline;
+  PZ_REQUIRE(p.x && p.wimg[0] && p.bqkv[0] && p.bo[0] && p.yb, PZ_ERR_ARG, "attention_layer_tc: null pointer");
   PZ_REQUIRE(p.ldx % 8 == 0 && p.ldyb % 8 == 0 && ((uintptr_t)p.x & 15) == 0 && ((uintptr_t)p.yb & 15) == 0 &&
-                 (!p.yf || (p.ldyf % 4 == 0 && ((uintptr_t)p.yf & 15) == 0)),
+                 (!p.yf || (p.ldyf % 4 == 0 && ((uintptr_t)p.yf & 15) == 0)) && ((uintptr_t)p.wimg[0] & 15) == 0,
              PZ_ERR_ARG, "attention_layer_tc: rows must be 16-byte aligned");
-  const size_t smem = 1024 + RA_BYTES + RB_BYTES + RW_BYTES + 1024 + 512 + 64;
+  const size_t smem = 1024 + RA_BYTES + RB_BYTES + RW_BYTES + MISC_BYTES;
+  static_assert(1024 + RA_BYTES + RB_BYTES + RW_BYTES + MISC_BYTES <= 232448, "attention layer: shared memory budget");
   PZ_CUDA(cudaFuncSetAttribute(attention_layer_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  attention_layer_tc_kernel<<<clouds, FT, smem, st>>>(p);
+  alignas(64) CUtensorMap tmx, tmy;
+  PZ_TRY(make_tile_map(p.x, p.ldx, (size_t)clouds * FL, &tmx));
+  PZ_TRY(make_tile_map(p.yb, p.ldyb, (size_t)clouds * FL, &tmy));
+  attention_layer_tc_kernel<<<clouds, FT, smem, st>>>(p, tmx, tmy);
   PZ_LAUNCH_CHECK();
   return 0;
 }
 
 }  // namespace pz
+
+// diagnostics: a device buffer of 64 int64 that CTA 0 of every following fused attention-layer launch fills with SM
+// clock stamps (slots 0-14 and 16 epilogue thread 0, 15 kernel entry, 32-41 the MMA issuer); null switches it off
+extern "C" int pz_profile_attention_timeline(long long* device_buf_or_null) {
+  pz::g_attn_timeline = device_buf_or_null;
+  return 0;
+}

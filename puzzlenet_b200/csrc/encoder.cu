@@ -582,12 +582,14 @@ __global__ void se3_exp_kernel(const float* __restrict__ x, int B, float* __rest
 // ------------------------------------------------ bf16 path helpers (PZ_PREC_BF16)
 // One launch converts / concatenates every weight the tensor-core path needs (fp32 reference layout ->
 // bf16 packs with 16-byte aligned rows).  Job y = blockIdx.y.
+// to_bf16 == 2: attention-layer tile images (attention_layer_tc.cu): cols == 256, ldo = first row of the block inside
+// the layer's row sequence; element (r, c) -> tile (r / 128) * 4 + c / 64, SWIZZLE_128B byte order inside the tile
 struct PackJob {
   const float* src;
   void* dst;
   int ldi, rows, cols, ldo, to_bf16;
 };
-constexpr int MAX_PACK_JOBS = 96;
+constexpr int MAX_PACK_JOBS = 128;
 struct PackJobs {
   PackJob j[MAX_PACK_JOBS];
   int n;
@@ -598,7 +600,11 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const PackJobs jobs) 
   for (int e = blockIdx.x * 256 + threadIdx.x; e < total; e += gridDim.x * 256) {
     const int r = e / jb.cols, c = e - r * jb.cols;
     const float v = jb.src[(size_t)r * jb.ldi + c];
-    if (jb.to_bf16) static_cast<__nv_bfloat16*>(jb.dst)[(size_t)r * jb.ldo + c] = __float2bfloat16_rn(v);
+    if (jb.to_bf16 == 2) {
+      const int rr = r + jb.ldo, tile = (rr >> 7) * 4 + (c >> 6), tr = rr & 127, tc = c & 63;
+      static_cast<__nv_bfloat16*>(jb.dst)[(size_t)tile * 8192 + tr * 64 + (((tc >> 3) ^ (tr & 7)) << 3) + (tc & 7)] =
+          __float2bfloat16_rn(v);
+    } else if (jb.to_bf16) static_cast<__nv_bfloat16*>(jb.dst)[(size_t)r * jb.ldo + c] = __float2bfloat16_rn(v);
     else static_cast<float*>(jb.dst)[(size_t)r * jb.ldo + c] = v;
   }
 }
@@ -638,10 +644,10 @@ struct EncoderScratch {
 };
 
 // bf16 weight pack of ONE encoder (elements): W3f[128,64] W4[128,128] W5f[256,128] W6[256,256]
-// 4 x (Wqkv[384,256] Wo[256,256]) Wout[1024,1280]
+// 4 x (Wqkv[384,256] Wo[256,256]) Wout[1024,1280]  4 x (20 tile images of Wqkv|Wo for the fused attention layer)
 constexpr size_t WP_W3F = 0, WP_W4 = WP_W3F + 128 * 64, WP_W5F = WP_W4 + 128 * 128, WP_W6 = WP_W5F + 256 * 128,
                  WP_ATT = WP_W6 + 256 * 256, WP_ATT_STRIDE = 384 * 256 + 256 * 256, WP_WOUT = WP_ATT + 4 * WP_ATT_STRIDE,
-                 WP_TOTAL = WP_WOUT + 1024 * 1280;
+                 WP_ATTIMG = WP_WOUT + 1024 * 1280, WP_TOTAL = WP_ATTIMG + 4 * ATTN_WIMG_ELEMS;
 
 static size_t encoder_scratch_layout(int C, Arena& a, EncoderScratch& s) {
   s.xfeat = a.take<float>((size_t)C * NPTS * D0);
@@ -717,6 +723,11 @@ static int encoder_forward_bf16(const PzEncoderWeights* w, int E, int B, const f
         add(we.k_w[l], CATT, 64, CATT, wl + 64 * CATT, CATT, 1);
         add(we.v_w[l], CATT, CATT, CATT, wl + 128 * CATT, CATT, 1);
         add(we.o_w[l], CATT, CATT, CATT, wl + 384 * CATT, CATT, 1);
+        __nv_bfloat16* wi = wp + WP_ATTIMG + (size_t)l * ATTN_WIMG_ELEMS;
+        add(we.q_w[l], CATT, 64, CATT, wi, 0, 2);
+        add(we.k_w[l], CATT, 64, CATT, wi, 64, 2);
+        add(we.v_w[l], CATT, CATT, CATT, wi, 128, 2);
+        add(we.o_w[l], CATT, CATT, CATT, wi, 384, 2);
         float* bq = s.bqkv + ((size_t)e * 4 + l) * 384;
         add(we.q_b[l], 64, 1, 64, bq, 64, 0);
         add(we.k_b[l], 64, 1, 64, bq + 64, 64, 0);
@@ -809,8 +820,7 @@ static int encoder_forward_bf16(const PzEncoderWeights* w, int E, int B, const f
   for (int l = 0; l < 4 && fused_attn; ++l) {   // one kernel per layer: nothing but x and out touches HBM
     AttnLayerTc p;
     p.x = l == 0 ? cat_b + 4 * CATT : cat_b + (l - 1) * CATT; p.ldx = 1280;
-    p.wqkv[0] = wpa + WP_ATT + (size_t)l * WP_ATT_STRIDE; p.wqkv[1] = wpb + WP_ATT + (size_t)l * WP_ATT_STRIDE;
-    p.wo[0] = p.wqkv[0] + 384 * CATT; p.wo[1] = p.wqkv[1] + 384 * CATT;
+    p.wimg[0] = wpa + WP_ATTIMG + (size_t)l * ATTN_WIMG_ELEMS; p.wimg[1] = wpb + WP_ATTIMG + (size_t)l * ATTN_WIMG_ELEMS;
     p.bqkv[0] = s.bqkv + (size_t)l * 384; p.bqkv[1] = s.bqkv + ((size_t)(E - 1) * 4 + l) * 384;
     p.bo[0] = wa.o_b[l]; p.bo[1] = wb.o_b[l];
     p.clouds_per_set = B; p.yb = cat_b + l * CATT; p.ldyb = 1280;
@@ -1247,7 +1257,10 @@ extern "C" int pz_linear(const float* x, int ldx, const float* W, const float* b
 extern "C" size_t pz_offset_attention_workspace_bytes(int B, int L, int C) {
   if (B < 1 || L < 1 || C < 4) return 0;
   const size_t rows = (size_t)B * L;
-  return align_up(rows * (C / 4) * sizeof(float), 256) * 2 + align_up(rows * C * sizeof(float), 256) * 2 + 256;
+  // fp32 path: q, k, v, r;  bf16 path (L == 256): x and out as bf16, one layer's weight tile images, the q|k|v bias
+  const size_t fp32_path = align_up(rows * (C / 4) * sizeof(float), 256) * 2 + align_up(rows * C * sizeof(float), 256) * 2;
+  const size_t bf16_path = align_up(rows * C * 2, 256) * 2 + align_up(ATTN_WIMG_ELEMS * 2, 256) + align_up(384 * 4, 256);
+  return (fp32_path > bf16_path ? fp32_path : bf16_path) + 256;
 }
 
 extern "C" int pz_offset_attention(const float* x, const float* Wq, const float* bq, const float* Wk, const float* bk,
@@ -1256,10 +1269,32 @@ extern "C" int pz_offset_attention(const float* x, const float* Wq, const float*
                                    size_t workspace_bytes, pz_stream_t stream) {
   PZ_REQUIRE(x && Wq && bq && Wk && bk && Wv && bv && Wo && bo && out, PZ_ERR_ARG, "pz_offset_attention: null pointer");
   PZ_REQUIRE(B >= 1 && C == 256, PZ_ERR_UNSUPPORTED, "pz_offset_attention: C must be 256 (got %d)", C);
-  PZ_REQUIRE(precision == PZ_PREC_FP32, PZ_ERR_UNSUPPORTED, "pz_offset_attention: precision %d not available", precision);
+  PZ_REQUIRE(precision == PZ_PREC_FP32 || precision == PZ_PREC_BF16, PZ_ERR_ARG, "pz_offset_attention: unknown precision %d", precision);
   cudaStream_t st = as_stream(stream);
   Arena a(workspace, workspace_bytes);
   const size_t rows = (size_t)B * L;
+  if (precision == PZ_PREC_BF16) {   // the fused tcgen05 layer kernel predict5 uses (attention_layer_tc.cu)
+    PZ_REQUIRE(L == 256, PZ_ERR_UNSUPPORTED, "pz_offset_attention(bf16): L must be 256 (got %d)", L);
+    __nv_bfloat16* xb = a.take<__nv_bfloat16>(rows * C);
+    __nv_bfloat16* yb = a.take<__nv_bfloat16>(rows * C);
+    __nv_bfloat16* wimg = a.take<__nv_bfloat16>(ATTN_WIMG_ELEMS);
+    float* bqkv = a.take<float>(384);
+    PZ_REQUIRE(workspace && a.ok(), PZ_ERR_WORKSPACE, "pz_offset_attention: workspace %zu B < required %zu B",
+               workspace_bytes, a.used);
+    PZ_TRY(launch_cvt_bf16(x, C, (int)rows, C, xb, C, st));
+    PZ_TRY(launch_attn_weight_image(Wq, 64, 0, wimg, st));
+    PZ_TRY(launch_attn_weight_image(Wk, 64, 64, wimg, st));
+    PZ_TRY(launch_attn_weight_image(Wv, C, 128, wimg, st));
+    PZ_TRY(launch_attn_weight_image(Wo, C, 384, wimg, st));
+    PZ_CUDA(cudaMemcpyAsync(bqkv, bq, 64 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    PZ_CUDA(cudaMemcpyAsync(bqkv + 64, bk, 64 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    PZ_CUDA(cudaMemcpyAsync(bqkv + 128, bv, C * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    AttnLayerTc p;
+    p.x = xb; p.ldx = C; p.wimg[0] = p.wimg[1] = wimg; p.bqkv[0] = p.bqkv[1] = bqkv; p.bo[0] = p.bo[1] = bo;
+    p.clouds_per_set = B; p.yb = yb; p.ldyb = C; p.yf = out; p.ldyf = C;
+    p.attn = attention_or_null; p.attn_mode = attention_or_null ? 1 : 0;
+    return launch_attention_layer_tc(p, B, st);
+  }
   float* q = a.take<float>(rows * (C / 4));
   float* k = a.take<float>(rows * (C / 4));
   float* v = a.take<float>(rows * C);

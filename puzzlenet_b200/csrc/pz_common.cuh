@@ -159,8 +159,9 @@ int launch_attention_tc(const __nv_bfloat16* qk, const __nv_bfloat16* vT, const 
 struct AttnLayerTc {
   const __nv_bfloat16* x = nullptr;       // [clouds*256, ldx] layer input
   int ldx = 0;
-  const __nv_bfloat16* wqkv[2] = {nullptr, nullptr};   // [384, 256]: q rows 0-63, k 64-127, v 128-383
-  const __nv_bfloat16* wo[2] = {nullptr, nullptr};     // [256, 256]
+  // 20 pre-swizzled [128 x 64] tile images (16 KB each): Wqkv [384, 256] (q rows 0-63, k 64-127, v 128-383) as
+  // tiles (row block, k-block) 0-11, then Wo [256, 256] as tiles 12-19 (launch_attn_weight_image)
+  const __nv_bfloat16* wimg[2] = {nullptr, nullptr};
   const float* bqkv[2] = {nullptr, nullptr};           // [384]
   const float* bo[2] = {nullptr, nullptr};             // [256]
   int clouds_per_set = 0;
@@ -170,8 +171,13 @@ struct AttnLayerTc {
   int ldyf = 0;
   float* attn = nullptr;                  // attention map accumulation (see attention_tc_kernel)
   int attn_mode = 0;
+  long long* prof = nullptr;              // pz_profile_attention_timeline
 };
 int launch_attention_layer_tc(const AttnLayerTc& p, int clouds, cudaStream_t st);
+constexpr size_t ATTN_WIMG_ELEMS = 20 * 128 * 64;   // bf16 elements of one layer's tile images
+// fp32 rows [rows, 256] of a weight block -> their place in the tile images (row_off = first row inside the block
+// sequence: q 0, k 64, v 128, o 384)
+int launch_attn_weight_image(const float* src, int rows, int row_off, __nv_bfloat16* img, cudaStream_t st);
 int launch_cvt_bf16(const float* in, int ldi, int rows, int cols, __nv_bfloat16* out, int ldo, cudaStream_t st);
 
 }  // namespace pz

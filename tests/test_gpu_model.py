@@ -45,6 +45,40 @@ def test_linear_and_attention_blocks(state_dict):
     assert rel_err(out, ro) < REL_FP32 and rel_err(a, ra) < REL_FP32
 
 
+@pytest.mark.parametrize("B", [1, 3, 150])
+def test_layer_attention_bf16_fused_kernel(state_dict, B):
+    """The fused tcgen05 layer kernel (attention_layer_tc.cu) through ``layerAttention(precision='bf16')``: 2e-2 of the
+    oracle's fp32 layer, and ~1e-3 of a torch emulation that rounds the same operands (x, weights, q, k, v, P, r) to
+    bf16 -- the second bound is what catches a mis-placed tile or a dropped k-block.  B = 150 > 148 SMs."""
+    from puzzlenet_b200.model5_b import layerAttention
+    g = torch.Generator().manual_seed(5)
+    layer = layerAttention(None, 256)
+    pre = "Encoder2.atten2."
+    sd = {kk[len(pre):]: vv for kk, vv in state_dict.items() if kk.startswith(pre)}
+    layer.load_state_dict(sd)
+    layer.precision = "bf16"
+    x = torch.randn(B, 256, 256, generator=g) * 0.5
+    out, a = layer.to(DEV)(x.to(DEV))
+    torch.cuda.synchronize()
+    ro, ra = po.layer_attention(state_dict, pre[:-1], x)
+    assert rel_err(out, ro) < 2e-2
+    assert rel_err(a, ra) < 0.25
+    np.testing.assert_allclose(a.sum(-1).cpu().numpy(), 1.0, atol=1e-4)
+
+    def bf(t):
+        return t.to(torch.bfloat16).float()
+    xb = bf(x)
+    q = bf(xb @ bf(sd["mlpq.weight"]).t() + sd["mlpq.bias"])
+    k = bf(xb @ bf(sd["mlpk.weight"]).t() + sd["mlpk.bias"])
+    v = bf(xb @ bf(sd["mlpv.weight"]).t() + sd["mlpv.bias"])
+    s_ = q @ k.transpose(1, 2) / 8.0
+    pexp = torch.exp(s_ - s_.max(-1, keepdim=True).values)
+    r = bf(xb - (bf(pexp) @ v) / pexp.sum(-1, keepdim=True))
+    emu = xb + torch.relu(r @ bf(sd["out.weight"]).t() + sd["out.bias"])
+    assert rel_err(out, emu) < 5e-3
+    assert rel_err(a, pexp / pexp.sum(-1, keepdim=True)) < 2e-2
+
+
 def test_group_mlp_maxpool_matches_materialised_path(state_dict):
     """Fused gather+MLP+max-pool == sample_and_group(...) -> mlp3 -> relu -> mlp4 -> relu -> max (oracle)."""
     from puzzlenet_b200 import pointnet_util as pu
