@@ -44,11 +44,11 @@ constexpr int NEPI = 256, FT = 320;                        // epilogue threads, 
 constexpr int NTILES = 20;
 
 // barrier indices (8 bytes each)
-constexpr int B_FULL = 0, B_CONS = NTILES, B_C = 2 * NTILES;            // c_qk c_v c_s c_pv0 c_pv1 c_out
+constexpr int B_FULL = 0, B_CONS = NTILES - 4, B_C = 2 * NTILES - 4;    // cons[t] exists for t >= 4; c_qk c_v c_s c_pv0 c_pv1 c_out
 constexpr int C_QK = B_C, C_V = B_C + 1, C_S = B_C + 2, C_PV0 = B_C + 3, C_PV1 = B_C + 4, C_OUT = B_C + 5;
-constexpr int F_X = B_C + 6;                                            // 4: x k-block landed (TMA), + x for r, x for out
-constexpr int F_XR = F_X + 4, F_XO = F_X + 5;
-constexpr int G_QK = F_X + 6, G_V = G_QK + 1, G_P0 = G_QK + 2, G_R = G_QK + 4;   // G_P1 = G_P0 + 1
+constexpr int F_X = B_C + 6;                       // x k-block kb landed (TMA): for the projections, for r, for out
+constexpr int F_XR = F_X + 4, F_XO = F_X + 8;
+constexpr int G_QK = F_X + 12, G_V = G_QK + 1, G_P0 = G_QK + 2, G_R = G_QK + 4;   // G_P1 = G_P0 + 1
 constexpr int NBARS = G_R + 1;
 constexpr uint32_t MISC_BYTES = 1024 /*xch*/ + 512 /*q|k bias*/ + NBARS * 8 + 16;
 
@@ -143,10 +143,10 @@ __global__ void __launch_bounds__(FT, 1) attention_layer_tc_kernel(const AttnLay
       // P and v^T are dead: x comes back into the slots where r is formed in place (block 0 in R_B, block 1 in
       // A0-A3), and the upper half of R_A takes four Wo tiles
       auto load_x_blocks = [&](int b) {
-        expect_tx(bar(b), 8 * SLOT);
         for (int kb = 0; kb < 4; ++kb) {
-          tma_load(rb + kb * SLOT, &tmx, kb * 64, (int)row0, bar(b));
-          tma_load(ra + kb * SLOT, &tmx, kb * 64, (int)row0 + 128, bar(b));
+          expect_tx(bar(b + kb), 2 * SLOT);
+          tma_load(rb + kb * SLOT, &tmx, kb * 64, (int)row0, bar(b + kb));
+          tma_load(ra + kb * SLOT, &tmx, kb * 64, (int)row0 + 128, bar(b + kb));
         }
       };
       mbar_wait(bar(C_PV1), 0);
@@ -246,7 +246,8 @@ __global__ void __launch_bounds__(FT, 1) attention_layer_tc_kernel(const AttnLay
     }
     __syncwarp();
   } else {
-    // ================= epilogue group (256 threads): thread = TMEM lane quarter*32 + lane, two warps per quarter
+    // ================= epilogue group (256 threads): thread = TMEM lane quarter*32 + lane, two warps per quarter.
+    // Accumulators are read 64 columns (= one 128-byte operand row) per tcgen05.ld.
     const int quarter = warp & 3, half = warp >> 2;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     const int lrow = quarter * 32 + lane;
@@ -263,7 +264,6 @@ __global__ void __launch_bounds__(FT, 1) attention_layer_tc_kernel(const AttnLay
     };
     long long* eprof = tid == 0 ? p.prof : nullptr;
     stamp(eprof, 0);
-    // x has landed, k-block by k-block
 
     // ---- q|k epilogue (under the v^T MMAs of channel block 0): warp half h owns token block h;
     // q -> R_B[0:32K) as [256 x 64], k -> R_B[32K:64K)
@@ -272,14 +272,14 @@ __global__ void __launch_bounds__(FT, 1) attention_layer_tc_kernel(const AttnLay
     {
       const int row = half * 128 + lrow;
 #pragma unroll 1
-      for (int c32 = 0; c32 < 4; ++c32) {
-        float v[32];
-        tmem_ld32(tmem + lane_base + half * 128 + c32 * 32, v);
+      for (int c64 = 0; c64 < 2; ++c64) {
+        float v[64];
+        tmem_ld64(tmem + lane_base + half * 128 + c64 * 64, v);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] += tab[c32 * 32 + i];
-        uint8_t* dst = gen + (rb - base) + (c32 >> 1) * (2 * SLOT);
+        for (int i = 0; i < 64; ++i) v[i] += tab[c64 * 64 + i];
+        uint8_t* dst = gen + (rb - base) + c64 * (2 * SLOT);
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) *reinterpret_cast<uint4*>(dst + sw128(row, (c32 & 1) * 4 + q4)) = pack8(v + q4 * 8);
+        for (int q8 = 0; q8 < 8; ++q8) *reinterpret_cast<uint4*>(dst + sw128(row, q8)) = pack8(v + q8 * 8);
       }
     }
     publish(G_QK);
@@ -293,21 +293,21 @@ __global__ void __launch_bounds__(FT, 1) attention_layer_tc_kernel(const AttnLay
       const float bv = bqkv[128 + ch];
       const uint32_t t_v = tmem + lane_base + (1 - half) * 256;
 #pragma unroll 1
-      for (int c32 = 0; c32 < 8; ++c32) {
-        float v[32];
-        tmem_ld32(t_v + c32 * 32, v);
+      for (int c64 = 0; c64 < 4; ++c64) {
+        float v[64];
+        tmem_ld64(t_v + c64 * 64, v);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] += bv;
-        uint8_t* dst = gen + (ra - base) + (c32 >> 1) * (2 * SLOT);
+        for (int i = 0; i < 64; ++i) v[i] += bv;
+        uint8_t* dst = gen + (ra - base) + c64 * (2 * SLOT);
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) *reinterpret_cast<uint4*>(dst + sw128(ch, (c32 & 1) * 4 + q4)) = pack8(v + q4 * 8);
+        for (int q8 = 0; q8 < 8; ++q8) *reinterpret_cast<uint4*>(dst + sw128(ch, q8)) = pack8(v + q8 * 8);
       }
     }
     publish(G_V);
     stamp(eprof, 5);
 
     // ---- softmax rows -> un-normalised P (bf16, K-major) in R_B.  The two warps of a lane quarter split the 256
-    // key columns (4 chunks each) and exchange row max / row sum through xch: a thread publishes in its own slot
+    // key columns (128 each) and exchange row max / row sum through xch: a thread publishes in its own slot
     // first (max), then in its partner's slot (sum), so the 1 KB is reused without a further barrier.
     const float cexp = 1.4426950408889634f / 8.0f;  // log2(e) / sqrt(d_k)
     float inv0 = 0.f, inv1 = 0.f;
@@ -319,11 +319,11 @@ __global__ void __launch_bounds__(FT, 1) attention_layer_tc_kernel(const AttnLay
       const size_t grow = row0 + qb * 128 + lrow;
       float mloc = -INFINITY;
 #pragma unroll 1
-      for (int c32 = half * 4; c32 < half * 4 + 4; ++c32) {
-        float v[32];
-        tmem_ld32(t_row + c32 * 32, v);
+      for (int c64 = half * 2; c64 < half * 2 + 2; ++c64) {
+        float v[64];
+        tmem_ld64(t_row + c64 * 64, v);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) mloc = fmaxf(mloc, v[i]);
+        for (int i = 0; i < 64; ++i) mloc = fmaxf(mloc, v[i]);
       }
       xch[half * 128 + lrow] = mloc;
       epi_bar();
@@ -335,17 +335,17 @@ __global__ void __launch_bounds__(FT, 1) attention_layer_tc_kernel(const AttnLay
       }
       float sum = 0.f;
 #pragma unroll 1
-      for (int c32 = half * 4; c32 < half * 4 + 4; ++c32) {
-        float v[32];
-        tmem_ld32(t_row + c32 * 32, v);
+      for (int c64 = half * 2; c64 < half * 2 + 2; ++c64) {
+        float v[64];
+        tmem_ld64(t_row + c64 * 64, v);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
+        for (int i = 0; i < 64; ++i) {
           v[i] = exp2f(fmaf(v[i], cexp, -mc));
           sum += v[i];
         }
-        uint8_t* pk = gen + (rb - base) + (c32 >> 1) * SLOT;
+        uint8_t* pk = gen + (rb - base) + c64 * SLOT;
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) *reinterpret_cast<uint4*>(pk + sw128(lrow, (c32 & 1) * 4 + q4)) = pack8(v + q4 * 8);
+        for (int q8 = 0; q8 < 8; ++q8) *reinterpret_cast<uint4*>(pk + sw128(lrow, q8)) = pack8(v + q8 * 8);
       }
       xch[(1 - half) * 128 + lrow] = sum;
       epi_bar();
@@ -382,31 +382,33 @@ __global__ void __launch_bounds__(FT, 1) attention_layer_tc_kernel(const AttnLay
     const int qb = half;
     const size_t grow = row0 + qb * 128 + lrow;
     const uint32_t t_row = tmem + lane_base + qb * 256;
-    uint8_t* rdst = gen + ((qb == 0 ? rb : ra) - base);   // the block's 4 slots: x -> r in place, x -> out in place
+    const uint32_t rslots = qb == 0 ? rb : ra;            // the block's 4 slots: x -> r in place, x -> out in place
+    uint8_t* rdst = gen + (rslots - base);
     // r = x - O / sum  -> the A operand of the out-projection, formed over the x tiles the producer brought back
     acquire(C_PV1);
     stamp(eprof, 11);   // both P v products are complete (commits complete in order): P and v^T are dead
-    mbar_wait(bar(F_XR), 0);
-    stamp(eprof, 1);
     {
       const float inv = qb == 0 ? inv0 : inv1;
 #pragma unroll 1
-      for (int c32 = 0; c32 < 8; ++c32) {
-        float v[32];
-        tmem_ld32(t_row + c32 * 32, v);
-        uint8_t* dst = rdst + (c32 >> 1) * SLOT;
+      for (int kb = 0; kb < 4; ++kb) {
+        float v[64];
+        tmem_ld64(t_row + kb * 64, v);
+        mbar_wait(bar(F_XR + kb), 0);
+        if (kb == 0) stamp(eprof, 1);
+        uint8_t* dst = rdst + kb * SLOT;
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          const uint4 xv = *reinterpret_cast<const uint4*>(dst + sw128(lrow, (c32 & 1) * 4 + q4));
+        for (int q8 = 0; q8 < 8; ++q8) {
+          uint4* slot16 = reinterpret_cast<uint4*>(dst + sw128(lrow, q8));
+          const uint4 xv = *slot16;
           const __nv_bfloat162* xp = reinterpret_cast<const __nv_bfloat162*>(&xv);
           float rr[8];
 #pragma unroll
           for (int h = 0; h < 4; ++h) {
             const float2 xf = __bfloat1622float2(xp[h]);
-            rr[2 * h] = xf.x - v[q4 * 8 + 2 * h] * inv;
-            rr[2 * h + 1] = xf.y - v[q4 * 8 + 2 * h + 1] * inv;
+            rr[2 * h] = xf.x - v[q8 * 8 + 2 * h] * inv;
+            rr[2 * h + 1] = xf.y - v[q8 * 8 + 2 * h + 1] * inv;
           }
-          *reinterpret_cast<uint4*>(dst + sw128(lrow, (c32 & 1) * 4 + q4)) = pack8(rr);
+          *slot16 = pack8(rr);
         }
       }
     }
@@ -416,50 +418,48 @@ __global__ void __launch_bounds__(FT, 1) attention_layer_tc_kernel(const AttnLay
     xch[tid] = bo[tid];
     epi_bar();
 
-    // ---- out = x + relu(acc + bo): thread = token row, 128-bit stores into the layer's slice of att_cat
+    // ---- out = x + relu(acc + bo), formed in place over x and handed to TMA one [128 x 64] tile at a time
     acquire(C_OUT);
     stamp(eprof, 13);
-    mbar_wait(bar(F_XO), 0);
-    stamp(eprof, 16);
     {
       float* yf = p.yf ? p.yf + grow * p.ldyf : nullptr;
 #pragma unroll 1
-      for (int c32 = 0; c32 < 8; ++c32) {
-        float v[32];
-        tmem_ld32(t_row + c32 * 32, v);
-        uint8_t* dst = rdst + (c32 >> 1) * SLOT;
+      for (int kb = 0; kb < 4; ++kb) {
+        float v[64];
+        tmem_ld64(t_row + kb * 64, v);
+        mbar_wait(bar(F_XO + kb), 0);
+        if (kb == 0) stamp(eprof, 16);
+        uint8_t* dst = rdst + kb * SLOT;
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          uint4* slot16 = reinterpret_cast<uint4*>(dst + sw128(lrow, (c32 & 1) * 4 + q4));
+        for (int q8 = 0; q8 < 8; ++q8) {
+          uint4* slot16 = reinterpret_cast<uint4*>(dst + sw128(lrow, q8));
           const uint4 xv = *slot16;
           const __nv_bfloat162* xp = reinterpret_cast<const __nv_bfloat162*>(&xv);
-          const float* bb = xch + c32 * 32 + q4 * 8;
+          const float* bb = xch + kb * 64 + q8 * 8;
           float o8[8];
 #pragma unroll
           for (int h = 0; h < 4; ++h) {
             const float2 xf = __bfloat1622float2(xp[h]);
-            o8[2 * h] = xf.x + fmaxf(v[q4 * 8 + 2 * h] + bb[2 * h], 0.f);
-            o8[2 * h + 1] = xf.y + fmaxf(v[q4 * 8 + 2 * h + 1] + bb[2 * h + 1], 0.f);
+            o8[2 * h] = xf.x + fmaxf(v[q8 * 8 + 2 * h] + bb[2 * h], 0.f);
+            o8[2 * h + 1] = xf.y + fmaxf(v[q8 * 8 + 2 * h + 1] + bb[2 * h + 1], 0.f);
           }
           *slot16 = pack8(o8);
           if (yf) {
-            *reinterpret_cast<float4*>(yf + c32 * 32 + q4 * 8) = make_float4(o8[0], o8[1], o8[2], o8[3]);
-            *reinterpret_cast<float4*>(yf + c32 * 32 + q4 * 8 + 4) = make_float4(o8[4], o8[5], o8[6], o8[7]);
+            *reinterpret_cast<float4*>(yf + kb * 64 + q8 * 8) = make_float4(o8[0], o8[1], o8[2], o8[3]);
+            *reinterpret_cast<float4*>(yf + kb * 64 + q8 * 8 + 4) = make_float4(o8[4], o8[5], o8[6], o8[7]);
           }
+        }
+        fence_proxy_async();
+        asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory");
+        if (lrow == 0) {
+          tma_store(&tmy, kb * 64, (int)row0 + qb * 128, rslots + kb * SLOT);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       }
     }
     tc_fence_before();
-    // the block's output tile is complete in its 4 slots: one thread hands it to TMA
-    fence_proxy_async();
-    asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory");
-    if (lrow == 0) {
-      const uint32_t src = qb == 0 ? rb : ra;
-#pragma unroll
-      for (int kb = 0; kb < 4; ++kb) tma_store(&tmy, kb * 64, (int)row0 + qb * 128, src + kb * SLOT);
-      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-    }
+    stamp(eprof, 17);
+    if (lrow == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     stamp(eprof, 14);
   }
   __syncthreads();   // every TMEM read has retired, the TMA stores have read their tiles
@@ -533,7 +533,7 @@ int launch_attention_layer_tc(const AttnLayerTc& p_in, int clouds, cudaStream_t 
 }  // namespace pz
 
 // diagnostics: a device buffer of 64 int64 that CTA 0 of every following fused attention-layer launch fills with SM
-// clock stamps (slots 0-14 and 16 epilogue thread 0, 15 kernel entry, 32-41 the MMA issuer); null switches it off
+// clock stamps (slots 0-14, 16, 17 epilogue thread 0, 15 kernel entry, 32-41 the MMA issuer); null switches it off
 extern "C" int pz_profile_attention_timeline(long long* device_buf_or_null) {
   pz::g_attn_timeline = device_buf_or_null;
   return 0;

@@ -15,7 +15,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from puzzlenet_b200 import _lib  # noqa: E402
 
 EPI = ["start", "x back for r", "q|k acc ready", "q|k written", "v^T acc ready", "v^T written", "S ready", "P0 written",
-       "P1 max done", "P v 0 done", "P1 written", "P v 1 done", "r written", "out acc ready", "out handed to TMA"]
+       "P1 max done", "P v 0 done", "P1 written", "P v 1 done", "r written", "out acc ready", "TMA stores have read"]
 MMA = {32: "mma start", 33: "phase 1 issued", 34: "v^T ch0 issued", 35: "q|k drained", 36: "v^T issued", 37: "v^T drained",
        38: "P0 ready", 39: "P1 ready", 40: "r ready", 41: "out issued"}
 
@@ -85,7 +85,7 @@ def main():
 def report(t, B, ms_call):
     t0 = t[15]
     mhz = 1965.0
-    rows = [(t[i] - t0, "epi", EPI[i]) for i in range(len(EPI))] + [(t[16] - t0, "epi", "x back for out")] + [(t[k] - t0, "mma", v) for k, v in MMA.items()]
+    rows = [(t[i] - t0, "epi", EPI[i]) for i in range(len(EPI))] + [(t[16] - t0, "epi", "x back for out"), (t[17] - t0, "epi", "out tiles formed")] + [(t[k] - t0, "mma", v) for k, v in MMA.items()]
     rows.sort()
     for cyc, who, what in rows:
         print(f"{cyc:8d} cyc {cyc / mhz:7.2f} us  {who}  {what}")
