@@ -63,9 +63,9 @@ int pz_device_arch(void);
 long long pz_launch_count(void);
 int pz_profile_enable(int on);
 int pz_profile_collect(double* ms_host, const char** names_host, int* calls_host, int max_stages);
-/* Kernel-internal timeline of the fused attention layer (attention_layer_tc.cu): while a device buffer of 64 int64 is
- * registered, CTA 0 of every such launch stores SM clock stamps of its phase boundaries there (slots 0-14: epilogue
- * thread 0, 32-41: the MMA-issuing thread).  NULL switches it off (the default). */
+/* Kernel-internal timeline of the fused attention layer (attention_layer_tc.cu): while a device buffer of 64 + 2 * clouds
+ * int64 is registered, CTA 0 of every such launch stores SM clock stamps of its phase boundaries there (slots 0-17:
+ * epilogue thread 0, 32-41: the MMA-issuing thread) and every CTA c its %globaltimer at entry / exit (64 + 2c, 65 + 2c).  NULL switches it off (the default). */
 int pz_profile_attention_timeline(long long* device_buf_or_null);
 
 /* ---------------------------------------------------------------- geometry */

@@ -99,6 +99,11 @@ __global__ void __launch_bounds__(FT, 1) attention_layer_tc_kernel(const AttnLay
   const int cloud = blockIdx.x, set = cloud / p.clouds_per_set;
   const size_t row0 = (size_t)cloud * FL;
   stamp(tid == 0 ? p.prof : nullptr, 15);
+  if (p.prof != nullptr && tid == 0) {   // every CTA: %globaltimer (ns) at entry / exit, slots 64 + 2 cta, 65 + 2 cta
+    unsigned long long ns;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+    p.prof[64 + 2 * blockIdx.x] = (long long)ns;
+  }
 
   auto slot_of = [&](int t) -> uint32_t {
     if (t < 4) return rb + t * SLOT;
@@ -463,6 +468,11 @@ __global__ void __launch_bounds__(FT, 1) attention_layer_tc_kernel(const AttnLay
     stamp(eprof, 14);
   }
   __syncthreads();   // every TMEM read has retired, the TMA stores have read their tiles
+  if (p.prof != nullptr && tid == 0) {
+    unsigned long long ns;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+    p.prof[65 + 2 * blockIdx.x] = (long long)ns;
+  }
   if (warp == 0) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
@@ -532,7 +542,7 @@ int launch_attention_layer_tc(const AttnLayerTc& p_in, int clouds, cudaStream_t 
 
 }  // namespace pz
 
-// diagnostics: a device buffer of 64 int64 that CTA 0 of every following fused attention-layer launch fills with SM
+// diagnostics: a device buffer of 64 + 2 * clouds int64 that CTA 0 of every following fused attention-layer launch fills with SM
 // clock stamps (slots 0-14, 16, 17 epilogue thread 0, 15 kernel entry, 32-41 the MMA issuer); null switches it off
 extern "C" int pz_profile_attention_timeline(long long* device_buf_or_null) {
   pz::g_attn_timeline = device_buf_or_null;

@@ -144,20 +144,35 @@ int launch_fps(const float* xyz, int B, int N, const int64_t* start, int S, int6
 }
 
 // ======================================================================================
-// kNN: one warp per query.  Keys are (dist_bits << 32) | index, so one unsigned 64-bit
-// compare orders by (distance, index).  The warp keeps its current best 32 keys sorted
-// across lanes; candidates that beat the 32nd key are compacted (ballot + popc) into a
-// per-warp queue and folded in 32 at a time with a bitonic sort + bitonic merge
-// (WarpSelect-style), so the [B,S,N] distance matrix of pointnet_util.py:118 never exists.
+// kNN: one warp per query.  Keys are (distance bits, index) pairs, ordered by distance and
+// then index.  The warp keeps its current best 32 keys sorted across lanes.  Per sub-chunk
+// of 1024 candidates (32 per lane, distances kept in registers):
+//   pass 1   distances + each lane's two smallest (m0 <= m1);
+//   bound    the current 32nd distance if one is known, else a bisection on the bit pattern
+//            for the smallest x (to 1/256 of [min m1, max m0]) with at least 32 of the 64
+//            lane minima <= x: an upper bound of the true 32nd distance that typically admits
+//            only ~36 candidates;
+//   compact  every lane counts its candidates <= bound, one warp scan gives each lane its
+//            slot range in the per-warp queue (no per-iteration ballots), the survivors are
+//            written with predicated stores;
+//   fold     first sub-chunk: one bitonic sort of 32 queue entries becomes the sorted list,
+//            the few extra entries are inserted one by one (shift by shuffle); later
+//            sub-chunks insert their few improvements the same way; more than 12 pending
+//            entries go through the bitonic sort + merge network 32 at a time.
+// More than 64 candidates under the bound (heavy distance ties) take the incremental path:
+// ballot compaction with a merge whenever the queue fills.  The [B,S,N] distance matrix of
+// pointnet_util.py:118 never exists.
 // ======================================================================================
 constexpr int KNN_WARPS = 8;      // warps per CTA
 constexpr int KNN_QPW = 4;        // queries per warp (amortises staging the cloud in shared memory)
 constexpr int KNN_CHUNK = 2048;   // points staged in smem per pass
+constexpr int KNN_PSTRIDE = KNN_CHUNK + 4;   // x / y / z planes, offset by 4 banks so the AoS -> SoA staging stores spread
 
 __device__ __forceinline__ void knn_merge_inl(unsigned& td, unsigned& ti, unsigned cd, unsigned ci, int lane, unsigned kmask);
-// Out-of-line wrapper: the merge network is ~200 instructions and is reached from inside fully unrolled
+// Out-of-line wrappers: the networks are ~120 / ~200 instructions and are reached from inside unrolled
 // candidate loops; one shared copy keeps the kernel inside the instruction cache.
 __device__ __noinline__ uint2 knn_merge_call(unsigned td, unsigned ti, unsigned cd, unsigned ci, int lane, unsigned kmask);
+__device__ __noinline__ uint2 knn_sort_call(unsigned cd, unsigned ci, unsigned kmask);
 __device__ __forceinline__ void knn_merge(unsigned& td, unsigned& ti, unsigned cd, unsigned ci, int lane, unsigned kmask) {
   const uint2 r = knn_merge_call(td, ti, cd, ci, lane, kmask);
   td = r.x;
@@ -186,14 +201,18 @@ __device__ __forceinline__ unsigned bitonic_keep_mask(int lane) {
     }
   return m;
 }
-// fold 32 candidate keys (one per lane, any order) into the sorted top-32 (td, ti)
-__device__ __forceinline__ void knn_merge_inl(unsigned& td, unsigned& ti, unsigned cd, unsigned ci, int lane, unsigned kmask) {
+// 32 keys (one per lane, any order) -> ascending across lanes
+__device__ __forceinline__ void knn_sort_inl(unsigned& cd, unsigned& ci, unsigned kmask) {
   int s = 0;
 #pragma unroll
   for (int k = 2; k <= 32; k <<= 1) {
 #pragma unroll
     for (int j = k >> 1; j > 0; j >>= 1, ++s) cx_stage(cd, ci, j, (kmask >> s) & 1u);
   }
+}
+// fold 32 candidate keys (one per lane, any order) into the sorted top-32 (td, ti)
+__device__ __forceinline__ void knn_merge_inl(unsigned& td, unsigned& ti, unsigned cd, unsigned ci, int lane, unsigned kmask) {
+  knn_sort_inl(cd, ci, kmask);
   const unsigned rd = __shfl_sync(0xffffffffu, cd, 31 - lane), ri = __shfl_sync(0xffffffffu, ci, 31 - lane);
   const bool lt = key_less(rd, ri, td, ti);   // elementwise min of ascending top and descending candidates:
   td = lt ? rd : td;                          // a bitonic sequence holding the 32 smallest of the union
@@ -206,6 +225,18 @@ __device__ __noinline__ uint2 knn_merge_call(unsigned td, unsigned ti, unsigned 
   knn_merge_inl(td, ti, cd, ci, lane, kmask);
   return make_uint2(td, ti);
 }
+__device__ __noinline__ uint2 knn_sort_call(unsigned cd, unsigned ci, unsigned kmask) {
+  knn_sort_inl(cd, ci, kmask);
+  return make_uint2(cd, ci);
+}
+// insert one key (the same in every lane) into the ascending list: lanes past its place shift up by one
+__device__ __forceinline__ void knn_insert(unsigned& td, unsigned& ti, unsigned xd, unsigned xi, int lane) {
+  const unsigned pd = __shfl_up_sync(0xffffffffu, td, 1), pi = __shfl_up_sync(0xffffffffu, ti, 1);
+  const bool lt = key_less(xd, xi, td, ti);
+  const bool ltp = lane > 0 && key_less(xd, xi, pd, pi);
+  td = lt ? (ltp ? pd : xd) : td;
+  ti = lt ? (ltp ? pi : xi) : ti;
+}
 
 __global__ void __launch_bounds__(KNN_WARPS * 32) knn_kernel(const float* __restrict__ query,
                                                              const float* __restrict__ xyz, int S,
@@ -213,9 +244,9 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_kernel(const float* __rest
                                                              int64_t* __restrict__ out64,
                                                              int* __restrict__ out_rows32,
                                                              float* __restrict__ out_d2) {
-  // the cloud is staged as raw xyz triples (coalesced copy, no index arithmetic); point i is read at words
-  // 3i..3i+2: stride 3 is coprime with the 32 banks, so the three scalar reads per lane are conflict-free
-  __shared__ float pts[KNN_CHUNK * 3];
+  // the cloud is staged as x / y / z planes: lane l reads points 4(32 t + l) .. +3 of a sub-chunk with three
+  // 128-bit loads
+  __shared__ __align__(16) float pts[3 * KNN_PSTRIDE];
   __shared__ unsigned qd[KNN_WARPS][64], qi[KNN_WARPS][64];
   const int b = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -227,14 +258,17 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_kernel(const float* __rest
   const unsigned lt_mask = (1u << lane) - 1u;
   // per-query selection state lives in registers while the query is being scanned and is parked in shared
   // memory between chunks (only clouds larger than KNN_CHUNK points have more than one chunk); the query loop
-  // is deliberately not unrolled so that the two merge networks are emitted once (instruction-cache footprint)
+  // is deliberately not unrolled so that the networks are emitted once (instruction-cache footprint)
   __shared__ unsigned park_d[KNN_WARPS][KNN_QPW][32], park_i[KNN_WARPS][KNN_QPW][32];
 
   for (int base = 0; base < N; base += KNN_CHUNK) {
     const int cnt = min(KNN_CHUNK, N - base);
     const bool first = base == 0, last = base + KNN_CHUNK >= N;
     __syncthreads();
-    for (int i = threadIdx.x; i < cnt * 3; i += KNN_WARPS * 32) pts[i] = p[(size_t)base * 3 + i];
+    for (int i = threadIdx.x; i < cnt * 3; i += KNN_WARPS * 32) {
+      const int pi = i / 3;
+      pts[(i - 3 * pi) * KNN_PSTRIDE + pi] = p[(size_t)base * 3 + i];
+    }
     __syncthreads();
 #pragma unroll 1
     for (int w = 0; w < KNN_QPW; ++w) {
@@ -245,25 +279,25 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_kernel(const float* __rest
       unsigned td = first ? 0xffffffffu : park_d[warp][w][lane];   // lane l holds the l-th smallest key so far
       unsigned ti = first ? 0xffffffffu : park_i[warp][w][lane];
       unsigned tau = __shfl_sync(0xffffffffu, td, 31);              // distance bits of the current 32nd smallest
-      int qn = 0;
-      // Two passes over sub-chunks of 1024 candidates (32 per lane, distances kept in registers):
-      //  pass 1  distances + each lane's two smallest (m0 <= m1);
-      //  bound   while no 32nd distance is known yet, bisect on the bit pattern for the smallest x (to 1/256 of
-      //          [min m1, max m0]) with at least 32 of the 64 lane minima <= x: an upper bound of the true 32nd
-      //          distance that typically admits only ~36 candidates;
-      //  pass 2  candidates <= bound are compacted into the warp queue and folded into the sorted top-32 by
-      //          bitonic sort + merge -- about two merges per query instead of one per ~30 admitted candidates.
+#pragma unroll 1
       for (int sub = 0; sub < cnt; sub += 1024) {
-        unsigned db[32];
+        unsigned db[32];   // db[4 t4 + j] = candidate sub + 4 (32 t4 + lane) + j
         unsigned m0 = 0xffffffffu, m1 = 0xffffffffu;
 #pragma unroll
-        for (int t = 0; t < 32; ++t) {
-          const int i = sub + t * 32 + lane;
-          unsigned x = 0xffffffffu;
-          if (i < cnt) x = __float_as_uint(sqdist3(qx, qy, qz, pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]));
-          db[t] = x;
-          m1 = min(m1, max(m0, x));
-          m0 = min(m0, x);
+        for (int t4 = 0; t4 < 8; ++t4) {
+          const int i0 = sub + (t4 * 32 + lane) * 4;
+          const float4 X = *reinterpret_cast<const float4*>(pts + i0);
+          const float4 Y = *reinterpret_cast<const float4*>(pts + KNN_PSTRIDE + i0);
+          const float4 Z = *reinterpret_cast<const float4*>(pts + 2 * KNN_PSTRIDE + i0);
+          const float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w}, zs[4] = {Z.x, Z.y, Z.z, Z.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            unsigned x = __float_as_uint(sqdist3(qx, qy, qz, xs[j], ys[j], zs[j]));
+            if (i0 + j >= cnt) x = 0xffffffffu;   // past the chunk: whatever the planes hold there is ignored
+            db[t4 * 4 + j] = x;
+            m1 = min(m1, max(m0, x));
+            m0 = min(m0, x);
+          }
         }
         unsigned thr = tau;
         if (thr == 0xffffffffu) {   // warp-uniform
@@ -279,15 +313,61 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_kernel(const float* __rest
           }
           thr = hi;
         }
+        thr = min(thr, 0xfffffffeu);   // the "no candidate" pattern never passes
+        int mine = 0;
 #pragma unroll
+        for (int t = 0; t < 32; ++t) mine += db[t] <= thr ? 1 : 0;
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int v = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += v;
+        }
+        const int c = __shfl_sync(0xffffffffu, incl, 31);
+        if (c == 0) continue;           // warp-uniform
+        if (c <= 64) {
+          int pos = incl - mine;
+#pragma unroll
+          for (int t = 0; t < 32; ++t) {
+            if (db[t] <= thr) {
+              myd[pos] = db[t];
+              myi[pos] = (unsigned)(base + sub + ((t >> 2) * 32 + lane) * 4 + (t & 3));
+              ++pos;
+            }
+          }
+          __syncwarp();
+          int o = 0;
+          if (first && sub == 0 && c >= 32) {   // nothing selected yet: the sorted first 32 entries are the list
+            const uint2 r = knn_sort_call(myd[lane], myi[lane], kmask);
+            td = r.x;
+            ti = r.y;
+            o = 32;
+          }
+          if (c - o > 12) {
+            for (; o < c; o += 32)
+              knn_merge(td, ti, o + lane < c ? myd[o + lane] : 0xffffffffu, o + lane < c ? myi[o + lane] : 0xffffffffu, lane, kmask);
+          } else {
+#pragma unroll 1
+            for (; o < c; ++o) knn_insert(td, ti, myd[o], myi[o], lane);
+          }
+          tau = __shfl_sync(0xffffffffu, td, 31);
+          __syncwarp();                 // the queue is rewritten by the next sub-chunk / query
+          continue;
+        }
+        // ---- incremental path: more than 64 candidates under the bound (ties)
+        int qn = 0;
+#pragma unroll 1
         for (int t = 0; t < 32; ++t) {
-          const bool pass = db[t] <= thr && db[t] != 0xffffffffu;
+          unsigned dt = 0;               // db[t] without dynamic register indexing
+#pragma unroll
+          for (int u = 0; u < 32; ++u) dt = u == t ? db[u] : dt;
+          const bool pass = dt <= thr;
           const unsigned m = __ballot_sync(0xffffffffu, pass);
           if (m == 0u) continue;
           if (pass) {
             const int pos = qn + __popc(m & lt_mask);
-            myd[pos] = db[t];
-            myi[pos] = (unsigned)(base + sub + t * 32 + lane);
+            myd[pos] = dt;
+            myi[pos] = (unsigned)(base + sub + ((t >> 2) * 32 + lane) * 4 + (t & 3));
           }
           qn += __popc(m);
           __syncwarp();
@@ -309,12 +389,9 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_kernel(const float* __rest
         if (qn > 0) {   // flush so that the next sub-chunk starts from an exact 32nd distance
           knn_merge(td, ti, lane < qn ? myd[lane] : 0xffffffffu, lane < qn ? myi[lane] : 0xffffffffu, lane, kmask);
           tau = __shfl_sync(0xffffffffu, td, 31);
-          qn = 0;
           __syncwarp();
         }
       }
-      if (qn > 0) knn_merge(td, ti, lane < qn ? myd[lane] : 0xffffffffu, lane < qn ? myi[lane] : 0xffffffffu, lane, kmask);
-      __syncwarp();
       if (!last) {
         park_d[warp][w][lane] = td;
         park_i[warp][w][lane] = ti;

@@ -28,7 +28,7 @@ def main():
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     lib = _lib.load()
-    tl = torch.zeros(64, device=dev, dtype=torch.int64)
+    tl = torch.zeros(64 + 2 * 4096, device=dev, dtype=torch.int64)
     if a.predict5:
         import types
         from puzzlenet_b200.model5_b import TouchedRegraster
@@ -92,6 +92,13 @@ def report(t, B, ms_call):
     flop = B * (2 * 256 * 256 * 384 + 2 * 256 * 256 * 64 + 2 * 256 * 256 * 256 + 2 * 256 * 256 * 256)
     span_us = (t[14] - t0) / mhz
     print(f"entry -> start {(t[0] - t0) / mhz:.2f} us")
+    ent = [t[64 + 2 * c] for c in range(B)]
+    ext = [t[65 + 2 * c] for c in range(B)]
+    e0 = min(ent)
+    spans = sorted(x - e for e, x in zip(ent, ext))
+    print(f"all CTAs (globaltimer): first entry -> last entry {(max(ent) - e0) / 1e3:.2f} us, first entry -> last exit "
+          f"{(max(ext) - e0) / 1e3:.2f} us, CTA span min/median/max {spans[0] / 1e3:.2f}/{spans[len(spans) // 2] / 1e3:.2f}/"
+          f"{spans[-1] / 1e3:.2f} us")
     print(json.dumps({"clouds": B, "ms_per_call_incl_conversions": ms_call, "cta0_span_us": span_us,
                       "tflops_if_all_ctas_like_cta0": flop / B * min(B, 148) / (span_us * 1e-6) / 1e12}))
 

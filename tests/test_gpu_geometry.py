@@ -76,7 +76,7 @@ def test_square_distance(pu, goldens):
 
 
 @pytest.mark.parametrize("B,S,N,K", [(2, 64, 300, 16), (3, 512, 1024, 32), (2, 256, 512, 32), (1, 40, 32, 32),
-                                     (1, 7, 5000, 32), (2, 100, 2049, 1)])
+                                     (1, 7, 5000, 32), (2, 100, 2049, 1), (2, 33, 1024, 5), (1, 50, 33, 32), (2, 64, 1500, 20)])
 def test_knn_vs_oracle(pu, B, S, N, K):
     g = torch.Generator().manual_seed(S + N)
     xyz = torch.rand(B, N, 3, generator=g) - 0.5
@@ -88,6 +88,21 @@ def test_knn_vs_oracle(pu, B, S, N, K):
     assert idx.dtype == torch.int64 and idx.shape == (B, S, K)
     assert torch.equal(d2.cpu(), ref_d), "distances must be bit-exact (fp32, no FMA)"
     assert torch.equal(idx.cpu(), ref_idx), "order is (distance, index) ascending, same as the stable oracle"
+
+
+@pytest.mark.parametrize("N,dups", [(1024, 200), (1024, 1024), (3000, 70), (512, 40)])
+def test_knn_heavy_ties(pu, N, dups):
+    """Many coincident points: more than 64 candidates tie under the selection bound (the incremental path of
+    knn_kernel); order among equal distances is by index, as in the stable oracle."""
+    g = torch.Generator().manual_seed(N + dups)
+    xyz = torch.rand(2, N, 3, generator=g) - 0.5
+    xyz[0, :dups] = xyz[0, 0]
+    xyz[1, N - dups:] = xyz[1, N - 1]
+    q = torch.cat([xyz[:, :40], xyz[:, N - 40:]], 1).clone()
+    ref_idx, ref_d = po.knn_select(po.square_distance(q, xyz), 32)
+    idx, d2 = pu.knn_point(32, xyz.to(DEV), q.to(DEV), return_dist=True)
+    assert torch.equal(d2.cpu(), ref_d)
+    assert torch.equal(idx.cpu(), ref_idx)
 
 
 def test_knn_rejects_k_above_32(pu):
