@@ -238,7 +238,7 @@ __device__ __forceinline__ void knn_insert(unsigned& td, unsigned& ti, unsigned 
   ti = lt ? (ltp ? pi : xi) : ti;
 }
 
-__global__ void __launch_bounds__(KNN_WARPS * 32) knn_kernel(const float* __restrict__ query,
+__global__ void __launch_bounds__(KNN_WARPS * 32, 3) knn_kernel(const float* __restrict__ query,
                                                              const float* __restrict__ xyz, int S,
                                                              int N, int K,
                                                              int64_t* __restrict__ out64,
@@ -247,14 +247,13 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_kernel(const float* __rest
   // the cloud is staged as x / y / z planes: lane l reads points 4(32 t + l) .. +3 of a sub-chunk with three
   // 128-bit loads
   __shared__ __align__(16) float pts[3 * KNN_PSTRIDE];
-  __shared__ unsigned qd[KNN_WARPS][64], qi[KNN_WARPS][64];
+  __shared__ uint2 qkey[KNN_WARPS][64];   // per-warp candidate queue: (distance bits, index)
   const int b = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int q0 = (blockIdx.x * KNN_WARPS + warp) * KNN_QPW;
   const float* p = xyz + (size_t)b * N * 3;
   const unsigned kmask = bitonic_keep_mask(lane);
-  unsigned* myd = qd[warp];
-  unsigned* myi = qi[warp];
+  uint2* myq = qkey[warp];
   const unsigned lt_mask = (1u << lane) - 1u;
   // per-query selection state lives in registers while the query is being scanned and is parked in shared
   // memory between chunks (only clouds larger than KNN_CHUNK points have more than one chunk); the query loop
@@ -269,6 +268,10 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_kernel(const float* __rest
       const int pi = i / 3;
       pts[(i - 3 * pi) * KNN_PSTRIDE + pi] = p[(size_t)base * 3 + i];
     }
+    // the tail of the last 1024-candidate sub-chunk is filled with far-away points (distance ~3e36, index >= N):
+    // they order after every real point, so they can only surface past the N-th neighbour, which K <= N never reads
+    for (int i = cnt + threadIdx.x; i < ((cnt + 1023) & ~1023); i += KNN_WARPS * 32)
+      pts[i] = pts[KNN_PSTRIDE + i] = pts[2 * KNN_PSTRIDE + i] = 1e18f;
     __syncthreads();
 #pragma unroll 1
     for (int w = 0; w < KNN_QPW; ++w) {
@@ -292,8 +295,7 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_kernel(const float* __rest
           const float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w}, zs[4] = {Z.x, Z.y, Z.z, Z.w};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            unsigned x = __float_as_uint(sqdist3(qx, qy, qz, xs[j], ys[j], zs[j]));
-            if (i0 + j >= cnt) x = 0xffffffffu;   // past the chunk: whatever the planes hold there is ignored
+            const unsigned x = __float_as_uint(sqdist3(qx, qy, qz, xs[j], ys[j], zs[j]));
             db[t4 * 4 + j] = x;
             m1 = min(m1, max(m0, x));
             m0 = min(m0, x);
@@ -307,7 +309,7 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_kernel(const float* __rest
 #pragma unroll 1
             for (int it = 0; it < 8 && lo < hi; ++it) {
               const unsigned mid = lo + ((hi - lo) >> 1);
-              const int c = __popc(__ballot_sync(0xffffffffu, m0 <= mid)) + __popc(__ballot_sync(0xffffffffu, m1 <= mid));
+              const int c = __reduce_add_sync(0xffffffffu, (m0 <= mid ? 1 : 0) + (m1 <= mid ? 1 : 0));
               if (c >= 32) hi = mid; else lo = mid + 1;
             }
           }
@@ -326,29 +328,32 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_kernel(const float* __rest
         const int c = __shfl_sync(0xffffffffu, incl, 31);
         if (c == 0) continue;           // warp-uniform
         if (c <= 64) {
-          int pos = incl - mine;
+          uint2* slot = myq + (incl - mine);
+          const unsigned idx0 = (unsigned)(base + sub + lane * 4);
 #pragma unroll
           for (int t = 0; t < 32; ++t) {
-            if (db[t] <= thr) {
-              myd[pos] = db[t];
-              myi[pos] = (unsigned)(base + sub + ((t >> 2) * 32 + lane) * 4 + (t & 3));
-              ++pos;
-            }
+            if (db[t] <= thr) *slot++ = make_uint2(db[t], idx0 + (unsigned)((t >> 2) * 128 + (t & 3)));
           }
           __syncwarp();
           int o = 0;
           if (first && sub == 0 && c >= 32) {   // nothing selected yet: the sorted first 32 entries are the list
-            const uint2 r = knn_sort_call(myd[lane], myi[lane], kmask);
+            const uint2 e = myq[lane];
+            const uint2 r = knn_sort_call(e.x, e.y, kmask);
             td = r.x;
             ti = r.y;
             o = 32;
           }
           if (c - o > 12) {
-            for (; o < c; o += 32)
-              knn_merge(td, ti, o + lane < c ? myd[o + lane] : 0xffffffffu, o + lane < c ? myi[o + lane] : 0xffffffffu, lane, kmask);
+            for (; o < c; o += 32) {
+              const uint2 e = o + lane < c ? myq[o + lane] : make_uint2(0xffffffffu, 0xffffffffu);
+              knn_merge(td, ti, e.x, e.y, lane, kmask);
+            }
           } else {
 #pragma unroll 1
-            for (; o < c; ++o) knn_insert(td, ti, myd[o], myi[o], lane);
+            for (; o < c; ++o) {
+              const uint2 e = myq[o];
+              knn_insert(td, ti, e.x, e.y, lane);
+            }
           }
           tau = __shfl_sync(0xffffffffu, td, 31);
           __syncwarp();                 // the queue is rewritten by the next sub-chunk / query
@@ -364,30 +369,26 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) knn_kernel(const float* __rest
           const bool pass = dt <= thr;
           const unsigned m = __ballot_sync(0xffffffffu, pass);
           if (m == 0u) continue;
-          if (pass) {
-            const int pos = qn + __popc(m & lt_mask);
-            myd[pos] = dt;
-            myi[pos] = (unsigned)(base + sub + ((t >> 2) * 32 + lane) * 4 + (t & 3));
-          }
+          if (pass)
+            myq[qn + __popc(m & lt_mask)] = make_uint2(dt, (unsigned)(base + sub + ((t >> 2) * 32 + lane) * 4 + (t & 3)));
           qn += __popc(m);
           __syncwarp();
           if (qn >= 32) {
-            knn_merge(td, ti, myd[lane], myi[lane], lane, kmask);
+            const uint2 e = myq[lane];
+            knn_merge(td, ti, e.x, e.y, lane, kmask);
             tau = __shfl_sync(0xffffffffu, td, 31);
             thr = min(thr, tau);
             const int rem = qn - 32;
-            const unsigned cd = lane < rem ? myd[32 + lane] : 0u, ci = lane < rem ? myi[32 + lane] : 0u;
+            const uint2 carry = lane < rem ? myq[32 + lane] : make_uint2(0u, 0u);
             __syncwarp();
-            if (lane < rem) {
-              myd[lane] = cd;
-              myi[lane] = ci;
-            }
+            if (lane < rem) myq[lane] = carry;
             __syncwarp();
             qn = rem;
           }
         }
         if (qn > 0) {   // flush so that the next sub-chunk starts from an exact 32nd distance
-          knn_merge(td, ti, lane < qn ? myd[lane] : 0xffffffffu, lane < qn ? myi[lane] : 0xffffffffu, lane, kmask);
+          const uint2 e = lane < qn ? myq[lane] : make_uint2(0xffffffffu, 0xffffffffu);
+          knn_merge(td, ti, e.x, e.y, lane, kmask);
           tau = __shfl_sync(0xffffffffu, td, 31);
           __syncwarp();
         }
