@@ -82,6 +82,143 @@ __global__ void __launch_bounds__(128) stem_kernel(const float* __restrict__ xyz
   }
 }
 
+__device__ __forceinline__ void stem_mma(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+               "{%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+constexpr int STEM_WS = 72;
+constexpr size_t STEM_TC_SMEM = 4 * 32 * STEM_WS * sizeof(float) + 64 * sizeof(float4) + 64 * sizeof(float) +
+                                2 * 64 * STEM_WS * sizeof(__nv_bfloat16);
+// bf16-path stem: layer 1 (3 -> 64) + BN + ReLU is computed straight into mma.sync A fragments, layer 2 (64 -> 64) runs
+// on the tensor cores (m16n8k16, bf16 x bf16 -> fp32; 1 GFLOP per forward does not warrant a tcgen05 pipeline) as a split
+// product (h = hi + lo, W = hi + lo; hi*hi + hi*lo + lo*hi, error ~2^-17) because x_feature is an output and feeds both
+// the grouped MLP and the boundary heads, BN + ReLU on the accumulator fragments, and the [32 points x 64] tile of each warp leaves through shared memory as one
+// contiguous 8 KB (fp32) + 4 KB (bf16) block.  The fp32 path keeps stem_kernel (FFMA, 1e-4 parity).
+__global__ void __launch_bounds__(128) stem_tc_kernel(const float* __restrict__ xyz, StemW wa, StemW wb,
+                                                      int clouds_per_set, float* __restrict__ out,
+                                                      __nv_bfloat16* __restrict__ out_b) {
+  constexpr int WS = STEM_WS;   // padded row strides: conflict-free fragment loads / stores
+  extern __shared__ __align__(16) uint8_t stem_smem[];
+  float* stage_all = reinterpret_cast<float*>(stem_smem);                               // [4][32 * WS]
+  float4* w1p = reinterpret_cast<float4*>(stage_all + 4 * 32 * WS);                     // (w1[c][0..2], b1[c])
+  float* b2s = reinterpret_cast<float*>(w1p + 64);
+  __nv_bfloat16* w2b = reinterpret_cast<__nv_bfloat16*>(b2s + 64);                      // hi, then lo: [2][64 * WS]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
+  const size_t p0 = (size_t)blockIdx.x * 128;               // first point of the CTA
+  const int cloud = (int)(p0 / NPTS);                        // uniform per block (128 | 1024)
+  const int n0 = (int)(p0 - (size_t)cloud * NPTS) + warp * 32;
+  const StemW& w = (cloud / clouds_per_set) == 0 ? wa : wb;
+  for (int i = tid; i < 64 * 64; i += 128) {
+    const float wv = w.w2[i];
+    const __nv_bfloat16 hi = __float2bfloat16_rn(wv);
+    w2b[(i >> 6) * WS + (i & 63)] = hi;
+    w2b[64 * WS + (i >> 6) * WS + (i & 63)] = __float2bfloat16_rn(wv - __bfloat162float(hi));
+  }
+  if (tid < 64) {
+    w1p[tid] = make_float4(w.w1[tid * 3], w.w1[tid * 3 + 1], w.w1[tid * 3 + 2], w.b1[tid]);
+    b2s[tid] = w.b2[tid];
+  }
+  __syncthreads();
+  // this thread's four rows of the warp tile: g, g + 8, g + 16, g + 24
+  float x[4], y[4], z[4], a1[4], c1[4], a2[4], c2[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int r = g + 8 * j, n = n0 + r;
+    const float* pp = xyz + (p0 + warp * 32 + r) * 3;
+    x[j] = pp[0]; y[j] = pp[1]; z[j] = pp[2];
+    a1[j] = w.g1[n] * (1.0f / sqrtf(w.v1[n] + 1e-5f));   // eval-mode BatchNorm1d over the point index
+    c1[j] = w.be1[n] - w.m1[n] * a1[j];
+    a2[j] = w.g2[n] * (1.0f / sqrtf(w.v2[n] + 1e-5f));
+    c2[j] = w.be2[n] - w.m2[n] * a2[j];
+  }
+  // A fragments of h = relu(bn1(W1 xyz + b1)): [2 m-tiles][4 k-tiles][4 regs]
+  uint32_t af[2][4][4], al[2][4][4];
+#pragma unroll
+  for (int kt = 0; kt < 4; ++kt) {
+#pragma unroll
+    for (int h2 = 0; h2 < 2; ++h2) {
+      const int col = kt * 16 + h2 * 8 + q * 2;
+      const float4 wA = w1p[col], wB = w1p[col + 1];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float vA = wA.w, vB = wB.w;
+        vA = fmaf(wA.x, x[j], vA); vA = fmaf(wA.y, y[j], vA); vA = fmaf(wA.z, z[j], vA);
+        vB = fmaf(wB.x, x[j], vB); vB = fmaf(wB.y, y[j], vB); vB = fmaf(wB.z, z[j], vB);
+        const float hA = fmaxf(fmaf(vA, a1[j], c1[j]), 0.f), hB = fmaxf(fmaf(vB, a1[j], c1[j]), 0.f);
+        const __nv_bfloat162 hh = __floats2bfloat162_rn(hA, hB);
+        const float2 hf = __bfloat1622float2(hh);
+        const __nv_bfloat162 hl = __floats2bfloat162_rn(hA - hf.x, hB - hf.y);
+        af[j >> 1][kt][(j & 1) + 2 * h2] = *reinterpret_cast<const uint32_t*>(&hh);
+        al[j >> 1][kt][(j & 1) + 2 * h2] = *reinterpret_cast<const uint32_t*>(&hl);
+      }
+    }
+  }
+  float acc[2][8][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.f;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+    for (int kt = 0; kt < 4; ++kt) {
+      const __nv_bfloat16* bp = w2b + (nt * 8 + g) * WS + kt * 16 + q * 2;
+      const uint32_t b0 = *reinterpret_cast<const uint32_t*>(bp), b1 = *reinterpret_cast<const uint32_t*>(bp + 8);
+      const uint32_t l0 = *reinterpret_cast<const uint32_t*>(bp + 64 * WS), l1 = *reinterpret_cast<const uint32_t*>(bp + 64 * WS + 8);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        stem_mma(acc[mt][nt], al[mt][kt], b0, b1);   // small terms first
+        stem_mma(acc[mt][nt], af[mt][kt], l0, l1);
+        stem_mma(acc[mt][nt], af[mt][kt], b0, b1);
+      }
+    }
+  }
+  // epilogue on the fragments: + b2, BN2, ReLU -> the warp's staging tile
+  float* st = stage_all + warp * 32 * WS;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    const int col = nt * 8 + q * 2;
+    const float bA = b2s[col], bB = b2s[col + 1];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const int j = 2 * mt + hf;   // row g + 8 j
+        float2 o;
+        o.x = fmaxf(fmaf(acc[mt][nt][2 * hf] + bA, a2[j], c2[j]), 0.f);
+        o.y = fmaxf(fmaf(acc[mt][nt][2 * hf + 1] + bB, a2[j], c2[j]), 0.f);
+        *reinterpret_cast<float2*>(st + (g + 8 * j) * WS + col) = o;
+      }
+    }
+  }
+  __syncwarp();
+  float* ot = out + (p0 + warp * 32) * 64;   // the warp's 32 rows are one contiguous 8 KB block
+#pragma unroll
+  for (int it = 0; it < 16; ++it) {
+    const int idx = it * 32 + lane, row = idx >> 4, c4 = idx & 15;
+    *reinterpret_cast<float4*>(ot + idx * 4) = *reinterpret_cast<const float4*>(st + row * WS + c4 * 4);
+  }
+  if (out_b) {
+    __nv_bfloat16* ob = out_b + (p0 + warp * 32) * 64;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int idx = it * 32 + lane, row = idx >> 3, c8 = idx & 7;
+      const float4 v0 = *reinterpret_cast<const float4*>(st + row * WS + c8 * 8);
+      const float4 v1 = *reinterpret_cast<const float4*>(st + row * WS + c8 * 8 + 4);
+      __nv_bfloat162 h0 = __floats2bfloat162_rn(v0.x, v0.y), h1 = __floats2bfloat162_rn(v0.z, v0.w);
+      __nv_bfloat162 h2 = __floats2bfloat162_rn(v1.x, v1.y), h3 = __floats2bfloat162_rn(v1.z, v1.w);
+      uint4 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+      pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+      *reinterpret_cast<uint4*>(ob + idx * 8) = pk;
+    }
+  }
+}
+
 // ------------------------------------------------- attention core (model5_b.py:67-75, :98-99)
 // One CTA per (cloud, 64 query rows): S = q k^T * scale in smem, row softmax, O = A v.
 // out = xres ? xres - O : O.   attn_mode: 0 none, 1 store A, 2 A += , 3 A = (A_old + A) * 0.25
@@ -766,7 +903,12 @@ static int encoder_forward_bf16(const PzEncoderWeights* w, int E, int B, const f
   prof_mark("knn2", sg, gl);
   PZ_CUDA(cudaEventRecord(ss->join_b, sg));
 
-  stem_kernel<<<C * NPTS / 128, 128, 0, st>>>(xyz, stem_of(wa), stem_of(wb), B, xfeat, s.xfeat_b);
+  static const bool stem_fp32 = getenv("PZ_STEM_FP32") && getenv("PZ_STEM_FP32")[0] == '1';   // A/B hook
+  if (stem_fp32) stem_kernel<<<C * NPTS / 128, 128, 0, st>>>(xyz, stem_of(wa), stem_of(wb), B, xfeat, s.xfeat_b);
+  else {
+    PZ_CUDA(cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STEM_TC_SMEM));
+    stem_tc_kernel<<<C * NPTS / 128, 128, STEM_TC_SMEM, st>>>(xyz, stem_of(wa), stem_of(wb), B, xfeat, s.xfeat_b);
+  }
   PZ_LAUNCH_CHECK();
   prof_mark("stem", st);
   {
