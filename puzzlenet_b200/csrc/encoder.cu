@@ -88,6 +88,7 @@ __device__ __forceinline__ void stem_mma(float (&d)[4], const uint32_t (&a)[4], 
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+constexpr int HD_REPS = 4;  // 128-point tiles per CTA (one weight conversion per 512 points; 512 | 1024: one cloud per CTA)
 constexpr int STEM_WS = 72;
 constexpr size_t STEM_TC_SMEM = 4 * 32 * STEM_WS * sizeof(float) + 64 * sizeof(float4) + 64 * sizeof(float) +
                                 2 * 64 * STEM_WS * sizeof(__nv_bfloat16);
@@ -106,9 +107,7 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const float* __restrict__ 
   float* b2s = reinterpret_cast<float*>(w1p + 64);
   __nv_bfloat16* w2b = reinterpret_cast<__nv_bfloat16*>(b2s + 64);                      // hi, then lo: [2][64 * WS]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
-  const size_t p0 = (size_t)blockIdx.x * 128;               // first point of the CTA
-  const int cloud = (int)(p0 / NPTS);                        // uniform per block (128 | 1024)
-  const int n0 = (int)(p0 - (size_t)cloud * NPTS) + warp * 32;
+  const int cloud = (int)(((size_t)blockIdx.x * HD_REPS * 128) / NPTS);   // uniform per block (512 | 1024)
   const StemW& w = (cloud / clouds_per_set) == 0 ? wa : wb;
   for (int i = tid; i < 64 * 64; i += 128) {
     const float wv = w.w2[i];
@@ -121,6 +120,10 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const float* __restrict__ 
     b2s[tid] = w.b2[tid];
   }
   __syncthreads();
+#pragma unroll 1
+  for (int rep = 0; rep < HD_REPS; ++rep) {
+  const size_t p0 = ((size_t)blockIdx.x * HD_REPS + rep) * 128;   // first point of this 128-point tile
+  const int n0 = (int)(p0 - (size_t)cloud * NPTS) + warp * 32;
   // this thread's four rows of the warp tile: g, g + 8, g + 16, g + 24
   float x[4], y[4], z[4], a1[4], c1[4], a2[4], c2[4];
 #pragma unroll
@@ -216,6 +219,8 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const float* __restrict__ 
       pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
       *reinterpret_cast<uint4*>(ob + idx * 8) = pk;
     }
+  }
+  __syncwarp();   // the staging tile is rewritten by the next repetition
   }
 }
 
@@ -705,6 +710,258 @@ __global__ void __launch_bounds__(128) head_seg_tail_kernel(const __nv_bfloat16*
   de[((size_t)b * 2 + 1) * NPTS + n] = o1;
 }
 
+// ---- bf16 path, boundary heads as two chained-MMA kernels (mma.sync m16n8k16; the accumulator fragments of one layer,
+// rounded to bf16, ARE the A fragments of the next, so activations never leave registers).  One warp = 32 points.
+constexpr int HD_WS = 72;   // padded bf16 row stride: conflict-free fragment loads
+
+// 32-point tile (contiguous 4 KB of a bf16 [P,64] tensor) -> padded smem tile -> A fragments
+__device__ __forceinline__ void head_load_tile(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* tile, int lane) {
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int idx = it * 32 + lane, row = idx >> 3, c8 = idx & 7;
+    *reinterpret_cast<uint4*>(tile + row * HD_WS + c8 * 8) = *reinterpret_cast<const uint4*>(src + idx * 8);
+  }
+}
+__device__ __forceinline__ void head_a_frags(const __nv_bfloat16* tile, int g, int q, uint32_t (&a)[2][4][4]) {
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int kt = 0; kt < 4; ++kt) {
+      const __nv_bfloat16* t0 = tile + (mt * 16 + g) * HD_WS + kt * 16 + q * 2;
+      a[mt][kt][0] = *reinterpret_cast<const uint32_t*>(t0);
+      a[mt][kt][1] = *reinterpret_cast<const uint32_t*>(t0 + 8 * HD_WS);
+      a[mt][kt][2] = *reinterpret_cast<const uint32_t*>(t0 + 8);
+      a[mt][kt][3] = *reinterpret_cast<const uint32_t*>(t0 + 8 * HD_WS + 8);
+    }
+}
+// acc[mt][nt] += A[mt] . W^T for NT n-tiles of a [NT*8, 64] bf16 weight block in smem (row stride HD_WS)
+template <int NT>
+__device__ __forceinline__ void head_layer(const uint32_t (&a)[2][4][4], const __nv_bfloat16* w, int g, int q,
+                                           float (&acc)[2][NT][4]) {
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+    for (int kt = 0; kt < 4; ++kt) {
+      const __nv_bfloat16* bp = w + (nt * 8 + g) * HD_WS + kt * 16 + q * 2;
+      const uint32_t b0 = *reinterpret_cast<const uint32_t*>(bp), b1 = *reinterpret_cast<const uint32_t*>(bp + 8);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) stem_mma(acc[mt][nt], a[mt][kt], b0, b1);
+    }
+}
+__device__ __forceinline__ uint32_t pack_bf2(float x, float y) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(x, y);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+// act(acc + bias) of a 64-wide layer, rounded to bf16 -> the next layer's A fragments
+__device__ __forceinline__ void head_next_frags(const float (&acc)[2][8][4], const float* bias, int q, bool relu,
+                                                uint32_t (&a)[2][4][4]) {
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const float bA = bias[nt * 8 + q * 2], bB = bias[nt * 8 + q * 2 + 1];
+      float v0 = acc[mt][nt][0] + bA, v1 = acc[mt][nt][1] + bB, v2 = acc[mt][nt][2] + bA, v3 = acc[mt][nt][3] + bB;
+      if (relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
+      a[mt][nt >> 1][(nt & 1) * 2] = pack_bf2(v0, v1);       // row g
+      a[mt][nt >> 1][(nt & 1) * 2 + 1] = pack_bf2(v2, v3);   // row g + 8
+    }
+}
+
+// MLPLocalPre{Fpc,Rpc} (model5_b.py:738-739): three 64 -> 64 layers (ReLU after the first two); writes the local
+// features (bf16 [P,64]) and, per CTA, the column maxima of its 128 points (tilemax [cloud][8][64]) for the global
+// max-pool of model5_b.py:741-744
+__global__ void __launch_bounds__(128) head_pre_tc_kernel(const __nv_bfloat16* __restrict__ xfeat_b, Mlp3W wa, Mlp3W wb,
+                                                          int B, __nv_bfloat16* __restrict__ local,
+                                                          float* __restrict__ tilemax) {
+  __shared__ __align__(16) __nv_bfloat16 ws[3][64 * HD_WS];
+  __shared__ __align__(16) __nv_bfloat16 tiles[4][32 * HD_WS];
+  __shared__ float bs[3][64];
+  __shared__ float cmax[4][64];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
+  const int cloud = (int)(((size_t)blockIdx.x * HD_REPS * 128) / NPTS);
+  const Mlp3W& w = cloud / B == 0 ? wa : wb;
+  const float* wsrc[3] = {w.w0, w.w1, w.w2};
+  const float* bsrc[3] = {w.b0, w.b1, w.b2};
+#pragma unroll
+  for (int l = 0; l < 3; ++l) {
+    for (int i = tid; i < 64 * 64; i += 128) ws[l][(i >> 6) * HD_WS + (i & 63)] = __float2bfloat16_rn(wsrc[l][i]);
+    if (tid < 64) bs[l][tid] = bsrc[l][tid];
+  }
+  __nv_bfloat16* tile = tiles[warp];
+  __syncthreads();
+#pragma unroll 1
+  for (int rep = 0; rep < HD_REPS; ++rep) {
+  const int tile_id = blockIdx.x * HD_REPS + rep;
+  const size_t p0 = (size_t)tile_id * 128;
+  head_load_tile(xfeat_b + (p0 + warp * 32) * 64, tile, lane);
+  __syncwarp();
+  uint32_t a[2][4][4];
+  head_a_frags(tile, g, q, a);
+  float acc[2][8][4];
+#pragma unroll 1
+  for (int l = 0; l < 2; ++l) {
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.f;
+    head_layer<8>(a, ws[l], g, q, acc);
+    head_next_frags(acc, bs[l], q, true, a);
+  }
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.f;
+  head_layer<8>(a, ws[2], g, q, acc);
+  // local features (no ReLU), rounded to bf16: staged in the warp's tile, column maxima of the ROUNDED values
+  __syncwarp();
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    const int col = nt * 8 + q * 2;
+    const float bA = bs[2][col], bB = bs[2][col + 1];
+    float mA = -INFINITY, mB = -INFINITY;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      const __nv_bfloat162 r0 = __floats2bfloat162_rn(acc[mt][nt][0] + bA, acc[mt][nt][1] + bB);
+      const __nv_bfloat162 r1 = __floats2bfloat162_rn(acc[mt][nt][2] + bA, acc[mt][nt][3] + bB);
+      *reinterpret_cast<__nv_bfloat162*>(tile + (mt * 16 + g) * HD_WS + col) = r0;
+      *reinterpret_cast<__nv_bfloat162*>(tile + (mt * 16 + g + 8) * HD_WS + col) = r1;
+      const float2 f0 = __bfloat1622float2(r0), f1 = __bfloat1622float2(r1);
+      mA = fmaxf(mA, fmaxf(f0.x, f1.x));
+      mB = fmaxf(mB, fmaxf(f0.y, f1.y));
+    }
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) {   // over the 8 row groups g
+      mA = fmaxf(mA, __shfl_xor_sync(0xffffffffu, mA, o));
+      mB = fmaxf(mB, __shfl_xor_sync(0xffffffffu, mB, o));
+    }
+    if (g == 0) {
+      cmax[warp][col] = mA;
+      cmax[warp][col + 1] = mB;
+    }
+  }
+  __syncwarp();
+  __nv_bfloat16* dst = local + (p0 + warp * 32) * 64;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int idx = it * 32 + lane, row = idx >> 3, c8 = idx & 7;
+    *reinterpret_cast<uint4*>(dst + idx * 8) = *reinterpret_cast<const uint4*>(tile + row * HD_WS + c8 * 8);
+  }
+  __syncthreads();
+  if (tid < 64)
+    tilemax[((size_t)cloud * 8 + (tile_id & 7)) * 64 + tid] =
+        fmaxf(fmaxf(cmax[0][tid], cmax[1][tid]), fmaxf(cmax[2][tid], cmax[3][tid]));
+  __syncthreads();   // cmax and the tiles are rewritten by the next repetition
+  }
+}
+
+// MLP{Fpcb,Rpcb} (model5_b.py:745-754): relu(W0 [g ; local] + b0) -> relu(W1 . + b1) -> W2 . + b2, logits as [B,2,1024].
+// g = the MRPC cloud's global max for BOTH heads (D6); its half of layer 0 is a per-cloud bias computed in the prologue.
+// Layer 1 uses split weights (hi + lo) so that, as before, only the activations are rounded to bf16.
+__global__ void __launch_bounds__(128) head_seg_tc_kernel(const __nv_bfloat16* __restrict__ local, Mlp3W wa, Mlp3W wb, int B,
+                                                          const float* __restrict__ tilemax, float* __restrict__ de_a,
+                                                          float* __restrict__ de_b) {
+  __shared__ __align__(16) __nv_bfloat16 w0s[64 * HD_WS], w1h[32 * HD_WS], w1l[32 * HD_WS];
+  __shared__ __align__(16) __nv_bfloat16 tiles[4][32 * HD_WS];
+  __shared__ float gs[64], gb[64], b1s[32], w2s[64], b2s[2];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
+  const int cloud = (int)(((size_t)blockIdx.x * HD_REPS * 128) / NPTS), set = cloud / B, b = cloud - set * B;
+  const Mlp3W& w = set == 0 ? wa : wb;
+  for (int i = tid; i < 64 * 64; i += 128)
+    w0s[(i >> 6) * HD_WS + (i & 63)] = __float2bfloat16_rn(w.w0[(i >> 6) * 128 + 64 + (i & 63)]);   // local half
+  for (int i = tid; i < 32 * 64; i += 128) {
+    const float wv = w.w1[i];
+    const __nv_bfloat16 hi = __float2bfloat16_rn(wv);
+    w1h[(i >> 6) * HD_WS + (i & 63)] = hi;
+    w1l[(i >> 6) * HD_WS + (i & 63)] = __float2bfloat16_rn(wv - __bfloat162float(hi));
+  }
+  if (tid < 64) {
+    const float* tm = tilemax + ((size_t)(B + b) * 8) * 64 + tid;   // the mrpc cloud of pair b
+    float m = tm[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) m = fmaxf(m, tm[i * 64]);
+    gs[tid] = m;
+    w2s[tid] = w.w2[tid];
+  }
+  if (tid < 32) b1s[tid] = w.b1[tid];
+  if (tid < 2) b2s[tid] = w.b2[tid];
+  __nv_bfloat16* tile = tiles[warp];
+  __syncthreads();
+  if (tid < 64) {
+    float v = w.b0[tid];
+    const float* wr = w.w0 + tid * 128;
+    for (int i = 0; i < 64; ++i) v = fmaf(wr[i], gs[i], v);
+    gb[tid] = v;
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (int rep = 0; rep < HD_REPS; ++rep) {
+  const size_t p0 = ((size_t)blockIdx.x * HD_REPS + rep) * 128;
+  const int n0 = (int)(p0 - (size_t)cloud * NPTS) + warp * 32;
+  head_load_tile(local + (p0 + warp * 32) * 64, tile, lane);
+  __syncwarp();
+  uint32_t a[2][4][4];
+  head_a_frags(tile, g, q, a);
+  float acc[2][8][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.f;
+  head_layer<8>(a, w0s, g, q, acc);
+  head_next_frags(acc, gb, q, true, a);
+  float h1[2][4][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) h1[mt][nt][i] = 0.f;
+  head_layer<4>(a, w1l, g, q, h1);
+  head_layer<4>(a, w1h, g, q, h1);
+  // layer 2 (32 -> 2) on the fp32 fragments: this thread holds 8 of the 32 hidden channels of its 4 rows
+  float o[4][2];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) o[j][0] = o[j][1] = 0.f;
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    const int col = nt * 8 + q * 2;
+    const float bA = b1s[col], bB = b1s[col + 1];
+    const float wA0 = w2s[col], wB0 = w2s[col + 1], wA1 = w2s[32 + col], wB1 = w2s[32 + col + 1];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const float hA = fmaxf(h1[mt][nt][2 * hf] + bA, 0.f), hB = fmaxf(h1[mt][nt][2 * hf + 1] + bB, 0.f);
+        const int j = 2 * mt + hf;
+        o[j][0] = fmaf(wA0, hA, fmaf(wB0, hB, o[j][0]));
+        o[j][1] = fmaf(wA1, hA, fmaf(wB1, hB, o[j][1]));
+      }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      o[j][c] += __shfl_xor_sync(0xffffffffu, o[j][c], 1);
+      o[j][c] += __shfl_xor_sync(0xffffffffu, o[j][c], 2);
+    }
+  if (q == 0) {
+    float* de = set == 0 ? de_a : de_b;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + g + 8 * j;
+      de[((size_t)b * 2 + 0) * NPTS + n] = o[j][0] + b2s[0];
+      de[((size_t)b * 2 + 1) * NPTS + n] = o[j][1] + b2s[1];
+    }
+  }
+  __syncwarp();   // the tile is rewritten by the next repetition
+  }
+}
+
 // ------------------------------------------------------------ se3.exp (se_math/se3.py:57-80)
 __global__ void se3_exp_kernel(const float* __restrict__ x, int B, float* __restrict__ g) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -907,7 +1164,7 @@ static int encoder_forward_bf16(const PzEncoderWeights* w, int E, int B, const f
   if (stem_fp32) stem_kernel<<<C * NPTS / 128, 128, 0, st>>>(xyz, stem_of(wa), stem_of(wb), B, xfeat, s.xfeat_b);
   else {
     PZ_CUDA(cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STEM_TC_SMEM));
-    stem_tc_kernel<<<C * NPTS / 128, 128, STEM_TC_SMEM, st>>>(xyz, stem_of(wa), stem_of(wb), B, xfeat, s.xfeat_b);
+    stem_tc_kernel<<<C * NPTS / (128 * HD_REPS), 128, STEM_TC_SMEM, st>>>(xyz, stem_of(wa), stem_of(wb), B, xfeat, s.xfeat_b);
   }
   PZ_LAUNCH_CHECK();
   prof_mark("stem", st);
@@ -1281,49 +1538,11 @@ extern "C" int pz_predict5(const PzEncoderWeights* enc_host, const PzHeadWeights
   // boundary heads (model5_b.py:738-754): they only need x_feature, so the encoder runs them right after its stem
   AfterStem heads_fn = [&](const float* xfeat, const __nv_bfloat16* xfeat_b) -> int {
     if (precision == PZ_PREC_BF16) {
-      // tensor-core version: 3 x (64->64) + the local half of MLP{F,R}pcb.0 as GEMMs with weights zero-padded to
-      // 128 output channels; the global max-pool over each cloud's 1024 points comes out of the third GEMM's
-      // epilogue as per-tile maxima; the global half of layer 0 is a per-cloud bias (rowbias).
-      if (!reuse_pack) {
-      PZ_CUDA(cudaMemsetAsync(s.hpack, 0, (size_t)2 * 4 * 128 * 64 * sizeof(__nv_bfloat16), st));
-      PZ_CUDA(cudaMemsetAsync(s.hbias, 0, (size_t)2 * 3 * 128 * sizeof(float), st));
-      PackJobs jobs;
-      int n = 0;
-      for (int e = 0; e < 2; ++e) {
-        const Mlp3W& pre = e == 0 ? pre_f : pre_r;
-        const Mlp3W& seg = e == 0 ? seg_f : seg_r;
-        __nv_bfloat16* wp = s.hpack + (size_t)e * 4 * 128 * 64;
-        float* bp = s.hbias + (size_t)e * 3 * 128;
-        jobs.j[n++] = PackJob{pre.w0, wp, 64, 64, 64, 64, 1};
-        jobs.j[n++] = PackJob{pre.w1, wp + 128 * 64, 64, 64, 64, 64, 1};
-        jobs.j[n++] = PackJob{pre.w2, wp + 2 * 128 * 64, 64, 64, 64, 64, 1};
-        jobs.j[n++] = PackJob{seg.w0 + 64, wp + 3 * 128 * 64, 128, 64, 64, 64, 1};   // local half: columns 64..127
-        jobs.j[n++] = PackJob{pre.b0, bp, 64, 1, 64, 64, 0};
-        jobs.j[n++] = PackJob{pre.b1, bp + 128, 64, 1, 64, 64, 0};
-        jobs.j[n++] = PackJob{pre.b2, bp + 256, 64, 1, 64, 64, 0};
-      }
-      jobs.n = n;
-      pack_weights_kernel<<<dim3(16, n), 256, 0, st>>>(jobs);
+      // two chained-MMA kernels (activations stay in registers between layers): the three local layers + per-CTA
+      // column maxima, then the segmentation head with the mrpc cloud's global feature folded into a per-cloud bias
+      head_pre_tc_kernel<<<P / (128 * HD_REPS), 128, 0, st>>>(xfeat_b, pre_f, pre_r, B, s.ha, s.tilemax);
       PZ_LAUNCH_CHECK();
-      }
-      auto layer = [&](const __nv_bfloat16* x, int li, int relu, __nv_bfloat16* y, bool with_max, bool seg0) {
-        TcGemm g;
-        g.X = x; g.ldx = 64; g.W[0] = s.hpack + (size_t)li * 128 * 64; g.W[1] = g.W[0] + 4 * 128 * 64; g.ldw = 64;
-        if (!seg0) { g.bias[0] = s.hbias + li * 128; g.bias[1] = s.hbias + 3 * 128 + li * 128; }
-        g.rows_per_wset = B * NPTS; g.M = P; g.Nout = 128; g.K = 64; g.relu = relu; g.n_valid = 64;
-        g.Yb = y; g.ldyb = 64;
-        (void)with_max;
-        if (seg0) { g.rowbias = s.gbias; g.rb_rows = NPTS; g.rb_ld = 64; }
-        return launch_tc_rowgemm(g, st);
-      };
-      PZ_TRY(layer(xfeat_b, 0, 1, s.ha, false, false));
-      PZ_TRY(layer(s.ha, 1, 1, s.hb, false, false));
-      PZ_TRY(layer(s.hb, 2, 0, s.ha, true, false));                 // local features (no ReLU) + per-tile maxima
-      seg_bias_cloudmax_kernel<<<B, 256, 0, st>>>(s.ha + (size_t)B * NPTS * 64, h.seg_fpc_w[0], h.seg_fpc_b[0],
-                                                  h.seg_rpc_w[0], h.seg_rpc_b[0], B, s.gbias);
-      PZ_LAUNCH_CHECK();
-      PZ_TRY(layer(s.ha, 3, 1, s.hb, false, true));                 // relu(W0[:,64:] local + W0[:,:64] g + b0)
-      head_seg_tail_kernel<<<P / 128, 128, 0, st>>>(s.hb, seg_f, seg_r, B, de_fpcb, de_mrpcb);
+      head_seg_tc_kernel<<<P / (128 * HD_REPS), 128, 0, st>>>(s.ha, seg_f, seg_r, B, s.tilemax, de_fpcb, de_mrpcb);
       PZ_LAUNCH_CHECK();
       prof_mark("boundary_heads", st);
       return 0;
