@@ -436,21 +436,27 @@ def run_gpu_arm(args):
              "traffic": None, "peak_source": src, "ms_per_launch": per_step[name] / nl, "launches_per_step": nl}
         if bound == "tensor":
             r["note"] = tensor_note
+        elif name.startswith("knn"):
+            r["note"] = ("fp32 ALU + selection bound, not HBM bound (SURVEY 8d): ncu issue slots 80 % busy, "
+                         "1 481 warp instructions per query (profiles/r01_knn_attn_full.txt); the HBM fraction is "
+                         "reported on the compulsory bytes as the contract asks")
+        elif name.startswith("fps"):
+            r["note"] = "serial arg-max chain (S dependent iterations per cloud): latency bound, cannot approach HBM peak"
         return r
 
     # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed ncu --set full
     # captures of this same command: profiles/r01_top_kernels_bf16.txt, profiles/r01_top_kernels_fwd_full.txt,
     # profiles/r01_prof_knn.txt (bf16 path)
     ncu_traffic = {"sg1_gather_layer2_maxpool": 58.84e6 + 3.92e6, "sg2_gather_layer2_maxpool": 54.84e6 + 3.96e6,
-                   "tail_linear_maxpool": 89.18e6 + 4.42e6, "fps1": 1.62e6, "knn1": 2.43e6,
-                   "attn_layer_fused": 17.55e6 + 0.07e6,
+                   "tail_linear_maxpool": 89.18e6 + 4.42e6, "fps1": 1.62e6, "knn1": 2.41e6, "knn2": 1.23e6,
+                   "attn_layer_fused": 17.51e6 + 0.06e6,
                    "attn_softmax_av": 41.97e6 + 0.08e6} if args.precision == "bf16" else {}
     rooflines = {k: roof(k) for k in work if per_step.get(k, 0) > 0}
     for k, r in rooflines.items():
         if k in ncu_traffic:
             r["traffic"] = ncu_traffic[k]
-            r["traffic_source"] = ("ncu --set full, profiles/r01_top_kernels_fwd_full.txt / r01_top_kernels_bf16.txt "
-                                   "(per launch, bytes)")
+            r["traffic_source"] = ("ncu --set full, profiles/r01_knn_attn_full.txt (kNN, attention layer) / "
+                                   "r01_top_kernels_bf16.txt (GEMMs) (per launch, bytes)")
     # dominant kernel = the stage with the largest live time among those with a defined roofline
     roofline = rooflines[max(rooflines, key=lambda k: per_step[k])] if rooflines else None
 

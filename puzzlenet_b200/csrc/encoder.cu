@@ -88,7 +88,7 @@ __device__ __forceinline__ void stem_mma(float (&d)[4], const uint32_t (&a)[4], 
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-constexpr int HD_REPS = 4;  // 128-point tiles per CTA (one weight conversion per 512 points; 512 | 1024: one cloud per CTA)
+constexpr int HD_REPS = 4;  // 128-point tiles per CTA (one weight conversion per 128 * HD_REPS points, which divide 1024: one cloud per CTA)
 constexpr int STEM_WS = 72;
 constexpr size_t STEM_TC_SMEM = 4 * 32 * STEM_WS * sizeof(float) + 64 * sizeof(float4) + 64 * sizeof(float) +
                                 2 * 64 * STEM_WS * sizeof(__nv_bfloat16);
@@ -629,79 +629,6 @@ __global__ void __launch_bounds__(128) head_seg_kernel(const float* __restrict__
 #pragma unroll
   for (int k = 0; k < 32; ++k) {
     const float v = outs[k * 128 + tid];
-    o0 = fmaf(w2s[k], v, o0);
-    o1 = fmaf(w2s[32 + k], v, o1);
-  }
-  float* de = set == 0 ? de_a : de_b;
-  de[((size_t)b * 2 + 0) * NPTS + n] = o0;
-  de[((size_t)b * 2 + 1) * NPTS + n] = o1;
-}
-
-// bf16 path: g[b] = max over the 1024 points of mrpc cloud b of its local features (bf16 [*,64]), then
-// gbias[set][b][k] = W0_set[k, 0:64] . g[b] + b0_set[k] for both heads (D6: the mrpc global feature feeds BOTH).
-__global__ void __launch_bounds__(256) seg_bias_cloudmax_kernel(const __nv_bfloat16* __restrict__ local_mrpc,
-                                                                const float* w0a, const float* b0a, const float* w0b,
-                                                                const float* b0b, int B, float* __restrict__ gbias) {
-  __shared__ float part[4][64];
-  __shared__ float g[64];
-  const int b = blockIdx.x, t = threadIdx.x, k = t & 63, q = t >> 6;
-  const __nv_bfloat16* p = local_mrpc + ((size_t)b * NPTS + q * 256) * 64 + k;
-  float m = -INFINITY;
-#pragma unroll 8
-  for (int r = 0; r < 256; ++r) m = fmaxf(m, __bfloat162float(p[(size_t)r * 64]));
-  part[q][k] = m;
-  __syncthreads();
-  if (t < 64) g[t] = fmaxf(fmaxf(part[0][t], part[1][t]), fmaxf(part[2][t], part[3][t]));
-  __syncthreads();
-  if (t < 128) {
-    const int set = t >> 6;
-    const float* w0 = set == 0 ? w0a : w0b;
-    float v = (set == 0 ? b0a : b0b)[k];
-    for (int i = 0; i < 64; ++i) v = fmaf(w0[k * 128 + i], g[i], v);
-    gbias[((size_t)set * B + b) * 64 + k] = v;
-  }
-}
-
-// bf16 path tail of MLP{F,R}pcb: h [P,64] bf16 -> relu(W1 h + b1) (32) -> W2 . + b2 (2), logits as [B,2,1024]
-__global__ void __launch_bounds__(128) head_seg_tail_kernel(const __nv_bfloat16* __restrict__ h, Mlp3W wa, Mlp3W wb, int B,
-                                                            float* __restrict__ de_a, float* __restrict__ de_b) {
-  __shared__ __align__(16) float w1s[32 * 64];
-  __shared__ float w2s[64], b1s[32], b2s[2];
-  const int tid = threadIdx.x;
-  const size_t p = (size_t)blockIdx.x * 128 + tid;
-  const int cloud = (int)(p / NPTS), n = (int)(p - (size_t)cloud * NPTS);
-  const int set = cloud / B, b = cloud - set * B;
-  const Mlp3W& w = set == 0 ? wa : wb;
-  for (int i = tid; i < 32 * 64; i += 128) w1s[i] = w.w1[i];
-  if (tid < 64) w2s[tid] = w.w2[tid];
-  if (tid < 32) b1s[tid] = w.b1[tid];
-  if (tid < 2) b2s[tid] = w.b2[tid];
-  __syncthreads();
-  float a[64];
-  const uint4* src = reinterpret_cast<const uint4*>(h + p * 64);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const uint4 u = src[i];
-    const __nv_bfloat162* p2 = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 f = __bfloat1622float2(p2[j]);
-      a[i * 8 + 2 * j] = f.x;
-      a[i * 8 + 2 * j + 1] = f.y;
-    }
-  }
-  float o0 = b2s[0], o1 = b2s[1];
-#pragma unroll 4
-  for (int k = 0; k < 32; ++k) {
-    const float4* wr = reinterpret_cast<const float4*>(w1s + k * 64);
-    float v = b1s[k];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const float4 ww = wr[i];
-      v = fmaf(ww.x, a[i * 4], v); v = fmaf(ww.y, a[i * 4 + 1], v);
-      v = fmaf(ww.z, a[i * 4 + 2], v); v = fmaf(ww.w, a[i * 4 + 3], v);
-    }
-    v = fmaxf(v, 0.f);
     o0 = fmaf(w2s[k], v, o0);
     o1 = fmaf(w2s[32 + k], v, o1);
   }
@@ -1445,8 +1372,8 @@ extern "C" int pz_encoder_forward(const PzEncoderWeights* weights_host, int E, i
 
 namespace {
 struct PredictScratch {
-  float *xyz, *fpair, *h0, *h1, *partial, *local, *gmax, *gbias, *tilemax, *hbias;
-  __nv_bfloat16 *ha, *hb, *hpack;
+  float *xyz, *fpair, *h0, *h1, *partial, *local, *gmax, *gbias, *tilemax;
+  __nv_bfloat16 *ha;
   int64_t *st1, *st2;
   void* enc;
   size_t enc_bytes, partial_floats;
@@ -1464,10 +1391,7 @@ size_t predict_layout(int B, Arena& a, PredictScratch& s) {
   s.gmax = a.take<float>((size_t)B * 64);
   s.gbias = a.take<float>((size_t)2 * B * 64);
   s.tilemax = a.take<float>((size_t)2 * B * 8 * 128);
-  s.hbias = a.take<float>(2 * 3 * 128);
   s.ha = a.take<__nv_bfloat16>((size_t)2 * B * NPTS * 64);
-  s.hb = a.take<__nv_bfloat16>((size_t)2 * B * NPTS * 64);
-  s.hpack = a.take<__nv_bfloat16>(2 * 4 * 128 * 64);
   s.enc_bytes = pz_encoder_workspace_bytes(2, B);
   s.enc = a.take<char>(s.enc_bytes);
   return a.used;
