@@ -532,7 +532,7 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("PZ_PRECISION", "bf16"), choices=["fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--single-precision", action="store_true", help="skip the short run of the other precision")
-    ap.add_argument("--pipes", type=int, default=3, help="CUDA streams the e2e leg alternates batches over")
+    ap.add_argument("--pipes", type=int, default=4, help="CUDA streams the e2e leg alternates batches over")
     ap.add_argument("--no-graphs", action="store_true", help="e2e leg: eager launches instead of CUDA-graph replay")
     ap.add_argument("--no-extras", action="store_true", help="skip the short training-step / assembly runs")
     args = ap.parse_args()
