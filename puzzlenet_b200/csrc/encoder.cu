@@ -88,7 +88,16 @@ __device__ __forceinline__ void stem_mma(float (&d)[4], const uint32_t (&a)[4], 
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-constexpr int HD_REPS = 4;  // 128-point tiles per CTA (one weight conversion per 128 * HD_REPS points, which divide 1024: one cloud per CTA)
+// 128-point tiles per CTA of the stem / boundary-head kernels (the tiles of one CTA belong to one cloud: reps | 8)
+constexpr int HD_REPS = 4;
+static int head_reps() {
+  static const int r = [] {
+    const char* e = getenv("PZ_HD_REPS");   // tuning hook
+    const int v = e ? atoi(e) : HD_REPS;
+    return (v == 1 || v == 2 || v == 4 || v == 8) ? v : HD_REPS;
+  }();
+  return r;
+}
 constexpr int STEM_WS = 72;
 constexpr size_t STEM_TC_SMEM = 4 * 32 * STEM_WS * sizeof(float) + 64 * sizeof(float4) + 64 * sizeof(float) +
                                 2 * 64 * STEM_WS * sizeof(__nv_bfloat16);
@@ -98,7 +107,9 @@ constexpr size_t STEM_TC_SMEM = 4 * 32 * STEM_WS * sizeof(float) + 64 * sizeof(f
 // the grouped MLP and the boundary heads, BN + ReLU on the accumulator fragments, and the [32 points x 64] tile of each warp leaves through shared memory as one
 // contiguous 8 KB (fp32) + 4 KB (bf16) block.  The fp32 path keeps stem_kernel (FFMA, 1e-4 parity).
 __global__ void __launch_bounds__(128) stem_tc_kernel(const float* __restrict__ xyz, StemW wa, StemW wb,
-                                                      int clouds_per_set, float* __restrict__ out,
+                                                      const __nv_bfloat16* __restrict__ w2img_a,
+                                                      const __nv_bfloat16* __restrict__ w2img_b,
+                                                      int clouds_per_set, int reps, float* __restrict__ out,
                                                       __nv_bfloat16* __restrict__ out_b) {
   constexpr int WS = STEM_WS;   // padded row strides: conflict-free fragment loads / stores
   extern __shared__ __align__(16) uint8_t stem_smem[];
@@ -107,13 +118,12 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const float* __restrict__ 
   float* b2s = reinterpret_cast<float*>(w1p + 64);
   __nv_bfloat16* w2b = reinterpret_cast<__nv_bfloat16*>(b2s + 64);                      // hi, then lo: [2][64 * WS]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
-  const int cloud = (int)(((size_t)blockIdx.x * HD_REPS * 128) / NPTS);   // uniform per block (512 | 1024)
+  const int cloud = (int)(((size_t)blockIdx.x * reps * 128) / NPTS);   // uniform per block (128 reps | 1024)
   const StemW& w = (cloud / clouds_per_set) == 0 ? wa : wb;
-  for (int i = tid; i < 64 * 64; i += 128) {
-    const float wv = w.w2[i];
-    const __nv_bfloat16 hi = __float2bfloat16_rn(wv);
-    w2b[(i >> 6) * WS + (i & 63)] = hi;
-    w2b[64 * WS + (i >> 6) * WS + (i & 63)] = __float2bfloat16_rn(wv - __bfloat162float(hi));
+  {   // W2 hi | lo images ([2][64, WS] bf16, written by the weight pack): a straight 16-byte copy
+    const uint4* src = reinterpret_cast<const uint4*>((cloud / clouds_per_set) == 0 ? w2img_a : w2img_b);
+    uint4* dst = reinterpret_cast<uint4*>(w2b);
+    for (int i = tid; i < 2 * 64 * WS / 8; i += 128) dst[i] = src[i];
   }
   if (tid < 64) {
     w1p[tid] = make_float4(w.w1[tid * 3], w.w1[tid * 3 + 1], w.w1[tid * 3 + 2], w.b1[tid]);
@@ -121,8 +131,8 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const float* __restrict__ 
   }
   __syncthreads();
 #pragma unroll 1
-  for (int rep = 0; rep < HD_REPS; ++rep) {
-  const size_t p0 = ((size_t)blockIdx.x * HD_REPS + rep) * 128;   // first point of this 128-point tile
+  for (int rep = 0; rep < reps; ++rep) {
+  const size_t p0 = ((size_t)blockIdx.x * reps + rep) * 128;   // first point of this 128-point tile
   const int n0 = (int)(p0 - (size_t)cloud * NPTS) + warp * 32;
   // this thread's four rows of the warp tile: g, g + 8, g + 16, g + 24
   float x[4], y[4], z[4], a1[4], c1[4], a2[4], c2[4];
@@ -640,6 +650,9 @@ __global__ void __launch_bounds__(128) head_seg_kernel(const float* __restrict__
 // ---- bf16 path, boundary heads as two chained-MMA kernels (mma.sync m16n8k16; the accumulator fragments of one layer,
 // rounded to bf16, ARE the A fragments of the next, so activations never leave registers).  One warp = 32 points.
 constexpr int HD_WS = 72;   // padded bf16 row stride: conflict-free fragment loads
+// packed head weights of one set (bf16, rows of HD_WS): pre.w0, pre.w1, pre.w2 [64 rows each], seg.w0[:, 64:128] [64],
+// seg.w1 hi [32], seg.w1 lo [32]
+constexpr size_t HEAD_IMG_SET = (size_t)(3 * 64 + 64 + 32 + 32) * HD_WS;
 
 // 32-point tile (contiguous 4 KB of a bf16 [P,64] tensor) -> padded smem tile -> A fragments
 __device__ __forceinline__ void head_load_tile(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* tile, int lane) {
@@ -698,27 +711,30 @@ __device__ __forceinline__ void head_next_frags(const float (&acc)[2][8][4], con
 // features (bf16 [P,64]) and, per CTA, the column maxima of its 128 points (tilemax [cloud][8][64]) for the global
 // max-pool of model5_b.py:741-744
 __global__ void __launch_bounds__(128) head_pre_tc_kernel(const __nv_bfloat16* __restrict__ xfeat_b, Mlp3W wa, Mlp3W wb,
-                                                          int B, __nv_bfloat16* __restrict__ local,
+                                                          const __nv_bfloat16* __restrict__ wimg, int B, int reps,
+                                                          __nv_bfloat16* __restrict__ local,
                                                           float* __restrict__ tilemax) {
   __shared__ __align__(16) __nv_bfloat16 ws[3][64 * HD_WS];
   __shared__ __align__(16) __nv_bfloat16 tiles[4][32 * HD_WS];
   __shared__ float bs[3][64];
   __shared__ float cmax[4][64];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
-  const int cloud = (int)(((size_t)blockIdx.x * HD_REPS * 128) / NPTS);
+  const int cloud = (int)(((size_t)blockIdx.x * reps * 128) / NPTS);
   const Mlp3W& w = cloud / B == 0 ? wa : wb;
-  const float* wsrc[3] = {w.w0, w.w1, w.w2};
   const float* bsrc[3] = {w.b0, w.b1, w.b2};
-#pragma unroll
-  for (int l = 0; l < 3; ++l) {
-    for (int i = tid; i < 64 * 64; i += 128) ws[l][(i >> 6) * HD_WS + (i & 63)] = __float2bfloat16_rn(wsrc[l][i]);
-    if (tid < 64) bs[l][tid] = bsrc[l][tid];
+  {   // the set's three [64, HD_WS] bf16 weight images (head_pack_layout), a straight 16-byte copy
+    const uint4* src = reinterpret_cast<const uint4*>(wimg + (size_t)(cloud / B) * HEAD_IMG_SET);
+    uint4* dst = reinterpret_cast<uint4*>(&ws[0][0]);
+    for (int i = tid; i < 3 * 64 * HD_WS / 8; i += 128) dst[i] = src[i];
   }
+#pragma unroll
+  for (int l = 0; l < 3; ++l)
+    if (tid < 64) bs[l][tid] = bsrc[l][tid];
   __nv_bfloat16* tile = tiles[warp];
   __syncthreads();
 #pragma unroll 1
-  for (int rep = 0; rep < HD_REPS; ++rep) {
-  const int tile_id = blockIdx.x * HD_REPS + rep;
+  for (int rep = 0; rep < reps; ++rep) {
+  const int tile_id = blockIdx.x * reps + rep;
   const size_t p0 = (size_t)tile_id * 128;
   head_load_tile(xfeat_b + (p0 + warp * 32) * 64, tile, lane);
   __syncwarp();
@@ -788,22 +804,21 @@ __global__ void __launch_bounds__(128) head_pre_tc_kernel(const __nv_bfloat16* _
 // MLP{Fpcb,Rpcb} (model5_b.py:745-754): relu(W0 [g ; local] + b0) -> relu(W1 . + b1) -> W2 . + b2, logits as [B,2,1024].
 // g = the MRPC cloud's global max for BOTH heads (D6); its half of layer 0 is a per-cloud bias computed in the prologue.
 // Layer 1 uses split weights (hi + lo) so that, as before, only the activations are rounded to bf16.
-__global__ void __launch_bounds__(128) head_seg_tc_kernel(const __nv_bfloat16* __restrict__ local, Mlp3W wa, Mlp3W wb, int B,
+__global__ void __launch_bounds__(128) head_seg_tc_kernel(const __nv_bfloat16* __restrict__ local, Mlp3W wa, Mlp3W wb,
+                                                          const __nv_bfloat16* __restrict__ wimg, int B, int reps,
                                                           const float* __restrict__ tilemax, float* __restrict__ de_a,
                                                           float* __restrict__ de_b) {
-  __shared__ __align__(16) __nv_bfloat16 w0s[64 * HD_WS], w1h[32 * HD_WS], w1l[32 * HD_WS];
+  __shared__ __align__(16) __nv_bfloat16 wseg[128 * HD_WS];   // W0 local half [64], W1 hi [32], W1 lo [32]
+  const __nv_bfloat16 *w0s = wseg, *w1h = wseg + 64 * HD_WS, *w1l = wseg + 96 * HD_WS;
   __shared__ __align__(16) __nv_bfloat16 tiles[4][32 * HD_WS];
   __shared__ float gs[64], gb[64], b1s[32], w2s[64], b2s[2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
-  const int cloud = (int)(((size_t)blockIdx.x * HD_REPS * 128) / NPTS), set = cloud / B, b = cloud - set * B;
+  const int cloud = (int)(((size_t)blockIdx.x * reps * 128) / NPTS), set = cloud / B, b = cloud - set * B;
   const Mlp3W& w = set == 0 ? wa : wb;
-  for (int i = tid; i < 64 * 64; i += 128)
-    w0s[(i >> 6) * HD_WS + (i & 63)] = __float2bfloat16_rn(w.w0[(i >> 6) * 128 + 64 + (i & 63)]);   // local half
-  for (int i = tid; i < 32 * 64; i += 128) {
-    const float wv = w.w1[i];
-    const __nv_bfloat16 hi = __float2bfloat16_rn(wv);
-    w1h[(i >> 6) * HD_WS + (i & 63)] = hi;
-    w1l[(i >> 6) * HD_WS + (i & 63)] = __float2bfloat16_rn(wv - __bfloat162float(hi));
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(wimg + (size_t)set * HEAD_IMG_SET + 3 * 64 * HD_WS);
+    uint4* dst = reinterpret_cast<uint4*>(wseg);
+    for (int i = tid; i < 128 * HD_WS / 8; i += 128) dst[i] = src[i];
   }
   if (tid < 64) {
     const float* tm = tilemax + ((size_t)(B + b) * 8) * 64 + tid;   // the mrpc cloud of pair b
@@ -825,8 +840,8 @@ __global__ void __launch_bounds__(128) head_seg_tc_kernel(const __nv_bfloat16* _
   }
   __syncthreads();
 #pragma unroll 1
-  for (int rep = 0; rep < HD_REPS; ++rep) {
-  const size_t p0 = ((size_t)blockIdx.x * HD_REPS + rep) * 128;
+  for (int rep = 0; rep < reps; ++rep) {
+  const size_t p0 = ((size_t)blockIdx.x * reps + rep) * 128;
   const int n0 = (int)(p0 - (size_t)cloud * NPTS) + warp * 32;
   head_load_tile(local + (p0 + warp * 32) * 64, tile, lane);
   __syncwarp();
@@ -925,6 +940,8 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const PackJobs jobs) 
       const int rr = r + jb.ldo, tile = (rr >> 7) * 4 + (c >> 6), tr = rr & 127, tc = c & 63;
       static_cast<__nv_bfloat16*>(jb.dst)[(size_t)tile * 8192 + tr * 64 + (((tc >> 3) ^ (tr & 7)) << 3) + (tc & 7)] =
           __float2bfloat16_rn(v);
+    } else if (jb.to_bf16 == 3) {   // low half of a split-bf16 weight: v - bf16(v)
+      static_cast<__nv_bfloat16*>(jb.dst)[(size_t)r * jb.ldo + c] = __float2bfloat16_rn(v - __bfloat162float(__float2bfloat16_rn(v)));
     } else if (jb.to_bf16) static_cast<__nv_bfloat16*>(jb.dst)[(size_t)r * jb.ldo + c] = __float2bfloat16_rn(v);
     else static_cast<float*>(jb.dst)[(size_t)r * jb.ldo + c] = v;
   }
@@ -968,7 +985,8 @@ struct EncoderScratch {
 // 4 x (Wqkv[384,256] Wo[256,256]) Wout[1024,1280]  4 x (20 tile images of Wqkv|Wo for the fused attention layer)
 constexpr size_t WP_W3F = 0, WP_W4 = WP_W3F + 128 * 64, WP_W5F = WP_W4 + 128 * 128, WP_W6 = WP_W5F + 256 * 128,
                  WP_ATT = WP_W6 + 256 * 256, WP_ATT_STRIDE = 384 * 256 + 256 * 256, WP_WOUT = WP_ATT + 4 * WP_ATT_STRIDE,
-                 WP_ATTIMG = WP_WOUT + 1024 * 1280, WP_TOTAL = WP_ATTIMG + 4 * ATTN_WIMG_ELEMS;
+                 WP_ATTIMG = WP_WOUT + 1024 * 1280, WP_STEM = WP_ATTIMG + 4 * ATTN_WIMG_ELEMS,
+                 WP_TOTAL = WP_STEM + 2 * 64 * STEM_WS;   // stem: W2 hi, lo as [64, STEM_WS] images
 
 static size_t encoder_scratch_layout(int C, Arena& a, EncoderScratch& s) {
   s.xfeat = a.take<float>((size_t)C * NPTS * D0);
@@ -1055,6 +1073,8 @@ static int encoder_forward_bf16(const PzEncoderWeights* w, int E, int B, const f
         add(we.v_b[l], CATT, 1, CATT, bq + 128, CATT, 0);
       }
       add(we.out_w, 1280, 1024, 1280, wp + WP_WOUT, 1280, 1);
+      add(we.mlp2_w, 64, 64, 64, wp + WP_STEM, STEM_WS, 1);
+      add(we.mlp2_w, 64, 64, 64, wp + WP_STEM + 64 * STEM_WS, STEM_WS, 3);
     }
     PZ_REQUIRE(n <= MAX_PACK_JOBS, PZ_ERR_ARG, "encoder: %d weight pack jobs exceed the table", n);
     jobs.n = n;
@@ -1091,7 +1111,8 @@ static int encoder_forward_bf16(const PzEncoderWeights* w, int E, int B, const f
   if (stem_fp32) stem_kernel<<<C * NPTS / 128, 128, 0, st>>>(xyz, stem_of(wa), stem_of(wb), B, xfeat, s.xfeat_b);
   else {
     PZ_CUDA(cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STEM_TC_SMEM));
-    stem_tc_kernel<<<C * NPTS / (128 * HD_REPS), 128, STEM_TC_SMEM, st>>>(xyz, stem_of(wa), stem_of(wb), B, xfeat, s.xfeat_b);
+    stem_tc_kernel<<<C * NPTS / (128 * head_reps()), 128, STEM_TC_SMEM, st>>>(xyz, stem_of(wa), stem_of(wb), wpa + WP_STEM,
+                                                                              wpb + WP_STEM, B, head_reps(), xfeat, s.xfeat_b);
   }
   PZ_LAUNCH_CHECK();
   prof_mark("stem", st);
@@ -1373,7 +1394,7 @@ extern "C" int pz_encoder_forward(const PzEncoderWeights* weights_host, int E, i
 namespace {
 struct PredictScratch {
   float *xyz, *fpair, *h0, *h1, *partial, *local, *gmax, *gbias, *tilemax;
-  __nv_bfloat16 *ha;
+  __nv_bfloat16 *ha, *himg;
   int64_t *st1, *st2;
   void* enc;
   size_t enc_bytes, partial_floats;
@@ -1392,6 +1413,7 @@ size_t predict_layout(int B, Arena& a, PredictScratch& s) {
   s.gbias = a.take<float>((size_t)2 * B * 64);
   s.tilemax = a.take<float>((size_t)2 * B * 8 * 128);
   s.ha = a.take<__nv_bfloat16>((size_t)2 * B * NPTS * 64);
+  s.himg = a.take<__nv_bfloat16>(2 * HEAD_IMG_SET);
   s.enc_bytes = pz_encoder_workspace_bytes(2, B);
   s.enc = a.take<char>(s.enc_bytes);
   return a.used;
@@ -1464,9 +1486,28 @@ extern "C" int pz_predict5(const PzEncoderWeights* enc_host, const PzHeadWeights
     if (precision == PZ_PREC_BF16) {
       // two chained-MMA kernels (activations stay in registers between layers): the three local layers + per-CTA
       // column maxima, then the segmentation head with the mrpc cloud's global feature folded into a per-cloud bias
-      head_pre_tc_kernel<<<P / (128 * HD_REPS), 128, 0, st>>>(xfeat_b, pre_f, pre_r, B, s.ha, s.tilemax);
+      if (!reuse_pack) {   // bf16 weight images of both heads (one launch; skipped while the caller vouches for the weights)
+        PackJobs jobs;
+        int n = 0;
+        for (int e = 0; e < 2; ++e) {
+          const Mlp3W& pre = e == 0 ? pre_f : pre_r;
+          const Mlp3W& seg = e == 0 ? seg_f : seg_r;
+          __nv_bfloat16* wp = s.himg + (size_t)e * HEAD_IMG_SET;
+          jobs.j[n++] = PackJob{pre.w0, wp, 64, 64, 64, HD_WS, 1};
+          jobs.j[n++] = PackJob{pre.w1, wp + 64 * HD_WS, 64, 64, 64, HD_WS, 1};
+          jobs.j[n++] = PackJob{pre.w2, wp + 128 * HD_WS, 64, 64, 64, HD_WS, 1};
+          jobs.j[n++] = PackJob{seg.w0 + 64, wp + 192 * HD_WS, 128, 64, 64, HD_WS, 1};   // local half: columns 64..127
+          jobs.j[n++] = PackJob{seg.w1, wp + 256 * HD_WS, 64, 32, 64, HD_WS, 1};
+          jobs.j[n++] = PackJob{seg.w1, wp + 288 * HD_WS, 64, 32, 64, HD_WS, 3};
+        }
+        jobs.n = n;
+        pack_weights_kernel<<<dim3(16, n), 256, 0, st>>>(jobs);
+        PZ_LAUNCH_CHECK();
+      }
+      head_pre_tc_kernel<<<P / (128 * head_reps()), 128, 0, st>>>(xfeat_b, pre_f, pre_r, s.himg, B, head_reps(), s.ha, s.tilemax);
       PZ_LAUNCH_CHECK();
-      head_seg_tc_kernel<<<P / (128 * HD_REPS), 128, 0, st>>>(s.ha, seg_f, seg_r, B, s.tilemax, de_fpcb, de_mrpcb);
+      head_seg_tc_kernel<<<P / (128 * head_reps()), 128, 0, st>>>(s.ha, seg_f, seg_r, s.himg, B, head_reps(), s.tilemax, de_fpcb,
+                                                                  de_mrpcb);
       PZ_LAUNCH_CHECK();
       prof_mark("boundary_heads", st);
       return 0;
