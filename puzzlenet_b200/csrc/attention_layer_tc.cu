@@ -497,6 +497,7 @@ int launch_attn_weight_image(const float* src, int rows, int row_off, __nv_bfloa
 }
 
 static long long* g_attn_timeline = nullptr;
+long long* kernel_timeline_buffer() { return g_attn_timeline; }
 
 // [rows, 256] bf16 view with a row stride of ld elements, traversed in [128 rows x 64 ch] SWIZZLE_128B boxes
 static int make_tile_map(const __nv_bfloat16* ptr, int ld, size_t rows, CUtensorMap* out) {

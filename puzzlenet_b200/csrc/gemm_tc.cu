@@ -33,6 +33,10 @@ constexpr int THREADS = 13 * 32;  // 416: epilogue + MMA + producer warps (split
 
 using namespace tc;
 
+__device__ __forceinline__ void tl_stamp(long long* prof, int slot) {
+  if (prof != nullptr && blockIdx.x == 0) prof[slot] = clock64();
+}
+
 // ROWS: activation rows per tile (UMMA N).  NCHB: 128-channel blocks per tile (accumulators).
 // RESIDENT: all of W for the tile's NCHB blocks stays in smem (K*NCHB*256 bytes).  GATHER: computed B.
 template <int ROWS, int NCHB, bool RESIDENT, bool GATHER, int NST>
@@ -130,18 +134,26 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcGemm g) {
       int my_tiles = 0;
       for (int t = tile_begin + rank_in_set; t < tile_begin + tiles_per_set; t += step) ++my_tiles;
       const int jobs = my_tiles * kblocks;
+      // the gathered row ids of a job are fetched one job ahead (into registers), so that the L2 round trip of the
+      // index load is not in front of every stage's cp.async burst
+      int src[GCH];
+      auto fetch_ids = [&](int j) {
+        const int ti = j / kblocks;
+        const int row0 = (tile_begin + rank_in_set + ti * step) * ROWS;
+#pragma unroll
+        for (int i = 0; i < GCH; ++i) src[i] = g.rows[row0 + r0 + i * 16];
+      };
+      if (grp < jobs) fetch_ids(grp);
       auto issue = [&](int j) {
         const int ti = j / kblocks, kb = j - ti * kblocks;
         const int row0 = (tile_begin + rank_in_set + ti * step) * ROWS;      // ch_tiles == 1 in gather mode
         const uint32_t s = (uint32_t)j % NST, ph = ((uint32_t)j / NST) & 1;
         mbar_wait(empty_bar + 8 * s, ph ^ 1);
         const uint32_t st_addr = stages_base + s * STAGE_BYTES;
-        int src[GCH];
-#pragma unroll
-        for (int i = 0; i < GCH; ++i) src[i] = g.rows[row0 + r0 + i * 16];
 #pragma unroll
         for (int i = 0; i < GCH; ++i)
           cp_async16(st_addr + sw128(r0 + i * 16, gc), g.X + (size_t)src[i] * g.ldx + kb * KB + gc * 8);
+        if (j + 2 < jobs) fetch_ids(j + 2);
         if (gt < (ROWS / 32) * 3) {   // the stage's group centres (fp32 xyz), 4-byte copies into a padded [g][4] tile
           const int gi = gt / 3, d = gt - gi * 3;
           asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(cstage_base + s * ((ROWS / 32) * 16) + gi * 16 + d * 4),
@@ -152,7 +164,9 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcGemm g) {
       };
       int j = grp;
       if (j < jobs) issue(j);
+      long long* pprof = (pt == 0) ? g.prof : nullptr;   // group 0, thread 0
       for (; j < jobs; j += 2) {
+        if (j < 48) tl_stamp(pprof, 1024 + (j >> 1) * 4);
         if (j + 2 < jobs) {
           issue(j + 2);
           cp_async_wait<1>();
@@ -161,6 +175,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcGemm g) {
         }
         // the centres were copied by other threads of the group
         asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory");
+        if (j < 48) tl_stamp(pprof, 1024 + (j >> 1) * 4 + 1);
         const uint32_t s = (uint32_t)j % NST;
         {  // Q[g][k] = W1[k,0:3] . centre_g for the 64 channels of this k-block: (ROWS/32)*64 values, 128 threads
           const int kb = j % kblocks;
@@ -176,6 +191,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcGemm g) {
           }
         }
         asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory");
+        if (j < 48) tl_stamp(pprof, 1024 + (j >> 1) * 4 + 2);
         uint8_t* st_gen = smem_gen + (stages_base + s * STAGE_BYTES - smem_base);
         // packed bf16x2 arithmetic: relu(p - q) on two channels per instruction (HFMA2.BF16 rounds once)
         const uint4* qs = reinterpret_cast<const uint4*>(smem_gen + (qstage_base + s * (QCH * 16) - smem_base));
@@ -197,6 +213,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcGemm g) {
         }
         fence_proxy_async();
         mbar_arrive(full_bar + 8 * s);
+        if (j < 48) tl_stamp(pprof, 1024 + (j >> 1) * 4 + 3);
         // a second group barrier keeps a fast thread from overwriting the Q tile of a slot that slower
         // threads of the group are still reading (slot s is reused by this group's job j + 2*NST at the earliest,
         // which is issued two iterations later -- so one barrier per iteration is enough)
@@ -254,6 +271,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcGemm g) {
           const uint32_t s = it % NST, ph = (it / NST) & 1;
           mbar_wait(full_bar + 8 * s, ph);
           tc_fence_after();
+          if (GATHER && it < 48) tl_stamp(g.prof, 1280 + it);
           const uint32_t st_addr = stages_base + s * STAGE_BYTES;
 #pragma unroll
           for (int chb = 0; chb < NCHB; ++chb) {
@@ -287,6 +305,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcGemm g) {
       }
       mbar_wait(accf_bar + 8 * buf, aph);
       tc_fence_after();
+      if (GATHER && tid == 0 && tc_count < 24) tl_stamp(g.prof, 1408 + tc_count * 2);
 #pragma unroll 1
       for (int chb = 0; chb < NCHB; ++chb) {
         const int ch = (cht * NCHB + chb) * 128 + quarter * 32 + lane;
@@ -303,8 +322,37 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcGemm g) {
         // store epilogue: the two warps of a lane quarter take alternate chunks; max epilogues run on half 0 only
         const int c_begin = g.epi == 0 ? half : (half == 0 ? 0 : ROWS / 32);
         const int c_step = g.epi == 0 ? HALVES : 1;
+        if (g.epi != 0 && half == 0) {
+          // max epilogues: 64 accumulator columns (two neighbourhoods of 32 rows) per tcgen05.ld, each reduced by a
+          // tree (depth 5, not a 31-long dependent chain): this loop paces the whole gather pipeline
 #pragma unroll 1
-        for (int c32 = c_begin; c32 < ROWS / 32; c32 += c_step) {
+          for (int c64 = 0; c64 < ROWS / 64; ++c64) {
+            float v[64];
+            tmem_ld64(t_addr + c64 * 64, v);
+#pragma unroll
+            for (int w = 32; w >= 2; w >>= 1) {
+#pragma unroll
+              for (int i = 0; i < w / 2; ++i) {
+                v[i] = fmaxf(v[i], v[i + w / 2]);
+                v[32 + i] = fmaxf(v[32 + i], v[32 + i + w / 2]);
+              }
+            }
+            if (g.epi == 1) {  // one output row per group of 32
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                float x = v[32 * h] + bv;
+                if (g.relu) x = fmaxf(x, 0.f);
+                const size_t grow = (size_t)(row0 >> 5) + c64 * 2 + h;
+                if (g.Yf) g.Yf[grow * g.ldyf + ch] = x;
+                if (g.Yb) g.Yb[grow * g.ldyb + ch] = __float2bfloat16_rn(x);
+              }
+            } else {
+              cmax = fmaxf(cmax, fmaxf(v[0], v[32]));
+            }
+          }
+        }
+#pragma unroll 1
+        for (int c32 = c_begin; c32 < ROWS / 32 && g.epi == 0; c32 += c_step) {
           float v[32];
           tmem_ld32(t_addr + c32 * 32, v);
           if (g.epi == 0) {
@@ -385,6 +433,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcGemm g) {
       }
       tc_fence_before();
       mbar_arrive(acce_bar + 8 * buf);
+      if (GATHER && tid == 0 && tc_count < 24) tl_stamp(g.prof, 1408 + tc_count * 2 + 1);
     }
   }
 
@@ -415,6 +464,7 @@ static int tc_launch(const TcGemm& g, cudaStream_t st) {
   return 0;
 }
 
+int launch_tc_gemm_gather(const TcGemm& g, cudaStream_t st, int nsets);
 int launch_tc_gemm(const TcGemm& g, cudaStream_t st) {
   PZ_REQUIRE(g.W[0] && g.X && (g.Yf || g.Yb || g.YT), PZ_ERR_ARG, "tc_gemm: null operand");
   PZ_REQUIRE(g.M > 0 && g.Nout > 0 && g.K > 0, PZ_ERR_ARG, "tc_gemm: bad shape");
@@ -425,6 +475,19 @@ int launch_tc_gemm(const TcGemm& g, cudaStream_t st) {
   const int nsets = (g.rows_per_wset > 0 && g.M > g.rows_per_wset) ? 2 : 1;
   if (nsets == 2) PZ_REQUIRE(g.W[1] && g.M == 2 * g.rows_per_wset, PZ_ERR_ARG, "tc_gemm: two weight sets need M == 2*rows_per_wset");
   if (g.rows) {  // gathered B, resident weights
+    if (kernel_timeline_buffer()) {   // diagnostics: only the 256-row (stage 1) variant stamps, so one forward leaves one timeline
+      TcGemm gp = g;
+      gp.prof = (g.Nout == 128) ? kernel_timeline_buffer() : nullptr;
+      return launch_tc_gemm_gather(gp, st, nsets);
+    }
+    return launch_tc_gemm_gather(g, st, nsets);
+  }
+  PZ_REQUIRE(g.M % (256 * nsets) == 0, PZ_ERR_UNSUPPORTED, "tc_gemm: M=%d must be a multiple of %d", g.M, 256 * nsets);
+  return tc_launch<256, 1, false, false, 4>(g, st);
+}
+
+static int launch_tc_gemm_gather_impl(const TcGemm& g, cudaStream_t st, int nsets) {
+  {
     PZ_REQUIRE(g.centers && g.W1x[0] && g.epi == 1, PZ_ERR_ARG, "tc_gemm: gathered operand needs centres, W1x and the group-max epilogue");
     if (g.Nout == 128 && g.K <= 256) {
       PZ_REQUIRE(g.M % (256 * nsets) == 0, PZ_ERR_UNSUPPORTED, "tc_gemm: M=%d must be a multiple of %d", g.M, 256 * nsets);
@@ -436,9 +499,8 @@ int launch_tc_gemm(const TcGemm& g, cudaStream_t st) {
     }
     return fail(PZ_ERR_UNSUPPORTED, "tc_gemm: gathered GEMM supports (Nout,K) in {(128,<=256),(256,<=256)} (got %d,%d)", g.Nout, g.K);
   }
-  PZ_REQUIRE(g.M % (256 * nsets) == 0, PZ_ERR_UNSUPPORTED, "tc_gemm: M=%d must be a multiple of %d", g.M, 256 * nsets);
-  return tc_launch<256, 1, false, false, 4>(g, st);
 }
+int launch_tc_gemm_gather(const TcGemm& g, cudaStream_t st, int nsets) { return launch_tc_gemm_gather_impl(g, st, nsets); }
 
 // fp32 -> bf16 with row strides (weights packs, activations entering the tensor-core path)
 __global__ void __launch_bounds__(256) cvt_bf16_kernel(const float* __restrict__ in, int ldi, int rows, int cols,

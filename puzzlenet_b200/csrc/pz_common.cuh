@@ -118,7 +118,9 @@ struct GemmF32 {
 int launch_gemm_f32(const GemmF32& g, cudaStream_t st);
 
 // gemm_tc.cu -- tcgen05 bf16 GEMM: D^T[ch,row] = W[ch,:] . X[row,:]  (see the file header)
+long long* kernel_timeline_buffer();   // pz_profile_attention_timeline's registered device buffer (or null)
 struct TcGemm {
+  long long* prof = nullptr;                       // gather mode: CTA 0 stamps its first jobs (slots 1024.., 1280.., 1408..)
   const __nv_bfloat16* W[2] = {nullptr, nullptr};  // [Nout, K] bf16 row-major, weight set = row / rows_per_wset
   int ldw = 0;
   const float* bias[2] = {nullptr, nullptr};       // [Nout] fp32

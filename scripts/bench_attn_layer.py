@@ -46,7 +46,9 @@ def main():
         model.predict5(batch, 0)
         torch.cuda.synchronize()
         _lib.call("pz_profile_attention_timeline", None)
-        report(tl.cpu().tolist(), 128, None)
+        t = tl.cpu().tolist()
+        report(t, 128, None)
+        report_gather(t)
         return
     B, L, C = a.clouds, 256, 256
     g = torch.Generator().manual_seed(0)
@@ -80,6 +82,23 @@ def main():
     torch.cuda.synchronize()
     _lib.call("pz_profile_attention_timeline", None)
     report(tl.cpu().tolist(), B, ms_call)
+
+
+def report_gather(t):
+    """CTA 0 of the stage-1 gather GEMM (tc_gemm_kernel<256,1,true,true>): producer group 0 (slots 1024 + 4 n: job
+    start, data landed, Q done, transformed + published), MMA issuer (1280 + job: operands ready), epilogue (1408 + 2 tile:
+    accumulator ready, tile done)."""
+    mhz = 1965.0
+    t0 = t[1024]
+    if t0 == 0:
+        return
+    print("gather GEMM (stage 1), CTA 0; us since producer group 0 started job 0")
+    for n in range(10):
+        a = [(t[1024 + 4 * n + k] - t0) / mhz for k in range(4)]
+        print(f"  group-0 job {2 * n:2d}: start {a[0]:7.2f}  landed {a[1]:7.2f}  Q {a[2]:7.2f}  published {a[3]:7.2f}")
+    print("  MMA: operands of job n ready at", [round((t[1280 + n] - t0) / mhz, 2) for n in range(20)])
+    print("  epilogue (acc ready, done) per tile:", [(round((t[1408 + 2 * n] - t0) / mhz, 2), round((t[1409 + 2 * n] - t0) / mhz, 2))
+                                                      for n in range(8)])
 
 
 def report(t, B, ms_call):
