@@ -409,19 +409,6 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const TcGemm g) {
 #pragma unroll
               for (int i = 0; i < 32; ++i, yp += g.ldyb) *yp = __float2bfloat16_rn(v[i]);
             }
-          } else {
-            float m = v[0];
-#pragma unroll
-            for (int i = 1; i < 32; ++i) m = fmaxf(m, v[i]);
-            if (g.epi == 1) {  // one output row per group of 32
-              float x = m + bv;
-              if (g.relu) x = fmaxf(x, 0.f);
-              const size_t grow = (size_t)(row0 >> 5) + c32;
-              if (g.Yf) g.Yf[grow * g.ldyf + ch] = x;
-              if (g.Yb) g.Yb[grow * g.ldyb + ch] = __float2bfloat16_rn(x);
-            } else {
-              cmax = fmaxf(cmax, m);
-            }
           }
         }
         if (g.epi == 0 && g.Ymax && ch_ok) g.Ymax[((size_t)rt * 2 + half) * g.ldmax + ch] = tmax;   // 2 partials per tile

@@ -227,6 +227,32 @@ def test_encoder_bf16_intermediates(bf16_model, state_dict):
     print("bf16 encoder rel errors:", errs, "attention map:", attn_err)
     assert max(errs.values()) < REL_BF16, errs
     assert attn_err < 0.25
+    # the tensor-core stem (stem_tc_kernel) is a split-bf16 product: x_feature, an output in its own right, stays at
+    # fp32 accuracy in the bf16 path too
+    assert errs["x_feature"] < 1e-4, errs["x_feature"]
+
+
+def test_attention_timeline_hook(bf16_model):
+    """pz_profile_attention_timeline: off by default, and when a buffer is registered CTA 0 of the fused attention
+    layer leaves increasing SM clock stamps at its phase boundaries (the instrumented bench script relies on it)."""
+    from puzzlenet_b200 import _lib
+    fpc, mrpc = synthetic_pairs(2, seed=3)
+    batch = make_batch(fpc.to(DEV), mrpc.to(DEV))
+    tl = torch.zeros(64 + 2 * 4096, device=DEV, dtype=torch.int64)
+    bf16_model.predict5(batch, 0)
+    torch.cuda.synchronize()
+    assert int(tl.abs().sum()) == 0
+    _lib.call("pz_profile_attention_timeline", tl.data_ptr())
+    try:
+        bf16_model.predict5(batch, 0)
+        torch.cuda.synchronize()
+    finally:
+        _lib.call("pz_profile_attention_timeline", None)
+    t = tl.cpu().tolist()
+    order = [15, 0, 2, 3, 4, 5, 6, 7, 10, 11, 12, 13, 17, 14]     # entry, start, q|k ... out stored (epilogue thread 0)
+    stamps = [t[i] for i in order]
+    assert all(b > a for a, b in zip(stamps, stamps[1:])), stamps
+    assert t[64 + 1] > t[64] > 0                                   # %globaltimer at entry / exit of CTA 0
 
 
 @pytest.mark.parametrize("B", [2, 3])
