@@ -414,8 +414,9 @@ def run_gpu_arm(args):
         "sg1_gather_layer2_maxpool": (2.0 * clouds * 512 * 32 * 128 * 128, "tensor", 1),
         "sg2_gather_layer2_maxpool": (2.0 * clouds * 256 * 32 * 256 * 256, "tensor", 1),
         "tail_linear_maxpool": (2.0 * clouds * 256 * 1280 * 1024, "tensor", 1),
-        # bf16 path: one fused kernel per layer = q|k|v projections + Q K^T + P V + out-projection (125.8 MFLOP per cloud)
-        "attn_layer_fused": (4 * 2.0 * clouds * 256 * 256 * (384 + 64 + 256 + 256), "tensor", 4),
+        # bf16 path: ONE launch for the four layers of every cloud; per layer q|k|v projections + Q K^T + P V + out-projection
+        # (125.8 MFLOP per cloud and layer)
+        "attn_layer_fused": (4 * 2.0 * clouds * 256 * 256 * (384 + 64 + 256 + 256), "tensor", 1),
         "attn_qkv_proj": (4 * 2.0 * clouds * 256 * 256 * 384, "tensor", 4 if args.precision == "bf16" else 12),
         "attn_out_proj": (4 * 2.0 * clouds * 256 * 256 * 256, "tensor", 4),
         "attn_softmax_av": (4 * 2.0 * clouds * 256 * 256 * (64 + 256), "tensor", 4),
@@ -451,7 +452,7 @@ def run_gpu_arm(args):
     # profiles/r01_prof_knn.txt (bf16 path)
     ncu_traffic = {"sg1_gather_layer2_maxpool": 58.84e6 + 3.92e6, "sg2_gather_layer2_maxpool": 54.84e6 + 3.96e6,
                    "tail_linear_maxpool": 89.18e6 + 4.42e6, "fps1": 1.62e6, "knn1": 2.41e6, "knn2": 1.23e6,
-                   "attn_layer_fused": 17.51e6 + 0.06e6,
+                   "attn_layer_fused": 4 * (17.51e6 + 0.06e6),
                    "attn_softmax_av": 41.97e6 + 0.08e6} if args.precision == "bf16" else {}
     rooflines = {k: roof(k) for k in work if per_step.get(k, 0) > 0}
     for k, r in rooflines.items():

@@ -48,8 +48,8 @@ constexpr int B_FULL = 0, B_CONS = NTILES - 4, B_C = 2 * NTILES - 4;    // cons[
 constexpr int C_QK = B_C, C_V = B_C + 1, C_S = B_C + 2, C_PV0 = B_C + 3, C_PV1 = B_C + 4, C_OUT = B_C + 5;
 constexpr int F_X = B_C + 6;                       // x k-block kb landed (TMA): for the projections, for r, for out
 constexpr int F_XR = F_X + 4, F_XO = F_X + 8;
-constexpr int G_QK = F_X + 12, G_V = G_QK + 1, G_P0 = G_QK + 2, G_R = G_QK + 4;   // G_P1 = G_P0 + 1
-constexpr int NBARS = G_R + 1;
+constexpr int G_QK = F_X + 12, G_V = G_QK + 1, G_P0 = G_QK + 2, G_R = G_QK + 4, G_OUT = G_QK + 5;   // G_P1 = G_P0 + 1
+constexpr int NBARS = G_OUT + 1;
 constexpr uint32_t MISC_BYTES = 1024 /*xch*/ + 512 /*q|k bias*/ + NBARS * 8 + 16;
 
 __device__ __forceinline__ uint4 pack8(const float* v) {
@@ -84,9 +84,11 @@ __device__ __forceinline__ void tma_store(const CUtensorMap* tm, int c0, int c1,
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(NEPI) : "memory"); }
 }  // namespace
 
-__global__ void __launch_bounds__(FT, 1) attention_layer_tc_kernel(const AttnLayerTc p,
-                                                                   const __grid_constant__ CUtensorMap tmx,
-                                                                   const __grid_constant__ CUtensorMap tmy) {
+struct alignas(64) AttnMaps {
+  CUtensorMap m[5];   // m[0]: input of layer 0; m[l + 1]: output of layer l = input of layer l + 1
+};
+
+__global__ void __launch_bounds__(FT, 1) attention_layer_tc_kernel(const AttnLayerTc p, const __grid_constant__ AttnMaps maps) {
   extern __shared__ __align__(1024) uint8_t fl_smem_raw[];
   const uint32_t base = (smem_u32(fl_smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = fl_smem_raw + (base - smem_u32(fl_smem_raw));
@@ -110,8 +112,13 @@ __global__ void __launch_bounds__(FT, 1) attention_layer_tc_kernel(const AttnLay
     if (t >= 14 && t < 18) return ra + (4 + t - 14) * SLOT;
     return rw + (t & 1) * SLOT;
   };
-  const uint8_t* wimg = reinterpret_cast<const uint8_t*>(p.wimg[set]);
-  auto load_w = [&](int t) { bulk_load(slot_of(t), wimg + (size_t)t * SLOT, SLOT, bar(B_FULL + t)); };
+  // layer l of the stack: weight images, biases and tensor maps advance per layer; every barrier completes exactly once
+  // per layer, so layer l waits with parity l & 1
+  const uint8_t* wimg0 = reinterpret_cast<const uint8_t*>(p.wimg[set]);
+  auto load_w = [&](int l, int t) {
+    bulk_load(slot_of(t), wimg0 + ((size_t)l * NTILES + t) * SLOT, SLOT, bar(B_FULL + t));
+  };
+  const CUtensorMap* tmx0 = &maps.m[0];
 
   if (tid < 128) tab[tid] = p.bqkv[set][tid];
   if (tid == NEPI) {
@@ -122,12 +129,12 @@ __global__ void __launch_bounds__(FT, 1) attention_layer_tc_kernel(const AttnLay
     fence_proxy_async();
     for (int kb = 0; kb < 4; ++kb) {
       expect_tx(bar(F_X + kb), 2 * SLOT);
-      tma_load(ra + kb * (2 * SLOT), &tmx, kb * 64, (int)row0, bar(F_X + kb));
-      tma_load(ra + kb * (2 * SLOT) + SLOT, &tmx, kb * 64, (int)row0 + 128, bar(F_X + kb));
-      load_w(kb);
+      tma_load(ra + kb * (2 * SLOT), tmx0, kb * 64, (int)row0, bar(F_X + kb));
+      tma_load(ra + kb * (2 * SLOT) + SLOT, tmx0, kb * 64, (int)row0 + 128, bar(F_X + kb));
+      load_w(0, kb);
     }
-    load_w(4);
-    load_w(5);
+    load_w(0, 4);
+    load_w(0, 5);
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
@@ -141,39 +148,56 @@ __global__ void __launch_bounds__(FT, 1) attention_layer_tc_kernel(const AttnLay
   if (warp == 8) {
     // ================= weight producer
     if (lane == 0) {
-      for (int t = 6; t < 14; ++t) {
-        mbar_wait(bar(B_CONS + t - 2), 0);
-        load_w(t);
-      }
-      // P and v^T are dead: x comes back into the slots where r is formed in place (block 0 in R_B, block 1 in
-      // A0-A3), and the upper half of R_A takes four Wo tiles
-      auto load_x_blocks = [&](int b) {
-        for (int kb = 0; kb < 4; ++kb) {
-          expect_tx(bar(b + kb), 2 * SLOT);
-          tma_load(rb + kb * SLOT, &tmx, kb * 64, (int)row0, bar(b + kb));
-          tma_load(ra + kb * SLOT, &tmx, kb * 64, (int)row0 + 128, bar(b + kb));
+#pragma unroll 1
+      for (int l = 0; l < p.nlayers; ++l) {
+        const uint32_t par = l & 1;
+        const CUtensorMap* tmx = &maps.m[l];
+        for (int t = 6; t < 14; ++t) {
+          mbar_wait(bar(B_CONS + t - 2), par);
+          load_w(l, t);
         }
-      };
-      mbar_wait(bar(C_PV1), 0);
-      load_x_blocks(F_XR);
-      for (int t = 14; t < 18; ++t) load_w(t);
-      for (int t = 18; t < 20; ++t) {
-        mbar_wait(bar(B_CONS + t - 6), 0);
-        load_w(t);
+        // P and v^T are dead: x comes back into the slots where r is formed in place (block 0 in R_B, block 1 in
+        // A0-A3), and the upper half of R_A takes four Wo tiles
+        mbar_wait(bar(C_PV1), par);
+        for (int kb = 0; kb < 4; ++kb) {
+          expect_tx(bar(F_XR + kb), 2 * SLOT);
+          tma_load(rb + kb * SLOT, tmx, kb * 64, (int)row0, bar(F_XR + kb));
+          tma_load(ra + kb * SLOT, tmx, kb * 64, (int)row0 + 128, bar(F_XR + kb));
+        }
+        for (int t = 14; t < 18; ++t) load_w(l, t);
+        for (int t = 18; t < 20; ++t) {
+          mbar_wait(bar(B_CONS + t - 6), par);
+          load_w(l, t);
+        }
+        // r and every weight tile are dead: x once more, for the output residual, into R_A in operand layout (the
+        // output tile formed over it is the next layer's x), and the next layer's first weight tiles
+        mbar_wait(bar(C_OUT), par);
+        for (int kb = 0; kb < 4; ++kb) {
+          expect_tx(bar(F_XO + kb), 2 * SLOT);
+          tma_load(ra + kb * (2 * SLOT), tmx, kb * 64, (int)row0, bar(F_XO + kb));
+          tma_load(ra + kb * (2 * SLOT) + SLOT, tmx, kb * 64, (int)row0 + 128, bar(F_XO + kb));
+        }
+        if (l + 1 < p.nlayers)
+          for (int t = 0; t < 6; ++t) load_w(l + 1, t);
       }
-      mbar_wait(bar(C_OUT), 0);   // r is dead: x once more, for the output residual
-      load_x_blocks(F_XO);
     }
     __syncwarp();
   } else if (warp == 9) {
     // ================= MMA issuer
     if (lane == 0) {
       const uint32_t id128 = make_idesc(128), id256 = make_idesc(256);
+#pragma unroll 1
+      for (int l = 0; l < p.nlayers; ++l) {
+      const uint32_t par = l & 1;
       stamp(p.prof, 32);
       // phase 1: q|k[tok, 0:128] = x Wqk^T   (rows on lanes; two 128-token blocks; N = 128) -> cols [0,256)
+      if (l > 0) {   // x = the previous layer's output tiles, formed in R_A; its accumulators are drained
+        mbar_wait(bar(G_OUT), par ^ 1);
+        tc_fence_after();
+      }
       for (int t = 0; t < 4; ++t) {
-        mbar_wait(bar(F_X + t), 0);
-        mbar_wait(bar(B_FULL + t), 0);
+        if (l == 0) mbar_wait(bar(F_X + t), 0);
+        mbar_wait(bar(B_FULL + t), par);
         tc_fence_after();
         const uint64_t bd = make_desc(slot_of(t));
 #pragma unroll
@@ -191,11 +215,11 @@ __global__ void __launch_bounds__(FT, 1) attention_layer_tc_kernel(const AttnLay
         const int t = 4 + j, chb = j >> 2, kb = j & 3;
         if (j == 4) {
           stamp(p.prof, 34);
-          mbar_wait(bar(G_QK), 0);
+          mbar_wait(bar(G_QK), par);
           tc_fence_after();
           stamp(p.prof, 35);
         }
-        mbar_wait(bar(B_FULL + t), 0);
+        mbar_wait(bar(B_FULL + t), par);
         tc_fence_after();
         const uint64_t ad = make_desc(slot_of(t)), bd = make_desc(ra + kb * (2 * SLOT));
 #pragma unroll
@@ -205,7 +229,7 @@ __global__ void __launch_bounds__(FT, 1) attention_layer_tc_kernel(const AttnLay
       umma_commit(bar(C_V));
       stamp(p.prof, 36);
       // phase 3: S_qb = q_qb k^T for both query blocks (N = 256 keys, K = 64)
-      mbar_wait(bar(G_V), 0);
+      mbar_wait(bar(G_V), par);
       tc_fence_after();
       stamp(p.prof, 37);
 #pragma unroll
@@ -217,7 +241,7 @@ __global__ void __launch_bounds__(FT, 1) attention_layer_tc_kernel(const AttnLay
       umma_commit(bar(C_S));
       // O_qb = P_qb v  (A = P [128 x 256 keys], B = v^T [256 ch x 256 keys]); overwrites S_qb
       for (int qb = 0; qb < 2; ++qb) {
-        mbar_wait(bar(G_P0 + qb), 0);
+        mbar_wait(bar(G_P0 + qb), par);
         tc_fence_after();
         stamp(p.prof, 38 + qb);
 #pragma unroll
@@ -229,12 +253,12 @@ __global__ void __launch_bounds__(FT, 1) attention_layer_tc_kernel(const AttnLay
         umma_commit(bar(C_PV0 + qb));
       }
       // out[tok, ch] = r Wo^T for both query blocks per weight tile, into the columns O occupied
-      mbar_wait(bar(G_R), 0);
+      mbar_wait(bar(G_R), par);
       tc_fence_after();
       stamp(p.prof, 40);
       for (int j = 0; j < 8; ++j) {
         const int t = 12 + j, chh = j >> 2, kb = j & 3;
-        mbar_wait(bar(B_FULL + t), 0);
+        mbar_wait(bar(B_FULL + t), par);
         tc_fence_after();
         const uint64_t bd = make_desc(slot_of(t));
 #pragma unroll
@@ -248,6 +272,7 @@ __global__ void __launch_bounds__(FT, 1) attention_layer_tc_kernel(const AttnLay
       }
       umma_commit(bar(C_OUT));
       stamp(p.prof, 41);
+      }
     }
     __syncwarp();
   } else {
@@ -256,19 +281,27 @@ __global__ void __launch_bounds__(FT, 1) attention_layer_tc_kernel(const AttnLay
     const int quarter = warp & 3, half = warp >> 2;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     const int lrow = quarter * 32 + lane;
-    const float* __restrict__ bqkv = p.bqkv[set];
-    const float* __restrict__ bo = p.bo[set];
+    long long* eprof = tid == 0 ? p.prof : nullptr;
+#pragma unroll 1
+    for (int l = 0; l < p.nlayers; ++l) {
+    const uint32_t par = l & 1;
+    const float* __restrict__ bqkv = p.bqkv[set] + (size_t)l * 384;
+    const float* __restrict__ bo = p.bo[set][l];
+    const int attn_mode = p.attn_mode[l];
     auto publish = [&](int b) {   // operand written / accumulator drained -> MMA issuer
       fence_proxy_async();
       tc_fence_before();
       mbar_arrive(bar(b));
     };
     auto acquire = [&](int b) {   // an MMA phase has completed
-      mbar_wait(bar(b), 0);
+      mbar_wait(bar(b), par);
       tc_fence_after();
     };
-    long long* eprof = tid == 0 ? p.prof : nullptr;
     stamp(eprof, 0);
+    if (l > 0) {   // this layer's q|k bias (the table's readers, the previous q|k epilogue, are long done)
+      if (tid < 128) tab[tid] = bqkv[tid];
+      epi_bar();
+    }
 
     // ---- q|k epilogue (under the v^T MMAs of channel block 0): warp half h owns token block h;
     // q -> R_B[0:32K) as [256 x 64], k -> R_B[32K:64K)
@@ -356,7 +389,7 @@ __global__ void __launch_bounds__(FT, 1) attention_layer_tc_kernel(const AttnLay
       epi_bar();
       const float inv_row = 1.0f / (sum + xch[half * 128 + lrow]);
       if (qb == 0) inv0 = inv_row; else inv1 = inv_row;
-      if (p.attn_mode != 0) {  // attention map (need=True): mean of the four layers' maps, model5_b.py:468-469
+      if (attn_mode != 0) {  // attention map (need=True): mean of the four layers' maps, model5_b.py:468-469
         float* ag = p.attn + grow * FL;
 #pragma unroll 1
         for (int c32 = half * 4; c32 < half * 4 + 4; ++c32) {
@@ -370,10 +403,10 @@ __global__ void __launch_bounds__(FT, 1) attention_layer_tc_kernel(const AttnLay
             a.z = exp2f(fmaf(v[q4 * 4 + 2], cexp, -mc)) * inv_row;
             a.w = exp2f(fmaf(v[q4 * 4 + 3], cexp, -mc)) * inv_row;
             float4* dst = reinterpret_cast<float4*>(ag + c32 * 32 + q4 * 4);
-            if (p.attn_mode != 1) {
+            if (attn_mode != 1) {
               const float4 o = *dst;
               a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w;
-              if (p.attn_mode == 3) { a.x *= 0.25f; a.y *= 0.25f; a.z *= 0.25f; a.w *= 0.25f; }
+              if (attn_mode == 3) { a.x *= 0.25f; a.y *= 0.25f; a.z *= 0.25f; a.w *= 0.25f; }
             }
             *dst = a;
           }
@@ -398,7 +431,7 @@ __global__ void __launch_bounds__(FT, 1) attention_layer_tc_kernel(const AttnLay
       for (int kb = 0; kb < 4; ++kb) {
         float v[64];
         tmem_ld64(t_row + kb * 64, v);
-        mbar_wait(bar(F_XR + kb), 0);
+        mbar_wait(bar(F_XR + kb), par);
         if (kb == 0) stamp(eprof, 1);
         uint8_t* dst = rdst + kb * SLOT;
 #pragma unroll
@@ -423,18 +456,20 @@ __global__ void __launch_bounds__(FT, 1) attention_layer_tc_kernel(const AttnLay
     xch[tid] = bo[tid];
     epi_bar();
 
-    // ---- out = x + relu(acc + bo), formed in place over x and handed to TMA one [128 x 64] tile at a time
+    // ---- out = x + relu(acc + bo), formed in place over x (R_A, operand layout: it is the next layer's x) and handed
+    // to TMA one [128 x 64] tile at a time
     acquire(C_OUT);
     stamp(eprof, 13);
     {
-      float* yf = p.yf ? p.yf + grow * p.ldyf : nullptr;
+      float* yf = p.yf ? p.yf + grow * p.ldyf + (size_t)l * p.yf_layer_stride : nullptr;
+      const CUtensorMap* tmy = &maps.m[l + 1];
 #pragma unroll 1
       for (int kb = 0; kb < 4; ++kb) {
         float v[64];
         tmem_ld64(t_row + kb * 64, v);
-        mbar_wait(bar(F_XO + kb), 0);
+        mbar_wait(bar(F_XO + kb), par);
         if (kb == 0) stamp(eprof, 16);
-        uint8_t* dst = rdst + kb * SLOT;
+        uint8_t* dst = gen + (ra - base) + kb * (2 * SLOT) + qb * SLOT;
 #pragma unroll
         for (int q8 = 0; q8 < 8; ++q8) {
           uint4* slot16 = reinterpret_cast<uint4*>(dst + sw128(lrow, q8));
@@ -457,15 +492,18 @@ __global__ void __launch_bounds__(FT, 1) attention_layer_tc_kernel(const AttnLay
         fence_proxy_async();
         asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory");
         if (lrow == 0) {
-          tma_store(&tmy, kb * 64, (int)row0 + qb * 128, rslots + kb * SLOT);
+          tma_store(tmy, kb * 64, (int)row0 + qb * 128, ra + kb * (2 * SLOT) + qb * SLOT);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       }
     }
-    tc_fence_before();
     stamp(eprof, 17);
-    if (lrow == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    // the stores are complete (the next layer reloads this output from global for its residuals) before the tiles and
+    // the accumulator columns are handed to the next layer
+    if (lrow == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    publish(G_OUT);
     stamp(eprof, 14);
+    }
   }
   __syncthreads();   // every TMEM read has retired, the TMA stores have read their tiles
   if (p.prof != nullptr && tid == 0) {
@@ -526,17 +564,22 @@ static int make_tile_map(const __nv_bfloat16* ptr, int ld, size_t rows, CUtensor
 int launch_attention_layer_tc(const AttnLayerTc& p_in, int clouds, cudaStream_t st) {
   AttnLayerTc p = p_in;
   p.prof = g_attn_timeline;
-  PZ_REQUIRE(p.x && p.wimg[0] && p.bqkv[0] && p.bo[0] && p.yb, PZ_ERR_ARG, "attention_layer_tc: null pointer");
+  PZ_REQUIRE(p.x && p.wimg[0] && p.bqkv[0] && p.bo[0][0] && p.yb, PZ_ERR_ARG, "attention_layer_tc: null pointer");
+  PZ_REQUIRE(p.nlayers >= 1 && p.nlayers <= 4, PZ_ERR_ARG, "attention_layer_tc: %d layers (1..4)", p.nlayers);
+  for (int l = 0; l < p.nlayers; ++l)
+    PZ_REQUIRE(p.bo[0][l] && (p.clouds_per_set >= clouds || p.bo[1][l]), PZ_ERR_ARG, "attention_layer_tc: missing bias of layer %d", l);
   PZ_REQUIRE(p.ldx % 8 == 0 && p.ldyb % 8 == 0 && ((uintptr_t)p.x & 15) == 0 && ((uintptr_t)p.yb & 15) == 0 &&
                  (!p.yf || (p.ldyf % 4 == 0 && ((uintptr_t)p.yf & 15) == 0)) && ((uintptr_t)p.wimg[0] & 15) == 0,
              PZ_ERR_ARG, "attention_layer_tc: rows must be 16-byte aligned");
   const size_t smem = 1024 + RA_BYTES + RB_BYTES + RW_BYTES + MISC_BYTES;
   static_assert(1024 + RA_BYTES + RB_BYTES + RW_BYTES + MISC_BYTES <= 232448, "attention layer: shared memory budget");
   PZ_CUDA(cudaFuncSetAttribute(attention_layer_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  alignas(64) CUtensorMap tmx, tmy;
-  PZ_TRY(make_tile_map(p.x, p.ldx, (size_t)clouds * FL, &tmx));
-  PZ_TRY(make_tile_map(p.yb, p.ldyb, (size_t)clouds * FL, &tmy));
-  attention_layer_tc_kernel<<<clouds, FT, smem, st>>>(p, tmx, tmy);
+  AttnMaps maps;
+  PZ_TRY(make_tile_map(p.x, p.ldx, (size_t)clouds * FL, &maps.m[0]));
+  for (int l = 0; l < 4; ++l)   // unused layers repeat the last output: every map handed to the kernel is valid
+    PZ_TRY(make_tile_map(p.yb + (size_t)(l < p.nlayers ? l : p.nlayers - 1) * p.yb_layer_stride, p.ldyb, (size_t)clouds * FL,
+                         &maps.m[l + 1]));
+  attention_layer_tc_kernel<<<clouds, FT, smem, st>>>(p, maps);
   PZ_LAUNCH_CHECK();
   return 0;
 }

@@ -1164,15 +1164,19 @@ static int encoder_forward_bf16(const PzEncoderWeights* w, int E, int B, const f
   // ---- 4 x offset attention
   const int rows = C * LATT;
   static const bool fused_attn = !(getenv("PZ_FUSED_ATTN") && getenv("PZ_FUSED_ATTN")[0] == '0');
-  for (int l = 0; l < 4 && fused_attn; ++l) {   // one kernel per layer: nothing but x and out touches HBM
+  if (fused_attn) {   // the four layers of a cloud in one launch: nothing but the layer inputs / outputs touches HBM
     AttnLayerTc p;
-    p.x = l == 0 ? cat_b + 4 * CATT : cat_b + (l - 1) * CATT; p.ldx = 1280;
-    p.wimg[0] = wpa + WP_ATTIMG + (size_t)l * ATTN_WIMG_ELEMS; p.wimg[1] = wpb + WP_ATTIMG + (size_t)l * ATTN_WIMG_ELEMS;
-    p.bqkv[0] = s.bqkv + (size_t)l * 384; p.bqkv[1] = s.bqkv + ((size_t)(E - 1) * 4 + l) * 384;
-    p.bo[0] = wa.o_b[l]; p.bo[1] = wb.o_b[l];
-    p.clouds_per_set = B; p.yb = cat_b + l * CATT; p.ldyb = 1280;
-    if (cat_f) { p.yf = cat_f + l * CATT; p.ldyf = 1280; }
-    p.attn = o.attention; p.attn_mode = o.attention ? (l == 0 ? 1 : (l == 3 ? 3 : 2)) : 0;
+    p.nlayers = 4;
+    p.x = cat_b + 4 * CATT; p.ldx = 1280;
+    p.wimg[0] = wpa + WP_ATTIMG; p.wimg[1] = wpb + WP_ATTIMG;
+    p.bqkv[0] = s.bqkv; p.bqkv[1] = s.bqkv + (size_t)(E - 1) * 4 * 384;
+    for (int l = 0; l < 4; ++l) {
+      p.bo[0][l] = wa.o_b[l]; p.bo[1][l] = wb.o_b[l];
+      p.attn_mode[l] = o.attention ? (l == 0 ? 1 : (l == 3 ? 3 : 2)) : 0;
+    }
+    p.clouds_per_set = B; p.yb = cat_b; p.ldyb = 1280; p.yb_layer_stride = CATT;
+    if (cat_f) { p.yf = cat_f; p.ldyf = 1280; p.yf_layer_stride = CATT; }
+    p.attn = o.attention;
     PZ_TRY(launch_attention_layer_tc(p, C, st));
     prof_mark("attn_layer_fused", st);
   }
@@ -1616,9 +1620,10 @@ extern "C" int pz_offset_attention(const float* x, const float* Wq, const float*
     PZ_CUDA(cudaMemcpyAsync(bqkv + 64, bk, 64 * sizeof(float), cudaMemcpyDeviceToDevice, st));
     PZ_CUDA(cudaMemcpyAsync(bqkv + 128, bv, C * sizeof(float), cudaMemcpyDeviceToDevice, st));
     AttnLayerTc p;
-    p.x = xb; p.ldx = C; p.wimg[0] = p.wimg[1] = wimg; p.bqkv[0] = p.bqkv[1] = bqkv; p.bo[0] = p.bo[1] = bo;
+    p.nlayers = 1;
+    p.x = xb; p.ldx = C; p.wimg[0] = p.wimg[1] = wimg; p.bqkv[0] = p.bqkv[1] = bqkv; p.bo[0][0] = p.bo[1][0] = bo;
     p.clouds_per_set = B; p.yb = yb; p.ldyb = C; p.yf = out; p.ldyf = C;
-    p.attn = attention_or_null; p.attn_mode = attention_or_null ? 1 : 0;
+    p.attn = attention_or_null; p.attn_mode[0] = attention_or_null ? 1 : 0;
     return launch_attention_layer_tc(p, B, st);
   }
   float* q = a.take<float>(rows * (C / 4));

@@ -157,22 +157,26 @@ int launch_tc_rowgemm(const TcGemm& g, cudaStream_t st);   // gemm_tc_rows.cu: s
 // attention_tc.cu: per cloud  r = x - softmax(q k^T / sqrt(64)) v   on tcgen05 (L == 256, d_k == 64, C == 256)
 int launch_attention_tc(const __nv_bfloat16* qk, const __nv_bfloat16* vT, const __nv_bfloat16* x, int ldx, int clouds,
                         __nv_bfloat16* r, float* attn, int attn_mode, cudaStream_t st);
-// attention_layer_tc.cu: one whole offset-attention layer per cloud (projections, softmax, P v, out-proj, residuals)
+// attention_layer_tc.cu: a stack of 1-4 offset-attention layers per cloud in ONE launch (per layer: projections, softmax,
+// P v, out-proj, residuals); layer l + 1 reads the output of layer l
 struct AttnLayerTc {
-  const __nv_bfloat16* x = nullptr;       // [clouds*256, ldx] layer input
+  int nlayers = 1;
+  const __nv_bfloat16* x = nullptr;       // [clouds*256, ldx] input of layer 0
   int ldx = 0;
-  // 20 pre-swizzled [128 x 64] tile images (16 KB each): Wqkv [384, 256] (q rows 0-63, k 64-127, v 128-383) as
-  // tiles (row block, k-block) 0-11, then Wo [256, 256] as tiles 12-19 (launch_attn_weight_image)
+  // per layer 20 pre-swizzled [128 x 64] tile images (16 KB each): Wqkv [384, 256] (q rows 0-63, k 64-127, v 128-383) as
+  // tiles (row block, k-block) 0-11, then Wo [256, 256] as tiles 12-19 (launch_attn_weight_image); layers contiguous
   const __nv_bfloat16* wimg[2] = {nullptr, nullptr};
-  const float* bqkv[2] = {nullptr, nullptr};           // [384]
-  const float* bo[2] = {nullptr, nullptr};             // [256]
+  const float* bqkv[2] = {nullptr, nullptr};           // [nlayers][384]
+  const float* bo[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};   // [256] per layer
   int clouds_per_set = 0;
-  __nv_bfloat16* yb = nullptr;            // [clouds*256, ldyb] layer output (bf16)
+  __nv_bfloat16* yb = nullptr;            // [clouds*256, ldyb] output of layer 0; layer l at yb + l * yb_layer_stride
   int ldyb = 0;
-  float* yf = nullptr;                    // optional fp32 copy
+  size_t yb_layer_stride = 0;
+  float* yf = nullptr;                    // optional fp32 copy, layer l at yf + l * yf_layer_stride
   int ldyf = 0;
-  float* attn = nullptr;                  // attention map accumulation (see attention_tc_kernel)
-  int attn_mode = 0;
+  size_t yf_layer_stride = 0;
+  float* attn = nullptr;                  // attention map accumulation (see attention_tc_kernel), mode per layer
+  int attn_mode[4] = {0, 0, 0, 0};
   long long* prof = nullptr;              // pz_profile_attention_timeline
 };
 int launch_attention_layer_tc(const AttnLayerTc& p, int clouds, cudaStream_t st);
