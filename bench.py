@@ -450,16 +450,16 @@ def run_gpu_arm(args):
     # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed ncu --set full
     # captures of this same command: profiles/r01_top_kernels_bf16.txt, profiles/r01_top_kernels_fwd_full.txt,
     # profiles/r01_prof_knn.txt (bf16 path)
-    ncu_traffic = {"sg1_gather_layer2_maxpool": 58.84e6 + 3.92e6, "sg2_gather_layer2_maxpool": 54.84e6 + 3.96e6,
-                   "tail_linear_maxpool": 89.18e6 + 4.42e6, "fps1": 1.62e6, "knn1": 2.41e6, "knn2": 1.23e6,
-                   "attn_layer_fused": 4 * (17.51e6 + 0.06e6),
+    ncu_traffic = {"sg1_gather_layer2_maxpool": 42.89e6 + 1.29e6, "sg2_gather_layer2_maxpool": 38.53e6 + 1.15e6,
+                   "tail_linear_maxpool": 89.18e6 + 4.74e6, "fps1": 1.62e6, "knn1": 2.40e6, "knn2": 1.22e6,
+                   "attn_layer_fused": 19.49e6 + 11.06e6,
                    "attn_softmax_av": 41.97e6 + 0.08e6} if args.precision == "bf16" else {}
     rooflines = {k: roof(k) for k in work if per_step.get(k, 0) > 0}
     for k, r in rooflines.items():
         if k in ncu_traffic:
             r["traffic"] = ncu_traffic[k]
-            r["traffic_source"] = ("ncu --set full, profiles/r01_knn_attn_full.txt (kNN, attention layer) / "
-                                   "r01_top_kernels_bf16.txt (GEMMs) (per launch, bytes)")
+            r["traffic_source"] = ("ncu --set full inside one B=64 forward, profiles/r01_knn_attn_full.txt (per launch, "
+                                   "bytes; FPS: r01_top_kernels_fwd_full.txt)")
     # dominant kernel = the stage with the largest live time among those with a defined roofline
     roofline = rooflines[max(rooflines, key=lambda k: per_step[k])] if rooflines else None
 
