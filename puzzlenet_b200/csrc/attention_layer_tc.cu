@@ -1,18 +1,22 @@
-// One offset-attention layer (layerAttention.forward, model5_b.py:92-101) as ONE tcgen05 kernel per cloud:
+// A stack of 1-4 offset-attention layers (layerAttention.forward, model5_b.py:92-101; the encoder applies four in a row,
+// model5_b.py:463-466) as ONE tcgen05 kernel, one CTA per cloud.  Per layer:
 //   q|k = x Wqk^T + b,  v = x Wv^T + b,  A = softmax(q k^T / sqrt(64)),  r = x - A v,  out = x + relu(r Wo^T + bo)
-// for L = 256 tokens, C = 256 channels, d_k = 64 (bf16 operands, fp32 accumulation in TMEM).
-// Nothing but x (in) and out (written into its 256-column slice of att_cat) touches HBM: q, k, v^T, P and r live
-// in shared memory as K-major SWIZZLE_128B MMA operands.  x enters through TMA tensor loads ([128 tok x 64 ch] boxes,
-// SWIZZLE_128B) three times -- as the projections' operand, then again straight into the slots where r and the output
-// tile are formed in place (the residuals) -- and the output leaves through TMA tensor stores: a thread owns a token
-// row (its TMEM lane), so direct global accesses would touch 32 cache lines per warp instruction.
+// for L = 256 tokens, C = 256 channels, d_k = 64 (bf16 operands, fp32 accumulation in TMEM); layer l + 1 only needs
+// layer l of the same cloud, so a CTA walks the layers back to back.
+// Nothing but each layer's x (in) and out (written into its 256-column slice of att_cat) touches HBM: q, k, v^T, P and
+// r live in shared memory as K-major SWIZZLE_128B MMA operands.  x enters through TMA tensor loads ([128 tok x 64 ch]
+// boxes, SWIZZLE_128B): as the projections' operand (layer 0 only -- afterwards the output tile of layer l, formed in
+// R_A in operand layout, IS the x of layer l + 1), then again straight into the slots where r and the output tile are
+// formed in place (the residuals); the output leaves through TMA tensor stores: a thread owns a token row (its TMEM
+// lane), so direct global accesses would touch 32 cache lines per warp instruction.
 //
 // Warp-specialised: warps 0-7 are the epilogue group (TMEM -> registers -> shared-memory operands / global output),
 // warp 8 lane 0 is the weight producer, warp 9 lane 0 issues every MMA.  The three roles only meet through
-// single-use mbarriers (one cloud per CTA, so every barrier completes exactly once: parity 0 everywhere):
+// mbarriers that complete exactly once per layer (layer l waits with parity l & 1):
 //   full[t]  weight tile t has landed (bulk-copy complete_tx)     cons[t]  the MMAs reading tile t have completed
 //   c_*      tcgen05.commit of an MMA phase (accumulator ready, operands dead)
-//   g_*      256 epilogue arrivals: operand written to shared memory and the accumulator columns drained
+//   g_*      256 epilogue arrivals: operand written to shared memory and the accumulator columns drained (g_out: the
+//            layer's output tiles are stored and in place as the next x)
 // so the q|k epilogue runs under the v^T MMAs, weight tiles stream under epilogues, and no phase starts with a cold
 // weight ring.
 //
@@ -23,7 +27,7 @@
 //   t 12-19 Wo   (ch half, k-block)  (B operand of the out-projection, streamed ONCE for both query blocks)
 //                                                                -> W0/W1, and A4-A7 once v^T is dead
 // Shared memory, 14 slots of 16 KB:  R_A = A0-A7: x [256 tok x 256 ch] as 4 k-blocks -> v^T [256 ch x 256 tok]
-//                                          -> r of query block 1 (A0-A3) + Wo tiles (A4-A7);
+//                                          -> r of query block 1 (A0-A3) + Wo tiles (A4-A7) -> x again -> out = next x;
 //                                    R_B = B0-B3: Wqk tiles -> q,k -> P0 -> P1 -> r of query block 0;   R_W = W0,W1.
 // TMEM (512 columns): q|k [0,256) | v^T ch 0-127 [256,512) -> v^T ch 128-255 [0,256) -> S0 [0,256) S1 [256,512)
 //                     -> O in place -> out in place.
