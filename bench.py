@@ -135,7 +135,7 @@ def run_reference_arm(args):
                          "sample": f"{args.steps} steps x {pairs} pairs, oracle.puzzle_oracle.predict5 (torch CPU fp32)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit_line(line)
     return 0
 
 
@@ -223,8 +223,6 @@ def run_gpu_arm(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # NCCL prints its version banner to stdout when NCCL_DEBUG is set: keep stdout to the one JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
 
@@ -520,10 +518,23 @@ def run_gpu_arm(args):
         "gflop_per_pair_reference_count": FLOP_PER_PAIR_REFERENCE / 1e9,
         "wall_s_timed_region": wall,
     }
-    print(json.dumps(line))
+    emit_line(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+_REAL_STDOUT = None
+
+
+def emit_line(line) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        sys.stdout.buffer.write(data)
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
@@ -540,6 +551,12 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip the short training-step / assembly runs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    # stdout carries exactly ONE JSON line: libraries that write to file descriptor 1 themselves (NCCL prints its version
+    # banner there when NCCL_DEBUG is set) are pointed at stderr for the whole run; emit_line writes to the real stdout
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference_arm(args)
     return run_gpu_arm(args)
