@@ -327,10 +327,10 @@ def run_gpu_arm(args):
         out_host[1].copy_(de_f, non_blocking=True)
         out_host[2].copy_(de_m, non_blocking=True)
 
-    # two CUDA streams alternate so that the copies and the latency-bound stages (FPS chain, pose MLP) of one
+    # several CUDA streams (--pipes) alternate so that the copies and the latency-bound stages (FPS chain, pose MLP) of one
     # batch overlap the tensor-core stages of the other; every copy and kernel of all K steps is inside the region
     pipes = [torch.cuda.Stream(device=dev) for _ in range(args.pipes)]
-    model.cuda_graphs = not args.no_graphs          # one captured CUDA graph per stream replays the ~75 launches
+    model.cuda_graphs = not args.no_graphs          # one captured CUDA graph per stream replays the 22 launches
 
     # ---- value: device-resident rotating batches over the same streams / graphs, K steps inside one event pair
     def run_resident(n):

@@ -315,7 +315,7 @@ class TouchedRegraster(_Base):
         return outs
 
     def _graph_replay(self, fpc, mrpc, starts, need, shared=False):
-        """CUDA-graph mode (``model.cuda_graphs = True``): the ~75 launches of one forward (both streams of the
+        """CUDA-graph mode (``model.cuda_graphs = True``): the 22 launches of one forward (both streams of the
         internal fork/join included) are captured once per (batch size, need, precision, stream) and replayed.
         Inputs are copied into static buffers; the returned tensors are static too -- they are overwritten by
         the next call on the same stream.  A change of any parameter re-captures."""
