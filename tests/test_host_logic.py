@@ -120,3 +120,21 @@ def test_flat_parameter_buffer_and_gradient_buckets():
         lo = (p.data_ptr() - flat.params.data_ptr()) // 4
         assert 0 <= lo and lo + p.numel() <= flat.n
     assert live == 7_270_218
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference` (the driver's reference arm: the oracle port on the host cores) writes exactly one
+    JSON line to stdout, with the keys of the bench contract; anything else a library prints goes to stderr."""
+    import json
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, r.stdout[:500]
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["unit"] == "pairs/s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
