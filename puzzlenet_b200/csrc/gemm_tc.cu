@@ -451,7 +451,20 @@ static int tc_launch(const TcGemm& g, cudaStream_t st) {
   return 0;
 }
 
-int launch_tc_gemm_gather(const TcGemm& g, cudaStream_t st, int nsets);
+// gathered B operand, resident weights: stage 1 (Nout 128, 256-row tiles) and stage 2 (Nout 256, 128-row tiles)
+static int launch_tc_gemm_gather(const TcGemm& g, cudaStream_t st, int nsets) {
+  PZ_REQUIRE(g.centers && g.W1x[0] && g.epi == 1, PZ_ERR_ARG, "tc_gemm: gathered operand needs centres, W1x and the group-max epilogue");
+  if (g.Nout == 128 && g.K <= 256) {
+    PZ_REQUIRE(g.M % (256 * nsets) == 0, PZ_ERR_UNSUPPORTED, "tc_gemm: M=%d must be a multiple of %d", g.M, 256 * nsets);
+    return tc_launch<256, 1, true, true, 4>(g, st);
+  }
+  if (g.Nout == 256 && g.K <= 256) {
+    PZ_REQUIRE(g.M % (128 * nsets) == 0, PZ_ERR_UNSUPPORTED, "tc_gemm: M=%d must be a multiple of %d", g.M, 128 * nsets);
+    return tc_launch<128, 2, true, true, 5>(g, st);
+  }
+  return fail(PZ_ERR_UNSUPPORTED, "tc_gemm: gathered GEMM supports (Nout,K) in {(128,<=256),(256,<=256)} (got %d,%d)", g.Nout, g.K);
+}
+
 int launch_tc_gemm(const TcGemm& g, cudaStream_t st) {
   PZ_REQUIRE(g.W[0] && g.X && (g.Yf || g.Yb || g.YT), PZ_ERR_ARG, "tc_gemm: null operand");
   PZ_REQUIRE(g.M > 0 && g.Nout > 0 && g.K > 0, PZ_ERR_ARG, "tc_gemm: bad shape");
@@ -461,33 +474,14 @@ int launch_tc_gemm(const TcGemm& g, cudaStream_t st) {
              PZ_ERR_ARG, "tc_gemm: operands must be 16-byte aligned");
   const int nsets = (g.rows_per_wset > 0 && g.M > g.rows_per_wset) ? 2 : 1;
   if (nsets == 2) PZ_REQUIRE(g.W[1] && g.M == 2 * g.rows_per_wset, PZ_ERR_ARG, "tc_gemm: two weight sets need M == 2*rows_per_wset");
-  if (g.rows) {  // gathered B, resident weights
-    if (kernel_timeline_buffer()) {   // diagnostics: only the 256-row (stage 1) variant stamps, so one forward leaves one timeline
-      TcGemm gp = g;
-      gp.prof = (g.Nout == 128) ? kernel_timeline_buffer() : nullptr;
-      return launch_tc_gemm_gather(gp, st, nsets);
-    }
-    return launch_tc_gemm_gather(g, st, nsets);
+  if (g.rows) {
+    TcGemm gp = g;   // diagnostics: only the stage-1 variant stamps, so one forward leaves one timeline
+    gp.prof = (g.Nout == 128) ? kernel_timeline_buffer() : nullptr;
+    return launch_tc_gemm_gather(gp, st, nsets);
   }
   PZ_REQUIRE(g.M % (256 * nsets) == 0, PZ_ERR_UNSUPPORTED, "tc_gemm: M=%d must be a multiple of %d", g.M, 256 * nsets);
   return tc_launch<256, 1, false, false, 4>(g, st);
 }
-
-static int launch_tc_gemm_gather_impl(const TcGemm& g, cudaStream_t st, int nsets) {
-  {
-    PZ_REQUIRE(g.centers && g.W1x[0] && g.epi == 1, PZ_ERR_ARG, "tc_gemm: gathered operand needs centres, W1x and the group-max epilogue");
-    if (g.Nout == 128 && g.K <= 256) {
-      PZ_REQUIRE(g.M % (256 * nsets) == 0, PZ_ERR_UNSUPPORTED, "tc_gemm: M=%d must be a multiple of %d", g.M, 256 * nsets);
-      return tc_launch<256, 1, true, true, 4>(g, st);
-    }
-    if (g.Nout == 256 && g.K <= 256) {
-      PZ_REQUIRE(g.M % (128 * nsets) == 0, PZ_ERR_UNSUPPORTED, "tc_gemm: M=%d must be a multiple of %d", g.M, 128 * nsets);
-      return tc_launch<128, 2, true, true, 5>(g, st);
-    }
-    return fail(PZ_ERR_UNSUPPORTED, "tc_gemm: gathered GEMM supports (Nout,K) in {(128,<=256),(256,<=256)} (got %d,%d)", g.Nout, g.K);
-  }
-}
-int launch_tc_gemm_gather(const TcGemm& g, cudaStream_t st, int nsets) { return launch_tc_gemm_gather_impl(g, st, nsets); }
 
 // fp32 -> bf16 with row strides (weights packs, activations entering the tensor-core path)
 __global__ void __launch_bounds__(256) cvt_bf16_kernel(const float* __restrict__ in, int ldi, int rows, int cols,
