@@ -63,10 +63,13 @@ int pz_device_arch(void);
 long long pz_launch_count(void);
 int pz_profile_enable(int on);
 int pz_profile_collect(double* ms_host, const char** names_host, int* calls_host, int max_stages);
-/* Kernel-internal timeline of the fused attention layer (attention_layer_tc.cu): while a device buffer of 64 + 2 * clouds
- * int64 is registered, CTA 0 of every such launch stores SM clock stamps of its phase boundaries there (slots 0-17:
- * epilogue thread 0, 32-41: the MMA-issuing thread) and every CTA c its %globaltimer at entry / exit (64 + 2c, 65 + 2c).  NULL switches it off (the default). */
-int pz_profile_attention_timeline(long long* device_buf_or_null);
+/* Kernel-internal timelines: while a device buffer of n_slots int64 is registered, CTA 0 of every fused attention-layer
+ * launch (attention_layer_tc.cu) stores SM clock stamps of its phase boundaries there (slots 0-17: epilogue thread 0,
+ * 32-41: the MMA-issuing thread) and every CTA c its %globaltimer at entry / exit (64 + 2c, 65 + 2c) -- only when
+ * n_slots >= 64 + 2 * clouds; CTA 0 of the stage-1 gather GEMM (gemm_tc.cu) stamps slots 1024..1455 -- only when
+ * n_slots >= 1456.  A buffer too short for a stamp set switches that set off; n_slots < 64 is an argument error.
+ * NULL switches everything off (the default). */
+int pz_profile_attention_timeline(long long* device_buf_or_null, long long n_slots);
 
 /* ---------------------------------------------------------------- geometry */
 

@@ -49,7 +49,7 @@ SIGNATURES = {
     "pz_device_arch": (C.c_int, []),
     "pz_launch_count": (C.c_longlong, []),
     "pz_profile_enable": (C.c_int, [C.c_int]),
-    "pz_profile_attention_timeline": (C.c_int, [C.c_void_p]),
+    "pz_profile_attention_timeline": (C.c_int, [C.c_void_p, C.c_longlong]),
     "pz_profile_collect": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_char_p), C.POINTER(C.c_int), C.c_int]),
     "pz_fps": (C.c_int, [c_f32p, C.c_int, C.c_int, c_i64p, C.c_int, c_i64p, c_f32p, c_stream]),
     "pz_sqdist": (C.c_int, [c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, c_f32p, c_stream]),

@@ -539,7 +539,11 @@ int launch_attn_weight_image(const float* src, int rows, int row_off, __nv_bfloa
 }
 
 static long long* g_attn_timeline = nullptr;
-long long* kernel_timeline_buffer() { return g_attn_timeline; }
+static long long g_attn_timeline_slots = 0;
+// the registered buffer when it holds at least min_slots int64, else null (a short buffer switches that stamp set off)
+long long* kernel_timeline_buffer(long long min_slots) {
+  return g_attn_timeline_slots >= min_slots ? g_attn_timeline : nullptr;
+}
 
 // [rows, 256] bf16 view with a row stride of ld elements, traversed in [128 rows x 64 ch] SWIZZLE_128B boxes
 static int make_tile_map(const __nv_bfloat16* ptr, int ld, size_t rows, CUtensorMap* out) {
@@ -567,7 +571,7 @@ static int make_tile_map(const __nv_bfloat16* ptr, int ld, size_t rows, CUtensor
 
 int launch_attention_layer_tc(const AttnLayerTc& p_in, int clouds, cudaStream_t st) {
   AttnLayerTc p = p_in;
-  p.prof = g_attn_timeline;
+  p.prof = kernel_timeline_buffer(64 + 2 * (long long)clouds);
   PZ_REQUIRE(p.x && p.wimg[0] && p.bqkv[0] && p.bo[0][0] && p.yb, PZ_ERR_ARG, "attention_layer_tc: null pointer");
   PZ_REQUIRE(p.nlayers >= 1 && p.nlayers <= 4, PZ_ERR_ARG, "attention_layer_tc: %d layers (1..4)", p.nlayers);
   for (int l = 0; l < p.nlayers; ++l)
@@ -590,9 +594,13 @@ int launch_attention_layer_tc(const AttnLayerTc& p_in, int clouds, cudaStream_t 
 
 }  // namespace pz
 
-// diagnostics: a device buffer of 64 + 2 * clouds int64 that CTA 0 of every following fused attention-layer launch fills with SM
-// clock stamps (slots 0-14, 16, 17 epilogue thread 0, 15 kernel entry, 32-41 the MMA issuer); null switches it off
-extern "C" int pz_profile_attention_timeline(long long* device_buf_or_null) {
+// diagnostics: a device buffer of n_slots int64 that CTA 0 of every following fused attention-layer launch fills with SM
+// clock stamps (slots 0-14, 16, 17 epilogue thread 0, 15 kernel entry, 32-41 the MMA issuer; needs n_slots >= 64 + 2 * clouds)
+// and CTA 0 of the stage-1 gather GEMM with its own (slots 1024..1455; needs n_slots >= 1456); null switches it off
+extern "C" int pz_profile_attention_timeline(long long* device_buf_or_null, long long n_slots) {
+  PZ_REQUIRE(device_buf_or_null == nullptr || n_slots >= 64, PZ_ERR_ARG,
+             "pz_profile_attention_timeline: the buffer must hold at least 64 int64 (got %lld)", n_slots);
   pz::g_attn_timeline = device_buf_or_null;
+  pz::g_attn_timeline_slots = device_buf_or_null ? n_slots : 0;
   return 0;
 }

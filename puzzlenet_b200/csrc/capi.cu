@@ -66,21 +66,50 @@ void prof_mark(const char* stage, cudaStream_t st, int lane) {
 
 bool prof_serial() { return g_prof_serial; }
 
-int side_stream(SideStream** out) {
+// One side stream + event set per (device, caller stream): two host threads that enqueue on different streams of the
+// same device never share fork/join events (a shared set lets one call's geometry wait on the other call's fork), and
+// concurrent callers do not serialise their geometry on one stream.  Calls on the SAME caller stream are ordered by that
+// stream, as in any CUDA API.  The table is bounded: past 256 distinct caller streams the oldest entry is recycled
+// (its events are only ever waited on by work enqueued before the recycling call returns).
+int side_stream(SideStream** out, cudaStream_t caller) {
+  struct Entry {
+    int dev = -1;
+    cudaStream_t caller = nullptr;
+    SideStream s;
+  };
   static std::mutex mu;
-  static SideStream per_device[64];
+  static std::vector<Entry>* table = nullptr;
+  static size_t next_victim = 0;
   int dev = 0;
   PZ_CUDA(cudaGetDevice(&dev));
-  PZ_REQUIRE(dev >= 0 && dev < 64, PZ_ERR_UNSUPPORTED, "device ordinal %d out of range", dev);
   std::lock_guard<std::mutex> lk(mu);
-  SideStream& s = per_device[dev];
-  if (!s.stream) {
-    PZ_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
-    PZ_CUDA(cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming));
-    PZ_CUDA(cudaEventCreateWithFlags(&s.join_a, cudaEventDisableTiming));
-    PZ_CUDA(cudaEventCreateWithFlags(&s.join_b, cudaEventDisableTiming));
+  if (!table) {
+    table = new std::vector<Entry>();
+    table->reserve(256);          // entries never move: callers keep SideStream* across the lock
   }
-  *out = &s;
+  for (Entry& e : *table)
+    if (e.dev == dev && e.caller == caller) {
+      *out = &e.s;
+      return 0;
+    }
+  Entry* e = nullptr;
+  if (table->size() < 256) {
+    table->emplace_back();
+    e = &table->back();
+    PZ_CUDA(cudaStreamCreateWithFlags(&e->s.stream, cudaStreamNonBlocking));
+    PZ_CUDA(cudaEventCreateWithFlags(&e->s.fork, cudaEventDisableTiming));
+    PZ_CUDA(cudaEventCreateWithFlags(&e->s.join_a, cudaEventDisableTiming));
+    PZ_CUDA(cudaEventCreateWithFlags(&e->s.join_b, cudaEventDisableTiming));
+  } else {
+    for (size_t tries = 0; tries < table->size() && !e; ++tries) {   // recycle an entry of the same device
+      Entry& c = (*table)[next_victim++ % table->size()];
+      if (c.dev == dev) e = &c;
+    }
+    PZ_REQUIRE(e != nullptr, PZ_ERR_UNSUPPORTED, "side_stream: stream table exhausted");
+  }
+  e->dev = dev;
+  e->caller = caller;
+  *out = &e->s;
   return 0;
 }
 

@@ -1088,7 +1088,7 @@ static int encoder_forward_bf16(const PzEncoderWeights* w, int E, int B, const f
   // ---- geometry (FPS -> kNN, both stages, plus the centroid halves Q of layer 1) depends on coordinates only:
   // it runs on the side stream while the feature chain (stem, layer-1 GEMM) runs on the caller's stream.
   SideStream* ss = nullptr;
-  PZ_TRY(side_stream(&ss));
+  PZ_TRY(side_stream(&ss, st));
   static const bool env_serial = getenv("PZ_NO_SIDE_STREAM") != nullptr;   // profiling aid: clean per-stage times
   const bool serial = env_serial || prof_serial();
   cudaStream_t sg = serial ? st : ss->stream;

@@ -476,7 +476,7 @@ int launch_tc_gemm(const TcGemm& g, cudaStream_t st) {
   if (nsets == 2) PZ_REQUIRE(g.W[1] && g.M == 2 * g.rows_per_wset, PZ_ERR_ARG, "tc_gemm: two weight sets need M == 2*rows_per_wset");
   if (g.rows) {
     TcGemm gp = g;   // diagnostics: only the stage-1 variant stamps, so one forward leaves one timeline
-    gp.prof = (g.Nout == 128) ? kernel_timeline_buffer() : nullptr;
+    gp.prof = (g.Nout == 128) ? kernel_timeline_buffer(1456) : nullptr;   // slots 1024..1455
     return launch_tc_gemm_gather(gp, st, nsets);
   }
   PZ_REQUIRE(g.M % (256 * nsets) == 0, PZ_ERR_UNSUPPORTED, "tc_gemm: M=%d must be a multiple of %d", g.M, 256 * nsets);

@@ -46,13 +46,13 @@ void count_launch();
 void prof_begin(cudaStream_t st);
 void prof_mark(const char* stage, cudaStream_t st, int lane = 0);   // lane 1 = the internal side stream
 
-// Internal fork/join helper: one non-blocking side stream + events per device, created on first use and
-// reused by every call (capturable: the side stream is always joined back into the caller's stream).
+// Internal fork/join helper: one non-blocking side stream + events per (device, caller stream), created on first use
+// and reused by every call on that stream (capturable: the side stream is always joined back into the caller's stream).
 struct SideStream {
   cudaStream_t stream = nullptr;
   cudaEvent_t fork = nullptr, join_a = nullptr, join_b = nullptr;
 };
-int side_stream(SideStream** out);
+int side_stream(SideStream** out, cudaStream_t caller);
 bool prof_serial();   // pz_profile_enable(2): run the geometry chain on the caller's stream (clean per-stage times)
 
 static inline cudaStream_t as_stream(pz_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
@@ -118,7 +118,7 @@ struct GemmF32 {
 int launch_gemm_f32(const GemmF32& g, cudaStream_t st);
 
 // gemm_tc.cu -- tcgen05 bf16 GEMM: D^T[ch,row] = W[ch,:] . X[row,:]  (see the file header)
-long long* kernel_timeline_buffer();   // pz_profile_attention_timeline's registered device buffer (or null)
+long long* kernel_timeline_buffer(long long min_slots);   // pz_profile_attention_timeline's buffer if it holds >= min_slots int64, else null
 struct TcGemm {
   long long* prof = nullptr;                       // gather mode: CTA 0 stamps its first jobs (slots 1024.., 1280.., 1408..)
   const __nv_bfloat16* W[2] = {nullptr, nullptr};  // [Nout, K] bf16 row-major, weight set = row / rows_per_wset

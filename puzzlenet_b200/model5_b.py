@@ -44,6 +44,16 @@ except Exception:  # pytorch_lightning is not part of this image
     _Base = nn.Module
 
 PRECISIONS = {"fp32": _lib.PZ_PREC_FP32, "bf16": _lib.PZ_PREC_BF16}
+PACKED_PRECISIONS = ("bf16",)     # precisions whose converted weight packs live in the caller's workspace
+
+
+class _Workspace:
+    """A predict5 workspace and the key of the weight packs it currently holds (None: no valid pack)."""
+    __slots__ = ("buf", "pack_key")
+
+    def __init__(self, buf: torch.Tensor):
+        self.buf = buf
+        self.pack_key = None
 
 
 def _ptr(t):
@@ -241,7 +251,6 @@ class TouchedRegraster(_Base):
         self.MLPFpcb = _seq(128, 64, 32, 2)
         self.precision = "fp32"
         self._ws = {}
-        self._pack_keys = {}
         self._graphs = {}
         self._capture_stream = None
         self._trainer_state = None
@@ -260,14 +269,18 @@ class TouchedRegraster(_Base):
                 getattr(h, f"{field}_b")[j] = _param(mod[li].bias).data_ptr()
         return h
 
-    def _workspace(self, B: int, device) -> torch.Tensor:
+    def _workspace(self, B: int, device) -> "_Workspace":
         """One workspace per (batch size, device, CUDA stream): calls issued on different streams may overlap on
-        the GPU (a pipelined caller alternates streams), so they must not share scratch.  At most four are kept."""
+        the GPU (a pipelined caller alternates streams), so they must not share scratch.  At most four are kept.
+        The validity of the bf16 / split weight packs stored inside a workspace is a property of the workspace OBJECT
+        (``_Workspace.pack_key``), never of its address: an evicted workspace takes its key with it, so a block the
+        caching allocator hands to a workspace of another batch size (other pack offset) can never be taken for a
+        packed one."""
         key = (B, str(device), torch.cuda.current_stream(device).cuda_stream)
         ws = self._ws.get(key)
         if ws is None:
             nbytes = _lib.load().pz_predict5_workspace_bytes(B)
-            ws = torch.empty(nbytes, device=device, dtype=torch.uint8)
+            ws = _Workspace(torch.empty(nbytes, device=device, dtype=torch.uint8))
             if len(self._ws) >= 4:
                 self._ws.pop(next(iter(self._ws)))
             self._ws[key] = ws
@@ -295,22 +308,21 @@ class TouchedRegraster(_Base):
         if ws is None:
             ws = self._workspace(B, dev)
         flags = _lib.PZ_FLAG_NEED if need else 0
-        if reuse_packs is None and self.precision == "bf16":
-            # the bf16 weight packs live in the workspace: reusable while no parameter was touched (in-place writes
-            # bump _version, reallocation changes data_ptr) and the workspace / precision are the same
-            key = (self._param_key(), shared)
-            reuse_packs = self._pack_keys.get(ws.data_ptr()) == key
-            if len(self._pack_keys) >= 8:
-                self._pack_keys.clear()
-            self._pack_keys[ws.data_ptr()] = key
-        elif self.precision != "bf16":
-            self._pack_keys.pop(ws.data_ptr(), None)
+        packed = self.precision in PACKED_PRECISIONS
+        if reuse_packs is None and packed:
+            # the weight packs live in the workspace: reusable while no parameter was touched (in-place writes
+            # bump _version, reallocation changes data_ptr) and the workspace object / precision are the same
+            key = (self._param_key(), shared, self.precision)
+            reuse_packs = ws.pack_key == key
+            ws.pack_key = key
+        elif not packed:
+            ws.pack_key = None
         if reuse_packs:
             flags |= _lib.PZ_FLAG_REUSE_PACKS
         with torch.cuda.device(dev):
             _lib.call("pz_predict5", enc, ctypes.byref(heads), fpc.data_ptr(), mrpc.data_ptr(), B, starts.data_ptr(),
                       PRECISIONS[self.precision], flags, out6.data_ptr(), de_fpcb.data_ptr(),
-                      de_mrpcb.data_ptr(), _ptr(x2f), _ptr(af), _ptr(x2m), _ptr(am), ws.data_ptr(), ws.numel(),
+                      de_mrpcb.data_ptr(), _ptr(x2f), _ptr(af), _ptr(x2m), _ptr(am), ws.buf.data_ptr(), ws.buf.numel(),
                       _lib.stream_ptr())
         return outs
 
@@ -328,7 +340,8 @@ class TouchedRegraster(_Base):
             f32 = dict(device=dev, dtype=torch.float32)
             st = dict(fpc=torch.empty(B, 1024, 3, **f32), mrpc=torch.empty(B, 1024, 3, **f32),
                       starts=torch.empty(4, B, device=dev, dtype=torch.int64),
-                      ws=torch.empty(_lib.load().pz_predict5_workspace_bytes(B), device=dev, dtype=torch.uint8))
+                      ws=_Workspace(torch.empty(_lib.load().pz_predict5_workspace_bytes(B), device=dev,
+                                                dtype=torch.uint8)))
             st["fpc"].copy_(fpc); st["mrpc"].copy_(mrpc); st["starts"].copy_(starts)
             outs = self._launch(st["fpc"], st["mrpc"], st["starts"], need, st["ws"], None, reuse_packs=False,
                                 shared=shared)                                           # builds the packs
@@ -341,7 +354,7 @@ class TouchedRegraster(_Base):
                 cap = self._capture_stream
             with torch.cuda.graph(graph, stream=cap):
                 self._launch(st["fpc"], st["mrpc"], st["starts"], need, st["ws"], outs,
-                             reuse_packs=self.precision == "bf16", shared=shared)
+                             reuse_packs=self.precision in PACKED_PRECISIONS, shared=shared)
             g = dict(pkey=pkey, st=st, outs=outs, graph=graph)
             if len(self._graphs) >= 8:
                 self._graphs.clear()

@@ -59,19 +59,60 @@ def square_distance(src, dst):
     return out
 
 
-def index_points(points, idx):
-    """pointnet_util.py:39-50 -- points [B,N,C], idx [B,S] or [B,S,K] -> [B,S,(K,)C]."""
-    _lib.require_cuda(points, idx)
-    points = points.contiguous()
-    idx = _i64c(idx, "idx")
+def _needs_grad(*tensors) -> bool:
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
+
+
+def _gather_rows(points: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
     B, N, Cc = points.shape
-    raw = idx.shape
     M = idx.numel() // B if B else 0
     out = torch.empty(B, M, Cc, device=points.device, dtype=points.dtype)
     with torch.cuda.device(points.device):
         _lib.call("pz_gather", points.data_ptr(), idx.data_ptr(), B, N, Cc, M, points.element_size(), out.data_ptr(),
                   _lib.stream_ptr())
-    return out.reshape(*raw, Cc)
+    return out.reshape(*idx.shape, Cc)
+
+
+def _scatter_rows(grad: torch.Tensor, c0: int, C: int, idx: torch.Tensor, N: int, dst: torch.Tensor) -> None:
+    """dst[b, idx[b, m], 0:C] += grad[b, m, c0:c0+C] -- the backward of a row gather (pz_scatter_add_rows)."""
+    B = idx.shape[0]
+    M = idx.numel() // B
+    with torch.cuda.device(grad.device):
+        _lib.call("pz_scatter_add_rows", grad.data_ptr(), grad.shape[-1], c0, C, idx.data_ptr(), B * M, M, N,
+                  dst.data_ptr(), dst.shape[-1], _lib.stream_ptr())
+
+
+class _IndexPoints(torch.autograd.Function):
+    """index_points with the gradient the reference's advanced indexing has (pointnet_util.py:39-50):
+    d points[b, idx[b, m]] += d out[b, m]."""
+
+    @staticmethod
+    def forward(ctx, points, idx):
+        ctx.save_for_backward(idx)
+        ctx.n = points.shape[1]
+        return _gather_rows(points, idx)
+
+    @staticmethod
+    def backward(ctx, grad):
+        (idx,) = ctx.saved_tensors
+        grad = grad.contiguous().float()
+        Cc = grad.shape[-1]
+        dpoints = torch.zeros(idx.shape[0], ctx.n, Cc, device=grad.device, dtype=torch.float32)
+        _scatter_rows(grad.reshape(idx.shape[0], -1, Cc), 0, Cc, idx, ctx.n, dpoints)
+        return dpoints, None
+
+
+def index_points(points, idx):
+    """pointnet_util.py:39-50 -- points [B,N,C], idx [B,S] or [B,S,K] -> [B,S,(K,)C].  Differentiable in ``points``
+    (float32) like the reference's indexing."""
+    _lib.require_cuda(points, idx)
+    points = points.contiguous()
+    idx = _i64c(idx, "idx")
+    if _needs_grad(points):
+        if points.dtype != torch.float32:
+            raise TypeError("index_points: gradients are implemented for float32 points only")
+        return _IndexPoints.apply(points, idx)
+    return _gather_rows(points, idx)
 
 
 def _draw_start(B: int, N: int, device) -> torch.Tensor:
@@ -126,19 +167,11 @@ def knn_point(nsample, xyz, new_xyz, return_dist=False):
     return (idx, d2) if return_dist else idx
 
 
-def sample_and_group(npoint, radius, nsample, xyz, points, returnfps=False, knn=False):
-    """pointnet_util.py:99-136.
-
-    Returns ``new_xyz [B,npoint,3]``, ``new_points [B,npoint,nsample,3+D]`` (xyz-relative first,
-    then features) and, with ``returnfps=True``, also ``grouped_xyz`` and ``fps_idx``.
-    """
-    xyz = _f32c(xyz, "xyz")
-    B, N, C = xyz.shape
-    S, K = int(npoint), int(nsample)
+def _sample_and_group_forward(S, radius, K, xyz, feat, returnfps, knn):
+    B, N, _ = xyz.shape
     start = _draw_start(B, N, xyz.device)
     fps_idx, new_xyz = _fps(xyz, S, start, True)
     idx = knn_point(K, xyz, new_xyz) if knn else query_ball_point(radius, K, xyz, new_xyz)
-    feat = _f32c(points, "points") if points is not None else None
     D = feat.shape[-1] if feat is not None else 0
     new_points = torch.empty(B, S, K, 3 + D, device=xyz.device, dtype=torch.float32)
     grouped_xyz = torch.empty(B, S, K, 3, device=xyz.device, dtype=torch.float32) if returnfps else None
@@ -146,6 +179,68 @@ def sample_and_group(npoint, radius, nsample, xyz, points, returnfps=False, knn=
         _lib.call("pz_group_concat", xyz.data_ptr(), feat.data_ptr() if feat is not None else None,
                   new_xyz.data_ptr(), idx.data_ptr(), B, N, D, S, K, new_points.data_ptr(),
                   grouped_xyz.data_ptr() if returnfps else None, _lib.stream_ptr())
+    return new_xyz, new_points, grouped_xyz, fps_idx, idx
+
+
+class _SampleAndGroup(torch.autograd.Function):
+    """sample_and_group with the reference's gradients (pointnet_util.py:115-130): the indices are constants;
+    ``new_points = cat(xyz[idx] - new_xyz[:, :, None], points[idx])`` and ``new_xyz = xyz[fps_idx]`` are differentiable
+    in ``points`` and ``xyz``.  In the model the gradient of mlp1/mlp2/bn1/bn2 (stage 1) and of mlp3/mlp4 (stage 2)
+    flows ONLY through this function (model5_b.py:449-461)."""
+
+    @staticmethod
+    def forward(ctx, xyz, feat, S, radius, K, returnfps, knn):
+        new_xyz, new_points, grouped_xyz, fps_idx, idx = _sample_and_group_forward(S, radius, K, xyz, feat, returnfps, knn)
+        ctx.save_for_backward(idx, fps_idx)
+        ctx.shape = (xyz.shape[1], feat.shape[-1] if feat is not None else 0, returnfps)
+        ctx.mark_non_differentiable(fps_idx)
+        if returnfps:
+            return new_xyz, new_points, grouped_xyz, fps_idx
+        return new_xyz, new_points, fps_idx
+
+    @staticmethod
+    def backward(ctx, g_new_xyz, g_new_points, *rest):
+        idx, fps_idx = ctx.saved_tensors
+        N, D, returnfps = ctx.shape
+        B, S, K = idx.shape
+        dev = idx.device
+        g_grouped = rest[0] if returnfps else None
+        need_xyz, need_feat = ctx.needs_input_grad[0], ctx.needs_input_grad[1] and D > 0
+        d_xyz = d_feat = None
+        gp = g_new_points.contiguous().float() if g_new_points is not None else None
+        if need_feat and gp is not None:
+            d_feat = torch.zeros(B, N, D, device=dev, dtype=torch.float32)
+            _scatter_rows(gp.reshape(B, S * K, 3 + D), 3, D, idx, N, d_feat)
+        elif need_feat:
+            d_feat = torch.zeros(B, N, D, device=dev, dtype=torch.float32)
+        if need_xyz:
+            d_xyz = torch.zeros(B, N, 3, device=dev, dtype=torch.float32)
+            d_centre = torch.zeros(B, S, 3, device=dev, dtype=torch.float32)
+            if gp is not None:
+                _scatter_rows(gp.reshape(B, S * K, 3 + D), 0, 3, idx, N, d_xyz)            # through xyz[idx]
+                d_centre -= gp[..., :3].sum(dim=2)                                          # - sum_k through new_xyz
+            if g_new_xyz is not None:
+                d_centre += g_new_xyz.float()
+            _scatter_rows(d_centre, 0, 3, fps_idx, N, d_xyz)                                # new_xyz = xyz[fps_idx]
+            if g_grouped is not None:
+                _scatter_rows(g_grouped.contiguous().float().reshape(B, S * K, 3), 0, 3, idx, N, d_xyz)
+        return d_xyz, d_feat, None, None, None, None, None
+
+
+def sample_and_group(npoint, radius, nsample, xyz, points, returnfps=False, knn=False):
+    """pointnet_util.py:99-136.
+
+    Returns ``new_xyz [B,npoint,3]``, ``new_points [B,npoint,nsample,3+D]`` (xyz-relative first,
+    then features) and, with ``returnfps=True``, also ``grouped_xyz`` and ``fps_idx``.  Differentiable in ``points``
+    and ``xyz`` exactly as the reference's gather / subtract / cat sequence is (the indices are constants).
+    """
+    xyz = _f32c(xyz, "xyz")
+    S, K = int(npoint), int(nsample)
+    feat = _f32c(points, "points") if points is not None else None
+    if _needs_grad(xyz, feat):
+        r = _SampleAndGroup.apply(xyz, feat, S, radius, K, bool(returnfps), bool(knn))
+        return r if returnfps else r[:2]
+    new_xyz, new_points, grouped_xyz, fps_idx, _ = _sample_and_group_forward(S, radius, K, xyz, feat, returnfps, knn)
     if returnfps:
         return new_xyz, new_points, grouped_xyz, fps_idx
     return new_xyz, new_points
@@ -163,6 +258,10 @@ def sample_and_group_all(xyz, points):
 def group_mlp_maxpool(xyz, points, new_xyz, idx, w1, b1, w2, b2, precision=_lib.PZ_PREC_FP32):
     """Fused form of ``sample_and_group``'s grouping + ``relu(mlp_b(relu(mlp_a(.)))).max(-2)``
     (model5_b.py:449-454): never materialises [B,S,K,3+D].  Returns [B,S,C2]."""
+    if _needs_grad(xyz, points, new_xyz, w1, b1, w2, b2):
+        raise RuntimeError("group_mlp_maxpool is the fused INFERENCE op and records no autograd graph: call it under "
+                           "torch.no_grad() / with detached tensors, or use sample_and_group (differentiable) followed by "
+                           "the layers; the train-mode forward/backward of the model lives in TouchedRegraster.training_step")
     xyz, points, new_xyz = _f32c(xyz, "xyz"), _f32c(points, "points"), _f32c(new_xyz, "new_xyz")
     idx = _i64c(idx, "idx")
     w1, b1, w2, b2 = (_f32c(t, "weight") for t in (w1, b1, w2, b2))

@@ -205,6 +205,34 @@ class Trainer:
         self._pending, self._reduced = [], set()
         self.dev = self.flat.params.device
         self._buf: Dict[str, torch.Tensor] = {}
+        self.sync_replicas()
+
+    def sync_replicas(self, src: int = 0):
+        """What DistributedDataParallel does at construction (the reference trains under Lightning DDP): rank ``src``'s
+        parameters, BatchNorm buffers and optimizer state become every rank's, so replicas that were built with
+        unseeded initialisation -- or of which only one loaded a checkpoint -- cannot silently diverge.  Called by the
+        constructor and by :meth:`load_state_dict`; a no-op outside a process group."""
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return
+        f = self.flat
+        meta = torch.tensor([float(self.step_count), self.lr0], device=self.dev, dtype=torch.float64)
+        dist.broadcast(meta, src)
+        self.step_count, self.lr0 = int(meta[0].item()), float(meta[1].item())
+        for t in (f.params, f.exp_avg, f.exp_avg_sq):
+            dist.broadcast(t, src)
+        for buf in self.model.buffers():          # BN running statistics and num_batches_tracked
+            dist.broadcast(buf, src)
+        for p in self.model.parameters():         # parameters outside the flat buffer (unused decoders, dt)
+            if id(p) not in f.grad_of:
+                dist.broadcast(p.data, src)
+        self._invalidate_inference_state()
+
+    def _invalidate_inference_state(self):
+        """Parameters were written behind torch's back (no _version bump): drop what the inference path derived from
+        them -- the weight packs inside its workspaces and the captured CUDA graphs."""
+        for ws in getattr(self.model, "_ws", {}).values():
+            ws.pack_key = None
+        getattr(self.model, "_graphs", {}).clear()
 
     # -------------------------------------------------------------------------------------------- scratch
     def buf(self, name, *shape, dtype=torch.float32):
@@ -712,10 +740,7 @@ class Trainer:
         with torch.cuda.device(self.dev):
             _lib.call("pz_adam_step", _p(f.params), _p(f.grads), _p(f.exp_avg), _p(f.exp_avg_sq), f.n, lr, 0.9, 0.999, 1e-8,
                       self.step_count, 1.0 / world, _st())
-        # the kernel wrote the parameters behind torch's back: drop the inference path's derived state (bf16 weight
-        # packs keyed on tensor versions, captured CUDA graphs)
-        for attr in ("_pack_keys", "_graphs"):
-            getattr(self.model, attr, {}).clear()
+        self._invalidate_inference_state()
         return lr
 
     # -------------------------------------------------------------------------------------------- checkpoint / resume
@@ -732,6 +757,7 @@ class Trainer:
         self.lr0 = float(sd["lr0"])
         self.flat.exp_avg.copy_(sd["exp_avg"])
         self.flat.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        self.sync_replicas()
 
     def training_step(self, batch, starts=None, pretrain: bool = False) -> Dict[str, float]:
         terms = self.forward_backward_pretrain(batch, starts) if pretrain else self.forward_backward(batch, starts)

@@ -42,10 +42,10 @@ def main():
         for _ in range(3):
             model.predict5(batch, 0)
         torch.cuda.synchronize()
-        _lib.call("pz_profile_attention_timeline", tl.data_ptr())
+        _lib.call("pz_profile_attention_timeline", tl.data_ptr(), tl.numel())
         model.predict5(batch, 0)
         torch.cuda.synchronize()
-        _lib.call("pz_profile_attention_timeline", None)
+        _lib.call("pz_profile_attention_timeline", None, 0)
         t = tl.cpu().tolist()
         report(t, 128, None)
         report_gather(t)
@@ -77,10 +77,10 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     ms_call = e0.elapsed_time(e1) / a.iters
-    _lib.call("pz_profile_attention_timeline", tl.data_ptr())
+    _lib.call("pz_profile_attention_timeline", tl.data_ptr(), tl.numel())
     run()
     torch.cuda.synchronize()
-    _lib.call("pz_profile_attention_timeline", None)
+    _lib.call("pz_profile_attention_timeline", None, 0)
     report(tl.cpu().tolist(), B, ms_call)
 
 

@@ -90,3 +90,44 @@ def test_gradient_buckets_all_reduce_world2_gloo():
         assert p.exitcode == 0
     want = (torch.arange(1000, dtype=torch.float32) * 3).tolist()
     assert res[0] == want and res[1] == want
+
+
+def _sync_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import types
+        from puzzlenet_b200.model5_b import TouchedRegraster
+        from puzzlenet_b200.training import Trainer
+        torch.manual_seed(100 + rank)                  # every rank draws DIFFERENT initial weights
+        model = TouchedRegraster(types.SimpleNamespace(dataset="vase"))
+        with torch.no_grad():
+            model.Encoder.bn1.running_mean.fill_(float(rank + 1))
+        tr = Trainer(model)                            # broadcasts rank 0's parameters / buffers / Adam state
+        first = (float(model.Encoder.mlp3.weight.double().sum()), float(model.dt.sum()),
+                 float(model.Encoder.bn1.running_mean.sum()), float(tr.flat.params.double().sum()))
+        # resume where only rank 0 holds the checkpoint's optimizer state
+        sd = tr.state_dict()
+        if rank == 0:
+            sd["step"], sd["exp_avg"] = 7, torch.full_like(sd["exp_avg"], 0.5)
+        tr.load_state_dict(sd)
+        q.put((rank, first, tr.step_count, float(tr.flat.exp_avg.double().sum())))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_trainer_broadcasts_replica_state_world2_gloo():
+    """Trainer construction and load_state_dict leave every rank with rank 0's parameters, BN buffers and Adam state
+    (what Lightning DDP does for the reference); ranks start from different seeds here."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 25500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_sync_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = {r[0]: r[1:] for r in (q.get(timeout=300) for _ in procs)}
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0] == res[1]
+    assert res[0][1] == 7 and res[0][0][2] == 1024.0       # step from rank 0, running_mean = rank 0's fill (1.0 * 1024)

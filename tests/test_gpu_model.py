@@ -242,17 +242,31 @@ def test_attention_timeline_hook(bf16_model):
     bf16_model.predict5(batch, 0)
     torch.cuda.synchronize()
     assert int(tl.abs().sum()) == 0
-    _lib.call("pz_profile_attention_timeline", tl.data_ptr())
+    _lib.call("pz_profile_attention_timeline", tl.data_ptr(), tl.numel())
     try:
         bf16_model.predict5(batch, 0)
         torch.cuda.synchronize()
     finally:
-        _lib.call("pz_profile_attention_timeline", None)
+        _lib.call("pz_profile_attention_timeline", None, 0)
     t = tl.cpu().tolist()
     order = [15, 0, 2, 3, 4, 5, 6, 7, 10, 11, 12, 13, 17, 14]     # entry, start, q|k ... out stored (epilogue thread 0)
     stamps = [t[i] for i in order]
     assert all(b > a for a, b in zip(stamps, stamps[1:])), stamps
     assert t[64 + 1] > t[64] > 0                                   # %globaltimer at entry / exit of CTA 0
+    assert t[1024] > 0                                             # the stage-1 gather GEMM stamps slots 1024..1455
+    # a buffer of exactly the documented minimum (64 + 2 * clouds, B = 2 -> 4 clouds): the attention stamps land, the
+    # gather GEMM's slots 1024.. are out of range and must be skipped -- nothing may be written behind the buffer
+    n = 64 + 2 * 4
+    guard = torch.zeros(n + 4096, device=DEV, dtype=torch.int64)
+    _lib.call("pz_profile_attention_timeline", guard.data_ptr(), n)
+    try:
+        bf16_model.predict5(batch, 0)
+        torch.cuda.synchronize()
+    finally:
+        _lib.call("pz_profile_attention_timeline", None, 0)
+    assert int(guard[15]) > 0 and int(guard[n:].abs().sum()) == 0
+    with pytest.raises(Exception):
+        _lib.call("pz_profile_attention_timeline", guard.data_ptr(), 8)
 
 
 @pytest.mark.parametrize("B", [2, 3])
