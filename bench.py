@@ -295,7 +295,7 @@ def run_gpu_arm(args):
 
     # ---- the other precision of BASELINE configs[1] ("fp32 and bf16"), same protocol, fewer steps
     other = None
-    other_prec = "fp32" if args.precision == "bf16" else "bf16"
+    other_prec = "fp32" if args.precision != "fp32" else "bf16"
     if not args.single_precision:
         model.precision = other_prec
         k2 = min(args.steps, 20)
@@ -485,7 +485,8 @@ def run_gpu_arm(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": value_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
+        "dtype": {"fp32": "f32", "bf16": "bf16", "split": "f16x3 (fp16 hi/lo operands, 3 MMAs per product, fp32 accumulate)"}[args.precision],
+        "data": "synthetic",
         "config": {"workload": "predict5 fwd (need=False, eval), B=64 pairs x 1024 pts per GPU (BASELINE configs[1])",
                    "pairs_per_gpu": B, "points": N_POINTS, "precision": args.precision, "parallelism": f"dp{world} (pairs sharded, no forward collective)",
                    "l2": "inputs larger than L2: 128 rotating device-resident batches (201 MB) -> static graph inputs; "
@@ -543,7 +544,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("PZ_PRECISION", "bf16"), choices=["fp32", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("PZ_PRECISION", "bf16"), choices=["fp32", "bf16", "split"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--single-precision", action="store_true", help="skip the short run of the other precision")
     ap.add_argument("--pipes", type=int, default=4, help="CUDA streams the e2e leg alternates batches over")

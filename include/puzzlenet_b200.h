@@ -39,6 +39,8 @@ typedef void* pz_stream_t; /* cudaStream_t */
 
 #define PZ_PREC_FP32 0 /* fp32 CUDA-core math, matches the reference to ~1e-6 rel */
 #define PZ_PREC_BF16 1 /* bf16 operands, fp32 accumulate on tcgen05 tensor cores */
+#define PZ_PREC_SPLIT 2 /* every operand as an fp16 hi/lo pair, three tcgen05 MMAs per product (hi*hi + hi*lo + lo*hi),
+                         * fp32 accumulate: the tensor-core path that meets the fp32 tolerances (1e-4, 0.01 deg) */
 
 #define PZ_ABI_VERSION 5
 

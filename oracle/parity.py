@@ -19,11 +19,14 @@ import torch
 from . import puzzle_oracle as po
 
 BOUNDS = {
-    # precision: (feature/logit bound on rel and rel_elem, rotation bound [deg], translation bound)
-    "fp32": (1e-4, 0.01, 1e-4),
-    "split": (1e-4, 0.01, 1e-4),
-    "bf16": (2e-2, None, None),        # north_star bounds the bf16 path's features only; its pose error is REPORTED
+    # precision: (bound on rel, bound on rel_elem, rotation bound [deg], translation bound)
+    "fp32": (1e-4, 1e-4, 0.01, 1e-4),
+    "split": (1e-4, 1e-4, 0.01, 1e-4),
+    # north_star bounds the bf16 path's features / logits at 2e-2 and says nothing about its pose; the pose error that
+    # path reaches is held to a looser figure of its own (1.5 deg / 5e-2) so that a regression is still caught
+    "bf16": (2e-2, 2e-2, 1.5, 5e-2),
 }
+POSE_CLAIMED = {"fp32": True, "split": True, "bf16": False}   # which paths claim north_star's 0.01 deg / 1e-4
 
 
 def rel(got, ref) -> float:
@@ -41,9 +44,12 @@ def rel_elem(got, ref) -> float:
 
 def pose_errors(twist_got, twist_ref):
     """(max rotation error [deg], max translation error) of se3.exp(twist) -- se_math/se3.py:57-80 and
-    metrics.py:54-84 (isotropic errors), evaluated with the oracle's own exp on both twists."""
-    g = po.se3_exp(torch.as_tensor(twist_got).detach().cpu().float())
-    r = po.se3_exp(torch.as_tensor(twist_ref).float())
+    metrics.py:54-84 (isotropic errors), evaluated with the oracle's own exp on both twists IN FLOAT64: rotation
+    matrices rounded to fp32 are orthonormal only to ~1e-7, which the trace formula turns into a 0.02-0.05 degree noise
+    floor -- above the 0.01 degree bound being checked.  In float64 the figure is the pose error the twist difference
+    causes, nothing else."""
+    g = po.se3_exp(torch.as_tensor(twist_got).detach().cpu().double())
+    r = po.se3_exp(torch.as_tensor(twist_ref).double())
     return (po.rotation_error_deg(g[:, :3, :3], r[:, :3, :3]).max().item(),
             po.translation_error(g[:, :3, 3], r[:, :3, 3]).max().item())
 
@@ -74,8 +80,6 @@ def oracle_subset(state_dict, fpc, mrpc, starts, idx) -> dict:
 
 
 def within(p: Dict[str, float], precision: str) -> bool:
-    feat, rot, trans = BOUNDS[precision]
-    ok = max(p["rel_out"], p["rel_logits"], p["rel_elem_out"], p["rel_elem_logits"]) < feat
-    if rot is not None:
-        ok = ok and p["rot_deg"] < rot and p["trans"] < trans
-    return bool(ok)
+    feat, feat_elem, rot, trans = BOUNDS[precision]
+    return bool(max(p["rel_out"], p["rel_logits"]) < feat and max(p["rel_elem_out"], p["rel_elem_logits"]) < feat_elem
+                and p["rot_deg"] < rot and p["trans"] < trans)

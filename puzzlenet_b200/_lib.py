@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libpuzzlenet_sm100.so")
 
 PZ_PREC_FP32 = 0
 PZ_PREC_BF16 = 1
+PZ_PREC_SPLIT = 2
 ABI_VERSION = 5
 PZ_SCORE_COLS = 12
 PZ_FLAG_NEED = 1

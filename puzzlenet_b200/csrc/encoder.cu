@@ -9,6 +9,8 @@
 
 #include <functional>
 
+#include <cuda_fp16.h>
+
 #include "pz_common.cuh"
 #include "se3_math.cuh"
 
@@ -523,9 +525,7 @@ static int skinny_linear(const float* A, int lda, const float* W, const float* b
 
 // ----------------------------------------------------- boundary heads (model5_b.py:738-754)
 // MLPLocalPre{Fpc,Rpc}: 64-64-64-64 per point, one thread per point, weights broadcast from smem.
-struct Mlp3W {
-  const float *w0, *b0, *w1, *b1, *w2, *b2;
-};
+using Mlp3W = HeadMlp3;   // (w0, b0, w1, b1, w2, b2); shared with heads_split.cu
 
 // out[k] = act(bias[k] + W[k,:] . in) for one point per thread; W rows broadcast from smem as
 // 128-bit loads, results parked in smem ([k][thread], conflict-free) so that the k loop need not be
@@ -942,6 +942,9 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const PackJobs jobs) 
           __float2bfloat16_rn(v);
     } else if (jb.to_bf16 == 3) {   // low half of a split-bf16 weight: v - bf16(v)
       static_cast<__nv_bfloat16*>(jb.dst)[(size_t)r * jb.ldo + c] = __float2bfloat16_rn(v - __bfloat162float(__float2bfloat16_rn(v)));
+    } else if (jb.to_bf16 == 4 || jb.to_bf16 == 5) {   // split path: fp16 hi plane / lo plane (v - hi)
+      const __half hi = __float2half_rn(v);
+      static_cast<__half*>(jb.dst)[(size_t)r * jb.ldo + c] = jb.to_bf16 == 4 ? hi : __float2half_rn(v - __half2float(hi));
     } else if (jb.to_bf16) static_cast<__nv_bfloat16*>(jb.dst)[(size_t)r * jb.ldo + c] = __float2bfloat16_rn(v);
     else static_cast<float*>(jb.dst)[(size_t)r * jb.ldo + c] = v;
   }
@@ -960,6 +963,18 @@ __global__ void __launch_bounds__(256) centre_proj_kernel(const float* __restric
   Q[e] = __float2bfloat16_rn(fmaf(w[0], c[0], fmaf(w[1], c[1], w[2] * c[2])));
 }
 
+// the same in fp32 for the split path: Q [rows, C1]
+__global__ void __launch_bounds__(256) centre_proj_f32_kernel(const float* __restrict__ centres, const float* w1a,
+                                                              const float* w1b, int ldw1, int rows_per_set, int rows,
+                                                              int C1, float* __restrict__ Q) {
+  const size_t e = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (e >= (size_t)rows * C1) return;
+  const int s = (int)(e / C1), k = (int)(e - (size_t)s * C1);
+  const float* w = (s / rows_per_set == 0 ? w1a : w1b) + (size_t)k * ldw1;
+  const float* c = centres + (size_t)s * 3;
+  Q[e] = fmaf(w[0], c[0], fmaf(w[1], c[1], w[2] * c[2]));
+}
+
 // ======================================================================== orchestration
 static StemW stem_of(const PzEncoderWeights& w) {
   return StemW{w.mlp1_w, w.mlp1_b, w.mlp2_w, w.mlp2_b, w.bn1_w, w.bn1_b, w.bn1_mean, w.bn1_var,
@@ -974,7 +989,7 @@ static bool encoder_weights_ok(const PzEncoderWeights& w) {
 }
 
 struct EncoderScratch {
-  float *xfeat, *F1, *nx1, *f1f, *F2, *nx2, *att_cat, *q, *k, *v, *r, *tailp, *fglob;
+  float *xfeat, *F1, *nx1, *f1f, *F2, *nx2, *att_cat, *q, *k, *v, *r, *tailp, *fglob, *tail_out;
   int *knn1r, *knn2r;
   // bf16 path
   __nv_bfloat16 *xfeat_b, *P1, *f1f_b, *P2, *att_cat_b, *r_b, *wpack, *qk_b, *vT_b, *Q1, *Q2;
@@ -987,6 +1002,12 @@ constexpr size_t WP_W3F = 0, WP_W4 = WP_W3F + 128 * 64, WP_W5F = WP_W4 + 128 * 1
                  WP_ATT = WP_W6 + 256 * 256, WP_ATT_STRIDE = 384 * 256 + 256 * 256, WP_WOUT = WP_ATT + 4 * WP_ATT_STRIDE,
                  WP_ATTIMG = WP_WOUT + 1024 * 1280, WP_STEM = WP_ATTIMG + 4 * ATTN_WIMG_ELEMS,
                  WP_TOTAL = WP_STEM + 2 * 64 * STEM_WS;   // stem: W2 hi, lo as [64, STEM_WS] images
+
+// split path: fp16 planes of ONE encoder (elements per plane): W3f[128,64] W4[128,128] W5f[256,128] W6[256,256]
+// 4 x (Wqk[128,256] Wv[256,256] Wo[256,256]) Wout[1024,1280]; planes at wpack + ((e * 2 + plane) * WS_TOTAL)
+constexpr size_t WS_W3F = 0, WS_W4 = WS_W3F + 128 * 64, WS_W5F = WS_W4 + 128 * 128, WS_W6 = WS_W5F + 256 * 128,
+                 WS_ATT = WS_W6 + 256 * 256, WS_ATT_STRIDE = 128 * 256 + 2 * 256 * 256, WS_WOUT = WS_ATT + 4 * WS_ATT_STRIDE,
+                 WS_TOTAL = WS_WOUT + 1024 * 1280;
 
 static size_t encoder_scratch_layout(int C, Arena& a, EncoderScratch& s) {
   s.xfeat = a.take<float>((size_t)C * NPTS * D0);
@@ -1014,8 +1035,9 @@ static size_t encoder_scratch_layout(int C, Arena& a, EncoderScratch& s) {
   s.qk_b = a.take<__nv_bfloat16>((size_t)C * LATT * 128);
   s.vT_b = a.take<__nv_bfloat16>((size_t)C * LATT * CATT);
   s.r_b = a.take<__nv_bfloat16>((size_t)C * LATT * CATT);
-  s.wpack = a.take<__nv_bfloat16>(2 * WP_TOTAL);
+  s.wpack = a.take<__nv_bfloat16>(2 * WP_TOTAL > 4 * WS_TOTAL ? 2 * WP_TOTAL : 4 * WS_TOTAL);   // bf16 packs OR split planes
   s.bqkv = a.take<float>(2 * 4 * 384);
+  s.tail_out = a.take<float>((size_t)C * LATT * 1024);   // split path: the tail Linear's output when the caller does not want it
   return a.used;
 }
 
@@ -1239,6 +1261,209 @@ static int encoder_forward_bf16(const PzEncoderWeights* w, int E, int B, const f
   return 0;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// split path (PZ_PREC_SPLIT): the bf16 path's dataflow with every tensor-core operand as fp16 hi / lo planes and
+// every product as three MMAs (gemm_split.cu, attention_split.cu) -- the fp32 tolerances at tensor-core speed.
+// P = layer 1 over the source points and Q = W1[:,0:3] c stay fp32 in HBM; the gather GEMM forms relu(P_j - Q_s) in
+// fp32 registers before splitting it.  Scratch is the bf16 / fp32 paths' scratch re-used (the planes of a tensor live
+// in two same-sized buffers that are idle in this precision).
+// ---------------------------------------------------------------------------------------------
+static int encoder_forward_split(const PzEncoderWeights* w, int E, int B, const float* xyz, const int64_t* start1,
+                                 const int64_t* start2, const PzEncoderOutputs& o, EncoderScratch& s, float* fglob_pair,
+                                 const float** xfeat_out, const AfterStem* after_stem, bool reuse_pack, cudaStream_t st) {
+  const int C = E * B;
+  const PzEncoderWeights& wa = w[0];
+  const PzEncoderWeights& wb = w[E - 1];
+  float* xfeat = o.x_feature ? o.x_feature : s.xfeat;
+  float* nx2 = o.x2 ? o.x2 : s.nx2;
+  if (xfeat_out) *xfeat_out = xfeat;
+  typedef __nv_bfloat16 h16;   // raw 16-bit storage; the split kernels read it as fp16
+  // plane pairs (hi, lo) carved out of buffers that are idle in this precision
+  h16* xfeat_h[2] = {s.P1, s.P1 + (size_t)C * NPTS * D0};
+  float* P1 = s.F1;                                      // [C*1024, 128] fp32
+  float* P2 = s.F2;                                      // [C*512, 256] fp32
+  float* Q1 = s.v;                                       // [C*512, 128] fp32
+  float* Q2 = s.r;                                       // [C*256, 256] fp32
+  h16* f1f_h[2] = {s.f1f_b, s.Q1};
+  h16* cat_h[2] = {s.att_cat_b, reinterpret_cast<h16*>(s.att_cat)};   // [C*256, 1280]
+  h16* qk_h[2] = {s.qk_b, reinterpret_cast<h16*>(s.q)};               // [C*256, 128]
+  h16* vT_h[2] = {s.vT_b, s.P2};                                      // [C][256 ch][256 tok]
+  h16* r_h[2] = {s.r_b, s.Q2};                                        // [C*256, 256]
+  float* tail_out = o.out ? o.out : s.tail_out;                       // [C*256, 1024] fp32
+
+  if (!reuse_pack) {
+    PackJobs jobs;
+    int n = 0;
+    auto add = [&](const float* src, int ldi, int rows, int cols, void* dst, int ldo, int mode) {
+      if (n < MAX_PACK_JOBS) jobs.j[n] = PackJob{src, dst, ldi, rows, cols, ldo, mode};
+      ++n;
+    };
+    for (int e = 0; e < E; ++e) {
+      const PzEncoderWeights& we = w[e];
+      for (int pl = 0; pl < 2; ++pl) {
+        h16* wp = s.wpack + (size_t)(e * 2 + pl) * WS_TOTAL;
+        const int mode = 4 + pl;
+        add(we.mlp3_w + 3, 3 + D0, C1A, D0, wp + WS_W3F, D0, mode);
+        add(we.mlp4_w, C1A, C1B, C1A, wp + WS_W4, C1A, mode);
+        add(we.mlp5_w + 3, 3 + C1B, C2A, C1B, wp + WS_W5F, C1B, mode);
+        add(we.mlp6_w, C2A, C2B, C2A, wp + WS_W6, C2A, mode);
+        for (int l = 0; l < 4; ++l) {
+          h16* wl = wp + WS_ATT + (size_t)l * WS_ATT_STRIDE;
+          add(we.q_w[l], CATT, 64, CATT, wl, CATT, mode);
+          add(we.k_w[l], CATT, 64, CATT, wl + 64 * CATT, CATT, mode);
+          add(we.v_w[l], CATT, CATT, CATT, wl + 128 * CATT, CATT, mode);
+          add(we.o_w[l], CATT, CATT, CATT, wl + 384 * CATT, CATT, mode);
+        }
+        add(we.out_w, 1280, 1024, 1280, wp + WS_WOUT, 1280, mode);
+      }
+      for (int l = 0; l < 4; ++l) {
+        float* bq = s.bqkv + ((size_t)e * 4 + l) * 384;
+        add(we.q_b[l], 64, 1, 64, bq, 64, 0);
+        add(we.k_b[l], 64, 1, 64, bq + 64, 64, 0);
+        add(we.v_b[l], CATT, 1, CATT, bq + 128, CATT, 0);
+      }
+    }
+    PZ_REQUIRE(n <= MAX_PACK_JOBS, PZ_ERR_ARG, "encoder: %d weight pack jobs exceed the table", n);
+    jobs.n = n;
+    pack_weights_kernel<<<dim3(64, n), 256, 0, st>>>(jobs);
+    PZ_LAUNCH_CHECK();
+    prof_mark("pack_weights_split", st);
+  }
+  const h16* wp_[2][2] = {{s.wpack, s.wpack + WS_TOTAL},
+                          {s.wpack + (size_t)(E - 1) * 2 * WS_TOTAL, s.wpack + ((size_t)(E - 1) * 2 + 1) * WS_TOTAL}};
+  auto set_w = [&](TcGemm& g, size_t off) {
+    g.W[0] = wp_[0][0] + off; g.Wlo[0] = wp_[0][1] + off; g.W[1] = wp_[1][0] + off; g.Wlo[1] = wp_[1][1] + off;
+  };
+
+  // ---- geometry on the side stream (FPS -> centre projection -> kNN, both stages)
+  SideStream* ss = nullptr;
+  PZ_TRY(side_stream(&ss, st));
+  static const bool env_serial = getenv("PZ_NO_SIDE_STREAM") != nullptr;
+  const bool serial = env_serial || prof_serial();
+  cudaStream_t sg = serial ? st : ss->stream;
+  const int gl = serial ? 0 : 1;
+  PZ_CUDA(cudaEventRecord(ss->fork, st));
+  PZ_CUDA(cudaStreamWaitEvent(sg, ss->fork, 0));
+  prof_mark("_side_begin", sg, gl);
+  PZ_TRY(launch_fps(xyz, C, NPTS, start1, S1, o.fps1, nullptr, s.nx1, sg));
+  prof_mark("fps1", sg, gl);
+  PZ_TRY(launch_knn(s.nx1, xyz, C, S1, NPTS, KNN, o.knn1, s.knn1r, nullptr, sg));
+  prof_mark("knn1", sg, gl);
+  centre_proj_f32_kernel<<<(unsigned)(((size_t)C * S1 * C1A + 255) / 256), 256, 0, sg>>>(s.nx1, wa.mlp3_w, wb.mlp3_w, 3 + D0,
+                                                                                         B * S1, C * S1, C1A, Q1);
+  PZ_LAUNCH_CHECK();
+  PZ_CUDA(cudaEventRecord(ss->join_a, sg));
+  PZ_TRY(launch_fps(s.nx1, C, S1, start2, S2, o.fps2, nullptr, nx2, sg));
+  prof_mark("fps2", sg, gl);
+  PZ_TRY(launch_knn(nx2, s.nx1, C, S2, S1, KNN, o.knn2, s.knn2r, nullptr, sg));
+  prof_mark("knn2", sg, gl);
+  centre_proj_f32_kernel<<<(unsigned)(((size_t)C * S2 * C2A + 255) / 256), 256, 0, sg>>>(nx2, wa.mlp5_w, wb.mlp5_w, 3 + C1B,
+                                                                                         B * S2, C * S2, C2A, Q2);
+  PZ_LAUNCH_CHECK();
+  PZ_CUDA(cudaEventRecord(ss->join_b, sg));
+
+  // ---- feature chain
+  stem_kernel<<<C * NPTS / 128, 128, 0, st>>>(xyz, stem_of(wa), stem_of(wb), B, xfeat, nullptr);
+  PZ_LAUNCH_CHECK();
+  PZ_TRY(launch_split_planes(xfeat, D0, (size_t)C * NPTS, D0, xfeat_h[0], xfeat_h[1], D0, st));
+  prof_mark("stem", st);
+  {
+    TcGemm g;  // P1 = x_feature W3[:,3:]^T + b3 + W3[:,0:3] xyz   (fp32 out)
+    g.X = xfeat_h[0]; g.Xlo = xfeat_h[1]; g.ldx = D0; set_w(g, WS_W3F); g.ldw = D0;
+    g.bias[0] = wa.mlp3_b; g.bias[1] = wb.mlp3_b; g.rows_per_wset = B * NPTS; g.M = C * NPTS; g.Nout = C1A; g.K = D0;
+    g.Yf = P1; g.ldyf = C1A; g.xyz = xyz; g.W1x[0] = wa.mlp3_w; g.W1x[1] = wb.mlp3_w; g.ldw1x = 3 + D0;
+    PZ_TRY(launch_split_rowgemm(g, st));
+    prof_mark("sg1_layer1", st);
+  }
+  if (after_stem) PZ_TRY((*after_stem)(xfeat, nullptr));
+  PZ_CUDA(cudaStreamWaitEvent(st, ss->join_a, 0));
+  prof_mark("_wait_geometry1", st);
+  {
+    TcGemm g;  // f1f = max_k relu(W4 relu(P1[j] - Q1[s]) + b4)
+    g.Xf = P1; g.ldx = C1A; g.Qf = Q1; g.rows = s.knn1r; set_w(g, WS_W4); g.ldw = C1A;
+    g.bias[0] = wa.mlp4_b; g.bias[1] = wb.mlp4_b; g.rows_per_wset = B * S1 * KNN; g.M = C * S1 * KNN; g.Nout = C1B;
+    g.K = C1A; g.epi = 1; g.relu = 1; g.Yf = o.f1f; g.ldyf = C1B; g.Yb = f1f_h[0]; g.Yblo = f1f_h[1]; g.ldyb = C1B;
+    PZ_TRY(launch_split_gather(g, st));
+    prof_mark("sg1_gather_layer2_maxpool", st);
+  }
+  {
+    TcGemm g;  // P2 = f1f W5[:,3:]^T + b5 + W5[:,0:3] x1
+    g.X = f1f_h[0]; g.Xlo = f1f_h[1]; g.ldx = C1B; set_w(g, WS_W5F); g.ldw = C1B;
+    g.bias[0] = wa.mlp5_b; g.bias[1] = wb.mlp5_b; g.rows_per_wset = B * S1; g.M = C * S1; g.Nout = C2A; g.K = C1B;
+    g.Yf = P2; g.ldyf = C2A; g.xyz = s.nx1; g.W1x[0] = wa.mlp5_w; g.W1x[1] = wb.mlp5_w; g.ldw1x = 3 + C1B;
+    PZ_TRY(launch_split_rowgemm(g, st));
+    prof_mark("sg2_layer1", st);
+  }
+  PZ_CUDA(cudaStreamWaitEvent(st, ss->join_b, 0));
+  prof_mark("_wait_geometry2", st);
+  float* cat_f = o.att_cat;
+  {
+    TcGemm g;
+    g.Xf = P2; g.ldx = C2A; g.Qf = Q2; g.rows = s.knn2r; set_w(g, WS_W6); g.ldw = C2A;
+    g.bias[0] = wa.mlp6_b; g.bias[1] = wb.mlp6_b; g.rows_per_wset = B * S2 * KNN; g.M = C * S2 * KNN; g.Nout = C2B;
+    g.K = C2A; g.epi = 1; g.relu = 1; g.Yb = cat_h[0] + 4 * CATT; g.Yblo = cat_h[1] + 4 * CATT; g.ldyb = 1280;
+    if (cat_f) { g.Yf = cat_f + 4 * CATT; g.ldyf = 1280; }
+    else if (o.f2f) { g.Yf = o.f2f; g.ldyf = CATT; }
+    PZ_TRY(launch_split_gather(g, st));
+    prof_mark("sg2_gather_layer2_maxpool", st);
+  }
+  if (o.f2f && cat_f)
+    PZ_CUDA(cudaMemcpy2DAsync(o.f2f, CATT * sizeof(float), cat_f + 4 * CATT, 1280 * sizeof(float), CATT * sizeof(float),
+                              (size_t)C * LATT, cudaMemcpyDeviceToDevice, st));
+
+  // ---- 4 x offset attention
+  const int rows = C * LATT;
+  for (int l = 0; l < 4; ++l) {
+    const size_t xoff = l == 0 ? 4 * CATT : (size_t)(l - 1) * CATT;
+    const size_t wl = WS_ATT + (size_t)l * WS_ATT_STRIDE;
+    TcGemm gq;  // [q | k] = x Wqk^T + b
+    gq.X = cat_h[0] + xoff; gq.Xlo = cat_h[1] + xoff; gq.ldx = 1280; set_w(gq, wl); gq.ldw = CATT;
+    gq.bias[0] = s.bqkv + (size_t)l * 384; gq.bias[1] = s.bqkv + ((size_t)(E - 1) * 4 + l) * 384;
+    gq.rows_per_wset = B * LATT; gq.M = rows; gq.Nout = 128; gq.K = CATT; gq.Yb = qk_h[0]; gq.Yblo = qk_h[1]; gq.ldyb = 128;
+    PZ_TRY(launch_split_rowgemm(gq, st));
+    TcGemm gv = gq;  // v^T per cloud (K-major operand of P v)
+    set_w(gv, wl + 128 * CATT); gv.bias[0] = gq.bias[0] + 128; gv.bias[1] = gq.bias[1] + 128;
+    gv.Nout = CATT; gv.Yb = nullptr; gv.Yblo = nullptr; gv.YT = vT_h[0]; gv.YTlo = vT_h[1]; gv.t_rows = LATT;
+    PZ_TRY(launch_split_rowgemm(gv, st));
+    prof_mark("attn_qkv_proj", st);
+    AttnSplit ap;
+    ap.qk_hi = qk_h[0]; ap.qk_lo = qk_h[1]; ap.vT_hi = vT_h[0]; ap.vT_lo = vT_h[1];
+    ap.x_hi = cat_h[0] + xoff; ap.x_lo = cat_h[1] + xoff; ap.ldx = 1280; ap.r_hi = r_h[0]; ap.r_lo = r_h[1];
+    ap.attn = o.attention; ap.attn_mode = o.attention ? (l == 0 ? 1 : (l == 3 ? 3 : 2)) : 0;
+    PZ_TRY(launch_attention_split(ap, C, st));
+    prof_mark("attn_softmax_av", st);
+    TcGemm g;  // out = x + relu(Wo r + bo)
+    g.X = r_h[0]; g.Xlo = r_h[1]; g.ldx = CATT; set_w(g, wl + 384 * CATT); g.ldw = CATT;
+    g.bias[0] = wa.o_b[l]; g.bias[1] = wb.o_b[l]; g.rows_per_wset = B * LATT; g.M = rows; g.Nout = CATT; g.K = CATT;
+    g.relu = 1; g.Rb = cat_h[0] + xoff; g.Rblo = cat_h[1] + xoff; g.ldrb = 1280;
+    g.Yb = cat_h[0] + (size_t)l * CATT; g.Yblo = cat_h[1] + (size_t)l * CATT; g.ldyb = 1280;
+    if (cat_f) { g.Yf = cat_f + (size_t)l * CATT; g.ldyf = 1280; }
+    PZ_TRY(launch_split_rowgemm(g, st));
+    prof_mark("attn_out_proj", st);
+  }
+  // ---- tail: Linear(1280, 1024), then the max over the 256 points of a cloud
+  {
+    float* fg = o.f_global ? o.f_global : s.fglob;
+    TcGemm g;
+    g.X = cat_h[0]; g.Xlo = cat_h[1]; g.ldx = 1280; set_w(g, WS_WOUT); g.ldw = 1280;
+    g.bias[0] = wa.out_b; g.bias[1] = wb.out_b; g.rows_per_wset = B * LATT; g.M = rows; g.Nout = 1024; g.K = 1280;
+    g.Yf = tail_out; g.ldyf = 1024;
+    PZ_TRY(launch_split_rowgemm(g, st));
+    prof_mark("tail_linear", st);
+    rowblock_max_kernel<<<dim3(4, C), 256, 0, st>>>(tail_out, 1024, LATT, 1024, C, C, 0, fg, 1024);
+    PZ_LAUNCH_CHECK();
+    prof_mark("tail_point_max", st);
+    if (fglob_pair)
+      PZ_CUDA(cudaMemcpy2DAsync(fglob_pair, (size_t)E * 1024 * sizeof(float), fg, 1024 * sizeof(float),
+                                1024 * sizeof(float), B, cudaMemcpyDeviceToDevice, st));
+    if (fglob_pair && E == 2)
+      PZ_CUDA(cudaMemcpy2DAsync(fglob_pair + 1024, (size_t)E * 1024 * sizeof(float), fg + (size_t)B * 1024,
+                                1024 * sizeof(float), 1024 * sizeof(float), B, cudaMemcpyDeviceToDevice, st));
+  }
+  return 0;
+}
+
 // fglob_pair: optional [B, E*1024] destination laid out for the pose MLP's concat (model5_b.py:723)
 static int encoder_forward_impl(const PzEncoderWeights* w, int E, int B, const float* xyz, const int64_t* start1,
                                 const int64_t* start2, int precision, const PzEncoderOutputs& o, void* ws,
@@ -1246,7 +1471,8 @@ static int encoder_forward_impl(const PzEncoderWeights* w, int E, int B, const f
                                 bool reuse_pack, cudaStream_t st) {
   PZ_REQUIRE(E == 1 || E == 2, PZ_ERR_ARG, "encoder: E must be 1 or 2 (got %d)", E);
   PZ_REQUIRE(B >= 1, PZ_ERR_ARG, "encoder: B must be >= 1");
-  PZ_REQUIRE(precision == PZ_PREC_FP32 || precision == PZ_PREC_BF16, PZ_ERR_ARG, "encoder: unknown precision %d", precision);
+  PZ_REQUIRE(precision == PZ_PREC_FP32 || precision == PZ_PREC_BF16 || precision == PZ_PREC_SPLIT, PZ_ERR_ARG,
+             "encoder: unknown precision %d", precision);
   for (int e = 0; e < E; ++e)
     PZ_REQUIRE(encoder_weights_ok(w[e]), PZ_ERR_ARG, "encoder: weight set %d has a null pointer", e);
   const int C = E * B;
@@ -1256,6 +1482,8 @@ static int encoder_forward_impl(const PzEncoderWeights* w, int E, int B, const f
   PZ_REQUIRE(ws && arena.ok(), PZ_ERR_WORKSPACE, "encoder: workspace %zu B < required %zu B", ws_bytes, arena.used);
   if (precision == PZ_PREC_BF16)
     return encoder_forward_bf16(w, E, B, xyz, start1, start2, o, s, fglob_pair, xfeat_out, after_stem, reuse_pack, st);
+  if (precision == PZ_PREC_SPLIT)
+    return encoder_forward_split(w, E, B, xyz, start1, start2, o, s, fglob_pair, xfeat_out, after_stem, reuse_pack, st);
   const PzEncoderWeights& wa = w[0];
   const PzEncoderWeights& wb = w[E - 1];
   float* xfeat = o.x_feature ? o.x_feature : s.xfeat;
@@ -1398,7 +1626,7 @@ extern "C" int pz_encoder_forward(const PzEncoderWeights* weights_host, int E, i
 namespace {
 struct PredictScratch {
   float *xyz, *fpair, *h0, *h1, *partial, *local, *gmax, *gbias, *tilemax;
-  __nv_bfloat16 *ha, *himg;
+  __nv_bfloat16 *ha, *himg, *himg_split;
   int64_t *st1, *st2;
   void* enc;
   size_t enc_bytes, partial_floats;
@@ -1418,6 +1646,7 @@ size_t predict_layout(int B, Arena& a, PredictScratch& s) {
   s.tilemax = a.take<float>((size_t)2 * B * 8 * 128);
   s.ha = a.take<__nv_bfloat16>((size_t)2 * B * NPTS * 64);
   s.himg = a.take<__nv_bfloat16>(2 * HEAD_IMG_SET);
+  s.himg_split = a.take<__nv_bfloat16>(2 * HEAD_SPLIT_IMG_SET);
   s.enc_bytes = pz_encoder_workspace_bytes(2, B);
   s.enc = a.take<char>(s.enc_bytes);
   return a.used;
@@ -1486,7 +1715,16 @@ extern "C" int pz_predict5(const PzEncoderWeights* enc_host, const PzHeadWeights
   const int P = 2 * B * NPTS;
 
   // boundary heads (model5_b.py:738-754): they only need x_feature, so the encoder runs them right after its stem
+  static const bool old_bf16_heads = getenv("PZ_HEADS_BF16") && getenv("PZ_HEADS_BF16")[0] == '1';   // A/B hook
   AfterStem heads_fn = [&](const float* xfeat, const __nv_bfloat16* xfeat_b) -> int {
+    if (precision == PZ_PREC_SPLIT || (precision == PZ_PREC_BF16 && !old_bf16_heads)) {
+      // split-fp16 chained-MMA heads on the fp32 x_feature (heads_split.cu): logits at fp32 tolerance in both
+      // tensor-core precisions (the bf16 path's stem is a split product too, so its x_feature is fp32-accurate)
+      PZ_TRY(launch_heads_split(xfeat, pre_f, pre_r, seg_f, seg_r, B, reuse_pack, s.himg_split, s.local, s.tilemax, de_fpcb,
+                                de_mrpcb, st));
+      prof_mark("boundary_heads", st);
+      return 0;
+    }
     if (precision == PZ_PREC_BF16) {
       // two chained-MMA kernels (activations stay in registers between layers): the three local layers + per-CTA
       // column maxima, then the segmentation head with the mrpc cloud's global feature folded into a per-cloud bias
@@ -1590,7 +1828,11 @@ extern "C" size_t pz_offset_attention_workspace_bytes(int B, int L, int C) {
   // fp32 path: q, k, v, r;  bf16 path (L == 256): x and out as bf16, one layer's weight tile images, the q|k|v bias
   const size_t fp32_path = align_up(rows * (C / 4) * sizeof(float), 256) * 2 + align_up(rows * C * sizeof(float), 256) * 2;
   const size_t bf16_path = align_up(rows * C * 2, 256) * 2 + align_up(ATTN_WIMG_ELEMS * 2, 256) + align_up(384 * 4, 256);
-  return (fp32_path > bf16_path ? fp32_path : bf16_path) + 256;
+  // split path: planes of x, q|k, v^T, r, the four weights, the q|k|v bias
+  const size_t split_path = align_up(rows * C * 2, 256) * 6 + align_up(rows * 128 * 2, 256) * 2 + align_up((size_t)640 * C * 2, 256) * 2 +
+                            align_up(384 * 4, 256);
+  const size_t m = fp32_path > bf16_path ? fp32_path : bf16_path;
+  return (m > split_path ? m : split_path) + 256;
 }
 
 extern "C" int pz_offset_attention(const float* x, const float* Wq, const float* bq, const float* Wk, const float* bk,
@@ -1599,10 +1841,55 @@ extern "C" int pz_offset_attention(const float* x, const float* Wq, const float*
                                    size_t workspace_bytes, pz_stream_t stream) {
   PZ_REQUIRE(x && Wq && bq && Wk && bk && Wv && bv && Wo && bo && out, PZ_ERR_ARG, "pz_offset_attention: null pointer");
   PZ_REQUIRE(B >= 1 && C == 256, PZ_ERR_UNSUPPORTED, "pz_offset_attention: C must be 256 (got %d)", C);
-  PZ_REQUIRE(precision == PZ_PREC_FP32 || precision == PZ_PREC_BF16, PZ_ERR_ARG, "pz_offset_attention: unknown precision %d", precision);
+  PZ_REQUIRE(precision == PZ_PREC_FP32 || precision == PZ_PREC_BF16 || precision == PZ_PREC_SPLIT, PZ_ERR_ARG,
+             "pz_offset_attention: unknown precision %d", precision);
   cudaStream_t st = as_stream(stream);
   Arena a(workspace, workspace_bytes);
   const size_t rows = (size_t)B * L;
+  if (precision == PZ_PREC_SPLIT) {   // the split path's layer: row GEMMs + attention_split_kernel (gemm_split.cu, attention_split.cu)
+    PZ_REQUIRE(L == 256, PZ_ERR_UNSUPPORTED, "pz_offset_attention(split): L must be 256 (got %d)", L);
+    typedef __nv_bfloat16 h16;
+    h16* xh = a.take<h16>(rows * C); h16* xl = a.take<h16>(rows * C);
+    h16* qkh = a.take<h16>(rows * 128); h16* qkl = a.take<h16>(rows * 128);
+    h16* vth = a.take<h16>(rows * C); h16* vtl = a.take<h16>(rows * C);
+    h16* rh = a.take<h16>(rows * C); h16* rl = a.take<h16>(rows * C);
+    h16* wh = a.take<h16>((size_t)640 * C); h16* wl = a.take<h16>((size_t)640 * C);   // rows: q 0-63, k 64-127, v 128-383, o 384-639
+    float* bqkv = a.take<float>(384);
+    PZ_REQUIRE(workspace && a.ok(), PZ_ERR_WORKSPACE, "pz_offset_attention: workspace %zu B < required %zu B",
+               workspace_bytes, a.used);
+    PackJobs jobs;
+    int n = 0;
+    for (int pl = 0; pl < 2; ++pl) {
+      h16* w = pl == 0 ? wh : wl;
+      jobs.j[n++] = PackJob{Wq, w, C, 64, C, C, 4 + pl};
+      jobs.j[n++] = PackJob{Wk, w + 64 * C, C, 64, C, C, 4 + pl};
+      jobs.j[n++] = PackJob{Wv, w + 128 * C, C, C, C, C, 4 + pl};
+      jobs.j[n++] = PackJob{Wo, w + 384 * C, C, C, C, C, 4 + pl};
+    }
+    jobs.j[n++] = PackJob{bq, bqkv, 64, 1, 64, 64, 0};
+    jobs.j[n++] = PackJob{bk, bqkv + 64, 64, 1, 64, 64, 0};
+    jobs.j[n++] = PackJob{bv, bqkv + 128, C, 1, C, C, 0};
+    jobs.n = n;
+    pack_weights_kernel<<<dim3(16, n), 256, 0, st>>>(jobs);
+    PZ_LAUNCH_CHECK();
+    PZ_TRY(launch_split_planes(x, C, rows, C, xh, xl, C, st));
+    TcGemm gq;
+    gq.X = xh; gq.Xlo = xl; gq.ldx = C; gq.W[0] = wh; gq.Wlo[0] = wl; gq.ldw = C; gq.bias[0] = bqkv;
+    gq.M = (int)rows; gq.Nout = 128; gq.K = C; gq.Yb = qkh; gq.Yblo = qkl; gq.ldyb = 128;
+    PZ_TRY(launch_split_rowgemm(gq, st));
+    TcGemm gv = gq;
+    gv.W[0] = wh + 128 * C; gv.Wlo[0] = wl + 128 * C; gv.bias[0] = bqkv + 128; gv.Nout = C; gv.Yb = nullptr; gv.Yblo = nullptr;
+    gv.YT = vth; gv.YTlo = vtl; gv.t_rows = L;
+    PZ_TRY(launch_split_rowgemm(gv, st));
+    AttnSplit ap;
+    ap.qk_hi = qkh; ap.qk_lo = qkl; ap.vT_hi = vth; ap.vT_lo = vtl; ap.x_hi = xh; ap.x_lo = xl; ap.ldx = C; ap.r_hi = rh; ap.r_lo = rl;
+    ap.attn = attention_or_null; ap.attn_mode = attention_or_null ? 1 : 0;
+    PZ_TRY(launch_attention_split(ap, B, st));
+    TcGemm go;
+    go.X = rh; go.Xlo = rl; go.ldx = C; go.W[0] = wh + 384 * C; go.Wlo[0] = wl + 384 * C; go.ldw = C; go.bias[0] = bo;
+    go.M = (int)rows; go.Nout = C; go.K = C; go.relu = 1; go.Rf = x; go.ldrf = C; go.Yf = out; go.ldyf = C;
+    return launch_split_rowgemm(go, st);
+  }
   if (precision == PZ_PREC_BF16) {   // the fused tcgen05 layer kernel predict5 uses (attention_layer_tc.cu)
     PZ_REQUIRE(L == 256, PZ_ERR_UNSUPPORTED, "pz_offset_attention(bf16): L must be 256 (got %d)", L);
     __nv_bfloat16* xb = a.take<__nv_bfloat16>(rows * C);
@@ -1653,7 +1940,12 @@ extern "C" size_t pz_group_mlp_workspace_bytes(int B, int N, int D, int S, int K
   const size_t bf16_path = align_up((size_t)B * N * D * 2, 256) + align_up((size_t)B * N * C1 * 2, 256) +
                            align_up((size_t)B * S * C1 * 2, 256) + align_up((size_t)C1 * D * 2, 256) +
                            align_up((size_t)C2 * C1 * 2, 256);
-  return (fp32_path > bf16_path ? fp32_path : bf16_path) + align_up((size_t)B * S * K * sizeof(int), 256) + 1024;
+  // split path: feat planes, P fp32, Q fp32, W1f planes, W2 planes
+  const size_t split_path = align_up((size_t)B * N * D * 2, 256) * 2 + align_up((size_t)B * N * C1 * 4, 256) +
+                            align_up((size_t)B * S * C1 * 4, 256) + align_up((size_t)C1 * D * 2, 256) * 2 +
+                            align_up((size_t)C2 * C1 * 2, 256) * 2;
+  const size_t m = fp32_path > bf16_path ? fp32_path : bf16_path;
+  return (m > split_path ? m : split_path) + align_up((size_t)B * S * K * sizeof(int), 256) + 1024;
 }
 
 extern "C" int pz_group_mlp_maxpool(const float* xyz, const float* feat, const float* new_xyz, const int64_t* knn_idx,
@@ -1666,11 +1958,49 @@ extern "C" int pz_group_mlp_maxpool(const float* xyz, const float* feat, const f
   PZ_REQUIRE(K == 32, PZ_ERR_UNSUPPORTED, "pz_group_mlp_maxpool: K must be 32 (got %d)", K);
   PZ_REQUIRE(C1 <= 256, PZ_ERR_UNSUPPORTED, "pz_group_mlp_maxpool: C1 must be <= 256 (got %d)", C1);
   PZ_REQUIRE(((size_t)B * S * K) % 128 == 0, PZ_ERR_UNSUPPORTED, "pz_group_mlp_maxpool: B*S must be a multiple of 4");
-  PZ_REQUIRE(precision == PZ_PREC_FP32 || precision == PZ_PREC_BF16, PZ_ERR_ARG, "pz_group_mlp_maxpool: unknown precision %d", precision);
+  PZ_REQUIRE(precision == PZ_PREC_FP32 || precision == PZ_PREC_BF16 || precision == PZ_PREC_SPLIT, PZ_ERR_ARG,
+             "pz_group_mlp_maxpool: unknown precision %d", precision);
   cudaStream_t st = as_stream(stream);
   Arena a(workspace, workspace_bytes);
   const size_t total = (size_t)B * S * K;
   int* rows = a.take<int>(total);
+  if (precision == PZ_PREC_SPLIT) {
+    // split path: P = feat W1[:,3:]^T + b1 + W1[:,0:3] xyz and Q = W1[:,0:3] c in fp32, then the split gather GEMM
+    PZ_REQUIRE(D % 64 == 0 && (C1 == 128 || C1 == 256) && (C2 == 128 || C2 == 256) && ((size_t)B * N) % 128 == 0 &&
+                   total % 256 == 0,
+               PZ_ERR_UNSUPPORTED,
+               "pz_group_mlp_maxpool(split): needs D %% 64 == 0, C1,C2 in {128,256}, B*N %% 128 == 0, B*S %% 8 == 0");
+    typedef __nv_bfloat16 h16;
+    h16* fh = a.take<h16>((size_t)B * N * D); h16* fl = a.take<h16>((size_t)B * N * D);
+    float* P = a.take<float>((size_t)B * N * C1);
+    float* Q = a.take<float>((size_t)B * S * C1);
+    h16* w1h = a.take<h16>((size_t)C1 * D); h16* w1l = a.take<h16>((size_t)C1 * D);
+    h16* w2h = a.take<h16>((size_t)C2 * C1); h16* w2l = a.take<h16>((size_t)C2 * C1);
+    PZ_REQUIRE(workspace && a.ok(), PZ_ERR_WORKSPACE, "pz_group_mlp_maxpool: workspace %zu B < required %zu B",
+               workspace_bytes, a.used);
+    idx64_to_rows32_kernel<<<(int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096), 256, 0, st>>>(
+        knn_idx, total, (size_t)S * K, N, rows);
+    PZ_LAUNCH_CHECK();
+    PackJobs jobs;
+    jobs.j[0] = PackJob{W1 + 3, w1h, 3 + D, C1, D, D, 4};
+    jobs.j[1] = PackJob{W1 + 3, w1l, 3 + D, C1, D, D, 5};
+    jobs.j[2] = PackJob{W2, w2h, C1, C2, C1, C1, 4};
+    jobs.j[3] = PackJob{W2, w2l, C1, C2, C1, C1, 5};
+    jobs.n = 4;
+    pack_weights_kernel<<<dim3(16, 4), 256, 0, st>>>(jobs);
+    PZ_LAUNCH_CHECK();
+    PZ_TRY(launch_split_planes(feat, D, (size_t)B * N, D, fh, fl, D, st));
+    centre_proj_f32_kernel<<<(unsigned)(((size_t)B * S * C1 + 255) / 256), 256, 0, st>>>(new_xyz, W1, W1, 3 + D, B * S, B * S, C1, Q);
+    PZ_LAUNCH_CHECK();
+    TcGemm g1;
+    g1.X = fh; g1.Xlo = fl; g1.ldx = D; g1.W[0] = w1h; g1.Wlo[0] = w1l; g1.ldw = D; g1.bias[0] = b1; g1.M = B * N; g1.Nout = C1; g1.K = D;
+    g1.Yf = P; g1.ldyf = C1; g1.xyz = xyz; g1.W1x[0] = W1; g1.ldw1x = 3 + D;
+    PZ_TRY(launch_split_rowgemm(g1, st));
+    TcGemm g2;
+    g2.Xf = P; g2.ldx = C1; g2.Qf = Q; g2.rows = rows; g2.W[0] = w2h; g2.Wlo[0] = w2l; g2.ldw = C1; g2.bias[0] = b2; g2.M = (int)total;
+    g2.Nout = C2; g2.K = C1; g2.epi = 1; g2.relu = 1; g2.Yf = out; g2.ldyf = C2;
+    return launch_split_gather(g2, st);
+  }
   if (precision == PZ_PREC_BF16) {
     // tensor-core path: P = feat W1[:,3:]^T + b1 + W1[:,0:3] xyz (row GEMM), Q = W1[:,0:3] c, then the gathered GEMM
     PZ_REQUIRE(D % 64 == 0 && (C1 == 128 || C1 == 256) && (C2 == 128 || C2 == 256) && ((size_t)B * N) % 128 == 0 &&

@@ -151,8 +151,40 @@ struct TcGemm {
   const float* xyz = nullptr;                      // epi 0 only: y += W1x[ch,0:3] . xyz[row]  (layer 1 of a grouped MLP)
   const float* W1x[2] = {nullptr, nullptr};
   int ldw1x = 0;
+  // ---- split path (gemm_split.cu): every 16-bit tensor is a pair of fp16 planes, hi (the pointer above) and lo (below),
+  // with the same leading dimension
+  const __nv_bfloat16* Xlo = nullptr;
+  const __nv_bfloat16* Wlo[2] = {nullptr, nullptr};
+  __nv_bfloat16* Yblo = nullptr;
+  const __nv_bfloat16* Rblo = nullptr;
+  __nv_bfloat16* YTlo = nullptr;
+  int t_rows = 0;                                  // split row GEMM: rows per transposed block (YT), e.g. 256 = one cloud
+  const float* Xf = nullptr;                       // split gather: P [*, K] fp32 (row stride ldx)
+  const float* Qf = nullptr;                       // split gather: Q [M/32, K] fp32 = W1x[:, 0:3] . centre
 };
 int launch_tc_gemm(const TcGemm& g, cudaStream_t st);
+// gemm_split.cu -- the same products as three fp16 MMAs (hi*hi + hi*lo + lo*hi), fp32 accumulation (PZ_PREC_SPLIT)
+int launch_split_rowgemm(const TcGemm& g, cudaStream_t st);
+int launch_split_gather(const TcGemm& g, cudaStream_t st);
+int launch_split_planes(const float* in, size_t ldi, size_t rows, int cols, void* hi, void* lo, size_t ldo, cudaStream_t st);
+// attention_split.cu: per cloud  r = x - softmax(q k^T / sqrt(64)) v  with split operands; q|k planes [rows,128],
+// v^T planes [cloud][256 ch][256 tokens], x / r planes (ldx / 256)
+struct AttnSplit {
+  const void *qk_hi = nullptr, *qk_lo = nullptr, *vT_hi = nullptr, *vT_lo = nullptr, *x_hi = nullptr, *x_lo = nullptr;
+  int ldx = 0;
+  void *r_hi = nullptr, *r_lo = nullptr;
+  float* attn = nullptr;
+  int attn_mode = 0;
+};
+int launch_attention_split(const AttnSplit& p, int clouds, cudaStream_t st);
+// heads_split.cu: the boundary heads of predict5 as split-fp16 chained-MMA kernels (used by the split and bf16 paths)
+struct HeadMlp3 {
+  const float *w0, *b0, *w1, *b1, *w2, *b2;
+};
+constexpr size_t HEAD_SPLIT_IMG_SET = (size_t)(2 * 3 * 64 + 2 * (64 + 32)) * 72;   // fp16 elements of one set's weight images
+int launch_heads_split(const float* xfeat, const HeadMlp3& pre_f, const HeadMlp3& pre_r, const HeadMlp3& seg_f,
+                       const HeadMlp3& seg_r, int B, bool reuse_images, void* img, float* local, float* tilemax,
+                       float* de_fpcb, float* de_mrpcb, cudaStream_t st);
 int launch_tc_rowgemm(const TcGemm& g, cudaStream_t st);   // gemm_tc_rows.cu: same struct, row-major store epilogue
 // attention_tc.cu: per cloud  r = x - softmax(q k^T / sqrt(64)) v   on tcgen05 (L == 256, d_k == 64, C == 256)
 int launch_attention_tc(const __nv_bfloat16* qk, const __nv_bfloat16* vT, const __nv_bfloat16* x, int ldx, int clouds,

@@ -43,8 +43,8 @@ try:  # pragma: no cover - depends on the environment
 except Exception:  # pytorch_lightning is not part of this image
     _Base = nn.Module
 
-PRECISIONS = {"fp32": _lib.PZ_PREC_FP32, "bf16": _lib.PZ_PREC_BF16}
-PACKED_PRECISIONS = ("bf16",)     # precisions whose converted weight packs live in the caller's workspace
+PRECISIONS = {"fp32": _lib.PZ_PREC_FP32, "bf16": _lib.PZ_PREC_BF16, "split": _lib.PZ_PREC_SPLIT}
+PACKED_PRECISIONS = ("bf16", "split")     # precisions whose converted weight packs live in the caller's workspace
 
 
 class _Workspace:

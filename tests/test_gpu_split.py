@@ -1,0 +1,98 @@
+"""The split path (PZ_PREC_SPLIT: fp16 hi/lo operand planes, three tcgen05 MMAs per product, fp32 accumulation) block by
+block against the CPU oracle, at the fp32 tolerance of north_star (1e-4 relative; measured ~1e-6).  The kernels:
+split_rowgemm_kernel / split_gather_kernel (gemm_split.cu), attention_split_kernel (attention_split.cu),
+head_*_split_kernel (heads_split.cu).  End to end at B=64: tests/test_gpu_b64_parity.py."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import parity
+from oracle import puzzle_oracle as po
+from puzzlenet_b200.weights import make_batch, synthetic_pairs
+from tests.golden_inputs import FPS_SEED
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TOL = 1e-4
+
+
+@pytest.mark.parametrize("B", [1, 3, 150])
+def test_layer_attention_split(state_dict, B):
+    """q|k and v projections, q k^T, softmax, P v, offset, out-projection + residual: values AND the attention map."""
+    from puzzlenet_b200.model5_b import layerAttention
+    g = torch.Generator().manual_seed(5)
+    layer = layerAttention(None, 256)
+    pre = "Encoder2.atten2."
+    layer.load_state_dict({k[len(pre):]: v for k, v in state_dict.items() if k.startswith(pre)})
+    layer.precision = "split"
+    x = torch.randn(B, 256, 256, generator=g) * 0.5
+    out, a = layer.to(DEV)(x.to(DEV))
+    torch.cuda.synchronize()
+    ro, ra = po.layer_attention(state_dict, pre[:-1], x)
+    errs = dict(out=parity.rel(out, ro), out_elem=parity.rel_elem(out, ro), attn=parity.rel(a, ra))
+    print(f"split attention layer B={B}:", errs)
+    assert max(errs.values()) < TOL, errs
+    np.testing.assert_allclose(a.sum(-1).cpu().numpy(), 1.0, atol=1e-5)
+
+
+@pytest.mark.parametrize("stage", [1, 2])
+def test_group_mlp_maxpool_split(state_dict, stage):
+    """Layer 1 over source points (row GEMM, fp32 P), fp32 Q, gathered relu(P - Q) formed in registers, three-MMA layer 2,
+    max over the 32 neighbours: both stage shapes of the encoder (67->128->128 on 1024 points, 131->256->256 on 512)."""
+    from puzzlenet_b200 import pointnet_util as pu
+    g = torch.Generator().manual_seed(2 + stage)
+    N, D, S = (1024, 64, 128) if stage == 1 else (512, 128, 64)
+    la, lb = ("Encoder.mlp3", "Encoder.mlp4") if stage == 1 else ("Encoder2.mlp5", "Encoder2.mlp6")
+    xyz = torch.rand(2, N, 3, generator=g) - 0.5
+    feat = torch.randn(2, N, D, generator=g)
+    torch.manual_seed(8)
+    nx, npts, _, _, idx = po.sample_and_group(S, 0, 32, xyz, feat, knn=True, return_idx=True)
+    ref = torch.relu(po._lin(state_dict, lb, torch.relu(po._lin(state_dict, la, npts)))).max(-2).values
+    got = pu.group_mlp_maxpool(xyz.to(DEV), feat.to(DEV), nx.to(DEV), idx.to(DEV),
+                               state_dict[la + ".weight"].to(DEV), state_dict[la + ".bias"].to(DEV),
+                               state_dict[lb + ".weight"].to(DEV), state_dict[lb + ".bias"].to(DEV), precision=2)
+    errs = dict(rel=parity.rel(got, ref), elem=parity.rel_elem(got, ref))
+    print(f"split group MLP stage {stage}:", errs)
+    assert got.shape == ref.shape and max(errs.values()) < TOL, errs
+
+
+def test_encoder_split_intermediates(cuda_model, state_dict):
+    fpc, _ = synthetic_pairs(2, seed=64)
+    cuda_model.Encoder.precision = "split"
+    try:
+        torch.manual_seed(FPS_SEED)
+        got = cuda_model.Encoder(fpc.to(DEV), return_intermediates=True)
+        torch.cuda.synchronize()
+    finally:
+        cuda_model.Encoder.precision = "fp32"
+    torch.manual_seed(FPS_SEED)
+    ref = po.encoder_forward(state_dict, "Encoder", fpc)
+    for name in ("fps1", "knn1", "fps2", "knn2"):
+        assert torch.equal(got[name].cpu(), ref[name]), name
+    errs = {n: parity.rel(got[n], ref[n]) for n in ("x_feature", "f1f", "f2f", "attention", "out", "f_global")}
+    errs["att_cat"] = parity.rel(got["att_cat"], torch.cat(ref["att"] + [ref["f2f"]], -1))
+    print("split encoder rel errors:", errs)
+    assert max(errs.values()) < TOL, errs
+
+
+@pytest.mark.parametrize("B", [1, 5])
+def test_predict5_split_vs_oracle(cuda_model, state_dict, B):
+    fpc, mrpc = synthetic_pairs(B, seed=100 + B)
+    cuda_model.precision = "split"
+    try:
+        torch.manual_seed(B)
+        out, _, de_f, de_m = cuda_model.predict5(make_batch(fpc.to(DEV), mrpc.to(DEV)), 0)
+        torch.cuda.synchronize()
+        again = cuda_model.predict5(make_batch(fpc.to(DEV), mrpc.to(DEV)), 0,
+                                    starts=None if False else None)   # second call re-uses the weight planes
+    finally:
+        cuda_model.precision = "fp32"
+    torch.manual_seed(B)
+    ref = po.predict5(state_dict, fpc, mrpc)
+    errs = dict(out=parity.rel(out, ref["out"]), de_f=parity.rel(de_f, ref["de_fpcb"]), de_m=parity.rel(de_m, ref["de_mrpcb"]),
+                de_f_elem=parity.rel_elem(de_f, ref["de_fpcb"]))
+    rot, trans = parity.pose_errors(out, ref["out"])
+    print(f"split predict5 B={B}:", errs, "rotation [deg]", rot, "translation", trans)
+    assert max(errs.values()) < TOL, errs
+    assert rot < 0.01 and trans < 1e-4
+    assert again[0].shape == out.shape
