@@ -28,6 +28,12 @@ import torch
 
 Tensor = torch.Tensor
 
+# bench.py's "stock PyTorch on the same GPU" baseline runs these same functions on CUDA tensors (only the placement of
+# arange / randint / constants follows the input's device; on CPU tensors nothing changes).  The reference additionally
+# calls torch.cuda.empty_cache() five times per sample_and_group; the baseline can switch that on to time the reference
+# as written.
+REFERENCE_EMPTY_CACHE = False
+
 # --------------------------------------------------------------------------
 # point-cloud operators (pointnet_util.py)
 # --------------------------------------------------------------------------
@@ -53,7 +59,7 @@ def index_points(points: Tensor, idx: Tensor) -> Tensor:
     """pointnet_util.py:39-50 -- batched row gather; idx [B,S] or [B,S,K]."""
     b = points.shape[0]
     flat = idx.reshape(b, -1)
-    rows = torch.arange(b).unsqueeze(1)
+    rows = torch.arange(b, device=points.device).unsqueeze(1)
     return points[rows, flat].reshape(*idx.shape, points.shape[-1])
 
 
@@ -70,10 +76,11 @@ def farthest_point_sample(xyz: Tensor, npoint: int, start: Optional[Tensor] = No
     (first maximum wins, as ``torch.max`` does on CPU).
     """
     b, n, _ = xyz.shape
-    far = draw_fps_start(b, n) if start is None else start.clone().long()
-    picked = torch.empty(b, npoint, dtype=torch.long)
-    mind = torch.full((b, n), 1e10, dtype=xyz.dtype)
-    rows = torch.arange(b)
+    dev = xyz.device                      # "cpu" for the oracle proper; a CUDA device only in bench.py's torch-on-GPU baseline
+    far = (draw_fps_start(b, n) if start is None else start.clone().long()).to(dev)
+    picked = torch.empty(b, npoint, dtype=torch.long, device=dev)
+    mind = torch.full((b, n), 1e10, dtype=xyz.dtype, device=dev)
+    rows = torch.arange(b, device=dev)
     for s in range(npoint):
         picked[:, s] = far
         c = xyz[rows, far].unsqueeze(1)
@@ -98,7 +105,7 @@ def query_ball_point(radius: float, nsample: int, xyz: Tensor, new_xyz: Tensor) 
     b, n, _ = xyz.shape
     s = new_xyz.shape[1]
     d2 = square_distance(new_xyz, xyz)
-    cand = torch.arange(n).view(1, 1, n).expand(b, s, n).clone()
+    cand = torch.arange(n, device=xyz.device).view(1, 1, n).expand(b, s, n).clone()
     cand[d2 > radius ** 2] = n
     cand = torch.sort(cand, dim=-1).values[:, :, :nsample]
     first = cand[:, :, :1].expand(-1, -1, nsample)
@@ -111,6 +118,9 @@ def sample_and_group(npoint: int, radius: float, nsample: int, xyz: Tensor, poin
     """pointnet_util.py:99-136 -- FPS, centre gather, kNN / ball query, group, centre, concat."""
     b, n, c = xyz.shape
     fps_idx = farthest_point_sample(xyz, npoint, start)
+    if REFERENCE_EMPTY_CACHE and xyz.is_cuda:     # pointnet_util.py:114,116,122,124,126 (no-ops on the CPU)
+        for _ in range(5):
+            torch.cuda.empty_cache()
     new_xyz = index_points(xyz, fps_idx)
     if knn:
         idx, _ = knn_select(square_distance(new_xyz, xyz), nsample)
