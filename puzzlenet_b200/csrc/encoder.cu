@@ -28,7 +28,8 @@ struct StemW {
 
 __global__ void __launch_bounds__(128) stem_kernel(const float* __restrict__ xyz, StemW wa, StemW wb,
                                                    int clouds_per_set, float* __restrict__ out,
-                                                   __nv_bfloat16* __restrict__ out_b) {
+                                                   __nv_bfloat16* __restrict__ out_b, __half* __restrict__ out_hi,
+                                                   __half* __restrict__ out_lo) {
   __shared__ __align__(16) float w2s[64 * 64];
   __shared__ float w1s[64 * 3], b1s[64], b2s[64];
   const size_t p = (size_t)blockIdx.x * 128 + threadIdx.x;  // global point id
@@ -80,6 +81,16 @@ __global__ void __launch_bounds__(128) stem_kernel(const float* __restrict__ xyz
       __nv_bfloat162 lo = __floats2bfloat162_rn(r[0], r[1]), hi = __floats2bfloat162_rn(r[2], r[3]);
       uint2 pk = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
       *reinterpret_cast<uint2*>(out_b + p * 64 + k0) = pk;
+    }
+    if (out_hi) {   // split path: the fp16 hi / lo planes of x_feature, straight from the registers
+      uint2 ph, pl;
+      const __half2 h0 = __floats2half2_rn(r[0], r[1]), h1 = __floats2half2_rn(r[2], r[3]);
+      const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+      const __half2 l0 = __floats2half2_rn(r[0] - f0.x, r[1] - f0.y), l1 = __floats2half2_rn(r[2] - f1.x, r[3] - f1.y);
+      ph.x = *reinterpret_cast<const uint32_t*>(&h0); ph.y = *reinterpret_cast<const uint32_t*>(&h1);
+      pl.x = *reinterpret_cast<const uint32_t*>(&l0); pl.y = *reinterpret_cast<const uint32_t*>(&l1);
+      *reinterpret_cast<uint2*>(out_hi + p * 64 + k0) = ph;
+      *reinterpret_cast<uint2*>(out_lo + p * 64 + k0) = pl;
     }
   }
 }
@@ -445,50 +456,83 @@ __global__ void __launch_bounds__(256) splitk_finish_kernel(const float* __restr
   y[(size_t)m * ldy + n] = s;
 }
 
-// Y[M,N] = act(X[M,K] W[N,K]^T + b) for skinny M (the pose MLP, model5_b.py:561-571: M = B <= 64 rows per block).
-// One CTA per 8 output columns and 64 rows: thread = (row, K-quarter); X and the 8 weight rows stream through
-// shared memory in 128-wide K chunks; the four K-quarters are summed in a fixed order (deterministic).
-constexpr int SK_COLS = 8, SK_ROWS = 64, SK_KC = 128;
+// Y[M,N] = act(X[M,K] W[N,K]^T + b) for skinny M (the pose MLP, model5_b.py:561-571 / :723-725: M = B <= 64 rows per
+// row block).  One CTA per SK_COLS output columns and 64 rows over the WHOLE K: grid = N / 8 CTAs (128 for the first
+// layer), so every layer is ONE launch with no split-K partials and no finishing pass.  X and the 8 weight rows stream
+// through shared memory in 128-wide K chunks, double-buffered with cp.async (16-byte copies; the next chunk lands while
+// the current one is multiplied).  Thread = (row pair, K-eighth): 2 rows x 8 columns of accumulators, 16 k per chunk;
+// the eight K-eighths are summed in a fixed order (deterministic, fp32).
+constexpr int SK_COLS = 8, SK_ROWS = 64, SK_KC = 128, SK_XLD = SK_KC + 4;   // +4 floats: conflict-free row reads, 16-byte rows
+constexpr size_t SK_SMEM = (size_t)(2 * SK_ROWS * SK_XLD + 2 * SK_COLS * SK_KC) * sizeof(float);
 __global__ void __launch_bounds__(256) skinny_linear_kernel(const float* __restrict__ X, int ldx,
                                                             const float* __restrict__ W, const float* __restrict__ bias,
                                                             int M, int N, int K, int relu, float* __restrict__ Y, int ldy) {
-  __shared__ float xs[SK_ROWS][SK_KC + 1];
-  __shared__ __align__(16) float ws[SK_KC][SK_COLS];
-  __shared__ float red[4][SK_ROWS][SK_COLS];
-  const int tid = threadIdx.x, r = tid & 63, kq = tid >> 6;
+  extern __shared__ __align__(16) float sk_smem[];
+  float* xs = sk_smem;                                   // [2][64][SK_XLD]
+  float* ws = sk_smem + 2 * SK_ROWS * SK_XLD;            // [2][8][128]
+  const int tid = threadIdx.x, r2 = tid & 31, ke = tid >> 5;
   const int n0 = blockIdx.x * SK_COLS, m0 = blockIdx.y * SK_ROWS;
-  float acc[SK_COLS];
+  const int chunks = K / SK_KC;                          // K % 128 == 0 (checked by the launcher)
+  auto issue = [&](int c) {
+    const int k0 = c * SK_KC;
+    float* xd = xs + (c & 1) * SK_ROWS * SK_XLD;
+    float* wd = ws + (c & 1) * SK_COLS * SK_KC;
+    for (int e = tid; e < SK_ROWS * (SK_KC / 4); e += 256) {        // 64 rows x 32 16-byte pieces
+      const int rr = e >> 5, k4 = (e & 31) * 4;
+      const int row = min(m0 + rr, M - 1);                         // rows past M are computed and dropped
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(xd + rr * SK_XLD + k4)),
+                   "l"(X + (size_t)row * ldx + k0 + k4) : "memory");
+    }
+    for (int e = tid; e < SK_COLS * (SK_KC / 4); e += 256) {
+      const int nn = e >> 5, k4 = (e & 31) * 4;
+      const int col = min(n0 + nn, N - 1);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(wd + nn * SK_KC + k4)),
+                   "l"(W + (size_t)col * K + k0 + k4) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  float acc[2][SK_COLS];
 #pragma unroll
-  for (int n = 0; n < SK_COLS; ++n) acc[n] = 0.f;
-  for (int k0 = 0; k0 < K; k0 += SK_KC) {
-    __syncthreads();
-    for (int e = tid; e < SK_ROWS * SK_KC; e += 256) {
-      const int rr = e >> 7, kk = e & 127;
-      xs[rr][kk] = (m0 + rr < M && k0 + kk < K) ? X[(size_t)(m0 + rr) * ldx + k0 + kk] : 0.f;
-    }
-    for (int e = tid; e < SK_COLS * SK_KC; e += 256) {
-      const int nn = e >> 7, kk = e & 127;
-      ws[kk][nn] = (n0 + nn < N && k0 + kk < K) ? W[(size_t)(n0 + nn) * K + k0 + kk] : 0.f;
+  for (int n = 0; n < SK_COLS; ++n) acc[0][n] = acc[1][n] = 0.f;
+  issue(0);
+  for (int c = 0; c < chunks; ++c) {
+    if (c + 1 < chunks) {
+      issue(c + 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
-#pragma unroll 8
-    for (int kk = kq * 32; kk < kq * 32 + 32; ++kk) {
-      const float xv = xs[r][kk];
-      const float4 w0 = *reinterpret_cast<const float4*>(&ws[kk][0]);
-      const float4 w1 = *reinterpret_cast<const float4*>(&ws[kk][4]);
-      acc[0] = fmaf(xv, w0.x, acc[0]); acc[1] = fmaf(xv, w0.y, acc[1]);
-      acc[2] = fmaf(xv, w0.z, acc[2]); acc[3] = fmaf(xv, w0.w, acc[3]);
-      acc[4] = fmaf(xv, w1.x, acc[4]); acc[5] = fmaf(xv, w1.y, acc[5]);
-      acc[6] = fmaf(xv, w1.z, acc[6]); acc[7] = fmaf(xv, w1.w, acc[7]);
+    const float* xa = xs + (c & 1) * SK_ROWS * SK_XLD + r2 * SK_XLD + ke * 16;
+    const float* xb = xa + 32 * SK_XLD;
+    const float* wc = ws + (c & 1) * SK_COLS * SK_KC + ke * 16;
+#pragma unroll
+    for (int k4 = 0; k4 < 16; k4 += 4) {
+      const float4 a4 = *reinterpret_cast<const float4*>(xa + k4), b4 = *reinterpret_cast<const float4*>(xb + k4);
+#pragma unroll
+      for (int n = 0; n < SK_COLS; ++n) {
+        const float4 w4 = *reinterpret_cast<const float4*>(wc + n * SK_KC + k4);
+        acc[0][n] = fmaf(a4.x, w4.x, acc[0][n]); acc[0][n] = fmaf(a4.y, w4.y, acc[0][n]);
+        acc[0][n] = fmaf(a4.z, w4.z, acc[0][n]); acc[0][n] = fmaf(a4.w, w4.w, acc[0][n]);
+        acc[1][n] = fmaf(b4.x, w4.x, acc[1][n]); acc[1][n] = fmaf(b4.y, w4.y, acc[1][n]);
+        acc[1][n] = fmaf(b4.z, w4.z, acc[1][n]); acc[1][n] = fmaf(b4.w, w4.w, acc[1][n]);
+      }
     }
+    __syncthreads();   // the buffer is refilled by the chunk after next
   }
+  float* red = xs;     // [8 k-eighths][64 rows][8 cols] = 16 KB, over the (now idle) X buffers
 #pragma unroll
-  for (int n = 0; n < SK_COLS; ++n) red[kq][r][n] = acc[n];
+  for (int n = 0; n < SK_COLS; ++n) {
+    red[(ke * SK_ROWS + r2) * SK_COLS + n] = acc[0][n];
+    red[(ke * SK_ROWS + r2 + 32) * SK_COLS + n] = acc[1][n];
+  }
   __syncthreads();
   for (int e = tid; e < SK_ROWS * SK_COLS; e += 256) {
     const int rr = e >> 3, nn = e & 7;
     if (m0 + rr < M && n0 + nn < N) {
-      float v = ((red[0][rr][nn] + red[1][rr][nn]) + red[2][rr][nn]) + red[3][rr][nn];
+      float v = 0.f;
+#pragma unroll
+      for (int z = 0; z < 8; ++z) v += red[(z * SK_ROWS + rr) * SK_COLS + nn];
       if (bias) v += bias[n0 + nn];
       if (relu) v = fmaxf(v, 0.f);
       Y[(size_t)(m0 + rr) * ldy + n0 + nn] = v;
@@ -496,31 +540,22 @@ __global__ void __launch_bounds__(256) skinny_linear_kernel(const float* __restr
   }
 }
 
-// Pose-MLP layer: wide layers go through the tiled GEMM with K split over grid.z (16 MB of L2 operand traffic for
-// layer 1 instead of every CTA re-reading all of X); narrow ones (N <= 64) through the one-launch skinny kernel.
+// Pose-MLP layer: one launch of skinny_linear_kernel (K % 128 == 0, 16-byte aligned rows); anything else through the
+// tiled fp32 GEMM.
 static int skinny_linear(const float* A, int lda, const float* W, const float* bias, int M, int N, int K,
                          int relu, float* Y, int ldy, float* partial, size_t partial_floats, cudaStream_t st) {
-  if (N <= 64) {
+  (void)partial; (void)partial_floats;
+  if (K % SK_KC == 0 && lda % 4 == 0 && (((uintptr_t)A | (uintptr_t)W) & 15) == 0) {
+    PZ_CUDA(cudaFuncSetAttribute(skinny_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SK_SMEM));
     dim3 grid((N + SK_COLS - 1) / SK_COLS, (M + SK_ROWS - 1) / SK_ROWS);
-    skinny_linear_kernel<<<grid, 256, 0, st>>>(A, lda, W, bias, M, N, K, relu, Y, ldy);
+    skinny_linear_kernel<<<grid, 256, SK_SMEM, st>>>(A, lda, W, bias, M, N, K, relu, Y, ldy);
     PZ_LAUNCH_CHECK();
     return 0;
   }
-  int splits = 1;
-  while (splits < 16 && K / (splits * 2) >= 64 && ((N + 127) / 128) * ((M + 127) / 128) * splits * 2 <= kNumSMs) splits *= 2;
-  if (splits == 1 || (size_t)splits * M * N > partial_floats) {
-    GemmF32 g;
-    g.A = A; g.lda = lda; g.W[0] = W; g.bias[0] = bias; g.ldw = K; g.Y = Y; g.ldy = ldy;
-    g.M = M; g.N = N; g.K = K; g.relu = relu;
-    return launch_gemm_f32(g, st);
-  }
-  GemmF32 g;  // grid.z = split index; raw partial sums, bias/relu applied by the finish kernel
-  g.A = A; g.lda = lda; g.W[0] = W; g.ldw = K; g.Y = partial; g.ldy = N; g.M = M; g.N = N; g.K = K;
-  g.ksplit = K / splits;  // K is a power-of-two multiple of 64 on this path
-  PZ_TRY(launch_gemm_f32(g, st));
-  splitk_finish_kernel<<<(M * N + 255) / 256, 256, 0, st>>>(partial, splits, M, N, bias, relu, Y, ldy);
-  PZ_LAUNCH_CHECK();
-  return 0;
+  GemmF32 g;
+  g.A = A; g.lda = lda; g.W[0] = W; g.bias[0] = bias; g.ldw = K; g.Y = Y; g.ldy = ldy;
+  g.M = M; g.N = N; g.K = K; g.relu = relu;
+  return launch_gemm_f32(g, st);
 }
 
 // ----------------------------------------------------- boundary heads (model5_b.py:738-754)
@@ -989,7 +1024,7 @@ static bool encoder_weights_ok(const PzEncoderWeights& w) {
 }
 
 struct EncoderScratch {
-  float *xfeat, *F1, *nx1, *f1f, *F2, *nx2, *att_cat, *q, *k, *v, *r, *tailp, *fglob, *tail_out;
+  float *xfeat, *F1, *nx1, *f1f, *F2, *nx2, *att_cat, *q, *k, *v, *r, *tailp, *fglob;
   int *knn1r, *knn2r;
   // bf16 path
   __nv_bfloat16 *xfeat_b, *P1, *f1f_b, *P2, *att_cat_b, *r_b, *wpack, *qk_b, *vT_b, *Q1, *Q2;
@@ -1037,7 +1072,6 @@ static size_t encoder_scratch_layout(int C, Arena& a, EncoderScratch& s) {
   s.r_b = a.take<__nv_bfloat16>((size_t)C * LATT * CATT);
   s.wpack = a.take<__nv_bfloat16>(2 * WP_TOTAL > 4 * WS_TOTAL ? 2 * WP_TOTAL : 4 * WS_TOTAL);   // bf16 packs OR split planes
   s.bqkv = a.take<float>(2 * 4 * 384);
-  s.tail_out = a.take<float>((size_t)C * LATT * 1024);   // split path: the tail Linear's output when the caller does not want it
   return a.used;
 }
 
@@ -1130,7 +1164,7 @@ static int encoder_forward_bf16(const PzEncoderWeights* w, int E, int B, const f
   PZ_CUDA(cudaEventRecord(ss->join_b, sg));
 
   static const bool stem_fp32 = getenv("PZ_STEM_FP32") && getenv("PZ_STEM_FP32")[0] == '1';   // A/B hook
-  if (stem_fp32) stem_kernel<<<C * NPTS / 128, 128, 0, st>>>(xyz, stem_of(wa), stem_of(wb), B, xfeat, s.xfeat_b);
+  if (stem_fp32) stem_kernel<<<C * NPTS / 128, 128, 0, st>>>(xyz, stem_of(wa), stem_of(wb), B, xfeat, s.xfeat_b, nullptr, nullptr);
   else {
     PZ_CUDA(cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STEM_TC_SMEM));
     stem_tc_kernel<<<C * NPTS / (128 * head_reps()), 128, STEM_TC_SMEM, st>>>(xyz, stem_of(wa), stem_of(wb), wpa + WP_STEM,
@@ -1290,7 +1324,6 @@ static int encoder_forward_split(const PzEncoderWeights* w, int E, int B, const 
   h16* qk_h[2] = {s.qk_b, reinterpret_cast<h16*>(s.q)};               // [C*256, 128]
   h16* vT_h[2] = {s.vT_b, s.P2};                                      // [C][256 ch][256 tok]
   h16* r_h[2] = {s.r_b, s.Q2};                                        // [C*256, 256]
-  float* tail_out = o.out ? o.out : s.tail_out;                       // [C*256, 1024] fp32
 
   if (!reuse_pack) {
     PackJobs jobs;
@@ -1364,9 +1397,12 @@ static int encoder_forward_split(const PzEncoderWeights* w, int E, int B, const 
   PZ_CUDA(cudaEventRecord(ss->join_b, sg));
 
   // ---- feature chain
-  stem_kernel<<<C * NPTS / 128, 128, 0, st>>>(xyz, stem_of(wa), stem_of(wb), B, xfeat, nullptr);
+  static const bool stem_planes = getenv("PZ_STEM_PLANES") && getenv("PZ_STEM_PLANES")[0] == '1';   // A/B hook
+  stem_kernel<<<C * NPTS / 128, 128, 0, st>>>(xyz, stem_of(wa), stem_of(wb), B, xfeat, nullptr,
+                                              stem_planes ? reinterpret_cast<__half*>(xfeat_h[0]) : nullptr,
+                                              stem_planes ? reinterpret_cast<__half*>(xfeat_h[1]) : nullptr);
   PZ_LAUNCH_CHECK();
-  PZ_TRY(launch_split_planes(xfeat, D0, (size_t)C * NPTS, D0, xfeat_h[0], xfeat_h[1], D0, st));
+  if (!stem_planes) PZ_TRY(launch_split_planes(xfeat, D0, (size_t)C * NPTS, D0, xfeat_h[0], xfeat_h[1], D0, st));
   prof_mark("stem", st);
   {
     TcGemm g;  // P1 = x_feature W3[:,3:]^T + b3 + W3[:,0:3] xyz   (fp32 out)
@@ -1448,10 +1484,11 @@ static int encoder_forward_split(const PzEncoderWeights* w, int E, int B, const 
     TcGemm g;
     g.X = cat_h[0]; g.Xlo = cat_h[1]; g.ldx = 1280; set_w(g, WS_WOUT); g.ldw = 1280;
     g.bias[0] = wa.out_b; g.bias[1] = wb.out_b; g.rows_per_wset = B * LATT; g.M = rows; g.Nout = 1024; g.K = 1280;
-    g.Yf = tail_out; g.ldyf = 1024;
+    if (o.out) { g.Yf = o.out; g.ldyf = 1024; }
+    g.Ymax = s.tailp; g.ldmax = 1024;            // per 128-row tile column maxima: two tiles per cloud
     PZ_TRY(launch_split_rowgemm(g, st));
-    prof_mark("tail_linear", st);
-    rowblock_max_kernel<<<dim3(4, C), 256, 0, st>>>(tail_out, 1024, LATT, 1024, C, C, 0, fg, 1024);
+    prof_mark("tail_linear_maxpool", st);
+    rowblock_max_kernel<<<dim3(4, C), 256, 0, st>>>(s.tailp, 1024, LATT / 128, 1024, C, C, 0, fg, 1024);
     PZ_LAUNCH_CHECK();
     prof_mark("tail_point_max", st);
     if (fglob_pair)
@@ -1493,7 +1530,7 @@ static int encoder_forward_impl(const PzEncoderWeights* w, int E, int B, const f
   if (xfeat_out) *xfeat_out = xfeat;
 
   // stem: Linear(3,64)+BN+ReLU, Linear(64,64)+BN+ReLU -> x_feature [C,1024,64]
-  stem_kernel<<<C * NPTS / 128, 128, 0, st>>>(xyz, stem_of(wa), stem_of(wb), B, xfeat, nullptr);
+  stem_kernel<<<C * NPTS / 128, 128, 0, st>>>(xyz, stem_of(wa), stem_of(wb), B, xfeat, nullptr, nullptr, nullptr);
   PZ_LAUNCH_CHECK();
   prof_mark("stem", st);
   if (after_stem) PZ_TRY((*after_stem)(xfeat, nullptr));

@@ -17,6 +17,7 @@
 //                          fp32 P rows (global -> registers -> one swizzled st.shared per plane) and the max over the
 //                          32 neighbours in the epilogue (pointnet_util.py:123-130 + model5_b.py:452-454, :459-461)
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "pz_common.cuh"
 #include "tc_common.cuh"
@@ -76,6 +77,7 @@ __global__ void __launch_bounds__(SG_THREADS, 1) split_rowgemm_kernel(const TcGe
   const uint32_t tmem_slot = acce_bar + 16;
   const uint32_t chan_s = tmem_slot + 16;           // [NCOLS] float4 (w1x, w1y, w1z, bias)
   float4* chan = reinterpret_cast<float4*>(smem_gen + (chan_s - smem_base));
+  int* colmax = reinterpret_cast<int*>(chan + NCOLS);   // [4 row quarters][NCOLS] order-preserving int images (Ymax epilogue)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int kblocks = g.K / KB;
@@ -273,6 +275,18 @@ __global__ void __launch_bounds__(SG_THREADS, 1) split_rowgemm_kernel(const TcGe
             v[q4 * 4] += b4.x; v[q4 * 4 + 1] += b4.y; v[q4 * 4 + 2] += b4.z; v[q4 * 4 + 3] += b4.w;
           }
         }
+        if (g.Ymax) {
+          // column maxima over the tile's 128 rows: one redux.sync.max per channel over the warp's 32 rows on the
+          // order-preserving integer image of the float, lane i keeps channel i; the four row quarters meet in smem
+          int keep = 0;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int o = __float_as_int(v[i]);
+            const int m = __reduce_max_sync(0xffffffffu, o >= 0 ? o : o ^ 0x7fffffff);
+            if (lane == i) keep = m;
+          }
+          colmax[quarter * NCOLS + c32 * 32 + lane] = keep;
+        }
         if (YThi) {
           // transposed planes, per block of t_rows rows (one cloud): YT[(blk * Nout + ch) * t_rows + row_in_blk];
           // the 32 lanes of a warp are 32 consecutive rows -> 64 contiguous bytes per channel and plane
@@ -312,6 +326,14 @@ __global__ void __launch_bounds__(SG_THREADS, 1) split_rowgemm_kernel(const TcGe
       }
       tc_fence_before();
       mbar_arrive(acce_bar + 8 * buf);
+      if (g.Ymax) {   // Ymax[row tile, ch] = max over the tile's rows (the caller folds the tiles of a cloud)
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        for (int c = tid; c < NCOLS && col0 + c < nvalid; c += EPI * 32) {
+          const int m = max(max(colmax[c], colmax[NCOLS + c]), max(colmax[2 * NCOLS + c], colmax[3 * NCOLS + c]));
+          g.Ymax[(size_t)rt * g.ldmax + col0 + c] = __int_as_float(m >= 0 ? m : m ^ 0x7fffffff);
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");   // colmax is rewritten by the next tile
+      }
     }
   }
   tc_fence_before();
@@ -323,8 +345,8 @@ __global__ void __launch_bounds__(SG_THREADS, 1) split_rowgemm_kernel(const TcGe
 
 template <int NCOLS, int NST>
 static int split_rowgemm_launch(const TcGemm& g, cudaStream_t st) {
-  const size_t smem = 1024 + (size_t)NST * (2 * TILE16K + 2 * NCOLS * 128) + 8 * (2 * NST + 4) + 32 + (size_t)NCOLS * 16;
-  static_assert(1024 + (size_t)NST * (2 * TILE16K + 2 * NCOLS * 128) + 8 * (2 * NST + 4) + 32 + (size_t)NCOLS * 16 <= 232448,
+  const size_t smem = 1024 + (size_t)NST * (2 * TILE16K + 2 * NCOLS * 128) + 8 * (2 * NST + 4) + 32 + (size_t)NCOLS * 32;
+  static_assert(1024 + (size_t)NST * (2 * TILE16K + 2 * NCOLS * 128) + 8 * (2 * NST + 4) + 32 + (size_t)NCOLS * 32 <= 232448,
                 "split_rowgemm: shared memory budget");
   auto kern = split_rowgemm_kernel<NCOLS, NST>;
   PZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -339,12 +361,13 @@ static int split_rowgemm_launch(const TcGemm& g, cudaStream_t st) {
 }
 
 // Row-major split GEMM.  Operands: X / Xlo [M, K] and W / Wlo [Nout, K] fp16 planes (same leading dimensions);
-// outputs: Yf fp32 and/or Yb + Yblo fp16 planes and/or YT + YTlo transposed planes; residual Rf (fp32) or Rb + Rblo.
+// outputs: Yf fp32 and/or Yb + Yblo fp16 planes and/or YT + YTlo transposed planes and/or Ymax [M / 128, ldmax] = the
+// column maxima of every 128-row tile; residual Rf (fp32) or Rb + Rblo.
 int launch_split_rowgemm(const TcGemm& g, cudaStream_t st) {
-  PZ_REQUIRE(g.W[0] && g.Wlo[0] && g.X && g.Xlo && (g.Yf || g.Yb || g.YT), PZ_ERR_ARG, "split_rowgemm: null operand");
+  PZ_REQUIRE(g.W[0] && g.Wlo[0] && g.X && g.Xlo && (g.Yf || g.Yb || g.YT || g.Ymax), PZ_ERR_ARG, "split_rowgemm: null operand");
   PZ_REQUIRE((!g.Yb || g.Yblo) && (!g.YT || (g.YTlo && g.t_rows > 0)) && (!g.Rb || g.Rblo), PZ_ERR_ARG,
              "split_rowgemm: a 16-bit tensor needs both of its planes");
-  PZ_REQUIRE(g.epi == 0 && !g.Ymax && !g.rows, PZ_ERR_ARG, "split_rowgemm: plain-store epilogue only");
+  PZ_REQUIRE(g.epi == 0 && !g.rows, PZ_ERR_ARG, "split_rowgemm: store / tile-max epilogue only");
   PZ_REQUIRE(g.K % 64 == 0 && g.Nout % 128 == 0 && g.ldx % 8 == 0 && g.ldw % 8 == 0, PZ_ERR_UNSUPPORTED,
              "split_rowgemm: needs K %% 64 == 0, Nout %% 128 == 0 and 16-byte aligned rows (K=%d Nout=%d)", g.K, g.Nout);
   PZ_REQUIRE((!g.Yb || (g.ldyb % 8 == 0 && ((uintptr_t)g.Yb & 15) == 0 && ((uintptr_t)g.Yblo & 15) == 0)) &&
@@ -371,10 +394,9 @@ int launch_split_rowgemm(const TcGemm& g, cudaStream_t st) {
 // channels on UMMA M (TMEM lanes), the ROWS gathered rows of a tile on UMMA N (TMEM columns): the max over the 32
 // neighbours of a group is an in-thread reduction over 32 consecutive columns.  One 128-channel block per CTA (the
 // CTAs of a weight set are split between the channel blocks), both planes of its weights resident in shared memory.
-// Producers (8 warps): P rows are fp32 in global memory; a thread owns the 16-byte chunk column (tid & 7) of the rows
-// (tid >> 3) + 32 i, loads them (2 x LDG.128 per chunk) one half-stage ahead into registers (the row ids one TILE
-// ahead), forms relu(P - Q) in fp32, splits it into hi / lo and writes each plane with ONE swizzled 16-byte st.shared
-// -- the operand is written once and never re-read by the producers.
+// Producers (8 warps): P rows are fp32 in global memory; they are loaded one half-stage ahead into registers (fully
+// coalesced LDG.128, the row ids one TILE ahead), relu(P - Q) is formed in fp32, split into hi / lo and each plane is
+// written with one swizzled st.shared -- the operand is written once and never re-read by the producers.
 template <int ROWS, int NST>
 __global__ void __launch_bounds__(SG_THREADS, 1) split_gather_kernel(const TcGemm g) {
   extern __shared__ __align__(1024) uint8_t sgg_smem_raw[];
@@ -388,6 +410,7 @@ __global__ void __launch_bounds__(SG_THREADS, 1) split_gather_kernel(const TcGem
   const uint32_t bars = stages_base + NST * STAGE;
   const uint32_t full_bar = bars, empty_bar = bars + 8 * NST, accf_bar = bars + 16 * NST, acce_bar = accf_bar + 16;
   const uint32_t tmem_slot = acce_bar + 16;
+  const uint32_t qring_s = tmem_slot + 16;                       // 2 x [ROWS/32 groups][64 ch] fp32 Q tiles (16-byte aligned)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // partitions: (weight set, 128-channel block); the CTAs are split evenly between them
@@ -437,15 +460,36 @@ __global__ void __launch_bounds__(SG_THREADS, 1) split_gather_kernel(const TcGem
   if (warp > EPI) {
     // =========================================================== producers
     constexpr int CH = ROWS / 32;                 // chunks per thread per stage (rows r0 + 32 i: one per group)
-    constexpr int HC = CH / 2;                    // ... handled as two half-stages of HC chunks
+    constexpr int QV = (ROWS / 32) * 16;          // float4 pieces of one stage's Q tile ([groups][64 ch] fp32)
     const int pt = tid - (EPI + 1) * 32, gc = pt & 7, r0 = pt >> 3;
     int my_tiles = 0;
     for (int t = tile_begin + rank; t < tile_end; t += step) ++my_tiles;
     const int jobs = my_tiles * kblocks;          // job j = (tile j / kblocks, k-block j % kblocks)
     const float* __restrict__ P = g.Xf;
     const float* __restrict__ Q = g.Qf;
-    float4 buf[2][HC][2];                         // the two half-stages in flight (fp32 P chunks)
+    // Two half-stages of HC chunks are in flight: the loads of half h of the NEXT job are issued right after half h of
+    // this job has been stored.  The loads stay under `if (more)`: the branch keeps ptxas from sinking them behind the
+    // barrier arrival (measured: with unconditional loads it groups all of a stage's loads after the arrival and the two
+    // halves are no longer staggered, +25 % run time).  A deeper ring (4 units in flight) is SLOWER as well: the kernel
+    // is bound by the LSU data pipe (fp32 P in + both operand planes out = 8 bytes per element through a 64 B/clk path;
+    // ncu l1tex__data_pipe_lsu_wavefronts 77 %), not by load latency.
+    constexpr int HC = CH / 2;
+    float4 buf[2][HC][2];
     int ids[CH], ids_n[CH];                       // source rows of the current / the next tile
+    // Q tiles go through a two-slot shared-memory ring: thread t < QV fetches ONE float4 of the tile of job j + 2 at
+    // the end of job j, parks it in a register for a whole stage, writes it to the ring at the end of job j + 1 (one
+    // producer-only barrier per stage); the subtraction then reads Q with LDS broadcasts instead of waiting for L2
+    float4 qpre = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto q_fetch = [&](int jt) {
+      const int ti = jt / kblocks, kb = jt - ti * kblocks;
+      const int group0 = ((tile_begin + rank + ti * step) * ROWS) >> 5;
+      if (pt < QV) qpre = __ldg(reinterpret_cast<const float4*>(Q + (size_t)(group0 + (pt >> 4)) * g.K + kb * KB + (pt & 15) * 4));
+    };
+    auto q_commit = [&](int slot) {
+      if (pt < QV)
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(qring_s + slot * (QV * 16) + pt * 16), "f"(qpre.x), "f"(qpre.y),
+                     "f"(qpre.z), "f"(qpre.w) : "memory");
+    };
     auto fetch_ids = [&](int ti, int (&dst)[CH]) {
       const int row0 = (tile_begin + rank + ti * step) * ROWS;
 #pragma unroll
@@ -461,23 +505,20 @@ __global__ void __launch_bounds__(SG_THREADS, 1) split_gather_kernel(const TcGem
         buf[h][i][1] = __ldg(src + 1);
       }
     };
-    auto store_half = [&](int h, int kb, int group0, uint32_t st_addr) {
-      float4 q[HC][2];                            // Q rows of the groups (L1 hits: 32 threads share each chunk)
+    auto store_half = [&](int h, int slot, uint32_t st_addr) {
 #pragma unroll
       for (int i = 0; i < HC; ++i) {
-        const float4* src = reinterpret_cast<const float4*>(Q + (size_t)(group0 + h * HC + i) * g.K + kb * KB + gc * 8);
-        q[i][0] = __ldg(src);
-        q[i][1] = __ldg(src + 1);
-      }
-#pragma unroll
-      for (int i = 0; i < HC; ++i) {
-        const int r = r0 + 32 * (h * HC + i);
+        const int ci = h * HC + i, r = r0 + 32 * ci;
+        float4 q0, q1;
+        const uint32_t qa = qring_s + slot * (QV * 16) + ci * 256 + gc * 32;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(q0.x), "=f"(q0.y), "=f"(q0.z), "=f"(q0.w) : "r"(qa));
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(q1.x), "=f"(q1.y), "=f"(q1.z), "=f"(q1.w) : "r"(qa + 16));
         const float4 p0 = buf[h][i][0], p1 = buf[h][i][1];
         uint4 oh, ol;
-        split2(fmaxf(p0.x - q[i][0].x, 0.f), fmaxf(p0.y - q[i][0].y, 0.f), oh.x, ol.x);
-        split2(fmaxf(p0.z - q[i][0].z, 0.f), fmaxf(p0.w - q[i][0].w, 0.f), oh.y, ol.y);
-        split2(fmaxf(p1.x - q[i][1].x, 0.f), fmaxf(p1.y - q[i][1].y, 0.f), oh.z, ol.z);
-        split2(fmaxf(p1.z - q[i][1].z, 0.f), fmaxf(p1.w - q[i][1].w, 0.f), oh.w, ol.w);
+        split2(fmaxf(p0.x - q0.x, 0.f), fmaxf(p0.y - q0.y, 0.f), oh.x, ol.x);
+        split2(fmaxf(p0.z - q0.z, 0.f), fmaxf(p0.w - q0.w, 0.f), oh.y, ol.y);
+        split2(fmaxf(p1.x - q1.x, 0.f), fmaxf(p1.y - q1.y, 0.f), oh.z, ol.z);
+        split2(fmaxf(p1.z - q1.z, 0.f), fmaxf(p1.w - q1.w, 0.f), oh.w, ol.w);
         const uint32_t off = sw128(r, gc);
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st_addr + off), "r"(oh.x), "r"(oh.y), "r"(oh.z), "r"(oh.w) : "memory");
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st_addr + X_PLANE + off), "r"(ol.x), "r"(ol.y), "r"(ol.z), "r"(ol.w) : "memory");
@@ -488,19 +529,22 @@ __global__ void __launch_bounds__(SG_THREADS, 1) split_gather_kernel(const TcGem
       if (my_tiles > 1) fetch_ids(1, ids_n);
       load_half(0, 0, false);
       load_half(1, 0, false);
+      q_fetch(0);
+      q_commit(0);
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      if (jobs > 1) q_fetch(1);
     }
     for (int j = 0; j < jobs; ++j) {
       const int ti = j / kblocks, kb = j - ti * kblocks;
       const uint32_t s = (uint32_t)j % NST, ph = ((uint32_t)j / NST) & 1;
       const uint32_t st_addr = stages_base + s * STAGE;
-      const int group0 = ((tile_begin + rank + ti * step) * ROWS) >> 5;
       const bool more = j + 1 < jobs;
       const int nkb = (kb + 1 == kblocks) ? 0 : kb + 1;
       const bool new_tile = more && nkb == 0;     // the next job starts the next tile: its rows are ids_n
       mbar_wait(empty_bar + 8 * s, ph ^ 1);
-      store_half(0, kb, group0, st_addr);
+      store_half(0, j & 1, st_addr);
       if (more) load_half(0, nkb, new_tile);      // the registers of half 0 are free again: next job's half 0
-      store_half(1, kb, group0, st_addr);
+      store_half(1, j & 1, st_addr);
       fence_proxy_async();
       mbar_arrive(full_bar + 8 * s);
       if (more) load_half(1, nkb, new_tile);
@@ -508,6 +552,11 @@ __global__ void __launch_bounds__(SG_THREADS, 1) split_gather_kernel(const TcGem
 #pragma unroll
         for (int i = 0; i < CH; ++i) ids[i] = ids_n[i];
         if (ti + 2 < my_tiles) fetch_ids(ti + 2, ids_n);   // needed one whole tile from now
+      }
+      if (more) {
+        q_commit((j + 1) & 1);                    // the tile of job j + 1 (fetched one stage ago) -> its ring slot
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        if (j + 2 < jobs) q_fetch(j + 2);
       }
     }
   } else if (warp == EPI) {
@@ -587,7 +636,8 @@ __global__ void __launch_bounds__(SG_THREADS, 1) split_gather_kernel(const TcGem
 template <int ROWS, int NST>
 static int split_gather_launch(const TcGemm& g, cudaStream_t st) {
   const int kblocks = g.K / KB;
-  const size_t smem = 1024 + 2 * (size_t)kblocks * TILE16K + (size_t)NST * 2 * ROWS * 128 + 8 * (2 * NST + 4) + 32;
+  const size_t smem = 1024 + 2 * (size_t)kblocks * TILE16K + (size_t)NST * 2 * ROWS * 128 + 8 * (2 * NST + 4) + 32 +
+                      2 * (size_t)(ROWS / 32) * 64 * sizeof(float);
   PZ_REQUIRE(smem <= 232448, PZ_ERR_UNSUPPORTED, "split_gather: needs %zu B of shared memory (K=%d)", smem, g.K);
   auto kern = split_gather_kernel<ROWS, NST>;
   PZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
