@@ -287,6 +287,22 @@ def _bench_c3(dev, world, hbm_peak, iters=5):
             stages[f"group_mlp_maxpool_{name}"] = (t, group_bytes)
         t_sg, _ = _timed(lambda: pu.sample_and_group(S, 0, K, xyz, feat, False, True), max(2, iters // 2))
         stages["sample_and_group_materialising"] = (t_sg, B * (12 * N + 4 * N * D + 12 * S + 4 * S * K * (3 + D)))
+        # the group stage alone (index_points + centre + concat, pointnet_util.py:123-130): the HBM-bound part of the path
+        from puzzlenet_b200 import _lib
+
+        def group_only(xyz_, feat_, nx_, idx_, n_, s_):
+            b_ = xyz_.shape[0]
+            out = torch.empty(b_, s_, K, 3 + D, device=dev)
+            fn = lambda: _lib.call("pz_group_concat", xyz_.data_ptr(), feat_.data_ptr(), nx_.data_ptr(), idx_.data_ptr(), b_, n_,  # noqa: E731
+                                   D, s_, K, out.data_ptr(), None, _lib.stream_ptr())
+            return _timed(fn, iters)[0], b_ * (12 * n_ + 4 * n_ * D + 8 * s_ * K + 12 * s_ + 4 * s_ * K * (3 + D))
+        stages["group_gather_concat_only"] = group_only(xyz, feat, new_xyz, idx, N, S)
+        # ... and at the C2 shape (128 clouds x 1024 points -> 512 groups), the shape of the model's first stage
+        x2 = xyz[:, :1024].repeat(2, 1, 1).contiguous()
+        f2 = feat[:, :1024].repeat(2, 1, 1).contiguous()
+        nx2 = x2[:, :512].contiguous()
+        idx2 = pu.knn_point(K, x2, nx2)
+        stages["group_gather_concat_only_c2_shape"] = group_only(x2, f2, nx2, idx2, 1024, 512)
     res = {"workload": f"C3: FPS {N}->{S}, kNN k={K}, gather+MLP 67->128->128+max-pool, B={B} clouds per GPU", "n_gpus": world,
            "clouds_total": B * world, "note": "FPS / kNN are latency / issue bound (SURVEY 8d): their HBM fraction is "
            "reported on the compulsory bytes as the contract asks; the materialising sample_and_group API is the HBM-bound one"}

@@ -384,7 +384,10 @@ int launch_split_rowgemm(const TcGemm& g, cudaStream_t st) {
   PZ_REQUIRE(g.M % (128 * nsets) == 0, PZ_ERR_UNSUPPORTED, "split_rowgemm: M=%d must be a multiple of %d", g.M, 128 * nsets);
   if (g.n_valid > 0) PZ_REQUIRE(g.n_valid % 32 == 0, PZ_ERR_ARG, "split_rowgemm: n_valid must be a multiple of 32");
   if (g.YT) PZ_REQUIRE(g.t_rows % 128 == 0, PZ_ERR_ARG, "split_rowgemm: t_rows must be a multiple of 128");
-  if (g.Nout % 256 == 0) return split_rowgemm_launch<256, 2>(g, st);
+  // 256-column tiles halve the re-reads of X but leave at most two tiles per CTA at M = 32768 (the epilogue of a tile then
+  // has little to overlap with); PZ_SPLIT_NCOLS=128 forces 128-column tiles everywhere (A/B hook)
+  static const bool narrow = getenv("PZ_SPLIT_NCOLS") && atoi(getenv("PZ_SPLIT_NCOLS")) == 128;
+  if (g.Nout % 256 == 0 && !(narrow && !g.Ymax)) return split_rowgemm_launch<256, 2>(g, st);
   return split_rowgemm_launch<128, 3>(g, st);
 }
 

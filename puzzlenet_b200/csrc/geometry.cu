@@ -646,6 +646,71 @@ extern "C" int pz_gather(const void* pts, const int64_t* idx, int B, int N, int 
   return 0;
 }
 
+// The HBM-bound form of the same op (the materialising sample_and_group API is a pure gather + write of
+// 4*S*K*(3+D) bytes per cloud): ONE WARP PER GROUP.  The K = 32 gathered rows of a group are one contiguous run of
+// 32*(3+D) floats in the output, so the warp assembles the run in shared memory (feature rows arrive as fully coalesced
+// 16-byte loads, two rows per warp instruction; the three centred coordinates per row from lane k) and writes it out as
+// 16-byte stores over the contiguous run -- the run starts on a 16-byte boundary because 32*(3+D)*4 is a multiple of 16.
+// Needs K == 32 and D % 4 == 0 (the model's shapes); everything else takes group_concat_kernel above.
+template <int WARPS, int D4>
+__global__ void __launch_bounds__(WARPS * 32) group_concat_tile_kernel(const float* __restrict__ xyz, const float* __restrict__ feat,
+                                                                        const float* __restrict__ new_xyz,
+                                                                        const int64_t* __restrict__ knn, int N, int D, int S,
+                                                                        size_t groups, float* __restrict__ new_points,
+                                                                        float* __restrict__ grouped_xyz) {
+  extern __shared__ __align__(16) float gc_smem[];
+  const int W = 3 + D, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* tile = gc_smem + (size_t)warp * 32 * W;              // [32][W], 32*W*4 bytes: a multiple of 16
+  const int d4 = D >> 2;                                       // float4 pieces per feature row
+  for (size_t g = (size_t)blockIdx.x * WARPS + warp; g < groups; g += (size_t)gridDim.x * WARPS) {
+    const size_t b = g / S;
+    const size_t r0 = g * 32;
+    const size_t jl = b * N + (size_t)knn[r0 + lane];          // lane k owns neighbour k's source row
+    {                                                          // centred coordinates (pointnet_util.py:125)
+      const float cx = new_xyz[g * 3], cy = new_xyz[g * 3 + 1], cz = new_xyz[g * 3 + 2];
+      const float x = xyz[jl * 3], y = xyz[jl * 3 + 1], z = xyz[jl * 3 + 2];
+      tile[lane * W] = __fsub_rn(x, cx);
+      tile[lane * W + 1] = __fsub_rn(y, cy);
+      tile[lane * W + 2] = __fsub_rn(z, cz);
+      if (grouped_xyz) {
+        grouped_xyz[(r0 + lane) * 3] = x;
+        grouped_xyz[(r0 + lane) * 3 + 1] = y;
+        grouped_xyz[(r0 + lane) * 3 + 2] = z;
+      }
+    }
+    // features: piece p = (row p / d4, float4 p % d4); consecutive lanes read consecutive 16 bytes of a row.  All loads
+    // of a batch of pieces are issued before the first is stored (the gather is latency bound otherwise).
+    if (D4 > 0) {                                              // compile-time D: every load of the group in flight at once
+      float4 v[D4 > 0 ? D4 : 1];
+#pragma unroll
+      for (int i = 0; i < D4; ++i) {
+        const int p = lane + 32 * i, k = p / D4, c = p % D4;
+        const size_t j = __shfl_sync(0xffffffffu, jl, k);
+        v[i] = __ldg(reinterpret_cast<const float4*>(feat + j * D) + c);
+      }
+#pragma unroll
+      for (int i = 0; i < D4; ++i) {
+        const int p = lane + 32 * i, k = p / D4, c = p % D4;
+        float* t = tile + k * W + 3 + c * 4;
+        t[0] = v[i].x; t[1] = v[i].y; t[2] = v[i].z; t[3] = v[i].w;
+      }
+    } else {
+      for (int p = lane; p < 32 * d4; p += 32) {
+        const int k = p / d4, c = p - k * d4;
+        const size_t j = __shfl_sync(0xffffffffu, jl, k);
+        const float4 v = __ldg(reinterpret_cast<const float4*>(feat + j * D) + c);
+        float* t = tile + k * W + 3 + c * 4;
+        t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
+      }
+    }
+    __syncwarp();
+    float4* dst = reinterpret_cast<float4*>(new_points + r0 * W);
+    const float4* src = reinterpret_cast<const float4*>(tile);
+    for (int p = lane; p < 8 * W; p += 32) dst[p] = src[p];   // 32*W floats = 8*W float4
+    __syncwarp();
+  }
+}
+
 extern "C" int pz_group_concat(const float* xyz, const float* feat_or_null, const float* new_xyz,
                                const int64_t* knn_idx, int B, int N, int D, int S, int K,
                                float* new_points, float* grouped_xyz_or_null, pz_stream_t stream) {
@@ -655,6 +720,24 @@ extern "C" int pz_group_concat(const float* xyz, const float* feat_or_null, cons
   if (rows == 0) return 0;
   PZ_REQUIRE(xyz && new_xyz && knn_idx && new_points, PZ_ERR_ARG, "pz_group_concat: null pointer");
   PZ_REQUIRE(feat_or_null || D == 0, PZ_ERR_ARG, "pz_group_concat: feat is null but D=%d", D);
+  if (K == 32 && D >= 4 && D % 4 == 0 && D <= 256 && ((uintptr_t)feat_or_null & 15) == 0 && ((uintptr_t)new_points & 15) == 0) {
+    constexpr int WARPS = 4;
+    const size_t groups = (size_t)B * S;
+    const size_t smem = (size_t)WARPS * 32 * ld * sizeof(float);
+    const size_t want_t = (groups + WARPS - 1) / WARPS;
+    const int blocks_t = (int)(want_t < (size_t)kNumSMs * 8 ? want_t : (size_t)kNumSMs * 8);
+    auto launch = [&](auto kern) {
+      PZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kern<<<blocks_t, WARPS * 32, smem, as_stream(stream)>>>(xyz, feat_or_null, new_xyz, knn_idx, N, D, S, groups, new_points,
+                                                              grouped_xyz_or_null);
+      return 0;
+    };
+    if (D == 64) PZ_TRY(launch(group_concat_tile_kernel<WARPS, 16>));         // the model's stage 1 / the C3 shape
+    else if (D == 128) PZ_TRY(launch(group_concat_tile_kernel<WARPS, 32>));   // the model's stage 2
+    else PZ_TRY(launch(group_concat_tile_kernel<WARPS, 0>));
+    PZ_LAUNCH_CHECK();
+    return 0;
+  }
   size_t want = (rows + 7) / 8;
   int blocks = (int)(want < (size_t)kNumSMs * 16 ? want : (size_t)kNumSMs * 16);
   group_concat_kernel<<<blocks, 256, 0, as_stream(stream)>>>(xyz, feat_or_null, new_xyz, knn_idx, N, D, S, K, rows, ld, new_points, grouped_xyz_or_null);
