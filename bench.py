@@ -372,7 +372,8 @@ def _bench_assembly(model, dev, world, pieces=32, points=11000, iters=5):
     from scripts.bench_assembly import dublin_like_piece
     raw = [dublin_like_piece(i, points) for i in range(pieces)]
     starts = [int(np.random.default_rng(100 + i).integers(0, points)) for i in range(pieces)]
-    scorer = assembly.ModelScorer(model)
+    scorer = assembly.ModelScorer(model, pipes=4)     # batches of 64 pairs alternate over 4 streams, one graph replay each
+    model.cuda_graphs = True
 
     def once():
         torch.manual_seed(1234)
@@ -380,7 +381,7 @@ def _bench_assembly(model, dev, world, pieces=32, points=11000, iters=5):
         pairs, rows = assembly.score_all_pairs(clouds, scorer, batch=64)
         return assembly.greedy_assemble(pieces, pairs, rows)
 
-    for _ in range(2):
+    for _ in range(3):
         once()
     torch.cuda.synchronize()
     if world > 1:
@@ -390,6 +391,7 @@ def _bench_assembly(model, dev, world, pieces=32, points=11000, iters=5):
         _, _, merges = once()
     torch.cuda.synchronize()
     ms = _max_over_ranks((time.perf_counter() - t0) / iters * 1e3, dev, world)
+    model.cuda_graphs = False
     n_pairs = pieces * (pieces - 1) // 2
     return {"workload": f"{pieces} pieces x {points} pts: FPS 11000->1024 (pieces sharded), {n_pairs} pairs scored (pairs "
                         "sharded), greedy merge", "n_gpus": world, "scaling": "strong", "precision": model.precision,

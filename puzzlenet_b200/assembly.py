@@ -31,8 +31,19 @@ class ModelScorer:
     """``scorer(fpc [b,1024,3], mrpc [b,1024,3]) -> rows [b, ROW_COLS]`` through the CUDA library:
     one ``pz_predict5`` and one ``pz_pair_score`` (assembly mode: ``src = mrpc``, no ground truth)."""
 
-    def __init__(self, model):
+    def __init__(self, model, pipes: int = 1):
+        """``pipes`` > 1: :func:`score_pairs` spreads its batches round-robin over that many CUDA streams (batches are
+        independent), so the latency-bound stages of one batch overlap the tensor-core stages of the others -- the
+        schedule ``bench.py`` times.  Combine with ``model.cuda_graphs = True`` for one graph replay per batch."""
         self.model = model
+        self.pipes = max(1, int(pipes))
+        self._streams = {}
+
+    def streams(self, device):
+        key = str(device)
+        if key not in self._streams:
+            self._streams[key] = [torch.cuda.Stream(device=device) for _ in range(self.pipes)]
+        return self._streams[key]
 
     def __call__(self, fpc: torch.Tensor, mrpc: torch.Tensor) -> torch.Tensor:
         from . import losses
@@ -71,6 +82,19 @@ def score_pairs(clouds: torch.Tensor, pairs: torch.Tensor, scorer: Callable, bat
     n = pairs.shape[0]
     rows = torch.empty(n, ROW_COLS, device=clouds.device, dtype=torch.float32)
     pairs = pairs.to(clouds.device)
+    pipes = int(getattr(scorer, "pipes", 1))
+    if pipes > 1 and n > batch and clouds.is_cuda:
+        cur = torch.cuda.current_stream(clouds.device)
+        streams = scorer.streams(clouds.device)
+        for st in streams:
+            st.wait_stream(cur)
+        for bi, lo in enumerate(range(0, n, batch)):
+            with torch.cuda.stream(streams[bi % pipes]):
+                sel = pairs[lo:lo + batch]
+                rows[lo:lo + sel.shape[0]] = scorer(clouds[sel[:, 0]].contiguous(), clouds[sel[:, 1]].contiguous())
+        for st in streams:
+            cur.wait_stream(st)
+        return rows
     for lo in range(0, n, batch):
         sel = pairs[lo:lo + batch]
         rows[lo:lo + sel.shape[0]] = scorer(clouds[sel[:, 0]].contiguous(), clouds[sel[:, 1]].contiguous())

@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(1024) emd_matchcost_kernel(int n, int m, const
     __syncthreads();
     for (int k = t; k < n; k += 1024) {
       const float x1 = p1[k * 3], y1 = p1[k * 3 + 1], z1 = p1[k * 3 + 2];
-#pragma unroll 4
+#pragma unroll 16   // 16 independent 4 KB row reads in flight per CTA pass: the loop is bound by HBM latency x concurrency
       for (int l = 0; l < cnt; ++l)
         sub += emd_d2(x1, y1, z1, q[l * 3], q[l * 3 + 1], q[l * 3 + 2]) * mt[(size_t)(l0 + l) * n + k];
     }
@@ -215,6 +215,7 @@ __global__ void __launch_bounds__(128) emd_grad1_kernel(int n, int m, const floa
   const float* mt = match + (size_t)item * n * m;
   const float x1 = p1[k * 3], y1 = p1[k * 3 + 1], z1 = p1[k * 3 + 2];
   float dx = 0, dy = 0, dz = 0;
+#pragma unroll 16
   for (int l = 0; l < m; ++l) {
     const float d = mt[(size_t)l * n + k] * 2;
     dx += (x1 - p2[l * 3]) * d;
@@ -240,6 +241,7 @@ __global__ void __launch_bounds__(256) emd_grad2_kernel(int n, int m, const floa
   const float* mr = match + (size_t)item * n * m + (size_t)l * n;
   const float x2 = p2[0], y2 = p2[1], z2 = p2[2];
   float sx = 0, sy = 0, sz = 0;
+#pragma unroll 8
   for (int k = lane; k < n; k += 32) {
     const float d = mr[k] * 2;
     sx += (x2 - p1[k * 3]) * d;

@@ -122,6 +122,166 @@ static int fps_launch_t(const float* xyz, int B, int N, const int64_t* start, in
   return 0;
 }
 
+// ---- large clouds (dataset shape, 11000 -> 1024): a thread-block cluster of CS = 2 or 4 CTAs per cloud.  Each CTA keeps
+// the running minimum distances of 1/CS of the points in registers (the per-iteration update -- 32 warps x PPT points x
+// ~12 instructions, issue bound -- shrinks by CS) and the whole cloud's coordinates in its own shared memory (the centroid
+// lookup stays local).  Per iteration the CTAs exchange ONE 64-bit key each (distance bits, ~index): a thread per peer
+// sends its CTA's winner into its slot at that peer with st.async, which also completes the transaction count of the
+// peer's mbarrier; every thread then waits on its own CTA's mbarrier and takes the largest key.  No cluster-wide barrier inside the loop
+// (cluster.sync costs ~380 cycles and flushes L1; the mbarrier round trip is one DSMEM store).
+__device__ __forceinline__ uint32_t fps_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+template <int PPT, int CS>
+__global__ void __launch_bounds__(1024) fps_cluster_kernel(const float* __restrict__ xyz, int N, int S,
+                                                           const int64_t* __restrict__ start, int64_t* __restrict__ out64,
+                                                           int* __restrict__ out_rows32, float* __restrict__ new_xyz) {
+  constexpr int T = 1024;
+  extern __shared__ float fps_smem[];
+  float* xs = fps_smem;
+  float* ys = xs + N;
+  float* zs = ys + N;
+  int* sel = reinterpret_cast<int*>(zs + N);
+  __shared__ unsigned int whi[2][32];
+  __shared__ unsigned int wlo[2][32];
+  __shared__ __align__(8) unsigned long long peer_key[2][CS]; // slot [parity][sender rank], written by the PEER CTAs (st.async)
+  __shared__ __align__(8) unsigned long long xbar[2];         // mbarriers completed by the peers' st.async
+
+  const int c = blockIdx.x / CS;
+  unsigned int rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  const int t = threadIdx.x;
+  const int lane = t & 31, warp = t >> 5;
+  const float* p = xyz + (size_t)c * N * 3;
+  for (int i = t; i < N * 3; i += T) {
+    float v = p[i];
+    int pt = i / 3, d = i - pt * 3;
+    fps_smem[d * N + pt] = v;
+  }
+  if (t < 64) (&whi[0][0])[t] = 0u, (&wlo[0][0])[t] = 0u;
+  if (t == 0) {
+    for (int b = 0; b < 2; ++b)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(fps_smem_u32(&xbar[b])) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  // both CTAs have initialised their barriers before anyone sends
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  // lanes 1 .. CS-1 of warp 0 each own one peer: the peer's copy of my slot in ITS peer_key and of its barriers
+  uint32_t remote_key[2] = {0, 0}, remote_bar[2] = {0, 0};
+  if (t >= 1 && t < CS) {
+    const unsigned int peer = (rank + t) % CS;
+    for (int b = 0; b < 2; ++b) {
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote_key[b]) : "r"(fps_smem_u32(&peer_key[b][rank])), "r"(peer));
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote_bar[b]) : "r"(fps_smem_u32(&xbar[b])), "r"(peer));
+    }
+  }
+
+  const int part = (N + CS - 1) / CS;                          // contiguous index ranges: CTA r owns [r*part, min(N, (r+1)*part))
+  const int base = (int)rank * part, cnt = max(0, min(N, base + part) - base);
+  float px[PPT], py[PPT], pz_[PPT], md[PPT];
+#pragma unroll
+  for (int j = 0; j < PPT; ++j) {
+    const int li = t + j * T;
+    const bool ok = li < cnt;
+    const int i = base + li;
+    px[j] = ok ? xs[i] : 0.f;
+    py[j] = ok ? ys[i] : 0.f;
+    pz_[j] = ok ? zs[i] : 0.f;
+    md[j] = ok ? 1e10f : 0.f;
+  }
+
+  int far = (int)start[c];
+  far = min(max(far, 0), N - 1);
+  for (int s = 0; s < S; ++s) {
+    if (t == 0) sel[s] = far;
+    if (s + 1 == S) break;
+    const float cx = xs[far], cy = ys[far], cz = zs[far];
+    float best = -1.f;
+    int bestj = 0;
+#pragma unroll
+    for (int j = 0; j < PPT; ++j) {
+      md[j] = fminf(md[j], sqdist3(px[j], py[j], pz_[j], cx, cy, cz));
+      const bool gt = md[j] > best;
+      best = gt ? md[j] : best;
+      bestj = gt ? j : bestj;
+    }
+    const unsigned int hi = __float_as_uint(best);
+    const unsigned int lo = ~(unsigned int)(base + t + bestj * T);
+    const unsigned int mhi = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned int mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
+    const int par = s & 1;
+    if (lane == 0) {
+      whi[par][warp] = mhi;
+      wlo[par][warp] = mlo;
+    }
+    __syncthreads();
+    const unsigned int h2 = whi[par][lane];
+    const unsigned int l2 = wlo[par][lane];
+    const unsigned int ghi = __reduce_max_sync(0xffffffffu, h2);
+    const unsigned int glo = __reduce_max_sync(0xffffffffu, h2 == ghi ? l2 : 0u);
+    const unsigned long long mine = ((unsigned long long)ghi << 32) | glo;
+    if (t == 0)      // arm my barrier for the peers' 8 bytes each
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fps_smem_u32(&xbar[par])), "r"(8 * (CS - 1)) : "memory");
+    else if (t < CS) // send my key into my slot at one peer (completes ITS barrier)
+      asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];"
+                   ::"r"(remote_key[par]), "l"(mine), "r"(remote_bar[par]) : "memory");
+    {  // wait for the peer's key of this iteration (phase of barrier `par` = its use count parity)
+      const uint32_t bar = fps_smem_u32(&xbar[par]), phase = (uint32_t)(s >> 1) & 1u;
+      uint32_t ok = 0;
+      for (uint32_t spin = 0; !ok; ++spin) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(phase) : "memory");
+        if (!ok && spin > (1u << 24)) __trap();   // a protocol bug must be a launch failure, never a hang
+      }
+    }
+    unsigned long long win = mine;
+#pragma unroll
+    for (int r = 0; r < CS; ++r) {
+      const unsigned long long theirs = *reinterpret_cast<volatile unsigned long long*>(&peer_key[par][r]);
+      if (r != (int)rank && theirs > win) win = theirs;
+    }
+    far = (int)(~(unsigned int)(win & 0xffffffffull));
+  }
+  __syncthreads();
+  if (rank == 0) {
+    for (int s = t; s < S; s += T) {
+      const int f = sel[s];
+      const size_t o = (size_t)c * S + s;
+      if (out64) out64[o] = f;
+      if (out_rows32) out_rows32[o] = c * N + f;
+      if (new_xyz) {
+        new_xyz[o * 3 + 0] = xs[f];
+        new_xyz[o * 3 + 1] = ys[f];
+        new_xyz[o * 3 + 2] = zs[f];
+      }
+    }
+  }
+  // neither CTA may exit while the other can still write into its shared memory
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <int PPT, int CS>
+static int fps_launch_cluster(const float* xyz, int B, int N, const int64_t* start, int S, int64_t* out64,
+                              int* out_rows32, float* new_xyz, cudaStream_t st) {
+  size_t smem = (size_t)N * 3 * sizeof(float) + (size_t)S * sizeof(int);
+  PZ_REQUIRE(smem <= 226 * 1024, PZ_ERR_UNSUPPORTED, "pz_fps: N=%d, S=%d need %zu B of shared memory", N, S, smem);
+  PZ_CUDA(cudaFuncSetAttribute(fps_cluster_kernel<PPT, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(CS * B);
+  cfg.blockDim = dim3(1024);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  PZ_CUDA(cudaLaunchKernelEx(&cfg, fps_cluster_kernel<PPT, CS>, xyz, N, S, start, out64, out_rows32, new_xyz));
+  count_launch();
+  return 0;
+}
+
 int launch_fps(const float* xyz, int B, int N, const int64_t* start, int S, int64_t* out64,
                int* out_rows32, float* new_xyz, cudaStream_t st) {
   if (const char* e = getenv("PZ_FPS_T")) {   // tuning experiment hook: threads per cloud for N <= 1024
@@ -132,6 +292,21 @@ int launch_fps(const float* xyz, int B, int N, const int64_t* start, int S, int6
       if (T == 512) return fps_launch_t<2, 512>(xyz, B, N, start, S, out64, out_rows32, new_xyz, st);
       if (T == 1024) return fps_launch_t<1, 1024>(xyz, B, N, start, S, out64, out_rows32, new_xyz, st);
     }
+  }
+  // large clouds, few enough of them that two CTAs per cloud still run in one wave: the 2-CTA cluster variant
+  static const bool no_cluster = getenv("PZ_FPS_NO_CLUSTER") != nullptr;   // A/B hook
+  if (N > 4096 && 4 * B <= kNumSMs && !no_cluster) {     // a handful of large clouds (assembly, dataset): 4 CTAs per cloud
+    const int part = (N + 3) / 4;
+    if (part <= 2 * 1024) return fps_launch_cluster<2, 4>(xyz, B, N, start, S, out64, out_rows32, new_xyz, st);
+    if (part <= 3 * 1024) return fps_launch_cluster<3, 4>(xyz, B, N, start, S, out64, out_rows32, new_xyz, st);
+    if (part <= 4 * 1024) return fps_launch_cluster<4, 4>(xyz, B, N, start, S, out64, out_rows32, new_xyz, st);
+  }
+  if (N > 4096 && 2 * B <= kNumSMs && !no_cluster) {
+    const int part = (N + 1) / 2;
+    if (part <= 3 * 1024) return fps_launch_cluster<3, 2>(xyz, B, N, start, S, out64, out_rows32, new_xyz, st);
+    if (part <= 4 * 1024) return fps_launch_cluster<4, 2>(xyz, B, N, start, S, out64, out_rows32, new_xyz, st);
+    if (part <= 6 * 1024) return fps_launch_cluster<6, 2>(xyz, B, N, start, S, out64, out_rows32, new_xyz, st);
+    if (part <= 8 * 1024) return fps_launch_cluster<8, 2>(xyz, B, N, start, S, out64, out_rows32, new_xyz, st);
   }
   if (N <= 256) return fps_launch_t<2, 128>(xyz, B, N, start, S, out64, out_rows32, new_xyz, st);
   if (N <= 512) return fps_launch_t<4, 128>(xyz, B, N, start, S, out64, out_rows32, new_xyz, st);

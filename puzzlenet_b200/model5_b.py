@@ -255,6 +255,8 @@ class TouchedRegraster(_Base):
         self._capture_stream = None
         self._trainer_state = None
         self.cuda_graphs = False      # opt-in: replay one captured CUDA graph per forward (see _graph_replay)
+        self.graph_static_outputs = False   # True: return the graph's own output buffers (overwritten by the next replay)
+        self.max_graphs = 16          # captured graphs kept (one per batch size, need, precision, device, stream); LRU
 
     # ---- weights as C structs (rebuilt per call: ~100 data_ptr() reads, no device work)
     def _head_struct(self) -> _lib.PzHeadWeights:
@@ -329,8 +331,10 @@ class TouchedRegraster(_Base):
     def _graph_replay(self, fpc, mrpc, starts, need, shared=False):
         """CUDA-graph mode (``model.cuda_graphs = True``): the 22 launches of one forward (both streams of the
         internal fork/join included) are captured once per (batch size, need, precision, stream) and replayed.
-        Inputs are copied into static buffers; the returned tensors are static too -- they are overwritten by
-        the next call on the same stream.  A change of any parameter re-captures."""
+        Inputs are copied into static buffers; the results are copied out of the graph's static output buffers into
+        fresh tensors (``graph_static_outputs = True`` returns the static buffers themselves: they are overwritten by
+        the next call on the same stream).  A change of any parameter re-captures; at most ``max_graphs`` graphs are
+        kept, least recently used first out."""
         B, dev = fpc.shape[0], fpc.device
         stream = torch.cuda.current_stream(dev)
         key = (B, bool(need), self.precision, str(dev), stream.cuda_stream, shared)
@@ -356,15 +360,22 @@ class TouchedRegraster(_Base):
                 self._launch(st["fpc"], st["mrpc"], st["starts"], need, st["ws"], outs,
                              reuse_packs=self.precision in PACKED_PRECISIONS, shared=shared)
             g = dict(pkey=pkey, st=st, outs=outs, graph=graph)
-            if len(self._graphs) >= 8:
-                self._graphs.clear()
+            self._graphs.pop(key, None)
+            while len(self._graphs) >= self.max_graphs:          # evict the least recently used entry, not the whole cache
+                self._graphs.pop(next(iter(self._graphs)))
             self._graphs[key] = g
+        else:
+            self._graphs[key] = self._graphs.pop(key)             # mark as most recently used
         st = g["st"]
         st["fpc"].copy_(fpc, non_blocking=True)
         st["mrpc"].copy_(mrpc, non_blocking=True)
         st["starts"].copy_(starts, non_blocking=True)
         g["graph"].replay()
-        return g["outs"]
+        if self.graph_static_outputs:
+            return g["outs"]
+        # fresh tensors, like the reference (and like eager mode): the graph's own output buffers are overwritten by the
+        # next replay on this stream, so a caller that keeps two results alive must not see them alias
+        return tuple(None if t is None else t.clone() for t in g["outs"])
 
     def forward(self, batch, bat):
         # The reference's forward() calls predict4, which needs modules that are commented out of

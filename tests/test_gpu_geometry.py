@@ -175,3 +175,25 @@ def test_full_size_properties_c3(pu):
     full = pu.square_distance(new_xyz[:, :16], xyz)
     kth = d2[:, :16, -1:]
     assert ((full < kth).sum(-1) <= 31).all() and ((full <= kth).sum(-1) >= 32).all()
+
+
+def test_fps_large_cloud_variants_agree():
+    """FPS at the dataset shape (11000 -> 1024) takes three code paths depending on how many clouds share the GPU: a
+    4-CTA cluster per cloud (4B <= 148 SMs), a 2-CTA cluster (2B <= 148) and one CTA per cloud.  All three must pick
+    the same indices for the same cloud and start (and B = 2 is pinned to the reference goldens above)."""
+    from puzzlenet_b200 import _lib
+    g = torch.Generator().manual_seed(11)
+    xyz = (torch.rand(80, 11000, 3, generator=g) - 0.5).to(DEV)
+    start = torch.randint(0, 11000, (80,), generator=g).to(DEV)
+
+    def run(b):
+        out = torch.empty(b, 1024, dtype=torch.int64, device=DEV)
+        _lib.call("pz_fps", xyz[:b].contiguous().data_ptr(), b, 11000, start[:b].contiguous().data_ptr(), 1024, out.data_ptr(), None,
+                  _lib.stream_ptr())
+        torch.cuda.synchronize()
+        return out.cpu()
+
+    four, two, one = run(3), run(40), run(80)
+    assert torch.equal(four, two[:3]) and torch.equal(two, one[:40])
+    ref = po.farthest_point_sample(xyz[:1].cpu(), 1024, start[:1].cpu())
+    assert torch.equal(four[:1], ref)

@@ -302,7 +302,7 @@ def test_cuda_graph_mode_matches_eager(cuda_model):
                           for i, n in enumerate((1024, 512, 1024, 512))])
     batch = make_batch(fpc.to(DEV), mrpc.to(DEV))
     try:
-        for prec in ("fp32", "bf16"):
+        for prec in ("fp32", "bf16", "split"):
             cuda_model.precision = prec
             cuda_model.cuda_graphs = False
             eager = [t.clone() for t in cuda_model.predict5(batch, 0, starts=starts)[1:]]
@@ -311,10 +311,14 @@ def test_cuda_graph_mode_matches_eager(cuda_model):
                 graphed = cuda_model.predict5(batch, 0, starts=starts)[1:]
             torch.cuda.synchronize()
             assert all(torch.equal(a, b) for a, b in zip(eager, graphed)), prec
-            # different inputs through the same graph
+            # different inputs through the same graph; results are FRESH tensors (as in eager mode and the reference):
+            # the first result must survive the second call on the same stream
             fpc2, mrpc2 = synthetic_pairs(4, seed=22)
             b2 = make_batch(fpc2.to(DEV), mrpc2.to(DEV))
-            g2 = [t.clone() for t in cuda_model.predict5(b2, 0, starts=starts)[1:]]
+            g2 = cuda_model.predict5(b2, 0, starts=starts)[1:]
+            assert all(a.data_ptr() != b.data_ptr() for a, b in zip(graphed, g2))
+            torch.cuda.synchronize()
+            assert all(torch.equal(a, b) for a, b in zip(eager, graphed)), prec
             cuda_model.cuda_graphs = False
             e2 = cuda_model.predict5(b2, 0, starts=starts)[1:]
             assert all(torch.equal(a, b) for a, b in zip(e2, g2)), prec
