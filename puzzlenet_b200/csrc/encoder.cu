@@ -998,16 +998,33 @@ __global__ void __launch_bounds__(256) centre_proj_kernel(const float* __restric
   Q[e] = __float2bfloat16_rn(fmaf(w[0], c[0], fmaf(w[1], c[1], w[2] * c[2])));
 }
 
-// the same in fp32 for the split path: Q [rows, C1]
+// the same in fp32 for the split path: Q [rows, C1].  The three xyz weights of every channel (both weight sets) are
+// staged in shared memory once per block (they sit 3 + D floats apart in the weight matrix); a thread then walks
+// consecutive (row, channel) elements, so the Q stores are coalesced and the centre is a broadcast read.
 __global__ void __launch_bounds__(256) centre_proj_f32_kernel(const float* __restrict__ centres, const float* w1a,
                                                               const float* w1b, int ldw1, int rows_per_set, int rows,
                                                               int C1, float* __restrict__ Q) {
-  const size_t e = (size_t)blockIdx.x * 256 + threadIdx.x;
-  if (e >= (size_t)rows * C1) return;
-  const int s = (int)(e / C1), k = (int)(e - (size_t)s * C1);
-  const float* w = (s / rows_per_set == 0 ? w1a : w1b) + (size_t)k * ldw1;
-  const float* c = centres + (size_t)s * 3;
-  Q[e] = fmaf(w[0], c[0], fmaf(w[1], c[1], w[2] * c[2]));
+  extern __shared__ float cp_w[];                 // [2 sets][C1][3]
+  for (int i = threadIdx.x; i < 2 * C1 * 3; i += 256) {
+    const int set = i / (C1 * 3), r = i - set * C1 * 3, k = r / 3, d = r - k * 3;
+    cp_w[i] = (set == 0 ? w1a : w1b)[(size_t)k * ldw1 + d];
+  }
+  __syncthreads();
+  const size_t total = (size_t)rows * C1;
+  for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (size_t)gridDim.x * 256) {
+    const int s = (int)(e / C1), k = (int)(e - (size_t)s * C1);
+    const float* w = cp_w + ((s / rows_per_set == 0 ? 0 : C1) + k) * 3;
+    const float* c = centres + (size_t)s * 3;
+    Q[e] = fmaf(w[0], c[0], fmaf(w[1], c[1], w[2] * c[2]));
+  }
+}
+static int launch_centre_proj_f32(const float* centres, const float* w1a, const float* w1b, int ldw1, int rows_per_set, int rows,
+                                  int C1, float* Q, cudaStream_t st) {
+  const size_t total = (size_t)rows * C1, want = (total + 255) / 256;
+  const unsigned blocks = (unsigned)(want < (size_t)kNumSMs * 8 ? want : (size_t)kNumSMs * 8);
+  centre_proj_f32_kernel<<<blocks, 256, (size_t)2 * C1 * 3 * sizeof(float), st>>>(centres, w1a, w1b, ldw1, rows_per_set, rows, C1, Q);
+  PZ_LAUNCH_CHECK();
+  return 0;
 }
 
 // ======================================================================== orchestration
@@ -1383,17 +1400,13 @@ static int encoder_forward_split(const PzEncoderWeights* w, int E, int B, const 
   prof_mark("fps1", sg, gl);
   PZ_TRY(launch_knn(s.nx1, xyz, C, S1, NPTS, KNN, o.knn1, s.knn1r, nullptr, sg));
   prof_mark("knn1", sg, gl);
-  centre_proj_f32_kernel<<<(unsigned)(((size_t)C * S1 * C1A + 255) / 256), 256, 0, sg>>>(s.nx1, wa.mlp3_w, wb.mlp3_w, 3 + D0,
-                                                                                         B * S1, C * S1, C1A, Q1);
-  PZ_LAUNCH_CHECK();
+  PZ_TRY(launch_centre_proj_f32(s.nx1, wa.mlp3_w, wb.mlp3_w, 3 + D0, B * S1, C * S1, C1A, Q1, sg));
   PZ_CUDA(cudaEventRecord(ss->join_a, sg));
   PZ_TRY(launch_fps(s.nx1, C, S1, start2, S2, o.fps2, nullptr, nx2, sg));
   prof_mark("fps2", sg, gl);
   PZ_TRY(launch_knn(nx2, s.nx1, C, S2, S1, KNN, o.knn2, s.knn2r, nullptr, sg));
   prof_mark("knn2", sg, gl);
-  centre_proj_f32_kernel<<<(unsigned)(((size_t)C * S2 * C2A + 255) / 256), 256, 0, sg>>>(nx2, wa.mlp5_w, wb.mlp5_w, 3 + C1B,
-                                                                                         B * S2, C * S2, C2A, Q2);
-  PZ_LAUNCH_CHECK();
+  PZ_TRY(launch_centre_proj_f32(nx2, wa.mlp5_w, wb.mlp5_w, 3 + C1B, B * S2, C * S2, C2A, Q2, sg));
   PZ_CUDA(cudaEventRecord(ss->join_b, sg));
 
   // ---- feature chain
@@ -2027,8 +2040,7 @@ extern "C" int pz_group_mlp_maxpool(const float* xyz, const float* feat, const f
     pack_weights_kernel<<<dim3(16, 4), 256, 0, st>>>(jobs);
     PZ_LAUNCH_CHECK();
     PZ_TRY(launch_split_planes(feat, D, (size_t)B * N, D, fh, fl, D, st));
-    centre_proj_f32_kernel<<<(unsigned)(((size_t)B * S * C1 + 255) / 256), 256, 0, st>>>(new_xyz, W1, W1, 3 + D, B * S, B * S, C1, Q);
-    PZ_LAUNCH_CHECK();
+    PZ_TRY(launch_centre_proj_f32(new_xyz, W1, W1, 3 + D, B * S, B * S, C1, Q, st));
     TcGemm g1;
     g1.X = fh; g1.Xlo = fl; g1.ldx = D; g1.W[0] = w1h; g1.Wlo[0] = w1l; g1.ldw = D; g1.bias[0] = b1; g1.M = B * N; g1.Nout = C1; g1.K = D;
     g1.Yf = P; g1.ldyf = C1; g1.xyz = xyz; g1.W1x[0] = W1; g1.ldw1x = 3 + D;
