@@ -114,21 +114,31 @@ def score_all_pairs(clouds: torch.Tensor, scorer: Callable, batch: int = 64,
 # ----------------------------------------------------------------------------- host-side greedy merge
 
 def _se3_exp_np(x: np.ndarray) -> np.ndarray:
-    """se_math/se3.py:57-80 in float64 (host-side pose composition only)."""
-    w, v = x[:3].astype(np.float64), x[3:].astype(np.float64)
-    t = np.linalg.norm(w)
-    W = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]], dtype=np.float64)
-    S = W @ W
+    """se_math/se3.py:57-80 in float64 (host-side pose composition only).  Scalar arithmetic on Python floats: the
+    31 calls of one assembly were the largest part of the host-side merge when written with 3x3 numpy temporaries."""
+    import math
+    w0, w1, w2, v0, v1, v2 = (float(t) for t in x[:6])
+    t = math.sqrt(w0 * w0 + w1 * w1 + w2 * w2)
     if abs(t) < 0.01:
         t2 = t * t
         s1 = 1 - t2 / 6 * (1 - t2 / 20 * (1 - t2 / 42))
         s2 = 0.5 * (1 - t2 / 12 * (1 - t2 / 30 * (1 - t2 / 56)))
         s3 = 1 / 6 * (1 - t2 / 20 * (1 - t2 / 42 * (1 - t2 / 72)))
     else:
-        s1, s2, s3 = np.sin(t) / t, (1 - np.cos(t)) / t ** 2, (t - np.sin(t)) / t ** 3
+        s1, s2, s3 = math.sin(t) / t, (1 - math.cos(t)) / t ** 2, (t - math.sin(t)) / t ** 3
+    # W = [[0,-w2,w1],[w2,0,-w0],[-w1,w0,0]];  S = W W = w w^T - |w|^2 I
+    W = ((0.0, -w2, w1), (w2, 0.0, -w0), (-w1, w0, 0.0))
+    ww = (w0, w1, w2)
+    n2 = t * t
+    v = (v0, v1, v2)
     g = np.eye(4)
-    g[:3, :3] = np.eye(3) + s1 * W + s2 * S
-    g[:3, 3] = (np.eye(3) + s2 * W + s3 * S) @ v
+    for r in range(3):
+        pr = 0.0
+        for c in range(3):
+            S_rc = ww[r] * ww[c] - (n2 if r == c else 0.0)
+            g[r, c] = (1.0 if r == c else 0.0) + s1 * W[r][c] + s2 * S_rc
+            pr += ((1.0 if r == c else 0.0) + s2 * W[r][c] + s3 * S_rc) * v[c]
+        g[r, 3] = pr
     return g
 
 
@@ -145,27 +155,39 @@ def greedy_assemble(n_pieces: int, pairs, rows, max_score: Optional[float] = Non
     if pairs.shape[0] != rows.shape[0]:
         raise ValueError("greedy_assemble: pairs and rows disagree in length")
     poses = np.tile(np.eye(4), (n_pieces, 1, 1))
-    comp = np.arange(n_pieces)
     merges: List[Tuple[int, int, float]] = []
     order = np.lexsort((np.arange(rows.shape[0]), rows[:, 6]))        # ascending score, ties by pair order
-    for e in order:
-        if rows[e, 7] == 0 or not np.isfinite(rows[e, 6]):
+    # the edge loop runs on plain Python lists (a numpy scalar access per edge costs more than the whole merge logic);
+    # `members[c]` lists the pieces of component c, `comp[k]` is piece k's component
+    score = rows[:, 6].tolist()
+    valid = ((rows[:, 7] != 0) & np.isfinite(rows[:, 6])).tolist()
+    pi, pj = pairs[:, 0].tolist(), pairs[:, 1].tolist()
+    comp = list(range(n_pieces))
+    members = {k: [k] for k in range(n_pieces)}
+    for e in order.tolist():
+        if not valid[e]:
             continue
-        if max_score is not None and rows[e, 6] > max_score:
+        if max_score is not None and score[e] > max_score:
             break
-        i, j = int(pairs[e, 0]), int(pairs[e, 1])
-        if comp[i] == comp[j]:
+        i, j = pi[e], pj[e]
+        ci, cj = comp[i], comp[j]
+        if ci == cj:
             continue
-        # new pose of every piece k in j's component:  T_i . g_ij . T_j^-1 . T_k
-        move = poses[i] @ _se3_exp_np(rows[e, :6]) @ np.linalg.inv(poses[j])
-        members = np.nonzero(comp == comp[j])[0]
-        for k in members:
-            poses[k] = move @ poses[k]
-        comp[members] = comp[i]
-        merges.append((i, j, float(rows[e, 6])))
+        # new pose of every piece k in j's component:  T_i . g_ij . T_j^-1 . T_k   (T_j is rigid: inverse = [R^T, -R^T t])
+        tj = poses[j]
+        tj_inv = np.eye(4)
+        tj_inv[:3, :3] = tj[:3, :3].T
+        tj_inv[:3, 3] = -tj[:3, :3].T @ tj[:3, 3]
+        move = poses[i] @ _se3_exp_np(rows[e, :6]) @ tj_inv
+        moved = members.pop(cj)
+        poses[moved] = move @ poses[moved]
+        for k in moved:
+            comp[k] = ci
+        members[ci] += moved
+        merges.append((i, j, score[e]))
         if len(merges) == n_pieces - 1:
             break
-    return poses, comp, merges
+    return poses, np.asarray(comp), merges
 
 
 def assemble(clouds: torch.Tensor, scorer: Callable, batch: int = 64, rescore: bool = True,
