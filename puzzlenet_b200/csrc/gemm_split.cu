@@ -32,8 +32,8 @@ constexpr int SG_THREADS = 13 * 32;
 constexpr uint32_t TILE16K = 128 * 128;   // one [128 rows x 64 k] fp16 SWIZZLE_128B tile
 
 // D=f32, A=B=f16 (format 0), both K-major, M=128, N=n
-__host__ __device__ constexpr uint32_t make_idesc_f16(int n) {
-  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc_f16(int n, int m = 128) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 // two floats -> packed fp16 hi pair and packed fp16 lo pair (lo = fp16(x - hi)); saturating, so no infinities
@@ -636,6 +636,283 @@ __global__ void __launch_bounds__(SG_THREADS, 1) split_gather_kernel(const TcGem
   }
 }
 
+// ---------------------------------------------------------------------------------------------- CTA-pair variant
+// Nout == 256: the two CTAs of a cluster (the two SMs of a TPC) hold one 128-channel block of the weights each and
+// execute ONE tcgen05.mma.cta_group::2 of M = 256 channels x N = 256 gathered rows per K step.  The B operand of such
+// an MMA is split between the pair -- each CTA forms relu(P - Q) for 128 of the 256 rows, in its own shared memory at
+// the same offset -- so every gathered row is fetched, transformed and written ONCE for all 256 channels (the
+// one-CTA kernel above makes two passes, one per channel block), and each SM reads half the operand bytes per MMA flop.
+// Protocol: the leader (cluster rank 0) owns the full / accumulator-empty barriers (one arrival per producer / epilogue
+// warp of BOTH CTAs, remote arrivals through mapa); the stage-empty and accumulator-full barriers exist in both CTAs and
+// are signalled by multicast tcgen05.commit.
+template <int NST>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SG_THREADS, 1) split_gather_pair_kernel(const TcGemm g) {
+  extern __shared__ __align__(1024) uint8_t sgp_smem_raw[];
+  // three stages + 128 KB of weights leave no room for an alignment pad: the dynamic shared memory of a kernel without
+  // static shared memory starts 1024-aligned; anything else must fail loudly
+  const uint32_t smem_base = smem_u32(sgp_smem_raw);
+  if ((smem_base & 1023u) != 0) __trap();
+  uint8_t* smem_gen = sgp_smem_raw;
+  constexpr int EPI = 4, PROD_THREADS = 256, ROWS = 128, NPAIR = 2 * ROWS;
+  constexpr uint32_t X_PLANE = ROWS * 128, STAGE = 2 * X_PLANE;
+  const int kblocks = g.K / KB;
+  const uint32_t w_plane = (uint32_t)kblocks * TILE16K;
+  const uint32_t stages_base = smem_base + 2 * w_plane;
+  const uint32_t bars = stages_base + NST * STAGE;
+  const uint32_t full_bar = bars, empty_bar = bars + 8 * NST, accf_bar = bars + 16 * NST, acce_bar = accf_bar + 16;
+  const uint32_t pfull_bar = acce_bar + 16;                      // leader only: stage s of the PEER is full
+  const uint32_t tmem_slot = pfull_bar + 8 * NST;
+  const uint32_t qring_s = (tmem_slot + 16 + 15) & ~15u;         // 2 x [4 groups][64 ch] fp32 Q tiles
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t crank = cluster_ctarank();
+  const int npairs = gridDim.x >> 1, pair = blockIdx.x >> 1;
+  const int nsets = (g.rows_per_wset > 0 && g.M > g.rows_per_wset) ? 2 : 1;
+  const int pairs_per_set = npairs / nsets;
+  const int wset = min(pair / pairs_per_set, nsets - 1);
+  const int rank = pair - wset * pairs_per_set;
+  const int step = (wset == nsets - 1) ? npairs - wset * pairs_per_set : pairs_per_set;
+  const int tiles_per_set = g.M / NPAIR / nsets;
+  const int tile_begin = wset * tiles_per_set, tile_end = tile_begin + tiles_per_set;
+  const __half* __restrict__ Whi = reinterpret_cast<const __half*>(g.W[wset]) + (size_t)crank * 128 * g.ldw;
+  const __half* __restrict__ Wlo = reinterpret_cast<const __half*>(g.Wlo[wset]) + (size_t)crank * 128 * g.ldw;
+  const float* __restrict__ bias = g.bias[wset];
+
+  if (tid == 0) {
+    for (int s = 0; s < NST; ++s) {
+      mbar_init(full_bar + 8 * s, PROD_THREADS);
+      mbar_init(empty_bar + 8 * s, 1);
+      mbar_init(pfull_bar + 8 * s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(accf_bar + 8 * b, 1);
+      mbar_init(acce_bar + 8 * b, 2 * EPI);          // used in the leader only
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == EPI) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  {  // resident weights of this CTA's channel block: both planes, swizzled [128 ch x 64 k] tiles per k-block
+    const int chunks = kblocks * 128 * 8;
+    for (int id = tid; id < chunks; id += SG_THREADS) {
+      const int c = id & 7, r = (id >> 3) & 127, kb = id >> 10;
+      const size_t off = (size_t)r * g.ldw + kb * KB + c * 8;
+      *reinterpret_cast<uint4*>(smem_gen + (size_t)kb * TILE16K + sw128(r, c)) = *reinterpret_cast<const uint4*>(Whi + off);
+      *reinterpret_cast<uint4*>(smem_gen + w_plane + (size_t)kb * TILE16K + sw128(r, c)) = *reinterpret_cast<const uint4*>(Wlo + off);
+    }
+    fence_proxy_async();
+  }
+  tc_fence_before();
+  cluster_sync_all();        // barriers initialised, TMEM allocated and weights resident in BOTH CTAs
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+
+  if (warp > EPI) {
+    // =========================================================== producers (both CTAs): 128 of the 256 rows each
+    constexpr int CH = ROWS / 32, HC = CH / 2, QV = (ROWS / 32) * 16;
+    const int pt = tid - (EPI + 1) * 32, gc = pt & 7, r0 = pt >> 3;
+    int my_tiles = 0;
+    for (int t = tile_begin + rank; t < tile_end; t += step) ++my_tiles;
+    const int jobs = my_tiles * kblocks;
+    const float* __restrict__ P = g.Xf;
+    const float* __restrict__ Q = g.Qf;
+    float4 buf[2][HC][2];
+    int ids[CH], ids_n[CH];
+    float4 qpre = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto tile_row0 = [&](int ti) { return (tile_begin + rank + ti * step) * NPAIR + (int)crank * ROWS; };
+    auto q_fetch = [&](int jt) {
+      const int ti = jt / kblocks, kb = jt - ti * kblocks;
+      const int group0 = tile_row0(ti) >> 5;
+      if (pt < QV) qpre = __ldg(reinterpret_cast<const float4*>(Q + (size_t)(group0 + (pt >> 4)) * g.K + kb * KB + (pt & 15) * 4));
+    };
+    // Q tile layout in the ring: per group 256 B = [first float4 of the 8 channel octets][second float4 of the 8 octets],
+    // so that the 8 distinct addresses of a warp's LDS.128 are 128 contiguous bytes (one wavefront, no bank conflict)
+    auto q_commit = [&](int slot) {
+      if (pt < QV)
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(qring_s + slot * (QV * 16) + (pt >> 4) * 256 + (pt & 1) * 128 + ((pt & 15) >> 1) * 16),
+                     "f"(qpre.x), "f"(qpre.y), "f"(qpre.z), "f"(qpre.w) : "memory");
+    };
+    auto fetch_ids = [&](int ti, int (&dst)[CH]) {
+      const int row0 = tile_row0(ti);
+#pragma unroll
+      for (int i = 0; i < CH; ++i) dst[i] = g.rows[row0 + r0 + 32 * i];
+    };
+    auto load_half = [&](int h, int kb, bool next_tile) {
+#pragma unroll
+      for (int i = 0; i < HC; ++i) {
+        const int id = next_tile ? ids_n[h * HC + i] : ids[h * HC + i];
+        const float4* src = reinterpret_cast<const float4*>(P + (size_t)id * g.ldx + kb * KB + gc * 8);
+        buf[h][i][0] = __ldg(src);
+        buf[h][i][1] = __ldg(src + 1);
+      }
+    };
+    auto store_half = [&](int h, int slot, uint32_t st_addr) {
+#pragma unroll
+      for (int i = 0; i < HC; ++i) {
+        const int ci = h * HC + i, r = r0 + 32 * ci;
+        float4 q0, q1;
+        const uint32_t qa = qring_s + slot * (QV * 16) + ci * 256 + gc * 16;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(q0.x), "=f"(q0.y), "=f"(q0.z), "=f"(q0.w) : "r"(qa));
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(q1.x), "=f"(q1.y), "=f"(q1.z), "=f"(q1.w) : "r"(qa + 128));
+        const float4 p0 = buf[h][i][0], p1 = buf[h][i][1];
+        uint4 oh, ol;
+        split2(fmaxf(p0.x - q0.x, 0.f), fmaxf(p0.y - q0.y, 0.f), oh.x, ol.x);
+        split2(fmaxf(p0.z - q0.z, 0.f), fmaxf(p0.w - q0.w, 0.f), oh.y, ol.y);
+        split2(fmaxf(p1.x - q1.x, 0.f), fmaxf(p1.y - q1.y, 0.f), oh.z, ol.z);
+        split2(fmaxf(p1.z - q1.z, 0.f), fmaxf(p1.w - q1.w, 0.f), oh.w, ol.w);
+        const uint32_t off = sw128(r, gc);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st_addr + off), "r"(oh.x), "r"(oh.y), "r"(oh.z), "r"(oh.w) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st_addr + X_PLANE + off), "r"(ol.x), "r"(ol.y), "r"(ol.z), "r"(ol.w) : "memory");
+      }
+    };
+    if (jobs > 0) {
+      fetch_ids(0, ids);
+      if (my_tiles > 1) fetch_ids(1, ids_n);
+      load_half(0, 0, false);
+      load_half(1, 0, false);
+      q_fetch(0);
+      q_commit(0);
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      if (jobs > 1) q_fetch(1);
+    }
+    for (int j = 0; j < jobs; ++j) {
+      const int ti = j / kblocks, kb = j - ti * kblocks;
+      const uint32_t s = (uint32_t)j % NST, ph = ((uint32_t)j / NST) & 1;
+      const uint32_t st_addr = stages_base + s * STAGE;
+      const bool more = j + 1 < jobs;
+      const int nkb = (kb + 1 == kblocks) ? 0 : kb + 1;
+      const bool new_tile = more && nkb == 0;
+      mbar_wait(empty_bar + 8 * s, ph ^ 1);
+      store_half(0, j & 1, st_addr);
+      if (more) load_half(0, nkb, new_tile);
+      store_half(1, j & 1, st_addr);
+      fence_proxy_async();
+      mbar_arrive(full_bar + 8 * s);
+      if (more) load_half(1, nkb, new_tile);
+      if (new_tile) {
+#pragma unroll
+        for (int i = 0; i < CH; ++i) ids[i] = ids_n[i];
+        if (ti + 2 < my_tiles) fetch_ids(ti + 2, ids_n);
+      }
+      if (more) {
+        q_commit((j + 1) & 1);
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        if (j + 2 < jobs) q_fetch(j + 2);
+      }
+    }
+  } else if (warp == EPI) {
+    // =========================================================== MMA issuer: one thread of the LEADER CTA
+    if (crank == 0 && lane == 0) {
+      const uint32_t idesc = make_idesc_f16(NPAIR, 256);
+      uint32_t it = 0, tcn = 0;
+      for (int t = tile_begin + rank; t < tile_end; t += step, ++tcn) {
+        const uint32_t buf = tcn & 1, aph = (tcn >> 1) & 1;
+        mbar_wait_cluster(acce_bar + 8 * buf, aph ^ 1);
+        tc_fence_after();
+        for (int kb = 0; kb < kblocks; ++kb, ++it) {
+          const uint32_t s = it % NST, ph = (it / NST) & 1;
+          mbar_wait(full_bar + 8 * s, ph);
+          mbar_wait_cluster(pfull_bar + 8 * s, ph);
+          tc_fence_after();
+          const uint32_t st_addr = stages_base + s * STAGE;
+          const uint64_t a_hi = make_desc(smem_base + (uint32_t)kb * TILE16K), a_lo = make_desc(smem_base + w_plane + (uint32_t)kb * TILE16K);
+          const uint64_t b_hi = make_desc(st_addr), b_lo = make_desc(st_addr + X_PLANE);
+#pragma unroll
+          for (int k4 = 0; k4 < KB / 16; ++k4) {
+            const uint32_t d = tmem_base + buf * NPAIR;
+            umma_f16_pair(d, a_hi + 2 * k4, b_hi + 2 * k4, idesc, (kb | k4) != 0);
+            umma_f16_pair(d, a_hi + 2 * k4, b_lo + 2 * k4, idesc, 1);
+            umma_f16_pair(d, a_lo + 2 * k4, b_hi + 2 * k4, idesc, 1);
+          }
+          umma_commit_pair(empty_bar + 8 * s);
+        }
+        umma_commit_pair(accf_bar + 8 * buf);
+      }
+    } else if (crank == 1 && lane == 0) {
+      // relay of the peer CTA: stage s of this CTA is full -> one arrival on the leader's peer-full barrier
+      const uint32_t pfull_remote = mapa_shared(pfull_bar, 0);
+      int my_tiles = 0;
+      for (int t = tile_begin + rank; t < tile_end; t += step) ++my_tiles;
+      const uint32_t jobs = (uint32_t)(my_tiles * kblocks);
+      for (uint32_t it = 0; it < jobs; ++it) {
+        const uint32_t s = it % NST, ph = (it / NST) & 1;
+        mbar_wait(full_bar + 8 * s, ph);
+        mbar_arrive_cluster(pfull_remote + 8 * s);
+      }
+    }
+  } else {
+    // =========================================================== epilogue (both CTAs): thread = channel of this CTA's
+    // block, max over the 8 groups of 32 rows of the pair tile
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    const int ch = (int)crank * 128 + warp * 32 + lane;
+    const float bv = bias ? bias[ch] : 0.f;
+    __half* Ybhi = reinterpret_cast<__half*>(g.Yb);
+    __half* Yblo = reinterpret_cast<__half*>(g.Yblo);
+    const uint32_t acce_remote = mapa_shared(acce_bar, 0);
+    uint32_t tcn = 0;
+    for (int t = tile_begin + rank; t < tile_end; t += step, ++tcn) {
+      const int row0 = t * NPAIR;
+      const uint32_t buf = tcn & 1, aph = (tcn >> 1) & 1;
+      mbar_wait(accf_bar + 8 * buf, aph);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + lane_base + buf * NPAIR;
+#pragma unroll 1
+      for (int c64 = 0; c64 < NPAIR / 64; ++c64) {
+        float v[64];
+        tmem_ld64(t_addr + c64 * 64, v);
+#pragma unroll
+        for (int w = 32; w >= 2; w >>= 1) {
+#pragma unroll
+          for (int i = 0; i < w / 2; ++i) {
+            v[i] = fmaxf(v[i], v[i + w / 2]);
+            v[32 + i] = fmaxf(v[32 + i], v[32 + i + w / 2]);
+          }
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float x = v[32 * h] + bv;
+          if (g.relu) x = fmaxf(x, 0.f);
+          const size_t grow = (size_t)(row0 >> 5) + c64 * 2 + h;
+          if (g.Yf) g.Yf[grow * g.ldyf + ch] = x;
+          if (Ybhi) {
+            const __half hi = __float2half_rn(x);
+            Ybhi[grow * g.ldyb + ch] = hi;
+            Yblo[grow * g.ldyb + ch] = __float2half_rn(x - __half2float(hi));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(acce_remote + 8 * buf);
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();        // the leader's MMAs read the peer's shared memory: nobody leaves before everybody is done
+  if (warp == EPI) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+template <int NST>
+static int split_gather_pair_launch(const TcGemm& g, cudaStream_t st) {
+  const int kblocks = g.K / KB;
+  const size_t smem = 2 * (size_t)kblocks * TILE16K + (size_t)NST * 2 * 128 * 128 + 8 * (3 * NST + 4) + 32 +
+                      2 * (size_t)4 * 64 * sizeof(float);
+  PZ_REQUIRE(smem <= 232448, PZ_ERR_UNSUPPORTED, "split_gather (pair): needs %zu B of shared memory (K=%d)", smem, g.K);
+  auto kern = split_gather_pair_kernel<NST>;
+  PZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int nsets = (g.rows_per_wset > 0 && g.M > g.rows_per_wset) ? 2 : 1;
+  const int tiles_per_set = g.M / 256 / nsets;
+  int per = (kNumSMs / 2) / nsets;                 // CTA pairs per weight set
+  if (per > tiles_per_set) per = tiles_per_set;
+  if (per < 1) per = 1;
+  kern<<<2 * per * nsets, SG_THREADS, smem, st>>>(g);
+  PZ_LAUNCH_CHECK();
+  return 0;
+}
+
 template <int ROWS, int NST>
 static int split_gather_launch(const TcGemm& g, cudaStream_t st) {
   const int kblocks = g.K / KB;
@@ -672,6 +949,11 @@ int launch_split_gather(const TcGemm& g, cudaStream_t st) {
     return split_gather_launch<256, 2>(g, st);
   }
   PZ_REQUIRE(g.M % (128 * nsets) == 0, PZ_ERR_UNSUPPORTED, "split_gather: M=%d must be a multiple of %d", g.M, 128 * nsets);
+  // 256 output channels: one CTA pair per tile (cta_group::2), every gathered row formed once for both channel blocks
+  static const bool no_pair = getenv("PZ_SG_NO_PAIR") != nullptr;   // A/B hook
+  static const int pair_nst = getenv("PZ_SG_PAIR_NST") ? atoi(getenv("PZ_SG_PAIR_NST")) : 3;
+  if (g.Nout == 256 && g.M % (256 * nsets) == 0 && !no_pair)
+    return pair_nst == 2 ? split_gather_pair_launch<2>(g, st) : split_gather_pair_launch<3>(g, st);
   return split_gather_launch<128, 2>(g, st);
 }
 
