@@ -360,6 +360,365 @@ static int split_rowgemm_launch(const TcGemm& g, cudaStream_t st) {
   return 0;
 }
 
+// ============================================================================================== row-major GEMM, CTA pair
+// The same GEMM on a CTA pair (tcgen05.mma.cta_group::2, M = 256 rows): every CTA streams the X planes of ITS 128 rows
+// and holds HALF of the output channels' weights -- the pair shares the B operand, so a CTA moves half the weight bytes
+// per flop.  RESIDENT (Nout == NCOLS and both planes of the CTA's weight half fit beside the stages: the attention
+// projections, P1, P2): the weights are loaded once per CTA and only X streams (32 KB per k-block instead of 96 KB, the
+// compulsory read of X); otherwise (the encoder tail) a stage carries X + the CTA's weight half of the column tile
+// (64 KB).  Barrier protocol as in split_gather_pair_kernel: CTA-local full barriers, two relay threads in the peer CTA
+// (stage full / accumulator drained) forward them to the leader with cluster-scope arrives, multicast commits back.
+constexpr int RP_THREADS = 14 * 32;   // 8 epilogue warps, MMA issuer (leader) / stage relay (peer), accumulator relay, 4 producer warps
+
+template <int NCOLS, int NST, bool RESIDENT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RP_THREADS, 1) split_rowgemm_pair_kernel(const TcGemm g) {
+  extern __shared__ __align__(1024) uint8_t srp_smem_raw[];
+  const uint32_t smem_base = smem_u32(srp_smem_raw);
+  if ((smem_base & 1023u) != 0) __trap();   // no alignment pad is budgeted (see split_gather_pair_kernel)
+  uint8_t* smem_gen = srp_smem_raw;
+  constexpr int EPI = 8, PROD_THREADS = 128, ROWS = 128, HALF = NCOLS / 2;
+  constexpr uint32_t STAGE_X = 2 * TILE16K, W_TILE = HALF * 128, STAGE = STAGE_X + (RESIDENT ? 0u : 2 * W_TILE);
+  const int kblocks = g.K / KB;
+  const uint32_t resident = RESIDENT ? (uint32_t)kblocks * 2 * W_TILE : 0u;   // per k-block [hi tile][lo tile]
+  const uint32_t stages_base = smem_base + resident;
+  const uint32_t bars = stages_base + NST * STAGE;
+  const uint32_t full_bar = bars, empty_bar = bars + 8 * NST, pfull_bar = bars + 16 * NST;
+  const uint32_t accf_bar = bars + 24 * NST, acce_bar = accf_bar + 16, pacce_bar = acce_bar + 16;
+  const uint32_t tmem_slot = pacce_bar + 16;
+  const uint32_t chan_s = (tmem_slot + 16 + 15) & ~15u;
+  const bool has_xyz = g.xyz != nullptr;
+  // per channel: (w1x, w1y, w1z, bias) when the layer has an xyz term, else the bias alone
+  float4* chan4 = reinterpret_cast<float4*>(smem_gen + (chan_s - smem_base));
+  float* chan1 = reinterpret_cast<float*>(chan4);
+  int* colmax = reinterpret_cast<int*>(smem_gen + (chan_s - smem_base) + (has_xyz ? NCOLS * 16 : NCOLS * 4));
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t crank = cluster_ctarank();
+  const int npairs = gridDim.x >> 1, pair = blockIdx.x >> 1;
+  const int nsets = (g.rows_per_wset > 0 && g.M > g.rows_per_wset) ? 2 : 1;
+  const int row_tiles = g.M / (2 * ROWS), col_tiles = g.Nout / NCOLS;
+  const int tiles_per_set = (row_tiles / nsets) * col_tiles;
+  const int pairs_per_set = npairs / nsets;
+  const int wset = min(pair / pairs_per_set, nsets - 1);
+  const int rank_in_set = pair - wset * pairs_per_set;
+  const int step = (wset == nsets - 1) ? npairs - wset * pairs_per_set : pairs_per_set;
+  const int tile_begin = wset * tiles_per_set;
+  const __half* __restrict__ Whi = reinterpret_cast<const __half*>(g.W[wset]);
+  const __half* __restrict__ Wlo = reinterpret_cast<const __half*>(g.Wlo[wset]);
+  const __half* __restrict__ Xhi = reinterpret_cast<const __half*>(g.X);
+  const __half* __restrict__ Xlo = reinterpret_cast<const __half*>(g.Xlo);
+  const float* __restrict__ bias = g.bias[wset];
+
+  if (tid == 0) {
+    for (int s = 0; s < NST; ++s) {
+      mbar_init(full_bar + 8 * s, PROD_THREADS);
+      mbar_init(empty_bar + 8 * s, 1);
+      mbar_init(pfull_bar + 8 * s, 1);     // leader: the peer's stage s is full
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(accf_bar + 8 * b, 1);
+      mbar_init(acce_bar + 8 * b, EPI * 32);
+      mbar_init(pacce_bar + 8 * b, 1);     // leader: the peer has drained accumulator b
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == EPI) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  if (RESIDENT) {   // this CTA's half of the output channels, both planes, swizzled [HALF ch x 64 k] tiles per k-block
+    const int chunks = kblocks * HALF * 8;
+    for (int id = tid; id < chunks; id += RP_THREADS) {
+      const int c = id & 7, r = (id >> 3) % HALF, kb = id / (HALF * 8);
+      const size_t off = (size_t)((int)crank * HALF + r) * g.ldw + kb * KB + c * 8;
+      *reinterpret_cast<uint4*>(smem_gen + (size_t)kb * 2 * W_TILE + sw128(r, c)) = *reinterpret_cast<const uint4*>(Whi + off);
+      *reinterpret_cast<uint4*>(smem_gen + (size_t)kb * 2 * W_TILE + W_TILE + sw128(r, c)) = *reinterpret_cast<const uint4*>(Wlo + off);
+    }
+    fence_proxy_async();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+
+  if (warp >= EPI + 2) {
+    // ================================================= producers: this CTA's X planes (+ its weight half when streamed)
+    const int pt = tid - (EPI + 2) * 32;
+    uint32_t issued = 0, arrived = 0;
+    for (int t = tile_begin + rank_in_set; t < tile_begin + tiles_per_set; t += step) {
+      const int ct = t % col_tiles, rt = t / col_tiles;
+      const int row0 = rt * 2 * ROWS + (int)crank * ROWS, col0 = ct * NCOLS + (int)crank * HALF;
+      for (int kb = 0; kb < kblocks; ++kb) {
+        const uint32_t s = issued % NST, ph = (issued / NST) & 1;
+        mbar_wait(empty_bar + 8 * s, ph ^ 1);
+        const uint32_t st_addr = stages_base + s * STAGE;
+        for (int id = pt; id < ROWS * 8; id += PROD_THREADS) {
+          const int c = id & 7, r = id >> 3;
+          const size_t off = (size_t)(row0 + r) * g.ldx + kb * KB + c * 8;
+          cp_async16(st_addr + sw128(r, c), Xhi + off);
+          cp_async16(st_addr + TILE16K + sw128(r, c), Xlo + off);
+        }
+        if (!RESIDENT) {
+          for (int id = pt; id < HALF * 8; id += PROD_THREADS) {
+            const int c = id & 7, r = id >> 3;
+            const size_t off = (size_t)(col0 + r) * g.ldw + kb * KB + c * 8;
+            cp_async16(st_addr + STAGE_X + sw128(r, c), Whi + off);
+            cp_async16(st_addr + STAGE_X + W_TILE + sw128(r, c), Wlo + off);
+          }
+        }
+        cp_async_commit();
+        ++issued;
+        if (issued - arrived > (NST > 2 ? 2u : 1u)) {
+          if (NST > 2) cp_async_wait<2>(); else cp_async_wait<1>();
+          fence_proxy_async();
+          mbar_arrive(full_bar + 8 * (arrived % NST));
+          ++arrived;
+        }
+      }
+    }
+    cp_async_wait<0>();
+    fence_proxy_async();
+    while (arrived < issued) {
+      mbar_arrive(full_bar + 8 * (arrived % NST));
+      ++arrived;
+    }
+  } else if (warp == EPI) {
+    if (crank == 0 && lane == 0) {
+      // ================================================= MMA issuer: one thread of the leader CTA
+      const uint32_t idesc = make_idesc_f16(NCOLS, 256);
+      uint32_t it = 0, tcn = 0;
+      for (int t = tile_begin + rank_in_set; t < tile_begin + tiles_per_set; t += step, ++tcn) {
+        const uint32_t buf = tcn & 1, aph = (tcn >> 1) & 1;
+        mbar_wait(acce_bar + 8 * buf, aph ^ 1);
+        mbar_wait_cluster(pacce_bar + 8 * buf, aph ^ 1);
+        tc_fence_after();
+        for (int kb = 0; kb < kblocks; ++kb, ++it) {
+          const uint32_t s = it % NST, ph = (it / NST) & 1;
+          mbar_wait(full_bar + 8 * s, ph);
+          mbar_wait_cluster(pfull_bar + 8 * s, ph);
+          tc_fence_after();
+          const uint32_t st_addr = stages_base + s * STAGE;
+          const uint32_t w_addr = RESIDENT ? smem_base + (uint32_t)kb * 2 * W_TILE : st_addr + STAGE_X;
+          const uint64_t a_hi = make_desc(st_addr), a_lo = make_desc(st_addr + TILE16K);
+          const uint64_t b_hi = make_desc(w_addr), b_lo = make_desc(w_addr + W_TILE);
+#pragma unroll
+          for (int k4 = 0; k4 < KB / 16; ++k4) {
+            const uint32_t d = tmem_base + buf * NCOLS;
+            umma_f16_pair(d, a_hi + 2 * k4, b_hi + 2 * k4, idesc, (kb | k4) != 0);
+            umma_f16_pair(d, a_hi + 2 * k4, b_lo + 2 * k4, idesc, 1);
+            umma_f16_pair(d, a_lo + 2 * k4, b_hi + 2 * k4, idesc, 1);
+          }
+          umma_commit_pair(empty_bar + 8 * s);
+        }
+        umma_commit_pair(accf_bar + 8 * buf);
+      }
+    } else if (crank == 1 && lane == 0) {
+      // ================================================= stage relay of the peer CTA
+      const uint32_t pfull_remote = mapa_shared(pfull_bar, 0);
+      uint32_t jobs = 0;
+      for (int t = tile_begin + rank_in_set; t < tile_begin + tiles_per_set; t += step) jobs += (uint32_t)kblocks;
+      for (uint32_t it = 0; it < jobs; ++it) {
+        const uint32_t s = it % NST, ph = (it / NST) & 1;
+        mbar_wait(full_bar + 8 * s, ph);
+        mbar_arrive_cluster(pfull_remote + 8 * s);
+      }
+    }
+  } else if (warp == EPI + 1) {
+    if (crank == 1 && lane == 0) {
+      // ================================================= accumulator relay of the peer CTA
+      const uint32_t pacce_remote = mapa_shared(pacce_bar, 0);
+      uint32_t tcn = 0;
+      for (int t = tile_begin + rank_in_set; t < tile_begin + tiles_per_set; t += step, ++tcn) {
+        const uint32_t buf = tcn & 1, aph = (tcn >> 1) & 1;
+        mbar_wait(acce_bar + 8 * buf, aph);
+        mbar_arrive_cluster(pacce_remote + 8 * buf);
+      }
+    }
+  } else {
+    // ================================================= epilogue: thread = row of this CTA's 128, 32 channels per TMEM load
+    const int quarter = warp & 3, half = warp >> 2;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    const bool relu = g.relu != 0;
+    const int nvalid = g.n_valid > 0 ? g.n_valid : g.Nout;
+    __half* Ybhi = reinterpret_cast<__half*>(g.Yb);
+    __half* Yblo = reinterpret_cast<__half*>(g.Yblo);
+    __half* YThi = reinterpret_cast<__half*>(g.YT);
+    __half* YTlo = reinterpret_cast<__half*>(g.YTlo);
+    const __half* Rhi = reinterpret_cast<const __half*>(g.Rb);
+    const __half* Rlo = reinterpret_cast<const __half*>(g.Rblo);
+    uint32_t tcn = 0;
+    int staged_ct = -1;
+    for (int t = tile_begin + rank_in_set; t < tile_begin + tiles_per_set; t += step, ++tcn) {
+      const int ct = t % col_tiles, rt = (t / col_tiles) * 2 + (int)crank;   // rt: this CTA's 128-row tile
+      const int col0 = ct * NCOLS;
+      const size_t row = (size_t)rt * ROWS + quarter * 32 + lane;
+      if (ct != staged_ct) {
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        for (int c = tid; c < NCOLS; c += EPI * 32) {
+          const int ch = col0 + c;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ch < nvalid) {
+            if (bias) v.w = bias[ch];
+            if (has_xyz) {
+              const float* wp = g.W1x[wset] + (size_t)ch * g.ldw1x;
+              v.x = wp[0]; v.y = wp[1]; v.z = wp[2];
+            }
+          }
+          if (has_xyz) chan4[c] = v; else chan1[c] = v.w;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        staged_ct = ct;
+      }
+      float px = 0.f, py = 0.f, pz = 0.f;
+      if (has_xyz) {
+        const float* p = g.xyz + row * 3;
+        px = p[0]; py = p[1]; pz = p[2];
+      }
+      const float* rbp = g.rowbias ? g.rowbias + (row / g.rb_rows) * g.rb_ld : nullptr;
+      const uint32_t buf = tcn & 1, aph = (tcn >> 1) & 1;
+      mbar_wait(accf_bar + 8 * buf, aph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c32 = half; c32 < NCOLS / 32; c32 += 2) {
+        const int cb = col0 + c32 * 32;
+        if (cb >= nvalid) break;
+        uint4 rh[4], rl[4];
+        if (Rhi) {
+          const uint4* ph = reinterpret_cast<const uint4*>(Rhi + row * g.ldrb + cb);
+          const uint4* pl = reinterpret_cast<const uint4*>(Rlo + row * g.ldrb + cb);
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) { rh[q4] = ph[q4]; rl[q4] = pl[q4]; }
+        }
+        float v[32];
+        tmem_ld32(tmem_base + lane_base + buf * NCOLS + c32 * 32, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if (has_xyz) {
+            const float4 cc = chan4[c32 * 32 + i];
+            v[i] = fmaf(cc.x, px, fmaf(cc.y, py, fmaf(cc.z, pz, v[i] + cc.w)));
+          } else {
+            v[i] += chan1[c32 * 32 + i];
+          }
+        }
+        if (rbp) {
+#pragma unroll
+          for (int q4 = 0; q4 < 8; ++q4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(rbp + cb + q4 * 4);
+            v[q4 * 4] += b4.x; v[q4 * 4 + 1] += b4.y; v[q4 * 4 + 2] += b4.z; v[q4 * 4 + 3] += b4.w;
+          }
+        }
+        if (relu) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+        }
+        if (Rhi) {
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const uint32_t* hp = reinterpret_cast<const uint32_t*>(&rh[q4]);
+            const uint32_t* lp = reinterpret_cast<const uint32_t*>(&rl[q4]);
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+              const float2 f = join2(hp[h], lp[h]);
+              v[q4 * 8 + 2 * h] += f.x;
+              v[q4 * 8 + 2 * h + 1] += f.y;
+            }
+          }
+        }
+        if (g.Rf) {
+          const float4* rp = reinterpret_cast<const float4*>(g.Rf + row * g.ldrf + cb);
+#pragma unroll
+          for (int q4 = 0; q4 < 8; ++q4) {
+            const float4 b4 = rp[q4];
+            v[q4 * 4] += b4.x; v[q4 * 4 + 1] += b4.y; v[q4 * 4 + 2] += b4.z; v[q4 * 4 + 3] += b4.w;
+          }
+        }
+        if (g.Ymax) {
+          // column maxima over the tile's 128 rows: one redux.sync.max per channel over the warp's 32 rows on the
+          // order-preserving integer image of the float, lane i keeps channel i; the four row quarters meet in smem
+          int keep = 0;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int o = __float_as_int(v[i]);
+            const int m = __reduce_max_sync(0xffffffffu, o >= 0 ? o : o ^ 0x7fffffff);
+            if (lane == i) keep = m;
+          }
+          colmax[quarter * NCOLS + c32 * 32 + lane] = keep;
+        }
+        if (YThi) {
+          // transposed planes, per block of t_rows rows (one cloud): YT[(blk * Nout + ch) * t_rows + row_in_blk];
+          // the 32 lanes of a warp are 32 consecutive rows -> 64 contiguous bytes per channel and plane
+          const size_t blk = row / g.t_rows, rin = row - blk * g.t_rows;
+          __half* dh = YThi + (blk * g.Nout + cb) * g.t_rows + rin;
+          __half* dl = YTlo + (blk * g.Nout + cb) * g.t_rows + rin;
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            uint32_t hi, lo;
+            split2(v[i], v[i + 1], hi, lo);
+            const __half2 h2 = *reinterpret_cast<const __half2*>(&hi), l2 = *reinterpret_cast<const __half2*>(&lo);
+            dh[(size_t)i * g.t_rows] = __low2half(h2);
+            dh[(size_t)(i + 1) * g.t_rows] = __high2half(h2);
+            dl[(size_t)i * g.t_rows] = __low2half(l2);
+            dl[(size_t)(i + 1) * g.t_rows] = __high2half(l2);
+          }
+        }
+        if (Ybhi) {
+          uint4* yh = reinterpret_cast<uint4*>(Ybhi + row * g.ldyb + cb);
+          uint4* yl = reinterpret_cast<uint4*>(Yblo + row * g.ldyb + cb);
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            uint4 oh, ol;
+            split2(v[q4 * 8 + 0], v[q4 * 8 + 1], oh.x, ol.x);
+            split2(v[q4 * 8 + 2], v[q4 * 8 + 3], oh.y, ol.y);
+            split2(v[q4 * 8 + 4], v[q4 * 8 + 5], oh.z, ol.z);
+            split2(v[q4 * 8 + 6], v[q4 * 8 + 7], oh.w, ol.w);
+            yh[q4] = oh;
+            yl[q4] = ol;
+          }
+        }
+        if (g.Yf) {
+          float4* yp = reinterpret_cast<float4*>(g.Yf + row * g.ldyf + cb);
+#pragma unroll
+          for (int q4 = 0; q4 < 8; ++q4) yp[q4] = make_float4(v[q4 * 4], v[q4 * 4 + 1], v[q4 * 4 + 2], v[q4 * 4 + 3]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(acce_bar + 8 * buf);
+      if (g.Ymax) {   // Ymax[row tile, ch] = max over the tile's rows (the caller folds the tiles of a cloud)
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        for (int c = tid; c < NCOLS && col0 + c < nvalid; c += EPI * 32) {
+          const int m = max(max(colmax[c], colmax[NCOLS + c]), max(colmax[2 * NCOLS + c], colmax[3 * NCOLS + c]));
+          g.Ymax[(size_t)rt * g.ldmax + col0 + c] = __int_as_float(m >= 0 ? m : m ^ 0x7fffffff);
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");   // colmax is rewritten by the next tile
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == EPI) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+template <int NCOLS, int NST, bool RESIDENT>
+static int split_rowgemm_pair_launch(const TcGemm& g, cudaStream_t st) {
+  const int kblocks = g.K / KB;
+  const size_t stage = 2 * TILE16K + (RESIDENT ? 0 : NCOLS * 128);
+  const size_t smem = (RESIDENT ? (size_t)kblocks * NCOLS * 128 : 0) + (size_t)NST * stage + 8 * (3 * NST + 6) + 48 +
+                      (size_t)NCOLS * (g.xyz ? 16 : 4) + (g.Ymax ? (size_t)NCOLS * 16 : 0);
+  PZ_REQUIRE(smem <= 232448, PZ_ERR_UNSUPPORTED, "split_rowgemm (pair): needs %zu B of shared memory", smem);
+  auto kern = split_rowgemm_pair_kernel<NCOLS, NST, RESIDENT>;
+  PZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int nsets = (g.rows_per_wset > 0 && g.M > g.rows_per_wset) ? 2 : 1;
+  const int tiles_per_set = (g.M / 256 / nsets) * (g.Nout / NCOLS);
+  int per = (kNumSMs / 2) / nsets;
+  if (per > tiles_per_set) per = tiles_per_set;
+  if (per < 1) per = 1;
+  kern<<<2 * per * nsets, RP_THREADS, smem, st>>>(g);
+  PZ_LAUNCH_CHECK();
+  return 0;
+}
+
 // Row-major split GEMM.  Operands: X / Xlo [M, K] and W / Wlo [Nout, K] fp16 planes (same leading dimensions);
 // outputs: Yf fp32 and/or Yb + Yblo fp16 planes and/or YT + YTlo transposed planes and/or Ymax [M / 128, ldmax] = the
 // column maxima of every 128-row tile; residual Rf (fp32) or Rb + Rblo.
@@ -386,6 +745,15 @@ int launch_split_rowgemm(const TcGemm& g, cudaStream_t st) {
   if (g.YT) PZ_REQUIRE(g.t_rows % 128 == 0, PZ_ERR_ARG, "split_rowgemm: t_rows must be a multiple of 128");
   // 256-column tiles halve the re-reads of X but leave at most two tiles per CTA at M = 32768 (the epilogue of a tile then
   // has little to overlap with); PZ_SPLIT_NCOLS=128 forces 128-column tiles everywhere (A/B hook)
+  // CTA-pair kernels (cta_group::2) whenever the rows tile by 256 per weight set
+  static const bool no_pair = getenv("PZ_RG_NO_PAIR") != nullptr;   // A/B hook
+  if (!no_pair && g.M % (256 * nsets) == 0) {
+    const size_t small = 8 * (3 * 4 + 6) + 48 + 256 * (size_t)(g.xyz ? 16 : 4);   // barriers + per-channel constants (upper bound)
+    const size_t resident256 = (size_t)(g.K / KB) * 256 * 128, resident128 = (size_t)(g.K / KB) * 128 * 128;
+    if (g.Nout == 256 && !g.Ymax && resident256 + 3 * 32768 + small <= 232448) return split_rowgemm_pair_launch<256, 3, true>(g, st);
+    if (g.Nout == 128 && !g.Ymax && resident128 + 4 * 32768 + small <= 232448) return split_rowgemm_pair_launch<128, 4, true>(g, st);
+    if (g.Nout % 256 == 0) return split_rowgemm_pair_launch<256, 3, false>(g, st);
+  }
   static const bool narrow = getenv("PZ_SPLIT_NCOLS") && atoi(getenv("PZ_SPLIT_NCOLS")) == 128;
   if (g.Nout % 256 == 0 && !(narrow && !g.Ymax)) return split_rowgemm_launch<256, 2>(g, st);
   return split_rowgemm_launch<128, 3>(g, st);

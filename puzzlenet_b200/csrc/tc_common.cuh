@@ -117,24 +117,15 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// arrive on an mbarrier of any CTA of the cluster (address from mapa_shared); release at cluster scope
+// arrive on an mbarrier of any CTA of the cluster (address from mapa_shared).  Default semantics (release, CTA scope), as
+// CUTLASS's ClusterBarrier::arrive(cta_id) issues it: a cluster-scope release compiles to MEMBAR.ALL.GPU + ERRBAR (~1 us
+// per arrival, measured), and a cluster-scope acquire on the waiting side to CCTL.IVALL (an L1 invalidate per wait).  What
+// crosses the CTAs here is shared memory written before a CTA-local mbarrier completed and read by the tensor core only
+// after the remote arrival has been observed.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
-// bounded wait with cluster-scope acquire (the arrivals may come from the peer CTA)
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
-  uint32_t ok = 0;
-  for (uint32_t spin = 0; !ok; ++spin) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (!ok && spin > (1u << 24)) __trap();
-  }
-}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) { mbar_wait(bar, parity); }
 __device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                               uint32_t accumulate) {
   asm volatile(
