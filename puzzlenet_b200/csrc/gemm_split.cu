@@ -384,13 +384,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RP_THREADS, 1) split
   const uint32_t bars = stages_base + NST * STAGE;
   const uint32_t full_bar = bars, empty_bar = bars + 8 * NST, pfull_bar = bars + 16 * NST;
   const uint32_t accf_bar = bars + 24 * NST, acce_bar = accf_bar + 16, pacce_bar = acce_bar + 16;
-  const uint32_t tmem_slot = pacce_bar + 16;
+  const uint32_t w_bar = pacce_bar + 16;                        // resident weights of THIS CTA have landed
+  const uint32_t tmem_slot = w_bar + 8;
   const uint32_t chan_s = (tmem_slot + 16 + 15) & ~15u;
   const bool has_xyz = g.xyz != nullptr;
   // per channel: (w1x, w1y, w1z, bias) when the layer has an xyz term, else the bias alone
   float4* chan4 = reinterpret_cast<float4*>(smem_gen + (chan_s - smem_base));
   float* chan1 = reinterpret_cast<float*>(chan4);
-  int* colmax = reinterpret_cast<int*>(smem_gen + (chan_s - smem_base) + (has_xyz ? NCOLS * 16 : NCOLS * 4));
+  const uint32_t colmax_s = chan_s + (has_xyz ? NCOLS * 16 : NCOLS * 4);
+  int* colmax = reinterpret_cast<int*>(smem_gen + (colmax_s - smem_base));
+  const uint32_t stage_s = (colmax_s + (g.Ymax ? NCOLS * 16 : 0) + 127) & ~127u;   // 8 x 4 KB epilogue staging tiles (when something is stored / a residual read)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t crank = cluster_ctarank();
@@ -420,25 +423,31 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RP_THREADS, 1) split
       mbar_init(acce_bar + 8 * b, EPI * 32);
       mbar_init(pacce_bar + 8 * b, 1);     // leader: the peer has drained accumulator b
     }
+    mbar_init(w_bar, (EPI + 2) * 32);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == EPI) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
-  if (RESIDENT) {   // this CTA's half of the output channels, both planes, swizzled [HALF ch x 64 k] tiles per k-block
+  tc_fence_before();
+  cluster_sync_all();        // barriers initialised and TMEM allocated in both CTAs
+  tc_fence_after();
+  if (RESIDENT && warp < EPI + 2) {
+    // this CTA's half of the output channels, both planes, swizzled [HALF ch x 64 k] tiles per k-block: fetched with
+    // cp.async by the ten non-producer warps (everything in flight at once) WHILE the producers already stream X
     const int chunks = kblocks * HALF * 8;
-    for (int id = tid; id < chunks; id += RP_THREADS) {
+    for (int id = tid; id < chunks; id += (EPI + 2) * 32) {
       const int c = id & 7, r = (id >> 3) % HALF, kb = id / (HALF * 8);
       const size_t off = (size_t)((int)crank * HALF + r) * g.ldw + kb * KB + c * 8;
-      *reinterpret_cast<uint4*>(smem_gen + (size_t)kb * 2 * W_TILE + sw128(r, c)) = *reinterpret_cast<const uint4*>(Whi + off);
-      *reinterpret_cast<uint4*>(smem_gen + (size_t)kb * 2 * W_TILE + W_TILE + sw128(r, c)) = *reinterpret_cast<const uint4*>(Wlo + off);
+      cp_async16(smem_base + (uint32_t)kb * 2 * W_TILE + sw128(r, c), Whi + off);
+      cp_async16(smem_base + (uint32_t)kb * 2 * W_TILE + W_TILE + sw128(r, c), Wlo + off);
     }
+    cp_async_commit();
+    cp_async_wait<0>();
     fence_proxy_async();
+    mbar_arrive(w_bar);
   }
-  tc_fence_before();
-  cluster_sync_all();
-  tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
   if (warp >= EPI + 2) {
@@ -487,6 +496,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RP_THREADS, 1) split
       // ================================================= MMA issuer: one thread of the leader CTA
       const uint32_t idesc = make_idesc_f16(NCOLS, 256);
       uint32_t it = 0, tcn = 0;
+      if (RESIDENT) mbar_wait(w_bar, 0);
       for (int t = tile_begin + rank_in_set; t < tile_begin + tiles_per_set; t += step, ++tcn) {
         const uint32_t buf = tcn & 1, aph = (tcn >> 1) & 1;
         mbar_wait(acce_bar + 8 * buf, aph ^ 1);
@@ -517,6 +527,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RP_THREADS, 1) split
       const uint32_t pfull_remote = mapa_shared(pfull_bar, 0);
       uint32_t jobs = 0;
       for (int t = tile_begin + rank_in_set; t < tile_begin + tiles_per_set; t += step) jobs += (uint32_t)kblocks;
+      if (RESIDENT) mbar_wait(w_bar, 0);   // the first forwarded stage also vouches for this CTA's weights
       for (uint32_t it = 0; it < jobs; ++it) {
         const uint32_t s = it % NST, ph = (it / NST) & 1;
         mbar_wait(full_bar + 8 * s, ph);
@@ -535,7 +546,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RP_THREADS, 1) split
       }
     }
   } else {
-    // ================================================= epilogue: thread = row of this CTA's 128, 32 channels per TMEM load
+    // ================================================= epilogue: thread = row of this CTA's 128 (its TMEM lane), 32
+    // channels per TMEM load.  Global traffic is COALESCED through a 4 KB per-warp staging tile: a thread owns a row, so
+    // direct 16-byte accesses touch 32 cache lines per warp instruction (measured: 46 us per launch against a 16 us HBM
+    // floor, L1 wavefronts 48 %); instead the warp's [32 rows x 32 ch] block goes through shared memory (XOR-swizzled
+    // 16-byte pieces, conflict-free both ways) and leaves / arrives as whole 64- or 128-byte row segments.  The residual
+    // block of the NEXT chunk is prefetched into registers while the current one is finished.
     const int quarter = warp & 3, half = warp >> 2;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     const bool relu = g.relu != 0;
@@ -546,12 +562,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RP_THREADS, 1) split
     __half* YTlo = reinterpret_cast<__half*>(g.YTlo);
     const __half* Rhi = reinterpret_cast<const __half*>(g.Rb);
     const __half* Rlo = reinterpret_cast<const __half*>(g.Rblo);
+    const uint32_t stg = stage_s + (uint32_t)warp * 4096;     // this warp's staging tile
+    // 16-bit tiles: two planes of [32 rows][64 B]; piece p (8 channels) of row r sits at r*64 + ((p ^ ((r>>1)&3)) << 4)
+    const int cr = lane >> 2, cp = lane & 3;                    // coalesced role: row 8j + cr, piece cp
+    const uint32_t own16 = stg + (uint32_t)lane * 64, sw_own16 = (uint32_t)((lane >> 1) & 3);
+    // fp32 tiles: [32 rows][128 B]; piece p (4 channels) of row r at r*128 + ((p ^ (r&7)) << 4)
+    const int fr = lane >> 3, fp = lane & 7;                    // coalesced role: row 4j + fr, piece fp
     uint32_t tcn = 0;
     int staged_ct = -1;
     for (int t = tile_begin + rank_in_set; t < tile_begin + tiles_per_set; t += step, ++tcn) {
       const int ct = t % col_tiles, rt = (t / col_tiles) * 2 + (int)crank;   // rt: this CTA's 128-row tile
       const int col0 = ct * NCOLS;
-      const size_t row = (size_t)rt * ROWS + quarter * 32 + lane;
+      const size_t rowbase = (size_t)rt * ROWS + quarter * 32;
+      const size_t row = rowbase + lane;
       if (ct != staged_ct) {
         asm volatile("bar.sync 1, 256;" ::: "memory");
         for (int c = tid; c < NCOLS; c += EPI * 32) {
@@ -575,6 +598,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RP_THREADS, 1) split
         px = p[0]; py = p[1]; pz = p[2];
       }
       const float* rbp = g.rowbias ? g.rowbias + (row / g.rb_rows) * g.rb_ld : nullptr;
+      uint4 pre[8];
+      auto r_prefetch = [&](int cb) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const size_t off = (rowbase + 8 * j + cr) * g.ldrb + cb + cp * 8;
+          pre[j] = *reinterpret_cast<const uint4*>(Rhi + off);
+          pre[4 + j] = *reinterpret_cast<const uint4*>(Rlo + off);
+        }
+      };
+      if (Rhi && col0 + half * 32 < nvalid) r_prefetch(col0 + half * 32);
       const uint32_t buf = tcn & 1, aph = (tcn >> 1) & 1;
       mbar_wait(accf_bar + 8 * buf, aph);
       tc_fence_after();
@@ -582,23 +615,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RP_THREADS, 1) split
       for (int c32 = half; c32 < NCOLS / 32; c32 += 2) {
         const int cb = col0 + c32 * 32;
         if (cb >= nvalid) break;
-        uint4 rh[4], rl[4];
-        if (Rhi) {
-          const uint4* ph = reinterpret_cast<const uint4*>(Rhi + row * g.ldrb + cb);
-          const uint4* pl = reinterpret_cast<const uint4*>(Rlo + row * g.ldrb + cb);
+        if (Rhi) {   // the prefetched residual block -> staging (coalesced role)
 #pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) { rh[q4] = ph[q4]; rl[q4] = pl[q4]; }
+          for (int j = 0; j < 4; ++j) {
+            const int r = 8 * j + cr;
+            const uint32_t a = stg + (uint32_t)r * 64 + (uint32_t)((cp ^ ((r >> 1) & 3)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pre[j].x), "r"(pre[j].y), "r"(pre[j].z), "r"(pre[j].w) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a + 2048), "r"(pre[4 + j].x), "r"(pre[4 + j].y), "r"(pre[4 + j].z), "r"(pre[4 + j].w) : "memory");
+          }
+          __syncwarp();
         }
         float v[32];
         tmem_ld32(tmem_base + lane_base + buf * NCOLS + c32 * 32, v);
+        if (has_xyz) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          if (has_xyz) {
+          for (int i = 0; i < 32; ++i) {
             const float4 cc = chan4[c32 * 32 + i];
             v[i] = fmaf(cc.x, px, fmaf(cc.y, py, fmaf(cc.z, pz, v[i] + cc.w)));
-          } else {
-            v[i] += chan1[c32 * 32 + i];
           }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] += chan1[c32 * 32 + i];
         }
         if (rbp) {
 #pragma unroll
@@ -611,18 +648,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RP_THREADS, 1) split
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
         }
-        if (Rhi) {
+        if (Rhi) {   // own row of the staged residual block
 #pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            const uint32_t* hp = reinterpret_cast<const uint32_t*>(&rh[q4]);
-            const uint32_t* lp = reinterpret_cast<const uint32_t*>(&rl[q4]);
+          for (int p4 = 0; p4 < 4; ++p4) {
+            uint4 h, l;
+            const uint32_t a = own16 + (((uint32_t)p4 ^ sw_own16) << 4);
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(h.x), "=r"(h.y), "=r"(h.z), "=r"(h.w) : "r"(a));
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(l.x), "=r"(l.y), "=r"(l.z), "=r"(l.w) : "r"(a + 2048));
+            const uint32_t* hp = reinterpret_cast<const uint32_t*>(&h);
+            const uint32_t* lp = reinterpret_cast<const uint32_t*>(&l);
 #pragma unroll
-            for (int h = 0; h < 4; ++h) {
-              const float2 f = join2(hp[h], lp[h]);
-              v[q4 * 8 + 2 * h] += f.x;
-              v[q4 * 8 + 2 * h + 1] += f.y;
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = join2(hp[e], lp[e]);
+              v[p4 * 8 + 2 * e] += f.x;
+              v[p4 * 8 + 2 * e + 1] += f.y;
             }
           }
+          __syncwarp();
+          if (c32 + 2 < NCOLS / 32 && cb + 64 < nvalid) r_prefetch(cb + 64);   // next chunk of this warp
         }
         if (g.Rf) {
           const float4* rp = reinterpret_cast<const float4*>(g.Rf + row * g.ldrf + cb);
@@ -633,8 +676,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RP_THREADS, 1) split
           }
         }
         if (g.Ymax) {
-          // column maxima over the tile's 128 rows: one redux.sync.max per channel over the warp's 32 rows on the
-          // order-preserving integer image of the float, lane i keeps channel i; the four row quarters meet in smem
           int keep = 0;
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
@@ -645,8 +686,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RP_THREADS, 1) split
           colmax[quarter * NCOLS + c32 * 32 + lane] = keep;
         }
         if (YThi) {
-          // transposed planes, per block of t_rows rows (one cloud): YT[(blk * Nout + ch) * t_rows + row_in_blk];
-          // the 32 lanes of a warp are 32 consecutive rows -> 64 contiguous bytes per channel and plane
           const size_t blk = row / g.t_rows, rin = row - blk * g.t_rows;
           __half* dh = YThi + (blk * g.Nout + cb) * g.t_rows + rin;
           __half* dl = YTlo + (blk * g.Nout + cb) * g.t_rows + rin;
@@ -662,23 +701,47 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RP_THREADS, 1) split
           }
         }
         if (Ybhi) {
-          uint4* yh = reinterpret_cast<uint4*>(Ybhi + row * g.ldyb + cb);
-          uint4* yl = reinterpret_cast<uint4*>(Yblo + row * g.ldyb + cb);
 #pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
+          for (int p4 = 0; p4 < 4; ++p4) {
             uint4 oh, ol;
-            split2(v[q4 * 8 + 0], v[q4 * 8 + 1], oh.x, ol.x);
-            split2(v[q4 * 8 + 2], v[q4 * 8 + 3], oh.y, ol.y);
-            split2(v[q4 * 8 + 4], v[q4 * 8 + 5], oh.z, ol.z);
-            split2(v[q4 * 8 + 6], v[q4 * 8 + 7], oh.w, ol.w);
-            yh[q4] = oh;
-            yl[q4] = ol;
+            split2(v[p4 * 8 + 0], v[p4 * 8 + 1], oh.x, ol.x);
+            split2(v[p4 * 8 + 2], v[p4 * 8 + 3], oh.y, ol.y);
+            split2(v[p4 * 8 + 4], v[p4 * 8 + 5], oh.z, ol.z);
+            split2(v[p4 * 8 + 6], v[p4 * 8 + 7], oh.w, ol.w);
+            const uint32_t a = own16 + (((uint32_t)p4 ^ sw_own16) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(oh.x), "r"(oh.y), "r"(oh.z), "r"(oh.w) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a + 2048), "r"(ol.x), "r"(ol.y), "r"(ol.z), "r"(ol.w) : "memory");
           }
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int r = 8 * j + cr;
+            const uint32_t a = stg + (uint32_t)r * 64 + (uint32_t)((cp ^ ((r >> 1) & 3)) << 4);
+            uint4 h, l;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(h.x), "=r"(h.y), "=r"(h.z), "=r"(h.w) : "r"(a));
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(l.x), "=r"(l.y), "=r"(l.z), "=r"(l.w) : "r"(a + 2048));
+            const size_t off = (rowbase + r) * g.ldyb + cb + cp * 8;
+            *reinterpret_cast<uint4*>(Ybhi + off) = h;
+            *reinterpret_cast<uint4*>(Yblo + off) = l;
+          }
+          __syncwarp();
         }
         if (g.Yf) {
-          float4* yp = reinterpret_cast<float4*>(g.Yf + row * g.ldyf + cb);
 #pragma unroll
-          for (int q4 = 0; q4 < 8; ++q4) yp[q4] = make_float4(v[q4 * 4], v[q4 * 4 + 1], v[q4 * 4 + 2], v[q4 * 4 + 3]);
+          for (int p8 = 0; p8 < 8; ++p8) {
+            const uint32_t a = stg + (uint32_t)lane * 128 + (uint32_t)((p8 ^ (lane & 7)) << 4);
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v[p8 * 4]), "f"(v[p8 * 4 + 1]), "f"(v[p8 * 4 + 2]), "f"(v[p8 * 4 + 3]) : "memory");
+          }
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int r = 4 * j + fr;
+            const uint32_t a = stg + (uint32_t)r * 128 + (uint32_t)((fp ^ (r & 7)) << 4);
+            float4 o;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w) : "r"(a));
+            *reinterpret_cast<float4*>(g.Yf + (rowbase + r) * g.ldyf + cb + fp * 4) = o;
+          }
+          __syncwarp();
         }
       }
       tc_fence_before();
@@ -700,12 +763,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RP_THREADS, 1) split
   }
 }
 
+static size_t split_rowgemm_pair_smem(const TcGemm& g, int ncols, int nst, bool resident) {
+  const size_t stage = 2 * TILE16K + (resident ? 0 : (size_t)ncols * 128);
+  const bool staging = g.Yb || g.Yf || g.Rb;
+  return (resident ? (size_t)(g.K / KB) * ncols * 128 : 0) + (size_t)nst * stage + 8 * (3 * nst + 7) + 48 +
+         (size_t)ncols * (g.xyz ? 16 : 4) + (g.Ymax ? (size_t)ncols * 16 : 0) + 128 + (staging ? 8 * 4096 : 0);
+}
+
 template <int NCOLS, int NST, bool RESIDENT>
 static int split_rowgemm_pair_launch(const TcGemm& g, cudaStream_t st) {
-  const int kblocks = g.K / KB;
-  const size_t stage = 2 * TILE16K + (RESIDENT ? 0 : NCOLS * 128);
-  const size_t smem = (RESIDENT ? (size_t)kblocks * NCOLS * 128 : 0) + (size_t)NST * stage + 8 * (3 * NST + 6) + 48 +
-                      (size_t)NCOLS * (g.xyz ? 16 : 4) + (g.Ymax ? (size_t)NCOLS * 16 : 0);
+  const size_t smem = split_rowgemm_pair_smem(g, NCOLS, NST, RESIDENT);
   PZ_REQUIRE(smem <= 232448, PZ_ERR_UNSUPPORTED, "split_rowgemm (pair): needs %zu B of shared memory", smem);
   auto kern = split_rowgemm_pair_kernel<NCOLS, NST, RESIDENT>;
   PZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -748,11 +815,18 @@ int launch_split_rowgemm(const TcGemm& g, cudaStream_t st) {
   // CTA-pair kernels (cta_group::2) whenever the rows tile by 256 per weight set
   static const bool no_pair = getenv("PZ_RG_NO_PAIR") != nullptr;   // A/B hook
   if (!no_pair && g.M % (256 * nsets) == 0) {
-    const size_t small = 8 * (3 * 4 + 6) + 48 + 256 * (size_t)(g.xyz ? 16 : 4);   // barriers + per-channel constants (upper bound)
-    const size_t resident256 = (size_t)(g.K / KB) * 256 * 128, resident128 = (size_t)(g.K / KB) * 128 * 128;
-    if (g.Nout == 256 && !g.Ymax && resident256 + 3 * 32768 + small <= 232448) return split_rowgemm_pair_launch<256, 3, true>(g, st);
-    if (g.Nout == 128 && !g.Ymax && resident128 + 4 * 32768 + small <= 232448) return split_rowgemm_pair_launch<128, 4, true>(g, st);
-    if (g.Nout % 256 == 0) return split_rowgemm_pair_launch<256, 3, false>(g, st);
+    if (g.Nout == 256 && !g.Ymax) {
+      if (split_rowgemm_pair_smem(g, 256, 3, true) <= 232448) return split_rowgemm_pair_launch<256, 3, true>(g, st);
+      if (split_rowgemm_pair_smem(g, 256, 2, true) <= 232448) return split_rowgemm_pair_launch<256, 2, true>(g, st);
+    }
+    if (g.Nout == 128 && !g.Ymax) {
+      if (split_rowgemm_pair_smem(g, 128, 4, true) <= 232448) return split_rowgemm_pair_launch<128, 4, true>(g, st);
+      if (split_rowgemm_pair_smem(g, 128, 2, true) <= 232448) return split_rowgemm_pair_launch<128, 2, true>(g, st);
+    }
+    if (g.Nout % 256 == 0) {
+      if (split_rowgemm_pair_smem(g, 256, 3, false) <= 232448) return split_rowgemm_pair_launch<256, 3, false>(g, st);
+      return split_rowgemm_pair_launch<256, 2, false>(g, st);
+    }
   }
   static const bool narrow = getenv("PZ_SPLIT_NCOLS") && atoi(getenv("PZ_SPLIT_NCOLS")) == 128;
   if (g.Nout % 256 == 0 && !(narrow && !g.Ymax)) return split_rowgemm_launch<256, 2>(g, st);
