@@ -18,6 +18,7 @@
 //                          32 neighbours in the epilogue (pointnet_util.py:123-130 + model5_b.py:452-454, :459-461)
 #include <cuda_fp16.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "pz_common.cuh"
 #include "tc_common.cuh"
@@ -370,6 +371,17 @@ static int split_rowgemm_launch(const TcGemm& g, cudaStream_t st) {
 // (stage full / accumulator drained) forward them to the leader with cluster-scope arrives, multicast commits back.
 constexpr int RP_THREADS = 14 * 32;   // 8 epilogue warps, MMA issuer (leader) / stage relay (peer), accumulator relay, 4 producer warps
 
+// timeline stamps of the first CTA pair (diagnostics, pz_profile_attention_timeline): globaltimer in ns, slot base
+// 2048 + 512 * cluster rank; layout: 0 entry, 1 after cluster sync, 2 weights landed, 16+2j / 17+2j producer issue /
+// arrive of job j, 128+j MMAs of job j issued, 192+2t / 193+2t epilogue of tile t sees the accumulator / is done, 3 exit
+__device__ __forceinline__ void rp_stamp(long long* prof, uint32_t crank, int slot) {
+  if (prof != nullptr && blockIdx.x < 2) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    prof[2048 + 512 * (int)crank + slot] = (long long)t;
+  }
+}
+
 template <int NCOLS, int NST, bool RESIDENT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RP_THREADS, 1) split_rowgemm_pair_kernel(const TcGemm g) {
   extern __shared__ __align__(1024) uint8_t srp_smem_raw[];
@@ -397,6 +409,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RP_THREADS, 1) split
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t crank = cluster_ctarank();
+  if (tid == 0) rp_stamp(g.prof, crank, 0);
   const int npairs = gridDim.x >> 1, pair = blockIdx.x >> 1;
   const int nsets = (g.rows_per_wset > 0 && g.M > g.rows_per_wset) ? 2 : 1;
   const int row_tiles = g.M / (2 * ROWS), col_tiles = g.Nout / NCOLS;
@@ -433,6 +446,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RP_THREADS, 1) split
   tc_fence_before();
   cluster_sync_all();        // barriers initialised and TMEM allocated in both CTAs
   tc_fence_after();
+  if (tid == 0) rp_stamp(g.prof, crank, 1);
   if (RESIDENT && warp < EPI + 2) {
     // this CTA's half of the output channels, both planes, swizzled [HALF ch x 64 k] tiles per k-block: fetched with
     // cp.async by the ten non-producer warps (everything in flight at once) WHILE the producers already stream X
@@ -461,6 +475,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RP_THREADS, 1) split
         const uint32_t s = issued % NST, ph = (issued / NST) & 1;
         mbar_wait(empty_bar + 8 * s, ph ^ 1);
         const uint32_t st_addr = stages_base + s * STAGE;
+        if (pt == 0 && issued < 48) rp_stamp(g.prof, crank, 16 + 2 * (int)issued);
         for (int id = pt; id < ROWS * 8; id += PROD_THREADS) {
           const int c = id & 7, r = id >> 3;
           const size_t off = (size_t)(row0 + r) * g.ldx + kb * KB + c * 8;
@@ -481,6 +496,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RP_THREADS, 1) split
           if (NST > 2) cp_async_wait<2>(); else cp_async_wait<1>();
           fence_proxy_async();
           mbar_arrive(full_bar + 8 * (arrived % NST));
+          if (pt == 0 && arrived < 48) rp_stamp(g.prof, crank, 17 + 2 * (int)arrived);
           ++arrived;
         }
       }
@@ -497,6 +513,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RP_THREADS, 1) split
       const uint32_t idesc = make_idesc_f16(NCOLS, 256);
       uint32_t it = 0, tcn = 0;
       if (RESIDENT) mbar_wait(w_bar, 0);
+      rp_stamp(g.prof, crank, 2);
       for (int t = tile_begin + rank_in_set; t < tile_begin + tiles_per_set; t += step, ++tcn) {
         const uint32_t buf = tcn & 1, aph = (tcn >> 1) & 1;
         mbar_wait(acce_bar + 8 * buf, aph ^ 1);
@@ -519,6 +536,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RP_THREADS, 1) split
             umma_f16_pair(d, a_lo + 2 * k4, b_hi + 2 * k4, idesc, 1);
           }
           umma_commit_pair(empty_bar + 8 * s);
+          if (it < 64) rp_stamp(g.prof, crank, 128 + (int)it);
         }
         umma_commit_pair(accf_bar + 8 * buf);
       }
@@ -611,6 +629,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RP_THREADS, 1) split
       const uint32_t buf = tcn & 1, aph = (tcn >> 1) & 1;
       mbar_wait(accf_bar + 8 * buf, aph);
       tc_fence_after();
+      if (tid == 0 && tcn < 32) rp_stamp(g.prof, crank, 192 + 2 * (int)tcn);
 #pragma unroll 1
       for (int c32 = half; c32 < NCOLS / 32; c32 += 2) {
         const int cb = col0 + c32 * 32;
@@ -746,6 +765,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RP_THREADS, 1) split
       }
       tc_fence_before();
       mbar_arrive(acce_bar + 8 * buf);
+      if (tid == 0 && tcn < 32) rp_stamp(g.prof, crank, 193 + 2 * (int)tcn);
       if (g.Ymax) {   // Ymax[row tile, ch] = max over the tile's rows (the caller folds the tiles of a cloud)
         asm volatile("bar.sync 1, 256;" ::: "memory");
         for (int c = tid; c < NCOLS && col0 + c < nvalid; c += EPI * 32) {
@@ -758,6 +778,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RP_THREADS, 1) split
   }
   tc_fence_before();
   cluster_sync_all();
+  if (tid == 0) rp_stamp(g.prof, crank, 3);
   if (warp == EPI) {
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
@@ -776,12 +797,20 @@ static int split_rowgemm_pair_launch(const TcGemm& g, cudaStream_t st) {
   PZ_REQUIRE(smem <= 232448, PZ_ERR_UNSUPPORTED, "split_rowgemm (pair): needs %zu B of shared memory", smem);
   auto kern = split_rowgemm_pair_kernel<NCOLS, NST, RESIDENT>;
   PZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  TcGemm gd = g;
+  static const char* tl_sel = getenv("PZ_RG_TIMELINE");   // "outproj" | "qk" | "vt" | "p1" | "tail": which launch stamps
+  gd.prof = nullptr;
+  if (tl_sel) {
+    const bool hit = (!strcmp(tl_sel, "outproj") && g.Rb) || (!strcmp(tl_sel, "qk") && g.Nout == 128 && g.K == 256) ||
+                     (!strcmp(tl_sel, "vt") && g.YT) || (!strcmp(tl_sel, "p1") && g.K == 64) || (!strcmp(tl_sel, "tail") && g.Ymax);
+    if (hit) gd.prof = kernel_timeline_buffer(2048 + 1024);
+  }
   const int nsets = (g.rows_per_wset > 0 && g.M > g.rows_per_wset) ? 2 : 1;
   const int tiles_per_set = (g.M / 256 / nsets) * (g.Nout / NCOLS);
   int per = (kNumSMs / 2) / nsets;
   if (per > tiles_per_set) per = tiles_per_set;
   if (per < 1) per = 1;
-  kern<<<2 * per * nsets, RP_THREADS, smem, st>>>(g);
+  kern<<<2 * per * nsets, RP_THREADS, smem, st>>>(gd);
   PZ_LAUNCH_CHECK();
   return 0;
 }
