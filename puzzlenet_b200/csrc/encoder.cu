@@ -101,6 +101,12 @@ __device__ __forceinline__ void stem_mma(float (&d)[4], const uint32_t (&a)[4], 
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+__device__ __forceinline__ void stem_mma_f16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+               "{%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
 // 128-point tiles per CTA of the stem / boundary-head kernels (the tiles of one CTA belong to one cloud: reps | 8)
 constexpr int HD_REPS = 4;
 static int head_reps() {
@@ -119,11 +125,15 @@ constexpr size_t STEM_TC_SMEM = 4 * 32 * STEM_WS * sizeof(float) + 64 * sizeof(f
 // product (h = hi + lo, W = hi + lo; hi*hi + hi*lo + lo*hi, error ~2^-17) because x_feature is an output and feeds both
 // the grouped MLP and the boundary heads, BN + ReLU on the accumulator fragments, and the [32 points x 64] tile of each warp leaves through shared memory as one
 // contiguous 8 KB (fp32) + 4 KB (bf16) block.  The fp32 path keeps stem_kernel (FFMA, 1e-4 parity).
+// F16 (split path): the halves are fp16 (11 + 11 mantissa bits: x_feature to ~1e-6), W2's hi | lo image is built from
+// the fp32 weights by the CTA itself, and the 16-bit outputs are the fp16 hi / lo PLANES of x_feature (out_b = hi plane,
+// out_lo = lo plane) that the split row GEMM of layer 1 consumes.
+template <bool F16>
 __global__ void __launch_bounds__(128) stem_tc_kernel(const float* __restrict__ xyz, StemW wa, StemW wb,
                                                       const __nv_bfloat16* __restrict__ w2img_a,
                                                       const __nv_bfloat16* __restrict__ w2img_b,
                                                       int clouds_per_set, int reps, float* __restrict__ out,
-                                                      __nv_bfloat16* __restrict__ out_b) {
+                                                      __nv_bfloat16* __restrict__ out_b, __half* __restrict__ out_lo) {
   constexpr int WS = STEM_WS;   // padded row strides: conflict-free fragment loads / stores
   extern __shared__ __align__(16) uint8_t stem_smem[];
   float* stage_all = reinterpret_cast<float*>(stem_smem);                               // [4][32 * WS]
@@ -133,7 +143,15 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const float* __restrict__ 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
   const int cloud = (int)(((size_t)blockIdx.x * reps * 128) / NPTS);   // uniform per block (128 reps | 1024)
   const StemW& w = (cloud / clouds_per_set) == 0 ? wa : wb;
-  {   // W2 hi | lo images ([2][64, WS] bf16, written by the weight pack): a straight 16-byte copy
+  if (F16) {   // W2 hi | lo fp16 images from the fp32 weights ([64 out][64 in] row-major)
+    __half* w2h = reinterpret_cast<__half*>(w2b);
+    for (int i = tid; i < 64 * 64; i += 128) {
+      const float v = w.w2[i];
+      const __half hi = __float2half_rn(v);
+      w2h[(i >> 6) * WS + (i & 63)] = hi;
+      w2h[64 * WS + (i >> 6) * WS + (i & 63)] = __float2half_rn(v - __half2float(hi));
+    }
+  } else {   // W2 hi | lo images ([2][64, WS] bf16, written by the weight pack): a straight 16-byte copy
     const uint4* src = reinterpret_cast<const uint4*>((cloud / clouds_per_set) == 0 ? w2img_a : w2img_b);
     uint4* dst = reinterpret_cast<uint4*>(w2b);
     for (int i = tid; i < 2 * 64 * WS / 8; i += 128) dst[i] = src[i];
@@ -173,11 +191,19 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const float* __restrict__ 
         vA = fmaf(wA.x, x[j], vA); vA = fmaf(wA.y, y[j], vA); vA = fmaf(wA.z, z[j], vA);
         vB = fmaf(wB.x, x[j], vB); vB = fmaf(wB.y, y[j], vB); vB = fmaf(wB.z, z[j], vB);
         const float hA = fmaxf(fmaf(vA, a1[j], c1[j]), 0.f), hB = fmaxf(fmaf(vB, a1[j], c1[j]), 0.f);
-        const __nv_bfloat162 hh = __floats2bfloat162_rn(hA, hB);
-        const float2 hf = __bfloat1622float2(hh);
-        const __nv_bfloat162 hl = __floats2bfloat162_rn(hA - hf.x, hB - hf.y);
-        af[j >> 1][kt][(j & 1) + 2 * h2] = *reinterpret_cast<const uint32_t*>(&hh);
-        al[j >> 1][kt][(j & 1) + 2 * h2] = *reinterpret_cast<const uint32_t*>(&hl);
+        if (F16) {
+          const __half2 hh = __floats2half2_rn(hA, hB);
+          const float2 hf = __half22float2(hh);
+          const __half2 hl = __floats2half2_rn(hA - hf.x, hB - hf.y);
+          af[j >> 1][kt][(j & 1) + 2 * h2] = *reinterpret_cast<const uint32_t*>(&hh);
+          al[j >> 1][kt][(j & 1) + 2 * h2] = *reinterpret_cast<const uint32_t*>(&hl);
+        } else {
+          const __nv_bfloat162 hh = __floats2bfloat162_rn(hA, hB);
+          const float2 hf = __bfloat1622float2(hh);
+          const __nv_bfloat162 hl = __floats2bfloat162_rn(hA - hf.x, hB - hf.y);
+          af[j >> 1][kt][(j & 1) + 2 * h2] = *reinterpret_cast<const uint32_t*>(&hh);
+          al[j >> 1][kt][(j & 1) + 2 * h2] = *reinterpret_cast<const uint32_t*>(&hl);
+        }
       }
     }
   }
@@ -197,9 +223,15 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const float* __restrict__ 
       const uint32_t l0 = *reinterpret_cast<const uint32_t*>(bp + 64 * WS), l1 = *reinterpret_cast<const uint32_t*>(bp + 64 * WS + 8);
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
-        stem_mma(acc[mt][nt], al[mt][kt], b0, b1);   // small terms first
-        stem_mma(acc[mt][nt], af[mt][kt], l0, l1);
-        stem_mma(acc[mt][nt], af[mt][kt], b0, b1);
+        if (F16) {
+          stem_mma_f16(acc[mt][nt], al[mt][kt], b0, b1);   // small terms first
+          stem_mma_f16(acc[mt][nt], af[mt][kt], l0, l1);
+          stem_mma_f16(acc[mt][nt], af[mt][kt], b0, b1);
+        } else {
+          stem_mma(acc[mt][nt], al[mt][kt], b0, b1);
+          stem_mma(acc[mt][nt], af[mt][kt], l0, l1);
+          stem_mma(acc[mt][nt], af[mt][kt], b0, b1);
+        }
       }
     }
   }
@@ -228,7 +260,28 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const float* __restrict__ 
     const int idx = it * 32 + lane, row = idx >> 4, c4 = idx & 15;
     *reinterpret_cast<float4*>(ot + idx * 4) = *reinterpret_cast<const float4*>(st + row * WS + c4 * 4);
   }
-  if (out_b) {
+  if (F16) {
+    uint4* oh = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(out_b) + (p0 + warp * 32) * 64);
+    uint4* ol = reinterpret_cast<uint4*>(out_lo + (p0 + warp * 32) * 64);
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int idx = it * 32 + lane, row = idx >> 3, c8 = idx & 7;
+      const float4 v0 = *reinterpret_cast<const float4*>(st + row * WS + c8 * 8);
+      const float4 v1 = *reinterpret_cast<const float4*>(st + row * WS + c8 * 8 + 4);
+      const float f[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+      uint32_t hw[4], lw[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const __half2 hh = __floats2half2_rn(f[2 * e], f[2 * e + 1]);
+        const float2 hf = __half22float2(hh);
+        const __half2 hl = __floats2half2_rn(f[2 * e] - hf.x, f[2 * e + 1] - hf.y);
+        hw[e] = *reinterpret_cast<const uint32_t*>(&hh);
+        lw[e] = *reinterpret_cast<const uint32_t*>(&hl);
+      }
+      oh[idx] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+      ol[idx] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+    }
+  } else if (out_b) {
     __nv_bfloat16* ob = out_b + (p0 + warp * 32) * 64;
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
@@ -1183,9 +1236,9 @@ static int encoder_forward_bf16(const PzEncoderWeights* w, int E, int B, const f
   static const bool stem_fp32 = getenv("PZ_STEM_FP32") && getenv("PZ_STEM_FP32")[0] == '1';   // A/B hook
   if (stem_fp32) stem_kernel<<<C * NPTS / 128, 128, 0, st>>>(xyz, stem_of(wa), stem_of(wb), B, xfeat, s.xfeat_b, nullptr, nullptr);
   else {
-    PZ_CUDA(cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STEM_TC_SMEM));
-    stem_tc_kernel<<<C * NPTS / (128 * head_reps()), 128, STEM_TC_SMEM, st>>>(xyz, stem_of(wa), stem_of(wb), wpa + WP_STEM,
-                                                                              wpb + WP_STEM, B, head_reps(), xfeat, s.xfeat_b);
+    PZ_CUDA(cudaFuncSetAttribute(stem_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STEM_TC_SMEM));
+    stem_tc_kernel<false><<<C * NPTS / (128 * head_reps()), 128, STEM_TC_SMEM, st>>>(xyz, stem_of(wa), stem_of(wb), wpa + WP_STEM,
+                                                                              wpb + WP_STEM, B, head_reps(), xfeat, s.xfeat_b, nullptr);
   }
   PZ_LAUNCH_CHECK();
   prof_mark("stem", st);
@@ -1410,12 +1463,21 @@ static int encoder_forward_split(const PzEncoderWeights* w, int E, int B, const 
   PZ_CUDA(cudaEventRecord(ss->join_b, sg));
 
   // ---- feature chain
-  static const bool stem_planes = getenv("PZ_STEM_PLANES") && getenv("PZ_STEM_PLANES")[0] == '1';   // A/B hook
-  stem_kernel<<<C * NPTS / 128, 128, 0, st>>>(xyz, stem_of(wa), stem_of(wb), B, xfeat, nullptr,
-                                              stem_planes ? reinterpret_cast<__half*>(xfeat_h[0]) : nullptr,
-                                              stem_planes ? reinterpret_cast<__half*>(xfeat_h[1]) : nullptr);
-  PZ_LAUNCH_CHECK();
-  if (!stem_planes) PZ_TRY(launch_split_planes(xfeat, D0, (size_t)C * NPTS, D0, xfeat_h[0], xfeat_h[1], D0, st));
+  // stem: layer 2 as a split-fp16 mma.sync product (x_feature within ~1e-6 of the fp32 stem), the fp16 hi / lo planes of
+  // x_feature written by the same kernel; PZ_STEM_FFMA=1 keeps the FFMA stem + a separate plane pass (A/B hook)
+  static const bool stem_ffma = getenv("PZ_STEM_FFMA") && getenv("PZ_STEM_FFMA")[0] == '1';
+  const int reps = head_reps();
+  if (stem_ffma || (C * NPTS) % (128 * reps) != 0) {
+    stem_kernel<<<C * NPTS / 128, 128, 0, st>>>(xyz, stem_of(wa), stem_of(wb), B, xfeat, nullptr, nullptr, nullptr);
+    PZ_LAUNCH_CHECK();
+    PZ_TRY(launch_split_planes(xfeat, D0, (size_t)C * NPTS, D0, xfeat_h[0], xfeat_h[1], D0, st));
+  } else {
+    PZ_CUDA(cudaFuncSetAttribute(stem_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STEM_TC_SMEM));
+    stem_tc_kernel<true><<<C * NPTS / (128 * reps), 128, STEM_TC_SMEM, st>>>(
+        xyz, stem_of(wa), stem_of(wb), nullptr, nullptr, B, reps, xfeat, reinterpret_cast<__nv_bfloat16*>(xfeat_h[0]),
+        reinterpret_cast<__half*>(xfeat_h[1]));
+    PZ_LAUNCH_CHECK();
+  }
   prof_mark("stem", st);
   {
     TcGemm g;  // P1 = x_feature W3[:,3:]^T + b3 + W3[:,0:3] xyz   (fp32 out)
