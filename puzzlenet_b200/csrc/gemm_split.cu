@@ -16,6 +16,7 @@
 //   split_gather_kernel  : grouped-MLP layer 2 with the gathered operand relu(P[j] - Q[s]) formed IN REGISTERS from
 //                          fp32 P rows (global -> registers -> one swizzled st.shared per plane) and the max over the
 //                          32 neighbours in the epilogue (pointnet_util.py:123-130 + model5_b.py:452-454, :459-461)
+#include <cuda.h>   // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint)
 #include <cuda_fp16.h>
 #include <stdlib.h>
 #include <string.h>
@@ -369,7 +370,23 @@ static int split_rowgemm_launch(const TcGemm& g, cudaStream_t st) {
 // compulsory read of X); otherwise (the encoder tail) a stage carries X + the CTA's weight half of the column tile
 // (64 KB).  Barrier protocol as in split_gather_pair_kernel: CTA-local full barriers, two relay threads in the peer CTA
 // (stage full / accumulator drained) forward them to the leader with cluster-scope arrives, multicast commits back.
-constexpr int RP_THREADS = 14 * 32;   // 8 epilogue warps, MMA issuer (leader) / stage relay (peer), accumulator relay, 4 producer warps
+constexpr int RP_THREADS = 11 * 32;   // 8 epilogue warps, MMA issuer (leader) / stage relay (peer), accumulator relay, TMA producer
+
+// operand tiles arrive by TMA (cp.async.bulk.tensor): one instruction per [rows x 64 k] SWIZZLE_128B tile, completion
+// counted in bytes on the stage's mbarrier.  With cp.async the 128 producer threads needed ~250 instructions each per
+// 64 KB stage and a stage took 3.4 us from issue to arrival (the tail GEMM ran at one k-block per 1.65 us against 0.78 us
+// of MMAs); an L2-resident stream reaches 15-19 TB/s on this chip (scripts/l2_probe.cu), so the copy engine is not the limit.
+struct alignas(64) RpMaps {
+  CUtensorMap x[2];      // X hi / lo planes: [M, K] fp16, boxes of [128 rows x 64 k]
+  CUtensorMap w[2][2];   // [weight set][hi / lo]: [Nout, K] fp16, boxes of [HALF rows x 64 k]
+};
+__device__ __forceinline__ void rp_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void rp_tma_load(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
 
 // timeline stamps of the first CTA pair (diagnostics, pz_profile_attention_timeline): globaltimer in ns, slot base
 // 2048 + 512 * cluster rank; layout: 0 entry, 1 after cluster sync, 2 weights landed, 16+2j / 17+2j producer issue /
@@ -383,12 +400,12 @@ __device__ __forceinline__ void rp_stamp(long long* prof, uint32_t crank, int sl
 }
 
 template <int NCOLS, int NST, bool RESIDENT>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RP_THREADS, 1) split_rowgemm_pair_kernel(const TcGemm g) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RP_THREADS, 1) split_rowgemm_pair_kernel(const TcGemm g, const __grid_constant__ RpMaps maps) {
   extern __shared__ __align__(1024) uint8_t srp_smem_raw[];
   const uint32_t smem_base = smem_u32(srp_smem_raw);
   if ((smem_base & 1023u) != 0) __trap();   // no alignment pad is budgeted (see split_gather_pair_kernel)
   uint8_t* smem_gen = srp_smem_raw;
-  constexpr int EPI = 8, PROD_THREADS = 128, ROWS = 128, HALF = NCOLS / 2;
+  constexpr int EPI = 8, ROWS = 128, HALF = NCOLS / 2;
   constexpr uint32_t STAGE_X = 2 * TILE16K, W_TILE = HALF * 128, STAGE = STAGE_X + (RESIDENT ? 0u : 2 * W_TILE);
   const int kblocks = g.K / KB;
   const uint32_t resident = RESIDENT ? (uint32_t)kblocks * 2 * W_TILE : 0u;   // per k-block [hi tile][lo tile]
@@ -419,15 +436,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RP_THREADS, 1) split
   const int rank_in_set = pair - wset * pairs_per_set;
   const int step = (wset == nsets - 1) ? npairs - wset * pairs_per_set : pairs_per_set;
   const int tile_begin = wset * tiles_per_set;
-  const __half* __restrict__ Whi = reinterpret_cast<const __half*>(g.W[wset]);
-  const __half* __restrict__ Wlo = reinterpret_cast<const __half*>(g.Wlo[wset]);
-  const __half* __restrict__ Xhi = reinterpret_cast<const __half*>(g.X);
-  const __half* __restrict__ Xlo = reinterpret_cast<const __half*>(g.Xlo);
   const float* __restrict__ bias = g.bias[wset];
 
   if (tid == 0) {
     for (int s = 0; s < NST; ++s) {
-      mbar_init(full_bar + 8 * s, PROD_THREADS);
+      mbar_init(full_bar + 8 * s, 1);          // the producer's expect_tx arrival + the stage's bytes
       mbar_init(empty_bar + 8 * s, 1);
       mbar_init(pfull_bar + 8 * s, 1);     // leader: the peer's stage s is full
     }
@@ -436,7 +449,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RP_THREADS, 1) split
       mbar_init(acce_bar + 8 * b, EPI * 32);
       mbar_init(pacce_bar + 8 * b, 1);     // leader: the peer has drained accumulator b
     }
-    mbar_init(w_bar, (EPI + 2) * 32);
+    mbar_init(w_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == EPI) {
@@ -447,65 +460,40 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RP_THREADS, 1) split
   cluster_sync_all();        // barriers initialised and TMEM allocated in both CTAs
   tc_fence_after();
   if (tid == 0) rp_stamp(g.prof, crank, 1);
-  if (RESIDENT && warp < EPI + 2) {
-    // this CTA's half of the output channels, both planes, swizzled [HALF ch x 64 k] tiles per k-block: fetched with
-    // cp.async by the ten non-producer warps (everything in flight at once) WHILE the producers already stream X
-    const int chunks = kblocks * HALF * 8;
-    for (int id = tid; id < chunks; id += (EPI + 2) * 32) {
-      const int c = id & 7, r = (id >> 3) % HALF, kb = id / (HALF * 8);
-      const size_t off = (size_t)((int)crank * HALF + r) * g.ldw + kb * KB + c * 8;
-      cp_async16(smem_base + (uint32_t)kb * 2 * W_TILE + sw128(r, c), Whi + off);
-      cp_async16(smem_base + (uint32_t)kb * 2 * W_TILE + W_TILE + sw128(r, c), Wlo + off);
-    }
-    cp_async_commit();
-    cp_async_wait<0>();
-    fence_proxy_async();
-    mbar_arrive(w_bar);
-  }
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
   if (warp >= EPI + 2) {
-    // ================================================= producers: this CTA's X planes (+ its weight half when streamed)
-    const int pt = tid - (EPI + 2) * 32;
-    uint32_t issued = 0, arrived = 0;
-    for (int t = tile_begin + rank_in_set; t < tile_begin + tiles_per_set; t += step) {
-      const int ct = t % col_tiles, rt = t / col_tiles;
-      const int row0 = rt * 2 * ROWS + (int)crank * ROWS, col0 = ct * NCOLS + (int)crank * HALF;
-      for (int kb = 0; kb < kblocks; ++kb) {
-        const uint32_t s = issued % NST, ph = (issued / NST) & 1;
-        mbar_wait(empty_bar + 8 * s, ph ^ 1);
-        const uint32_t st_addr = stages_base + s * STAGE;
-        if (pt == 0 && issued < 48) rp_stamp(g.prof, crank, 16 + 2 * (int)issued);
-        for (int id = pt; id < ROWS * 8; id += PROD_THREADS) {
-          const int c = id & 7, r = id >> 3;
-          const size_t off = (size_t)(row0 + r) * g.ldx + kb * KB + c * 8;
-          cp_async16(st_addr + sw128(r, c), Xhi + off);
-          cp_async16(st_addr + TILE16K + sw128(r, c), Xlo + off);
-        }
-        if (!RESIDENT) {
-          for (int id = pt; id < HALF * 8; id += PROD_THREADS) {
-            const int c = id & 7, r = id >> 3;
-            const size_t off = (size_t)(col0 + r) * g.ldw + kb * KB + c * 8;
-            cp_async16(st_addr + STAGE_X + sw128(r, c), Whi + off);
-            cp_async16(st_addr + STAGE_X + W_TILE + sw128(r, c), Wlo + off);
-          }
-        }
-        cp_async_commit();
-        ++issued;
-        if (issued - arrived > (NST > 2 ? 2u : 1u)) {
-          if (NST > 2) cp_async_wait<2>(); else cp_async_wait<1>();
-          fence_proxy_async();
-          mbar_arrive(full_bar + 8 * (arrived % NST));
-          if (pt == 0 && arrived < 48) rp_stamp(g.prof, crank, 17 + 2 * (int)arrived);
-          ++arrived;
+    // ================================================= producer: ONE thread issues the TMA loads of this CTA's tiles
+    if (lane == 0) {
+      const CUtensorMap* tx_hi = &maps.x[0];
+      const CUtensorMap* tx_lo = &maps.x[1];
+      const CUtensorMap* tw_hi = &maps.w[wset][0];
+      const CUtensorMap* tw_lo = &maps.w[wset][1];
+      if (RESIDENT) {   // this CTA's half of the output channels, both planes, one [HALF ch x 64 k] tile per k-block and plane
+        rp_expect_tx(w_bar, (uint32_t)kblocks * 2 * W_TILE);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          rp_tma_load(smem_base + (uint32_t)kb * 2 * W_TILE, tw_hi, kb * KB, (int)crank * HALF, w_bar);
+          rp_tma_load(smem_base + (uint32_t)kb * 2 * W_TILE + W_TILE, tw_lo, kb * KB, (int)crank * HALF, w_bar);
         }
       }
-    }
-    cp_async_wait<0>();
-    fence_proxy_async();
-    while (arrived < issued) {
-      mbar_arrive(full_bar + 8 * (arrived % NST));
-      ++arrived;
+      uint32_t issued = 0;
+      for (int t = tile_begin + rank_in_set; t < tile_begin + tiles_per_set; t += step) {
+        const int ct = t % col_tiles, rt = t / col_tiles;
+        const int row0 = rt * 2 * ROWS + (int)crank * ROWS, col0 = ct * NCOLS + (int)crank * HALF;
+        for (int kb = 0; kb < kblocks; ++kb, ++issued) {
+          const uint32_t s = issued % NST, ph = (issued / NST) & 1;
+          mbar_wait(empty_bar + 8 * s, ph ^ 1);
+          const uint32_t st_addr = stages_base + s * STAGE;
+          if (issued < 48) rp_stamp(g.prof, crank, 16 + 2 * (int)issued);
+          rp_expect_tx(full_bar + 8 * s, STAGE);
+          rp_tma_load(st_addr, tx_hi, kb * KB, row0, full_bar + 8 * s);
+          rp_tma_load(st_addr + TILE16K, tx_lo, kb * KB, row0, full_bar + 8 * s);
+          if (!RESIDENT) {
+            rp_tma_load(st_addr + STAGE_X, tw_hi, kb * KB, col0, full_bar + 8 * s);
+            rp_tma_load(st_addr + STAGE_X + W_TILE, tw_lo, kb * KB, col0, full_bar + 8 * s);
+          }
+        }
+      }
     }
   } else if (warp == EPI) {
     if (crank == 0 && lane == 0) {
@@ -791,12 +779,49 @@ static size_t split_rowgemm_pair_smem(const TcGemm& g, int ncols, int nst, bool 
          (size_t)ncols * (g.xyz ? 16 : 4) + (g.Ymax ? (size_t)ncols * 16 : 0) + 128 + (staging ? 8 * 4096 : 0);
 }
 
+// 2-D fp16 view [rows, cols] with a row stride of ld elements, traversed in [box_rows x 64] SWIZZLE_128B boxes
+static int rp_make_map(const void* ptr, int ld, size_t rows, int cols, int box_rows, CUtensorMap* out) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      fn = nullptr;
+    return reinterpret_cast<EncodeFn>(fn);
+  }();
+  PZ_REQUIRE(encode != nullptr, PZ_ERR_UNSUPPORTED, "split_rowgemm: the driver does not export cuTensorMapEncodeTiled");
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(__half)};
+  const cuuint32_t box[2] = {64, (cuuint32_t)box_rows}, estr[2] = {1, 1};
+  const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PZ_REQUIRE(r == CUDA_SUCCESS, PZ_ERR_ARG, "split_rowgemm: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return 0;
+}
+
 template <int NCOLS, int NST, bool RESIDENT>
 static int split_rowgemm_pair_launch(const TcGemm& g, cudaStream_t st) {
   const size_t smem = split_rowgemm_pair_smem(g, NCOLS, NST, RESIDENT);
   PZ_REQUIRE(smem <= 232448, PZ_ERR_UNSUPPORTED, "split_rowgemm (pair): needs %zu B of shared memory", smem);
   auto kern = split_rowgemm_pair_kernel<NCOLS, NST, RESIDENT>;
   PZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int nsets = (g.rows_per_wset > 0 && g.M > g.rows_per_wset) ? 2 : 1;
+  const int tiles_per_set = (g.M / 256 / nsets) * (g.Nout / NCOLS);
+  int per = (kNumSMs / 2) / nsets;
+  if (per > tiles_per_set) per = tiles_per_set;
+  if (per < 1) per = 1;
+  RpMaps maps;
+  PZ_TRY(rp_make_map(g.X, g.ldx, (size_t)g.M, g.K, 128, &maps.x[0]));
+  PZ_TRY(rp_make_map(g.Xlo, g.ldx, (size_t)g.M, g.K, 128, &maps.x[1]));
+  for (int ws = 0; ws < 2; ++ws) {
+    const int src = ws < nsets ? ws : 0;   // an unused second set repeats the first: every map handed over is valid
+    PZ_TRY(rp_make_map(g.W[src], g.ldw, (size_t)g.Nout, g.K, NCOLS / 2, &maps.w[ws][0]));
+    PZ_TRY(rp_make_map(g.Wlo[src], g.ldw, (size_t)g.Nout, g.K, NCOLS / 2, &maps.w[ws][1]));
+  }
   TcGemm gd = g;
   static const char* tl_sel = getenv("PZ_RG_TIMELINE");   // "outproj" | "qk" | "vt" | "p1" | "tail": which launch stamps
   gd.prof = nullptr;
@@ -805,12 +830,7 @@ static int split_rowgemm_pair_launch(const TcGemm& g, cudaStream_t st) {
                      (!strcmp(tl_sel, "vt") && g.YT) || (!strcmp(tl_sel, "p1") && g.K == 64) || (!strcmp(tl_sel, "tail") && g.Ymax);
     if (hit) gd.prof = kernel_timeline_buffer(2048 + 1024);
   }
-  const int nsets = (g.rows_per_wset > 0 && g.M > g.rows_per_wset) ? 2 : 1;
-  const int tiles_per_set = (g.M / 256 / nsets) * (g.Nout / NCOLS);
-  int per = (kNumSMs / 2) / nsets;
-  if (per > tiles_per_set) per = tiles_per_set;
-  if (per < 1) per = 1;
-  kern<<<2 * per * nsets, RP_THREADS, smem, st>>>(gd);
+  kern<<<2 * per * nsets, RP_THREADS, smem, st>>>(gd, maps);
   PZ_LAUNCH_CHECK();
   return 0;
 }
