@@ -7,10 +7,12 @@
 // One CTA per (cloud, block of 128 queries): 2 CTAs per cloud.  S = q k^T lands with the query rows on the TMEM lanes,
 // so each of the 128 softmax threads owns one full row (max / exp2 / sum in-thread).  The un-normalised probabilities go
 // back to shared memory as the K-major A operand of O = P v (both planes), whose B operand v^T (written transposed by
-// the v projection's epilogue) streams through a 3-stage ring of [128 channels x 64 keys] x 2 planes while the softmax
+// the v projection's epilogue) streams by TMA through a 2-stage ring of [128 channels x 64 keys] x 2 planes while the softmax
 // runs; O is produced as two 128-channel halves so the epilogue of the first overlaps the MMAs of the second.
-// Warps 0-3 softmax + epilogue, warp 4 the MMA-issuing thread, warps 5-7 the v^T producers.
-// Shared memory: region A 128 KB (q, k planes -> P planes) + ring 96 KB.  TMEM: S [0,256), O halves [256,384), [384,512).
+// Warps 0-3 softmax + epilogue, warp 4 the MMA-issuing thread, one thread of warp 5 issues every TMA load of v^T (q and k
+// arrive by TMA as well, issued by thread 0 before the CTA-wide barrier).
+// Shared memory: region A 128 KB (q, k planes -> P planes) + ring 64 KB + 16 KB staging tiles of the r epilogue.  TMEM: S [0,256), O halves [256,384), [384,512).
+#include <cuda.h>   // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint)
 #include <cuda_fp16.h>
 
 #include "pz_common.cuh"
@@ -25,9 +27,8 @@ constexpr int AS_THREADS = 256;
 constexpr int AS_L = 256, AS_C = 256;
 constexpr uint32_t T16 = 128 * 128;                 // one [128 x 64] fp16 tile
 constexpr uint32_t REGA = 8 * T16;                  // 128 KB
-constexpr int AS_NST = 3;
+constexpr int AS_NST = 2;                            // two stages: the freed 32 KB hold the epilogue's staging tiles
 constexpr uint32_t AS_STAGE = 2 * T16;              // hi + lo of [128 ch x 64 keys]
-constexpr int AS_PROD = 96;
 
 __host__ __device__ constexpr uint32_t idesc_f16(int n) {
   return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -47,94 +48,184 @@ __device__ __forceinline__ void umma3(uint32_t d, uint64_t a_hi, uint64_t a_lo, 
   umma_bf16(d, a_hi, b_lo, idesc, 1);
   umma_bf16(d, a_lo, b_hi, idesc, 1);
 }
+__device__ __forceinline__ void as_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// one [128 rows x 64 columns] fp16 box at (column c0, row c1) -> a 16 KB SWIZZLE_128B tile
+__device__ __forceinline__ void as_tma_load(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+// timeline stamps of CTA 0 (diagnostics, pz_profile_attention_timeline): globaltimer ns at slots 3072..: 0 entry, 1 q|k
+// landed, 2 S in TMEM, 3 P written, 4 / 6 O half 0 / 1 complete, 5 / 7 r half 0 / 1 stored
+__device__ __forceinline__ void as_stamp(long long* prof, int slot) {
+  if (prof != nullptr && blockIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    prof[3072 + slot] = (long long)t;
+  }
+}
+struct alignas(64) AsMaps {
+  CUtensorMap qk[2];   // q|k hi / lo planes: [rows, 128]
+  CUtensorMap vT[2];   // v^T hi / lo planes: [clouds * 256 channels, 256 keys]
+};
 }  // namespace
 
-__global__ void __launch_bounds__(AS_THREADS, 1) attention_split_kernel(const AttnSplit p) {
+__global__ void __launch_bounds__(AS_THREADS, 1) attention_split_kernel(const AttnSplit p, const __grid_constant__ AsMaps maps, long long* prof) {
   extern __shared__ __align__(1024) uint8_t as_smem_raw[];
   const uint32_t base = (smem_u32(as_smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = as_smem_raw + (base - smem_u32(as_smem_raw));
   const uint32_t ring = base + REGA;
   const uint32_t bars = ring + AS_NST * AS_STAGE;
   const uint32_t bar_s = bars, bar_p = bars + 8, bar_o = bars + 16 /* 2 */, full_bar = bars + 32, empty_bar = full_bar + 8 * AS_NST;
-  const uint32_t tmem_slot = empty_bar + 8 * AS_NST;
+  const uint32_t bar_qk = empty_bar + 8 * AS_NST;
+  const uint32_t tmem_slot = bar_qk + 8;
+  const uint32_t stg_all = (tmem_slot + 16 + 127) & ~127u;   // 4 x 4 KB staging tiles of the r epilogue (reused by both halves)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cloud = blockIdx.x >> 1, qb = blockIdx.x & 1;
   const size_t row0 = (size_t)cloud * AS_L;
-  const __half* qk_hi = static_cast<const __half*>(p.qk_hi);
-  const __half* qk_lo = static_cast<const __half*>(p.qk_lo);
-  const __half* vT_hi = static_cast<const __half*>(p.vT_hi) + row0 * AS_L;
-  const __half* vT_lo = static_cast<const __half*>(p.vT_lo) + row0 * AS_L;
 
-  // ---- q (this block's 128 rows) and k (all 256 rows), both planes -> region A
+  // ---- q (this block's 128 rows) and k (all 256 rows), both planes -> region A, by TMA (six 16 KB tiles on one mbarrier)
   const uint32_t q_hi_s = base, q_lo_s = base + T16, k_hi_s = base + 2 * T16, k_lo_s = base + 4 * T16;
-  for (int id = tid; id < 128 * 8; id += AS_THREADS) {
-    const int c = id & 7, i = id >> 3;
-    const size_t off = (row0 + qb * 128 + i) * 128 + c * 8;
-    cp_async16(q_hi_s + sw128(i, c), qk_hi + off);
-    cp_async16(q_lo_s + sw128(i, c), qk_lo + off);
-  }
-  for (int id = tid; id < 256 * 8; id += AS_THREADS) {
-    const int c = id & 7, i = id >> 3;
-    const size_t off = (row0 + i) * 128 + 64 + c * 8;
-    cp_async16(k_hi_s + sw128(i, c), qk_hi + off);
-    cp_async16(k_lo_s + sw128(i, c), qk_lo + off);
-  }
-  cp_async_commit();
   if (tid == 0) {
+    as_stamp(prof, 0);
     mbar_init(bar_s, 1);
     mbar_init(bar_p, 128);
     mbar_init(bar_o, 1);
     mbar_init(bar_o + 8, 1);
+    mbar_init(bar_qk, 1);
     for (int s = 0; s < AS_NST; ++s) {
-      mbar_init(full_bar + 8 * s, AS_PROD);
+      mbar_init(full_bar + 8 * s, 1);
       mbar_init(empty_bar + 8 * s, 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the inits are visible to the TMA unit
+    const int r = (int)row0;
+    as_expect_tx(bar_qk, 6 * T16);
+    as_tma_load(q_hi_s, &maps.qk[0], 0, r + qb * 128, bar_qk);
+    as_tma_load(q_lo_s, &maps.qk[1], 0, r + qb * 128, bar_qk);
+    as_tma_load(k_hi_s, &maps.qk[0], 64, r, bar_qk);
+    as_tma_load(k_hi_s + T16, &maps.qk[0], 64, r + 128, bar_qk);
+    as_tma_load(k_lo_s, &maps.qk[1], 64, r, bar_qk);
+    as_tma_load(k_lo_s + T16, &maps.qk[1], 64, r + 128, bar_qk);
   }
   if (warp == 4) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  cp_async_wait<0>();
-  fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
 
-  if (warp >= 5) {
-    // =========================================================== v^T producers: 8 stage loads (2 channel halves x 4 key blocks)
-    const int pt = tid - 5 * 32;
-    uint32_t arrived = 0;
-    for (uint32_t it = 0; it < 8; ++it) {
-      const uint32_t s = it % AS_NST, ph = (it / AS_NST) & 1;
-      const int h = it >> 2, kb = it & 3;
-      mbar_wait(empty_bar + 8 * s, ph ^ 1);
-      const uint32_t st = ring + s * AS_STAGE;
-      for (int id = pt; id < 128 * 8; id += AS_PROD) {
-        const int c = id & 7, r = id >> 3;
-        const size_t off = (size_t)(h * 128 + r) * AS_L + kb * 64 + c * 8;
-        cp_async16(st + sw128(r, c), vT_hi + off);
-        cp_async16(st + T16 + sw128(r, c), vT_lo + off);
+  // r = x - O / sum for one 128-channel half `eh` of the block's 128 rows, by the four warps (quarters wq) of one group
+  auto r_epilogue = [&](const int eh, const int wq, float inv) {
+    const uint32_t tq_row = tmem + ((uint32_t)(wq * 32) << 16);
+    // Global traffic is coalesced through a 4 KB per-warp staging tile (two planes of [32 rows][64 B], 16-byte pieces XOR-
+    // swizzled so that both the row-per-thread and the row-segment-per-4-lanes accesses are conflict-free): a thread owns a
+    // row, and direct 16-byte accesses touch 32 cache lines per warp instruction -- measured, the r epilogue took 13 of the
+    // CTA's 21 us on L1 wavefronts alone.  The x block of chunk c + 1 is fetched (coalesced role) while chunk c is finished.
+    const uint32_t stg = stg_all + (uint32_t)wq * 4096;
+    const int cr = lane >> 2, cp = lane & 3;                    // coalesced role: row 8 j + cr, piece cp
+    const uint32_t own16 = stg + (uint32_t)lane * 64, sw_own = (uint32_t)((lane >> 1) & 3);
+    const size_t rowbase = row0 + qb * 128 + wq * 32;
+    const __half* xhb = static_cast<const __half*>(p.x_hi);
+    const __half* xlb = static_cast<const __half*>(p.x_lo);
+    __half* rhb = static_cast<__half*>(p.r_hi);
+    __half* rlb = static_cast<__half*>(p.r_lo);
+    uint4 pre[8];
+    auto x_fetch = [&](int cb) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const size_t off = (rowbase + 8 * j + cr) * p.ldx + cb + cp * 8;
+        pre[j] = *reinterpret_cast<const uint4*>(xhb + off);
+        pre[4 + j] = *reinterpret_cast<const uint4*>(xlb + off);
       }
-      cp_async_commit();
-      if (it - arrived >= 1) {       // keep two stage loads in flight
-        cp_async_wait<1>();
-        fence_proxy_async();
-        mbar_arrive(full_bar + 8 * (arrived % AS_NST));
-        ++arrived;
+    };
+    x_fetch(eh * 128);
+    {
+      const int h = eh;
+      mbar_wait(bar_o + 8 * h, 0);
+      tc_fence_after();
+      if (lane == 0 && wq == 0) as_stamp(prof, 4 + 2 * h);
+#pragma unroll 1
+      for (int c32 = 0; c32 < 4; ++c32) {
+        const int cb = h * 128 + c32 * 32;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {   // the prefetched x block -> staging
+          const int r = 8 * j + cr;
+          const uint32_t a = stg + (uint32_t)r * 64 + (uint32_t)((cp ^ ((r >> 1) & 3)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pre[j].x), "r"(pre[j].y), "r"(pre[j].z), "r"(pre[j].w) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a + 2048), "r"(pre[4 + j].x), "r"(pre[4 + j].y), "r"(pre[4 + j].z), "r"(pre[4 + j].w) : "memory");
+        }
+        __syncwarp();
+        if (c32 + 1 < 4) x_fetch(cb + 32);
+        float v[32];
+        tmem_ld32(tq_row + 256 + cb, v);
+        uint4 oh[4], ol[4];
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          uint4 xh4, xl4;
+          const uint32_t a = own16 + (((uint32_t)q4 ^ sw_own) << 4);
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(xh4.x), "=r"(xh4.y), "=r"(xh4.z), "=r"(xh4.w) : "r"(a));
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(xl4.x), "=r"(xl4.y), "=r"(xl4.z), "=r"(xl4.w) : "r"(a + 2048));
+          const uint32_t* hp = reinterpret_cast<const uint32_t*>(&xh4);
+          const uint32_t* lp = reinterpret_cast<const uint32_t*>(&xl4);
+          uint32_t* ohp = reinterpret_cast<uint32_t*>(&oh[q4]);
+          uint32_t* olp = reinterpret_cast<uint32_t*>(&ol[q4]);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 a2 = __half22float2(*reinterpret_cast<const __half2*>(&hp[e]));
+            const float2 b2 = __half22float2(*reinterpret_cast<const __half2*>(&lp[e]));
+            split2h((a2.x + b2.x) - v[q4 * 8 + 2 * e] * inv, (a2.y + b2.y) - v[q4 * 8 + 2 * e + 1] * inv, ohp[e], olp[e]);
+          }
+        }
+        __syncwarp();                 // every lane has read its x row: the tile takes the r block
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const uint32_t a = own16 + (((uint32_t)q4 ^ sw_own) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(oh[q4].x), "r"(oh[q4].y), "r"(oh[q4].z), "r"(oh[q4].w) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a + 2048), "r"(ol[q4].x), "r"(ol[q4].y), "r"(ol[q4].z), "r"(ol[q4].w) : "memory");
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int r = 8 * j + cr;
+          const uint32_t a = stg + (uint32_t)r * 64 + (uint32_t)((cp ^ ((r >> 1) & 3)) << 4);
+          uint4 hh, ll;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(hh.x), "=r"(hh.y), "=r"(hh.z), "=r"(hh.w) : "r"(a));
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(ll.x), "=r"(ll.y), "=r"(ll.z), "=r"(ll.w) : "r"(a + 2048));
+          const size_t off = (rowbase + r) * AS_C + cb + cp * 8;
+          *reinterpret_cast<uint4*>(rhb + off) = hh;
+          *reinterpret_cast<uint4*>(rlb + off) = ll;
+        }
+        __syncwarp();
       }
+      if (lane == 0 && wq == 0) as_stamp(prof, 5 + 2 * h);
     }
-    cp_async_wait<0>();
-    fence_proxy_async();
-    while (arrived < 8) {
-      mbar_arrive(full_bar + 8 * (arrived % AS_NST));
-      ++arrived;
+  };
+  if (warp >= 5) {
+    // =========================================================== v^T producer: ONE thread, 8 stage loads (2 channel halves
+    // x 4 key blocks), two TMA tiles (hi, lo) per stage
+    if (warp == 5 && lane == 0) {
+      const int vrow = cloud * AS_C;
+      for (uint32_t it = 0; it < 8; ++it) {
+        const uint32_t s = it % AS_NST, ph = (it / AS_NST) & 1;
+        const int h = it >> 2, kb = it & 3;
+        mbar_wait(empty_bar + 8 * s, ph ^ 1);
+        const uint32_t st = ring + s * AS_STAGE;
+        as_expect_tx(full_bar + 8 * s, AS_STAGE);
+        as_tma_load(st, &maps.vT[0], kb * 64, vrow + h * 128, full_bar + 8 * s);
+        as_tma_load(st + T16, &maps.vT[1], kb * 64, vrow + h * 128, full_bar + 8 * s);
+      }
     }
   } else if (warp == 4) {
     // =========================================================== MMA issuer
     if (lane == 0) {
       {  // S[i, j] = sum_d q[i, d] k[j, d]
+        mbar_wait(bar_qk, 0);
+        tc_fence_after();
+        as_stamp(prof, 1);
         const uint32_t idesc = idesc_f16(256);
         const uint64_t a_hi = make_desc(q_hi_s), a_lo = make_desc(q_lo_s), b_hi = make_desc(k_hi_s), b_lo = make_desc(k_lo_s);
 #pragma unroll
@@ -167,6 +258,7 @@ __global__ void __launch_bounds__(AS_THREADS, 1) attention_split_kernel(const At
     const float cexp = 1.4426950408889634f / 8.0f;  // log2(e) / sqrt(d_k)
     mbar_wait(bar_s, 0);
     tc_fence_after();
+    if (tid == 0) as_stamp(prof, 2);
     float m = -INFINITY;
 #pragma unroll 1
     for (int c32 = 0; c32 < 8; ++c32) {
@@ -203,6 +295,7 @@ __global__ void __launch_bounds__(AS_THREADS, 1) attention_split_kernel(const At
     fence_proxy_async();
     tc_fence_before();
     mbar_arrive(bar_p);
+    if (tid == 0) as_stamp(prof, 3);
     const float inv = 1.0f / sum;
     if (p.attn_mode != 0) {  // attention map (need=True): mean of the four layers' maps, model5_b.py:468-469
       float* ag = p.attn + grow * AS_L;
@@ -228,42 +321,10 @@ __global__ void __launch_bounds__(AS_THREADS, 1) attention_split_kernel(const At
       }
     }
     // r = x - O / sum, one 128-channel half at a time (the second half's MMAs run under the first half's epilogue)
-    const __half* xh = static_cast<const __half*>(p.x_hi) + grow * p.ldx;
-    const __half* xl = static_cast<const __half*>(p.x_lo) + grow * p.ldx;
-    __half* rh = static_cast<__half*>(p.r_hi) + grow * AS_C;
-    __half* rl = static_cast<__half*>(p.r_lo) + grow * AS_C;
-    for (int h = 0; h < 2; ++h) {
-      mbar_wait(bar_o + 8 * h, 0);
-      tc_fence_after();
-#pragma unroll 1
-      for (int c32 = 0; c32 < 4; ++c32) {
-        const int cb = h * 128 + c32 * 32;
-        uint4 xhv[4], xlv[4];
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          xhv[q4] = *reinterpret_cast<const uint4*>(xh + cb + q4 * 8);
-          xlv[q4] = *reinterpret_cast<const uint4*>(xl + cb + q4 * 8);
-        }
-        float v[32];
-        tmem_ld32(t_row + 256 + cb, v);
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          const uint32_t* hp = reinterpret_cast<const uint32_t*>(&xhv[q4]);
-          const uint32_t* lp = reinterpret_cast<const uint32_t*>(&xlv[q4]);
-          uint4 oh, ol;
-          uint32_t* ohp = reinterpret_cast<uint32_t*>(&oh);
-          uint32_t* olp = reinterpret_cast<uint32_t*>(&ol);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&hp[e]));
-            const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&lp[e]));
-            split2h((a.x + b.x) - v[q4 * 8 + 2 * e] * inv, (a.y + b.y) - v[q4 * 8 + 2 * e + 1] * inv, ohp[e], olp[e]);
-          }
-          *reinterpret_cast<uint4*>(rh + cb + q4 * 8) = oh;
-          *reinterpret_cast<uint4*>(rl + cb + q4 * 8) = ol;
-        }
-      }
-    }
+    // (a second group of four warps taking the other half was measured: both halves slow down to the same total -- the
+    // phase moves 256 KB per CTA at ~5.4 TB/s over the chip, it is HBM-bound)
+    r_epilogue(0, warp, inv);
+    r_epilogue(1, warp, inv);
   }
   tc_fence_before();
   __syncthreads();
@@ -272,16 +333,46 @@ __global__ void __launch_bounds__(AS_THREADS, 1) attention_split_kernel(const At
   }
 }
 
+// 2-D fp16 view [rows, cols] (row stride ld elements) traversed in [128 rows x 64 columns] SWIZZLE_128B boxes
+static int as_make_map(const void* ptr, int ld, size_t rows, int cols, CUtensorMap* out) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      fn = nullptr;
+    return reinterpret_cast<EncodeFn>(fn);
+  }();
+  PZ_REQUIRE(encode != nullptr, PZ_ERR_UNSUPPORTED, "attention_split: the driver does not export cuTensorMapEncodeTiled");
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(__half)};
+  const cuuint32_t box[2] = {64, 128}, estr[2] = {1, 1};
+  const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PZ_REQUIRE(r == CUDA_SUCCESS, PZ_ERR_ARG, "attention_split: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return 0;
+}
+
 int launch_attention_split(const AttnSplit& p, int clouds, cudaStream_t st) {
   PZ_REQUIRE(p.qk_hi && p.qk_lo && p.vT_hi && p.vT_lo && p.x_hi && p.x_lo && p.r_hi && p.r_lo, PZ_ERR_ARG, "attention_split: null pointer");
   PZ_REQUIRE(p.ldx % 8 == 0 && (((uintptr_t)p.x_hi | (uintptr_t)p.x_lo | (uintptr_t)p.r_hi | (uintptr_t)p.r_lo | (uintptr_t)p.qk_hi |
                                  (uintptr_t)p.qk_lo | (uintptr_t)p.vT_hi | (uintptr_t)p.vT_lo) & 15) == 0,
              PZ_ERR_ARG, "attention_split: rows must be 16-byte aligned");
   PZ_REQUIRE(p.attn_mode == 0 || p.attn, PZ_ERR_ARG, "attention_split: attention map requested without a buffer");
-  const size_t smem = 1024 + REGA + AS_NST * AS_STAGE + 8 * (4 + 2 * AS_NST) + 32;
-  static_assert(1024 + REGA + AS_NST * AS_STAGE + 8 * (4 + 2 * AS_NST) + 32 <= 232448, "attention_split: shared memory budget");
+  const size_t smem = 1024 + REGA + AS_NST * AS_STAGE + 8 * (5 + 2 * AS_NST) + 32 + 128 + 4 * 4096;
+  static_assert(1024 + REGA + AS_NST * AS_STAGE + 8 * (5 + 2 * AS_NST) + 32 + 128 + 4 * 4096 <= 232448, "attention_split: shared memory budget");
   PZ_CUDA(cudaFuncSetAttribute(attention_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  attention_split_kernel<<<2 * clouds, AS_THREADS, smem, st>>>(p);
+  AsMaps maps;
+  const size_t rows = (size_t)clouds * AS_L;
+  PZ_TRY(as_make_map(p.qk_hi, 128, rows, 128, &maps.qk[0]));
+  PZ_TRY(as_make_map(p.qk_lo, 128, rows, 128, &maps.qk[1]));
+  PZ_TRY(as_make_map(p.vT_hi, AS_L, (size_t)clouds * AS_C, AS_L, &maps.vT[0]));
+  PZ_TRY(as_make_map(p.vT_lo, AS_L, (size_t)clouds * AS_C, AS_L, &maps.vT[1]));
+  attention_split_kernel<<<2 * clouds, AS_THREADS, smem, st>>>(p, maps, kernel_timeline_buffer(3072 + 16));
   PZ_LAUNCH_CHECK();
   return 0;
 }

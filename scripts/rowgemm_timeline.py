@@ -33,3 +33,8 @@ for crank in (0, 1):
     print("  producer issue/arrive per job:", " ".join(f"{fmt(g(16 + 2 * j))}/{fmt(g(17 + 2 * j))}" for j in range(16) if t[b + 16 + 2 * j]))
     print("  MMAs issued per job:          ", " ".join(fmt(g(128 + j)) for j in range(16) if t[b + 128 + j]))
     print("  epilogue accf/done per tile:  ", " ".join(f"{fmt(g(192 + 2 * j))}/{fmt(g(193 + 2 * j))}" for j in range(8) if t[b + 192 + 2 * j]))
+
+a = [t[3072 + i] for i in range(8)]
+if a[0]:
+    names = ["entry", "q|k landed", "S in TMEM", "P written", "O half 0", "r half 0 stored", "O half 1", "r half 1 stored"]
+    print("attention_split_kernel, CTA 0 (us since entry): " + ", ".join(f"{n} {(v - a[0]) / 1e3:.2f}" for n, v in zip(names, a)))
