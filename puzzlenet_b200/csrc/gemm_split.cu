@@ -994,28 +994,33 @@ __global__ void __launch_bounds__(SG_THREADS, 1) split_gather_kernel(const TcGem
 #pragma unroll
       for (int i = 0; i < HC; ++i) {
         const int id = next_tile ? ids_n[h * HC + i] : ids[h * HC + i];
-        const float4* src = reinterpret_cast<const float4*>(P + (size_t)id * g.ldx + kb * KB + gc * 8);
+        // piece gc and piece 8 + gc of the row's sixteen 16-byte pieces: the eight lanes of a row read 128 contiguous
+        // bytes per instruction (whole sectors; with pieces 2 gc, 2 gc + 1 every sector was fetched by two instructions)
+        const float4* src = reinterpret_cast<const float4*>(P + (size_t)id * g.ldx + kb * KB) + gc;
         buf[h][i][0] = __ldg(src);
-        buf[h][i][1] = __ldg(src + 1);
+        buf[h][i][1] = __ldg(src + 8);
       }
     };
     auto store_half = [&](int h, int slot, uint32_t st_addr) {
 #pragma unroll
       for (int i = 0; i < HC; ++i) {
         const int ci = h * HC + i, r = r0 + 32 * ci;
-        float4 q0, q1;
-        const uint32_t qa = qring_s + slot * (QV * 16) + ci * 256 + gc * 32;
+        float4 q0, q1;   // channels 4 gc .. + 3 and 32 + 4 gc .. + 3
+        const uint32_t qa = qring_s + slot * (QV * 16) + ci * 256 + gc * 16;
         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(q0.x), "=f"(q0.y), "=f"(q0.z), "=f"(q0.w) : "r"(qa));
-        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(q1.x), "=f"(q1.y), "=f"(q1.z), "=f"(q1.w) : "r"(qa + 16));
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(q1.x), "=f"(q1.y), "=f"(q1.z), "=f"(q1.w) : "r"(qa + 128));
         const float4 p0 = buf[h][i][0], p1 = buf[h][i][1];
-        uint4 oh, ol;
-        split2(fmaxf(p0.x - q0.x, 0.f), fmaxf(p0.y - q0.y, 0.f), oh.x, ol.x);
-        split2(fmaxf(p0.z - q0.z, 0.f), fmaxf(p0.w - q0.w, 0.f), oh.y, ol.y);
-        split2(fmaxf(p1.x - q1.x, 0.f), fmaxf(p1.y - q1.y, 0.f), oh.z, ol.z);
-        split2(fmaxf(p1.z - q1.z, 0.f), fmaxf(p1.w - q1.w, 0.f), oh.w, ol.w);
-        const uint32_t off = sw128(r, gc);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st_addr + off), "r"(oh.x), "r"(oh.y), "r"(oh.z), "r"(oh.w) : "memory");
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st_addr + X_PLANE + off), "r"(ol.x), "r"(ol.y), "r"(ol.z), "r"(ol.w) : "memory");
+        uint2 h0, l0, h1, l1;
+        split2(fmaxf(p0.x - q0.x, 0.f), fmaxf(p0.y - q0.y, 0.f), h0.x, l0.x);
+        split2(fmaxf(p0.z - q0.z, 0.f), fmaxf(p0.w - q0.w, 0.f), h0.y, l0.y);
+        split2(fmaxf(p1.x - q1.x, 0.f), fmaxf(p1.y - q1.y, 0.f), h1.x, l1.x);
+        split2(fmaxf(p1.z - q1.z, 0.f), fmaxf(p1.w - q1.w, 0.f), h1.y, l1.y);
+        // 4 channels = 8 bytes: half (gc & 1) of 16-byte chunk gc >> 1 (and of chunk 4 + (gc >> 1)) of the swizzled row
+        const uint32_t o0 = sw128(r, gc >> 1) + ((gc & 1) << 3), o1 = sw128(r, 4 + (gc >> 1)) + ((gc & 1) << 3);
+        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(st_addr + o0), "r"(h0.x), "r"(h0.y) : "memory");
+        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(st_addr + o1), "r"(h1.x), "r"(h1.y) : "memory");
+        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(st_addr + X_PLANE + o0), "r"(l0.x), "r"(l0.y) : "memory");
+        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(st_addr + X_PLANE + o1), "r"(l1.x), "r"(l1.y) : "memory");
       }
     };
     if (jobs > 0) {

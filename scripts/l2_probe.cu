@@ -4,6 +4,7 @@
 //     nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o /tmp/l2_probe scripts/l2_probe.cu && /tmp/l2_probe
 #include <cstdio>
 #include <cstdint>
+#include <cstdlib>
 #include <cuda_runtime.h>
 
 __global__ void __launch_bounds__(512) read_ldg(const uint4* __restrict__ buf, size_t n16, int reps, unsigned* sink) {
@@ -49,6 +50,48 @@ __global__ void __launch_bounds__(512) read_cpasync(const uint4* __restrict__ bu
   if (acc == 0x12345678u) *sink = acc;
 }
 
+// random ROW gather: each group of 8 lanes reads one 128-byte piece of a random 512-byte row (the access pattern of the
+// gathered GEMM's producers), UNROLL independent pieces in flight per thread
+template <int UNROLL>
+__global__ void __launch_bounds__(512) gather_rows(const uint4* __restrict__ buf, const int* __restrict__ rows, size_t nidx,
+                                                   int reps, unsigned* sink) {
+  unsigned acc = 0;
+  const size_t gstride = ((size_t)gridDim.x * blockDim.x) >> 3;   // row slots per sweep
+  const size_t slot0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  const int piece = threadIdx.x & 7;
+  for (int r = 0; r < reps; ++r)
+    for (size_t i = slot0; i + (UNROLL - 1) * gstride < nidx; i += gstride * UNROLL) {
+      uint4 v[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const int row = rows[i + u * gstride];
+        const uint4* src = buf + (size_t)row * 32 + (r & 3) * 8 + piece;   // 512-byte rows = 32 pieces; quarter r & 3
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(v[u].x), "=r"(v[u].y), "=r"(v[u].z), "=r"(v[u].w) : "l"(src));
+      }
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) acc ^= v[u].x ^ v[u].y ^ v[u].z ^ v[u].w;
+    }
+  if (acc == 0x12345678u) *sink = acc;
+}
+
+template <int UNROLL>
+static void run_gather(const uint4* buf, const int* rows, size_t nidx, unsigned* sink, int blocks) {
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  const int reps = 8;
+  for (int it = 0; it < 2; ++it) {
+    cudaEventRecord(e0);
+    gather_rows<UNROLL><<<blocks, 512>>>(buf, rows, nidx, reps, sink);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+  }
+  float ms;
+  cudaEventElapsedTime(&ms, e0, e1);
+  printf("random 128-byte row pieces from a 64 MB buffer, %d in flight per thread, %d x 512 threads: %.1f GB/s\n", UNROLL, blocks,
+         (double)nidx * 128 * reps / ms / 1e6);
+}
+
 int main() {
   unsigned* sink;
   cudaMalloc(&sink, 4);
@@ -75,6 +118,21 @@ int main() {
              (double)bytes * reps / ms / 1e6, mb <= 96 ? "L2-resident" : "HBM");
     }
     cudaFree(buf);
+  }
+  {
+    const size_t bytes = 64ull << 20, nrows = bytes / 512, nidx = 4ull << 20;
+    uint4* buf; int* rows;
+    cudaMalloc(&buf, bytes); cudaMemset(buf, 1, bytes);
+    cudaMalloc(&rows, nidx * sizeof(int));
+    int* h = (int*)malloc(nidx * sizeof(int));
+    unsigned long long st = 88172645463325252ull;
+    for (size_t i = 0; i < nidx; ++i) { st ^= st << 13; st ^= st >> 7; st ^= st << 17; h[i] = (int)(st % nrows); }
+    cudaMemcpy(rows, h, nidx * sizeof(int), cudaMemcpyHostToDevice);
+    run_gather<1>(buf, rows, nidx, sink, 148 * 2);
+    run_gather<4>(buf, rows, nidx, sink, 148 * 2);
+    run_gather<8>(buf, rows, nidx, sink, 148 * 2);
+    run_gather<8>(buf, rows, nidx, sink, 148 * 4);
+    run_gather<4>(buf, rows, nidx, sink, 148);
   }
   printf("%s\n", cudaGetErrorString(cudaDeviceSynchronize()));
   return 0;
