@@ -773,6 +773,14 @@ def run_gpu_arm(args):
             if mma_factor != 1:
                 r["executed"] = {"achieved": ach * mma_factor, "unit": unit, "frac": ach * mma_factor / peak,
                                  "what": "MMA FLOPs issued to the tensor pipe (3 per algorithmic FLOP)"}
+            if name.startswith("sg") and args.precision != "fp32":
+                # the gathered operand: rows x channels of layer-1 output fetched through L2 (fp32 in the split path,
+                # bf16 in the bf16 path); each source row is gathered ~16 times, so this traffic never reaches HBM
+                rows_k = {"sg1_gather_layer2_maxpool": (clouds * 512 * 32, 128), "sg2_gather_layer2_maxpool": (clouds * 256 * 32, 256)}[name]
+                gb = rows_k[0] * rows_k[1] * (4 if args.precision == "split" else 2) / 1e9
+                r["l2_gather"] = {"GB_per_launch": round(gb, 3), "GBps": round(gb / sec, 1),
+                                  "what": "gathered P rows (L2 -> SM); scripts/l2_probe.cu measures 14-20 TB/s for random 128-byte "
+                                          "row pieces when enough loads are in flight: the producers, not L2, bound this stage"}
         elif name.startswith("knn"):
             r["note"] = ("fp32 ALU + selection bound, not HBM bound (SURVEY 8d); the HBM fraction is reported on the compulsory "
                          "bytes as the contract asks")

@@ -882,6 +882,17 @@ int launch_split_rowgemm(const TcGemm& g, cudaStream_t st) {
   return split_rowgemm_launch<128, 3>(g, st);
 }
 
+// 16-byte read-only global load as a VOLATILE asm: ptxas moves plain __ldg loads freely -- in the gather producers it
+// sank the loads of the next half-stage behind the stores of the current one (SASS: all 16 LDG.128 of a job issued back
+// to back right before the barrier arrival), so nothing was in flight while the operand was formed and every job began
+// with a full L2 latency (50 % of the producers' samples).  Volatile asm statements keep their program order relative to
+// the (volatile) st.shared of the operand.
+__device__ __forceinline__ float4 ldg_nc_pinned(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+
 // ============================================================================================== gathered GEMM
 //   D^T[ch, r] = sum_k W[ch, k] * relu(P[rows[r], k] - Q[r / 32, k])     P [*, K] and Q [M / 32, K] fp32 (Q[g, k] =
 //   W1x[k, 0:3] . centre_g, written by centre_proj_f32_kernel)
@@ -891,12 +902,13 @@ int launch_split_rowgemm(const TcGemm& g, cudaStream_t st) {
 // Producers (8 warps): P rows are fp32 in global memory; they are loaded one half-stage ahead into registers (fully
 // coalesced LDG.128, the row ids one TILE ahead), relu(P - Q) is formed in fp32, split into hi / lo and each plane is
 // written with one swizzled st.shared -- the operand is written once and never re-read by the producers.
-template <int ROWS, int NST>
-__global__ void __launch_bounds__(SG_THREADS, 1) split_gather_kernel(const TcGemm g) {
+// PW: producer warps (8 or 16; 16 = twice the warps per scheduler to hide the latencies of the producer chain)
+template <int ROWS, int NST, int PW>
+__global__ void __launch_bounds__((5 + PW) * 32, 1) split_gather_kernel(const TcGemm g) {
   extern __shared__ __align__(1024) uint8_t sgg_smem_raw[];
   const uint32_t smem_base = (smem_u32(sgg_smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = sgg_smem_raw + (smem_base - smem_u32(sgg_smem_raw));
-  constexpr int EPI = 4, PROD_THREADS = 256;
+  constexpr int EPI = 4, PROD_THREADS = PW * 32, THREADS = (5 + PW) * 32, RP = PW * 4;   // RP: rows per producer pass
   constexpr uint32_t X_PLANE = ROWS * 128, STAGE = 2 * X_PLANE;
   const int kblocks = g.K / KB;
   const uint32_t w_plane = (uint32_t)kblocks * TILE16K;          // resident: [W hi kblocks tiles][W lo kblocks tiles]
@@ -938,7 +950,7 @@ __global__ void __launch_bounds__(SG_THREADS, 1) split_gather_kernel(const TcGem
   }
   {  // resident weights of this channel block: both planes, swizzled [128 ch x 64 k] tiles per k-block
     const int chunks = kblocks * 128 * 8;
-    for (int id = tid; id < chunks; id += SG_THREADS) {
+    for (int id = tid; id < chunks; id += THREADS) {
       const int c = id & 7, r = (id >> 3) & 127, kb = id >> 10;
       const size_t off = (size_t)r * g.ldw + kb * KB + c * 8;
       *reinterpret_cast<uint4*>(smem_gen + (size_t)kb * TILE16K + sw128(r, c)) = *reinterpret_cast<const uint4*>(Whi + off);
@@ -953,7 +965,7 @@ __global__ void __launch_bounds__(SG_THREADS, 1) split_gather_kernel(const TcGem
 
   if (warp > EPI) {
     // =========================================================== producers
-    constexpr int CH = ROWS / 32;                 // chunks per thread per stage (rows r0 + 32 i: one per group)
+    constexpr int CH = ROWS / RP;                 // chunks per thread per stage (rows r0 + RP i)
     constexpr int QV = (ROWS / 32) * 16;          // float4 pieces of one stage's Q tile ([groups][64 ch] fp32)
     const int pt = tid - (EPI + 1) * 32, gc = pt & 7, r0 = pt >> 3;
     int my_tiles = 0;
@@ -987,7 +999,7 @@ __global__ void __launch_bounds__(SG_THREADS, 1) split_gather_kernel(const TcGem
     auto fetch_ids = [&](int ti, int (&dst)[CH]) {
       const int row0 = (tile_begin + rank + ti * step) * ROWS;
 #pragma unroll
-      for (int i = 0; i < CH; ++i) dst[i] = g.rows[row0 + r0 + 32 * i];
+      for (int i = 0; i < CH; ++i) dst[i] = g.rows[row0 + r0 + RP * i];
     };
     // loads of half h (chunks h*HC .. h*HC+HC-1) of k-block kb, rows taken from the current or the next tile's ids
     auto load_half = [&](int h, int kb, bool next_tile) {
@@ -997,16 +1009,16 @@ __global__ void __launch_bounds__(SG_THREADS, 1) split_gather_kernel(const TcGem
         // piece gc and piece 8 + gc of the row's sixteen 16-byte pieces: the eight lanes of a row read 128 contiguous
         // bytes per instruction (whole sectors; with pieces 2 gc, 2 gc + 1 every sector was fetched by two instructions)
         const float4* src = reinterpret_cast<const float4*>(P + (size_t)id * g.ldx + kb * KB) + gc;
-        buf[h][i][0] = __ldg(src);
-        buf[h][i][1] = __ldg(src + 8);
+        buf[h][i][0] = ldg_nc_pinned(src);
+        buf[h][i][1] = ldg_nc_pinned(src + 8);
       }
     };
     auto store_half = [&](int h, int slot, uint32_t st_addr) {
 #pragma unroll
       for (int i = 0; i < HC; ++i) {
-        const int ci = h * HC + i, r = r0 + 32 * ci;
+        const int ci = h * HC + i, r = r0 + RP * ci;
         float4 q0, q1;   // channels 4 gc .. + 3 and 32 + 4 gc .. + 3
-        const uint32_t qa = qring_s + slot * (QV * 16) + ci * 256 + gc * 16;
+        const uint32_t qa = qring_s + slot * (QV * 16) + (r >> 5) * 256 + gc * 16;
         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(q0.x), "=f"(q0.y), "=f"(q0.z), "=f"(q0.w) : "r"(qa));
         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(q1.x), "=f"(q1.y), "=f"(q1.z), "=f"(q1.w) : "r"(qa + 128));
         const float4 p0 = buf[h][i][0], p1 = buf[h][i][1];
@@ -1030,7 +1042,7 @@ __global__ void __launch_bounds__(SG_THREADS, 1) split_gather_kernel(const TcGem
       load_half(1, 0, false);
       q_fetch(0);
       q_commit(0);
-      asm volatile("bar.sync 2, 256;" ::: "memory");
+      asm volatile("bar.sync 2, %0;" ::"n"(PROD_THREADS) : "memory");
       if (jobs > 1) q_fetch(1);
     }
     for (int j = 0; j < jobs; ++j) {
@@ -1043,6 +1055,7 @@ __global__ void __launch_bounds__(SG_THREADS, 1) split_gather_kernel(const TcGem
       mbar_wait(empty_bar + 8 * s, ph ^ 1);
       store_half(0, j & 1, st_addr);
       if (more) load_half(0, nkb, new_tile);      // the registers of half 0 are free again: next job's half 0
+      __syncwarp();                               // scheduling fence: ptxas must not sink those loads behind half 1
       store_half(1, j & 1, st_addr);
       fence_proxy_async();
       mbar_arrive(full_bar + 8 * s);
@@ -1054,7 +1067,7 @@ __global__ void __launch_bounds__(SG_THREADS, 1) split_gather_kernel(const TcGem
       }
       if (more) {
         q_commit((j + 1) & 1);                    // the tile of job j + 1 (fetched one stage ago) -> its ring slot
-        asm volatile("bar.sync 2, 256;" ::: "memory");
+        asm volatile("bar.sync 2, %0;" ::"n"(PROD_THREADS) : "memory");
         if (j + 2 < jobs) q_fetch(j + 2);
       }
     }
@@ -1097,28 +1110,22 @@ __global__ void __launch_bounds__(SG_THREADS, 1) split_gather_kernel(const TcGem
       tc_fence_after();
       const uint32_t t_addr = tmem_base + lane_base + buf * ROWS;
 #pragma unroll 1
-      for (int c64 = 0; c64 < ROWS / 64; ++c64) {
-        float v[64];
-        tmem_ld64(t_addr + c64 * 64, v);
+      for (int c32 = 0; c32 < ROWS / 32; ++c32) {   // one group of 32 neighbours per TMEM load
+        float v[32];
+        tmem_ld32(t_addr + c32 * 32, v);
 #pragma unroll
         for (int w = 32; w >= 2; w >>= 1) {
 #pragma unroll
-          for (int i = 0; i < w / 2; ++i) {
-            v[i] = fmaxf(v[i], v[i + w / 2]);
-            v[32 + i] = fmaxf(v[32 + i], v[32 + i + w / 2]);
-          }
+          for (int i = 0; i < w / 2; ++i) v[i] = fmaxf(v[i], v[i + w / 2]);
         }
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          float x = v[32 * h] + bv;
-          if (g.relu) x = fmaxf(x, 0.f);
-          const size_t grow = (size_t)(row0 >> 5) + c64 * 2 + h;
-          if (g.Yf) g.Yf[grow * g.ldyf + ch] = x;
-          if (Ybhi) {
-            const __half hi = __float2half_rn(x);
-            Ybhi[grow * g.ldyb + ch] = hi;
-            Yblo[grow * g.ldyb + ch] = __float2half_rn(x - __half2float(hi));
-          }
+        float x = v[0] + bv;
+        if (g.relu) x = fmaxf(x, 0.f);
+        const size_t grow = (size_t)(row0 >> 5) + c32;
+        if (g.Yf) g.Yf[grow * g.ldyf + ch] = x;
+        if (Ybhi) {
+          const __half hi = __float2half_rn(x);
+          Ybhi[grow * g.ldyb + ch] = hi;
+          Yblo[grow * g.ldyb + ch] = __float2half_rn(x - __half2float(hi));
         }
       }
       tc_fence_before();
@@ -1240,8 +1247,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SG_THREADS, 1) split
       for (int i = 0; i < HC; ++i) {
         const int id = next_tile ? ids_n[h * HC + i] : ids[h * HC + i];
         const float4* src = reinterpret_cast<const float4*>(P + (size_t)id * g.ldx + kb * KB + gc * 8);
-        buf[h][i][0] = __ldg(src);
-        buf[h][i][1] = __ldg(src + 1);
+        buf[h][i][0] = ldg_nc_pinned(src);
+        buf[h][i][1] = ldg_nc_pinned(src + 1);
       }
     };
     auto store_half = [&](int h, int slot, uint32_t st_addr) {
@@ -1282,7 +1289,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SG_THREADS, 1) split
       const bool new_tile = more && nkb == 0;
       mbar_wait(empty_bar + 8 * s, ph ^ 1);
       store_half(0, j & 1, st_addr);
-      if (more) load_half(0, nkb, new_tile);
+      if (more) load_half(0, nkb, new_tile);      // (a scheduling fence here, as in split_gather_kernel, measured slower: 0.294 vs 0.281 ms)
       store_half(1, j & 1, st_addr);
       fence_proxy_async();
       mbar_arrive(full_bar + 8 * s);
@@ -1355,28 +1362,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SG_THREADS, 1) split
       tc_fence_after();
       const uint32_t t_addr = tmem_base + lane_base + buf * NPAIR;
 #pragma unroll 1
-      for (int c64 = 0; c64 < NPAIR / 64; ++c64) {
-        float v[64];
-        tmem_ld64(t_addr + c64 * 64, v);
+      for (int c32 = 0; c32 < NPAIR / 32; ++c32) {   // one group of 32 neighbours per TMEM load
+        float v[32];
+        tmem_ld32(t_addr + c32 * 32, v);
 #pragma unroll
         for (int w = 32; w >= 2; w >>= 1) {
 #pragma unroll
-          for (int i = 0; i < w / 2; ++i) {
-            v[i] = fmaxf(v[i], v[i + w / 2]);
-            v[32 + i] = fmaxf(v[32 + i], v[32 + i + w / 2]);
-          }
+          for (int i = 0; i < w / 2; ++i) v[i] = fmaxf(v[i], v[i + w / 2]);
         }
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          float x = v[32 * h] + bv;
-          if (g.relu) x = fmaxf(x, 0.f);
-          const size_t grow = (size_t)(row0 >> 5) + c64 * 2 + h;
-          if (g.Yf) g.Yf[grow * g.ldyf + ch] = x;
-          if (Ybhi) {
-            const __half hi = __float2half_rn(x);
-            Ybhi[grow * g.ldyb + ch] = hi;
-            Yblo[grow * g.ldyb + ch] = __float2half_rn(x - __half2float(hi));
-          }
+        float x = v[0] + bv;
+        if (g.relu) x = fmaxf(x, 0.f);
+        const size_t grow = (size_t)(row0 >> 5) + c32;
+        if (g.Yf) g.Yf[grow * g.ldyf + ch] = x;
+        if (Ybhi) {
+          const __half hi = __float2half_rn(x);
+          Ybhi[grow * g.ldyb + ch] = hi;
+          Yblo[grow * g.ldyb + ch] = __float2half_rn(x - __half2float(hi));
         }
       }
       tc_fence_before();
@@ -1409,13 +1410,13 @@ static int split_gather_pair_launch(const TcGemm& g, cudaStream_t st) {
   return 0;
 }
 
-template <int ROWS, int NST>
+template <int ROWS, int NST, int PW>
 static int split_gather_launch(const TcGemm& g, cudaStream_t st) {
   const int kblocks = g.K / KB;
   const size_t smem = 1024 + 2 * (size_t)kblocks * TILE16K + (size_t)NST * 2 * ROWS * 128 + 8 * (2 * NST + 4) + 32 +
                       2 * (size_t)(ROWS / 32) * 64 * sizeof(float);
   PZ_REQUIRE(smem <= 232448, PZ_ERR_UNSUPPORTED, "split_gather: needs %zu B of shared memory (K=%d)", smem, g.K);
-  auto kern = split_gather_kernel<ROWS, NST>;
+  auto kern = split_gather_kernel<ROWS, NST, PW>;
   PZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int nsets = (g.rows_per_wset > 0 && g.M > g.rows_per_wset) ? 2 : 1;
   const int nparts = nsets * (g.Nout / 128);
@@ -1423,7 +1424,7 @@ static int split_gather_launch(const TcGemm& g, cudaStream_t st) {
   int per = kNumSMs / nparts;
   if (per > tiles_per_part) per = tiles_per_part;
   if (per < 1) per = 1;
-  kern<<<per * nparts, SG_THREADS, smem, st>>>(g);
+  kern<<<per * nparts, (5 + PW) * 32, smem, st>>>(g);
   PZ_LAUNCH_CHECK();
   return 0;
 }
@@ -1442,7 +1443,8 @@ int launch_split_gather(const TcGemm& g, cudaStream_t st) {
     PZ_REQUIRE(g.W[1] && g.Wlo[1] && g.M == 2 * g.rows_per_wset, PZ_ERR_ARG, "split_gather: two weight sets need M == 2*rows_per_wset");
   if (g.K <= 128) {
     PZ_REQUIRE(g.M % (256 * nsets) == 0, PZ_ERR_UNSUPPORTED, "split_gather: M=%d must be a multiple of %d", g.M, 256 * nsets);
-    return split_gather_launch<256, 2>(g, st);
+    static const bool pw16 = getenv("PZ_SG_PW16") != nullptr;   // A/B hook: 16 producer warps (measured slower: 0.242 vs 0.229 ms)
+    return pw16 ? split_gather_launch<256, 2, 16>(g, st) : split_gather_launch<256, 2, 8>(g, st);
   }
   PZ_REQUIRE(g.M % (128 * nsets) == 0, PZ_ERR_UNSUPPORTED, "split_gather: M=%d must be a multiple of %d", g.M, 128 * nsets);
   // 256 output channels: one CTA pair per tile (cta_group::2), every gathered row formed once for both channel blocks
@@ -1450,7 +1452,7 @@ int launch_split_gather(const TcGemm& g, cudaStream_t st) {
   static const int pair_nst = getenv("PZ_SG_PAIR_NST") ? atoi(getenv("PZ_SG_PAIR_NST")) : 3;
   if (g.Nout == 256 && g.M % (256 * nsets) == 0 && !no_pair)
     return pair_nst == 2 ? split_gather_pair_launch<2>(g, st) : split_gather_pair_launch<3>(g, st);
-  return split_gather_launch<128, 2>(g, st);
+  return split_gather_launch<128, 2, 8>(g, st);
 }
 
 // fp32 [rows, cols] (row stride ldi) -> fp16 hi / lo planes (row stride ldo)
