@@ -1444,6 +1444,7 @@ int launch_split_gather(const TcGemm& g, cudaStream_t st) {
   if (g.K <= 128) {
     PZ_REQUIRE(g.M % (256 * nsets) == 0, PZ_ERR_UNSUPPORTED, "split_gather: M=%d must be a multiple of %d", g.M, 256 * nsets);
     static const bool pw16 = getenv("PZ_SG_PW16") != nullptr;   // A/B hook: 16 producer warps (measured slower: 0.242 vs 0.229 ms)
+    // (128-row stages, three or four deep, measured slower as well: 0.258 / 0.262 ms)
     return pw16 ? split_gather_launch<256, 2, 16>(g, st) : split_gather_launch<256, 2, 8>(g, st);
   }
   PZ_REQUIRE(g.M % (128 * nsets) == 0, PZ_ERR_UNSUPPORTED, "split_gather: M=%d must be a multiple of %d", g.M, 128 * nsets);
