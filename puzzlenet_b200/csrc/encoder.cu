@@ -1063,17 +1063,26 @@ __global__ void __launch_bounds__(256) centre_proj_f32_kernel(const float* __res
     cp_w[i] = (set == 0 ? w1a : w1b)[(size_t)k * ldw1 + d];
   }
   __syncthreads();
-  const size_t total = (size_t)rows * C1;
-  for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (size_t)gridDim.x * 256) {
-    const int s = (int)(e / C1), k = (int)(e - (size_t)s * C1);
-    const float* w = cp_w + ((s / rows_per_set == 0 ? 0 : C1) + k) * 3;
+  // four consecutive channels of a row per thread: one 16-byte store, 32-bit index arithmetic (C1 % 4 == 0, rows * C1 < 2^31)
+  const unsigned c4 = (unsigned)C1 >> 2, total4 = (unsigned)rows * c4;
+  for (unsigned e = blockIdx.x * 256u + threadIdx.x; e < total4; e += gridDim.x * 256u) {
+    const unsigned s = e / c4, k = (e - s * c4) * 4;
+    const float* w = cp_w + (((int)s / rows_per_set == 0 ? 0 : C1) + (int)k) * 3;
     const float* c = centres + (size_t)s * 3;
-    Q[e] = fmaf(w[0], c[0], fmaf(w[1], c[1], w[2] * c[2]));
+    const float cx = c[0], cy = c[1], cz = c[2];
+    float4 q;
+    q.x = fmaf(w[0], cx, fmaf(w[1], cy, w[2] * cz));
+    q.y = fmaf(w[3], cx, fmaf(w[4], cy, w[5] * cz));
+    q.z = fmaf(w[6], cx, fmaf(w[7], cy, w[8] * cz));
+    q.w = fmaf(w[9], cx, fmaf(w[10], cy, w[11] * cz));
+    *reinterpret_cast<float4*>(Q + (size_t)s * C1 + k) = q;
   }
 }
 static int launch_centre_proj_f32(const float* centres, const float* w1a, const float* w1b, int ldw1, int rows_per_set, int rows,
                                   int C1, float* Q, cudaStream_t st) {
-  const size_t total = (size_t)rows * C1, want = (total + 255) / 256;
+  PZ_REQUIRE(C1 % 4 == 0 && (size_t)rows * C1 < (1ull << 31) && ((uintptr_t)Q & 15) == 0, PZ_ERR_UNSUPPORTED,
+             "centre projection: needs C1 %% 4 == 0, rows * C1 < 2^31 and a 16-byte aligned Q");
+  const size_t total = (size_t)rows * C1 / 4, want = (total + 255) / 256;
   const unsigned blocks = (unsigned)(want < (size_t)kNumSMs * 8 ? want : (size_t)kNumSMs * 8);
   centre_proj_f32_kernel<<<blocks, 256, (size_t)2 * C1 * 3 * sizeof(float), st>>>(centres, w1a, w1b, ldw1, rows_per_set, rows, C1, Q);
   PZ_LAUNCH_CHECK();
