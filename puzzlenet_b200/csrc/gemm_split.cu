@@ -9,13 +9,17 @@
 // Operands are scaled nowhere: |x| < 65504 is required of every activation (true of this network by four orders of
 // magnitude); the fp16 conversions saturate instead of producing infinities.
 //
-// Two kernels, both persistent, warp-specialised (epilogue warps / one MMA-issuing thread / producers) with an smem
-// stage ring and a double-buffered TMEM accumulator like their bf16 counterparts (gemm_tc_rows.cu, gemm_tc.cu):
-//   split_rowgemm_kernel : Y[row, ch] row-major epilogue for every plain nn.Linear (layer 1 of the grouped MLPs over
-//                          source points, q|k and v projections, out-projection with residual, encoder tail)
-//   split_gather_kernel  : grouped-MLP layer 2 with the gathered operand relu(P[j] - Q[s]) formed IN REGISTERS from
-//                          fp32 P rows (global -> registers -> one swizzled st.shared per plane) and the max over the
-//                          32 neighbours in the epilogue (pointnet_util.py:123-130 + model5_b.py:452-454, :459-461)
+// The kernels, all persistent and warp-specialised (epilogue warps / one MMA-issuing thread / producers) with an smem
+// stage ring and a double-buffered TMEM accumulator:
+//   split_rowgemm_pair_kernel : Y[row, ch] row-major GEMM on a CTA PAIR (tcgen05.mma.cta_group::2, M = 256 rows), operands
+//                               by TMA, the CTA's weight half resident where it fits; every plain nn.Linear (layer 1 of the
+//                               grouped MLPs over source points, q|k and v projections, out-projection with residual, tail)
+//   split_rowgemm_kernel      : the one-CTA cp.async version (shapes that do not tile by 256 rows; PZ_RG_NO_PAIR)
+//   split_gather_kernel       : grouped-MLP layer 2 with the gathered operand relu(P[j] - Q[s]) formed IN REGISTERS from
+//                               fp32 P rows (global -> registers -> swizzled st.shared per plane) and the max over the 32
+//                               neighbours in the epilogue (pointnet_util.py:123-130 + model5_b.py:452-454, :459-461)
+//   split_gather_pair_kernel  : the same for 256 output channels on a CTA pair: each gathered row is formed once for both
+//                               128-channel blocks
 #include <cuda.h>   // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint)
 #include <cuda_fp16.h>
 #include <stdlib.h>

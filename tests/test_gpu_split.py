@@ -1,7 +1,12 @@
 """The split path (PZ_PREC_SPLIT: fp16 hi/lo operand planes, three tcgen05 MMAs per product, fp32 accumulation) block by
 block against the CPU oracle, at the fp32 tolerance of north_star (1e-4 relative; measured ~1e-6).  The kernels:
-split_rowgemm_kernel / split_gather_kernel (gemm_split.cu), attention_split_kernel (attention_split.cu),
-head_*_split_kernel (heads_split.cu).  End to end at B=64: tests/test_gpu_b64_parity.py."""
+split_rowgemm_pair_kernel / split_gather_kernel / split_gather_pair_kernel (gemm_split.cu: CTA pairs, TMA),
+attention_split_kernel (attention_split.cu), head_*_split_kernel (heads_split.cu), stem_tc_kernel<true> (encoder.cu); the
+one-CTA fallbacks (split_rowgemm_kernel, the 128-row split_gather_kernel, the FFMA stem) through their A/B hooks.
+End to end at B=64: tests/test_gpu_b64_parity.py."""
+import os
+import subprocess
+import sys
 import numpy as np
 import pytest
 import torch
@@ -96,3 +101,36 @@ def test_predict5_split_vs_oracle(cuda_model, state_dict, B):
     assert max(errs.values()) < TOL, errs
     assert rot < 0.01 and trans < 1e-4
     assert again[0].shape == out.shape
+
+
+_FALLBACK_SNIPPET = r"""
+import sys, types, torch
+sys.path.insert(0, %r)
+from oracle import parity, puzzle_oracle as po
+from puzzlenet_b200.model5_b import TouchedRegraster
+from puzzlenet_b200.weights import make_batch, synthetic_pairs, synthetic_state_dict
+sd = synthetic_state_dict(0)
+m = TouchedRegraster(types.SimpleNamespace(dataset="vase")); m.load_state_dict(sd, strict=True); m.to("cuda:0").eval()
+m.precision = "split"
+fpc, mrpc = synthetic_pairs(2, seed=64)
+torch.manual_seed(1234)
+out, _, de_f, de_m = m.predict5(make_batch(fpc.cuda(), mrpc.cuda()), 0)
+torch.cuda.synchronize()
+torch.manual_seed(1234)
+ref = po.predict5(sd, fpc, mrpc)
+errs = [parity.rel(out, ref["out"]), parity.rel(de_f, ref["de_fpcb"]), parity.rel(de_m, ref["de_mrpcb"])]
+rot, trans = parity.pose_errors(out, ref["out"])
+print("FALLBACK", max(errs), rot, trans)
+assert max(errs) < 1e-4 and rot < 0.01 and trans < 1e-4, (errs, rot, trans)
+"""
+
+
+@pytest.mark.parametrize("env", [{"PZ_SG_NO_PAIR": "1", "PZ_RG_NO_PAIR": "1", "PZ_STEM_FFMA": "1"}, {"PZ_SG_PAIR_NST": "2", "PZ_SG_PW16": "1"}])
+def test_split_fallback_kernels(env):
+    """The A/B hooks select the one-CTA kernels (cp.async row GEMM, two-pass gather GEMM, FFMA stem) / the alternative
+    pipeline depths; they are read once per process, so the forward runs in a child process.  Same bounds as the default."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", _FALLBACK_SNIPPET % root], env={**os.environ, **env}, capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "FALLBACK" in r.stdout
