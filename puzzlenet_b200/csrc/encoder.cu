@@ -1774,6 +1774,23 @@ size_t predict_layout(int B, Arena& a, PredictScratch& s) {
 }
 }  // namespace
 
+namespace pz {
+namespace {
+__global__ void __launch_bounds__(256) stage_inputs_kernel(const float4* __restrict__ fpc, const float4* __restrict__ mrpc, size_t n16,
+                                                           float4* __restrict__ xyz, const int64_t* __restrict__ starts, int B,
+                                                           int64_t* __restrict__ st1, int64_t* __restrict__ st2) {
+  const size_t stride = (size_t)gridDim.x * 256;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < 2 * n16; i += stride) xyz[i] = i < n16 ? fpc[i] : mrpc[i - n16];
+  if (blockIdx.x == 0) {
+    for (int i = threadIdx.x; i < 4 * B; i += 256) {
+      const int row = i / B, c = i - row * B;
+      ((row & 1) ? st2 : st1)[(row >> 1) * B + c] = starts[i];
+    }
+  }
+}
+}  // namespace
+}  // namespace pz
+
 extern "C" size_t pz_predict5_workspace_bytes(int B) {
   if (B < 1) return 0;
   Arena a(nullptr, 0);
@@ -1806,14 +1823,21 @@ extern "C" int pz_predict5(const PzEncoderWeights* enc_host, const PzHeadWeights
              workspace_bytes, arena.used);
   prof_begin(st);
   const size_t cloud_bytes = (size_t)B * NPTS * 3 * sizeof(float);
-  PZ_CUDA(cudaMemcpyAsync(s.xyz, fpc, cloud_bytes, cudaMemcpyDeviceToDevice, st));
-  PZ_CUDA(cudaMemcpyAsync(s.xyz + (size_t)B * NPTS * 3, mrpc, cloud_bytes, cudaMemcpyDeviceToDevice, st));
-  // starts [4,B]: (Encoder s1, Encoder s2, Encoder2 s1, Encoder2 s2) -> st1 = rows 0,2; st2 = rows 1,3
-  const size_t sb = (size_t)B * sizeof(int64_t);
-  PZ_CUDA(cudaMemcpyAsync(s.st1, starts, sb, cudaMemcpyDeviceToDevice, st));
-  PZ_CUDA(cudaMemcpyAsync(s.st2, starts + B, sb, cudaMemcpyDeviceToDevice, st));
-  PZ_CUDA(cudaMemcpyAsync(s.st1 + B, starts + 2 * (size_t)B, sb, cudaMemcpyDeviceToDevice, st));
-  PZ_CUDA(cudaMemcpyAsync(s.st2 + B, starts + 3 * (size_t)B, sb, cudaMemcpyDeviceToDevice, st));
+  // both clouds into one [2B, 1024, 3] batch; starts [4,B]: (Encoder s1, Encoder s2, Encoder2 s1, Encoder2 s2) -> st1 =
+  // rows 0,2; st2 = rows 1,3.  One launch instead of six copy operations (each ~4 us of stream time).
+  if ((((uintptr_t)fpc | (uintptr_t)mrpc) & 15) == 0) {
+    stage_inputs_kernel<<<kNumSMs, 256, 0, st>>>(reinterpret_cast<const float4*>(fpc), reinterpret_cast<const float4*>(mrpc),
+                                                 cloud_bytes / 16, reinterpret_cast<float4*>(s.xyz), starts, B, s.st1, s.st2);
+    PZ_LAUNCH_CHECK();
+  } else {
+    PZ_CUDA(cudaMemcpyAsync(s.xyz, fpc, cloud_bytes, cudaMemcpyDeviceToDevice, st));
+    PZ_CUDA(cudaMemcpyAsync(s.xyz + (size_t)B * NPTS * 3, mrpc, cloud_bytes, cudaMemcpyDeviceToDevice, st));
+    const size_t sb = (size_t)B * sizeof(int64_t);
+    PZ_CUDA(cudaMemcpyAsync(s.st1, starts, sb, cudaMemcpyDeviceToDevice, st));
+    PZ_CUDA(cudaMemcpyAsync(s.st2, starts + B, sb, cudaMemcpyDeviceToDevice, st));
+    PZ_CUDA(cudaMemcpyAsync(s.st1 + B, starts + 2 * (size_t)B, sb, cudaMemcpyDeviceToDevice, st));
+    PZ_CUDA(cudaMemcpyAsync(s.st2 + B, starts + 3 * (size_t)B, sb, cudaMemcpyDeviceToDevice, st));
+  }
 
   prof_mark("stage_inputs", st);
   PzEncoderOutputs eo = {};

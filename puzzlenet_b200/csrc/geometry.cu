@@ -581,11 +581,341 @@ __global__ void __launch_bounds__(KNN_WARPS * 32, 3) knn_kernel(const float* __r
   }
 }
 
+// ======================================================================================
+// kNN for LARGE clouds (2048 < N <= KG_MAXN, the dataset shape 11000): block pruning.  The whole cloud is binned by
+// the CTA into an 8 x 8 x 8 grid over its bounding box and laid out in shared memory in Morton order of the cells
+// (histogram with one shared-memory atomic per point, a 512-entry scan, a cursor scatter), so that every run of 128
+// consecutive points -- a BLOCK, which a warp scans with one float4 per lane and plane -- is a compact region with its
+// own bounding box.  Per query the warp computes the distance to every block's box with the SAME rounded operations as
+// the point distances (sqdist3 to the clamped query; every operation is monotonic, so the bound never exceeds the
+// computed distance of a point inside), visits the blocks in ascending order of that bound and stops as soon as the
+// smallest remaining bound exceeds the current 32nd distance.  Distances are still ((dx^2 + dy^2) + dz^2) with
+// round-to-nearest multiplies and adds and the order is still (distance, ORIGINAL index): bit-identical to the exhaustive
+// scan (pointnet_util.py:118-119), of which a 11000-point cloud visits ~5 %.  (For N <= 2048 the same scheme was measured
+// SLOWER than the exhaustive kernel above -- 2080 vs 1328 warp instructions per query, profiles/r02_knn_block_pruning_
+// experiment.txt -- and is not used there.)
+// ======================================================================================
+constexpr int KG_BLK = 128;                 // points per block
+constexpr int KG_MAXN = 14336;              // 112 blocks: planes + permutation + boxes fit 227 KB
+constexpr int KG_WARPS = 16;                // warps per CTA (one CTA per SM: the cloud fills its shared memory)
+constexpr int KG_QPW = 8;                   // queries per warp (amortises binning the cloud)
+constexpr int KG_PB = 8;                    // points per thread and batch of the binning passes (loads issued together)
+constexpr int KG_CELLS = 512;
+__device__ __forceinline__ unsigned fkey(float x) {   // order-preserving image of a float (for redux min / max)
+  const unsigned b = __float_as_uint(x);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float fkey_inv(unsigned k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+__device__ __forceinline__ int kg_cell(float x, float y, float z, const float (&lo)[3], const float (&inv)[3]) {
+  const int ix = min(7, max(0, (int)((x - lo[0]) * inv[0])));
+  const int iy = min(7, max(0, (int)((y - lo[1]) * inv[1])));
+  const int iz = min(7, max(0, (int)((z - lo[2]) * inv[2])));
+  int c = 0;   // Morton order: bit 3 b + {0, 1, 2} = bit b of {x, y, z}
+#pragma unroll
+  for (int b = 0; b < 3; ++b) c |= (((ix >> b) & 1) << (3 * b)) | (((iy >> b) & 1) << (3 * b + 1)) | (((iz >> b) & 1) << (3 * b + 2));
+  return c;
+}
+
+__global__ void __launch_bounds__(KG_WARPS * 32, 1) knn_grid_kernel(const float* __restrict__ query,
+                                                                     const float* __restrict__ xyz, int S, int N, int K,
+                                                                     int64_t* __restrict__ out64,
+                                                                     int* __restrict__ out_rows32,
+                                                                     float* __restrict__ out_d2) {
+  extern __shared__ __align__(16) unsigned char kg_smem[];
+  const int nblk = (N + KG_BLK - 1) / KG_BLK, npad = nblk * KG_BLK, pstride = npad + 4;
+  float* pts = reinterpret_cast<float*>(kg_smem);                              // x / y / z planes, sorted order
+  unsigned short* perm = reinterpret_cast<unsigned short*>(pts + 3 * pstride); // sorted position -> original index
+  float* bbox = reinterpret_cast<float*>(perm + npad);                         // [nblk][6]: lo xyz, hi xyz
+  int* hist = reinterpret_cast<int*>(bbox + 6 * nblk);                         // [KG_CELLS]
+  unsigned* redk = reinterpret_cast<unsigned*>(hist + KG_CELLS);               // [KG_WARPS][6]
+  uint2* qkey = reinterpret_cast<uint2*>(redk + KG_WARPS * 6);                 // [KG_WARPS][64]
+  const int b = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* p = xyz + (size_t)b * N * 3;
+  const unsigned kmask = bitonic_keep_mask(lane);
+  uint2* myq = qkey + warp * 64;
+  const unsigned lt_mask = (1u << lane) - 1u;
+
+  // ---- bounding box of the cloud
+  unsigned kmin[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, kmax[3] = {0u, 0u, 0u};
+  constexpr int T = KG_WARPS * 32;
+  // every pass walks the cloud in batches of KG_PB points per thread whose 3 * KG_PB loads are issued together (the
+  // shared-memory atomics of the later passes would otherwise serialise one global-memory latency per point)
+  for (int base = tid; base < N; base += T * KG_PB) {
+    float v[KG_PB][3];
+#pragma unroll
+    for (int u = 0; u < KG_PB; ++u) {
+      const int i = min(base + u * T, N - 1);
+#pragma unroll
+      for (int d = 0; d < 3; ++d) v[u][d] = p[(size_t)i * 3 + d];
+    }
+#pragma unroll
+    for (int u = 0; u < KG_PB; ++u) {
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const unsigned kk = fkey(v[u][d]);
+        kmin[d] = min(kmin[d], kk);
+        kmax[d] = max(kmax[d], kk);
+      }
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const unsigned mn = __reduce_min_sync(0xffffffffu, kmin[d]), mx = __reduce_max_sync(0xffffffffu, kmax[d]);
+    if (lane == 0) { redk[warp * 6 + d] = mn; redk[warp * 6 + 3 + d] = mx; }
+  }
+  for (int i = tid; i < KG_CELLS; i += T) hist[i] = 0;
+  __syncthreads();
+  float lo[3], inv[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    unsigned mn = 0xffffffffu, mx = 0u;
+#pragma unroll
+    for (int w = 0; w < KG_WARPS; ++w) { mn = min(mn, redk[w * 6 + d]); mx = max(mx, redk[w * 6 + 3 + d]); }
+    lo[d] = fkey_inv(mn);
+    const float ext = fkey_inv(mx) - lo[d];
+    inv[d] = ext > 0.f ? 8.0f / ext : 0.f;
+  }
+  // ---- histogram of the cells, exclusive scan (cursor per cell), scatter in Morton order
+  for (int base = tid; base < N; base += T * KG_PB) {
+    float v[KG_PB][3];
+#pragma unroll
+    for (int u = 0; u < KG_PB; ++u) {
+      const int i = min(base + u * T, N - 1);
+#pragma unroll
+      for (int d = 0; d < 3; ++d) v[u][d] = p[(size_t)i * 3 + d];
+    }
+#pragma unroll
+    for (int u = 0; u < KG_PB; ++u)
+      if (base + u * T < N) atomicAdd(&hist[kg_cell(v[u][0], v[u][1], v[u][2], lo, inv)], 1);
+  }
+  __syncthreads();
+  if (warp == 0) {                      // 512 counts, 16 consecutive per lane
+    int loc[16], sum = 0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { loc[j] = hist[lane * 16 + j]; sum += loc[j]; }
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    int run = incl - sum;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { hist[lane * 16 + j] = run; run += loc[j]; }
+  }
+  __syncthreads();
+  for (int base = tid; base < N; base += T * KG_PB) {
+    float v[KG_PB][3];
+#pragma unroll
+    for (int u = 0; u < KG_PB; ++u) {
+      const int i = min(base + u * T, N - 1);
+#pragma unroll
+      for (int d = 0; d < 3; ++d) v[u][d] = p[(size_t)i * 3 + d];
+    }
+#pragma unroll
+    for (int u = 0; u < KG_PB; ++u) {
+      const int i = base + u * T;
+      if (i < N) {
+        const int pos = atomicAdd(&hist[kg_cell(v[u][0], v[u][1], v[u][2], lo, inv)], 1);
+        pts[pos] = v[u][0];
+        pts[pstride + pos] = v[u][1];
+        pts[2 * pstride + pos] = v[u][2];
+        perm[pos] = (unsigned short)i;
+      }
+    }
+  }
+  // the tail of the last block: far-away points (distance ~3e36); their index (N + something) is never read (K <= N)
+  for (int i = N + tid; i < npad; i += T) {
+    pts[i] = pts[pstride + i] = pts[2 * pstride + i] = 1e18f;
+    perm[i] = 0xffffu;
+  }
+  __syncthreads();
+  for (int blk = warp; blk < nblk; blk += KG_WARPS) {   // bounding boxes of the blocks (real points only)
+    const int i0 = blk * KG_BLK + lane * 4;
+    unsigned bmin[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, bmax[3] = {0u, 0u, 0u};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (i0 + j < N) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          const unsigned k = fkey(pts[d * pstride + i0 + j]);
+          bmin[d] = min(bmin[d], k);
+          bmax[d] = max(bmax[d], k);
+        }
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const unsigned mn = __reduce_min_sync(0xffffffffu, bmin[d]), mx = __reduce_max_sync(0xffffffffu, bmax[d]);
+      if (lane == 0) { bbox[blk * 6 + d] = fkey_inv(mn); bbox[blk * 6 + 3 + d] = fkey_inv(mx); }
+    }
+  }
+  __syncthreads();
+
+  // ---- queries
+  const int q0 = (blockIdx.x * KG_WARPS + warp) * KG_QPW;
+#pragma unroll 1
+  for (int w = 0; w < KG_QPW; ++w) {
+    const int q = q0 + w;
+    if (q >= S) break;                  // warp-uniform
+    const float* qp = query + ((size_t)b * S + q) * 3;
+    const float qx = qp[0], qy = qp[1], qz = qp[2];
+    unsigned td = 0xffffffffu, ti = 0xffffffffu;   // lane l holds the l-th smallest key so far
+    unsigned tau = 0xffffffffu;                    // distance bits of the current 32nd smallest
+    unsigned lbv[4];                               // lower bounds of blocks lane, lane + 32, lane + 64, lane + 96
+#pragma unroll
+    for (int sl = 0; sl < 4; ++sl) {
+      const int blk = sl * 32 + lane;
+      lbv[sl] = 0xffffffffu;
+      if (blk < nblk) {
+        const float cx = fminf(fmaxf(qx, bbox[blk * 6 + 0]), bbox[blk * 6 + 3]);
+        const float cy = fminf(fmaxf(qy, bbox[blk * 6 + 1]), bbox[blk * 6 + 4]);
+        const float cz = fminf(fmaxf(qz, bbox[blk * 6 + 2]), bbox[blk * 6 + 5]);
+        lbv[sl] = min(__float_as_uint(sqdist3(qx, qy, qz, cx, cy, cz)), 0xfffffffeu);
+      }
+    }
+#pragma unroll 1
+    while (true) {
+      const unsigned mine_lb = min(min(lbv[0], lbv[1]), min(lbv[2], lbv[3]));
+      const unsigned mlb = __reduce_min_sync(0xffffffffu, mine_lb);
+      if (mlb == 0xffffffffu || mlb > tau) break;   // every remaining point is farther than the 32nd
+      const int src = __ffs(__ballot_sync(0xffffffffu, mine_lb == mlb)) - 1;
+      int blk = 0;
+      if (lane == src) {                // the owning lane takes its first slot with that bound and marks it visited
+        const int sl = lbv[0] == mlb ? 0 : (lbv[1] == mlb ? 1 : (lbv[2] == mlb ? 2 : 3));
+        blk = sl * 32 + lane;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) lbv[u] = u == sl ? 0xffffffffu : lbv[u];
+      }
+      blk = __shfl_sync(0xffffffffu, blk, src);
+      const int i0 = blk * KG_BLK + lane * 4;
+      const float4 X = *reinterpret_cast<const float4*>(pts + i0);
+      const float4 Y = *reinterpret_cast<const float4*>(pts + pstride + i0);
+      const float4 Z = *reinterpret_cast<const float4*>(pts + 2 * pstride + i0);
+      unsigned db[4];
+      db[0] = __float_as_uint(sqdist3(qx, qy, qz, X.x, Y.x, Z.x));
+      db[1] = __float_as_uint(sqdist3(qx, qy, qz, X.y, Y.y, Z.y));
+      db[2] = __float_as_uint(sqdist3(qx, qy, qz, X.z, Y.z, Z.z));
+      db[3] = __float_as_uint(sqdist3(qx, qy, qz, X.w, Y.w, Z.w));
+      const bool have = tau != 0xffffffffu;
+      unsigned thr = tau;
+      if (!have) {                      // warp-uniform: nothing selected yet -> a bound from the lane minima
+        const unsigned lo01 = min(db[0], db[1]), hi01 = max(db[0], db[1]), lo23 = min(db[2], db[3]), hi23 = max(db[2], db[3]);
+        const unsigned m0 = min(lo01, lo23), m1 = min(max(lo01, lo23), min(hi01, hi23));
+        unsigned hi = __reduce_max_sync(0xffffffffu, m0);   // >= 32 candidates are <= the largest lane minimum
+        unsigned lo2 = __reduce_min_sync(0xffffffffu, m1);
+        if (lo2 < hi) {
+#pragma unroll 1
+          for (int it = 0; it < 8 && lo2 < hi; ++it) {
+            const unsigned mid = lo2 + ((hi - lo2) >> 1);
+            const int c = __reduce_add_sync(0xffffffffu, (m0 <= mid ? 1 : 0) + (m1 <= mid ? 1 : 0));
+            if (c >= 32) hi = mid; else lo2 = mid + 1;
+          }
+        }
+        thr = hi;
+      }
+      thr = min(thr, 0xfffffffeu);
+      const int mine = (db[0] <= thr) + (db[1] <= thr) + (db[2] <= thr) + (db[3] <= thr);
+      int incl = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      const int c = __shfl_sync(0xffffffffu, incl, 31);
+      if (c == 0) continue;             // warp-uniform
+      const uint2 pm = *reinterpret_cast<const uint2*>(perm + i0);   // four 16-bit original indices
+      const unsigned idx4[4] = {pm.x & 0xffffu, pm.x >> 16, pm.y & 0xffffu, pm.y >> 16};
+      if (c <= 64) {
+        uint2* slot = myq + (incl - mine);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          if (db[t] <= thr) *slot++ = make_uint2(db[t], idx4[t]);
+        }
+        __syncwarp();
+        int o = 0;
+        if (!have && c >= 32) {         // nothing selected yet: the sorted first 32 entries are the list
+          const uint2 e = myq[lane];
+          const uint2 r = knn_sort_call(e.x, e.y, kmask);
+          td = r.x;
+          ti = r.y;
+          o = 32;
+        }
+        if (c - o > 12) {
+          for (; o < c; o += 32) {
+            const uint2 e = o + lane < c ? myq[o + lane] : make_uint2(0xffffffffu, 0xffffffffu);
+            knn_merge(td, ti, e.x, e.y, lane, kmask);
+          }
+        } else {
+#pragma unroll 1
+          for (; o < c; ++o) {
+            const uint2 e = myq[o];
+            knn_insert(td, ti, e.x, e.y, lane);
+          }
+        }
+        tau = __shfl_sync(0xffffffffu, td, 31);
+        __syncwarp();                   // the queue is rewritten by the next block / query
+        continue;
+      }
+      // ---- more than 64 candidates under the bound (ties, the padded block): 32 at a time through the merge network
+      int qn = 0;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const bool pass = db[t] <= thr;
+        const unsigned m = __ballot_sync(0xffffffffu, pass);
+        if (m == 0u) continue;
+        if (pass) myq[qn + __popc(m & lt_mask)] = make_uint2(db[t], idx4[t]);
+        qn += __popc(m);
+        __syncwarp();
+        if (qn >= 32) {
+          const uint2 e = myq[lane];
+          knn_merge(td, ti, e.x, e.y, lane, kmask);
+          tau = __shfl_sync(0xffffffffu, td, 31);
+          thr = min(thr, tau);
+          const int rem = qn - 32;
+          const uint2 carry = lane < rem ? myq[32 + lane] : make_uint2(0u, 0u);
+          __syncwarp();
+          if (lane < rem) myq[lane] = carry;
+          __syncwarp();
+          qn = rem;
+        }
+      }
+      if (qn > 0) {
+        const uint2 e = lane < qn ? myq[lane] : make_uint2(0xffffffffu, 0xffffffffu);
+        knn_merge(td, ti, e.x, e.y, lane, kmask);
+        __syncwarp();
+      }
+      tau = __shfl_sync(0xffffffffu, td, 31);
+    }
+    if (lane < K) {
+      const size_t o = ((size_t)b * S + q) * K + lane;
+      if (out64) out64[o] = (int64_t)ti;
+      if (out_rows32) out_rows32[o] = b * N + (int)ti;
+      if (out_d2) out_d2[o] = __uint_as_float(td);
+    }
+  }
+}
+
 int launch_knn(const float* query, const float* xyz, int B, int S, int N, int K, int64_t* out64,
                int* out_rows32, float* out_d2, cudaStream_t st) {
   PZ_REQUIRE(K >= 1 && K <= 32, PZ_ERR_UNSUPPORTED, "pz_knn: K=%d not in [1,32]", K);
   PZ_REQUIRE(N >= K, PZ_ERR_UNSUPPORTED, "pz_knn: N=%d < K=%d", N, K);
   PZ_REQUIRE(B <= 65535, PZ_ERR_UNSUPPORTED, "pz_knn: B=%d > 65535", B);
+  static const bool brute = getenv("PZ_KNN_BRUTE") != nullptr;   // A/B hook: the exhaustive scan for every N
+  if (!brute && N > KNN_CHUNK && N <= KG_MAXN && S >= 64) {        // large clouds (the dataset shape): block pruning
+    const int nblk = (N + KG_BLK - 1) / KG_BLK, npad = nblk * KG_BLK;
+    const size_t smem = (size_t)3 * (npad + 4) * sizeof(float) + (size_t)npad * sizeof(unsigned short) + (size_t)6 * nblk * sizeof(float) +
+                        KG_CELLS * sizeof(int) + KG_WARPS * 6 * sizeof(unsigned) + (size_t)KG_WARPS * 64 * sizeof(uint2);
+    PZ_REQUIRE(smem <= 232448, PZ_ERR_UNSUPPORTED, "pz_knn: N=%d needs %zu B of shared memory", N, smem);
+    PZ_CUDA(cudaFuncSetAttribute(knn_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((S + KG_WARPS * KG_QPW - 1) / (KG_WARPS * KG_QPW), B);
+    knn_grid_kernel<<<grid, KG_WARPS * 32, smem, st>>>(query, xyz, S, N, K, out64, out_rows32, out_d2);
+    PZ_LAUNCH_CHECK();
+    return 0;
+  }
   dim3 grid((S + KNN_WARPS * KNN_QPW - 1) / (KNN_WARPS * KNN_QPW), B);
   knn_kernel<<<grid, KNN_WARPS * 32, 0, st>>>(query, xyz, S, N, K, out64, out_rows32, out_d2);
   PZ_LAUNCH_CHECK();

@@ -105,6 +105,23 @@ def test_knn_heavy_ties(pu, N, dups):
     assert torch.equal(idx.cpu(), ref_idx)
 
 
+@pytest.mark.parametrize("B,S,N,K", [(2, 1024, 11000, 32), (1, 200, 14336, 32), (2, 64, 2049, 7), (1, 96, 4100, 32)])
+def test_knn_large_cloud_block_pruning(pu, B, S, N, K):
+    """N > 2048 takes knn_grid_kernel (cloud binned into a Morton-ordered grid, 128-point blocks pruned by their bounding
+    boxes): indices and distances must stay bit-identical to the exhaustive oracle, including clustered points, exact
+    duplicates and queries far outside the cloud."""
+    g = torch.Generator().manual_seed(N + S)
+    xyz = torch.rand(B, N, 3, generator=g) - 0.5
+    xyz[:, : N // 4] = xyz[:, : N // 4] * 0.05 + 0.3             # a dense cluster
+    xyz[0, 500:560] = xyz[0, 17]                                  # duplicates (ties broken by index)
+    q = xyz[:, :S].clone()
+    q[:, -3:] = torch.tensor([[5.0, 5.0, 5.0], [-4.0, 0.0, 0.0], [0.3, 0.3, 0.3]])
+    ref_idx, ref_d = po.knn_select(po.square_distance(q, xyz), K)
+    idx, d2 = pu.knn_point(K, xyz.to(DEV), q.to(DEV), return_dist=True)
+    assert torch.equal(d2.cpu(), ref_d)
+    assert torch.equal(idx.cpu(), ref_idx)
+
+
 def test_knn_rejects_k_above_32(pu):
     x = torch.rand(1, 100, 3, device=DEV)
     with pytest.raises(RuntimeError, match="K="):
