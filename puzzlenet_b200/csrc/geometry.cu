@@ -282,6 +282,9 @@ static int fps_launch_cluster(const float* xyz, int B, int N, const int64_t* sta
   return 0;
 }
 
+static int fps_grid_launch(const float* xyz, int B, int N, const int64_t* start, int S, int64_t* out64, int* out_rows32,
+                           float* new_xyz, cudaStream_t st);   // large clouds: block-pruned updates (defined next to the grid kNN)
+
 int launch_fps(const float* xyz, int B, int N, const int64_t* start, int S, int64_t* out64,
                int* out_rows32, float* new_xyz, cudaStream_t st) {
   if (const char* e = getenv("PZ_FPS_T")) {   // tuning experiment hook: threads per cloud for N <= 1024
@@ -293,6 +296,8 @@ int launch_fps(const float* xyz, int B, int N, const int64_t* start, int S, int6
       if (T == 1024) return fps_launch_t<1, 1024>(xyz, B, N, start, S, out64, out_rows32, new_xyz, st);
     }
   }
+  static const bool no_grid = getenv("PZ_FPS_NO_GRID") != nullptr;         // A/B hook
+  if (N > 4096 && N <= 14336 && S <= 8192 && !no_grid) return fps_grid_launch(xyz, B, N, start, S, out64, out_rows32, new_xyz, st);
   // large clouds, few enough of them that two CTAs per cloud still run in one wave: the 2-CTA cluster variant
   static const bool no_cluster = getenv("PZ_FPS_NO_CLUSTER") != nullptr;   // A/B hook
   if (N > 4096 && 4 * B <= kNumSMs && !no_cluster) {     // a handful of large clouds (assembly, dataset): 4 CTAs per cloud
@@ -897,6 +902,248 @@ __global__ void __launch_bounds__(KG_WARPS * 32, 1) knn_grid_kernel(const float*
       if (out_d2) out_d2[o] = __uint_as_float(td);
     }
   }
+}
+
+// ======================================================================================
+// FPS for LARGE clouds (4096 < N <= KG_MAXN) with block-pruned updates.  The exhaustive kernels above touch all N
+// running minima in every one of the S iterations; here the cloud is binned and Morton-ordered once (as in
+// knn_grid_kernel), every 128-point block keeps its current maximum of the running minima, and an iteration only
+// updates the blocks the new centroid can reach: a block is skipped when the distance from the centroid to its bounding
+// box -- computed with the same rounded operations as the point distances, so it never exceeds any of them -- is >= the
+// block's maximum (then fminf(md, d) = md for every point inside).  After a few dozen samples most blocks are skipped.
+// The selection is unchanged: arg-max of the running minima, lowest ORIGINAL index on ties (pointnet_util.py:67-72), so
+// the sampled indices are bit-identical.  One CTA of 16 warps per cloud; warp w owns blocks w, w + 16, ...: their running
+// minima live in registers (4 points per lane and block), lane j < 8 carries the box, the maximum and the arg-max key of
+// the warp's j-th block; per iteration one ballot finds the blocks to update, two redux give the warp's best key, one
+// CTA barrier and two more redux the winner.
+// ======================================================================================
+constexpr int FG_WARPS = 16, FG_T = FG_WARPS * 32, FG_SLOTS = 8;   // FG_SLOTS blocks per warp: KG_MAXN / 128 / 16 = 7
+__global__ void __launch_bounds__(FG_T, 1) fps_grid_kernel(const float* __restrict__ xyz, int N, int S,
+                                                           const int64_t* __restrict__ start, int64_t* __restrict__ out64,
+                                                           int* __restrict__ out_rows32, float* __restrict__ new_xyz) {
+  extern __shared__ __align__(16) unsigned char fg_smem[];
+  const int nblk = (N + KG_BLK - 1) / KG_BLK, npad = nblk * KG_BLK, pstride = npad + 4;
+  float* pts = reinterpret_cast<float*>(fg_smem);                              // x / y / z planes, Morton order
+  unsigned short* perm = reinterpret_cast<unsigned short*>(pts + 3 * pstride); // sorted position -> original index
+  float* bbox = reinterpret_cast<float*>(perm + npad);                         // [nblk][6]
+  int* hist = reinterpret_cast<int*>(bbox + 6 * nblk);                         // [KG_CELLS]
+  unsigned* redk = reinterpret_cast<unsigned*>(hist + KG_CELLS);               // [FG_WARPS][6]
+  unsigned* wkey = redk + FG_WARPS * 6;                                        // [2 parities][FG_WARPS][2] (hi, lo)
+  int* sel = reinterpret_cast<int*>(wkey + 2 * FG_WARPS * 2);                  // [S] picked original indices
+  const int c = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* p = xyz + (size_t)c * N * 3;
+  constexpr int T = FG_T;
+
+  // ---- bin the cloud (see knn_grid_kernel): bounding box, histogram of the 8 x 8 x 8 cells, scan, scatter
+  unsigned kmin[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, kmax[3] = {0u, 0u, 0u};
+  for (int base = tid; base < N; base += T * KG_PB) {
+    float v[KG_PB][3];
+#pragma unroll
+    for (int u = 0; u < KG_PB; ++u) {
+      const int i = min(base + u * T, N - 1);
+#pragma unroll
+      for (int d = 0; d < 3; ++d) v[u][d] = p[(size_t)i * 3 + d];
+    }
+#pragma unroll
+    for (int u = 0; u < KG_PB; ++u) {
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const unsigned kk = fkey(v[u][d]);
+        kmin[d] = min(kmin[d], kk);
+        kmax[d] = max(kmax[d], kk);
+      }
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const unsigned mn = __reduce_min_sync(0xffffffffu, kmin[d]), mx = __reduce_max_sync(0xffffffffu, kmax[d]);
+    if (lane == 0) { redk[warp * 6 + d] = mn; redk[warp * 6 + 3 + d] = mx; }
+  }
+  for (int i = tid; i < KG_CELLS; i += T) hist[i] = 0;
+  if (tid < 2 * FG_WARPS * 2) wkey[tid] = 0u;
+  __syncthreads();
+  float lo[3], inv[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    unsigned mn = 0xffffffffu, mx = 0u;
+#pragma unroll
+    for (int w = 0; w < FG_WARPS; ++w) { mn = min(mn, redk[w * 6 + d]); mx = max(mx, redk[w * 6 + 3 + d]); }
+    lo[d] = fkey_inv(mn);
+    const float ext = fkey_inv(mx) - lo[d];
+    inv[d] = ext > 0.f ? 8.0f / ext : 0.f;
+  }
+  for (int base = tid; base < N; base += T * KG_PB) {
+    float v[KG_PB][3];
+#pragma unroll
+    for (int u = 0; u < KG_PB; ++u) {
+      const int i = min(base + u * T, N - 1);
+#pragma unroll
+      for (int d = 0; d < 3; ++d) v[u][d] = p[(size_t)i * 3 + d];
+    }
+#pragma unroll
+    for (int u = 0; u < KG_PB; ++u)
+      if (base + u * T < N) atomicAdd(&hist[kg_cell(v[u][0], v[u][1], v[u][2], lo, inv)], 1);
+  }
+  __syncthreads();
+  if (warp == 0) {
+    int loc[16], sum = 0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { loc[j] = hist[lane * 16 + j]; sum += loc[j]; }
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    int run = incl - sum;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { hist[lane * 16 + j] = run; run += loc[j]; }
+  }
+  __syncthreads();
+  for (int base = tid; base < N; base += T * KG_PB) {
+    float v[KG_PB][3];
+#pragma unroll
+    for (int u = 0; u < KG_PB; ++u) {
+      const int i = min(base + u * T, N - 1);
+#pragma unroll
+      for (int d = 0; d < 3; ++d) v[u][d] = p[(size_t)i * 3 + d];
+    }
+#pragma unroll
+    for (int u = 0; u < KG_PB; ++u) {
+      const int i = base + u * T;
+      if (i < N) {
+        const int pos = atomicAdd(&hist[kg_cell(v[u][0], v[u][1], v[u][2], lo, inv)], 1);
+        pts[pos] = v[u][0];
+        pts[pstride + pos] = v[u][1];
+        pts[2 * pstride + pos] = v[u][2];
+        perm[pos] = (unsigned short)i;
+      }
+    }
+  }
+  for (int i = N + tid; i < npad; i += T) {      // padding of the last block: never selected (running minimum 0, largest index)
+    pts[i] = pts[pstride + i] = pts[2 * pstride + i] = 0.f;
+    perm[i] = 0xffffu;
+  }
+  __syncthreads();
+  for (int blk = warp; blk < nblk; blk += FG_WARPS) {   // bounding boxes of the blocks (real points only)
+    const int i0 = blk * KG_BLK + lane * 4;
+    unsigned bmin[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, bmx[3] = {0u, 0u, 0u};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (i0 + j < N) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          const unsigned k = fkey(pts[d * pstride + i0 + j]);
+          bmin[d] = min(bmin[d], k);
+          bmx[d] = max(bmx[d], k);
+        }
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const unsigned mn = __reduce_min_sync(0xffffffffu, bmin[d]), mx = __reduce_max_sync(0xffffffffu, bmx[d]);
+      if (lane == 0) { bbox[blk * 6 + d] = fkey_inv(mn); bbox[blk * 6 + 3 + d] = fkey_inv(mx); }
+    }
+  }
+  __syncthreads();
+
+  // ---- per-warp state: running minima of the owned blocks (registers), lane j < FG_SLOTS: box / maximum / key of block j
+  float md[FG_SLOTS][4];
+#pragma unroll
+  for (int j = 0; j < FG_SLOTS; ++j) {
+    const int i0 = (warp + FG_WARPS * j) * KG_BLK + lane * 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) md[j][i] = (warp + FG_WARPS * j < nblk && i0 + i < N) ? 1e10f : 0.f;
+  }
+  const int myblk = warp + FG_WARPS * lane;                  // the block lane `lane` speaks for (lanes < FG_SLOTS)
+  const bool owns = lane < FG_SLOTS && myblk < nblk;
+  float bb[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (owns) {
+#pragma unroll
+    for (int d = 0; d < 6; ++d) bb[d] = bbox[myblk * 6 + d];
+  }
+  unsigned bmax = owns ? __float_as_uint(1e10f) : 0u, blo = 0u;   // block maximum (bits) and its key (~original index | position)
+
+  int far = (int)start[c];
+  far = min(max(far, 0), N - 1);
+  float cx = p[(size_t)far * 3], cy = p[(size_t)far * 3 + 1], cz = p[(size_t)far * 3 + 2];
+  for (int s = 0; s < S; ++s) {
+    if (tid == 0) sel[s] = far;
+    if (s + 1 == S) break;
+    // which of my blocks can the new centroid change?  (the distance to the box never exceeds a point's distance)
+    bool need = false;
+    if (owns) {
+      const float qx = fminf(fmaxf(cx, bb[0]), bb[3]), qy = fminf(fmaxf(cy, bb[1]), bb[4]), qz = fminf(fmaxf(cz, bb[2]), bb[5]);
+      need = __float_as_uint(sqdist3(qx, qy, qz, cx, cy, cz)) < bmax;
+    }
+    const unsigned needmask = __ballot_sync(0xffffffffu, need);
+#pragma unroll
+    for (int j = 0; j < FG_SLOTS; ++j) {
+      if ((needmask >> j) & 1u) {                            // warp-uniform
+        const int i0 = (warp + FG_WARPS * j) * KG_BLK + lane * 4;
+        const float4 X = *reinterpret_cast<const float4*>(pts + i0);
+        const float4 Y = *reinterpret_cast<const float4*>(pts + pstride + i0);
+        const float4 Z = *reinterpret_cast<const float4*>(pts + 2 * pstride + i0);
+        const uint2 pm = *reinterpret_cast<const uint2*>(perm + i0);
+        md[j][0] = fminf(md[j][0], sqdist3(X.x, Y.x, Z.x, cx, cy, cz));
+        md[j][1] = fminf(md[j][1], sqdist3(X.y, Y.y, Z.y, cx, cy, cz));
+        md[j][2] = fminf(md[j][2], sqdist3(X.z, Y.z, Z.z, cx, cy, cz));
+        md[j][3] = fminf(md[j][3], sqdist3(X.w, Y.w, Z.w, cx, cy, cz));
+        // key = (running minimum bits, ~original index << 16 | sorted position): largest minimum, lowest original index
+        const unsigned l0 = ((0xffffu - (pm.x & 0xffffu)) << 16) | (unsigned)i0, l1 = ((0xffffu - (pm.x >> 16)) << 16) | (unsigned)(i0 + 1);
+        const unsigned l2 = ((0xffffu - (pm.y & 0xffffu)) << 16) | (unsigned)(i0 + 2), l3 = ((0xffffu - (pm.y >> 16)) << 16) | (unsigned)(i0 + 3);
+        unsigned hi = __float_as_uint(md[j][0]), lo2 = l0;
+        { const unsigned h = __float_as_uint(md[j][1]); const bool g = h > hi || (h == hi && l1 > lo2); hi = g ? h : hi; lo2 = g ? l1 : lo2; }
+        { const unsigned h = __float_as_uint(md[j][2]); const bool g = h > hi || (h == hi && l2 > lo2); hi = g ? h : hi; lo2 = g ? l2 : lo2; }
+        { const unsigned h = __float_as_uint(md[j][3]); const bool g = h > hi || (h == hi && l3 > lo2); hi = g ? h : hi; lo2 = g ? l3 : lo2; }
+        const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
+        const unsigned mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo2 : 0u);
+        if (lane == j) { bmax = mhi; blo = mlo; }
+      }
+    }
+    // the warp's best block, then the CTA's
+    const unsigned whi = __reduce_max_sync(0xffffffffu, owns ? bmax : 0u);
+    const unsigned wlo = __reduce_max_sync(0xffffffffu, (owns && bmax == whi) ? blo : 0u);
+    const int par = s & 1;
+    if (lane == 0) {
+      wkey[(par * FG_WARPS + warp) * 2] = whi;
+      wkey[(par * FG_WARPS + warp) * 2 + 1] = wlo;
+    }
+    __syncthreads();
+    const unsigned h2 = lane < FG_WARPS ? wkey[(par * FG_WARPS + lane) * 2] : 0u;
+    const unsigned l2k = lane < FG_WARPS ? wkey[(par * FG_WARPS + lane) * 2 + 1] : 0u;
+    const unsigned ghi = __reduce_max_sync(0xffffffffu, h2);
+    const unsigned glo = __reduce_max_sync(0xffffffffu, h2 == ghi ? l2k : 0u);
+    const int pos = (int)(glo & 0xffffu);
+    far = (int)(0xffffu - (glo >> 16));
+    cx = pts[pos]; cy = pts[pstride + pos]; cz = pts[2 * pstride + pos];
+  }
+  __syncthreads();
+  for (int s = tid; s < S; s += T) {
+    const int f = sel[s];
+    const size_t o = (size_t)c * S + s;
+    if (out64) out64[o] = f;
+    if (out_rows32) out_rows32[o] = c * N + f;
+    if (new_xyz) {
+      new_xyz[o * 3 + 0] = p[(size_t)f * 3];
+      new_xyz[o * 3 + 1] = p[(size_t)f * 3 + 1];
+      new_xyz[o * 3 + 2] = p[(size_t)f * 3 + 2];
+    }
+  }
+}
+
+static int fps_grid_launch(const float* xyz, int B, int N, const int64_t* start, int S, int64_t* out64, int* out_rows32,
+                           float* new_xyz, cudaStream_t st) {
+  const int nblk = (N + KG_BLK - 1) / KG_BLK, npad = nblk * KG_BLK;
+  PZ_REQUIRE(nblk <= FG_WARPS * FG_SLOTS, PZ_ERR_UNSUPPORTED, "pz_fps: N=%d exceeds the block-pruned kernel's %d points", N, FG_WARPS * FG_SLOTS * KG_BLK);
+  const size_t smem = (size_t)3 * (npad + 4) * sizeof(float) + (size_t)npad * sizeof(unsigned short) + (size_t)6 * nblk * sizeof(float) +
+                      KG_CELLS * sizeof(int) + FG_WARPS * 6 * sizeof(unsigned) + 2 * FG_WARPS * 2 * sizeof(unsigned) + (size_t)S * sizeof(int);
+  PZ_REQUIRE(smem <= 232448, PZ_ERR_UNSUPPORTED, "pz_fps: N=%d, S=%d need %zu B of shared memory", N, S, smem);
+  PZ_CUDA(cudaFuncSetAttribute(fps_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  fps_grid_kernel<<<B, FG_T, smem, st>>>(xyz, N, S, start, out64, out_rows32, new_xyz);
+  PZ_LAUNCH_CHECK();
+  return 0;
 }
 
 int launch_knn(const float* query, const float* xyz, int B, int S, int N, int K, int64_t* out64,

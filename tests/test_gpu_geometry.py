@@ -52,6 +52,24 @@ def test_fps_vs_oracle(pu, B, N, S):
     assert torch.equal(got.cpu(), ref)
 
 
+@pytest.mark.parametrize("B,N,S", [(3, 11000, 1024), (2, 4097, 200), (1, 14336, 512), (2, 8000, 2048)])
+def test_fps_large_cloud_block_pruning(pu, B, N, S):
+    """4096 < N <= 14336 takes fps_grid_kernel (Morton-binned cloud, blocks skipped when the centroid's distance to their
+    bounding box is >= their maximum running minimum): the sampled indices must stay identical to the oracle's, including
+    dense clusters, exact duplicates (arg-max ties -> lowest index) and a cloud whose points all coincide."""
+    g = torch.Generator().manual_seed(N * 3 + S)
+    xyz = torch.rand(B, N, 3, generator=g) - 0.5
+    xyz[0, : N // 3] = xyz[0, : N // 3] * 0.02 + 0.4              # a dense cluster
+    xyz[-1, 100:400] = xyz[-1, 7]                                 # 300 duplicates of one point
+    if B > 2:
+        xyz[1] = 0.25                                             # degenerate cloud
+    torch.manual_seed(N + 1)
+    ref = po.farthest_point_sample(xyz, S)
+    torch.manual_seed(N + 1)
+    got = pu.farthest_point_sample(xyz.to(DEV), S)
+    assert torch.equal(got.cpu(), ref)
+
+
 def test_fps_degenerate_cloud(pu):
     xyz = torch.zeros(2, 64, 3)                                  # all points identical: argmax of zeros -> 0
     torch.manual_seed(3)
