@@ -605,7 +605,11 @@ constexpr int KG_MAXN = 14336;              // 112 blocks: planes + permutation 
 constexpr int KG_WARPS = 16;                // warps per CTA (one CTA per SM: the cloud fills its shared memory)
 constexpr int KG_QPW = 8;                   // queries per warp (amortises binning the cloud)
 constexpr int KG_PB = 8;                    // points per thread and batch of the binning passes (loads issued together)
-constexpr int KG_CELLS = 512;
+#ifndef PZ_KG_BITS
+#define PZ_KG_BITS 3
+#endif
+constexpr int KG_BITS = PZ_KG_BITS;          // grid cells per axis = 2^KG_BITS
+constexpr int KG_CELLS = 1 << (3 * KG_BITS);
 __device__ __forceinline__ unsigned fkey(float x) {   // order-preserving image of a float (for redux min / max)
   const unsigned b = __float_as_uint(x);
   return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
@@ -614,13 +618,32 @@ __device__ __forceinline__ float fkey_inv(unsigned k) {
   return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 __device__ __forceinline__ int kg_cell(float x, float y, float z, const float (&lo)[3], const float (&inv)[3]) {
-  const int ix = min(7, max(0, (int)((x - lo[0]) * inv[0])));
-  const int iy = min(7, max(0, (int)((y - lo[1]) * inv[1])));
-  const int iz = min(7, max(0, (int)((z - lo[2]) * inv[2])));
+  constexpr int G = (1 << KG_BITS) - 1;
+  const int ix = min(G, max(0, (int)((x - lo[0]) * inv[0])));
+  const int iy = min(G, max(0, (int)((y - lo[1]) * inv[1])));
+  const int iz = min(G, max(0, (int)((z - lo[2]) * inv[2])));
   int c = 0;   // Morton order: bit 3 b + {0, 1, 2} = bit b of {x, y, z}
 #pragma unroll
-  for (int b = 0; b < 3; ++b) c |= (((ix >> b) & 1) << (3 * b)) | (((iy >> b) & 1) << (3 * b + 1)) | (((iz >> b) & 1) << (3 * b + 2));
+  for (int b = 0; b < KG_BITS; ++b) c |= (((ix >> b) & 1) << (3 * b)) | (((iy >> b) & 1) << (3 * b + 1)) | (((iz >> b) & 1) << (3 * b + 2));
   return c;
+}
+// exclusive scan of the KG_CELLS cell counts in place (one warp, KG_CELLS / 32 consecutive counts per lane)
+__device__ __forceinline__ void kg_scan(int* hist, int lane) {
+  constexpr int PER = KG_CELLS / 32;
+  int sum = 0;
+  for (int j = 0; j < PER; ++j) sum += hist[lane * PER + j];
+  int incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  int run = incl - sum;
+  for (int j = 0; j < PER; ++j) {
+    const int c = hist[lane * PER + j];
+    hist[lane * PER + j] = run;
+    run += c;
+  }
 }
 
 __global__ void __launch_bounds__(KG_WARPS * 32, 1) knn_grid_kernel(const float* __restrict__ query,
@@ -681,7 +704,7 @@ __global__ void __launch_bounds__(KG_WARPS * 32, 1) knn_grid_kernel(const float*
     for (int w = 0; w < KG_WARPS; ++w) { mn = min(mn, redk[w * 6 + d]); mx = max(mx, redk[w * 6 + 3 + d]); }
     lo[d] = fkey_inv(mn);
     const float ext = fkey_inv(mx) - lo[d];
-    inv[d] = ext > 0.f ? 8.0f / ext : 0.f;
+    inv[d] = ext > 0.f ? (float)(1 << KG_BITS) / ext : 0.f;
   }
   // ---- histogram of the cells, exclusive scan (cursor per cell), scatter in Morton order
   for (int base = tid; base < N; base += T * KG_PB) {
@@ -697,19 +720,8 @@ __global__ void __launch_bounds__(KG_WARPS * 32, 1) knn_grid_kernel(const float*
       if (base + u * T < N) atomicAdd(&hist[kg_cell(v[u][0], v[u][1], v[u][2], lo, inv)], 1);
   }
   __syncthreads();
-  if (warp == 0) {                      // 512 counts, 16 consecutive per lane
-    int loc[16], sum = 0;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) { loc[j] = hist[lane * 16 + j]; sum += loc[j]; }
-    int incl = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int v = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += v;
-    }
-    int run = incl - sum;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) { hist[lane * 16 + j] = run; run += loc[j]; }
+  if (warp == 0) {
+    kg_scan(hist, lane);
   }
   __syncthreads();
   for (int base = tid; base < N; base += T * KG_PB) {
@@ -971,7 +983,7 @@ __global__ void __launch_bounds__(FG_T, 1) fps_grid_kernel(const float* __restri
     for (int w = 0; w < FG_WARPS; ++w) { mn = min(mn, redk[w * 6 + d]); mx = max(mx, redk[w * 6 + 3 + d]); }
     lo[d] = fkey_inv(mn);
     const float ext = fkey_inv(mx) - lo[d];
-    inv[d] = ext > 0.f ? 8.0f / ext : 0.f;
+    inv[d] = ext > 0.f ? (float)(1 << KG_BITS) / ext : 0.f;
   }
   for (int base = tid; base < N; base += T * KG_PB) {
     float v[KG_PB][3];
@@ -987,18 +999,7 @@ __global__ void __launch_bounds__(FG_T, 1) fps_grid_kernel(const float* __restri
   }
   __syncthreads();
   if (warp == 0) {
-    int loc[16], sum = 0;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) { loc[j] = hist[lane * 16 + j]; sum += loc[j]; }
-    int incl = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int v = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += v;
-    }
-    int run = incl - sum;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) { hist[lane * 16 + j] = run; run += loc[j]; }
+    kg_scan(hist, lane);
   }
   __syncthreads();
   for (int base = tid; base < N; base += T * KG_PB) {
