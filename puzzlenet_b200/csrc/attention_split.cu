@@ -11,7 +11,12 @@
 // runs; O is produced as two 128-channel halves so the epilogue of the first overlaps the MMAs of the second.
 // Warps 0-3 softmax + epilogue, warp 4 the MMA-issuing thread, one thread of warp 5 issues every TMA load of v^T (q and k
 // arrive by TMA as well, issued by thread 0 before the CTA-wide barrier).
-// Shared memory: region A 128 KB (q, k planes -> P planes) + ring 64 KB + 16 KB staging tiles of the r epilogue.  TMEM: S [0,256), O halves [256,384), [384,512).
+// Shared memory: region A 128 KB (q, k planes -> P planes -> r planes) + ring 64 KB + 16 KB staging tiles of the epilogues.
+// FUSED OUT-PROJECTION (AttnSplit::wo_hi set; the split encoder's default): r is not written to HBM -- the epilogue writes
+// its hi / lo planes over P as the K-major A operand of  out = x + relu(Wo r + bo), Wo streams through the same ring (k-block
+// major, so the first two k-blocks run under the epilogue of r's second half), the accumulators land over S, and a second
+// epilogue adds bias / ReLU / residual and stores the layer's output planes (and fp32 rows): one launch and 67 MB of HBM
+// traffic per layer less than a separate out-projection GEMM.  TMEM: S [0,256), O halves [256,384), [384,512).
 #include <cuda.h>   // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint)
 #include <cuda_fp16.h>
 
@@ -68,6 +73,7 @@ __device__ __forceinline__ void as_stamp(long long* prof, int slot) {
 struct alignas(64) AsMaps {
   CUtensorMap qk[2];   // q|k hi / lo planes: [rows, 128]
   CUtensorMap vT[2];   // v^T hi / lo planes: [clouds * 256 channels, 256 keys]
+  CUtensorMap wo[2][2];   // fused out-projection: [weight set][hi / lo] Wo planes [256 out channels, 256 k]
 };
 }  // namespace
 
@@ -79,11 +85,15 @@ __global__ void __launch_bounds__(AS_THREADS, 1) attention_split_kernel(const At
   const uint32_t bars = ring + AS_NST * AS_STAGE;
   const uint32_t bar_s = bars, bar_p = bars + 8, bar_o = bars + 16 /* 2 */, full_bar = bars + 32, empty_bar = full_bar + 8 * AS_NST;
   const uint32_t bar_qk = empty_bar + 8 * AS_NST;
-  const uint32_t tmem_slot = bar_qk + 8;
-  const uint32_t stg_all = (tmem_slot + 16 + 127) & ~127u;   // 4 x 4 KB staging tiles of the r epilogue (reused by both halves)
+  const uint32_t bar_r = bar_qk + 8 /* 2 */, bar_y = bar_r + 16 /* 2 */;   // fused out-projection: r half h written / out half h accumulated
+  const uint32_t tmem_slot = bar_y + 16;
+  const uint32_t bo_s = (tmem_slot + 16 + 15) & ~15u;         // [256] out-projection bias of this CTA's weight set
+  const uint32_t stg_all = (bo_s + 1024 + 127) & ~127u;       // 4 x 4 KB staging tiles of the epilogues (reused by both halves)
+  const bool fuse = p.wo_hi[0] != nullptr;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cloud = blockIdx.x >> 1, qb = blockIdx.x & 1;
   const size_t row0 = (size_t)cloud * AS_L;
+  const int wset = (fuse && p.clouds_per_set > 0 && cloud >= p.clouds_per_set) ? 1 : 0;
 
   // ---- q (this block's 128 rows) and k (all 256 rows), both planes -> region A, by TMA (six 16 KB tiles on one mbarrier)
   const uint32_t q_hi_s = base, q_lo_s = base + T16, k_hi_s = base + 2 * T16, k_lo_s = base + 4 * T16;
@@ -94,6 +104,10 @@ __global__ void __launch_bounds__(AS_THREADS, 1) attention_split_kernel(const At
     mbar_init(bar_o, 1);
     mbar_init(bar_o + 8, 1);
     mbar_init(bar_qk, 1);
+    mbar_init(bar_r, 128);
+    mbar_init(bar_r + 8, 128);
+    mbar_init(bar_y, 1);
+    mbar_init(bar_y + 8, 1);
     for (int s = 0; s < AS_NST; ++s) {
       mbar_init(full_bar + 8 * s, 1);
       mbar_init(empty_bar + 8 * s, 1);
@@ -113,6 +127,7 @@ __global__ void __launch_bounds__(AS_THREADS, 1) attention_split_kernel(const At
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  if (fuse) reinterpret_cast<float*>(gen + (bo_s - base))[tid] = p.bo[wset][tid];   // AS_THREADS == 256 == channels
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -146,6 +161,7 @@ __global__ void __launch_bounds__(AS_THREADS, 1) attention_split_kernel(const At
     {
       const int h = eh;
       mbar_wait(bar_o + 8 * h, 0);
+      if (fuse) mbar_wait(bar_o + 8, 0);   // r goes over P in region A: every P v MMA must have completed
       tc_fence_after();
       if (lane == 0 && wq == 0) as_stamp(prof, 4 + 2 * h);
 #pragma unroll 1
@@ -181,6 +197,17 @@ __global__ void __launch_bounds__(AS_THREADS, 1) attention_split_kernel(const At
           }
         }
         __syncwarp();                 // every lane has read its x row: the tile takes the r block
+        if (fuse) {                   // r stays on chip: K-major A operand of the out-projection, k-block cb / 64 of region A
+          const uint32_t rk = base + (uint32_t)(cb >> 6) * T16;
+          const int prow_ = wq * 32 + lane;
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const uint32_t off = sw128(prow_, ((cb & 63) >> 3) + q4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rk + off), "r"(oh[q4].x), "r"(oh[q4].y), "r"(oh[q4].z), "r"(oh[q4].w) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rk + 4 * T16 + off), "r"(ol[q4].x), "r"(ol[q4].y), "r"(ol[q4].z), "r"(ol[q4].w) : "memory");
+          }
+          continue;
+        }
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) {
           const uint32_t a = own16 + (((uint32_t)q4 ^ sw_own) << 4);
@@ -204,6 +231,108 @@ __global__ void __launch_bounds__(AS_THREADS, 1) attention_split_kernel(const At
       if (lane == 0 && wq == 0) as_stamp(prof, 5 + 2 * h);
     }
   };
+  // fused out-projection epilogue: out = x + relu(acc + bo) for one 128-channel half of the block's rows -> y planes (+ fp32)
+  auto y_epilogue = [&](const int h, const int wq) {
+    const uint32_t tq_row = tmem + ((uint32_t)(wq * 32) << 16);
+    const uint32_t stg = stg_all + (uint32_t)wq * 4096;
+    const int cr = lane >> 2, cp = lane & 3, fr = lane >> 3, fp = lane & 7;
+    const uint32_t own16 = stg + (uint32_t)lane * 64, sw_own = (uint32_t)((lane >> 1) & 3);
+    const size_t rowbase = row0 + qb * 128 + wq * 32;
+    const __half* xhb = static_cast<const __half*>(p.x_hi);
+    const __half* xlb = static_cast<const __half*>(p.x_lo);
+    __half* yhb = static_cast<__half*>(p.y_hi);
+    __half* ylb = static_cast<__half*>(p.y_lo);
+    const float* bsm = reinterpret_cast<const float*>(gen + (bo_s - base));
+    uint4 pre[8];
+    auto x_fetch = [&](int cb) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const size_t off = (rowbase + 8 * j + cr) * p.ldx + cb + cp * 8;
+        pre[j] = *reinterpret_cast<const uint4*>(xhb + off);
+        pre[4 + j] = *reinterpret_cast<const uint4*>(xlb + off);
+      }
+    };
+    x_fetch(h * 128);
+    mbar_wait(bar_y + 8 * h, 0);
+    tc_fence_after();
+    if (lane == 0 && wq == 0) as_stamp(prof, 8 + 2 * h);
+#pragma unroll 1
+    for (int c32 = 0; c32 < 4; ++c32) {
+      const int cb = h * 128 + c32 * 32;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {   // the prefetched residual block -> staging
+        const int r = 8 * j + cr;
+        const uint32_t a = stg + (uint32_t)r * 64 + (uint32_t)((cp ^ ((r >> 1) & 3)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pre[j].x), "r"(pre[j].y), "r"(pre[j].z), "r"(pre[j].w) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a + 2048), "r"(pre[4 + j].x), "r"(pre[4 + j].y), "r"(pre[4 + j].z), "r"(pre[4 + j].w) : "memory");
+      }
+      __syncwarp();
+      if (c32 + 1 < 4) x_fetch(cb + 32);
+      float v[32];
+      tmem_ld32(tq_row + cb, v);        // the out-projection accumulators sit over S: columns [0, 256)
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + bsm[cb + i], 0.f);
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        uint4 xh4, xl4;
+        const uint32_t a = own16 + (((uint32_t)q4 ^ sw_own) << 4);
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(xh4.x), "=r"(xh4.y), "=r"(xh4.z), "=r"(xh4.w) : "r"(a));
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(xl4.x), "=r"(xl4.y), "=r"(xl4.z), "=r"(xl4.w) : "r"(a + 2048));
+        const uint32_t* hp = reinterpret_cast<const uint32_t*>(&xh4);
+        const uint32_t* lp = reinterpret_cast<const uint32_t*>(&xl4);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 a2 = __half22float2(*reinterpret_cast<const __half2*>(&hp[e]));
+          const float2 b2 = __half22float2(*reinterpret_cast<const __half2*>(&lp[e]));
+          v[q4 * 8 + 2 * e] += a2.x + b2.x;
+          v[q4 * 8 + 2 * e + 1] += a2.y + b2.y;
+        }
+      }
+      __syncwarp();                   // every lane has read its residual row: the tile takes the output block
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        uint4 oh, ol;
+        split2h(v[q4 * 8 + 0], v[q4 * 8 + 1], oh.x, ol.x);
+        split2h(v[q4 * 8 + 2], v[q4 * 8 + 3], oh.y, ol.y);
+        split2h(v[q4 * 8 + 4], v[q4 * 8 + 5], oh.z, ol.z);
+        split2h(v[q4 * 8 + 6], v[q4 * 8 + 7], oh.w, ol.w);
+        const uint32_t a = own16 + (((uint32_t)q4 ^ sw_own) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(oh.x), "r"(oh.y), "r"(oh.z), "r"(oh.w) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a + 2048), "r"(ol.x), "r"(ol.y), "r"(ol.z), "r"(ol.w) : "memory");
+      }
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int r = 8 * j + cr;
+        const uint32_t a = stg + (uint32_t)r * 64 + (uint32_t)((cp ^ ((r >> 1) & 3)) << 4);
+        uint4 hh, ll;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(hh.x), "=r"(hh.y), "=r"(hh.z), "=r"(hh.w) : "r"(a));
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(ll.x), "=r"(ll.y), "=r"(ll.z), "=r"(ll.w) : "r"(a + 2048));
+        const size_t off = (rowbase + r) * p.ldy + cb + cp * 8;
+        *reinterpret_cast<uint4*>(yhb + off) = hh;
+        *reinterpret_cast<uint4*>(ylb + off) = ll;
+      }
+      __syncwarp();
+      if (p.yf) {                     // fp32 rows (need=True): [32 rows][128 B] through the same tile
+#pragma unroll
+        for (int p8 = 0; p8 < 8; ++p8) {
+          const uint32_t a = stg + (uint32_t)lane * 128 + (uint32_t)((p8 ^ (lane & 7)) << 4);
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v[p8 * 4]), "f"(v[p8 * 4 + 1]), "f"(v[p8 * 4 + 2]), "f"(v[p8 * 4 + 3]) : "memory");
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int r = 4 * j + fr;
+          const uint32_t a = stg + (uint32_t)r * 128 + (uint32_t)((fp ^ (r & 7)) << 4);
+          float4 o4;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o4.x), "=f"(o4.y), "=f"(o4.z), "=f"(o4.w) : "r"(a));
+          *reinterpret_cast<float4*>(p.yf + (rowbase + r) * p.ldyf + cb + fp * 4) = o4;
+        }
+        __syncwarp();
+      }
+    }
+    if (lane == 0 && wq == 0) as_stamp(prof, 9 + 2 * h);
+  };
   if (warp >= 5) {
     // =========================================================== v^T producer: ONE thread, 8 stage loads (2 channel halves
     // x 4 key blocks), two TMA tiles (hi, lo) per stage
@@ -217,6 +346,17 @@ __global__ void __launch_bounds__(AS_THREADS, 1) attention_split_kernel(const At
         as_expect_tx(full_bar + 8 * s, AS_STAGE);
         as_tma_load(st, &maps.vT[0], kb * 64, vrow + h * 128, full_bar + 8 * s);
         as_tma_load(st + T16, &maps.vT[1], kb * 64, vrow + h * 128, full_bar + 8 * s);
+      }
+      if (fuse) {   // 8 more stage loads: Wo [128 out channels x 64 k] x 2 planes per (channel half, k-block)
+        for (uint32_t it = 8; it < 16; ++it) {
+          const uint32_t s = it % AS_NST, ph = (it / AS_NST) & 1;
+          const int kb = (it - 8) >> 1, h = (it - 8) & 1;   // k-block major: k-blocks 0, 1 only need r half 0
+          mbar_wait(empty_bar + 8 * s, ph ^ 1);
+          const uint32_t st = ring + s * AS_STAGE;
+          as_expect_tx(full_bar + 8 * s, AS_STAGE);
+          as_tma_load(st, &maps.wo[wset][0], kb * 64, h * 128, full_bar + 8 * s);
+          as_tma_load(st + T16, &maps.wo[wset][1], kb * 64, h * 128, full_bar + 8 * s);
+        }
       }
     }
   } else if (warp == 4) {
@@ -248,6 +388,24 @@ __global__ void __launch_bounds__(AS_THREADS, 1) attention_split_kernel(const At
           umma3(tmem + 256 + h * 128, a_hi + 2 * k4, a_lo + 2 * k4, b_hi + 2 * k4, b_lo + 2 * k4, idesc, (kb | k4) != 0);
         umma_commit(empty_bar + 8 * s);
         if (kb == 3) umma_commit(bar_o + 8 * h);
+      }
+      if (fuse) {   // out[i, c] = sum_k r[i, k] Wo[c, k]: r planes in region A (over P), accumulators over S
+        for (uint32_t it = 8; it < 16; ++it) {
+          const uint32_t s = it % AS_NST, ph = (it / AS_NST) & 1;
+          const int kb = (it - 8) >> 1, h = (it - 8) & 1;
+          if (it == 8) mbar_wait(bar_r, 0);        // r channels 0..127 = k-blocks 0, 1 (under the epilogue of r half 1)
+          if (it == 12) mbar_wait(bar_r + 8, 0);   // r channels 128..255 = k-blocks 2, 3
+          mbar_wait(full_bar + 8 * s, ph);
+          tc_fence_after();
+          const uint32_t st = ring + s * AS_STAGE;
+          const uint64_t a_hi = make_desc(base + kb * T16), a_lo = make_desc(base + 4 * T16 + kb * T16);
+          const uint64_t b_hi = make_desc(st), b_lo = make_desc(st + T16);
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4)
+            umma3(tmem + h * 128, a_hi + 2 * k4, a_lo + 2 * k4, b_hi + 2 * k4, b_lo + 2 * k4, idesc, (kb | k4) != 0);
+          umma_commit(empty_bar + 8 * s);
+          if (kb == 3) umma_commit(bar_y + 8 * h);
+        }
       }
     }
   } else {
@@ -324,7 +482,19 @@ __global__ void __launch_bounds__(AS_THREADS, 1) attention_split_kernel(const At
     // (a second group of four warps taking the other half was measured: both halves slow down to the same total -- the
     // phase moves 256 KB per CTA at ~5.4 TB/s over the chip, it is HBM-bound)
     r_epilogue(0, warp, inv);
+    if (fuse) {
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(bar_r);
+    }
     r_epilogue(1, warp, inv);
+    if (fuse) {
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(bar_r + 8);
+      y_epilogue(0, warp);
+      y_epilogue(1, warp);
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -358,13 +528,19 @@ static int as_make_map(const void* ptr, int ld, size_t rows, int cols, CUtensorM
 }
 
 int launch_attention_split(const AttnSplit& p, int clouds, cudaStream_t st) {
-  PZ_REQUIRE(p.qk_hi && p.qk_lo && p.vT_hi && p.vT_lo && p.x_hi && p.x_lo && p.r_hi && p.r_lo, PZ_ERR_ARG, "attention_split: null pointer");
+  const bool fuse = p.wo_hi[0] != nullptr;
+  PZ_REQUIRE(p.qk_hi && p.qk_lo && p.vT_hi && p.vT_lo && p.x_hi && p.x_lo && (fuse || (p.r_hi && p.r_lo)), PZ_ERR_ARG, "attention_split: null pointer");
+  if (fuse)
+    PZ_REQUIRE(p.wo_lo[0] && p.bo[0] && p.y_hi && p.y_lo && p.ldy % 8 == 0 && (((uintptr_t)p.y_hi | (uintptr_t)p.y_lo | (uintptr_t)p.wo_hi[0] | (uintptr_t)p.wo_lo[0]) & 15) == 0 &&
+                   (p.clouds_per_set <= 0 || p.clouds_per_set >= clouds || (p.wo_hi[1] && p.wo_lo[1] && p.bo[1])) &&
+                   (!p.yf || (p.ldyf % 4 == 0 && ((uintptr_t)p.yf & 15) == 0)),
+               PZ_ERR_ARG, "attention_split: fused out-projection needs Wo planes, bias and 16-byte aligned output planes");
   PZ_REQUIRE(p.ldx % 8 == 0 && (((uintptr_t)p.x_hi | (uintptr_t)p.x_lo | (uintptr_t)p.r_hi | (uintptr_t)p.r_lo | (uintptr_t)p.qk_hi |
                                  (uintptr_t)p.qk_lo | (uintptr_t)p.vT_hi | (uintptr_t)p.vT_lo) & 15) == 0,
              PZ_ERR_ARG, "attention_split: rows must be 16-byte aligned");
   PZ_REQUIRE(p.attn_mode == 0 || p.attn, PZ_ERR_ARG, "attention_split: attention map requested without a buffer");
-  const size_t smem = 1024 + REGA + AS_NST * AS_STAGE + 8 * (5 + 2 * AS_NST) + 32 + 128 + 4 * 4096;
-  static_assert(1024 + REGA + AS_NST * AS_STAGE + 8 * (5 + 2 * AS_NST) + 32 + 128 + 4 * 4096 <= 232448, "attention_split: shared memory budget");
+  const size_t smem = 1024 + REGA + AS_NST * AS_STAGE + 8 * (9 + 2 * AS_NST) + 32 + 16 + 1024 + 128 + 4 * 4096;
+  static_assert(1024 + REGA + AS_NST * AS_STAGE + 8 * (9 + 2 * AS_NST) + 32 + 16 + 1024 + 128 + 4 * 4096 <= 232448, "attention_split: shared memory budget");
   PZ_CUDA(cudaFuncSetAttribute(attention_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   AsMaps maps;
   const size_t rows = (size_t)clouds * AS_L;
@@ -372,6 +548,12 @@ int launch_attention_split(const AttnSplit& p, int clouds, cudaStream_t st) {
   PZ_TRY(as_make_map(p.qk_lo, 128, rows, 128, &maps.qk[1]));
   PZ_TRY(as_make_map(p.vT_hi, AS_L, (size_t)clouds * AS_C, AS_L, &maps.vT[0]));
   PZ_TRY(as_make_map(p.vT_lo, AS_L, (size_t)clouds * AS_C, AS_L, &maps.vT[1]));
+  for (int ws = 0; ws < 2; ++ws) {   // without fusion (or with one weight set) the maps repeat a valid tensor and are never used
+    const void* wh = fuse ? (p.wo_hi[ws] ? p.wo_hi[ws] : p.wo_hi[0]) : p.vT_hi;
+    const void* wl = fuse ? (p.wo_lo[ws] ? p.wo_lo[ws] : p.wo_lo[0]) : p.vT_lo;
+    PZ_TRY(as_make_map(wh, AS_C, AS_C, AS_C, &maps.wo[ws][0]));
+    PZ_TRY(as_make_map(wl, AS_C, AS_C, AS_C, &maps.wo[ws][1]));
+  }
   attention_split_kernel<<<2 * clouds, AS_THREADS, smem, st>>>(p, maps, kernel_timeline_buffer(3072 + 16));
   PZ_LAUNCH_CHECK();
   return 0;

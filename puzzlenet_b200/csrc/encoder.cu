@@ -1551,6 +1551,19 @@ static int encoder_forward_split(const PzEncoderWeights* w, int E, int B, const 
     ap.qk_hi = qk_h[0]; ap.qk_lo = qk_h[1]; ap.vT_hi = vT_h[0]; ap.vT_lo = vT_h[1];
     ap.x_hi = cat_h[0] + xoff; ap.x_lo = cat_h[1] + xoff; ap.ldx = 1280; ap.r_hi = r_h[0]; ap.r_lo = r_h[1];
     ap.attn = o.attention; ap.attn_mode = o.attention ? (l == 0 ? 1 : (l == 3 ? 3 : 2)) : 0;
+    // the out-projection  out = x + relu(Wo r + bo)  runs inside the attention kernel (r never leaves the SM: 67 MB of HBM
+    // traffic and one launch per layer less); PZ_ATTN_NO_FUSE keeps it a separate row GEMM (A/B hook)
+    static const bool attn_no_fuse = getenv("PZ_ATTN_NO_FUSE") != nullptr;
+    if (!attn_no_fuse) {
+      ap.wo_hi[0] = wp_[0][0] + wl + 384 * CATT; ap.wo_lo[0] = wp_[0][1] + wl + 384 * CATT;
+      ap.wo_hi[1] = wp_[1][0] + wl + 384 * CATT; ap.wo_lo[1] = wp_[1][1] + wl + 384 * CATT;
+      ap.bo[0] = wa.o_b[l]; ap.bo[1] = wb.o_b[l]; ap.clouds_per_set = B;
+      ap.y_hi = cat_h[0] + (size_t)l * CATT; ap.y_lo = cat_h[1] + (size_t)l * CATT; ap.ldy = 1280;
+      if (cat_f) { ap.yf = cat_f + (size_t)l * CATT; ap.ldyf = 1280; }
+      PZ_TRY(launch_attention_split(ap, C, st));
+      prof_mark("attn_softmax_av", st);
+      continue;
+    }
     PZ_TRY(launch_attention_split(ap, C, st));
     prof_mark("attn_softmax_av", st);
     TcGemm g;  // out = x + relu(Wo r + bo)

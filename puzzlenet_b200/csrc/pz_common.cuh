@@ -175,6 +175,15 @@ struct AttnSplit {
   void *r_hi = nullptr, *r_lo = nullptr;
   float* attn = nullptr;
   int attn_mode = 0;
+  // fused out-projection (wo_hi[0] != null): instead of r the kernel writes  out = x + relu(Wo r + bo)  as planes y (and as
+  // fp32 rows yf when given); Wo planes [256, 256] fp16 K-major and bo [256] per weight set, cloud / clouds_per_set = set
+  const void *wo_hi[2] = {nullptr, nullptr}, *wo_lo[2] = {nullptr, nullptr};
+  const float* bo[2] = {nullptr, nullptr};
+  int clouds_per_set = 0;
+  void *y_hi = nullptr, *y_lo = nullptr;
+  int ldy = 0;
+  float* yf = nullptr;
+  int ldyf = 0;
 };
 int launch_attention_split(const AttnSplit& p, int clouds, cudaStream_t st);
 // heads_split.cu: the boundary heads of predict5 as split-fp16 chained-MMA kernels (used by the split and bf16 paths)
