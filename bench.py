@@ -748,7 +748,9 @@ def run_gpu_arm(args):
         "attn_layer_fused": (4 * 2.0 * clouds * 256 * 256 * (384 + 64 + 256 + 256), "tensor", 1),
         "attn_qkv_proj": (4 * 2.0 * clouds * 256 * 256 * 384, "tensor", 8 if not fused and args.precision != "fp32" else 12),
         "attn_out_proj": (4 * 2.0 * clouds * 256 * 256 * 256, "tensor", 4),
-        "attn_softmax_av": (4 * 2.0 * clouds * 256 * 256 * (64 + 256), "tensor", 4),
+        # split path: the out-projection runs inside the attention kernel (no attn_out_proj stage): its FLOPs count here
+        "attn_softmax_av": (4 * 2.0 * clouds * 256 * 256 * (64 + 256 + (256 if (args.precision == "split" and per_step.get("attn_out_proj", 0) == 0) else 0)),
+                            "tensor", 4),
         "fps1": (clouds * (12 * 1024 + 8 * 512), "hbm", 1),
         "fps2": (clouds * (12 * 512 + 8 * 256), "hbm", 1),
         "knn1": (clouds * (12 * 1024 + 12 * 512 + 8 * 512 * 32), "hbm", 1),
