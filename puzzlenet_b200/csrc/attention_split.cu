@@ -86,7 +86,8 @@ __global__ void __launch_bounds__(AS_THREADS, 1) attention_split_kernel(const At
   const uint32_t bar_s = bars, bar_p = bars + 8, bar_o = bars + 16 /* 2 */, full_bar = bars + 32, empty_bar = full_bar + 8 * AS_NST;
   const uint32_t bar_qk = empty_bar + 8 * AS_NST;
   const uint32_t bar_r = bar_qk + 8 /* 2 */, bar_y = bar_r + 16 /* 2 */;   // fused out-projection: r half h written / out half h accumulated
-  const uint32_t tmem_slot = bar_y + 16;
+  const uint32_t bar_pk = bar_y + 16 /* 4 */;                  // P key block kb (64 keys, both planes) written
+  const uint32_t tmem_slot = bar_pk + 32;
   const uint32_t bo_s = (tmem_slot + 16 + 15) & ~15u;         // [256] out-projection bias of this CTA's weight set
   const uint32_t stg_all = (bo_s + 1024 + 127) & ~127u;       // 4 x 4 KB staging tiles of the epilogues (reused by both halves)
   const bool fuse = p.wo_hi[0] != nullptr;
@@ -106,6 +107,7 @@ __global__ void __launch_bounds__(AS_THREADS, 1) attention_split_kernel(const At
     mbar_init(bar_qk, 1);
     mbar_init(bar_r, 128);
     mbar_init(bar_r + 8, 128);
+    for (int kb = 0; kb < 4; ++kb) mbar_init(bar_pk + 8 * kb, 128);
     mbar_init(bar_y, 1);
     mbar_init(bar_y + 8, 1);
     for (int s = 0; s < AS_NST; ++s) {
@@ -372,12 +374,11 @@ __global__ void __launch_bounds__(AS_THREADS, 1) attention_split_kernel(const At
         for (int k4 = 0; k4 < 4; ++k4) umma3(tmem, a_hi + 2 * k4, a_lo + 2 * k4, b_hi + 2 * k4, b_lo + 2 * k4, idesc, k4 != 0);
         umma_commit(bar_s);
       }
-      mbar_wait(bar_p, 0);          // both planes of P are in region A
-      tc_fence_after();
       const uint32_t idesc = idesc_f16(128);
       for (uint32_t it = 0; it < 8; ++it) {
         const uint32_t s = it % AS_NST, ph = (it / AS_NST) & 1;
         const int h = it >> 2, kb = it & 3;
+        if (h == 0) mbar_wait(bar_pk + 8 * kb, 0);   // P's key block kb is in region A (the softmax is still writing later ones)
         mbar_wait(full_bar + 8 * s, ph);
         tc_fence_after();
         const uint32_t st = ring + s * AS_STAGE;
@@ -449,10 +450,12 @@ __global__ void __launch_bounds__(AS_THREADS, 1) attention_split_kernel(const At
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(pk + off), "r"(oh.x), "r"(oh.y), "r"(oh.z), "r"(oh.w) : "memory");
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(pk + 4 * T16 + off), "r"(ol.x), "r"(ol.y), "r"(ol.z), "r"(ol.w) : "memory");
       }
+      if (c32 & 1) {   // key block c32 / 2 complete: the P v MMAs over it may start under the rest of the pass
+        fence_proxy_async();
+        tc_fence_before();
+        mbar_arrive(bar_pk + 8 * (c32 >> 1));
+      }
     }
-    fence_proxy_async();
-    tc_fence_before();
-    mbar_arrive(bar_p);
     if (tid == 0) as_stamp(prof, 3);
     const float inv = 1.0f / sum;
     if (p.attn_mode != 0) {  // attention map (need=True): mean of the four layers' maps, model5_b.py:468-469
@@ -539,8 +542,8 @@ int launch_attention_split(const AttnSplit& p, int clouds, cudaStream_t st) {
                                  (uintptr_t)p.qk_lo | (uintptr_t)p.vT_hi | (uintptr_t)p.vT_lo) & 15) == 0,
              PZ_ERR_ARG, "attention_split: rows must be 16-byte aligned");
   PZ_REQUIRE(p.attn_mode == 0 || p.attn, PZ_ERR_ARG, "attention_split: attention map requested without a buffer");
-  const size_t smem = 1024 + REGA + AS_NST * AS_STAGE + 8 * (9 + 2 * AS_NST) + 32 + 16 + 1024 + 128 + 4 * 4096;
-  static_assert(1024 + REGA + AS_NST * AS_STAGE + 8 * (9 + 2 * AS_NST) + 32 + 16 + 1024 + 128 + 4 * 4096 <= 232448, "attention_split: shared memory budget");
+  const size_t smem = 1024 + REGA + AS_NST * AS_STAGE + 8 * (13 + 2 * AS_NST) + 32 + 16 + 1024 + 128 + 4 * 4096;
+  static_assert(1024 + REGA + AS_NST * AS_STAGE + 8 * (13 + 2 * AS_NST) + 32 + 16 + 1024 + 128 + 4 * 4096 <= 232448, "attention_split: shared memory budget");
   PZ_CUDA(cudaFuncSetAttribute(attention_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   AsMaps maps;
   const size_t rows = (size_t)clouds * AS_L;
