@@ -69,7 +69,10 @@ int pz_profile_collect(double* ms_host, const char** names_host, int* calls_host
  * launch (attention_layer_tc.cu) stores SM clock stamps of its phase boundaries there (slots 0-17: epilogue thread 0,
  * 32-41: the MMA-issuing thread) and every CTA c its %globaltimer at entry / exit (64 + 2c, 65 + 2c) -- only when
  * n_slots >= 64 + 2 * clouds; CTA 0 of the stage-1 gather GEMM (gemm_tc.cu) stamps slots 1024..1455 -- only when
- * n_slots >= 1456.  A buffer too short for a stamp set switches that set off; n_slots < 64 is an argument error.
+ * n_slots >= 1456.  Split path (%globaltimer, ns): the first CTA pair of the row GEMM launch selected by the environment
+ * variable PZ_RG_TIMELINE (p1 | qk | vt | outproj | tail) stamps slots 2048..3071 (n_slots >= 3072), CTA 0 of every
+ * attention_split_kernel launch slots 3072..3087 (n_slots >= 3088); scripts/rowgemm_timeline.py prints both.
+ * A buffer too short for a stamp set switches that set off; n_slots < 64 is an argument error.
  * NULL switches everything off (the default). */
 int pz_profile_attention_timeline(long long* device_buf_or_null, long long n_slots);
 
