@@ -16,7 +16,13 @@
 // its hi / lo planes over P as the K-major A operand of  out = x + relu(Wo r + bo), Wo streams through the same ring (k-block
 // major, so the first two k-blocks run under the epilogue of r's second half), the accumulators land over S, and a second
 // epilogue adds bias / ReLU / residual and stores the layer's output planes (and fp32 rows): one launch and 67 MB of HBM
-// traffic per layer less than a separate out-projection GEMM.  TMEM: S [0,256), O halves [256,384), [384,512).
+// traffic per layer less than a separate out-projection GEMM.
+// CHAINED PROJECTIONS (AttnSplit::wqkv_hi set; layers 0-2 of the split encoder): the second epilogue also writes the output
+// planes over r as the A operand of the NEXT layer's [q | k | v] = out Wqkv^T + b, Wqkv streams through the ring (12 more
+// stages; the first six under the epilogue of the output's second half, the rest block-major so that every block's epilogue
+// overlaps the remaining MMAs), q|k accumulates over the drained output half, v over the O halves, and a third epilogue
+// stores the next layer's q|k planes and v^T planes into the OTHER buffer set (the CTAs of this launch still read the
+// current one): two more launches and one more read of the layer's output per layer less.  TMEM: S [0,256), O halves [256,384), [384,512).
 #include <cuda.h>   // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint)
 #include <cuda_fp16.h>
 
@@ -74,6 +80,7 @@ struct alignas(64) AsMaps {
   CUtensorMap qk[2];   // q|k hi / lo planes: [rows, 128]
   CUtensorMap vT[2];   // v^T hi / lo planes: [clouds * 256 channels, 256 keys]
   CUtensorMap wo[2][2];   // fused out-projection: [weight set][hi / lo] Wo planes [256 out channels, 256 k]
+  CUtensorMap wn[2][2];   // chained projections: [weight set][hi / lo] next layer's Wqkv planes [384, 256]
 };
 }  // namespace
 
@@ -87,10 +94,12 @@ __global__ void __launch_bounds__(AS_THREADS, 1) attention_split_kernel(const At
   const uint32_t bar_qk = empty_bar + 8 * AS_NST;
   const uint32_t bar_r = bar_qk + 8 /* 2 */, bar_y = bar_r + 16 /* 2 */;   // fused out-projection: r half h written / out half h accumulated
   const uint32_t bar_pk = bar_y + 16 /* 4 */;                  // P key block kb (64 keys, both planes) written
-  const uint32_t tmem_slot = bar_pk + 32;
-  const uint32_t bo_s = (tmem_slot + 16 + 15) & ~15u;         // [256] out-projection bias of this CTA's weight set
-  const uint32_t stg_all = (bo_s + 1024 + 127) & ~127u;       // 4 x 4 KB staging tiles of the epilogues (reused by both halves)
+  const uint32_t bar_x2 = bar_pk + 32 /* 2 */, bar_z = bar_x2 + 16 /* 3 */;   // chained projections: out half h in region A / block accumulated
+  const uint32_t tmem_slot = bar_z + 24;
+  const uint32_t bo_s = (tmem_slot + 16 + 15) & ~15u;         // [256] out-projection bias of this CTA's weight set, then [384] next q|k|v bias
+  const uint32_t stg_all = (bo_s + 1024 + 1536 + 127) & ~127u;   // 4 x 4 KB staging tiles of the epilogues (reused by all phases)
   const bool fuse = p.wo_hi[0] != nullptr;
+  const bool chain = fuse && p.wqkv_hi[0] != nullptr;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cloud = blockIdx.x >> 1, qb = blockIdx.x & 1;
   const size_t row0 = (size_t)cloud * AS_L;
@@ -108,6 +117,9 @@ __global__ void __launch_bounds__(AS_THREADS, 1) attention_split_kernel(const At
     mbar_init(bar_r, 128);
     mbar_init(bar_r + 8, 128);
     for (int kb = 0; kb < 4; ++kb) mbar_init(bar_pk + 8 * kb, 128);
+    mbar_init(bar_x2, 128);
+    mbar_init(bar_x2 + 8, 128);
+    for (int b3 = 0; b3 < 3; ++b3) mbar_init(bar_z + 8 * b3, 1);
     mbar_init(bar_y, 1);
     mbar_init(bar_y + 8, 1);
     for (int s = 0; s < AS_NST; ++s) {
@@ -130,6 +142,8 @@ __global__ void __launch_bounds__(AS_THREADS, 1) attention_split_kernel(const At
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (fuse) reinterpret_cast<float*>(gen + (bo_s - base))[tid] = p.bo[wset][tid];   // AS_THREADS == 256 == channels
+  if (chain)
+    for (int i = tid; i < 384; i += AS_THREADS) reinterpret_cast<float*>(gen + (bo_s - base))[256 + i] = p.bqkv[wset][i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -256,6 +270,7 @@ __global__ void __launch_bounds__(AS_THREADS, 1) attention_split_kernel(const At
     };
     x_fetch(h * 128);
     mbar_wait(bar_y + 8 * h, 0);
+    if (chain) mbar_wait(bar_y + 8, 0);   // the output goes over r in region A: every out-projection MMA must have completed
     tc_fence_after();
     if (lane == 0 && wq == 0) as_stamp(prof, 8 + 2 * h);
 #pragma unroll 1
@@ -301,6 +316,11 @@ __global__ void __launch_bounds__(AS_THREADS, 1) attention_split_kernel(const At
         const uint32_t a = own16 + (((uint32_t)q4 ^ sw_own) << 4);
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(oh.x), "r"(oh.y), "r"(oh.z), "r"(oh.w) : "memory");
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a + 2048), "r"(ol.x), "r"(ol.y), "r"(ol.z), "r"(ol.w) : "memory");
+        if (chain) {   // ... and the same planes as the K-major A operand of the next layer's projections (region A, over r)
+          const uint32_t xk = base + (uint32_t)(cb >> 6) * T16 + sw128(wq * 32 + lane, ((cb & 63) >> 3) + q4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(xk), "r"(oh.x), "r"(oh.y), "r"(oh.z), "r"(oh.w) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(xk + 4 * T16), "r"(ol.x), "r"(ol.y), "r"(ol.z), "r"(ol.w) : "memory");
+        }
       }
       __syncwarp();
 #pragma unroll
@@ -335,6 +355,69 @@ __global__ void __launch_bounds__(AS_THREADS, 1) attention_split_kernel(const At
     }
     if (lane == 0 && wq == 0) as_stamp(prof, 9 + 2 * h);
   };
+  // chained projections epilogue, block b3 = 0: next q|k planes [rows, 128]; b3 = 1, 2: next v^T planes (channels
+  // (b3 - 1) * 128 ..), transposed: the 32 lanes of a warp are 32 consecutive tokens = 64 contiguous bytes per channel
+  auto z_epilogue = [&](const int b3, const int wq) {
+    const uint32_t tcol = b3 == 0 ? 0u : 128u + 128u * (uint32_t)b3;   // accumulator columns: [0,128), [256,384), [384,512)
+    const uint32_t tq_row = tmem + ((uint32_t)(wq * 32) << 16) + tcol;
+    const uint32_t stg = stg_all + (uint32_t)wq * 4096;
+    const int cr = lane >> 2, cp = lane & 3;
+    const uint32_t own16 = stg + (uint32_t)lane * 64, sw_own = (uint32_t)((lane >> 1) & 3);
+    const size_t rowbase = row0 + qb * 128 + wq * 32;
+    const float* bsm = reinterpret_cast<const float*>(gen + (bo_s - base)) + 256 + b3 * 128;
+    mbar_wait(bar_z + 8 * b3, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c32 = 0; c32 < 4; ++c32) {
+      float v[32];
+      tmem_ld32(tq_row + c32 * 32, v);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] += bsm[c32 * 32 + i];
+      if (b3 == 0) {
+        __half* qh = static_cast<__half*>(p.qk2_hi);
+        __half* ql = static_cast<__half*>(p.qk2_lo);
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          uint4 oh, ol;
+          split2h(v[q4 * 8 + 0], v[q4 * 8 + 1], oh.x, ol.x);
+          split2h(v[q4 * 8 + 2], v[q4 * 8 + 3], oh.y, ol.y);
+          split2h(v[q4 * 8 + 4], v[q4 * 8 + 5], oh.z, ol.z);
+          split2h(v[q4 * 8 + 6], v[q4 * 8 + 7], oh.w, ol.w);
+          const uint32_t a = own16 + (((uint32_t)q4 ^ sw_own) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(oh.x), "r"(oh.y), "r"(oh.z), "r"(oh.w) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a + 2048), "r"(ol.x), "r"(ol.y), "r"(ol.z), "r"(ol.w) : "memory");
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int r = 8 * j + cr;
+          const uint32_t a = stg + (uint32_t)r * 64 + (uint32_t)((cp ^ ((r >> 1) & 3)) << 4);
+          uint4 hh, ll;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(hh.x), "=r"(hh.y), "=r"(hh.z), "=r"(hh.w) : "r"(a));
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(ll.x), "=r"(ll.y), "=r"(ll.z), "=r"(ll.w) : "r"(a + 2048));
+          const size_t off = (rowbase + r) * 128 + c32 * 32 + cp * 8;
+          *reinterpret_cast<uint4*>(qh + off) = hh;
+          *reinterpret_cast<uint4*>(ql + off) = ll;
+        }
+        __syncwarp();
+      } else {
+        const int ch0 = (b3 - 1) * 128 + c32 * 32;
+        const size_t tok = (size_t)qb * 128 + wq * 32 + lane;
+        __half* dh = static_cast<__half*>(p.vT2_hi) + ((size_t)cloud * AS_C + ch0) * AS_L + tok;
+        __half* dl = static_cast<__half*>(p.vT2_lo) + ((size_t)cloud * AS_C + ch0) * AS_L + tok;
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          uint32_t hi, lo;
+          split2h(v[i], v[i + 1], hi, lo);
+          const __half2 h2 = *reinterpret_cast<const __half2*>(&hi), l2 = *reinterpret_cast<const __half2*>(&lo);
+          dh[(size_t)i * AS_L] = __low2half(h2);
+          dh[(size_t)(i + 1) * AS_L] = __high2half(h2);
+          dl[(size_t)i * AS_L] = __low2half(l2);
+          dl[(size_t)(i + 1) * AS_L] = __high2half(l2);
+        }
+      }
+    }
+  };
   if (warp >= 5) {
     // =========================================================== v^T producer: ONE thread, 8 stage loads (2 channel halves
     // x 4 key blocks), two TMA tiles (hi, lo) per stage
@@ -358,6 +441,19 @@ __global__ void __launch_bounds__(AS_THREADS, 1) attention_split_kernel(const At
           as_expect_tx(full_bar + 8 * s, AS_STAGE);
           as_tma_load(st, &maps.wo[wset][0], kb * 64, h * 128, full_bar + 8 * s);
           as_tma_load(st + T16, &maps.wo[wset][1], kb * 64, h * 128, full_bar + 8 * s);
+        }
+      }
+      if (chain) {   // 12 more: the next layer's Wqkv [128 rows x 64 k] x 2 planes per (k-block, block of 128 output rows)
+        for (uint32_t it = 16; it < 28; ++it) {
+          const uint32_t s = it % AS_NST, ph = (it / AS_NST) & 1;
+          // k-blocks 0, 1 block-interleaved (they run under the second out epilogue); k-blocks 2, 3 block-major, so that a
+          // block completes every two stages and its epilogue overlaps the remaining MMAs
+          const int j = (int)it - 16, kb = j < 6 ? j / 3 : 2 + ((j - 6) & 1), b3 = j < 6 ? j % 3 : (j - 6) >> 1;
+          mbar_wait(empty_bar + 8 * s, ph ^ 1);
+          const uint32_t st = ring + s * AS_STAGE;
+          as_expect_tx(full_bar + 8 * s, AS_STAGE);
+          as_tma_load(st, &maps.wn[wset][0], kb * 64, b3 * 128, full_bar + 8 * s);
+          as_tma_load(st + T16, &maps.wn[wset][1], kb * 64, b3 * 128, full_bar + 8 * s);
         }
       }
     }
@@ -406,6 +502,26 @@ __global__ void __launch_bounds__(AS_THREADS, 1) attention_split_kernel(const At
             umma3(tmem + h * 128, a_hi + 2 * k4, a_lo + 2 * k4, b_hi + 2 * k4, b_lo + 2 * k4, idesc, (kb | k4) != 0);
           umma_commit(empty_bar + 8 * s);
           if (kb == 3) umma_commit(bar_y + 8 * h);
+        }
+      }
+      if (chain) {   // [q | k | v][i, c] = sum_k out[i, k] Wqkv[c, k]: out planes in region A (over r); accumulators: q|k over
+                     // columns [0, 128) (the out half the second epilogue has drained), v over the O halves [256, 512)
+        for (uint32_t it = 16; it < 28; ++it) {
+          const uint32_t s = it % AS_NST, ph = (it / AS_NST) & 1;
+          const int j = (int)it - 16, kb = j < 6 ? j / 3 : 2 + ((j - 6) & 1), b3 = j < 6 ? j % 3 : (j - 6) >> 1;
+          if (it == 16) mbar_wait(bar_x2, 0);        // out channels 0..127 = k-blocks 0, 1
+          if (it == 22) mbar_wait(bar_x2 + 8, 0);    // out channels 128..255 = k-blocks 2, 3
+          mbar_wait(full_bar + 8 * s, ph);
+          tc_fence_after();
+          const uint32_t st = ring + s * AS_STAGE;
+          const uint64_t a_hi = make_desc(base + kb * T16), a_lo = make_desc(base + 4 * T16 + kb * T16);
+          const uint64_t b_hi = make_desc(st), b_lo = make_desc(st + T16);
+          const uint32_t dcol = b3 == 0 ? 0u : 128u + 128u * (uint32_t)b3;
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4)
+            umma3(tmem + dcol, a_hi + 2 * k4, a_lo + 2 * k4, b_hi + 2 * k4, b_lo + 2 * k4, idesc, (kb | k4) != 0);
+          umma_commit(empty_bar + 8 * s);
+          if (kb == 3) umma_commit(bar_z + 8 * b3);
         }
       }
     }
@@ -496,7 +612,20 @@ __global__ void __launch_bounds__(AS_THREADS, 1) attention_split_kernel(const At
       tc_fence_before();
       mbar_arrive(bar_r + 8);
       y_epilogue(0, warp);
+      if (chain) {
+        fence_proxy_async();
+        tc_fence_before();
+        mbar_arrive(bar_x2);
+      }
       y_epilogue(1, warp);
+      if (chain) {
+        fence_proxy_async();
+        tc_fence_before();
+        mbar_arrive(bar_x2 + 8);
+        z_epilogue(0, warp);
+        z_epilogue(1, warp);
+        z_epilogue(2, warp);
+      }
     }
   }
   tc_fence_before();
@@ -542,8 +671,15 @@ int launch_attention_split(const AttnSplit& p, int clouds, cudaStream_t st) {
                                  (uintptr_t)p.qk_lo | (uintptr_t)p.vT_hi | (uintptr_t)p.vT_lo) & 15) == 0,
              PZ_ERR_ARG, "attention_split: rows must be 16-byte aligned");
   PZ_REQUIRE(p.attn_mode == 0 || p.attn, PZ_ERR_ARG, "attention_split: attention map requested without a buffer");
-  const size_t smem = 1024 + REGA + AS_NST * AS_STAGE + 8 * (13 + 2 * AS_NST) + 32 + 16 + 1024 + 128 + 4 * 4096;
-  static_assert(1024 + REGA + AS_NST * AS_STAGE + 8 * (13 + 2 * AS_NST) + 32 + 16 + 1024 + 128 + 4 * 4096 <= 232448, "attention_split: shared memory budget");
+  const bool chain = fuse && p.wqkv_hi[0] != nullptr;
+  if (chain)
+    PZ_REQUIRE(p.wqkv_lo[0] && p.bqkv[0] && p.qk2_hi && p.qk2_lo && p.vT2_hi && p.vT2_lo &&
+                   (((uintptr_t)p.wqkv_hi[0] | (uintptr_t)p.wqkv_lo[0] | (uintptr_t)p.qk2_hi | (uintptr_t)p.qk2_lo | (uintptr_t)p.vT2_hi | (uintptr_t)p.vT2_lo) & 15) == 0 &&
+                   (p.clouds_per_set <= 0 || p.clouds_per_set >= clouds || (p.wqkv_hi[1] && p.wqkv_lo[1] && p.bqkv[1])) &&
+                   p.qk2_hi != p.qk_hi && p.vT2_hi != p.vT_hi,
+               PZ_ERR_ARG, "attention_split: chained projections need next-layer weights, bias and separate output planes");
+  const size_t smem = 1024 + REGA + AS_NST * AS_STAGE + 8 * (18 + 2 * AS_NST) + 32 + 16 + 1024 + 1536 + 128 + 4 * 4096;
+  static_assert(1024 + REGA + AS_NST * AS_STAGE + 8 * (18 + 2 * AS_NST) + 32 + 16 + 1024 + 1536 + 128 + 4 * 4096 <= 232448, "attention_split: shared memory budget");
   PZ_CUDA(cudaFuncSetAttribute(attention_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   AsMaps maps;
   const size_t rows = (size_t)clouds * AS_L;
@@ -556,6 +692,10 @@ int launch_attention_split(const AttnSplit& p, int clouds, cudaStream_t st) {
     const void* wl = fuse ? (p.wo_lo[ws] ? p.wo_lo[ws] : p.wo_lo[0]) : p.vT_lo;
     PZ_TRY(as_make_map(wh, AS_C, AS_C, AS_C, &maps.wo[ws][0]));
     PZ_TRY(as_make_map(wl, AS_C, AS_C, AS_C, &maps.wo[ws][1]));
+    const void* nh = chain ? (p.wqkv_hi[ws] ? p.wqkv_hi[ws] : p.wqkv_hi[0]) : wh;
+    const void* nl = chain ? (p.wqkv_lo[ws] ? p.wqkv_lo[ws] : p.wqkv_lo[0]) : wl;
+    PZ_TRY(as_make_map(nh, AS_C, chain ? 384 : AS_C, AS_C, &maps.wn[ws][0]));
+    PZ_TRY(as_make_map(nl, AS_C, chain ? 384 : AS_C, AS_C, &maps.wn[ws][1]));
   }
   attention_split_kernel<<<2 * clouds, AS_THREADS, smem, st>>>(p, maps, kernel_timeline_buffer(3072 + 16));
   PZ_LAUNCH_CHECK();

@@ -1534,32 +1534,46 @@ static int encoder_forward_split(const PzEncoderWeights* w, int E, int B, const 
 
   // ---- 4 x offset attention
   const int rows = C * LATT;
+  // the out-projection  out = x + relu(Wo r + bo)  runs inside the attention kernel (r never leaves the SM: 67 MB of HBM
+  // traffic and one launch per layer less), and so do the NEXT layer's q|k|v projections of the same rows (chained: two
+  // more launches per layer less); q|k and v^T planes then alternate between two buffer sets, because the CTAs of a launch
+  // still read the current ones.  PZ_ATTN_NO_FUSE / PZ_ATTN_NO_CHAIN keep them separate row GEMMs (A/B hooks).
+  static const bool attn_no_fuse = getenv("PZ_ATTN_NO_FUSE") != nullptr;
+  static const bool attn_no_chain = attn_no_fuse || getenv("PZ_ATTN_NO_CHAIN") != nullptr;
+  h16* qk_set[2][2] = {{qk_h[0], qk_h[1]}, {s.xfeat_b, reinterpret_cast<h16*>(s.k)}};   // second set: idle buffers of equal size
+  h16* vT_set[2][2] = {{vT_h[0], vT_h[1]}, {r_h[0], r_h[1]}};                           // (r is not materialised when fused)
   for (int l = 0; l < 4; ++l) {
     const size_t xoff = l == 0 ? 4 * CATT : (size_t)(l - 1) * CATT;
     const size_t wl = WS_ATT + (size_t)l * WS_ATT_STRIDE;
-    TcGemm gq;  // [q | k] = x Wqk^T + b
-    gq.X = cat_h[0] + xoff; gq.Xlo = cat_h[1] + xoff; gq.ldx = 1280; set_w(gq, wl); gq.ldw = CATT;
-    gq.bias[0] = s.bqkv + (size_t)l * 384; gq.bias[1] = s.bqkv + ((size_t)(E - 1) * 4 + l) * 384;
-    gq.rows_per_wset = B * LATT; gq.M = rows; gq.Nout = 128; gq.K = CATT; gq.Yb = qk_h[0]; gq.Yblo = qk_h[1]; gq.ldyb = 128;
-    PZ_TRY(launch_split_rowgemm(gq, st));
-    TcGemm gv = gq;  // v^T per cloud (K-major operand of P v)
-    set_w(gv, wl + 128 * CATT); gv.bias[0] = gq.bias[0] + 128; gv.bias[1] = gq.bias[1] + 128;
-    gv.Nout = CATT; gv.Yb = nullptr; gv.Yblo = nullptr; gv.YT = vT_h[0]; gv.YTlo = vT_h[1]; gv.t_rows = LATT;
-    PZ_TRY(launch_split_rowgemm(gv, st));
-    prof_mark("attn_qkv_proj", st);
+    const int cur = attn_no_chain ? 0 : (l & 1);
+    if (l == 0 || attn_no_chain) {
+      TcGemm gq;  // [q | k] = x Wqk^T + b
+      gq.X = cat_h[0] + xoff; gq.Xlo = cat_h[1] + xoff; gq.ldx = 1280; set_w(gq, wl); gq.ldw = CATT;
+      gq.bias[0] = s.bqkv + (size_t)l * 384; gq.bias[1] = s.bqkv + ((size_t)(E - 1) * 4 + l) * 384;
+      gq.rows_per_wset = B * LATT; gq.M = rows; gq.Nout = 128; gq.K = CATT; gq.Yb = qk_set[cur][0]; gq.Yblo = qk_set[cur][1]; gq.ldyb = 128;
+      PZ_TRY(launch_split_rowgemm(gq, st));
+      TcGemm gv = gq;  // v^T per cloud (K-major operand of P v)
+      set_w(gv, wl + 128 * CATT); gv.bias[0] = gq.bias[0] + 128; gv.bias[1] = gq.bias[1] + 128;
+      gv.Nout = CATT; gv.Yb = nullptr; gv.Yblo = nullptr; gv.YT = vT_set[cur][0]; gv.YTlo = vT_set[cur][1]; gv.t_rows = LATT;
+      PZ_TRY(launch_split_rowgemm(gv, st));
+      prof_mark("attn_qkv_proj", st);
+    }
     AttnSplit ap;
-    ap.qk_hi = qk_h[0]; ap.qk_lo = qk_h[1]; ap.vT_hi = vT_h[0]; ap.vT_lo = vT_h[1];
+    ap.qk_hi = qk_set[cur][0]; ap.qk_lo = qk_set[cur][1]; ap.vT_hi = vT_set[cur][0]; ap.vT_lo = vT_set[cur][1];
     ap.x_hi = cat_h[0] + xoff; ap.x_lo = cat_h[1] + xoff; ap.ldx = 1280; ap.r_hi = r_h[0]; ap.r_lo = r_h[1];
     ap.attn = o.attention; ap.attn_mode = o.attention ? (l == 0 ? 1 : (l == 3 ? 3 : 2)) : 0;
-    // the out-projection  out = x + relu(Wo r + bo)  runs inside the attention kernel (r never leaves the SM: 67 MB of HBM
-    // traffic and one launch per layer less); PZ_ATTN_NO_FUSE keeps it a separate row GEMM (A/B hook)
-    static const bool attn_no_fuse = getenv("PZ_ATTN_NO_FUSE") != nullptr;
     if (!attn_no_fuse) {
       ap.wo_hi[0] = wp_[0][0] + wl + 384 * CATT; ap.wo_lo[0] = wp_[0][1] + wl + 384 * CATT;
       ap.wo_hi[1] = wp_[1][0] + wl + 384 * CATT; ap.wo_lo[1] = wp_[1][1] + wl + 384 * CATT;
       ap.bo[0] = wa.o_b[l]; ap.bo[1] = wb.o_b[l]; ap.clouds_per_set = B;
       ap.y_hi = cat_h[0] + (size_t)l * CATT; ap.y_lo = cat_h[1] + (size_t)l * CATT; ap.ldy = 1280;
       if (cat_f) { ap.yf = cat_f + (size_t)l * CATT; ap.ldyf = 1280; }
+      if (!attn_no_chain && l < 3) {   // the next layer's projections of these rows
+        const size_t wn = WS_ATT + (size_t)(l + 1) * WS_ATT_STRIDE;
+        ap.wqkv_hi[0] = wp_[0][0] + wn; ap.wqkv_lo[0] = wp_[0][1] + wn; ap.wqkv_hi[1] = wp_[1][0] + wn; ap.wqkv_lo[1] = wp_[1][1] + wn;
+        ap.bqkv[0] = s.bqkv + (size_t)(l + 1) * 384; ap.bqkv[1] = s.bqkv + ((size_t)(E - 1) * 4 + l + 1) * 384;
+        ap.qk2_hi = qk_set[cur ^ 1][0]; ap.qk2_lo = qk_set[cur ^ 1][1]; ap.vT2_hi = vT_set[cur ^ 1][0]; ap.vT2_lo = vT_set[cur ^ 1][1];
+      }
       PZ_TRY(launch_attention_split(ap, C, st));
       prof_mark("attn_softmax_av", st);
       continue;

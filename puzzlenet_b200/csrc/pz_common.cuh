@@ -184,6 +184,13 @@ struct AttnSplit {
   int ldy = 0;
   float* yf = nullptr;
   int ldyf = 0;
+  // chained projections (wqkv_hi[0] != null; needs the fused out-projection): the kernel also computes the NEXT layer's
+  // [q | k | v] = out Wqkv^T + b from its output rows (they never leave the SM between the two products) and writes the next
+  // layer's q|k planes [rows, 128] and v^T planes [cloud][256 ch][256 tokens] -- into buffers other than qk / vT, which the
+  // other CTAs of this launch are still reading.  Wqkv planes [384, 256] fp16 K-major and bias [384] per weight set.
+  const void *wqkv_hi[2] = {nullptr, nullptr}, *wqkv_lo[2] = {nullptr, nullptr};
+  const float* bqkv[2] = {nullptr, nullptr};
+  void *qk2_hi = nullptr, *qk2_lo = nullptr, *vT2_hi = nullptr, *vT2_lo = nullptr;
 };
 int launch_attention_split(const AttnSplit& p, int clouds, cudaStream_t st);
 // heads_split.cu: the boundary heads of predict5 as split-fp16 chained-MMA kernels (used by the split and bf16 paths)

@@ -126,7 +126,7 @@ assert max(errs) < 1e-4 and rot < 0.01 and trans < 1e-4, (errs, rot, trans)
 
 
 @pytest.mark.parametrize("env", [{"PZ_SG_NO_PAIR": "1", "PZ_RG_NO_PAIR": "1", "PZ_STEM_FFMA": "1", "PZ_ATTN_NO_FUSE": "1"},
-                                 {"PZ_SG_PAIR_NST": "2", "PZ_SG_PW16": "1", "PZ_ATTN_NO_FUSE": "1"}])
+                                 {"PZ_SG_PAIR_NST": "2", "PZ_SG_PW16": "1", "PZ_ATTN_NO_CHAIN": "1"}])
 def test_split_fallback_kernels(env):
     """The A/B hooks select the one-CTA kernels (cp.async row GEMM, two-pass gather GEMM, FFMA stem) / the alternative
     pipeline depths; they are read once per process, so the forward runs in a child process.  Same bounds as the default."""
