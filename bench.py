@@ -737,6 +737,8 @@ def run_gpu_arm(args):
     clouds = 2 * B
     mma_factor = 3 if args.precision == "split" else 1
     fused = args.precision == "bf16"
+    split_fused = args.precision == "split" and not os.environ.get("PZ_ATTN_NO_FUSE")
+    chained = split_fused and not os.environ.get("PZ_ATTN_NO_CHAIN")
     # algorithmic work of each stage per step: FLOPs of the reference's product for the dense stages (tensor
     # bound; the split path EXECUTES three MMAs per product -- `executed` below), compulsory bytes for the geometry stages
     # (they are latency / issue bound, the HBM fraction is reported truthfully).  (work, bound, launches)
@@ -746,10 +748,12 @@ def run_gpu_arm(args):
         "tail_linear_maxpool": (2.0 * clouds * 256 * 1280 * 1024, "tensor", 1),
         "tail_linear": (2.0 * clouds * 256 * 1280 * 1024, "tensor", 1),
         "attn_layer_fused": (4 * 2.0 * clouds * 256 * 256 * (384 + 64 + 256 + 256), "tensor", 1),
-        "attn_qkv_proj": (4 * 2.0 * clouds * 256 * 256 * 384, "tensor", 8 if not fused and args.precision != "fp32" else 12),
+        # split path (default build): the out-projection and the NEXT layer's q|k|v projections run inside the attention kernel
+        # (attention_split.cu); only layer 0's projections are launches of their own
+        "attn_qkv_proj": ((1 if chained else 4) * 2.0 * clouds * 256 * 256 * 384, "tensor",
+                          (2 if chained else 8) if not fused and args.precision != "fp32" else 12),
         "attn_out_proj": (4 * 2.0 * clouds * 256 * 256 * 256, "tensor", 4),
-        # split path: the out-projection runs inside the attention kernel (no attn_out_proj stage): its FLOPs count here
-        "attn_softmax_av": (4 * 2.0 * clouds * 256 * 256 * (64 + 256 + (256 if (args.precision == "split" and per_step.get("attn_out_proj", 0) == 0) else 0)),
+        "attn_softmax_av": (2.0 * clouds * 256 * 256 * (4 * (64 + 256) + (4 * 256 if split_fused else 0) + (3 * 384 if chained else 0)),
                             "tensor", 4),
         "fps1": (clouds * (12 * 1024 + 8 * 512), "hbm", 1),
         "fps2": (clouds * (12 * 512 + 8 * 256), "hbm", 1),

@@ -25,6 +25,7 @@
 // current one): two more launches and one more read of the layer's output per layer less.  TMEM: S [0,256), O halves [256,384), [384,512).
 #include <cuda.h>   // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint)
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "pz_common.cuh"
 #include "tc_common.cuh"
@@ -68,7 +69,8 @@ __device__ __forceinline__ void as_tma_load(uint32_t dst, const CUtensorMap* tm,
                ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
 // timeline stamps of CTA 0 (diagnostics, pz_profile_attention_timeline): globaltimer ns at slots 3072..: 0 entry, 1 q|k
-// landed, 2 S in TMEM, 3 P written, 4 / 6 O half 0 / 1 complete, 5 / 7 r half 0 / 1 stored
+// landed, 2 S in TMEM, 3 P written, 4 / 6 O half 0 / 1 complete, 5 / 7 r half 0 / 1 formed, 8 / 10 out half accumulated, 9 / 11
+// stored, 12-14 next q|k / v block accumulated, 15 all stored
 __device__ __forceinline__ void as_stamp(long long* prof, int slot) {
   if (prof != nullptr && blockIdx.x == 0) {
     unsigned long long t;
@@ -367,6 +369,7 @@ __global__ void __launch_bounds__(AS_THREADS, 1) attention_split_kernel(const At
     const float* bsm = reinterpret_cast<const float*>(gen + (bo_s - base)) + 256 + b3 * 128;
     mbar_wait(bar_z + 8 * b3, 0);
     tc_fence_after();
+    if (lane == 0 && wq == 0) as_stamp(prof, 12 + b3);
 #pragma unroll 1
     for (int c32 = 0; c32 < 4; ++c32) {
       float v[32];
@@ -625,6 +628,7 @@ __global__ void __launch_bounds__(AS_THREADS, 1) attention_split_kernel(const At
         z_epilogue(0, warp);
         z_epilogue(1, warp);
         z_epilogue(2, warp);
+        if (tid == 0) as_stamp(prof, 15);
       }
     }
   }
@@ -697,7 +701,8 @@ int launch_attention_split(const AttnSplit& p, int clouds, cudaStream_t st) {
     PZ_TRY(as_make_map(nh, AS_C, chain ? 384 : AS_C, AS_C, &maps.wn[ws][0]));
     PZ_TRY(as_make_map(nl, AS_C, chain ? 384 : AS_C, AS_C, &maps.wn[ws][1]));
   }
-  attention_split_kernel<<<2 * clouds, AS_THREADS, smem, st>>>(p, maps, kernel_timeline_buffer(3072 + 16));
+  static const bool tl_chain_only = getenv("PZ_AS_TL_CHAIN") != nullptr;   // diagnostics: only launches with chained projections stamp
+  attention_split_kernel<<<2 * clouds, AS_THREADS, smem, st>>>(p, maps, (tl_chain_only && !chain) ? nullptr : kernel_timeline_buffer(3072 + 16));
   PZ_LAUNCH_CHECK();
   return 0;
 }

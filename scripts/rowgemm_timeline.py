@@ -35,10 +35,11 @@ if t[2048] or t[2048 + 512]:
         print("  MMAs issued per job:          ", " ".join(fmt(g(128 + j)) for j in range(16) if t[b + 128 + j]))
         print("  epilogue accf/done per tile:  ", " ".join(f"{fmt(g(192 + 2 * j))}/{fmt(g(193 + 2 * j))}" for j in range(8) if t[b + 192 + 2 * j]))
 
-a = [t[3072 + i] for i in range(12)]
+a = [t[3072 + i] for i in range(16)]
 if a[0]:
     names = ["entry", "q|k landed", "S in TMEM", "P written", "O half 0", "r half 0 stored", "O half 1", "r half 1 stored",
-             "out half 0 accumulated", "out half 0 stored", "out half 1 accumulated", "out half 1 stored"]
+             "out half 0 accumulated", "out half 0 stored", "out half 1 accumulated", "out half 1 stored",
+             "next q|k accumulated", "next v block 0 accumulated", "next v block 1 accumulated", "next q|k|v stored"]
     a = [v for v in a if v]
     print("attention_split_kernel, CTA 0 (us since entry): " + ", ".join(f"{n} {(v - a[0]) / 1e3:.2f}" for n, v in zip(names, a)))
 
