@@ -18,7 +18,9 @@ value : device-resident inputs (128 rotating batches = 201 MB, larger than the 1
         (the same schedule as the e2e leg, minus the host copies); max over ranks; the K-step region is repeated
         --repeats times and the MEDIAN is reported (spread alongside).
 single_stream : the same K steps launched eagerly on ONE stream with per-step events and an L2 flush between steps
-        (the latency view; its per-stage events feed the rooflines).
+        (the latency view: what a plain `predict5` call costs; the kernels of the split path chain by programmatic
+        dependent launch here).  The per-stage events that feed the rooflines come from separate passes with the stage
+        recorder on.
 e2e   : same metric through the public API from pinned HOST buffers: H2D of both clouds + FPS starts and D2H of the
         twist + both boundary-logit tensors inside the timed region.
 parity: the outputs the LAST e2e step copied to the host, checked against the CPU oracle on 8 pairs of that batch (pairs
@@ -536,7 +538,6 @@ def run_gpu_arm(args):
 
     # ---- single-stream leg: device-resident inputs, eager launches, per-step events, L2 flush between steps
     sampler = ClockSampler(local) if rank == 0 else None
-    lib.pz_profile_enable(1)
     launches0 = lib.pz_launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
@@ -549,9 +550,17 @@ def run_gpu_arm(args):
     barrier()
     wall = time.perf_counter() - t_wall0
     launches = lib.pz_launch_count() - launches0
+    total_ms = sum(a.elapsed_time(b) for a, b in ev)
+
+    # ---- the same steps with the stage recorder on (an event after every stage: the kernels are then launched without
+    # programmatic dependent launch, so this pass is slower than the leg above and only its per-stage split is used)
+    lib.pz_profile_enable(1)
+    for i in range(min(args.steps, 20)):
+        flush.zero_()
+        step_resident(i)
+    torch.cuda.synchronize()
     calls, stages = _lib.profile_collect()
     lib.pz_profile_enable(0)
-    total_ms = sum(a.elapsed_time(b) for a, b in ev)
 
     # ---- per-kernel durations for the rooflines: the same steps once more with the internal side stream switched off,
     # so that every stage's CUDA-event time is its own (above, the geometry chain overlaps the feature chain)
@@ -843,7 +852,8 @@ def run_gpu_arm(args):
                        + ("" if args.no_graphs else ", each replaying one captured CUDA graph per forward")},
         "parity": parity_all[args.precision] if parity_all else None,
         "single_stream": {"value": single_value, "unit": UNIT, "ms_per_step": total_ms / args.steps,
-                          "how": "eager launches on one stream, per-step CUDA events, L2 flushed between steps"},
+                          "how": "eager launches on one stream (programmatic dependent launch between the split path's "
+                                 "kernels), per-step CUDA events, L2 flushed between steps"},
         "gpu_launches": int(round(launches_eager_per_step * args.steps)),
         "gpu_launches_note": f"{launches_eager_per_step:.0f} kernels per forward (counted on the eager single-stream leg; "
                              "the value / e2e legs replay the same kernels from a captured CUDA graph)",
@@ -856,8 +866,8 @@ def run_gpu_arm(args):
         "torch_gpu_baseline": torch_gpu,
         "stages_ms_per_step": {k: round(v, 4) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])},
         "stages_note": "stages_ms_per_step: CUDA events, stages back to back on one stream (used for the rooflines); "
-                       "stages_ms_per_step_timed_region: the same events inside the single-stream leg, where the geometry "
-                       "chain runs on a second stream and overlaps the feature chain",
+                       "stages_ms_per_step_timed_region: the same events with the schedule of a plain call (bf16 / fp32 "
+                       "paths: the geometry chain on a second stream, overlapping the feature chain; split path: one chain)",
         "stages_ms_per_step_timed_region": {k: round(v, 4) for k, v in sorted(per_step_overlapped.items(), key=lambda kv: -kv[1])},
         "split_path": path_line("split"), "bf16_path": path_line("bf16"), "fp32_path": path_line("fp32"),
         "other_configs": other_configs,

@@ -130,6 +130,16 @@ __global__ void __launch_bounds__(AS_THREADS, 1) attention_split_kernel(const At
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the inits are visible to the TMA unit
+    if (p.dep_flags == nullptr) {
+      pdl_wait();                   // the whole previous grid (pz_common.cuh: programmatic dependent launch)
+    } else {                        // both CTAs of this cloud in the previous layer's launch have stored their last row
+      const int* f = p.dep_flags + cloud;
+      int v;
+      do {
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+      } while (v < 2);
+      asm volatile("fence.proxy.async;" ::: "memory");   // their generic-proxy stores, before this CTA's TMA reads
+    }
     const int r = (int)row0;
     as_expect_tx(bar_qk, 6 * T16);
     as_tma_load(q_hi_s, &maps.qk[0], 0, r + qb * 128, bar_qk);
@@ -143,12 +153,16 @@ __global__ void __launch_bounds__(AS_THREADS, 1) attention_split_kernel(const At
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  if (p.dep_flags == nullptr) pdl_wait();
   if (fuse) reinterpret_cast<float*>(gen + (bo_s - base))[tid] = p.bo[wset][tid];   // AS_THREADS == 256 == channels
   if (chain)
     for (int i = tid; i < 384; i += AS_THREADS) reinterpret_cast<float*>(gen + (bo_s - base))[256 + i] = p.bqkv[wset][i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  // every CTA of this launch has passed its own wait (grid or cloud flag) before the next launch may become resident: its
+  // CTAs then never run ahead of anything older than this launch (the flags they poll were zeroed long before)
+  pdl_trigger();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
 
   // r = x - O / sum for one 128-channel half `eh` of the block's 128 rows, by the four warps (quarters wq) of one group
@@ -634,6 +648,10 @@ __global__ void __launch_bounds__(AS_THREADS, 1) attention_split_kernel(const At
   }
   tc_fence_before();
   __syncthreads();
+  if (tid == 0 && p.sig_flags != nullptr) {   // every store of this CTA is ordered before the barrier: release them to the next layer
+    __threadfence();
+    asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(p.sig_flags + cloud) : "memory");
+  }
   if (warp == 4) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
   }
@@ -702,7 +720,8 @@ int launch_attention_split(const AttnSplit& p, int clouds, cudaStream_t st) {
     PZ_TRY(as_make_map(nl, AS_C, chain ? 384 : AS_C, AS_C, &maps.wn[ws][1]));
   }
   static const bool tl_chain_only = getenv("PZ_AS_TL_CHAIN") != nullptr;   // diagnostics: only launches with chained projections stamp
-  attention_split_kernel<<<2 * clouds, AS_THREADS, smem, st>>>(p, maps, (tl_chain_only && !chain) ? nullptr : kernel_timeline_buffer(3072 + 16));
+  long long* prof = (tl_chain_only && !chain) ? nullptr : kernel_timeline_buffer(3072 + 16);
+  PZ_CUDA(launch_pdl(attention_split_kernel, dim3(2 * clouds), dim3(AS_THREADS), smem, st, p, maps, prof));
   PZ_LAUNCH_CHECK();
   return 0;
 }

@@ -160,6 +160,7 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const float* __restrict__ 
     w1p[tid] = make_float4(w.w1[tid * 3], w.w1[tid * 3 + 1], w.w1[tid * 3 + 2], w.b1[tid]);
     b2s[tid] = w.b2[tid];
   }
+  pdl_enter();   // the weights above are model parameters / images packed at least two launches ago; xyz is the predecessor's
   __syncthreads();
 #pragma unroll 1
   for (int rep = 0; rep < reps; ++rep) {
@@ -480,6 +481,7 @@ static int launch_attention(const float* q, int ldq, const float* k, int ldk, co
 __global__ void __launch_bounds__(256) rowblock_max_kernel(const float* __restrict__ in, int ldi, int G, int N,
                                                            int R, int rmod, int coloff, float* __restrict__ out,
                                                            int ldo) {
+  pdl_enter();
   const int r = blockIdx.y;
   const int c = blockIdx.x * 256 + threadIdx.x;
   if (c >= N || r >= R) return;
@@ -521,6 +523,7 @@ __global__ void __launch_bounds__(256) skinny_linear_kernel(const float* __restr
                                                             const float* __restrict__ W, const float* __restrict__ bias,
                                                             int M, int N, int K, int relu, float* __restrict__ Y, int ldy) {
   extern __shared__ __align__(16) float sk_smem[];
+  pdl_enter();
   float* xs = sk_smem;                                   // [2][64][SK_XLD]
   float* ws = sk_smem + 2 * SK_ROWS * SK_XLD;            // [2][8][128]
   const int tid = threadIdx.x, r2 = tid & 31, ke = tid >> 5;
@@ -601,7 +604,7 @@ static int skinny_linear(const float* A, int lda, const float* W, const float* b
   if (K % SK_KC == 0 && lda % 4 == 0 && (((uintptr_t)A | (uintptr_t)W) & 15) == 0) {
     PZ_CUDA(cudaFuncSetAttribute(skinny_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SK_SMEM));
     dim3 grid((N + SK_COLS - 1) / SK_COLS, (M + SK_ROWS - 1) / SK_ROWS);
-    skinny_linear_kernel<<<grid, 256, SK_SMEM, st>>>(A, lda, W, bias, M, N, K, relu, Y, ldy);
+    PZ_CUDA(launch_pdl(skinny_linear_kernel, grid, dim3(256), SK_SMEM, st, A, lda, W, bias, M, N, K, relu, Y, ldy));
     PZ_LAUNCH_CHECK();
     return 0;
   }
@@ -1060,8 +1063,9 @@ __global__ void __launch_bounds__(256) centre_proj_f32_kernel(const float* __res
   extern __shared__ float cp_w[];                 // [2 sets][C1][3]
   for (int i = threadIdx.x; i < 2 * C1 * 3; i += 256) {
     const int set = i / (C1 * 3), r = i - set * C1 * 3, k = r / 3, d = r - k * 3;
-    cp_w[i] = (set == 0 ? w1a : w1b)[(size_t)k * ldw1 + d];
+    cp_w[i] = (set == 0 ? w1a : w1b)[(size_t)k * ldw1 + d];   // model parameters: never written by a kernel
   }
+  pdl_enter();
   __syncthreads();
   // four consecutive channels of a row per thread: one 16-byte store, 32-bit index arithmetic (C1 % 4 == 0, rows * C1 < 2^31)
   const unsigned c4 = (unsigned)C1 >> 2, total4 = (unsigned)rows * c4;
@@ -1084,7 +1088,8 @@ static int launch_centre_proj_f32(const float* centres, const float* w1a, const 
              "centre projection: needs C1 %% 4 == 0, rows * C1 < 2^31 and a 16-byte aligned Q");
   const size_t total = (size_t)rows * C1 / 4, want = (total + 255) / 256;
   const unsigned blocks = (unsigned)(want < (size_t)kNumSMs * 8 ? want : (size_t)kNumSMs * 8);
-  centre_proj_f32_kernel<<<blocks, 256, (size_t)2 * C1 * 3 * sizeof(float), st>>>(centres, w1a, w1b, ldw1, rows_per_set, rows, C1, Q);
+  PZ_CUDA(launch_pdl(centre_proj_f32_kernel, dim3(blocks), dim3(256), (size_t)2 * C1 * 3 * sizeof(float), st, centres, w1a, w1b, ldw1,
+                     rows_per_set, rows, C1, Q));
   PZ_LAUNCH_CHECK();
   return 0;
 }
@@ -1448,28 +1453,38 @@ static int encoder_forward_split(const PzEncoderWeights* w, int E, int B, const 
     g.W[0] = wp_[0][0] + off; g.Wlo[0] = wp_[0][1] + off; g.W[1] = wp_[1][0] + off; g.Wlo[1] = wp_[1][1] + off;
   };
 
-  // ---- geometry on the side stream (FPS -> centre projection -> kNN, both stages)
+  // the attention launches' hand-over counters (see the attention block): zeroed here, where no kernel-to-kernel link of the
+  // programmatic launch chain is broken by the memset node
+  PZ_CUDA(cudaMemsetAsync(s.tailp, 0, (size_t)3 * C * sizeof(int), st));
+
+  // ---- geometry (FPS -> centre projection -> kNN, both stages): ahead of the feature chain on the caller's stream
   SideStream* ss = nullptr;
   PZ_TRY(side_stream(&ss, st));
-  static const bool env_serial = getenv("PZ_NO_SIDE_STREAM") != nullptr;
+  // ONE chain by default: every GEMM CTA of this path fills an SM (shared memory), so a geometry kernel on a second stream
+  // does not share SMs with them, it delays some of the CTAs of a persistent GEMM and the whole launch waits for those
+  // (eager forward 1.70 ms with the side stream, 1.59 without, 1.51 with programmatic dependent launch on the one chain;
+  // the 4-stream graph schedule 1.39 vs 1.37 ms per step).  PZ_SIDE_STREAM=1 restores the second stream (A/B hook).
+  static const bool env_serial = getenv("PZ_SIDE_STREAM") == nullptr || getenv("PZ_NO_SIDE_STREAM") != nullptr;
   const bool serial = env_serial || prof_serial();
   cudaStream_t sg = serial ? st : ss->stream;
   const int gl = serial ? 0 : 1;
-  PZ_CUDA(cudaEventRecord(ss->fork, st));
-  PZ_CUDA(cudaStreamWaitEvent(sg, ss->fork, 0));
+  if (!serial) {
+    PZ_CUDA(cudaEventRecord(ss->fork, st));
+    PZ_CUDA(cudaStreamWaitEvent(sg, ss->fork, 0));
+  }
   prof_mark("_side_begin", sg, gl);
   PZ_TRY(launch_fps(xyz, C, NPTS, start1, S1, o.fps1, nullptr, s.nx1, sg));
   prof_mark("fps1", sg, gl);
   PZ_TRY(launch_knn(s.nx1, xyz, C, S1, NPTS, KNN, o.knn1, s.knn1r, nullptr, sg));
   prof_mark("knn1", sg, gl);
   PZ_TRY(launch_centre_proj_f32(s.nx1, wa.mlp3_w, wb.mlp3_w, 3 + D0, B * S1, C * S1, C1A, Q1, sg));
-  PZ_CUDA(cudaEventRecord(ss->join_a, sg));
+  if (!serial) PZ_CUDA(cudaEventRecord(ss->join_a, sg));
   PZ_TRY(launch_fps(s.nx1, C, S1, start2, S2, o.fps2, nullptr, nx2, sg));
   prof_mark("fps2", sg, gl);
   PZ_TRY(launch_knn(nx2, s.nx1, C, S2, S1, KNN, o.knn2, s.knn2r, nullptr, sg));
   prof_mark("knn2", sg, gl);
   PZ_TRY(launch_centre_proj_f32(nx2, wa.mlp5_w, wb.mlp5_w, 3 + C1B, B * S2, C * S2, C2A, Q2, sg));
-  PZ_CUDA(cudaEventRecord(ss->join_b, sg));
+  if (!serial) PZ_CUDA(cudaEventRecord(ss->join_b, sg));
 
   // ---- feature chain
   // stem: layer 2 as a split-fp16 mma.sync product (x_feature within ~1e-6 of the fp32 stem), the fp16 hi / lo planes of
@@ -1482,9 +1497,9 @@ static int encoder_forward_split(const PzEncoderWeights* w, int E, int B, const 
     PZ_TRY(launch_split_planes(xfeat, D0, (size_t)C * NPTS, D0, xfeat_h[0], xfeat_h[1], D0, st));
   } else {
     PZ_CUDA(cudaFuncSetAttribute(stem_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STEM_TC_SMEM));
-    stem_tc_kernel<true><<<C * NPTS / (128 * reps), 128, STEM_TC_SMEM, st>>>(
-        xyz, stem_of(wa), stem_of(wb), nullptr, nullptr, B, reps, xfeat, reinterpret_cast<__nv_bfloat16*>(xfeat_h[0]),
-        reinterpret_cast<__half*>(xfeat_h[1]));
+    PZ_CUDA(launch_pdl(stem_tc_kernel<true>, dim3(C * NPTS / (128 * reps)), dim3(128), STEM_TC_SMEM, st, xyz, stem_of(wa), stem_of(wb),
+                       (const __nv_bfloat16*)nullptr, (const __nv_bfloat16*)nullptr, B, reps, xfeat,
+                       reinterpret_cast<__nv_bfloat16*>(xfeat_h[0]), reinterpret_cast<__half*>(xfeat_h[1])));
     PZ_LAUNCH_CHECK();
   }
   prof_mark("stem", st);
@@ -1497,7 +1512,7 @@ static int encoder_forward_split(const PzEncoderWeights* w, int E, int B, const 
     prof_mark("sg1_layer1", st);
   }
   if (after_stem) PZ_TRY((*after_stem)(xfeat, nullptr));
-  PZ_CUDA(cudaStreamWaitEvent(st, ss->join_a, 0));
+  if (!serial) PZ_CUDA(cudaStreamWaitEvent(st, ss->join_a, 0));
   prof_mark("_wait_geometry1", st);
   {
     TcGemm g;  // f1f = max_k relu(W4 relu(P1[j] - Q1[s]) + b4)
@@ -1515,7 +1530,7 @@ static int encoder_forward_split(const PzEncoderWeights* w, int E, int B, const 
     PZ_TRY(launch_split_rowgemm(g, st));
     prof_mark("sg2_layer1", st);
   }
-  PZ_CUDA(cudaStreamWaitEvent(st, ss->join_b, 0));
+  if (!serial) PZ_CUDA(cudaStreamWaitEvent(st, ss->join_b, 0));
   prof_mark("_wait_geometry2", st);
   float* cat_f = o.att_cat;
   {
@@ -1540,6 +1555,10 @@ static int encoder_forward_split(const PzEncoderWeights* w, int E, int B, const 
   // still read the current ones.  PZ_ATTN_NO_FUSE / PZ_ATTN_NO_CHAIN keep them separate row GEMMs (A/B hooks).
   static const bool attn_no_fuse = getenv("PZ_ATTN_NO_FUSE") != nullptr;
   static const bool attn_no_chain = attn_no_fuse || getenv("PZ_ATTN_NO_CHAIN") != nullptr;
+  // chained launches hand over per cloud (AttnSplit::dep_flags): 3 x C counters in the tail's scratch, idle until the tail
+  static const bool attn_no_pdl = getenv("PZ_ATTN_NO_PDL") != nullptr;   // A/B hook
+  int* aflags = reinterpret_cast<int*>(s.tailp);
+  const bool handover = !attn_no_chain && !attn_no_pdl && pdl_enabled();
   h16* qk_set[2][2] = {{qk_h[0], qk_h[1]}, {s.xfeat_b, reinterpret_cast<h16*>(s.k)}};   // second set: idle buffers of equal size
   h16* vT_set[2][2] = {{vT_h[0], vT_h[1]}, {r_h[0], r_h[1]}};                           // (r is not materialised when fused)
   for (int l = 0; l < 4; ++l) {
@@ -1573,7 +1592,9 @@ static int encoder_forward_split(const PzEncoderWeights* w, int E, int B, const 
         ap.wqkv_hi[0] = wp_[0][0] + wn; ap.wqkv_lo[0] = wp_[0][1] + wn; ap.wqkv_hi[1] = wp_[1][0] + wn; ap.wqkv_lo[1] = wp_[1][1] + wn;
         ap.bqkv[0] = s.bqkv + (size_t)(l + 1) * 384; ap.bqkv[1] = s.bqkv + ((size_t)(E - 1) * 4 + l + 1) * 384;
         ap.qk2_hi = qk_set[cur ^ 1][0]; ap.qk2_lo = qk_set[cur ^ 1][1]; ap.vT2_hi = vT_set[cur ^ 1][0]; ap.vT2_lo = vT_set[cur ^ 1][1];
+        if (handover) ap.sig_flags = aflags + (size_t)l * C;
       }
+      if (handover && l > 0) ap.dep_flags = aflags + (size_t)(l - 1) * C;
       PZ_TRY(launch_attention_split(ap, C, st));
       prof_mark("attn_softmax_av", st);
       continue;
@@ -1599,7 +1620,7 @@ static int encoder_forward_split(const PzEncoderWeights* w, int E, int B, const 
     g.Ymax = s.tailp; g.ldmax = 1024;            // per 128-row tile column maxima: two tiles per cloud
     PZ_TRY(launch_split_rowgemm(g, st));
     prof_mark("tail_linear_maxpool", st);
-    rowblock_max_kernel<<<dim3(4, C), 256, 0, st>>>(s.tailp, 1024, LATT / 128, 1024, C, C, 0, fg, 1024);
+    PZ_CUDA(launch_pdl(rowblock_max_kernel, dim3(4, C), dim3(256), 0, st, (const float*)s.tailp, 1024, LATT / 128, 1024, C, C, 0, fg, 1024));
     PZ_LAUNCH_CHECK();
     prof_mark("tail_point_max", st);
     if (fglob_pair)
@@ -1806,6 +1827,7 @@ namespace {
 __global__ void __launch_bounds__(256) stage_inputs_kernel(const float4* __restrict__ fpc, const float4* __restrict__ mrpc, size_t n16,
                                                            float4* __restrict__ xyz, const int64_t* __restrict__ starts, int B,
                                                            int64_t* __restrict__ st1, int64_t* __restrict__ st2) {
+  pdl_enter();
   const size_t stride = (size_t)gridDim.x * 256;
   for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < 2 * n16; i += stride) xyz[i] = i < n16 ? fpc[i] : mrpc[i - n16];
   if (blockIdx.x == 0) {
@@ -1853,8 +1875,8 @@ extern "C" int pz_predict5(const PzEncoderWeights* enc_host, const PzHeadWeights
   // both clouds into one [2B, 1024, 3] batch; starts [4,B]: (Encoder s1, Encoder s2, Encoder2 s1, Encoder2 s2) -> st1 =
   // rows 0,2; st2 = rows 1,3.  One launch instead of six copy operations (each ~4 us of stream time).
   if ((((uintptr_t)fpc | (uintptr_t)mrpc) & 15) == 0) {
-    stage_inputs_kernel<<<kNumSMs, 256, 0, st>>>(reinterpret_cast<const float4*>(fpc), reinterpret_cast<const float4*>(mrpc),
-                                                 cloud_bytes / 16, reinterpret_cast<float4*>(s.xyz), starts, B, s.st1, s.st2);
+    PZ_CUDA(launch_pdl(stage_inputs_kernel, dim3(kNumSMs), dim3(256), 0, st, reinterpret_cast<const float4*>(fpc),
+                       reinterpret_cast<const float4*>(mrpc), cloud_bytes / 16, reinterpret_cast<float4*>(s.xyz), starts, B, s.st1, s.st2));
     PZ_LAUNCH_CHECK();
   } else {
     PZ_CUDA(cudaMemcpyAsync(s.xyz, fpc, cloud_bytes, cudaMemcpyDeviceToDevice, st));

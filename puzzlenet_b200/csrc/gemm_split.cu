@@ -116,6 +116,7 @@ __global__ void __launch_bounds__(SG_THREADS, 1) split_rowgemm_kernel(const TcGe
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  pdl_enter();   // the prologue above touched no global memory
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -361,7 +362,7 @@ static int split_rowgemm_launch(const TcGemm& g, cudaStream_t st) {
   int grid = tiles < kNumSMs ? tiles : kNumSMs;
   if (nsets == 2 && (grid & 1)) --grid;
   if (grid < nsets) grid = nsets;
-  kern<<<grid, SG_THREADS, smem, st>>>(g);
+  PZ_CUDA(launch_pdl(kern, dim3(grid), dim3(SG_THREADS), smem, st, g));
   PZ_LAUNCH_CHECK();
   return 0;
 }
@@ -460,6 +461,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RP_THREADS, 1) split
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
+  pdl_enter();   // the prologue above touched no global memory
   tc_fence_before();
   cluster_sync_all();        // barriers initialised and TMEM allocated in both CTAs
   tc_fence_after();
@@ -834,7 +836,7 @@ static int split_rowgemm_pair_launch(const TcGemm& g, cudaStream_t st) {
                      (!strcmp(tl_sel, "vt") && g.YT) || (!strcmp(tl_sel, "p1") && g.K == 64) || (!strcmp(tl_sel, "tail") && g.Ymax);
     if (hit) gd.prof = kernel_timeline_buffer(2048 + 1024);
   }
-  kern<<<2 * per * nsets, RP_THREADS, smem, st>>>(gd, maps);
+  PZ_CUDA(launch_pdl(kern, dim3(2 * per * nsets), dim3(RP_THREADS), smem, st, gd, maps));
   PZ_LAUNCH_CHECK();
   return 0;
 }
@@ -962,6 +964,8 @@ __global__ void __launch_bounds__((5 + PW) * 32, 1) split_gather_kernel(const Tc
     }
     fence_proxy_async();
   }
+  // the weight planes above were packed at least two launches ago (complete before this grid can be resident, see pdl_enter)
+  pdl_enter();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -1211,6 +1215,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SG_THREADS, 1) split
     }
     fence_proxy_async();
   }
+  // the weight planes above were packed at least two launches ago (complete before this grid can be resident, see pdl_enter)
+  pdl_enter();
   tc_fence_before();
   cluster_sync_all();        // barriers initialised, TMEM allocated and weights resident in BOTH CTAs
   tc_fence_after();
@@ -1409,7 +1415,7 @@ static int split_gather_pair_launch(const TcGemm& g, cudaStream_t st) {
   int per = (kNumSMs / 2) / nsets;                 // CTA pairs per weight set
   if (per > tiles_per_set) per = tiles_per_set;
   if (per < 1) per = 1;
-  kern<<<2 * per * nsets, SG_THREADS, smem, st>>>(g);
+  PZ_CUDA(launch_pdl(kern, dim3(2 * per * nsets), dim3(SG_THREADS), smem, st, g));
   PZ_LAUNCH_CHECK();
   return 0;
 }
@@ -1428,7 +1434,7 @@ static int split_gather_launch(const TcGemm& g, cudaStream_t st) {
   int per = kNumSMs / nparts;
   if (per > tiles_per_part) per = tiles_per_part;
   if (per < 1) per = 1;
-  kern<<<per * nparts, (5 + PW) * 32, smem, st>>>(g);
+  PZ_CUDA(launch_pdl(kern, dim3(per * nparts), dim3((5 + PW) * 32), smem, st, g));
   PZ_LAUNCH_CHECK();
   return 0;
 }

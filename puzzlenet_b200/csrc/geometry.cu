@@ -43,6 +43,7 @@ __global__ void __launch_bounds__(T) fps_kernel(const float* __restrict__ xyz, i
   const int c = blockIdx.x;
   const int t = threadIdx.x;
   const int lane = t & 31, warp = t >> 5;
+  pdl_enter();
   const float* p = xyz + (size_t)c * N * 3;
   for (int i = t; i < N * 3; i += T) {
     float v = p[i];
@@ -117,7 +118,7 @@ static int fps_launch_t(const float* xyz, int B, int N, const int64_t* start, in
   PZ_REQUIRE(smem <= 227 * 1024, PZ_ERR_UNSUPPORTED, "pz_fps: N=%d, S=%d need %zu B of shared memory", N, S, smem);
   if (smem > 48 * 1024)
     PZ_CUDA(cudaFuncSetAttribute(fps_kernel<PPT, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  fps_kernel<PPT, T><<<B, T, smem, st>>>(xyz, N, S, start, out64, out_rows32, new_xyz);
+  PZ_CUDA(launch_pdl(fps_kernel<PPT, T>, dim3(B), dim3(T), smem, st, xyz, N, S, start, out64, out_rows32, new_xyz));
   PZ_LAUNCH_CHECK();
   return 0;
 }
@@ -439,6 +440,7 @@ __global__ void __launch_bounds__(KNN_WARPS * 32, 3) knn_kernel(const float* __r
   // memory between chunks (only clouds larger than KNN_CHUNK points have more than one chunk); the query loop
   // is deliberately not unrolled so that the networks are emitted once (instruction-cache footprint)
   __shared__ unsigned park_d[KNN_WARPS][KNN_QPW][32], park_i[KNN_WARPS][KNN_QPW][32];
+  pdl_enter();
 
   for (int base = 0; base < N; base += KNN_CHUNK) {
     const int cnt = min(KNN_CHUNK, N - base);
@@ -1165,7 +1167,7 @@ int launch_knn(const float* query, const float* xyz, int B, int S, int N, int K,
     return 0;
   }
   dim3 grid((S + KNN_WARPS * KNN_QPW - 1) / (KNN_WARPS * KNN_QPW), B);
-  knn_kernel<<<grid, KNN_WARPS * 32, 0, st>>>(query, xyz, S, N, K, out64, out_rows32, out_d2);
+  PZ_CUDA(launch_pdl(knn_kernel, grid, dim3(KNN_WARPS * 32), 0, st, query, xyz, S, N, K, out64, out_rows32, out_d2));
   PZ_LAUNCH_CHECK();
   return 0;
 }

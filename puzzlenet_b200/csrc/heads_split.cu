@@ -135,6 +135,7 @@ __global__ void __launch_bounds__(128) head_pre_split_kernel(const float* __rest
   const int cloud = (int)(((size_t)blockIdx.x * reps * 128) / NPTS_H);
   const int set = cloud / B;
   const HeadMlp3& w = set == 0 ? wa : wb;
+  pdl_enter();   // the images may be the direct predecessor's (head_images_kernel)
   {
     const uint4* src = reinterpret_cast<const uint4*>(img + (size_t)set * HEAD_SPLIT_IMG_SET);
     uint4* dst = reinterpret_cast<uint4*>(ws);
@@ -209,6 +210,7 @@ __global__ void __launch_bounds__(128) head_seg_split_kernel(const float* __rest
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
   const int cloud = (int)(((size_t)blockIdx.x * reps * 128) / NPTS_H), set = cloud / B, b = cloud - set * B;
   const HeadMlp3& w = set == 0 ? wa : wb;
+  pdl_enter();
   {
     const uint4* src = reinterpret_cast<const uint4*>(img + (size_t)set * HEAD_SPLIT_IMG_SET + 2 * PRE_ROWS * HS_WS);
     uint4* dst = reinterpret_cast<uint4*>(wseg);
@@ -300,9 +302,11 @@ int launch_heads_split(const float* xfeat, const HeadMlp3& pre_f, const HeadMlp3
   const int P = 2 * B * NPTS_H, reps = 4;
   const size_t pre_smem = (size_t)2 * PRE_ROWS * HS_WS * sizeof(__half) + (3 * 64 + 4 * 64) * sizeof(float);
   PZ_CUDA(cudaFuncSetAttribute(head_pre_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pre_smem));
-  head_pre_split_kernel<<<P / (128 * reps), 128, pre_smem, st>>>(xfeat, pre_f, pre_r, im, B, reps, local, tilemax);
+  PZ_CUDA(launch_pdl(head_pre_split_kernel, dim3(P / (128 * reps)), dim3(128), pre_smem, st, xfeat, pre_f, pre_r, (const __half*)im, B, reps,
+                     local, tilemax));
   PZ_LAUNCH_CHECK();
-  head_seg_split_kernel<<<P / (128 * reps), 128, 0, st>>>(local, seg_f, seg_r, im, B, reps, tilemax, de_fpcb, de_mrpcb);
+  PZ_CUDA(launch_pdl(head_seg_split_kernel, dim3(P / (128 * reps)), dim3(128), 0, st, (const float*)local, seg_f, seg_r, (const __half*)im, B,
+                     reps, (const float*)tilemax, de_fpcb, de_mrpcb));
   PZ_LAUNCH_CHECK();
   return 0;
 }

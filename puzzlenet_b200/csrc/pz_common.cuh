@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <utility>
 
 #include "../../include/puzzlenet_b200.h"
 
@@ -33,6 +34,41 @@ int fail(int code, const char* fmt, ...);
     ::pz::count_launch();            \
     PZ_CUDA(cudaGetLastError());     \
   } while (0)
+
+// Programmatic dependent launch (PDL) of the forward's kernel chain.  A kernel launched through launch_pdl() may become
+// resident while its predecessor in the stream is still draining (launch latency, barrier / TMEM set-up and descriptor
+// fetches overlap the predecessor's tail); every such kernel calls pdl_enter() BEFORE its first access to global memory:
+// it blocks until the predecessor grid has completed and its writes are visible, and only then lets the successor in, so
+// at most two grids of the chain are in flight and a resident CTA never runs ahead of anything but its direct predecessor.
+// Only kernels that call pdl_enter() may be launched with launch_pdl().  PZ_NO_PDL=1: plain launches (A/B hook).
+// Measured (B=64 split forward, 1 B200): eager launches on one stream 1.59 -> 1.51 ms per forward.  NOT used under stream
+// capture: in the 4-stream graph schedule the early-resident CTAs of one stream's next kernel hold SMs that another
+// stream's ready kernel would have used (1.37 -> 1.52 ms per step), nor with the stage recorder on (an event record between
+// two launches turns the programmatic edge into a slower full one: 1.67 -> 1.79 ms).
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() {
+  pdl_wait();
+  pdl_trigger();
+}
+#endif
+bool pdl_enabled();                   // capi.cu: not disabled by PZ_NO_PDL
+bool pdl_for_stream(cudaStream_t st);   // capi.cu: pdl_enabled(), the stage recorder is off and `st` is not capturing
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_for_stream(st) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
 
 // propagate a non-zero status from an internal call
 #define PZ_TRY(expr)         \
@@ -191,6 +227,12 @@ struct AttnSplit {
   const void *wqkv_hi[2] = {nullptr, nullptr}, *wqkv_lo[2] = {nullptr, nullptr};
   const float* bqkv[2] = {nullptr, nullptr};
   void *qk2_hi = nullptr, *qk2_lo = nullptr, *vT2_hi = nullptr, *vT2_lo = nullptr;
+  // cloud-granular hand-over between consecutive chained launches (256 CTAs on 148 SMs = 1.73 waves each: the second wave
+  // of a layer leaves 40 SMs idle).  sig_flags[cloud] is incremented by each of a cloud's two CTAs after their last store;
+  // a launch with dep_flags set is started with programmatic stream serialisation (its CTAs become resident as soon as every
+  // CTA of the previous launch is) and every CTA waits for dep_flags[cloud] == 2 instead of the whole previous grid.
+  const int* dep_flags = nullptr;
+  int* sig_flags = nullptr;
 };
 int launch_attention_split(const AttnSplit& p, int clouds, cudaStream_t st);
 // heads_split.cu: the boundary heads of predict5 as split-fp16 chained-MMA kernels (used by the split and bf16 paths)
