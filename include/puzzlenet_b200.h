@@ -57,7 +57,9 @@ int pz_device_arch(void);
 /* Instrumentation used by bench.py (the only process-global state besides the error string).
  * pz_launch_count: kernels launched by this library in this process so far.
  * pz_profile_enable(2): as 1, and the internal side stream is not used (stages run back to back on the caller's
- * stream), which gives per-stage times free of overlap.
+ * stream), which gives per-stage times free of overlap.  While the recorder is on (1 or 2) the split precision launches
+ * its kernels plainly instead of by programmatic dependent launch (an event between two launches would turn the
+ * programmatic edge into a slower full one), so a recorded call is slower than an unrecorded one.
  * pz_profile_enable(1): record CUDA events on the caller's stream between the stages of every following
  * pz_predict5 / pz_encoder_forward call (at most 512 calls are kept); pz_profile_collect synchronises the
  * device, sums the elapsed milliseconds per stage over those calls into ms[0..n), stores the stage names
