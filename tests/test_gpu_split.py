@@ -103,6 +103,33 @@ def test_predict5_split_vs_oracle(cuda_model, state_dict, B):
     assert again[0].shape == out.shape
 
 
+def test_split_chain_is_race_free_at_b64(cuda_model):
+    """The split forward is ONE chain of launches linked by programmatic dependent launch, and consecutive attention
+    launches hand over per cloud (counters in the tail's scratch): 40 eager forwards back to back on one workspace, alternating
+    two inputs, must reproduce the first result of each input bit for bit."""
+    a = synthetic_pairs(64, seed=900)
+    b = synthetic_pairs(64, seed=901)
+    ba, bb = (make_batch(x[0].to(DEV), x[1].to(DEV)) for x in (a, b))
+    starts = torch.stack([torch.randint(0, n, (64,), generator=torch.Generator().manual_seed(i))
+                          for i, n in enumerate((1024, 512, 1024, 512))]).to(DEV)
+    cuda_model.precision = "split"
+    try:
+        first = {}
+        for i in range(40):
+            key, batch = ("a", ba) if i % 2 == 0 else ("b", bb)
+            out, _, de_f, de_m = cuda_model.predict5(batch, 0, starts=starts)
+            got = (out.clone(), de_f.clone(), de_m.clone())
+            if key not in first:
+                first[key] = got
+            else:
+                for x, y in zip(got, first[key]):
+                    assert torch.equal(x, y), (i, key)
+        torch.cuda.synchronize()
+    finally:
+        cuda_model.precision = "fp32"
+    assert not torch.equal(first["a"][0], first["b"][0])
+
+
 _FALLBACK_SNIPPET = r"""
 import sys, types, torch
 sys.path.insert(0, %r)
@@ -113,23 +140,31 @@ sd = synthetic_state_dict(0)
 m = TouchedRegraster(types.SimpleNamespace(dataset="vase")); m.load_state_dict(sd, strict=True); m.to("cuda:0").eval()
 m.precision = "split"
 fpc, mrpc = synthetic_pairs(2, seed=64)
-torch.manual_seed(1234)
-out, _, de_f, de_m = m.predict5(make_batch(fpc.cuda(), mrpc.cuda()), 0)
-torch.cuda.synchronize()
+other = synthetic_pairs(2, seed=65)
 torch.manual_seed(1234)
 ref = po.predict5(sd, fpc, mrpc)
-errs = [parity.rel(out, ref["out"]), parity.rel(de_f, ref["de_fpcb"]), parity.rel(de_m, ref["de_mrpcb"])]
-rot, trans = parity.pose_errors(out, ref["out"])
-print("FALLBACK", max(errs), rot, trans)
-assert max(errs) < 1e-4 and rot < 0.01 and trans < 1e-4, (errs, rot, trans)
+for graphs in (False, True):     # eager launches (programmatic dependent launch), then CUDA-graph replay
+    m.cuda_graphs = graphs
+    for i in range(3):           # back-to-back calls on one workspace: the last one is checked
+        pair = (fpc, mrpc) if i == 2 else other
+        torch.manual_seed(1234)
+        out, _, de_f, de_m = m.predict5(make_batch(pair[0].cuda(), pair[1].cuda()), 0)
+    torch.cuda.synchronize()
+    errs = [parity.rel(out, ref["out"]), parity.rel(de_f, ref["de_fpcb"]), parity.rel(de_m, ref["de_mrpcb"])]
+    rot, trans = parity.pose_errors(out, ref["out"])
+    print("FALLBACK", graphs, max(errs), rot, trans)
+    assert max(errs) < 1e-4 and rot < 0.01 and trans < 1e-4, (graphs, errs, rot, trans)
 """
 
 
 @pytest.mark.parametrize("env", [{"PZ_SG_NO_PAIR": "1", "PZ_RG_NO_PAIR": "1", "PZ_STEM_FFMA": "1", "PZ_ATTN_NO_FUSE": "1"},
-                                 {"PZ_SG_PAIR_NST": "2", "PZ_SG_PW16": "1", "PZ_ATTN_NO_CHAIN": "1"}])
+                                 {"PZ_SG_PAIR_NST": "2", "PZ_SG_PW16": "1", "PZ_ATTN_NO_CHAIN": "1"},
+                                 {"PZ_NO_PDL": "1"}, {"PZ_SIDE_STREAM": "1", "PZ_ATTN_NO_PDL": "1"}, {"PZ_PDL_IN_GRAPHS": "1"}])
 def test_split_fallback_kernels(env):
     """The A/B hooks select the one-CTA kernels (cp.async row GEMM, two-pass gather GEMM, FFMA stem) / the alternative
-    pipeline depths; they are read once per process, so the forward runs in a child process.  Same bounds as the default."""
+    pipeline depths / plain launches instead of programmatic dependent launch / the geometry on a side stream / programmatic
+    edges inside captured graphs; they are read once per process, so the forward runs in a child process (three calls back to
+    back on one workspace, eager and as graph replays).  Same bounds as the default."""
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", _FALLBACK_SNIPPET % root], env={**os.environ, **env}, capture_output=True,
                        text=True, timeout=600)
