@@ -41,6 +41,7 @@ constexpr uint32_t T16 = 128 * 128;                 // one [128 x 64] fp16 tile
 constexpr uint32_t REGA = 8 * T16;                  // 128 KB
 constexpr int AS_NST = 2;                            // two stages: the freed 32 KB hold the epilogue's staging tiles
 constexpr uint32_t AS_STAGE = 2 * T16;              // hi + lo of [128 ch x 64 keys]
+#define AS_VSLOT(it) ((it) == 2 ? 6u : 2u * ((it) - 3u))   // first region-A tile of v^T stage it (2..5): 6, 0, 2, 4
 
 __host__ __device__ constexpr uint32_t idesc_f16(int n) {
   return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -59,6 +60,27 @@ __device__ __forceinline__ void umma3(uint32_t d, uint64_t a_hi, uint64_t a_lo, 
   umma_bf16(d, a_hi, b_hi, idesc, acc);
   umma_bf16(d, a_hi, b_lo, idesc, 1);
   umma_bf16(d, a_lo, b_hi, idesc, 1);
+}
+// A operand from TENSOR memory (lane = row, a 32-bit column = two consecutive K elements)
+__device__ __forceinline__ void umma_ts(uint32_t d, uint32_t a_tmem, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d), "r"(a_tmem), "l"(b), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// 32 consecutive 32-bit columns of this thread's TMEM lane <- 32 registers
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]),
+        "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]),
+        "r"(r[30]), "r"(r[31])
+      : "memory");
 }
 __device__ __forceinline__ void as_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -97,7 +119,8 @@ __global__ void __launch_bounds__(AS_THREADS, 1) attention_split_kernel(const At
   const uint32_t bar_r = bar_qk + 8 /* 2 */, bar_y = bar_r + 16 /* 2 */;   // fused out-projection: r half h written / out half h accumulated
   const uint32_t bar_pk = bar_y + 16 /* 4 */;                  // P key block kb (64 keys, both planes) written
   const uint32_t bar_x2 = bar_pk + 32 /* 2 */, bar_z = bar_x2 + 16 /* 3 */;   // chained projections: out half h in region A / block accumulated
-  const uint32_t tmem_slot = bar_z + 24;
+  const uint32_t bar_va = bar_z + 24 /* 4 */;                  // v^T stages 2..5 landed in region A (slots of two tiles: 6, 0, 2, 4)
+  const uint32_t tmem_slot = bar_va + 32;
   const uint32_t bo_s = (tmem_slot + 16 + 15) & ~15u;         // [256] out-projection bias of this CTA's weight set, then [384] next q|k|v bias
   const uint32_t stg_all = (bo_s + 1024 + 1536 + 127) & ~127u;   // 4 x 4 KB staging tiles of the epilogues (reused by all phases)
   const bool fuse = p.wo_hi[0] != nullptr;
@@ -122,6 +145,7 @@ __global__ void __launch_bounds__(AS_THREADS, 1) attention_split_kernel(const At
     mbar_init(bar_x2, 128);
     mbar_init(bar_x2 + 8, 128);
     for (int b3 = 0; b3 < 3; ++b3) mbar_init(bar_z + 8 * b3, 1);
+    for (int a = 0; a < 4; ++a) mbar_init(bar_va + 8 * a, 1);
     mbar_init(bar_y, 1);
     mbar_init(bar_y + 8, 1);
     for (int s = 0; s < AS_NST; ++s) {
@@ -440,14 +464,25 @@ __global__ void __launch_bounds__(AS_THREADS, 1) attention_split_kernel(const At
     // x 4 key blocks), two TMA tiles (hi, lo) per stage
     if (warp == 5 && lane == 0) {
       const int vrow = cloud * AS_C;
+      // P lives in tensor memory (over S), so region A is free for v^T while q k^T and the softmax run: stages 0, 1 and 6, 7
+      // go through the ring, stage 2 into tiles 6, 7 at once, stages 3..5 into the q / k tiles as soon as S is complete --
+      // six of the eight stages are in flight or landed before the first P v MMA can be issued
       for (uint32_t it = 0; it < 8; ++it) {
-        const uint32_t s = it % AS_NST, ph = (it / AS_NST) & 1;
         const int h = it >> 2, kb = it & 3;
-        mbar_wait(empty_bar + 8 * s, ph ^ 1);
-        const uint32_t st = ring + s * AS_STAGE;
-        as_expect_tx(full_bar + 8 * s, AS_STAGE);
-        as_tma_load(st, &maps.vT[0], kb * 64, vrow + h * 128, full_bar + 8 * s);
-        as_tma_load(st + T16, &maps.vT[1], kb * 64, vrow + h * 128, full_bar + 8 * s);
+        uint32_t st, fb;
+        if (it >= 2 && it < 6) {
+          if (it == 3) mbar_wait(bar_s, 0);   // q and k have been read
+          st = base + AS_VSLOT(it) * T16;
+          fb = bar_va + 8 * (it - 2);
+        } else {
+          const uint32_t s = it % AS_NST, ph = (it / AS_NST) & 1;
+          mbar_wait(empty_bar + 8 * s, ph ^ 1);
+          st = ring + s * AS_STAGE;
+          fb = full_bar + 8 * s;
+        }
+        as_expect_tx(fb, AS_STAGE);
+        as_tma_load(st, &maps.vT[0], kb * 64, vrow + h * 128, fb);
+        as_tma_load(st + T16, &maps.vT[1], kb * 64, vrow + h * 128, fb);
       }
       if (fuse) {   // 8 more stage loads: Wo [128 out channels x 64 k] x 2 planes per (channel half, k-block)
         for (uint32_t it = 8; it < 16; ++it) {
@@ -476,7 +511,7 @@ __global__ void __launch_bounds__(AS_THREADS, 1) attention_split_kernel(const At
     }
   } else if (warp == 4) {
     // =========================================================== MMA issuer
-    if (lane == 0) {
+    if (elect_one()) {
       {  // S[i, j] = sum_d q[i, d] k[j, d]
         mbar_wait(bar_qk, 0);
         tc_fence_after();
@@ -491,16 +526,22 @@ __global__ void __launch_bounds__(AS_THREADS, 1) attention_split_kernel(const At
       for (uint32_t it = 0; it < 8; ++it) {
         const uint32_t s = it % AS_NST, ph = (it / AS_NST) & 1;
         const int h = it >> 2, kb = it & 3;
-        if (h == 0) mbar_wait(bar_pk + 8 * kb, 0);   // P's key block kb is in region A (the softmax is still writing later ones)
-        mbar_wait(full_bar + 8 * s, ph);
+        const bool in_a = it >= 2 && it < 6;
+        if (h == 0) mbar_wait(bar_pk + 8 * kb, 0);   // P's key block kb is in tensor memory (the softmax is still writing later ones)
+        if (in_a) mbar_wait(bar_va + 8 * (it - 2), 0);
+        else mbar_wait(full_bar + 8 * s, ph);
         tc_fence_after();
-        const uint32_t st = ring + s * AS_STAGE;
-        const uint64_t a_hi = make_desc(base + kb * T16), a_lo = make_desc(base + 4 * T16 + kb * T16);
+        const uint32_t st = in_a ? base + AS_VSLOT(it) * T16 : ring + s * AS_STAGE;
         const uint64_t b_hi = make_desc(st), b_lo = make_desc(st + T16);
 #pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4)
-          umma3(tmem + 256 + h * 128, a_hi + 2 * k4, a_lo + 2 * k4, b_hi + 2 * k4, b_lo + 2 * k4, idesc, (kb | k4) != 0);
-        umma_commit(empty_bar + 8 * s);
+        for (int k4 = 0; k4 < 4; ++k4) {
+          // keys 64 kb + 16 k4 .. + 15 of P: chunk 2 kb + (k4 >> 1) of 32 columns = [16 hi columns | 16 lo columns]
+          const uint32_t a_hi = tmem + (uint32_t)(2 * kb + (k4 >> 1)) * 32 + (uint32_t)(k4 & 1) * 8, a_lo = a_hi + 16;
+          umma_ts(tmem + 256 + h * 128, a_hi, b_hi + 2 * k4, idesc, (kb | k4) != 0);
+          umma_ts(tmem + 256 + h * 128, a_hi, b_lo + 2 * k4, idesc, 1);
+          umma_ts(tmem + 256 + h * 128, a_lo, b_hi + 2 * k4, idesc, 1);
+        }
+        if (!in_a) umma_commit(empty_bar + 8 * s);
         if (kb == 3) umma_commit(bar_o + 8 * h);
       }
       if (fuse) {   // out[i, c] = sum_k r[i, k] Wo[c, k]: r planes in region A (over P), accumulators over S
@@ -560,38 +601,17 @@ __global__ void __launch_bounds__(AS_THREADS, 1) attention_split_kernel(const At
       for (int i = 0; i < 32; ++i) m = fmaxf(m, v[i]);
     }
     const float mc = m * cexp;
-    float sum = 0.f;
+    if (p.attn_mode != 0) {  // attention map (need=True): mean of the four layers' maps, model5_b.py:468-469.  Two extra passes over
+      // S BEFORE the pass below overwrites it with P: the row sum (same order of additions as below), then the map
+      float s0 = 0.f;
 #pragma unroll 1
-    for (int c32 = 0; c32 < 8; ++c32) {
-      float v[32];
-      tmem_ld32(t_row + c32 * 32, v);
+      for (int c32 = 0; c32 < 8; ++c32) {
+        float v[32];
+        tmem_ld32(t_row + c32 * 32, v);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        v[i] = exp2f(fmaf(v[i], cexp, -mc));
-        sum += v[i];
+        for (int i = 0; i < 32; ++i) s0 += exp2f(fmaf(v[i], cexp, -mc));
       }
-      // un-normalised probabilities -> K-major operand planes: k-block c32 / 2, chunks (c32 & 1) * 4 .. +3
-      const uint32_t pk = base + (c32 >> 1) * T16;
-#pragma unroll
-      for (int q4 = 0; q4 < 4; ++q4) {
-        uint4 oh, ol;
-        split2h(v[q4 * 8 + 0], v[q4 * 8 + 1], oh.x, ol.x);
-        split2h(v[q4 * 8 + 2], v[q4 * 8 + 3], oh.y, ol.y);
-        split2h(v[q4 * 8 + 4], v[q4 * 8 + 5], oh.z, ol.z);
-        split2h(v[q4 * 8 + 6], v[q4 * 8 + 7], oh.w, ol.w);
-        const uint32_t off = sw128(prow, (c32 & 1) * 4 + q4);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(pk + off), "r"(oh.x), "r"(oh.y), "r"(oh.z), "r"(oh.w) : "memory");
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(pk + 4 * T16 + off), "r"(ol.x), "r"(ol.y), "r"(ol.z), "r"(ol.w) : "memory");
-      }
-      if (c32 & 1) {   // key block c32 / 2 complete: the P v MMAs over it may start under the rest of the pass
-        fence_proxy_async();
-        tc_fence_before();
-        mbar_arrive(bar_pk + 8 * (c32 >> 1));
-      }
-    }
-    if (tid == 0) as_stamp(prof, 3);
-    const float inv = 1.0f / sum;
-    if (p.attn_mode != 0) {  // attention map (need=True): mean of the four layers' maps, model5_b.py:468-469
+      const float inv = 1.0f / s0;
       float* ag = p.attn + grow * AS_L;
 #pragma unroll 1
       for (int c32 = 0; c32 < 8; ++c32) {
@@ -614,6 +634,30 @@ __global__ void __launch_bounds__(AS_THREADS, 1) attention_split_kernel(const At
         }
       }
     }
+    float sum = 0.f;
+#pragma unroll 1
+    for (int c32 = 0; c32 < 8; ++c32) {
+      float v[32];
+      tmem_ld32(t_row + c32 * 32, v);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        v[i] = exp2f(fmaf(v[i], cexp, -mc));
+        sum += v[i];
+      }
+      // un-normalised probabilities -> the A operand of P v, IN PLACE over the 32 S columns just read: 16 columns of hi
+      // pairs (keys 2 i, 2 i + 1 in column i), then 16 columns of lo pairs
+      uint32_t pr[32];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) split2h(v[2 * i], v[2 * i + 1], pr[i], pr[16 + i]);
+      tmem_st32(t_row + c32 * 32, pr);
+      if (c32 & 1) {   // key block c32 / 2 complete: the P v MMAs over it may start under the rest of the pass
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        mbar_arrive(bar_pk + 8 * (c32 >> 1));
+      }
+    }
+    if (tid == 0) as_stamp(prof, 3);
+    const float inv = 1.0f / sum;
     // r = x - O / sum, one 128-channel half at a time (the second half's MMAs run under the first half's epilogue)
     // (a second group of four warps taking the other half was measured: both halves slow down to the same total -- the
     // phase moves 256 KB per CTA at ~5.4 TB/s over the chip, it is HBM-bound)
@@ -700,8 +744,8 @@ int launch_attention_split(const AttnSplit& p, int clouds, cudaStream_t st) {
                    (p.clouds_per_set <= 0 || p.clouds_per_set >= clouds || (p.wqkv_hi[1] && p.wqkv_lo[1] && p.bqkv[1])) &&
                    p.qk2_hi != p.qk_hi && p.vT2_hi != p.vT_hi,
                PZ_ERR_ARG, "attention_split: chained projections need next-layer weights, bias and separate output planes");
-  const size_t smem = 1024 + REGA + AS_NST * AS_STAGE + 8 * (18 + 2 * AS_NST) + 32 + 16 + 1024 + 1536 + 128 + 4 * 4096;
-  static_assert(1024 + REGA + AS_NST * AS_STAGE + 8 * (18 + 2 * AS_NST) + 32 + 16 + 1024 + 1536 + 128 + 4 * 4096 <= 232448, "attention_split: shared memory budget");
+  const size_t smem = 1024 + REGA + AS_NST * AS_STAGE + 8 * (22 + 2 * AS_NST) + 32 + 16 + 1024 + 1536 + 128 + 4 * 4096;
+  static_assert(1024 + REGA + AS_NST * AS_STAGE + 8 * (22 + 2 * AS_NST) + 32 + 16 + 1024 + 1536 + 128 + 4 * 4096 <= 232448, "attention_split: shared memory budget");
   PZ_CUDA(cudaFuncSetAttribute(attention_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   AsMaps maps;
   const size_t rows = (size_t)clouds * AS_L;

@@ -68,6 +68,15 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// The lane of a CONVERGENT warp that issues the tcgen05 instructions.  With `if (lane == 0)` ptxas cannot know that one lane
+// is active and wraps every UTCHMMA in an elect-and-branch loop (PLOP3, ELECT, UTCHMMA, PLOP3, PLOP3, BRA.U.ANY); with
+// elect.sync it emits the UTCHMMAs back to back.  Measured with scripts/mma_rate_probe.cu: the loop form is what paces
+// N = 128 MMAs (floor 64 clocks each), N = 256 MMAs (128 clocks) hide it.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t p;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(p));
+  return p != 0;
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
