@@ -112,6 +112,9 @@ __global__ void __launch_bounds__(288, 1) probe(int n, int mode, int noise, int 
       if (blockIdx.x == 0) out[0] = t1 - t0;
       stop = 1;
     }
+  } else if (noise == 2) {
+    // what the epilogue warps of the kernels do while the MMAs run: spin on an mbarrier (here: the one the final commit completes)
+    if (warp <= 4) mbar_wait(bar, 0);
   } else if (noise) {
     uint32_t addr = noise_s + (uint32_t)(warp - 1) * 8192 + lane * 16;
     uint32_t x = tid;
@@ -148,6 +151,16 @@ int main() {
       }
       printf("kernel-shaped loop (12 MMAs per stage), issuing lane by %s, N=%3d: %.1f clocks per MMA\n", mode == 2 ? "elect.sync" : "lane == 0", n, (double)h / 4092);
     }
+  for (int n : {128, 256}) {
+    long long h = 0;
+    for (int rep = 0; rep < 2; ++rep) {
+      probe<<<148, 288, smem>>>(n, 0, 2, iters, d);
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
+      cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
+    }
+    printf("SS N=%3d with 4 warps spinning on mbarrier.try_wait: %.1f clocks per MMA\n", n, (double)h / iters);
+  }
   for (int noise = 0; noise < 2; ++noise)
     for (int mode = 0; mode < 2; ++mode)
       for (int n : {64, 128, 256}) {
